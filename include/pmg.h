@@ -1,0 +1,116 @@
+/* pmg.h -- C-ABI of the B200-native batched Kuka multigoal simulator (libpmg.so).
+ *
+ * The reference (IanYangChina/pybullet_multigoal_gym) has no FFI layer of its own for this
+ * path: `env.step()` is Python calling into the pybullet C extension.  The entry points
+ * below are what a binding that replaces that path has to call; each one cites the reference
+ * interface it stands in for (paths relative to /root/reference/pybullet_multigoal_gym/).
+ * INTEGRATION.md shows the ctypes stub a maintainer of the reference would add.
+ *
+ * Conventions: every function returns 0 on success and a negative pmg_status on failure; the
+ * message is available from pmg_last_error() (thread-local).  Nothing throws across the ABI.
+ * `stream` arguments are cudaStream_t passed as void* (NULL = the legacy default stream).
+ * `*_dev` pointers are device pointers on the handle's device, `*_host` are host pointers.
+ * The caller owns every I/O buffer; the handle owns the persistent per-env state (SoA in HBM).
+ * Calls on one handle must be serialised by the caller; different handles are independent.
+ */
+#ifndef PMG_H
+#define PMG_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PMG_ABI_VERSION 1
+
+typedef enum {
+  PMG_OK = 0,
+  PMG_ERR_INVALID = -1, /* bad argument (task name, num_block > 5, null pointer, ...) */
+  PMG_ERR_CUDA = -2,    /* a CUDA runtime call failed; message holds cudaGetErrorString */
+  PMG_ERR_STATE = -3    /* call order violated (e.g. step before the first reset) */
+} pmg_status;
+
+/* task ids: envs/task_envs/kuka_single_step_envs.py:4-46, kuka_multi_step_envs.py:6-32 */
+typedef enum { PMG_REACH = 0, PMG_PUSH = 1, PMG_PICK_AND_PLACE = 2, PMG_BLOCK_STACK = 3 } pmg_task;
+
+/* make_env(...) kwargs that reach the step path (__init__.py:4-11,88-131) + batch/device */
+typedef struct {
+  int32_t task;               /* pmg_task */
+  int32_t num_block;          /* block_stack only, 1..5 (__init__.py:108) */
+  int32_t batch;              /* environments stepped in lockstep on this handle */
+  int32_t binary_reward;      /* 1: sparse -1/0 float32, 0: dense -distance */
+  float distance_threshold;   /* default 0.05 (__init__.py:6) */
+  int32_t max_episode_steps;  /* gym TimeLimit, default 50 (__init__.py:6,105) */
+  int32_t device;             /* CUDA device ordinal */
+} pmg_config;
+
+typedef struct pmg_handle pmg_handle;
+
+int pmg_abi_version(void);
+const char* pmg_last_error(void);
+
+/* replaces: make_env() -> gym.make -> Kuka*Env.__init__ (__init__.py:178,
+ * kuka_single_step_base_env.py:12-74, base_env.py:15-45,203-220).  Does NOT reset. */
+int pmg_create(const pmg_config* cfg, pmg_handle** out);
+int pmg_destroy(pmg_handle* h);
+
+/* dims[0..5] = observation, policy_state, achieved_goal, desired_goal, action, packed-row width
+ * (= sum of the first four).  replaces: observation_space / action_space (base_env.py:85-92). */
+int pmg_dims(const pmg_handle* h, int32_t dims[6]);
+
+/* replaces: env.seed() (base_env.py:120-122).  keys_host: [batch, max_key_len] uint32
+ * MT19937 init_by_array keys (gym's sha512 seed hash is computed by the caller),
+ * key_lens_host: [batch]. */
+int pmg_seed(pmg_handle* h, const uint32_t* keys_host, const int32_t* key_lens_host, int32_t max_key_len);
+
+/* replaces: env.reset() (base_env.py:124-128; kuka.py:157-165; kuka_single_step_base_env.py:
+ * 104-148; kuka_multi_step_base_env.py:223-246; kuka_multi_step_envs.py:34-87).
+ * mask_host: nullable [batch] bytes, non-zero = reset that env (NULL = all).
+ * spawn_host: nullable [batch, spawn_width] floats = [block xy (2*nb) | desired_goal (G)];
+ *   NULL = sample on the host from each env's numpy-compatible MT19937 stream, exactly as the
+ *   reference consumes it.
+ * obs_dev: [batch, packed-row width] row-major, rows of envs not reset are rewritten unchanged. */
+int pmg_reset(pmg_handle* h, const uint8_t* mask_host, const float* spawn_host, float* obs_dev, void* stream);
+int pmg_spawn_width(const pmg_handle* h);
+/* the spawn rows used by the most recent pmg_reset, [batch, spawn_width] (for parity tests) */
+int pmg_last_spawn(const pmg_handle* h, float* spawn_host);
+
+/* replaces: env.step(action) (base_env.py:130-138 -> kuka.py:167-225 -> 5 x stepSimulation;
+ * kuka_single_step_base_env.py:193-244; kuka_multi_step_base_env.py:255-345; gym TimeLimit).
+ * action_dev [batch, A] row-major in [-1, 1]; obs_dev [batch, W] packed
+ * [observation | policy_state | achieved_goal | desired_goal]; reward_dev [batch];
+ * done_dev / success_dev [batch] bytes (done = elapsed >= max_episode_steps,
+ * success = info['goal_achieved']).  One kernel launch, asynchronous on `stream`. */
+int pmg_step(pmg_handle* h, const float* action_dev, float* obs_dev, float* reward_dev,
+             uint8_t* done_dev, uint8_t* success_dev, void* stream);
+
+/* Same call with HOST buffers (pinned or pageable): H2D of the actions, the step kernel, D2H of
+ * obs / reward / done / success, then a stream synchronise.  This is the end-to-end entry a
+ * reference-side binding calls once per env.step(). */
+int pmg_step_host(pmg_handle* h, const float* action_host, float* obs_host, float* reward_host,
+                  uint8_t* done_host, uint8_t* success_host, void* stream);
+
+/* replaces: env._compute_reward(achieved_goal, desired_goal) on arbitrary leading axes
+ * (kuka_single_step_base_env.py:237-244; kuka_multi_step_base_env.py:338-345), e.g. HER relabelling.
+ * ag_dev, dg_dev: [n, g] row-major. */
+int pmg_compute_reward(const float* ag_dev, const float* dg_dev, int64_t n, int32_t g, float threshold,
+                       int32_t binary_reward, float* reward_dev, uint8_t* achieved_dev, void* stream);
+
+/* State access for teacher-forced parity tests (no reference counterpart).  Row layout, floats:
+ * q[9] qd[9] ee_target[3] rest_pose[7] motor_target[9] motor_max_impulse[9], then per block
+ * pos[3] quat_xyzw[4] linvel[3] angvel[3], then desired_goal[G], then elapsed steps.
+ * pmg_set_state also clears the contact caches. */
+int pmg_state_width(const pmg_handle* h);
+int pmg_get_state(pmg_handle* h, float* state_host);
+int pmg_set_state(pmg_handle* h, const float* state_host);
+
+/* number of kernels this library has launched on the handle since creation */
+int64_t pmg_launch_count(const pmg_handle* h);
+/* contact points dropped because a per-env scratch pool overflowed (0 in every shipped config) */
+int64_t pmg_overflow_count(pmg_handle* h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PMG_H */

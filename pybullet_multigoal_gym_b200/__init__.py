@@ -1,0 +1,59 @@
+"""B200-native batched drop-in for the `env.step()` path of pybullet_multigoal_gym.
+
+`make_env` keeps the reference's signature (/root/reference/pybullet_multigoal_gym/__init__.py:4-11)
+and adds `batch` (number of environments stepped in lockstep; None = one unbatched env with the
+reference's numpy shapes), `device` and `seed`.  Tasks on the accelerated path: reach, push,
+pick_and_place, block_stack with the parallel-jaw gripper and state observations.
+"""
+from .envs import (ActionError, KukaBlockStackEnv, KukaBulletMGEnv, KukaPickAndPlaceEnv,  # noqa: F401
+                   KukaPushEnv, KukaReachEnv)
+
+__all__ = ["make_env", "KukaBulletMGEnv", "KukaReachEnv", "KukaPushEnv", "KukaPickAndPlaceEnv",
+           "KukaBlockStackEnv", "ActionError"]
+
+_TASKS = ['push', 'reach', 'slide', 'pick_and_place',
+          'block_stack', 'block_rearrange', 'chest_pick_and_place', 'chest_push',
+          'primitive_push_assemble', 'primitive_push_reach', 'insertion']
+_TAGS = {'reach': 'Reach', 'push': 'Push', 'pick_and_place': 'PickAndPlace', 'block_stack': 'BlockStack'}
+_ENTRY = {'reach': KukaReachEnv, 'push': KukaPushEnv, 'pick_and_place': KukaPickAndPlaceEnv,
+          'block_stack': KukaBlockStackEnv}
+
+
+def make_env(task='reach', gripper='parallel_jaw', num_block=5, render=False, binary_reward=True,
+             grip_informed_goal=False, task_decomposition=False,
+             joint_control=False, max_episode_steps=50, distance_threshold=0.05,
+             primitive=None,
+             image_observation=False, depth_image=False, goal_image=False, point_cloud=False, state_noise=False,
+             visualize_target=True,
+             camera_setup=None, observation_cam_id=None, goal_cam_id=0,
+             use_curriculum=False, num_goals_to_generate=1e6,
+             batch=None, device=0, seed=0, check_actions=True):
+    grippers = ['robotiq85', 'parallel_jaw']
+    assert gripper in grippers, 'invalid gripper: {}, only support: {}'.format(gripper, grippers)
+    if task not in _TASKS:
+        raise ValueError('invalid task name: {}, only support: {}'.format(task, _TASKS))
+    unsupported = []
+    if task not in _TAGS:
+        unsupported.append("task=%r" % task)
+    if gripper != 'parallel_jaw':
+        unsupported.append("gripper=%r" % gripper)
+    for name, val in (('render', render), ('grip_informed_goal', grip_informed_goal),
+                      ('task_decomposition', task_decomposition), ('joint_control', joint_control),
+                      ('image_observation', image_observation), ('depth_image', depth_image),
+                      ('goal_image', goal_image), ('point_cloud', point_cloud), ('state_noise', state_noise),
+                      ('use_curriculum', use_curriculum)):
+        if val:
+            unsupported.append("%s=True" % name)
+    if primitive is not None:
+        unsupported.append("primitive=%r" % primitive)
+    if unsupported:
+        raise NotImplementedError(
+            "outside the accelerated step path (reach/push/pick_and_place/block_stack, parallel_jaw, "
+            "state observations): " + ", ".join(unsupported))
+    if task == 'block_stack':
+        assert num_block <= 5, "only support up to 5 blocks"
+    env_id = 'Kuka' + _TAGS[task] + 'ParallelGrip' + ('SparseReward' if binary_reward else 'DenseReward') + '-v0'
+    print('Task id: %s' % env_id)  # __init__.py:84
+    return _ENTRY[task](batch=batch, device=device, binary_reward=binary_reward,
+                        distance_threshold=distance_threshold, max_episode_steps=max_episode_steps,
+                        num_block=num_block, seed=seed, check_actions=check_actions)

@@ -1,0 +1,83 @@
+"""ctypes loader for libpmg.so, the CUDA kernels + C-ABI declared in include/pmg.h.
+
+There is no CPU fallback: if the shared library is missing or cannot be loaded the import
+fails loudly.  Build it with `python -m pybullet_multigoal_gym_b200.build` (or
+`__graft_entry__.build()`).
+"""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+SO_PATH = os.path.join(_HERE, "libpmg.so")
+
+ABI_VERSION = 1
+
+# every symbol include/pmg.h declares
+SYMBOLS = [
+    "pmg_abi_version", "pmg_last_error", "pmg_create", "pmg_destroy", "pmg_dims", "pmg_seed",
+    "pmg_reset", "pmg_spawn_width", "pmg_last_spawn", "pmg_step", "pmg_step_host",
+    "pmg_compute_reward", "pmg_state_width", "pmg_get_state", "pmg_set_state",
+    "pmg_launch_count", "pmg_overflow_count",
+]
+
+
+class PmgConfig(C.Structure):
+    _fields_ = [("task", C.c_int32), ("num_block", C.c_int32), ("batch", C.c_int32),
+                ("binary_reward", C.c_int32), ("distance_threshold", C.c_float),
+                ("max_episode_steps", C.c_int32), ("device", C.c_int32)]
+
+
+_lib = None
+
+
+def load():
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(SO_PATH):
+        raise ImportError(
+            "pybullet_multigoal_gym_b200: %s is missing. This package has no CPU fallback; build the "
+            "CUDA extension with `python -m pybullet_multigoal_gym_b200.build`." % SO_PATH)
+    L = C.CDLL(SO_PATH)
+    missing = [s for s in SYMBOLS if not hasattr(L, s)]
+    if missing:
+        raise ImportError("libpmg.so does not export: %s" % ", ".join(missing))
+    vp, fp, u8p = C.c_void_p, C.c_void_p, C.c_void_p
+    L.pmg_abi_version.restype = C.c_int
+    L.pmg_last_error.restype = C.c_char_p
+    L.pmg_create.argtypes = [C.POINTER(PmgConfig), C.POINTER(vp)]
+    L.pmg_destroy.argtypes = [vp]
+    L.pmg_dims.argtypes = [vp, C.POINTER(C.c_int32)]
+    L.pmg_seed.argtypes = [vp, vp, vp, C.c_int32]
+    L.pmg_reset.argtypes = [vp, u8p, fp, fp, vp]
+    L.pmg_spawn_width.argtypes = [vp]
+    L.pmg_last_spawn.argtypes = [vp, fp]
+    L.pmg_step.argtypes = [vp, fp, fp, fp, u8p, u8p, vp]
+    L.pmg_step_host.argtypes = [vp, fp, fp, fp, u8p, u8p, vp]
+    L.pmg_compute_reward.argtypes = [fp, fp, C.c_int64, C.c_int32, C.c_float, C.c_int32, fp, u8p, vp]
+    L.pmg_state_width.argtypes = [vp]
+    L.pmg_get_state.argtypes = [vp, fp]
+    L.pmg_set_state.argtypes = [vp, fp]
+    L.pmg_launch_count.argtypes = [vp]
+    L.pmg_launch_count.restype = C.c_int64
+    L.pmg_overflow_count.argtypes = [vp]
+    L.pmg_overflow_count.restype = C.c_int64
+    if L.pmg_abi_version() != ABI_VERSION:
+        raise ImportError("libpmg.so ABI version %d, expected %d" % (L.pmg_abi_version(), ABI_VERSION))
+    _lib = L
+    return L
+
+
+class PmgError(RuntimeError):
+    pass
+
+
+def check(rc):
+    """Maps the C status convention onto Python exceptions (PMG_ERR_INVALID -> ValueError, the
+    condition the reference asserts / raises ValueError on)."""
+    if rc == 0:
+        return
+    msg = load().pmg_last_error().decode("utf8", "replace")
+    if rc == -1:
+        raise ValueError(msg)
+    raise PmgError("pmg error %d: %s" % (rc, msg))

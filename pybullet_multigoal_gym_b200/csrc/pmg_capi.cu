@@ -1,0 +1,643 @@
+// pmg_capi.cu -- kernels and the C-ABI (include/pmg.h) of the batched Kuka multigoal simulator.
+//
+// Kernels (one thread = one environment, see pmg_physics.cuh for why):
+//   step_kernel<TASK,NBLK>   : action map + IK + 5 x 20 substeps + observation/reward/flags
+//   reset_kernel<TASK,NBLK>  : robot reset (IK to the start pose), object/goal placement, observation
+//   reward_kernel            : _compute_reward over arbitrary rows (HER relabelling)
+// Host side: handle bookkeeping and the numpy-compatible MT19937 reset sampler.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <new>
+#include <vector>
+
+#include "../../include/pmg.h"
+#include "pmg_sim.cuh"
+
+using namespace pmg;
+
+// ------------------------------------------------------------------------------------------------
+// device: observation assembly (kuka.py:227-256, kuka_single_step_base_env.py:193-221,
+// kuka_multi_step_base_env.py:255-320) and reward (kuka_single_step_base_env.py:237-244)
+// ------------------------------------------------------------------------------------------------
+struct StepIO {
+  float* state; float* manifold; int batch; int state_words;
+  const float* action; float* obs; float* reward; uint8_t* done; uint8_t* success;
+  float thr; int binary; int max_steps; int* overflow;
+};
+
+template <int TASK, int NBLK> struct Dims {
+  static constexpr int O = TASK == 0 ? 3 : (TASK == 3 ? 8 + 16 * NBLK : 20);
+  static constexpr int P = TASK == 0 ? 3 : (TASK == 3 ? 4 + 3 * NBLK : 7);
+  static constexpr int G = TASK == 3 ? 3 * NBLK : 3;
+  static constexpr int W = O + P + 2 * G;
+  static constexpr int A = TASK >= 2 ? 4 : 3;
+  static constexpr int STATE = ST_BLK + 13 * NBLK + G + 1;
+};
+
+__device__ __forceinline__ float clip5(float v) { return fminf(fmaxf(v, -5.0f), 5.0f); }
+
+template <int TASK, int NBLK>
+__device__ void load_env(Env<NBLK>& e, const StepIO& io, int i) {
+  const size_t B = io.batch;
+  const float* s = io.state + i;
+#pragma unroll
+  for (int k = 0; k < ND; k++) {
+    e.q[k] = s[(ST_Q + k) * B]; e.qd[k] = s[(ST_QD + k) * B];
+    e.mt[k] = s[(ST_MT + k) * B]; e.mi[k] = s[(ST_MI + k) * B]; e.dtau[k] = 0.0f;
+  }
+#pragma unroll
+  for (int b = 0; b < NBLK; b++) {
+    const float* bs = s + (ST_BLK + 13 * b) * B;
+    e.bpos[b] = v3(bs[0], bs[B], bs[2 * B]);
+#pragma unroll
+    for (int k = 0; k < 4; k++) e.bquat[b][k] = bs[(3 + k) * B];
+    e.bv[b] = v3(bs[7 * B], bs[8 * B], bs[9 * B]);
+    e.bw[b] = v3(bs[10 * B], bs[11 * B], bs[12 * B]);
+  }
+  e.man = io.manifold + i; e.stride = B; e.overflow = 0;
+}
+
+template <int TASK, int NBLK>
+__device__ void store_env(const Env<NBLK>& e, const StepIO& io, int i) {
+  const size_t B = io.batch;
+  float* s = io.state + i;
+#pragma unroll
+  for (int k = 0; k < ND; k++) {
+    s[(ST_Q + k) * B] = e.q[k]; s[(ST_QD + k) * B] = e.qd[k];
+    s[(ST_MT + k) * B] = e.mt[k]; s[(ST_MI + k) * B] = e.mi[k];
+  }
+#pragma unroll
+  for (int b = 0; b < NBLK; b++) {
+    float* bs = s + (ST_BLK + 13 * b) * B;
+    bs[0] = e.bpos[b].x; bs[B] = e.bpos[b].y; bs[2 * B] = e.bpos[b].z;
+#pragma unroll
+    for (int k = 0; k < 4; k++) bs[(3 + k) * B] = e.bquat[b][k];
+    bs[7 * B] = e.bv[b].x; bs[8 * B] = e.bv[b].y; bs[9 * B] = e.bv[b].z;
+    bs[10 * B] = e.bw[b].x; bs[11 * B] = e.bw[b].y; bs[12 * B] = e.bw[b].z;
+  }
+  if (e.overflow) atomicAdd(io.overflow, e.overflow);
+}
+
+// Stage the warp's rows in shared memory so that the global stores are contiguous 128-byte lines
+// (rows of consecutive envs are adjacent in the packed [batch, W] output).  Every lane of the warp
+// must call this; lanes past the end of the batch pass live = false.
+template <int W>
+__device__ __forceinline__ void stage_row(const float* row, const StepIO& io, int i, bool live) {
+  extern __shared__ float stage[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float* ws = stage + warp * 32 * W;
+  if (live) {
+#pragma unroll
+    for (int k = 0; k < W; k++) ws[lane * W + k] = row[k];
+  }
+  __syncwarp();
+  const int env0 = i - lane;
+  const int nvalid = min(32, io.batch - env0) * W;
+  float* out = io.obs + (size_t)env0 * W;
+  for (int k = lane; k < nvalid; k += 32) out[k] = ws[k];
+  __syncwarp();
+}
+
+// Writes the packed row [observation | policy_state | achieved_goal | desired_goal] and returns
+// the goal distance.
+template <int TASK, int NBLK>
+__device__ float write_obs(const Env<NBLK>& e, const StepIO& io, int i) {
+  using D = Dims<TASK, NBLK>;
+  const size_t B = io.batch;
+  Frames f;
+  forward_kinematics<NB>(e.q, f);
+  V3 tip = tip_position(f), tv, tw;
+  point_velocity<PMG_BODY_LINK7>(f, e.qd, tip, tv, tw);
+  float closeness = 0.0f, finger_vel = 0.0f;
+  if (TASK >= 2) {
+    const float t1[3] = PMG_TAB1_OFFSET, t2[3] = PMG_TAB2_OFFSET;
+    V3 tab1 = f.p[PMG_BODY_FINGER1] + mul(f.R[PMG_BODY_FINGER1], v3(t1[0], t1[1], t1[2]));
+    V3 tab2 = f.p[PMG_BODY_FINGER2] + mul(f.R[PMG_BODY_FINGER2], v3(t2[0], t2[1], t2[2]));
+    closeness = norm(tab1 - tab2);
+    V3 vb, wb, vt, wt;
+    point_velocity<PMG_BODY_GBASE>(f, e.qd, f.p[PMG_BODY_GBASE], vb, wb);
+    point_velocity<PMG_BODY_FINGER1>(f, e.qd, tab1, vt, wt);
+    finger_vel = vb.y - vt.y;
+  }
+  float row[D::W];
+  float* obs = row; float* pol = row + D::O; float* ag = pol + D::P; float* dg = ag + D::G;
+  const float* goal = io.state + (size_t)(ST_BLK + 13 * NBLK) * B + i;
+#pragma unroll
+  for (int k = 0; k < D::G; k++) dg[k] = goal[k * B];
+  if (TASK == 0) {
+    obs[0] = pol[0] = ag[0] = tip.x; obs[1] = pol[1] = ag[1] = tip.y; obs[2] = pol[2] = ag[2] = tip.z;
+  } else if (TASK != 3) {
+    V3 bx = e.bpos[0], rel = tip - bx, rv = tv - e.bv[0], rw = tw - e.bw[0];
+    obs[0] = tip.x; obs[1] = tip.y; obs[2] = tip.z; obs[3] = bx.x; obs[4] = bx.y; obs[5] = bx.z; obs[6] = closeness;
+    obs[7] = rel.x; obs[8] = rel.y; obs[9] = rel.z; obs[10] = tv.x; obs[11] = tv.y; obs[12] = tv.z; obs[13] = finger_vel;
+    obs[14] = rv.x; obs[15] = rv.y; obs[16] = rv.z; obs[17] = rw.x; obs[18] = rw.y; obs[19] = rw.z;
+    pol[0] = tip.x; pol[1] = tip.y; pol[2] = tip.z; pol[3] = closeness; pol[4] = rel.x; pol[5] = rel.y; pol[6] = rel.z;
+    ag[0] = bx.x; ag[1] = bx.y; ag[2] = bx.z;
+  } else {
+    obs[0] = tip.x; obs[1] = tip.y; obs[2] = tip.z; obs[3] = closeness; obs[4] = tv.x; obs[5] = tv.y; obs[6] = tv.z; obs[7] = finger_vel;
+    pol[0] = tip.x; pol[1] = tip.y; pol[2] = tip.z; pol[3] = closeness;
+#pragma unroll
+    for (int n = 0; n < NBLK; n++) {
+      float* bs = obs + 8 + 16 * n;
+      V3 bx = e.bpos[n], rel = tip - bx, rv = tv - e.bv[n], rw = tw - e.bw[n];
+      bs[0] = bx.x; bs[1] = bx.y; bs[2] = bx.z; bs[3] = rel.x; bs[4] = rel.y; bs[5] = rel.z;
+      bs[6] = e.bquat[n][0]; bs[7] = e.bquat[n][1]; bs[8] = e.bquat[n][2]; bs[9] = e.bquat[n][3];
+      bs[10] = rv.x; bs[11] = rv.y; bs[12] = rv.z; bs[13] = rw.x; bs[14] = rw.y; bs[15] = rw.z;
+      pol[4 + 3 * n] = rel.x; pol[5 + 3 * n] = rel.y; pol[6 + 3 * n] = rel.z;
+      ag[3 * n] = bx.x; ag[3 * n + 1] = bx.y; ag[3 * n + 2] = bx.z;
+    }
+#pragma unroll
+    for (int k = 0; k < D::O + D::P; k++) row[k] = clip5(row[k]);
+  }
+  float d2 = 0.0f;
+#pragma unroll
+  for (int k = 0; k < D::G; k++) { float d = ag[k] - dg[k]; d2 += d * d; }
+  stage_row<D::W>(row, io, i, true);
+  return sqrtf(d2);
+}
+
+template <int TASK, int NBLK>
+__global__ void __launch_bounds__(128) step_kernel(StepIO io) {
+  using D = Dims<TASK, NBLK>;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= io.batch) { stage_row<D::W>(nullptr, io, i, false); return; }  // tail lanes only help the staged store
+  const size_t B = io.batch;
+  Env<NBLK> e;
+  load_env<TASK, NBLK>(e, io, i);
+  float* s = io.state + i;
+  // ---- Kuka.apply_action (kuka.py:167-222) ----
+  float a[D::A];
+#pragma unroll
+  for (int k = 0; k < D::A; k++) a[k] = io.action[(size_t)i * D::A + k];
+  if (TASK >= 2) {
+    float grip = (a[D::A - 1] + 1.0f) * (GRIPPER_ABS_LIMIT / 2);
+    e.mt[7] = e.mt[8] = grip; e.mi[7] = e.mi[8] = FINGER_FORCE * OUTER_DT;
+  }
+  const float lo[3] = {-0.67f, -0.20f, 0.175f}, hi[3] = {-0.37f, 0.20f, 0.55f};  // kuka.py:40-41
+  float ee[3];
+#pragma unroll
+  for (int k = 0; k < 3; k++) ee[k] = fminf(fmaxf(s[(ST_EE + k) * B] + a[k] * 0.01f, lo[k]), hi[k]);
+  {
+    float qik[ND];
+#pragma unroll
+    for (int k = 0; k < ND; k++) qik[k] = e.q[k];
+    const float tq[4] = {0.f, -1.f, 0.f, 0.f};  // kuka.py:42
+    inverse_kinematics(qik, v3(ee[0], ee[1], ee[2]), tq);
+#pragma unroll
+    for (int k = 0; k < 7; k++) { e.mt[k] = qik[k]; e.mi[k] = ARM_FORCE * OUTER_DT; }
+  }
+  // ---- 5 x stepSimulation (kuka.py:223-225), each 20 substeps of 2 ms ----
+  for (int call = 0; call < CALLS_PER_ENV_STEP; call++) {
+#pragma unroll
+    for (int k = 0; k < ND; k++) e.dtau[k] = -c_dof_damping[k] * e.qd[k];
+    for (int sub = 0; sub < SUBSTEPS_PER_CALL; sub++) substep(e);
+  }
+  float dist = write_obs<TASK, NBLK>(e, io, i);
+  store_env<TASK, NBLK>(e, io, i);
+#pragma unroll
+  for (int k = 0; k < 3; k++) s[(ST_EE + k) * B] = ee[k];
+  float* el = s + (size_t)(D::STATE - 1) * B;
+  int elapsed = (int)(*el) + 1;
+  *el = (float)elapsed;
+  bool na = dist > io.thr;
+  io.reward[i] = io.binary ? -(na ? 1.0f : 0.0f) : -dist;
+  io.success[i] = na ? 0 : 1;
+  io.done[i] = elapsed >= io.max_steps ? 1 : 0;
+}
+
+struct ResetIO { StepIO io; const uint8_t* mask; const float* spawn; float tip_init[3]; };
+
+template <int TASK, int NBLK>
+__global__ void __launch_bounds__(128) reset_kernel(ResetIO r) {
+  using D = Dims<TASK, NBLK>;
+  const StepIO& io = r.io;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= io.batch) { stage_row<D::W>(nullptr, io, i, false); return; }
+  const size_t B = io.batch;
+  Env<NBLK> e;
+  load_env<TASK, NBLK>(e, io, i);
+  float* s = io.state + i;
+  const bool doit = r.mask == nullptr || r.mask[i] != 0;
+  if (doit) {
+    // Kuka.robot_specific_reset (kuka.py:157-165): joints to the rest pose, rest pose <- IK(start
+    // position) seeded there, joints to the new rest pose, jaws closed with their motor on.
+    float qik[ND];
+#pragma unroll
+    for (int k = 0; k < 7; k++) qik[k] = s[(ST_REST + k) * B];
+    qik[7] = e.q[7]; qik[8] = e.q[8];
+    const float tq[4] = {0.f, -1.f, 0.f, 0.f};
+    inverse_kinematics(qik, v3(r.tip_init[0], r.tip_init[1], r.tip_init[2]), tq);
+#pragma unroll
+    for (int k = 0; k < 7; k++) { e.q[k] = qik[k]; e.qd[k] = 0.0f; e.mt[k] = 0.0f; e.mi[k] = 0.0f; }
+#pragma unroll
+    for (int k = 7; k < ND; k++) { e.q[k] = GRIPPER_ABS_LIMIT; e.qd[k] = 0.0f; e.mt[k] = GRIPPER_ABS_LIMIT; e.mi[k] = FINGER_FORCE * OUTER_DT; }
+    Frames f;
+    forward_kinematics<7>(e.q, f);
+    V3 tip = tip_position(f);
+    const float* sp = r.spawn + (size_t)i * (2 * NBLK + D::G);
+#pragma unroll
+    for (int b = 0; b < NBLK; b++) {
+      e.bpos[b] = v3(sp[2 * b], sp[2 * b + 1], BLOCK_SPAWN_Z);
+      e.bquat[b][0] = e.bquat[b][1] = e.bquat[b][2] = 0.0f; e.bquat[b][3] = 1.0f;
+      e.bv[b] = v3(0, 0, 0); e.bw[b] = v3(0, 0, 0);
+    }
+#pragma unroll
+    for (int k = 0; k < 7; k++) s[(ST_REST + k) * B] = qik[k];
+    s[(ST_EE + 0) * B] = tip.x; s[(ST_EE + 1) * B] = tip.y; s[(ST_EE + 2) * B] = tip.z;
+#pragma unroll
+    for (int k = 0; k < D::G; k++) s[(size_t)(ST_BLK + 13 * NBLK + k) * B] = sp[2 * NBLK + k];
+    s[(size_t)(D::STATE - 1) * B] = 0.0f;
+    store_env<TASK, NBLK>(e, io, i);
+  }
+  write_obs<TASK, NBLK>(e, io, i);
+}
+
+__global__ void reward_kernel(const float* ag, const float* dg, int64_t n, int g, float thr, int binary, float* reward, uint8_t* ok) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float d2 = 0.0f;
+  for (int k = 0; k < g; k++) { float d = ag[i * g + k] - dg[i * g + k]; d2 += d * d; }
+  float d = sqrtf(d2);
+  bool na = d > thr;
+  reward[i] = binary ? -(na ? 1.0f : 0.0f) : -d;
+  ok[i] = na ? 0 : 1;
+}
+
+__global__ void init_state_kernel(float* state, int batch, int nblk, int state_words) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= batch) return;
+  const size_t B = batch;
+  for (int k = 0; k < 7; k++) { state[(ST_REST + k) * B + i] = c_rest_pose0[k]; state[(ST_Q + k) * B + i] = c_rest_pose0[k]; }
+  for (int b = 0; b < nblk; b++) state[(ST_BLK + 13 * b + 6) * B + i] = 1.0f;  // identity quaternion
+  (void)state_words;
+}
+
+// ------------------------------------------------------------------------------------------------
+// host: numpy legacy RandomState (MT19937) -- the reference draws object / goal poses from
+// gym's np_random (base_env.py:120-122); same stream => same resets.
+// ------------------------------------------------------------------------------------------------
+namespace {
+
+struct MT {
+  uint32_t mt[624]; int idx;
+  void init_genrand(uint32_t s) {
+    mt[0] = s;
+    for (int i = 1; i < 624; i++) mt[i] = 1812433253u * (mt[i - 1] ^ (mt[i - 1] >> 30)) + (uint32_t)i;
+    idx = 624;
+  }
+  void init_by_array(const uint32_t* key, int len) {
+    init_genrand(19650218u);
+    int i = 1, j = 0, k = 624 > len ? 624 : len;
+    for (; k; k--) {
+      mt[i] = (mt[i] ^ ((mt[i - 1] ^ (mt[i - 1] >> 30)) * 1664525u)) + key[j] + (uint32_t)j;
+      if (++i >= 624) { mt[0] = mt[623]; i = 1; }
+      if (++j >= len) j = 0;
+    }
+    for (k = 623; k; k--) {
+      mt[i] = (mt[i] ^ ((mt[i - 1] ^ (mt[i - 1] >> 30)) * 1566083941u)) - (uint32_t)i;
+      if (++i >= 624) { mt[0] = mt[623]; i = 1; }
+    }
+    mt[0] = 0x80000000u; idx = 624;
+  }
+  uint32_t next() {
+    if (idx >= 624) {
+      for (int k = 0; k < 624; k++) {
+        uint32_t y = (mt[k] & 0x80000000u) | (mt[(k + 1) % 624] & 0x7fffffffu);
+        mt[k] = mt[(k + 397) % 624] ^ (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
+      }
+      idx = 0;
+    }
+    uint32_t y = mt[idx++];
+    y ^= y >> 11; y ^= (y << 7) & 0x9d2c5680u; y ^= (y << 15) & 0xefc60000u; y ^= y >> 18;
+    return y;
+  }
+  double random_sample() { uint32_t a = next() >> 5, b = next() >> 6; return (a * 67108864.0 + b) / 9007199254740992.0; }
+  double uniform(double lo, double hi) { return lo + (hi - lo) * random_sample(); }
+  uint32_t interval(uint32_t max) {
+    if (max == 0) return 0;
+    uint32_t mask = max, v;
+    mask |= mask >> 1; mask |= mask >> 2; mask |= mask >> 4; mask |= mask >> 8; mask |= mask >> 16;
+    while ((v = next() & mask) > max) {}
+    return v;
+  }
+};
+
+thread_local char g_err[512] = "";
+int fail(int code, const char* fmt, const char* detail = "") {
+  snprintf(g_err, sizeof g_err, fmt, detail);
+  return code;
+}
+#define CUDA_TRY(expr) do { cudaError_t err__ = (expr); if (err__ != cudaSuccess) return fail(PMG_ERR_CUDA, #expr ": %s", cudaGetErrorString(err__)); } while (0)
+
+}  // namespace
+
+struct pmg_handle {
+  pmg_config cfg;
+  int nblk, O, P, G, W, A, state_words, man_words, spawn_w;
+  float* d_state = nullptr; float* d_man = nullptr; float* d_spawn = nullptr; uint8_t* d_mask = nullptr; int* d_overflow = nullptr;
+  float* d_action = nullptr; float* d_obs = nullptr; float* d_reward = nullptr; uint8_t* d_done = nullptr; uint8_t* d_success = nullptr;
+  float* h_spawn = nullptr;  // pinned
+  std::vector<MT> rng;
+  double tip_init[3], obj_lo[3], obj_hi[3], tgt_lo[3], tgt_hi[3];
+  bool was_reset = false;
+  int64_t launches = 0;
+  int block = 32;
+};
+
+namespace {
+
+// Sampling of one reset, consuming the env's stream exactly like the reference:
+// kuka_single_step_base_env.py:104-148, kuka_multi_step_base_env.py:223-240, kuka_multi_step_envs.py:34-63
+void sample_spawn(pmg_handle* h, int i, float* out) {
+  MT& r = h->rng[i];
+  const int nb = h->nblk;
+  double xy[2 * 5];
+  if (h->cfg.task == PMG_BLOCK_STACK) {
+    for (int b = 0; b < nb; b++) {
+      for (;;) {
+        double x = r.uniform(h->obj_lo[0], h->obj_hi[0]), y = r.uniform(h->obj_lo[1], h->obj_hi[1]);
+        bool ok = true;
+        for (int k = 0; k < b; k++) if (!(hypot(x - xy[2 * k], y - xy[2 * k + 1]) > 0.06)) ok = false;
+        if (!(hypot(x - h->tip_init[0], y - h->tip_init[1]) > 0.06)) ok = false;
+        if (ok) { xy[2 * b] = x; xy[2 * b + 1] = y; break; }
+      }
+    }
+    int order[5];
+    for (int k = 0; k < nb; k++) order[k] = k;
+    for (int k = nb - 1; k > 0; k--) { int j = (int)r.interval((uint32_t)k); int t = order[k]; order[k] = order[j]; order[j] = t; }
+    double bx, by;
+    for (;;) {
+      bx = r.uniform(h->tgt_lo[0], h->tgt_hi[0]); by = r.uniform(h->tgt_lo[1], h->tgt_hi[1]);
+      bool ok = true;
+      for (int k = 0; k < nb; k++) if (!(hypot(bx - xy[2 * k], by - xy[2 * k + 1]) > 0.08)) ok = false;
+      if (ok) break;
+    }
+    for (int b = 0; b < nb; b++) { out[2 * b] = (float)xy[2 * b]; out[2 * b + 1] = (float)xy[2 * b + 1]; }
+    float* goal = out + 2 * nb;
+    for (int k = 0; k < nb; k++) {
+      goal[3 * order[k]] = (float)bx; goal[3 * order[k] + 1] = (float)by;
+      goal[3 * order[k] + 2] = (float)(k == 0 ? 0.175 : 0.175 + 0.03 * k);
+    }
+    return;
+  }
+  double center[3] = {h->tip_init[0], h->tip_init[1], h->tip_init[2]};
+  if (nb) {
+    double x = h->tip_init[0], y = h->tip_init[1];
+    while (hypot(x - h->tip_init[0], y - h->tip_init[1]) < 0.1) {
+      x = r.uniform(h->obj_lo[0], h->obj_hi[0]); y = r.uniform(h->obj_lo[1], h->obj_hi[1]);
+    }
+    out[0] = (float)x; out[1] = (float)y;
+    center[0] = x; center[1] = y; center[2] = 0.175;
+  }
+  double g[3];
+  for (;;) {
+    for (int k = 0; k < 3; k++) g[k] = r.uniform(h->tgt_lo[k], h->tgt_hi[k]);
+    double dx = g[0] - center[0], dy = g[1] - center[1], dz = g[2] - center[2];
+    if (sqrt(dx * dx + dy * dy + dz * dz) > 0.1) break;
+  }
+  if (h->cfg.task == PMG_PUSH) g[2] = 0.175;
+  else if (h->cfg.task == PMG_PICK_AND_PLACE) { if (r.uniform(0, 1) >= 0.5) g[2] = 0.175; }
+  for (int k = 0; k < 3; k++) out[2 * nb + k] = (float)g[k];
+}
+
+StepIO make_io(pmg_handle* h, const float* action, float* obs, float* reward, uint8_t* done, uint8_t* success) {
+  StepIO io;
+  io.state = h->d_state; io.manifold = h->d_man; io.batch = h->cfg.batch; io.state_words = h->state_words;
+  io.action = action; io.obs = obs; io.reward = reward; io.done = done; io.success = success;
+  io.thr = h->cfg.distance_threshold; io.binary = h->cfg.binary_reward; io.max_steps = h->cfg.max_episode_steps;
+  io.overflow = h->d_overflow;
+  return io;
+}
+
+template <int TASK, int NBLK>
+void launch_step(pmg_handle* h, const StepIO& io, cudaStream_t st) {
+  int blocks = (h->cfg.batch + h->block - 1) / h->block;
+  size_t smem = (size_t)(h->block / 32) * 32 * Dims<TASK, NBLK>::W * sizeof(float);
+  step_kernel<TASK, NBLK><<<blocks, h->block, smem, st>>>(io);
+}
+template <int TASK, int NBLK>
+void launch_reset(pmg_handle* h, const ResetIO& r, cudaStream_t st) {
+  int blocks = (h->cfg.batch + h->block - 1) / h->block;
+  size_t smem = (size_t)(h->block / 32) * 32 * Dims<TASK, NBLK>::W * sizeof(float);
+  reset_kernel<TASK, NBLK><<<blocks, h->block, smem, st>>>(r);
+}
+
+#define PMG_DISPATCH(FN, ...)                                                        \
+  switch (h->cfg.task) {                                                             \
+    case PMG_REACH: FN<0, 0>(__VA_ARGS__); break;                                    \
+    case PMG_PUSH: FN<1, 1>(__VA_ARGS__); break;                                     \
+    case PMG_PICK_AND_PLACE: FN<2, 1>(__VA_ARGS__); break;                           \
+    default:                                                                         \
+      switch (h->nblk) {                                                             \
+        case 1: FN<3, 1>(__VA_ARGS__); break;                                        \
+        case 2: FN<3, 2>(__VA_ARGS__); break;                                        \
+        case 3: FN<3, 3>(__VA_ARGS__); break;                                        \
+        case 4: FN<3, 4>(__VA_ARGS__); break;                                        \
+        default: FN<3, 5>(__VA_ARGS__); break;                                       \
+      }                                                                              \
+  }
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------
+// C-ABI
+// ------------------------------------------------------------------------------------------------
+extern "C" {
+
+int pmg_abi_version(void) { return PMG_ABI_VERSION; }
+const char* pmg_last_error(void) { return g_err; }
+
+int pmg_create(const pmg_config* cfg, pmg_handle** out) {
+  if (!cfg || !out) return fail(PMG_ERR_INVALID, "pmg_create: null argument%s");
+  if (cfg->task < PMG_REACH || cfg->task > PMG_BLOCK_STACK) return fail(PMG_ERR_INVALID, "pmg_create: invalid task id%s");
+  if (cfg->task == PMG_BLOCK_STACK && (cfg->num_block < 1 || cfg->num_block > 5)) return fail(PMG_ERR_INVALID, "pmg_create: only support up to 5 blocks%s");
+  if (cfg->batch < 1) return fail(PMG_ERR_INVALID, "pmg_create: batch must be >= 1%s");
+  if (cfg->max_episode_steps < 1 || cfg->max_episode_steps >= (1 << 24)) return fail(PMG_ERR_INVALID, "pmg_create: max_episode_steps out of range%s");
+  int ndev = 0;
+  CUDA_TRY(cudaGetDeviceCount(&ndev));
+  if (cfg->device < 0 || cfg->device >= ndev) return fail(PMG_ERR_INVALID, "pmg_create: no such CUDA device%s");
+  CUDA_TRY(cudaSetDevice(cfg->device));
+  pmg_handle* h = new (std::nothrow) pmg_handle();
+  if (!h) return fail(PMG_ERR_INVALID, "pmg_create: out of host memory%s");
+  h->cfg = *cfg;
+  const int t = cfg->task;
+  h->nblk = t == PMG_REACH ? 0 : (t == PMG_BLOCK_STACK ? cfg->num_block : 1);
+  h->O = t == PMG_REACH ? 3 : (t == PMG_BLOCK_STACK ? 8 + 16 * h->nblk : 20);
+  h->P = t == PMG_REACH ? 3 : (t == PMG_BLOCK_STACK ? 4 + 3 * h->nblk : 7);
+  h->G = t == PMG_BLOCK_STACK ? 3 * h->nblk : 3;
+  h->W = h->O + h->P + 2 * h->G;
+  h->A = t >= PMG_PICK_AND_PLACE ? 4 : 3;
+  h->state_words = ST_BLK + 13 * h->nblk + h->G + 1;
+  h->man_words = num_pairs(h->nblk) * MAN_WORDS;
+  h->spawn_w = 2 * h->nblk + h->G;
+  // kuka.py:35-51 with obj_range = target_range = 0.15 (kuka_single_step_envs.py, kuka_multi_step_envs.py:29)
+  h->tip_init[0] = -0.52; h->tip_init[1] = 0.0; h->tip_init[2] = t == PMG_PUSH ? 0.175 + 0.001 : 0.25;
+  for (int k = 0; k < 3; k++) {
+    h->obj_lo[k] = h->tip_init[k] - 0.15; h->obj_hi[k] = h->tip_init[k] + 0.15;
+    h->tgt_lo[k] = h->tip_init[k] - 0.15; h->tgt_hi[k] = h->tip_init[k] + 0.15;
+  }
+  h->obj_lo[0] += 0.03; h->obj_hi[0] -= 0.03;
+  h->tgt_lo[0] += 0.03; h->tgt_lo[2] = 0.175; h->tgt_hi[0] -= 0.03;
+  const size_t B = cfg->batch;
+  h->rng.resize(B);
+  for (size_t i = 0; i < B; i++) h->rng[i].init_genrand(5489u + (uint32_t)i);
+#define ALLOC(ptr, bytes) do { cudaError_t e_ = cudaMalloc((void**)&(ptr), (bytes)); if (e_ != cudaSuccess) { pmg_destroy(h); return fail(PMG_ERR_CUDA, "cudaMalloc: %s", cudaGetErrorString(e_)); } } while (0)
+  ALLOC(h->d_state, sizeof(float) * h->state_words * B);
+  ALLOC(h->d_man, sizeof(float) * h->man_words * B);
+  ALLOC(h->d_spawn, sizeof(float) * h->spawn_w * B);
+  ALLOC(h->d_mask, B);
+  ALLOC(h->d_overflow, sizeof(int));
+  ALLOC(h->d_action, sizeof(float) * h->A * B);
+  ALLOC(h->d_obs, sizeof(float) * h->W * B);
+  ALLOC(h->d_reward, sizeof(float) * B);
+  ALLOC(h->d_done, B);
+  ALLOC(h->d_success, B);
+#undef ALLOC
+  if (cudaMallocHost((void**)&h->h_spawn, sizeof(float) * h->spawn_w * B) != cudaSuccess) { pmg_destroy(h); return fail(PMG_ERR_CUDA, "cudaMallocHost failed%s"); }
+  cudaMemset(h->d_state, 0, sizeof(float) * h->state_words * B);
+  cudaMemset(h->d_man, 0, sizeof(float) * h->man_words * B);
+  cudaMemset(h->d_overflow, 0, sizeof(int));
+  init_state_kernel<<<(int)((B + 127) / 128), 128>>>(h->d_state, (int)B, h->nblk, h->state_words);
+  h->launches++;
+  CUDA_TRY(cudaDeviceSynchronize());
+  *out = h;
+  return PMG_OK;
+}
+
+int pmg_destroy(pmg_handle* h) {
+  if (!h) return PMG_OK;
+  cudaSetDevice(h->cfg.device);
+  cudaFree(h->d_state); cudaFree(h->d_man); cudaFree(h->d_spawn); cudaFree(h->d_mask); cudaFree(h->d_overflow);
+  cudaFree(h->d_action); cudaFree(h->d_obs); cudaFree(h->d_reward); cudaFree(h->d_done); cudaFree(h->d_success);
+  if (h->h_spawn) cudaFreeHost(h->h_spawn);
+  delete h;
+  return PMG_OK;
+}
+
+int pmg_dims(const pmg_handle* h, int32_t dims[6]) {
+  if (!h || !dims) return fail(PMG_ERR_INVALID, "pmg_dims: null argument%s");
+  dims[0] = h->O; dims[1] = h->P; dims[2] = h->G; dims[3] = h->G; dims[4] = h->A; dims[5] = h->W;
+  return PMG_OK;
+}
+
+int pmg_seed(pmg_handle* h, const uint32_t* keys, const int32_t* lens, int32_t max_len) {
+  if (!h || !keys || !lens || max_len < 1) return fail(PMG_ERR_INVALID, "pmg_seed: bad argument%s");
+  for (int i = 0; i < h->cfg.batch; i++) {
+    if (lens[i] < 1 || lens[i] > max_len) return fail(PMG_ERR_INVALID, "pmg_seed: key length out of range%s");
+    h->rng[i].init_by_array(keys + (size_t)i * max_len, lens[i]);
+  }
+  return PMG_OK;
+}
+
+int pmg_spawn_width(const pmg_handle* h) { return h ? h->spawn_w : PMG_ERR_INVALID; }
+
+int pmg_last_spawn(const pmg_handle* h, float* spawn_host) {
+  if (!h || !spawn_host) return fail(PMG_ERR_INVALID, "pmg_last_spawn: null argument%s");
+  memcpy(spawn_host, h->h_spawn, sizeof(float) * h->spawn_w * h->cfg.batch);
+  return PMG_OK;
+}
+
+int pmg_reset(pmg_handle* h, const uint8_t* mask_host, const float* spawn_host, float* obs_dev, void* stream) {
+  if (!h || !obs_dev) return fail(PMG_ERR_INVALID, "pmg_reset: null argument%s");
+  cudaStream_t st = (cudaStream_t)stream;
+  CUDA_TRY(cudaSetDevice(h->cfg.device));
+  const size_t B = h->cfg.batch;
+  // the pinned staging buffer is reused: wait for the previous reset's copy to have been consumed
+  CUDA_TRY(cudaStreamSynchronize(st));
+  for (size_t i = 0; i < B; i++) {
+    if (mask_host && !mask_host[i]) continue;
+    if (spawn_host) memcpy(h->h_spawn + i * h->spawn_w, spawn_host + i * h->spawn_w, sizeof(float) * h->spawn_w);
+    else sample_spawn(h, (int)i, h->h_spawn + i * h->spawn_w);
+  }
+  CUDA_TRY(cudaMemcpyAsync(h->d_spawn, h->h_spawn, sizeof(float) * h->spawn_w * B, cudaMemcpyHostToDevice, st));
+  if (mask_host) CUDA_TRY(cudaMemcpyAsync(h->d_mask, mask_host, B, cudaMemcpyHostToDevice, st));
+  ResetIO r;
+  r.io = make_io(h, nullptr, obs_dev, nullptr, nullptr, nullptr);
+  r.mask = mask_host ? h->d_mask : nullptr;
+  r.spawn = h->d_spawn;
+  for (int k = 0; k < 3; k++) r.tip_init[k] = (float)h->tip_init[k];
+  PMG_DISPATCH(launch_reset, h, r, st);
+  h->launches++;
+  CUDA_TRY(cudaGetLastError());
+  if (mask_host) CUDA_TRY(cudaStreamSynchronize(st));  // mask_host may be pageable caller memory
+  h->was_reset = true;
+  return PMG_OK;
+}
+
+int pmg_step(pmg_handle* h, const float* action_dev, float* obs_dev, float* reward_dev, uint8_t* done_dev, uint8_t* success_dev, void* stream) {
+  if (!h || !action_dev || !obs_dev || !reward_dev || !done_dev || !success_dev) return fail(PMG_ERR_INVALID, "pmg_step: null argument%s");
+  if (!h->was_reset) return fail(PMG_ERR_STATE, "pmg_step: call pmg_reset first%s");
+  cudaStream_t st = (cudaStream_t)stream;
+  CUDA_TRY(cudaSetDevice(h->cfg.device));
+  StepIO io = make_io(h, action_dev, obs_dev, reward_dev, done_dev, success_dev);
+  PMG_DISPATCH(launch_step, h, io, st);
+  h->launches++;
+  CUDA_TRY(cudaGetLastError());
+  return PMG_OK;
+}
+
+int pmg_step_host(pmg_handle* h, const float* action_host, float* obs_host, float* reward_host, uint8_t* done_host, uint8_t* success_host, void* stream) {
+  if (!h || !action_host || !obs_host || !reward_host || !done_host || !success_host) return fail(PMG_ERR_INVALID, "pmg_step_host: null argument%s");
+  cudaStream_t st = (cudaStream_t)stream;
+  CUDA_TRY(cudaSetDevice(h->cfg.device));
+  const size_t B = h->cfg.batch;
+  CUDA_TRY(cudaMemcpyAsync(h->d_action, action_host, sizeof(float) * h->A * B, cudaMemcpyHostToDevice, st));
+  int rc = pmg_step(h, h->d_action, h->d_obs, h->d_reward, h->d_done, h->d_success, stream);
+  if (rc != PMG_OK) return rc;
+  CUDA_TRY(cudaMemcpyAsync(obs_host, h->d_obs, sizeof(float) * h->W * B, cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaMemcpyAsync(reward_host, h->d_reward, sizeof(float) * B, cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaMemcpyAsync(done_host, h->d_done, B, cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaMemcpyAsync(success_host, h->d_success, B, cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaStreamSynchronize(st));
+  return PMG_OK;
+}
+
+int pmg_compute_reward(const float* ag, const float* dg, int64_t n, int32_t g, float thr, int32_t binary, float* reward, uint8_t* ok, void* stream) {
+  if (!ag || !dg || !reward || !ok || n < 0 || g < 1) return fail(PMG_ERR_INVALID, "pmg_compute_reward: bad argument%s");
+  if (n == 0) return PMG_OK;
+  reward_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(ag, dg, n, g, thr, binary, reward, ok);
+  CUDA_TRY(cudaGetLastError());
+  return PMG_OK;
+}
+
+int pmg_state_width(const pmg_handle* h) { return h ? h->state_words : PMG_ERR_INVALID; }
+
+int pmg_get_state(pmg_handle* h, float* out) {
+  if (!h || !out) return fail(PMG_ERR_INVALID, "pmg_get_state: null argument%s");
+  CUDA_TRY(cudaSetDevice(h->cfg.device));
+  const size_t B = h->cfg.batch, Wd = h->state_words;
+  std::vector<float> tmp(B * Wd);
+  CUDA_TRY(cudaDeviceSynchronize());
+  CUDA_TRY(cudaMemcpy(tmp.data(), h->d_state, sizeof(float) * B * Wd, cudaMemcpyDeviceToHost));
+  for (size_t i = 0; i < B; i++) for (size_t w = 0; w < Wd; w++) out[i * Wd + w] = tmp[w * B + i];
+  return PMG_OK;
+}
+
+int pmg_set_state(pmg_handle* h, const float* in) {
+  if (!h || !in) return fail(PMG_ERR_INVALID, "pmg_set_state: null argument%s");
+  CUDA_TRY(cudaSetDevice(h->cfg.device));
+  const size_t B = h->cfg.batch, Wd = h->state_words;
+  std::vector<float> tmp(B * Wd);
+  for (size_t i = 0; i < B; i++) for (size_t w = 0; w < Wd; w++) tmp[w * B + i] = in[i * Wd + w];
+  CUDA_TRY(cudaDeviceSynchronize());
+  CUDA_TRY(cudaMemcpy(h->d_state, tmp.data(), sizeof(float) * B * Wd, cudaMemcpyHostToDevice));
+  CUDA_TRY(cudaMemset(h->d_man, 0, sizeof(float) * h->man_words * B));
+  h->was_reset = true;
+  return PMG_OK;
+}
+
+int64_t pmg_launch_count(const pmg_handle* h) { return h ? h->launches : 0; }
+
+int64_t pmg_overflow_count(pmg_handle* h) {
+  if (!h) return 0;
+  int v = 0;
+  cudaSetDevice(h->cfg.device);
+  cudaDeviceSynchronize();
+  cudaMemcpy(&v, h->d_overflow, sizeof(int), cudaMemcpyDeviceToHost);
+  return v;
+}
+
+}  // extern "C"

@@ -1,0 +1,658 @@
+// pmg_physics.cuh -- per-environment device routines of the batched Kuka simulator (sm_100a).
+//
+// One CUDA thread owns one environment for the whole env.step(): the hot loop (100 substeps
+// of forward dynamics + contact generation + 5-iteration projected Gauss-Seidel) is strictly
+// sequential per environment, so lanes are spent on independent environments, not on one.
+// Persistent state is struct-of-arrays in HBM ([word][env]) so that a warp's 32 environments
+// read and write 128-byte lines; the working set of a substep lives in registers / L1-resident
+// local memory.  No tensor cores: the largest matrix on this path is 9x9.
+//
+// What is computed follows the reference's call sequence (paths relative to
+// /root/reference/pybullet_multigoal_gym/): robots/kuka.py:167-225 (action map, IK, motors,
+// 5 x stepSimulation), envs/base_envs/base_env.py:215-219 (0.002 s x 20 substeps, 5 solver
+// iterations, contact ERP 0.9), and the Bullet behaviours listed in DESIGN.md.  The arithmetic
+// is organised differently from Bullet (composite-rigid-body mass matrix + Cholesky instead of
+// per-row articulated-body impulse responses) but is mathematically the same system.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <float.h>
+#include <math.h>
+#include <stdint.h>
+
+#include "../../include/pmg_model_constants.h"
+
+namespace pmg {
+
+constexpr int NB = PMG_NBODY;  // 10 robot bodies
+constexpr int ND = PMG_NDOF;   // 9 dofs
+
+// ---- physics parameters (base_env.py:215-219, kuka.py:223-225,282-301; Bullet defaults) ----
+constexpr float DT = 0.002f;
+constexpr float INV_DT = 500.0f;
+constexpr float OUTER_DT = 0.04f;
+constexpr int SUBSTEPS_PER_CALL = 20;
+constexpr int CALLS_PER_ENV_STEP = 5;
+constexpr int SOLVER_ITERS = 5;
+constexpr float CONTACT_ERP = 0.9f;
+constexpr float LINEAR_SLOP = 1e-5f;
+constexpr float RESIDUAL_THRESHOLD = 1e-7f;
+constexpr float GRAVITY = 9.81f;
+constexpr float LINK_DAMPING = 0.04f;
+constexpr float MAX_COORD_VEL = 100.0f;
+constexpr float LIMIT_MAX_IMPULSE = 100.0f;
+constexpr float SPLIT_IMPULSE_PEN_THRESHOLD = -0.04f;
+constexpr float MOTOR_KP = 0.03f;
+constexpr float MOTOR_KD = 1.0f;
+constexpr float ARM_FORCE = 200.0f;
+constexpr float FINGER_FORCE = 50.0f;
+constexpr float BREAKING_THRESHOLD_FACTOR = 0.02f;
+constexpr float BROADPHASE_MARGIN = 0.02f;
+constexpr float IK_JOINT_DAMPING = 0.5f;
+constexpr float IK_MAX_STEP = 0.78539816339744831f;
+constexpr float BOX_FUDGE = 1.05f;
+constexpr float PI_F = 3.14159265358979323846f;
+constexpr float GRIPPER_ABS_LIMIT = 0.035f;
+constexpr float BLOCK_SPAWN_Z = 0.175f;
+constexpr float BLOCK_HALF = (float)PMG_BLOCK_HALF;
+constexpr float BLOCK_INV_MASS = (float)(1.0 / PMG_BLOCK_MASS);
+constexpr float BLOCK_INV_INERTIA = (float)(1.0 / PMG_BLOCK_INERTIA);
+
+// ---- model tables (constant memory; indices are compile-time after unrolling) ---------------
+__constant__ float c_jxyz[NB][3] = PMG_BODY_JXYZ;
+__constant__ float c_jrot[NB][9] = PMG_BODY_JROT;
+__constant__ float c_mass[NB] = PMG_BODY_MASS;
+__constant__ float c_com[NB][3] = PMG_BODY_COM;
+__constant__ float c_inertia[NB][3] = PMG_BODY_INERTIA;
+__constant__ float c_dof_lower[ND] = PMG_DOF_LOWER;
+__constant__ float c_dof_upper[ND] = PMG_DOF_UPPER;
+__constant__ float c_dof_damping[ND] = PMG_DOF_DAMPING;
+__constant__ int c_nc_order[2 * ND] = PMG_NONCONTACT_ORDER;
+__constant__ float c_rest_pose0[7] = {0.f, -0.5592432f, 0.f, 1.733180f, 0.f, -0.8501557f, 0.f};  // kuka.py:27
+
+__host__ __device__ constexpr int body_parent(int b) { return b == 0 ? -1 : (b <= 7 ? b - 1 : 7); }
+__host__ __device__ constexpr int body_jtype(int b) { return b <= 6 ? 0 : (b == 7 ? 2 : 1); }
+__host__ __device__ constexpr int body_dof(int b) { return b <= 6 ? b : (b == 7 ? -1 : b - 1); }
+__host__ __device__ constexpr int dof_body(int d) { return d <= 6 ? d : d + 1; }
+
+// ---- small vector types ---------------------------------------------------------------------
+struct V3 { float x, y, z; };
+__device__ __forceinline__ V3 v3(float x, float y, float z) { V3 r; r.x = x; r.y = y; r.z = z; return r; }
+__device__ __forceinline__ V3 operator+(V3 a, V3 b) { return v3(a.x + b.x, a.y + b.y, a.z + b.z); }
+__device__ __forceinline__ V3 operator-(V3 a, V3 b) { return v3(a.x - b.x, a.y - b.y, a.z - b.z); }
+__device__ __forceinline__ V3 operator-(V3 a) { return v3(-a.x, -a.y, -a.z); }
+__device__ __forceinline__ V3 operator*(float s, V3 a) { return v3(s * a.x, s * a.y, s * a.z); }
+__device__ __forceinline__ V3 operator*(V3 a, float s) { return v3(s * a.x, s * a.y, s * a.z); }
+__device__ __forceinline__ V3& operator+=(V3& a, V3 b) { a.x += b.x; a.y += b.y; a.z += b.z; return a; }
+__device__ __forceinline__ V3& operator-=(V3& a, V3 b) { a.x -= b.x; a.y -= b.y; a.z -= b.z; return a; }
+__device__ __forceinline__ float dot(V3 a, V3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+__device__ __forceinline__ V3 cross(V3 a, V3 b) { return v3(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x); }
+__device__ __forceinline__ float norm(V3 a) { return sqrtf(dot(a, a)); }
+__device__ __forceinline__ float comp(V3 a, int i) { return i == 0 ? a.x : (i == 1 ? a.y : a.z); }
+__device__ __forceinline__ void setcomp(V3& a, int i, float v) { if (i == 0) a.x = v; else if (i == 1) a.y = v; else a.z = v; }
+
+struct M3 { V3 r0, r1, r2; };  // rows
+__device__ __forceinline__ M3 m3_identity() { M3 m; m.r0 = v3(1, 0, 0); m.r1 = v3(0, 1, 0); m.r2 = v3(0, 0, 1); return m; }
+__device__ __forceinline__ V3 mul(const M3& m, V3 v) { return v3(dot(m.r0, v), dot(m.r1, v), dot(m.r2, v)); }
+__device__ __forceinline__ V3 mulT(const M3& m, V3 v) { return v.x * m.r0 + v.y * m.r1 + v.z * m.r2; }
+__device__ __forceinline__ V3 col(const M3& m, int i) { return v3(comp(m.r0, i), comp(m.r1, i), comp(m.r2, i)); }
+__device__ __forceinline__ V3 row(const M3& m, int i) { return i == 0 ? m.r0 : (i == 1 ? m.r1 : m.r2); }
+__device__ __forceinline__ M3 mul(const M3& a, const M3& b) {
+  M3 r;
+  r.r0 = a.r0.x * b.r0 + a.r0.y * b.r1 + a.r0.z * b.r2;
+  r.r1 = a.r1.x * b.r0 + a.r1.y * b.r1 + a.r1.z * b.r2;
+  r.r2 = a.r2.x * b.r0 + a.r2.y * b.r1 + a.r2.z * b.r2;
+  return r;
+}
+__device__ __forceinline__ M3 quat_to_m3(float x, float y, float z, float w) {
+  float d = x * x + y * y + z * z + w * w, s = 2.0f / d;
+  float xs = x * s, ys = y * s, zs = z * s;
+  float wx = w * xs, wy = w * ys, wz = w * zs, xx = x * xs, xy = x * ys, xz = x * zs, yy = y * ys, yz = y * zs, zz = z * zs;
+  M3 m;
+  m.r0 = v3(1 - (yy + zz), xy - wz, xz + wy);
+  m.r1 = v3(xy + wz, 1 - (xx + zz), yz - wx);
+  m.r2 = v3(xz - wy, yz + wx, 1 - (xx + yy));
+  return m;
+}
+__device__ __forceinline__ void m3_to_quat(const M3& m, float q[4]) {  // xyzw
+  float e[3][3] = {{m.r0.x, m.r0.y, m.r0.z}, {m.r1.x, m.r1.y, m.r1.z}, {m.r2.x, m.r2.y, m.r2.z}};
+  float trace = e[0][0] + e[1][1] + e[2][2];
+  if (trace > 0) {
+    float s = sqrtf(trace + 1.0f);
+    q[3] = s * 0.5f; s = 0.5f / s;
+    q[0] = (e[2][1] - e[1][2]) * s; q[1] = (e[0][2] - e[2][0]) * s; q[2] = (e[1][0] - e[0][1]) * s;
+  } else {
+    int i = e[0][0] < e[1][1] ? (e[1][1] < e[2][2] ? 2 : 1) : (e[0][0] < e[2][2] ? 2 : 0);
+    int j = (i + 1) % 3, k = (i + 2) % 3;
+    float s = sqrtf(e[i][i] - e[j][j] - e[k][k] + 1.0f);
+    q[i] = s * 0.5f; s = 0.5f / s;
+    q[3] = (e[k][j] - e[j][k]) * s;
+    q[j] = (e[j][i] + e[i][j]) * s;
+    q[k] = (e[k][i] + e[i][k]) * s;
+  }
+}
+
+// ---- kinematics -----------------------------------------------------------------------------
+struct Frames {
+  M3 R[NB];   // link frame orientation (world)
+  V3 p[NB];   // link frame origin (world)
+  V3 a[NB];   // joint axis (world); zero for the fixed gripper base
+};
+
+__device__ __forceinline__ M3 load_jrot(int b) {
+  M3 m;
+  m.r0 = v3(c_jrot[b][0], c_jrot[b][1], c_jrot[b][2]);
+  m.r1 = v3(c_jrot[b][3], c_jrot[b][4], c_jrot[b][5]);
+  m.r2 = v3(c_jrot[b][6], c_jrot[b][7], c_jrot[b][8]);
+  return m;
+}
+
+// Link frames of bodies [0, NBODIES).  Arm joints rotate about their local z, the fingers slide
+// along -/+ y of the gripper base (iiwa14_parallel_jaw.urdf:94-288,418-456).
+template <int NBODIES>
+__device__ __forceinline__ void forward_kinematics(const float* q, Frames& f) {
+#pragma unroll
+  for (int b = 0; b < NBODIES; b++) {
+    constexpr int dummy = 0; (void)dummy;
+    const int par = body_parent(b);
+    M3 Rp = par < 0 ? m3_identity() : f.R[par];
+    V3 pp = par < 0 ? v3(0, 0, 0) : f.p[par];
+    M3 Rj = mul(Rp, load_jrot(b));
+    V3 pj = pp + mul(Rp, v3(c_jxyz[b][0], c_jxyz[b][1], c_jxyz[b][2]));
+    if (body_jtype(b) == 0) {
+      float s, c;
+      sincosf(q[body_dof(b)], &s, &c);
+      // Rj * Rz(q): new x column = c*x + s*y, new y column = -s*x + c*y
+      M3 R;
+      R.r0 = v3(c * Rj.r0.x + s * Rj.r0.y, -s * Rj.r0.x + c * Rj.r0.y, Rj.r0.z);
+      R.r1 = v3(c * Rj.r1.x + s * Rj.r1.y, -s * Rj.r1.x + c * Rj.r1.y, Rj.r1.z);
+      R.r2 = v3(c * Rj.r2.x + s * Rj.r2.y, -s * Rj.r2.x + c * Rj.r2.y, Rj.r2.z);
+      f.R[b] = R; f.p[b] = pj; f.a[b] = col(Rj, 2);
+    } else if (body_jtype(b) == 1) {
+      V3 ay = col(Rj, 1);
+      V3 ax = b == PMG_BODY_FINGER1 ? -ay : ay;  // axis (0,-1,0) / (0,+1,0)
+      f.R[b] = Rj; f.a[b] = ax; f.p[b] = pj + q[body_dof(b)] * ax;
+    } else {
+      f.R[b] = Rj; f.p[b] = pj; f.a[b] = v3(0, 0, 0);
+    }
+  }
+}
+
+__device__ __forceinline__ V3 tip_position(const Frames& f) {
+  const float t[3] = PMG_TIP_OFFSET;
+  return f.p[PMG_BODY_LINK7] + mul(f.R[PMG_BODY_LINK7], v3(t[0], t[1], t[2]));
+}
+
+// velocity of world point `pt` rigidly attached to `body`, and the body's angular velocity
+template <int BODY>
+__device__ __forceinline__ void point_velocity(const Frames& f, const float* qd, V3 pt, V3& lin, V3& ang) {
+  lin = v3(0, 0, 0); ang = v3(0, 0, 0);
+#pragma unroll
+  for (int j = 0; j <= 6; j++) {
+    lin += qd[j] * cross(f.a[j], pt - f.p[j]);
+    ang += qd[j] * f.a[j];
+  }
+  if (BODY == PMG_BODY_FINGER1 || BODY == PMG_BODY_FINGER2) lin += qd[body_dof(BODY)] * f.a[BODY];
+}
+
+// ---- inverse kinematics (pybullet calculateInverseKinematics, DLS, no null space) -----------
+// kuka.py:266-279: <= 40 iterations, stop when the tip is within 1e-5 of the target; per
+// iteration dtheta = (J^T J + 0.5 I)^-1 J^T e with e = [position error; orientation error as
+// axis*angle], largest |dtheta| clamped to 45 degrees.  Finger columns of J are zero, so the
+// 9x9 system splits into the 7x7 arm block solved here and dtheta_finger = 0.
+__device__ void inverse_kinematics(float* q /* in: seed, out: result (first 7 used) */, V3 target, const float tq[4]) {
+  float diff = 1e30f;
+  for (int it = 0; it < 40 && diff > 1e-5f; it++) {
+    Frames f;
+    forward_kinematics<7>(q, f);
+    V3 tip = tip_position(f);
+    V3 ep = target - tip;
+    diff = norm(ep);
+    float qc[4];
+    m3_to_quat(f.R[PMG_BODY_LINK7], qc);
+    // dq = target * conj(current)
+    float ax = -qc[0], ay = -qc[1], az = -qc[2], aw = qc[3];
+    float dx = tq[3] * ax + tq[0] * aw + tq[1] * az - tq[2] * ay;
+    float dy = tq[3] * ay + tq[1] * aw + tq[2] * ax - tq[0] * az;
+    float dz = tq[3] * az + tq[2] * aw + tq[0] * ay - tq[1] * ax;
+    float dw = tq[3] * aw - tq[0] * ax - tq[1] * ay - tq[2] * az;
+    // axis*angle; 2*atan2(|v|, w) equals Bullet's 2*acos(w) but stays accurate in fp32 near 0
+    float vn2 = dx * dx + dy * dy + dz * dz;
+    V3 er;
+    if (vn2 < 10.0f * 2.220446049250313e-16f) {
+      float ang = 2.0f * atan2f(sqrtf(vn2), dw);
+      if (ang > PI_F) ang -= 2.0f * PI_F;
+      er = v3(ang, 0, 0);
+    } else {
+      float vn = sqrtf(vn2);
+      float ang = 2.0f * atan2f(vn, dw);
+      if (ang > PI_F) ang -= 2.0f * PI_F;
+      float s = ang / vn;
+      er = v3(dx * s, dy * s, dz * s);
+    }
+    // J columns: linear a_j x (tip - o_j), angular a_j
+    V3 Jl[7], Ja[7];
+#pragma unroll
+    for (int j = 0; j < 7; j++) { Jl[j] = cross(f.a[j], tip - f.p[j]); Ja[j] = f.a[j]; }
+    float A[7][7], rhs[7];
+#pragma unroll
+    for (int i = 0; i < 7; i++) {
+#pragma unroll
+      for (int j = 0; j <= i; j++) A[i][j] = dot(Jl[i], Jl[j]) + dot(Ja[i], Ja[j]) + (i == j ? IK_JOINT_DAMPING : 0.0f);
+      rhs[i] = dot(Jl[i], ep) + dot(Ja[i], er);
+    }
+    // Cholesky solve of the SPD 7x7 system
+#pragma unroll
+    for (int j = 0; j < 7; j++) {
+      float d = A[j][j];
+#pragma unroll
+      for (int k = 0; k < j; k++) d -= A[j][k] * A[j][k];
+      d = sqrtf(d);
+      A[j][j] = d;
+      float inv = 1.0f / d;
+#pragma unroll
+      for (int i = j + 1; i < 7; i++) {
+        float s = A[i][j];
+#pragma unroll
+        for (int k = 0; k < j; k++) s -= A[i][k] * A[j][k];
+        A[i][j] = s * inv;
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 7; i++) {
+      float s = rhs[i];
+#pragma unroll
+      for (int k = 0; k < i; k++) s -= A[i][k] * rhs[k];
+      rhs[i] = s / A[i][i];
+    }
+#pragma unroll
+    for (int i = 6; i >= 0; i--) {
+      float s = rhs[i];
+#pragma unroll
+      for (int k = i + 1; k < 7; k++) s -= A[k][i] * rhs[k];
+      rhs[i] = s / A[i][i];
+    }
+    float mx = 0.0f;
+#pragma unroll
+    for (int i = 0; i < 7; i++) mx = fmaxf(mx, fabsf(rhs[i]));
+    float scale = mx > IK_MAX_STEP ? IK_MAX_STEP / mx : 1.0f;
+#pragma unroll
+    for (int i = 0; i < 7; i++) q[i] += scale * rhs[i];
+  }
+}
+
+// ---- robot dynamics: bias forces (recursive Newton-Euler) and mass matrix (CRBA) -------------
+struct BodyInertia { V3 rc; M3 Iw; };  // COM offset from the link origin (world axes), world inertia about the COM
+
+__device__ __forceinline__ BodyInertia body_inertia(const Frames& f, int b) {
+  BodyInertia bi;
+  const M3& R = f.R[b];
+  bi.rc = mul(R, v3(c_com[b][0], c_com[b][1], c_com[b][2]));
+  float i0 = c_inertia[b][0], i1 = c_inertia[b][1], i2 = c_inertia[b][2];
+  // R diag(I) R^T
+  V3 a0 = v3(R.r0.x * i0, R.r0.y * i1, R.r0.z * i2);
+  V3 a1 = v3(R.r1.x * i0, R.r1.y * i1, R.r1.z * i2);
+  V3 a2 = v3(R.r2.x * i0, R.r2.y * i1, R.r2.z * i2);
+  bi.Iw.r0 = v3(dot(a0, R.r0), dot(a0, R.r1), dot(a0, R.r2));
+  bi.Iw.r1 = v3(bi.Iw.r0.y, dot(a1, R.r1), dot(a1, R.r2));
+  bi.Iw.r2 = v3(bi.Iw.r0.z, bi.Iw.r1.z, dot(a2, R.r2));
+  return bi;
+}
+
+// Generalised bias force C(q,qd) + g(q) + Bullet's per-link velocity damping, by the classical
+// recursive Newton-Euler sweep with qdd = 0 (lever arms stay link-local => fp32 friendly).
+__device__ void bias_forces(const Frames& f, const float* qd, float* bias) {
+  V3 w[NB], al[NB], acc[NB], vel[NB];  // angular vel / accel, origin accel / vel
+  V3 F[NB], N[NB];                      // net force at the COM, net moment about the link origin
+#pragma unroll
+  for (int b = 0; b < NB; b++) {
+    const int par = body_parent(b);
+    V3 wp = par < 0 ? v3(0, 0, 0) : w[par], alp = par < 0 ? v3(0, 0, 0) : al[par];
+    V3 accp = par < 0 ? v3(0, 0, GRAVITY) : acc[par], velp = par < 0 ? v3(0, 0, 0) : vel[par];
+    V3 r = par < 0 ? f.p[b] : f.p[b] - f.p[par];
+    V3 wxr = cross(wp, r);
+    V3 a_o = accp + cross(alp, r) + cross(wp, wxr);
+    V3 v_o = velp + wxr;
+    if (body_jtype(b) == 0) {
+      V3 aq = qd[body_dof(b)] * f.a[b];
+      w[b] = wp + aq;
+      al[b] = alp + cross(wp, aq);
+    } else if (body_jtype(b) == 1) {
+      V3 aq = qd[body_dof(b)] * f.a[b];
+      w[b] = wp; al[b] = alp;
+      a_o += 2.0f * cross(wp, aq);
+      v_o += aq;
+    } else { w[b] = wp; al[b] = alp; }
+    acc[b] = a_o; vel[b] = v_o;
+    BodyInertia bi = body_inertia(f, b);
+    V3 wxrc = cross(w[b], bi.rc);
+    V3 a_c = a_o + cross(al[b], bi.rc) + cross(w[b], wxrc);
+    V3 v_c = v_o + wxrc;
+    float m = c_mass[b];
+    float kl = LINK_DAMPING + LINK_DAMPING * norm(v_c), ka = LINK_DAMPING + LINK_DAMPING * norm(w[b]);
+    V3 Fc = m * a_c + (m * kl) * v_c;
+    V3 Iw_w = mul(bi.Iw, w[b]);
+    V3 Nc = mul(bi.Iw, al[b]) + cross(w[b], Iw_w) + ka * Iw_w;
+    F[b] = Fc;
+    N[b] = Nc + cross(bi.rc, Fc);
+  }
+#pragma unroll
+  for (int b = NB - 1; b >= 0; b--) {
+    const int par = body_parent(b);
+    if (body_jtype(b) == 0) bias[body_dof(b)] = dot(f.a[b], N[b]);
+    else if (body_jtype(b) == 1) bias[body_dof(b)] = dot(f.a[b], F[b]);
+    if (par >= 0) {
+      F[par] += F[b];
+      N[par] += N[b] + cross(f.p[b] - f.p[par], F[b]);
+    }
+  }
+}
+
+// Joint-space mass matrix by the composite-rigid-body algorithm (lower triangle, M[i][j], j<=i).
+__device__ void mass_matrix(const Frames& f, float M[ND][ND]) {
+  float mc[NB]; V3 hc[NB]; M3 Ic[NB];  // composite mass, first moment, inertia about the link origin
+#pragma unroll
+  for (int b = 0; b < NB; b++) {
+    BodyInertia bi = body_inertia(f, b);
+    float m = c_mass[b];
+    mc[b] = m; hc[b] = m * bi.rc;
+    float cc = dot(bi.rc, bi.rc);
+    Ic[b].r0 = bi.Iw.r0 + m * (v3(cc, 0, 0) - bi.rc.x * bi.rc);
+    Ic[b].r1 = bi.Iw.r1 + m * (v3(0, cc, 0) - bi.rc.y * bi.rc);
+    Ic[b].r2 = bi.Iw.r2 + m * (v3(0, 0, cc) - bi.rc.z * bi.rc);
+  }
+#pragma unroll
+  for (int b = NB - 1; b >= 1; b--) {
+    const int par = body_parent(b);
+    V3 r = f.p[b] - f.p[par];
+    float hr = 2.0f * dot(hc[b], r) + mc[b] * dot(r, r);
+    // I' = I + (2 h.r + m r.r) 1 - (h r^T + r h^T) - m r r^T
+    V3 hm = hc[b] + mc[b] * r;
+    Ic[par].r0 += Ic[b].r0 + v3(hr, 0, 0) - hc[b].x * r - r.x * hm;
+    Ic[par].r1 += Ic[b].r1 + v3(0, hr, 0) - hc[b].y * r - r.y * hm;
+    Ic[par].r2 += Ic[b].r2 + v3(0, 0, hr) - hc[b].z * r - r.z * hm;
+    hc[par] += hc[b] + mc[b] * r;
+    mc[par] += mc[b];
+  }
+#pragma unroll
+  for (int i = 0; i < ND; i++) {
+#pragma unroll
+    for (int j = 0; j < ND; j++) M[i][j] = 0.0f;
+  }
+#pragma unroll
+  for (int i = 0; i < ND; i++) {
+    const int b = dof_body(i);
+    V3 n, l;  // moment about p[b] and force produced by unit acceleration of joint i
+    if (body_jtype(b) == 0) { n = mul(Ic[b], f.a[b]); l = cross(f.a[b], hc[b]); M[i][i] = dot(f.a[b], n); }
+    else { l = mc[b] * f.a[b]; n = cross(hc[b], f.a[b]); M[i][i] = mc[b]; }
+    // walk up the arm: every proper ancestor with a dof is a revolute arm joint
+#pragma unroll
+    for (int j = (i <= 6 ? i - 1 : 6); j >= 0; j--) {
+      V3 nj = n + cross(f.p[b] - f.p[j], l);
+      M[i][j] = dot(f.a[j], nj);
+    }
+  }
+}
+
+// In-place Cholesky of the lower triangle, then Minv = L^-T L^-1 (full symmetric matrix out).
+__device__ void invert_spd9(float M[ND][ND], float Minv[ND][ND]) {
+#pragma unroll
+  for (int j = 0; j < ND; j++) {
+    float d = M[j][j];
+#pragma unroll
+    for (int k = 0; k < j; k++) d -= M[j][k] * M[j][k];
+    d = sqrtf(d);
+    float inv = 1.0f / d;
+    M[j][j] = inv;  // store the reciprocal of the diagonal
+#pragma unroll
+    for (int i = j + 1; i < ND; i++) {
+      float s = M[i][j];
+#pragma unroll
+      for (int k = 0; k < j; k++) s -= M[i][k] * M[j][k];
+      M[i][j] = s * inv;
+    }
+  }
+  // Linv (lower): column by column
+  float Li[ND][ND];
+#pragma unroll
+  for (int c = 0; c < ND; c++) {
+    Li[c][c] = M[c][c];
+#pragma unroll
+    for (int i = c + 1; i < ND; i++) {
+      float s = 0.0f;
+#pragma unroll
+      for (int k = c; k < i; k++) s -= M[i][k] * Li[k][c];
+      Li[i][c] = s * M[i][i];
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < ND; i++) {
+#pragma unroll
+    for (int j = 0; j <= i; j++) {
+      float s = 0.0f;
+#pragma unroll
+      for (int k = i; k < ND; k++) s += Li[k][i] * Li[k][j];
+      Minv[i][j] = s; Minv[j][i] = s;
+    }
+  }
+}
+
+// ---- box-box contact generation (SAT + incident-face clipping, after btBoxBoxDetector) -------
+struct Contact { V3 pB, nB; float dist; };
+
+__device__ int clip_quad_to_rect(const float h[2], const float quad[8], float out[16]) {
+  float buf[2][16];
+  int nq = 4, nr = 0, cur = 0;
+#pragma unroll
+  for (int i = 0; i < 8; i++) buf[0][i] = quad[i];
+  bool full = false;
+  for (int dir = 0; dir <= 1 && !full; dir++) {
+    for (int sign = -1; sign <= 1 && !full; sign += 2) {
+      const float* q = buf[cur];
+      float* r = buf[cur ^ 1];
+      nr = 0;
+      for (int i = 0; i < nq; i++) {
+        const float* pq = q + 2 * i;
+        const float* nx = q + 2 * ((i + 1) % nq);
+        bool in0 = sign * pq[dir] < h[dir], in1 = sign * nx[dir] < h[dir];
+        if (in0) {
+          r[2 * nr] = pq[0]; r[2 * nr + 1] = pq[1]; nr++;
+          if (nr & 8) { full = true; break; }
+        }
+        if (in0 != in1) {
+          r[2 * nr + (1 - dir)] = pq[1 - dir] + (nx[1 - dir] - pq[1 - dir]) / (nx[dir] - pq[dir]) * (sign * h[dir] - pq[dir]);
+          r[2 * nr + dir] = sign * h[dir];
+          nr++;
+          if (nr & 8) { full = true; break; }
+        }
+      }
+      cur ^= 1;
+      nq = nr;
+    }
+  }
+  for (int i = 0; i < 2 * nr; i++) out[i] = buf[cur][i];
+  return nr;
+}
+
+__device__ void cull_points(int n, const float* p, int m, int i0, int* iret) {
+  float a, cx, cy, q;
+  if (n == 1) { cx = p[0]; cy = p[1]; }
+  else if (n == 2) { cx = 0.5f * (p[0] + p[2]); cy = 0.5f * (p[1] + p[3]); }
+  else {
+    a = 0; cx = 0; cy = 0;
+    for (int i = 0; i < n - 1; i++) {
+      q = p[2 * i] * p[2 * i + 3] - p[2 * i + 2] * p[2 * i + 1];
+      a += q; cx += q * (p[2 * i] + p[2 * i + 2]); cy += q * (p[2 * i + 1] + p[2 * i + 3]);
+    }
+    q = p[2 * n - 2] * p[1] - p[0] * p[2 * n - 1];
+    a = fabsf(a + q) > FLT_EPSILON ? 1.0f / (3.0f * (a + q)) : 1e18f;
+    cx = a * (cx + q * (p[2 * n - 2] + p[0]));
+    cy = a * (cy + q * (p[2 * n - 1] + p[1]));
+  }
+  float A[8]; bool avail[8];
+  for (int i = 0; i < n; i++) { A[i] = atan2f(p[2 * i + 1] - cy, p[2 * i] - cx); avail[i] = true; }
+  avail[i0] = false; iret[0] = i0;
+  for (int j = 1; j < m; j++) {
+    a = j * (2.0f * PI_F / m) + A[i0];
+    if (a > PI_F) a -= 2.0f * PI_F;
+    float best = 1e9f; int bi = i0;
+    for (int i = 0; i < n; i++) if (avail[i]) {
+      float d = fabsf(A[i] - a);
+      if (d > PI_F) d = 2.0f * PI_F - d;
+      if (d < best) { best = d; bi = i; }
+    }
+    avail[bi] = false; iret[j] = bi;
+  }
+}
+
+// Boxes: centre p, orientation R (columns = box axes), half extents.  Up to 4 contacts out:
+// point on B, normal on B (pointing from B to A), signed distance (<= 0).
+__device__ int box_box(V3 p1, const M3& R1, V3 A, V3 p2, const M3& R2, V3 B, Contact* out) {
+  V3 p = p2 - p1;
+  V3 pp = mulT(R1, p);
+  float R[3][3], Q[3][3];
+#pragma unroll
+  for (int i = 0; i < 3; i++) {
+    V3 ci = col(R1, i);
+#pragma unroll
+    for (int j = 0; j < 3; j++) { R[i][j] = dot(ci, col(R2, j)); Q[i][j] = fabsf(R[i][j]); }
+  }
+  const float Ah[3] = {A.x, A.y, A.z}, Bh[3] = {B.x, B.y, B.z}, ppa[3] = {pp.x, pp.y, pp.z};
+  float s = -FLT_MAX, s2;
+  int code = 0; bool invert = false;
+  int from_R = 0, ncol = 0;
+  V3 normalC = v3(0, 0, 0);
+#pragma unroll
+  for (int i = 0; i < 3; i++) {
+    s2 = fabsf(ppa[i]) - (Ah[i] + Bh[0] * Q[i][0] + Bh[1] * Q[i][1] + Bh[2] * Q[i][2]);
+    if (s2 > 0) return 0;
+    if (s2 > s) { s = s2; from_R = 1; ncol = i; invert = ppa[i] < 0; code = i + 1; }
+  }
+#pragma unroll
+  for (int j = 0; j < 3; j++) {
+    float e1 = dot(col(R2, j), p);
+    s2 = fabsf(e1) - (Ah[0] * Q[0][j] + Ah[1] * Q[1][j] + Ah[2] * Q[2][j] + Bh[j]);
+    if (s2 > 0) return 0;
+    if (s2 > s) { s = s2; from_R = 2; ncol = j; invert = e1 < 0; code = j + 4; }
+  }
+#pragma unroll
+  for (int i = 0; i < 3; i++) {
+#pragma unroll
+    for (int j = 0; j < 3; j++) Q[i][j] += 1.0e-5f;
+  }
+#pragma unroll
+  for (int i = 0; i < 3; i++) {
+    const int i1 = (i + 1) % 3, i2 = (i + 2) % 3;
+#pragma unroll
+    for (int j = 0; j < 3; j++) {
+      const int j1 = (j + 1) % 3, j2 = (j + 2) % 3;
+      float e1 = ppa[i2] * R[i1][j] - ppa[i1] * R[i2][j];
+      float e2 = Ah[i1] * Q[i2][j] + Ah[i2] * Q[i1][j] + Bh[j1] * Q[i][j2] + Bh[j2] * Q[i][j1];
+      s2 = fabsf(e1) - e2;
+      if (s2 > FLT_EPSILON) return 0;
+      float n1 = -R[i2][j], n2 = R[i1][j];
+      float l = sqrtf(n1 * n1 + n2 * n2);
+      if (l > FLT_EPSILON) {
+        s2 /= l;
+        if (s2 * BOX_FUDGE > s) {
+          s = s2; from_R = 0;
+          float nn[3]; nn[i] = 0; nn[i1] = n1 / l; nn[i2] = n2 / l;
+          normalC = v3(nn[0], nn[1], nn[2]);
+          invert = e1 < 0; code = 7 + 3 * i + j;
+        }
+      }
+    }
+  }
+  if (!code) return 0;
+  V3 normal = from_R == 1 ? col(R1, ncol) : (from_R == 2 ? col(R2, ncol) : mul(R1, normalC));
+  if (invert) normal = -normal;
+  float depth = -s;
+  if (code > 6) {  // edge-edge: the closest point on B's edge
+    V3 pa = p1, pb = p2;
+#pragma unroll
+    for (int j = 0; j < 3; j++) {
+      V3 c1 = col(R1, j), c2 = col(R2, j);
+      pa += ((dot(normal, c1) > 0 ? 1.0f : -1.0f) * Ah[j]) * c1;
+      pb += ((dot(normal, c2) > 0 ? -1.0f : 1.0f) * Bh[j]) * c2;
+    }
+    V3 ua = col(R1, (code - 7) / 3), ub = col(R2, (code - 7) % 3);
+    V3 d = pb - pa;
+    float uaub = dot(ua, ub), q1 = dot(ua, d), q2 = -dot(ub, d), den = 1 - uaub * uaub;
+    float beta = den <= 1e-4f ? 0.0f : (uaub * q1 + q2) / den;
+    out[0].pB = pb + beta * ub; out[0].nB = -normal; out[0].dist = -depth;
+    return 1;
+  }
+  // face contact: reference face on `a`, incident face on `b`
+  const bool swap = code > 3;
+  const M3& Ra = swap ? R2 : R1;
+  const M3& Rb = swap ? R1 : R2;
+  V3 pa = swap ? p2 : p1, pb = swap ? p1 : p2;
+  const float* Sa = swap ? Bh : Ah;
+  const float* Sb = swap ? Ah : Bh;
+  V3 normal2 = swap ? -normal : normal;
+  V3 nr = mulT(Rb, normal2);
+  float anr[3] = {fabsf(nr.x), fabsf(nr.y), fabsf(nr.z)};
+  int lanr, a1, a2;
+  if (anr[1] > anr[0]) {
+    if (anr[1] > anr[2]) { a1 = 0; lanr = 1; a2 = 2; } else { a1 = 0; a2 = 1; lanr = 2; }
+  } else {
+    if (anr[0] > anr[2]) { lanr = 0; a1 = 1; a2 = 2; } else { a1 = 0; a2 = 1; lanr = 2; }
+  }
+  V3 center = pb - pa + ((comp(nr, lanr) < 0 ? 1.0f : -1.0f) * Sb[lanr]) * col(Rb, lanr);
+  int codeN = swap ? code - 4 : code - 1, code1, code2;
+  if (codeN == 0) { code1 = 1; code2 = 2; } else if (codeN == 1) { code1 = 0; code2 = 2; } else { code1 = 0; code2 = 1; }
+  V3 ra1 = col(Ra, code1), ra2 = col(Ra, code2), rb1 = col(Rb, a1), rb2 = col(Rb, a2);
+  float c1 = dot(center, ra1), c2 = dot(center, ra2);
+  float m11 = dot(ra1, rb1), m12 = dot(ra1, rb2), m21 = dot(ra2, rb1), m22 = dot(ra2, rb2);
+  float quad[8];
+  {
+    float k1 = m11 * Sb[a1], k2 = m21 * Sb[a1], k3 = m12 * Sb[a2], k4 = m22 * Sb[a2];
+    quad[0] = c1 - k1 - k3; quad[1] = c2 - k2 - k4;
+    quad[2] = c1 - k1 + k3; quad[3] = c2 - k2 + k4;
+    quad[4] = c1 + k1 + k3; quad[5] = c2 + k2 + k4;
+    quad[6] = c1 + k1 - k3; quad[7] = c2 + k2 - k4;
+  }
+  float rect[2] = {Sa[code1], Sa[code2]}, ret[16];
+  int n = clip_quad_to_rect(rect, quad, ret);
+  if (n < 1) return 0;
+  V3 point[8]; float dep[8];
+  float det1 = 1.0f / (m11 * m22 - m12 * m21);
+  m11 *= det1; m12 *= det1; m21 *= det1; m22 *= det1;
+  int cnum = 0;
+  for (int j = 0; j < n; j++) {
+    float k1 = m22 * (ret[2 * j] - c1) - m12 * (ret[2 * j + 1] - c2);
+    float k2 = -m21 * (ret[2 * j] - c1) + m11 * (ret[2 * j + 1] - c2);
+    V3 pt = center + k1 * rb1 + k2 * rb2;
+    float dp = Sa[codeN] - dot(normal2, pt);
+    if (dp >= 0) { point[cnum] = pt; dep[cnum] = dp; ret[2 * cnum] = ret[2 * j]; ret[2 * cnum + 1] = ret[2 * j + 1]; cnum++; }
+  }
+  if (cnum < 1) return 0;
+  int maxc = cnum < 4 ? cnum : 4, idx[8];
+  if (cnum <= maxc) { for (int j = 0; j < cnum; j++) idx[j] = j; }
+  else {
+    int i1 = 0; float maxdepth = dep[0];
+    for (int i = 1; i < cnum; i++) if (dep[i] > maxdepth) { maxdepth = dep[i]; i1 = i; }
+    cull_points(cnum, ret, maxc, i1, idx);
+  }
+  for (int j = 0; j < maxc; j++) {
+    int k = idx[j];
+    V3 w = point[k] + pa;
+    if (swap) w -= dep[k] * normal;  // incident face was on A: move the point onto B
+    out[j].pB = w; out[j].nB = -normal; out[j].dist = -dep[k];
+  }
+  return maxc;
+}
+
+__device__ __forceinline__ void plane_space(V3 n, V3& p, V3& q) {  // btPlaneSpace1
+  if (fabsf(n.z) > 0.70710678118654752440f) {
+    float a = n.y * n.y + n.z * n.z, k = 1.0f / sqrtf(a);
+    p = v3(0, -n.z * k, n.y * k);
+    q = v3(a * k, -n.x * p.z, n.x * p.y);
+  } else {
+    float a = n.x * n.x + n.y * n.y, k = 1.0f / sqrtf(a);
+    p = v3(-n.y * k, n.x * k, 0);
+    q = v3(-n.z * p.y, n.z * p.x, a * k);
+  }
+}
+
+}  // namespace pmg

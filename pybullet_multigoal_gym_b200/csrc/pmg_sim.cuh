@@ -1,0 +1,462 @@
+// pmg_sim.cuh -- one environment's substep / env-step on top of pmg_physics.cuh.
+//
+// Persistent per-env state lives in two struct-of-arrays buffers in HBM:
+//   state[word][env]   : q[9] qd[9] ee_target[3] rest_pose[7] motor_target[9] motor_max_impulse[9]
+//                        | per block pos[3] quat[4] linvel[3] angvel[3] | desired_goal[G] | elapsed
+//   manifold[word][env]: per collision pair: count, then 4 x (localA[3] localB[3] normalB[3] dist)
+// Thread t of a warp touches word w at address (w*batch + env), so every access of a warp is one
+// or two 128-byte lines.
+#pragma once
+
+#include "pmg_physics.cuh"
+
+namespace pmg {
+
+constexpr int MAN_WORDS = 41;  // per pair
+constexpr int ST_Q = 0, ST_QD = 9, ST_EE = 18, ST_REST = 21, ST_MT = 28, ST_MI = 37, ST_BLK = 46;
+
+__host__ __device__ constexpr int num_pairs(int nblk) { return 2 + 4 * nblk + nblk * (nblk - 1) / 2; }
+__host__ __device__ constexpr int max_points(int nblk) { return nblk <= 1 ? 4 * num_pairs(nblk) : 64; }
+__host__ __device__ constexpr int max_robot_points(int nblk) { return nblk == 0 ? 8 : (nblk == 1 ? 16 : 24); }
+
+// geometry endpoints of a collision pair
+enum GeomKind { G_TABLE = 0, G_FLOOR = 1, G_FINGER1 = 2, G_FINGER2 = 3, G_BLOCK = 4 };
+struct PairInfo { int ka, kb, ia, ib; };  // kinds and block indices (for G_BLOCK)
+
+template <int NBLK>
+__device__ __forceinline__ PairInfo pair_info(int k) {
+  PairInfo p; p.ia = p.ib = 0;
+  if (k < 2) { p.ka = G_FINGER1 + k; p.kb = G_TABLE; return p; }
+  k -= 2;
+  if (k < 4 * NBLK) {
+    int i = k >> 2, w = k & 3;
+    p.kb = G_BLOCK; p.ib = i;
+    p.ka = w == 0 ? G_TABLE : (w == 1 ? G_FLOOR : (w == 2 ? G_FINGER1 : G_FINGER2));
+    return p;
+  }
+  k -= 4 * NBLK;
+  int i = 0;
+  while (k >= NBLK - 1 - i) { k -= NBLK - 1 - i; i++; }
+  p.ka = G_BLOCK; p.kb = G_BLOCK; p.ia = i; p.ib = i + 1 + k;
+  return p;
+}
+
+__device__ __forceinline__ V3 geom_half(int kind) {
+  const float th[3] = PMG_TABLE_HALF, fh[3] = PMG_FLOOR_HALF, gh[3] = PMG_FINGER_HALF;
+  if (kind == G_TABLE) return v3(th[0], th[1], th[2]);
+  if (kind == G_FLOOR) return v3(fh[0], fh[1], fh[2]);
+  if (kind == G_BLOCK) return v3(BLOCK_HALF, BLOCK_HALF, BLOCK_HALF);
+  return v3(gh[0], gh[1], gh[2]);
+}
+__device__ __forceinline__ float geom_friction(int kind) {
+  if (kind == G_TABLE) return (float)PMG_TABLE_FRICTION;
+  if (kind == G_FLOOR) return (float)PMG_FLOOR_FRICTION;
+  if (kind == G_BLOCK) return (float)PMG_BLOCK_FRICTION;
+  return (float)PMG_FINGER_FRICTION;
+}
+
+template <int NBLK>
+struct Env {
+  static constexpr int NBA = NBLK > 0 ? NBLK : 1;
+  float q[ND], qd[ND], mt[ND], mi[ND], dtau[ND];
+  V3 bpos[NBA], bv[NBA], bw[NBA];
+  float bquat[NBA][4];
+  M3 bR[NBA];
+  float* man;      // this env's first manifold word
+  size_t stride;   // = batch
+  int overflow;
+  __device__ __forceinline__ float& mw(int pair, int w) { return man[(size_t)(pair * MAN_WORDS + w) * stride]; }
+};
+
+template <int NBLK>
+__device__ __forceinline__ void geom_pose(const Env<NBLK>& e, const Frames& f, int kind, int idx, V3& p, M3& R) {
+  const float tc[3] = PMG_TABLE_CENTER, fc[3] = PMG_FLOOR_CENTER;
+  if (kind == G_TABLE) { p = v3(tc[0], tc[1], tc[2]); R = m3_identity(); }
+  else if (kind == G_FLOOR) { p = v3(fc[0], fc[1], fc[2]); R = m3_identity(); }
+  else if (kind == G_FINGER1) { p = f.p[PMG_BODY_FINGER1]; R = f.R[PMG_BODY_FINGER1]; }
+  else if (kind == G_FINGER2) { p = f.p[PMG_BODY_FINGER2]; R = f.R[PMG_BODY_FINGER2]; }
+  else { p = e.bpos[idx]; R = e.bR[idx]; }
+}
+
+// ---- collision detection + persistent manifolds (btPersistentManifold semantics) -----------
+template <int NBLK>
+__device__ void manifold_add(Env<NBLK>& e, int k, float thr, V3 lA, V3 lB, V3 nB, float dist) {
+  int n = __float_as_int(e.mw(k, 0));
+  float shortest = thr * thr;
+  int nearest = -1;
+  for (int i = 0; i < n; i++) {
+    V3 c = v3(e.mw(k, 1 + 10 * i), e.mw(k, 2 + 10 * i), e.mw(k, 3 + 10 * i));
+    V3 d = c - lA;
+    float dd = dot(d, d);
+    if (dd < shortest) { shortest = dd; nearest = i; }
+  }
+  int slot = nearest;
+  if (slot < 0) {
+    if (n < 4) { slot = n; e.mw(k, 0) = __int_as_float(n + 1); }
+    else {
+      V3 c[4]; float dd[4];
+      for (int i = 0; i < 4; i++) { c[i] = v3(e.mw(k, 1 + 10 * i), e.mw(k, 2 + 10 * i), e.mw(k, 3 + 10 * i)); dd[i] = e.mw(k, 10 + 10 * i); }
+      int deepest = -1; float maxpen = dist;
+      for (int i = 0; i < 4; i++) if (dd[i] < maxpen) { deepest = i; maxpen = dd[i]; }
+      float res[4] = {0, 0, 0, 0};
+      V3 x;
+      if (deepest != 0) { x = cross(lA - c[1], c[3] - c[2]); res[0] = dot(x, x); }
+      if (deepest != 1) { x = cross(lA - c[0], c[3] - c[2]); res[1] = dot(x, x); }
+      if (deepest != 2) { x = cross(lA - c[0], c[3] - c[1]); res[2] = dot(x, x); }
+      if (deepest != 3) { x = cross(lA - c[0], c[2] - c[1]); res[3] = dot(x, x); }
+      slot = 0; float best = fabsf(res[0]);
+      for (int i = 1; i < 4; i++) if (fabsf(res[i]) > best) { best = fabsf(res[i]); slot = i; }
+    }
+  }
+  int o = 1 + 10 * slot;
+  e.mw(k, o) = lA.x; e.mw(k, o + 1) = lA.y; e.mw(k, o + 2) = lA.z;
+  e.mw(k, o + 3) = lB.x; e.mw(k, o + 4) = lB.y; e.mw(k, o + 5) = lB.z;
+  e.mw(k, o + 6) = nB.x; e.mw(k, o + 7) = nB.y; e.mw(k, o + 8) = nB.z;
+  e.mw(k, o + 9) = dist;
+}
+
+template <int NBLK>
+__device__ void collide(Env<NBLK>& e, const Frames& f) {
+#pragma unroll
+  for (int b = 0; b < NBLK; b++) e.bR[b] = quat_to_m3(e.bquat[b][0], e.bquat[b][1], e.bquat[b][2], e.bquat[b][3]);
+  constexpr int NP = num_pairs(NBLK);
+  for (int k = 0; k < NP; k++) {
+    PairInfo pi = pair_info<NBLK>(k);
+    V3 pa, pb; M3 Ra, Rb;
+    geom_pose(e, f, pi.ka, pi.ia, pa, Ra);
+    geom_pose(e, f, pi.kb, pi.ib, pb, Rb);
+    V3 ha = geom_half(pi.ka), hb = geom_half(pi.kb);
+    // broadphase: world AABBs grown by gContactBreakingThreshold
+    V3 d = pa - pb;
+    float ex = fabsf(Ra.r0.x) * ha.x + fabsf(Ra.r0.y) * ha.y + fabsf(Ra.r0.z) * ha.z + fabsf(Rb.r0.x) * hb.x + fabsf(Rb.r0.y) * hb.y + fabsf(Rb.r0.z) * hb.z + 2 * BROADPHASE_MARGIN;
+    float ey = fabsf(Ra.r1.x) * ha.x + fabsf(Ra.r1.y) * ha.y + fabsf(Ra.r1.z) * ha.z + fabsf(Rb.r1.x) * hb.x + fabsf(Rb.r1.y) * hb.y + fabsf(Rb.r1.z) * hb.z + 2 * BROADPHASE_MARGIN;
+    float ez = fabsf(Ra.r2.x) * ha.x + fabsf(Ra.r2.y) * ha.y + fabsf(Ra.r2.z) * ha.z + fabsf(Rb.r2.x) * hb.x + fabsf(Rb.r2.y) * hb.y + fabsf(Rb.r2.z) * hb.z + 2 * BROADPHASE_MARGIN;
+    if (fabsf(d.x) > ex || fabsf(d.y) > ey || fabsf(d.z) > ez) {
+      if (__float_as_int(e.mw(k, 0)) != 0) e.mw(k, 0) = __int_as_float(0);
+      continue;
+    }
+    float thr = BREAKING_THRESHOLD_FACTOR * fminf(norm(ha), norm(hb));
+    Contact c[4];
+    int nc = box_box(pa, Ra, ha, pb, Rb, hb, c);
+    for (int i = 0; i < nc; i++) {
+      V3 wa = c[i].pB + c[i].dist * c[i].nB;
+      manifold_add(e, k, thr, mulT(Ra, wa - pa), mulT(Rb, c[i].pB - pb), c[i].nB, c[i].dist);
+    }
+    // refreshContactPoints
+    int n = __float_as_int(e.mw(k, 0));
+    for (int i = n - 1; i >= 0; i--) {
+      int o = 1 + 10 * i;
+      V3 lA = v3(e.mw(k, o), e.mw(k, o + 1), e.mw(k, o + 2)), lB = v3(e.mw(k, o + 3), e.mw(k, o + 4), e.mw(k, o + 5));
+      V3 nB = v3(e.mw(k, o + 6), e.mw(k, o + 7), e.mw(k, o + 8));
+      V3 wa = mul(Ra, lA) + pa, wb = mul(Rb, lB) + pb;
+      float dist = dot(wa - wb, nB);
+      bool drop = dist > thr;
+      if (!drop) {
+        V3 pd = wb - (wa - dist * nB);
+        drop = dot(pd, pd) > thr * thr;
+      }
+      if (drop) {
+        int last = n - 1;
+        if (i != last) for (int w = 0; w < 10; w++) e.mw(k, o + w) = e.mw(k, 1 + 10 * last + w);
+        n--;
+      } else e.mw(k, o + 9) = dist;
+    }
+    if (n != __float_as_int(e.mw(k, 0))) e.mw(k, 0) = __int_as_float(n);
+  }
+}
+
+// ---- constraint rows + projected Gauss-Seidel ------------------------------------------------
+__host__ __device__ constexpr int nc_order(int i) {
+  constexpr int o[2 * ND] = PMG_NONCONTACT_ORDER;
+  return o[i];
+}
+
+struct NcRows {  // slot 2*oi + side; motors use side 0
+  float rhs[4 * ND], dinv[4 * ND], app[4 * ND], lo[4 * ND], hi[4 * ND];
+  bool active[4 * ND];
+};
+
+template <int D>
+__device__ __forceinline__ void nc_row(NcRows& nc, int slot, float sign, const float (*Minv)[ND], float* dqd, float& res) {
+  if (!nc.active[slot]) return;
+  float dl = nc.rhs[slot] - sign * dqd[D] * nc.dinv[slot];
+  float sum = nc.app[slot] + dl;
+  if (sum < nc.lo[slot]) { dl = nc.lo[slot] - nc.app[slot]; nc.app[slot] = nc.lo[slot]; }
+  else if (sum > nc.hi[slot]) { dl = nc.hi[slot] - nc.app[slot]; nc.app[slot] = nc.hi[slot]; }
+  else nc.app[slot] = sum;
+  float sdl = sign * dl;
+#pragma unroll
+  for (int r = 0; r < ND; r++) dqd[r] += Minv[r][D] * sdl;
+  float rr = dl * Minv[D][D];
+  res = fmaxf(res, rr * rr);
+}
+
+template <int OI, bool REV>
+__device__ __forceinline__ void nc_constraint(NcRows& nc, const float (*Minv)[ND], float* dqd, float& res) {
+  constexpr int id = nc_order(OI);
+  constexpr int d = id % ND;
+  if (id >= ND) nc_row<d>(nc, 2 * OI, 1.0f, Minv, dqd, res);
+  else if (!REV) { nc_row<d>(nc, 2 * OI, 1.0f, Minv, dqd, res); nc_row<d>(nc, 2 * OI + 1, -1.0f, Minv, dqd, res); }
+  else { nc_row<d>(nc, 2 * OI + 1, -1.0f, Minv, dqd, res); nc_row<d>(nc, 2 * OI, 1.0f, Minv, dqd, res); }
+}
+
+template <int OI>
+__device__ __forceinline__ void nc_setup(NcRows& nc, const float* q, const float* qd, const float* mt, const float* mi, const float (*Minv)[ND]) {
+  constexpr int id = nc_order(OI);
+  constexpr int d = id % ND;
+  const float dinv = 1.0f / Minv[d][d];
+  if (id >= ND) {  // btMultiBodyJointMotor in POSITION_CONTROL (kuka.py:282-301)
+    const int s = 2 * OI;
+    float target_vel = MOTOR_KP * (mt[d] - q[d]) * INV_DT + qd[d] + MOTOR_KD * (0.0f - qd[d]);
+    nc.active[s] = true; nc.active[s + 1] = false;
+    nc.dinv[s] = dinv; nc.rhs[s] = (target_vel - qd[d]) * dinv;
+    nc.lo[s] = -mi[d]; nc.hi[s] = mi[d]; nc.app[s] = 0.0f;
+  } else {         // btMultiBodyJointLimitConstraint: row 0 lower bound, row 1 upper bound
+#pragma unroll
+    for (int side = 0; side < 2; side++) {
+      const int s = 2 * OI + side;
+      float pen = side == 0 ? q[d] - c_dof_lower[d] : c_dof_upper[d] - q[d];
+      float sign = side ? -1.0f : 1.0f;
+      nc.active[s] = !(pen > 0.0f);
+      float pos_err = pen > SPLIT_IMPULSE_PEN_THRESHOLD ? -pen * CONTACT_ERP * INV_DT : 0.0f;
+      nc.dinv[s] = dinv; nc.rhs[s] = (pos_err - sign * qd[d]) * dinv;
+      nc.lo[s] = 0.0f; nc.hi[s] = LIMIT_MAX_IMPULSE; nc.app[s] = 0.0f;
+    }
+  }
+}
+
+template <int... I> struct Seq {};
+template <int N, int... I> struct MakeSeq : MakeSeq<N - 1, N - 1, I...> {};
+template <int... I> struct MakeSeq<0, I...> { using type = Seq<I...>; };
+
+template <int... I>
+__device__ __forceinline__ void nc_setup_all(Seq<I...>, NcRows& nc, const float* q, const float* qd, const float* mt, const float* mi, const float (*Minv)[ND]) {
+  int dummy[] = {(nc_setup<I>(nc, q, qd, mt, mi, Minv), 0)...};
+  (void)dummy;
+}
+template <int... I>
+__device__ __forceinline__ void nc_forward(Seq<I...>, NcRows& nc, const float (*Minv)[ND], float* dqd, float& res) {
+  int dummy[] = {(nc_constraint<I, false>(nc, Minv, dqd, res), 0)...};
+  (void)dummy;
+}
+template <int... I>
+__device__ __forceinline__ void nc_backward(Seq<I...>, NcRows& nc, const float (*Minv)[ND], float* dqd, float& res) {
+  int dummy[] = {(nc_constraint<2 * ND - 1 - I, true>(nc, Minv, dqd, res), 0)...};
+  (void)dummy;
+}
+
+template <int NBLK>
+struct ContactRows {
+  static constexpr int MP = max_points(NBLK), MR = max_robot_points(NBLK);
+  int n, nrob;
+  signed char rob[MP], blkA[MP], blkB[MP];  // robot-pool index / block indices, -1 = none
+  V3 dir[MP][3], rA[MP], rB[MP];            // normal + two tangents; lever arms about the block centres
+  float rhs[MP][3], dinv[MP][3], app[MP][3], mu[MP];
+  float Jr[MR][3][ND], MJr[MR][3][ND];
+};
+
+template <int NBLK>
+__device__ __forceinline__ float contact_row_velocity(const ContactRows<NBLK>& cr, int c, int k, const float* vq, const V3* vlin, const V3* vang) {
+  float v = 0.0f;
+  V3 d = cr.dir[c][k];
+  int ri = cr.rob[c];
+  if (ri >= 0) {
+#pragma unroll
+    for (int j = 0; j < ND; j++) v += cr.Jr[ri][k][j] * vq[j];
+  }
+  int a = cr.blkA[c], b = cr.blkB[c];
+  if (a >= 0) v += dot(d, vlin[a] + cross(vang[a], cr.rA[c]));
+  if (b >= 0) v -= dot(d, vlin[b] + cross(vang[b], cr.rB[c]));
+  return v;
+}
+
+template <int NBLK>
+__device__ __forceinline__ void contact_row_apply(const ContactRows<NBLK>& cr, int c, int k, float dl, float* dqd, V3* dlin, V3* dang) {
+  V3 d = cr.dir[c][k];
+  int ri = cr.rob[c];
+  if (ri >= 0) {
+#pragma unroll
+    for (int j = 0; j < ND; j++) dqd[j] += cr.MJr[ri][k][j] * dl;
+  }
+  int a = cr.blkA[c], b = cr.blkB[c];
+  if (a >= 0) { dlin[a] += (dl * BLOCK_INV_MASS) * d; dang[a] += (dl * BLOCK_INV_INERTIA) * cross(cr.rA[c], d); }
+  if (b >= 0) { dlin[b] -= (dl * BLOCK_INV_MASS) * d; dang[b] -= (dl * BLOCK_INV_INERTIA) * cross(cr.rB[c], d); }
+}
+
+template <int NBLK>
+__device__ void solve_constraints(Env<NBLK>& e, const Frames& f, const float (*Minv)[ND]) {
+  constexpr int NBA = Env<NBLK>::NBA;
+  NcRows nc;
+  nc_setup_all(typename MakeSeq<2 * ND>::type(), nc, e.q, e.qd, e.mt, e.mi, Minv);
+  // ---- contact rows: one normal + two tangents per cached manifold point ----------------------
+  ContactRows<NBLK> cr;
+  cr.n = 0; cr.nrob = 0;
+  constexpr int NP = num_pairs(NBLK);
+  for (int k = 0; k < NP; k++) {
+    int n = __float_as_int(e.mw(k, 0));
+    if (n == 0) continue;
+    PairInfo pi = pair_info<NBLK>(k);
+    V3 pa, pb; M3 Ra, Rb;
+    geom_pose(e, f, pi.ka, pi.ia, pa, Ra);
+    geom_pose(e, f, pi.kb, pi.ib, pb, Rb);
+    float mu = geom_friction(pi.ka) * geom_friction(pi.kb);
+    bool robotA = pi.ka == G_FINGER1 || pi.ka == G_FINGER2;
+    for (int i = 0; i < n; i++) {
+      if (cr.n >= ContactRows<NBLK>::MP || (robotA && cr.nrob >= ContactRows<NBLK>::MR)) { e.overflow++; continue; }
+      int c = cr.n++;
+      int o = 1 + 10 * i;
+      V3 lA = v3(e.mw(k, o), e.mw(k, o + 1), e.mw(k, o + 2)), lB = v3(e.mw(k, o + 3), e.mw(k, o + 4), e.mw(k, o + 5));
+      V3 nB = v3(e.mw(k, o + 6), e.mw(k, o + 7), e.mw(k, o + 8));
+      float dist = e.mw(k, o + 9);
+      V3 wa = mul(Ra, lA) + pa, wb = mul(Rb, lB) + pb;
+      V3 t1, t2;
+      plane_space(nB, t1, t2);
+      cr.dir[c][0] = nB; cr.dir[c][1] = t1; cr.dir[c][2] = t2;
+      cr.mu[c] = mu;
+      cr.blkA[c] = pi.ka == G_BLOCK ? pi.ia : -1;
+      cr.blkB[c] = pi.kb == G_BLOCK ? pi.ib : -1;
+      cr.rA[c] = wa - pa; cr.rB[c] = wb - pb;
+      int ri = -1;
+      if (robotA) {
+        ri = cr.nrob++;
+        const int fb = pi.ka == G_FINGER1 ? PMG_BODY_FINGER1 : PMG_BODY_FINGER2;
+#pragma unroll
+        for (int kk = 0; kk < 3; kk++) {
+          V3 d = cr.dir[c][kk];
+          float J[ND];
+#pragma unroll
+          for (int j = 0; j < 7; j++) J[j] = dot(f.a[j], cross(wa - f.p[j], d));
+          J[7] = fb == PMG_BODY_FINGER1 ? dot(f.a[PMG_BODY_FINGER1], d) : 0.0f;
+          J[8] = fb == PMG_BODY_FINGER2 ? dot(f.a[PMG_BODY_FINGER2], d) : 0.0f;
+#pragma unroll
+          for (int r = 0; r < ND; r++) {
+            float s = 0.0f;
+#pragma unroll
+            for (int j = 0; j < ND; j++) s += Minv[r][j] * J[j];
+            cr.Jr[ri][kk][r] = J[r]; cr.MJr[ri][kk][r] = s;
+          }
+        }
+      }
+      cr.rob[c] = (signed char)ri;
+#pragma unroll
+      for (int kk = 0; kk < 3; kk++) {
+        V3 d = cr.dir[c][kk];
+        float denom = 0.0f;
+        if (ri >= 0) {
+#pragma unroll
+          for (int j = 0; j < ND; j++) denom += cr.Jr[ri][kk][j] * cr.MJr[ri][kk][j];
+        }
+        if (cr.blkA[c] >= 0) { V3 x = cross(cr.rA[c], d); denom += BLOCK_INV_MASS + BLOCK_INV_INERTIA * dot(x, x); }
+        if (cr.blkB[c] >= 0) { V3 x = cross(cr.rB[c], d); denom += BLOCK_INV_MASS + BLOCK_INV_INERTIA * dot(x, x); }
+        float dinv = 1.0f / denom;
+        cr.dinv[c][kk] = dinv; cr.app[c][kk] = 0.0f;
+        float rel_vel = contact_row_velocity(cr, c, kk, e.qd, e.bv, e.bw);
+        if (kk == 0) {
+          float pen = dist + LINEAR_SLOP;
+          float pos_err = 0.0f, vel_err = -rel_vel;
+          if (pen > 0.0f) vel_err -= pen * INV_DT; else pos_err = -pen * CONTACT_ERP * INV_DT;
+          cr.rhs[c][0] = (pos_err + vel_err) * dinv;
+        } else cr.rhs[c][kk] = -rel_vel * dinv;
+      }
+    }
+  }
+  // ---- PGS: <= 5 iterations, early exit on the largest squared velocity change ---------------
+  float dqd[ND];
+  V3 dlin[NBA], dang[NBA];
+#pragma unroll
+  for (int j = 0; j < ND; j++) dqd[j] = 0.0f;
+#pragma unroll
+  for (int b = 0; b < NBA; b++) { dlin[b] = v3(0, 0, 0); dang[b] = v3(0, 0, 0); }
+  for (int it = 0; it < SOLVER_ITERS; it++) {
+    float res = 0.0f;
+    if (it & 1) nc_forward(typename MakeSeq<2 * ND>::type(), nc, Minv, dqd, res);
+    else nc_backward(typename MakeSeq<2 * ND>::type(), nc, Minv, dqd, res);
+    for (int c = 0; c < cr.n; c++) {
+      float dl = cr.rhs[c][0] - contact_row_velocity(cr, c, 0, dqd, dlin, dang) * cr.dinv[c][0];
+      float sum = cr.app[c][0] + dl;
+      if (sum < 0.0f) { dl = -cr.app[c][0]; cr.app[c][0] = 0.0f; }
+      else if (sum > 1e10f) { dl = 1e10f - cr.app[c][0]; cr.app[c][0] = 1e10f; }
+      else cr.app[c][0] = sum;
+      contact_row_apply(cr, c, 0, dl, dqd, dlin, dang);
+      float rr = dl / cr.dinv[c][0];
+      res = fmaxf(res, rr * rr);
+    }
+    for (int c = 0; c < cr.n; c++) {  // implicit friction cone: both tangent rows of a point together
+      float total = cr.app[c][0];
+      if (!(total > 0.0f)) continue;
+      float lim = cr.mu[c] * total;
+      float dA = cr.rhs[c][1] - contact_row_velocity(cr, c, 1, dqd, dlin, dang) * cr.dinv[c][1];
+      float dB = cr.rhs[c][2] - contact_row_velocity(cr, c, 2, dqd, dlin, dang) * cr.dinv[c][2];
+      float sA = cr.app[c][1] + dA, sB = cr.app[c][2] + dB;
+      if (sA * sA + sB * sB >= lim * lim) {
+        float ang = atan2f(sA, sB);
+        float sn, cs;
+        sincosf(ang, &sn, &cs);
+        float cA = fabsf(lim * sn), cB = fabsf(lim * cs);
+        if (sA < -cA) { dA = -cA - cr.app[c][1]; cr.app[c][1] = -cA; }
+        else if (sA > cA) { dA = cA - cr.app[c][1]; cr.app[c][1] = cA; }
+        else cr.app[c][1] = sA;
+        if (sB < -cB) { dB = -cB - cr.app[c][2]; cr.app[c][2] = -cB; }
+        else if (sB > cB) { dB = cB - cr.app[c][2]; cr.app[c][2] = cB; }
+        else cr.app[c][2] = sB;
+      } else { cr.app[c][1] = sA; cr.app[c][2] = sB; }
+      contact_row_apply(cr, c, 1, dA, dqd, dlin, dang);
+      contact_row_apply(cr, c, 2, dB, dqd, dlin, dang);
+      float r1 = dA / cr.dinv[c][1], r2 = dB / cr.dinv[c][2];
+      res = fmaxf(res, fmaxf(r1 * r1, r2 * r2));
+    }
+    if (res <= RESIDUAL_THRESHOLD) break;
+  }
+#pragma unroll
+  for (int j = 0; j < ND; j++) e.qd[j] = fminf(fmaxf(e.qd[j] + dqd[j], -MAX_COORD_VEL), MAX_COORD_VEL);
+#pragma unroll
+  for (int b = 0; b < NBLK; b++) { e.bv[b] += dlin[b]; e.bw[b] += dang[b]; }
+}
+
+// ---- one 2 ms substep (btMultiBodyDynamicsWorld::internalSingleStepSimulation) ---------------
+template <int NBLK>
+__device__ void substep(Env<NBLK>& e) {
+  Frames f;
+  forward_kinematics<NB>(e.q, f);
+  collide(e, f);
+  float Minv[ND][ND];
+  {
+    float bias[ND], M[ND][ND];
+    bias_forces(f, e.qd, bias);
+    mass_matrix(f, M);
+    invert_spd9(M, Minv);
+#pragma unroll
+    for (int i = 0; i < ND; i++) {
+      float s = 0.0f;
+#pragma unroll
+      for (int j = 0; j < ND; j++) s += Minv[i][j] * (e.dtau[j] - bias[j]);
+      e.qd[i] = fminf(fmaxf(e.qd[i] + s * DT, -MAX_COORD_VEL), MAX_COORD_VEL);
+    }
+  }
+#pragma unroll
+  for (int b = 0; b < NBLK; b++) {  // free cubes: gravity + Bullet's velocity damping; isotropic inertia => no gyro term
+    float kl = LINK_DAMPING + LINK_DAMPING * norm(e.bv[b]), ka = LINK_DAMPING + LINK_DAMPING * norm(e.bw[b]);
+    e.bv[b] += DT * (v3(0, 0, -GRAVITY) - kl * e.bv[b]);
+    e.bw[b] -= (DT * ka) * e.bw[b];
+  }
+  solve_constraints(e, f, Minv);
+#pragma unroll
+  for (int j = 0; j < ND; j++) e.q[j] += e.qd[j] * DT;
+#pragma unroll
+  for (int b = 0; b < NBLK; b++) {
+    e.bpos[b] += DT * e.bv[b];
+    float w = norm(e.bw[b]);
+    if (w * DT > 0.25f * PI_F) w = 0.25f * PI_F / DT;  // ANGULAR_MOTION_THRESHOLD
+    float s = w < 0.001f ? 0.5f * DT - DT * DT * DT * 0.020833333333f * w * w : sinf(0.5f * w * DT) / w;
+    float ax = e.bw[b].x * s, ay = e.bw[b].y * s, az = e.bw[b].z * s, aw = cosf(0.5f * w * DT);
+    float bx = e.bquat[b][0], by = e.bquat[b][1], bz = e.bquat[b][2], bw_ = e.bquat[b][3];
+    float nx = aw * bx + ax * bw_ + ay * bz - az * by;
+    float ny = aw * by + ay * bw_ + az * bx - ax * bz;
+    float nz = aw * bz + az * bw_ + ax * by - ay * bx;
+    float nw = aw * bw_ - ax * bx - ay * by - az * bz;
+    float inv = 1.0f / sqrtf(nx * nx + ny * ny + nz * nz + nw * nw);
+    e.bquat[b][0] = nx * inv; e.bquat[b][1] = ny * inv; e.bquat[b][2] = nz * inv; e.bquat[b][3] = nw * inv;
+  }
+}
+
+}  // namespace pmg

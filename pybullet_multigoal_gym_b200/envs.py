@@ -1,0 +1,289 @@
+"""Batched Kuka multigoal environments behind the reference's env API.
+
+Mirrors (paths relative to /root/reference/pybullet_multigoal_gym/):
+  envs/base_envs/base_env.py:120-138          seed / reset / step
+  envs/base_envs/kuka_single_step_base_env.py:193-244   observation dict, _compute_reward
+  envs/base_envs/kuka_multi_step_base_env.py:255-345    multi-block observation dict, reward
+  envs/task_envs/kuka_single_step_envs.py:4-46, kuka_multi_step_envs.py:6-32   task presets
+  gym 0.17.3 wrappers/time_limit.py           done = elapsed >= max_episode_steps
+
+Every array of the reference gains a leading [batch] axis (unless batch=None, which gives the
+reference's unbatched numpy shapes for a single environment).  All physics runs in the CUDA
+extension (libpmg.so); there is no CPU path.
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib, seeding, spaces
+
+TASK_IDS = {"reach": 0, "push": 1, "pick_and_place": 2, "block_stack": 3}
+
+
+class ActionError(AssertionError, ValueError):
+    """Raised where the reference hits `assert self.action_space.contains(a)` (kuka.py:168)."""
+
+
+def _ptr(t):
+    return C.c_void_p(t.data_ptr())
+
+
+class KukaBulletMGEnv:
+    """Batched goal-conditioned Kuka environment (one CUDA thread per environment)."""
+
+    metadata = {"render.modes": []}
+
+    def __init__(self, task, batch=None, device=0, binary_reward=True, distance_threshold=0.05,
+                 max_episode_steps=50, num_block=4, seed=0, check_actions=True):
+        if task not in TASK_IDS:
+            raise ValueError("invalid task name: %s, only support: %s" % (task, sorted(TASK_IDS)))
+        self._L = _lib.load()
+        if not torch.cuda.is_available():
+            raise RuntimeError("pybullet_multigoal_gym_b200 needs a CUDA device (no CPU fallback)")
+        self.task = task
+        self._squeeze = batch is None
+        self.batch = self.num_envs = 1 if batch is None else int(batch)
+        self.device = torch.device("cuda", int(device) if not isinstance(device, torch.device) else device.index or 0)
+        self.binary_reward = bool(binary_reward)
+        self.distance_threshold = float(distance_threshold)
+        self._max_episode_steps = int(max_episode_steps)
+        self.num_block = int(num_block) if task == "block_stack" else (0 if task == "reach" else 1)
+        self.grasping = task in ("pick_and_place", "block_stack")
+        self.has_obj = task != "reach"
+        self.check_actions = check_actions
+        cfg = _lib.PmgConfig(TASK_IDS[task], int(num_block), self.batch, int(self.binary_reward),
+                             self.distance_threshold, self._max_episode_steps, self.device.index)
+        h = C.c_void_p()
+        _lib.check(self._L.pmg_create(C.byref(cfg), C.byref(h)))
+        self._h = h
+        dims = (C.c_int32 * 6)()
+        _lib.check(self._L.pmg_dims(self._h, dims))
+        self.obs_dim, self.policy_dim, self.goal_dim, _, self.action_dim, self.row_width = list(dims)
+        self._slices = {
+            "observation": slice(0, self.obs_dim),
+            "policy_state": slice(self.obs_dim, self.obs_dim + self.policy_dim),
+            "achieved_goal": slice(self.obs_dim + self.policy_dim, self.obs_dim + self.policy_dim + self.goal_dim),
+            "desired_goal": slice(self.obs_dim + self.policy_dim + self.goal_dim, self.row_width),
+        }
+        B = self.batch
+        # pinned host staging for the host-buffer path (pmg_step_host)
+        self._h_action = torch.empty((B, self.action_dim), dtype=torch.float32).pin_memory()
+        self._h_obs = torch.empty((B, self.row_width), dtype=torch.float32).pin_memory()
+        self._h_reward = torch.empty((B,), dtype=torch.float32).pin_memory()
+        self._h_done = torch.empty((B,), dtype=torch.uint8).pin_memory()
+        self._h_success = torch.empty((B,), dtype=torch.uint8).pin_memory()
+        self.action_space = spaces.Box(-np.ones([self.action_dim]), np.ones([self.action_dim]))  # kuka.py:109-118
+        self.desired_goal = None
+        self.seed(seed)
+        obs = self.reset()  # the reference ctor resets once (base_env.py:84) and so consumes the RNG
+        shp = (lambda k: tuple(obs[k].shape))
+        self.observation_space = spaces.Dict(dict(  # base_env.py:86-92 (note: 'state', not 'observation')
+            state=spaces.Box(-np.inf, np.inf, shape=shp("observation"), dtype="float32"),
+            policy_state=spaces.Box(-np.inf, np.inf, shape=shp("policy_state"), dtype="float32"),
+            achieved_goal=spaces.Box(-np.inf, np.inf, shape=shp("achieved_goal"), dtype="float32"),
+            desired_goal=spaces.Box(-np.inf, np.inf, shape=shp("desired_goal"), dtype="float32"),
+        ))
+
+    # ---- gym.Env surface ------------------------------------------------------------------
+    def seed(self, seed=None):
+        """base_env.py:120-122.  Environment i of the batch is seeded with seed + i, so env 0
+        reproduces the reference's stream for `seed` and the others are decorrelated."""
+        if seed is None:
+            seed = int(np.random.SeedSequence().generate_state(1)[0])
+        keys = [seeding.seed_key(int(seed) + i) for i in range(self.batch)]
+        width = max(len(k) for k in keys)
+        arr = np.zeros((self.batch, width), dtype=np.uint32)
+        lens = np.zeros((self.batch,), dtype=np.int32)
+        for i, k in enumerate(keys):
+            arr[i, :len(k)] = k
+            lens[i] = len(k)
+        _lib.check(self._L.pmg_seed(self._h, arr.ctypes.data_as(C.c_void_p), lens.ctypes.data_as(C.c_void_p), width))
+        return [seed]
+
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def _split(self, packed):
+        return {k: packed[:, s] for k, s in self._slices.items()}
+
+    def _to_host_obs(self, packed_np):
+        obs = {k: packed_np[:, s].copy() for k, s in self._slices.items()}
+        if self._squeeze:
+            obs = {k: v[0].astype(np.float64) for k, v in obs.items()}
+        return obs
+
+    def reset(self, test=False, mask=None, spawn=None, device_output=None):
+        """base_env.py:124-128.  `mask` ([batch] bool) resets a subset; `spawn` ([batch, 2*nb+G])
+        overrides the sampled block xy / goal.  Returns torch CUDA tensors when the env is batched
+        (numpy for batch=None) unless device_output says otherwise."""
+        with torch.cuda.device(self.device):
+            out = torch.empty((self.batch, self.row_width), dtype=torch.float32, device=self.device)
+            m = None
+            if mask is not None:
+                m = np.ascontiguousarray(np.asarray(mask.cpu() if torch.is_tensor(mask) else mask), dtype=np.uint8)
+                if m.shape != (self.batch,):
+                    raise ValueError("mask must have shape (%d,)" % self.batch)
+            sp = None
+            if spawn is not None:
+                sp = np.ascontiguousarray(np.asarray(spawn.cpu() if torch.is_tensor(spawn) else spawn), dtype=np.float32)
+                if sp.shape != (self.batch, self._L.pmg_spawn_width(self._h)):
+                    raise ValueError("spawn must have shape (%d, %d)" % (self.batch, self._L.pmg_spawn_width(self._h)))
+            _lib.check(self._L.pmg_reset(self._h, m.ctypes.data_as(C.c_void_p) if m is not None else None,
+                                         sp.ctypes.data_as(C.c_void_p) if sp is not None else None, _ptr(out), self._stream()))
+            obs = self._split(out)
+            self.desired_goal = obs["desired_goal"]
+            if device_output is None:
+                device_output = not self._squeeze
+            if device_output:
+                return obs
+            host = self._to_host_obs(out.cpu().numpy())
+            if self._squeeze:
+                self.desired_goal = host["desired_goal"]
+            return host
+
+    def _check_action(self, a_np):
+        if a_np.shape != (self.batch, self.action_dim) or not (np.all(a_np >= -1.0) and np.all(a_np <= 1.0)):
+            raise ActionError("action outside the action space Box(-1, 1, (%d,))" % self.action_dim)
+
+    def step(self, action):
+        """base_env.py:130-138 + TimeLimit.  CUDA tensor in -> CUDA tensors out (asynchronous on the
+        current stream); numpy / CPU tensor in -> numpy out through the host-buffer C-ABI call."""
+        if torch.is_tensor(action) and action.is_cuda:
+            return self._step_device(action)
+        a = np.asarray(action.numpy() if torch.is_tensor(action) else action, dtype=np.float32)
+        if self._squeeze:
+            if a.shape != (self.action_dim,):
+                raise ActionError("action must have shape (%d,)" % self.action_dim)
+            a = a[None]
+        if a.ndim == 2 and a.shape[1] == 4 and self.action_dim == 3:
+            a = a[:, :3]  # BASELINE config "4-dim action" on a non-grasping task: the grip column is ignored
+        if self.check_actions or a.shape != (self.batch, self.action_dim):
+            self._check_action(a)
+        self._h_action.numpy()[...] = a
+        with torch.cuda.device(self.device):
+            _lib.check(self._L.pmg_step_host(self._h, _ptr(self._h_action), _ptr(self._h_obs), _ptr(self._h_reward),
+                                             _ptr(self._h_done), _ptr(self._h_success), self._stream()))
+        obs = self._to_host_obs(self._h_obs.numpy())
+        reward = self._h_reward.numpy().copy()
+        done = self._h_done.numpy().astype(bool)
+        ok = self._h_success.numpy().astype(bool)
+        if not self.binary_reward:
+            reward = reward.astype(np.float64)
+        if self._squeeze:
+            self.desired_goal = obs["desired_goal"]
+            info = {"goal_achieved": bool(ok[0]), "is_success": bool(ok[0]), "TimeLimit.truncated": bool(done[0])}
+            return obs, reward[0], bool(done[0]), info
+        info = {"goal_achieved": ok, "is_success": ok, "TimeLimit.truncated": done.copy()}
+        return obs, reward, done, info
+
+    def _step_device(self, action):
+        if action.dim() == 2 and action.shape[1] == 4 and self.action_dim == 3:
+            action = action[:, :3]
+        if tuple(action.shape) != (self.batch, self.action_dim):
+            raise ActionError("action must have shape (%d, %d)" % (self.batch, self.action_dim))
+        action = action.to(dtype=torch.float32).contiguous()
+        if self.check_actions and bool((action.abs() > 1.0).any()):
+            raise ActionError("action outside the action space Box(-1, 1, (%d,))" % self.action_dim)
+        with torch.cuda.device(self.device):
+            out = torch.empty((self.batch, self.row_width), dtype=torch.float32, device=self.device)
+            reward = torch.empty((self.batch,), dtype=torch.float32, device=self.device)
+            flags = torch.empty((2, self.batch), dtype=torch.uint8, device=self.device)
+            _lib.check(self._L.pmg_step(self._h, _ptr(action), _ptr(out), _ptr(reward), _ptr(flags[0]), _ptr(flags[1]), self._stream()))
+        obs = self._split(out)
+        self.desired_goal = obs["desired_goal"]
+        done, ok = flags[0].bool(), flags[1].bool()
+        return obs, reward, done, {"goal_achieved": ok, "is_success": ok, "TimeLimit.truncated": done}
+
+    def step_packed(self, action, out, reward, done, success):
+        """Zero-allocation device path: caller-owned CUDA buffers (used by bench.py and the sharded env)."""
+        _lib.check(self._L.pmg_step(self._h, _ptr(action), _ptr(out), _ptr(reward), _ptr(done), _ptr(success), self._stream()))
+
+    def _compute_reward(self, achieved_goal, desired_goal):
+        """kuka_single_step_base_env.py:237-244: (reward, goal_achieved) with any leading axes."""
+        if tuple(achieved_goal.shape) != tuple(desired_goal.shape):
+            raise AssertionError("achieved_goal.shape != desired_goal.shape")
+        as_numpy = not torch.is_tensor(achieved_goal)
+        ag = torch.as_tensor(np.asarray(achieved_goal, dtype=np.float32) if as_numpy else achieved_goal).to(self.device, torch.float32).contiguous()
+        dg = torch.as_tensor(np.asarray(desired_goal, dtype=np.float32) if as_numpy else desired_goal).to(self.device, torch.float32).contiguous()
+        g = ag.shape[-1]
+        lead = tuple(ag.shape[:-1])
+        n = ag.numel() // g if g else 0
+        with torch.cuda.device(self.device):
+            r = torch.empty((n,), dtype=torch.float32, device=self.device)
+            ok = torch.empty((n,), dtype=torch.uint8, device=self.device)
+            _lib.check(self._L.pmg_compute_reward(_ptr(ag), _ptr(dg), n, g, self.distance_threshold, int(self.binary_reward),
+                                                  _ptr(r), _ptr(ok), self._stream()))
+        r, ok = r.reshape(lead), ok.bool().reshape(lead)
+        if as_numpy:
+            r, ok = r.cpu().numpy(), ok.cpu().numpy()
+            if not self.binary_reward:
+                r = r.astype(np.float64)
+            if lead == ():
+                return r[()], bool(ok)
+        return r, ok
+
+    def compute_reward(self, achieved_goal, desired_goal, info=None):
+        """gym GoalEnv-style alias (not in the reference; BASELINE.json names it)."""
+        return self._compute_reward(achieved_goal, desired_goal)[0]
+
+    def render(self, mode="human", camera_id=0):
+        raise NotImplementedError("rendering / image observations are outside the accelerated step path")
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h.value:
+            self._L.pmg_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- extras (no reference counterpart) ----------------------------------------------------
+    def get_state(self):
+        w = self._L.pmg_state_width(self._h)
+        out = np.zeros((self.batch, w), dtype=np.float32)
+        _lib.check(self._L.pmg_get_state(self._h, out.ctypes.data_as(C.c_void_p)))
+        return out
+
+    def set_state(self, state):
+        w = self._L.pmg_state_width(self._h)
+        s = np.ascontiguousarray(state, dtype=np.float32)
+        if s.shape != (self.batch, w):
+            raise ValueError("state must have shape (%d, %d)" % (self.batch, w))
+        _lib.check(self._L.pmg_set_state(self._h, s.ctypes.data_as(C.c_void_p)))
+
+    def last_spawn(self):
+        out = np.zeros((self.batch, self._L.pmg_spawn_width(self._h)), dtype=np.float32)
+        _lib.check(self._L.pmg_last_spawn(self._h, out.ctypes.data_as(C.c_void_p)))
+        return out
+
+    @property
+    def launch_count(self):
+        return int(self._L.pmg_launch_count(self._h))
+
+    @property
+    def overflow_count(self):
+        return int(self._L.pmg_overflow_count(self._h))
+
+
+class KukaReachEnv(KukaBulletMGEnv):  # kuka_single_step_envs.py:35-46
+    def __init__(self, **kw):
+        super().__init__("reach", **kw)
+
+
+class KukaPushEnv(KukaBulletMGEnv):  # kuka_single_step_envs.py:20-32
+    def __init__(self, **kw):
+        super().__init__("push", **kw)
+
+
+class KukaPickAndPlaceEnv(KukaBulletMGEnv):  # kuka_single_step_envs.py:4-17
+    def __init__(self, **kw):
+        super().__init__("pick_and_place", **kw)
+
+
+class KukaBlockStackEnv(KukaBulletMGEnv):  # kuka_multi_step_envs.py:6-32
+    def __init__(self, **kw):
+        super().__init__("block_stack", **kw)
