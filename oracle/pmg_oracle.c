@@ -1111,6 +1111,8 @@ void pmgo_step_simulation(PmgoEnv* e) {
 /* ------------------------------------------------------------------------------------------ */
 /* environment plumbing                                                                       */
 /* ------------------------------------------------------------------------------------------ */
+static void robot_reset(PmgoEnv* e);
+
 PmgoEnv* pmgo_create(int task, int num_block, int binary_reward, double thr, int max_steps) {
   PmgoEnv* e = (PmgoEnv*)calloc(1, sizeof *e);
   e->task = task; e->binary = binary_reward; e->thr = thr; e->max_steps = max_steps;
@@ -1136,6 +1138,9 @@ PmgoEnv* pmgo_create(int task, int num_block, int binary_reward, double thr, int
   build_pairs(e);
   uint32_t key0 = 0;
   mt_init_by_array(&e->rng, &key0, 1);
+  /* BaseBulletMGEnv.__init__ resets the robot once on its own (base_env.py:41) before its first
+   * self.reset() (base_env.py:84): the rest pose gets one extra IK refinement, no RNG draw. */
+  robot_reset(e);
   return e;
 }
 void pmgo_destroy(PmgoEnv* e) { free(e); }
@@ -1385,6 +1390,13 @@ void pmgo_set_state(PmgoEnv* e, const double* o) {
       copy3(e->last_targets[k], e->goal + 3 * b);
     }
   memset(e->man, 0, sizeof e->man);
+}
+
+void pmgo_poke_state(PmgoEnv* e, const double* o) { /* like set_state, but the contact caches survive */
+  Manifold keep[MAX_PAIRS];
+  memcpy(keep, e->man, sizeof keep);
+  pmgo_set_state(e, o);
+  memcpy(e->man, keep, sizeof keep);
 }
 
 void pmgo_mass_matrix_inverse(PmgoEnv* e, double* out) {

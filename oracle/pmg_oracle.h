@@ -73,6 +73,7 @@ void pmgo_compute_reward(const double* ag, const double* dg, int64_t n, int g, d
 int pmgo_state_size(const PmgoEnv* e);
 void pmgo_get_state(const PmgoEnv* e, double* out);
 void pmgo_set_state(PmgoEnv* e, const double* in); /* also clears the contact caches */
+void pmgo_poke_state(PmgoEnv* e, const double* in); /* same, contact caches kept (pybullet_shim) */
 
 /* ---- pieces exposed for unit tests and for oracle/pybullet_shim ------------------------ */
 void pmgo_fk_tip(const double q[9], double pos[3], double quat_xyzw[4]);

@@ -49,6 +49,7 @@ def lib():
         L.pmgo_state_size.restype = C.c_int
         L.pmgo_get_state.argtypes = [C.c_void_p, dp]
         L.pmgo_set_state.argtypes = [C.c_void_p, dp]
+        L.pmgo_poke_state.argtypes = [C.c_void_p, dp]
         L.pmgo_fk_tip.argtypes = [dp, dp, dp]
         L.pmgo_ik.argtypes = [dp, dp, dp, C.c_int, C.c_double, dp]
         L.pmgo_substeps.argtypes = [C.c_void_p, C.c_int]
@@ -150,6 +151,11 @@ class OracleEnv:
         s = np.ascontiguousarray(s, dtype=np.float64)
         assert s.shape == (self.L.pmgo_state_size(self.h),)
         self.L.pmgo_set_state(self.h, _dp(s))
+
+    def poke_state(self, s):
+        s = np.ascontiguousarray(s, dtype=np.float64)
+        assert s.shape == (self.L.pmgo_state_size(self.h),)
+        self.L.pmgo_poke_state(self.h, _dp(s))
 
     def substeps(self, n):
         self.L.pmgo_substeps(self.h, n)

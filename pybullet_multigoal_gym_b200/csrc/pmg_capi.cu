@@ -8,6 +8,7 @@
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <new>
@@ -26,7 +27,16 @@ struct StepIO {
   float* state; float* manifold; int batch; int state_words;
   const float* action; float* obs; float* reward; uint8_t* done; uint8_t* success;
   float thr; int binary; int max_steps; int* overflow;
+  int epw;  // environments per warp: lanes [0, epw) of every warp own one environment each
 };
+
+// env index owned by this thread, or -1 for an idle lane / past the end of the batch
+__device__ __forceinline__ int env_of_thread(const StepIO& io) {
+  const int lane = threadIdx.x & 31;
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int i = warp * io.epw + lane;
+  return (lane < io.epw && i < io.batch) ? i : -1;
+}
 
 template <int TASK, int NBLK> struct Dims {
   static constexpr int O = TASK == 0 ? 3 : (TASK == 3 ? 8 + 16 * NBLK : 20);
@@ -83,19 +93,19 @@ __device__ void store_env(const Env<NBLK>& e, const StepIO& io, int i) {
 
 // Stage the warp's rows in shared memory so that the global stores are contiguous 128-byte lines
 // (rows of consecutive envs are adjacent in the packed [batch, W] output).  Every lane of the warp
-// must call this; lanes past the end of the batch pass live = false.
+// must call this; lanes that own no environment pass live = false.
 template <int W>
-__device__ __forceinline__ void stage_row(const float* row, const StepIO& io, int i, bool live) {
+__device__ __forceinline__ void stage_row(const float* row, const StepIO& io, bool live) {
   extern __shared__ float stage[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  float* ws = stage + warp * 32 * W;
+  float* ws = stage + warp * io.epw * W;
   if (live) {
 #pragma unroll
     for (int k = 0; k < W; k++) ws[lane * W + k] = row[k];
   }
   __syncwarp();
-  const int env0 = i - lane;
-  const int nvalid = min(32, io.batch - env0) * W;
+  const int env0 = ((blockIdx.x * blockDim.x + threadIdx.x) >> 5) * io.epw;
+  const int nvalid = max(0, min(io.epw, io.batch - env0)) * W;
   float* out = io.obs + (size_t)env0 * W;
   for (int k = lane; k < nvalid; k += 32) out[k] = ws[k];
   __syncwarp();
@@ -155,15 +165,15 @@ __device__ float write_obs(const Env<NBLK>& e, const StepIO& io, int i) {
   float d2 = 0.0f;
 #pragma unroll
   for (int k = 0; k < D::G; k++) { float d = ag[k] - dg[k]; d2 += d * d; }
-  stage_row<D::W>(row, io, i, true);
+  stage_row<D::W>(row, io, true);
   return sqrtf(d2);
 }
 
 template <int TASK, int NBLK>
-__global__ void __launch_bounds__(128) step_kernel(StepIO io) {
+__global__ void __launch_bounds__(32) step_kernel(StepIO io) {
   using D = Dims<TASK, NBLK>;
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= io.batch) { stage_row<D::W>(nullptr, io, i, false); return; }  // tail lanes only help the staged store
+  const int i = env_of_thread(io);
+  if (i < 0) { stage_row<D::W>(nullptr, io, false); return; }  // idle lanes only help the staged store
   const size_t B = io.batch;
   Env<NBLK> e;
   load_env<TASK, NBLK>(e, io, i);
@@ -211,11 +221,11 @@ __global__ void __launch_bounds__(128) step_kernel(StepIO io) {
 struct ResetIO { StepIO io; const uint8_t* mask; const float* spawn; float tip_init[3]; };
 
 template <int TASK, int NBLK>
-__global__ void __launch_bounds__(128) reset_kernel(ResetIO r) {
+__global__ void __launch_bounds__(32) reset_kernel(ResetIO r) {
   using D = Dims<TASK, NBLK>;
   const StepIO& io = r.io;
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= io.batch) { stage_row<D::W>(nullptr, io, i, false); return; }
+  const int i = env_of_thread(io);
+  if (i < 0) { stage_row<D::W>(nullptr, io, false); return; }
   const size_t B = io.batch;
   Env<NBLK> e;
   load_env<TASK, NBLK>(e, io, i);
@@ -266,13 +276,20 @@ __global__ void reward_kernel(const float* ag, const float* dg, int64_t n, int g
   ok[i] = na ? 0 : 1;
 }
 
-__global__ void init_state_kernel(float* state, int batch, int nblk, int state_words) {
+// Construction-time state: BaseBulletMGEnv.__init__ resets the robot once on its own (base_env.py:41)
+// before its first self.reset(), i.e. the rest pose (kuka.py:27) gets one IK refinement here.
+__global__ void init_state_kernel(float* state, int batch, int nblk, float tx, float ty, float tz) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= batch) return;
   const size_t B = batch;
-  for (int k = 0; k < 7; k++) { state[(ST_REST + k) * B + i] = c_rest_pose0[k]; state[(ST_Q + k) * B + i] = c_rest_pose0[k]; }
+  float q[ND];
+  for (int k = 0; k < 7; k++) q[k] = c_rest_pose0[k];
+  q[7] = q[8] = 0.0f;
+  const float tq[4] = {0.f, -1.f, 0.f, 0.f};
+  inverse_kinematics(q, v3(tx, ty, tz), tq);
+  for (int k = 0; k < 7; k++) { state[(ST_REST + k) * B + i] = q[k]; state[(ST_Q + k) * B + i] = q[k]; }
+  for (int k = 7; k < ND; k++) state[(ST_Q + k) * B + i] = GRIPPER_ABS_LIMIT;
   for (int b = 0; b < nblk; b++) state[(ST_BLK + 13 * b + 6) * B + i] = 1.0f;  // identity quaternion
-  (void)state_words;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -344,7 +361,7 @@ struct pmg_handle {
   double tip_init[3], obj_lo[3], obj_hi[3], tgt_lo[3], tgt_hi[3];
   bool was_reset = false;
   int64_t launches = 0;
-  int block = 32;
+  int epw = 32;  // environments per warp (launch geometry, see pmg_create)
 };
 
 namespace {
@@ -409,20 +426,22 @@ StepIO make_io(pmg_handle* h, const float* action, float* obs, float* reward, ui
   io.action = action; io.obs = obs; io.reward = reward; io.done = done; io.success = success;
   io.thr = h->cfg.distance_threshold; io.binary = h->cfg.binary_reward; io.max_steps = h->cfg.max_episode_steps;
   io.overflow = h->d_overflow;
+  io.epw = h->epw;
   return io;
 }
 
+// one warp per block: the block scheduler then spreads the (few) warps evenly over the 148 SMs
 template <int TASK, int NBLK>
 void launch_step(pmg_handle* h, const StepIO& io, cudaStream_t st) {
-  int blocks = (h->cfg.batch + h->block - 1) / h->block;
-  size_t smem = (size_t)(h->block / 32) * 32 * Dims<TASK, NBLK>::W * sizeof(float);
-  step_kernel<TASK, NBLK><<<blocks, h->block, smem, st>>>(io);
+  int warps = (h->cfg.batch + h->epw - 1) / h->epw;
+  size_t smem = (size_t)h->epw * Dims<TASK, NBLK>::W * sizeof(float);
+  step_kernel<TASK, NBLK><<<warps, 32, smem, st>>>(io);
 }
 template <int TASK, int NBLK>
 void launch_reset(pmg_handle* h, const ResetIO& r, cudaStream_t st) {
-  int blocks = (h->cfg.batch + h->block - 1) / h->block;
-  size_t smem = (size_t)(h->block / 32) * 32 * Dims<TASK, NBLK>::W * sizeof(float);
-  reset_kernel<TASK, NBLK><<<blocks, h->block, smem, st>>>(r);
+  int warps = (h->cfg.batch + h->epw - 1) / h->epw;
+  size_t smem = (size_t)h->epw * Dims<TASK, NBLK>::W * sizeof(float);
+  reset_kernel<TASK, NBLK><<<warps, 32, smem, st>>>(r);
 }
 
 #define PMG_DISPATCH(FN, ...)                                                        \
@@ -482,6 +501,19 @@ int pmg_create(const pmg_config* cfg, pmg_handle** out) {
   h->obj_lo[0] += 0.03; h->obj_hi[0] -= 0.03;
   h->tgt_lo[0] += 0.03; h->tgt_lo[2] = 0.175; h->tgt_hi[0] -= 0.03;
   const size_t B = cfg->batch;
+  {
+    // Launch geometry: lanes [0, epw) of every warp own one environment.  Spreading a batch over
+    // more warps (epw < 32) was measured to be slower at every shipped size (it multiplies the L1
+    // footprint of the per-thread scratch), so the default is a full warp; PMG_ENVS_PER_WARP
+    // overrides it for experiments.
+    cudaDeviceProp prop;
+    CUDA_TRY(cudaGetDeviceProperties(&prop, cfg->device));
+    const long target_warps = 1;  // measured: 32 envs/warp is fastest at every shipped batch (profiles/)
+    int epw = 32;
+    while (epw > 1 && (long)(B + epw - 1) / epw < target_warps) epw >>= 1;
+    if (const char* ev = getenv("PMG_ENVS_PER_WARP")) { int v = atoi(ev); if (v >= 1 && v <= 32) epw = v; }
+    h->epw = epw;
+  }
   h->rng.resize(B);
   for (size_t i = 0; i < B; i++) h->rng[i].init_genrand(5489u + (uint32_t)i);
 #define ALLOC(ptr, bytes) do { cudaError_t e_ = cudaMalloc((void**)&(ptr), (bytes)); if (e_ != cudaSuccess) { pmg_destroy(h); return fail(PMG_ERR_CUDA, "cudaMalloc: %s", cudaGetErrorString(e_)); } } while (0)
@@ -500,7 +532,7 @@ int pmg_create(const pmg_config* cfg, pmg_handle** out) {
   cudaMemset(h->d_state, 0, sizeof(float) * h->state_words * B);
   cudaMemset(h->d_man, 0, sizeof(float) * h->man_words * B);
   cudaMemset(h->d_overflow, 0, sizeof(int));
-  init_state_kernel<<<(int)((B + 127) / 128), 128>>>(h->d_state, (int)B, h->nblk, h->state_words);
+  init_state_kernel<<<(int)((B + 31) / 32), 32>>>(h->d_state, (int)B, h->nblk, (float)h->tip_init[0], (float)h->tip_init[1], (float)h->tip_init[2]);
   h->launches++;
   CUDA_TRY(cudaDeviceSynchronize());
   *out = h;

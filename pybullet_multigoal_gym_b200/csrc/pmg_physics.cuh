@@ -150,8 +150,8 @@ __device__ __forceinline__ M3 load_jrot(int b) {
 // Link frames of bodies [0, NBODIES).  Arm joints rotate about their local z, the fingers slide
 // along -/+ y of the gripper base (iiwa14_parallel_jaw.urdf:94-288,418-456).
 template <int NBODIES>
-__device__ __forceinline__ void forward_kinematics(const float* q, Frames& f) {
-#pragma unroll
+__device__ __noinline__ void forward_kinematics(const float* q, Frames& f) {
+#pragma unroll 1
   for (int b = 0; b < NBODIES; b++) {
     constexpr int dummy = 0; (void)dummy;
     const int par = body_parent(b);
@@ -301,10 +301,10 @@ __device__ __forceinline__ BodyInertia body_inertia(const Frames& f, int b) {
 
 // Generalised bias force C(q,qd) + g(q) + Bullet's per-link velocity damping, by the classical
 // recursive Newton-Euler sweep with qdd = 0 (lever arms stay link-local => fp32 friendly).
-__device__ void bias_forces(const Frames& f, const float* qd, float* bias) {
+__device__ __noinline__ void bias_forces(const Frames& f, const float* qd, float* bias) {
   V3 w[NB], al[NB], acc[NB], vel[NB];  // angular vel / accel, origin accel / vel
   V3 F[NB], N[NB];                      // net force at the COM, net moment about the link origin
-#pragma unroll
+#pragma unroll 1
   for (int b = 0; b < NB; b++) {
     const int par = body_parent(b);
     V3 wp = par < 0 ? v3(0, 0, 0) : w[par], alp = par < 0 ? v3(0, 0, 0) : al[par];
@@ -336,7 +336,7 @@ __device__ void bias_forces(const Frames& f, const float* qd, float* bias) {
     F[b] = Fc;
     N[b] = Nc + cross(bi.rc, Fc);
   }
-#pragma unroll
+#pragma unroll 1
   for (int b = NB - 1; b >= 0; b--) {
     const int par = body_parent(b);
     if (body_jtype(b) == 0) bias[body_dof(b)] = dot(f.a[b], N[b]);
@@ -349,9 +349,9 @@ __device__ void bias_forces(const Frames& f, const float* qd, float* bias) {
 }
 
 // Joint-space mass matrix by the composite-rigid-body algorithm (lower triangle, M[i][j], j<=i).
-__device__ void mass_matrix(const Frames& f, float M[ND][ND]) {
+__device__ __noinline__ void mass_matrix(const Frames& f, float M[ND][ND]) {
   float mc[NB]; V3 hc[NB]; M3 Ic[NB];  // composite mass, first moment, inertia about the link origin
-#pragma unroll
+#pragma unroll 1
   for (int b = 0; b < NB; b++) {
     BodyInertia bi = body_inertia(f, b);
     float m = c_mass[b];
@@ -361,7 +361,7 @@ __device__ void mass_matrix(const Frames& f, float M[ND][ND]) {
     Ic[b].r1 = bi.Iw.r1 + m * (v3(0, cc, 0) - bi.rc.y * bi.rc);
     Ic[b].r2 = bi.Iw.r2 + m * (v3(0, 0, cc) - bi.rc.z * bi.rc);
   }
-#pragma unroll
+#pragma unroll 1
   for (int b = NB - 1; b >= 1; b--) {
     const int par = body_parent(b);
     V3 r = f.p[b] - f.p[par];
@@ -379,14 +379,14 @@ __device__ void mass_matrix(const Frames& f, float M[ND][ND]) {
 #pragma unroll
     for (int j = 0; j < ND; j++) M[i][j] = 0.0f;
   }
-#pragma unroll
+#pragma unroll 1
   for (int i = 0; i < ND; i++) {
     const int b = dof_body(i);
     V3 n, l;  // moment about p[b] and force produced by unit acceleration of joint i
     if (body_jtype(b) == 0) { n = mul(Ic[b], f.a[b]); l = cross(f.a[b], hc[b]); M[i][i] = dot(f.a[b], n); }
     else { l = mc[b] * f.a[b]; n = cross(hc[b], f.a[b]); M[i][i] = mc[b]; }
     // walk up the arm: every proper ancestor with a dof is a revolute arm joint
-#pragma unroll
+#pragma unroll 1
     for (int j = (i <= 6 ? i - 1 : 6); j >= 0; j--) {
       V3 nj = n + cross(f.p[b] - f.p[j], l);
       M[i][j] = dot(f.a[j], nj);
@@ -395,7 +395,7 @@ __device__ void mass_matrix(const Frames& f, float M[ND][ND]) {
 }
 
 // In-place Cholesky of the lower triangle, then Minv = L^-T L^-1 (full symmetric matrix out).
-__device__ void invert_spd9(float M[ND][ND], float Minv[ND][ND]) {
+__device__ __noinline__ void invert_spd9(float M[ND][ND], float Minv[ND][ND]) {
 #pragma unroll
   for (int j = 0; j < ND; j++) {
     float d = M[j][j];

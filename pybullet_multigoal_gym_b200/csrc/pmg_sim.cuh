@@ -166,83 +166,75 @@ __device__ void collide(Env<NBLK>& e, const Frames& f) {
 }
 
 // ---- constraint rows + projected Gauss-Seidel ------------------------------------------------
-__host__ __device__ constexpr int nc_order(int i) {
-  constexpr int o[2 * ND] = PMG_NONCONTACT_ORDER;
-  return o[i];
-}
-
-struct NcRows {  // slot 2*oi + side; motors use side 0
-  float rhs[4 * ND], dinv[4 * ND], app[4 * ND], lo[4 * ND], hi[4 * ND];
-  bool active[4 * ND];
+// The 18 non-contact constraints (9 joint motors, 9 joint-limit constraints of two rows each) are
+// visited in Bullet's sorted order c_nc_order; rows live in slots 2*oi + side (motors: side 0).
+// The loops are deliberately rolled: the step kernel is instruction-fetch bound, not FLOP bound.
+struct NcRows {
+  float rhs[4 * ND], lo[4 * ND], hi[4 * ND], app[4 * ND];
+  float dinv[ND];        // 1 / Minv[d][d]
+  unsigned active;       // bit per slot
 };
 
-template <int D>
-__device__ __forceinline__ void nc_row(NcRows& nc, int slot, float sign, const float (*Minv)[ND], float* dqd, float& res) {
-  if (!nc.active[slot]) return;
-  float dl = nc.rhs[slot] - sign * dqd[D] * nc.dinv[slot];
-  float sum = nc.app[slot] + dl;
-  if (sum < nc.lo[slot]) { dl = nc.lo[slot] - nc.app[slot]; nc.app[slot] = nc.lo[slot]; }
-  else if (sum > nc.hi[slot]) { dl = nc.hi[slot] - nc.app[slot]; nc.app[slot] = nc.hi[slot]; }
-  else nc.app[slot] = sum;
-  float sdl = sign * dl;
+__device__ __forceinline__ float pick9(const float* v, int d) {  // v stays in registers
+  float r = v[0];
 #pragma unroll
-  for (int r = 0; r < ND; r++) dqd[r] += Minv[r][D] * sdl;
-  float rr = dl * Minv[D][D];
-  res = fmaxf(res, rr * rr);
+  for (int k = 1; k < ND; k++) r = d == k ? v[k] : r;
+  return r;
 }
 
-template <int OI, bool REV>
-__device__ __forceinline__ void nc_constraint(NcRows& nc, const float (*Minv)[ND], float* dqd, float& res) {
-  constexpr int id = nc_order(OI);
-  constexpr int d = id % ND;
-  if (id >= ND) nc_row<d>(nc, 2 * OI, 1.0f, Minv, dqd, res);
-  else if (!REV) { nc_row<d>(nc, 2 * OI, 1.0f, Minv, dqd, res); nc_row<d>(nc, 2 * OI + 1, -1.0f, Minv, dqd, res); }
-  else { nc_row<d>(nc, 2 * OI + 1, -1.0f, Minv, dqd, res); nc_row<d>(nc, 2 * OI, 1.0f, Minv, dqd, res); }
-}
-
-template <int OI>
 __device__ __forceinline__ void nc_setup(NcRows& nc, const float* q, const float* qd, const float* mt, const float* mi, const float (*Minv)[ND]) {
-  constexpr int id = nc_order(OI);
-  constexpr int d = id % ND;
-  const float dinv = 1.0f / Minv[d][d];
-  if (id >= ND) {  // btMultiBodyJointMotor in POSITION_CONTROL (kuka.py:282-301)
-    const int s = 2 * OI;
-    float target_vel = MOTOR_KP * (mt[d] - q[d]) * INV_DT + qd[d] + MOTOR_KD * (0.0f - qd[d]);
-    nc.active[s] = true; nc.active[s + 1] = false;
-    nc.dinv[s] = dinv; nc.rhs[s] = (target_vel - qd[d]) * dinv;
-    nc.lo[s] = -mi[d]; nc.hi[s] = mi[d]; nc.app[s] = 0.0f;
-  } else {         // btMultiBodyJointLimitConstraint: row 0 lower bound, row 1 upper bound
+  nc.active = 0u;
 #pragma unroll
-    for (int side = 0; side < 2; side++) {
-      const int s = 2 * OI + side;
-      float pen = side == 0 ? q[d] - c_dof_lower[d] : c_dof_upper[d] - q[d];
-      float sign = side ? -1.0f : 1.0f;
-      nc.active[s] = !(pen > 0.0f);
-      float pos_err = pen > SPLIT_IMPULSE_PEN_THRESHOLD ? -pen * CONTACT_ERP * INV_DT : 0.0f;
-      nc.dinv[s] = dinv; nc.rhs[s] = (pos_err - sign * qd[d]) * dinv;
-      nc.lo[s] = 0.0f; nc.hi[s] = LIMIT_MAX_IMPULSE; nc.app[s] = 0.0f;
+  for (int d = 0; d < ND; d++) nc.dinv[d] = 1.0f / Minv[d][d];
+#pragma unroll 1
+  for (int oi = 0; oi < 2 * ND; oi++) {
+    const int id = c_nc_order[oi];
+    const int d = id >= ND ? id - ND : id;
+    const float qv = pick9(q, d), qdv = pick9(qd, d), dinv = nc.dinv[d];
+    const int s = 2 * oi;
+    if (id >= ND) {  // btMultiBodyJointMotor in POSITION_CONTROL (kuka.py:282-301)
+      float target_vel = MOTOR_KP * (pick9(mt, d) - qv) * INV_DT + qdv + MOTOR_KD * (0.0f - qdv);
+      float m = pick9(mi, d);
+      nc.active |= 1u << s;
+      nc.rhs[s] = (target_vel - qdv) * dinv; nc.lo[s] = -m; nc.hi[s] = m; nc.app[s] = 0.0f;
+    } else {         // btMultiBodyJointLimitConstraint: row 0 lower bound (+), row 1 upper bound (-)
+      float pen0 = qv - c_dof_lower[d], pen1 = c_dof_upper[d] - qv;
+      if (!(pen0 > 0.0f)) {
+        float pos_err = pen0 > SPLIT_IMPULSE_PEN_THRESHOLD ? -pen0 * CONTACT_ERP * INV_DT : 0.0f;
+        nc.active |= 1u << s;
+        nc.rhs[s] = (pos_err - qdv) * dinv; nc.lo[s] = 0.0f; nc.hi[s] = LIMIT_MAX_IMPULSE; nc.app[s] = 0.0f;
+      }
+      if (!(pen1 > 0.0f)) {
+        float pos_err = pen1 > SPLIT_IMPULSE_PEN_THRESHOLD ? -pen1 * CONTACT_ERP * INV_DT : 0.0f;
+        nc.active |= 1u << (s + 1);
+        nc.rhs[s + 1] = (pos_err + qdv) * dinv; nc.lo[s + 1] = 0.0f; nc.hi[s + 1] = LIMIT_MAX_IMPULSE; nc.app[s + 1] = 0.0f;
+      }
     }
   }
 }
 
-template <int... I> struct Seq {};
-template <int N, int... I> struct MakeSeq : MakeSeq<N - 1, N - 1, I...> {};
-template <int... I> struct MakeSeq<0, I...> { using type = Seq<I...>; };
-
-template <int... I>
-__device__ __forceinline__ void nc_setup_all(Seq<I...>, NcRows& nc, const float* q, const float* qd, const float* mt, const float* mi, const float (*Minv)[ND]) {
-  int dummy[] = {(nc_setup<I>(nc, q, qd, mt, mi, Minv), 0)...};
-  (void)dummy;
-}
-template <int... I>
-__device__ __forceinline__ void nc_forward(Seq<I...>, NcRows& nc, const float (*Minv)[ND], float* dqd, float& res) {
-  int dummy[] = {(nc_constraint<I, false>(nc, Minv, dqd, res), 0)...};
-  (void)dummy;
-}
-template <int... I>
-__device__ __forceinline__ void nc_backward(Seq<I...>, NcRows& nc, const float (*Minv)[ND], float* dqd, float& res) {
-  int dummy[] = {(nc_constraint<2 * ND - 1 - I, true>(nc, Minv, dqd, res), 0)...};
-  (void)dummy;
+// One Gauss-Seidel sweep over the non-contact rows, forwards or backwards in slot order.
+__device__ __forceinline__ void nc_sweep(NcRows& nc, bool forward, const float (*Minv)[ND], float* dqd, float& res) {
+#pragma unroll 1
+  for (int t = 0; t < 4 * ND; t++) {
+    const int s = forward ? t : 4 * ND - 1 - t;
+    if (!((nc.active >> s) & 1u)) continue;
+    const int id = c_nc_order[s >> 1];
+    const int d = id >= ND ? id - ND : id;
+    const float sign = (s & 1) ? -1.0f : 1.0f;
+    const float dinv = nc.dinv[d];
+    float dl = nc.rhs[s] - sign * pick9(dqd, d) * dinv;
+    float app = nc.app[s], sum = app + dl;
+    if (sum < nc.lo[s]) { dl = nc.lo[s] - app; sum = nc.lo[s]; }
+    else if (sum > nc.hi[s]) { dl = nc.hi[s] - app; sum = nc.hi[s]; }
+    nc.app[s] = sum;
+    const float sdl = sign * dl;
+    const float* col = Minv[d];  // Minv is symmetric: column d == row d
+#pragma unroll
+    for (int r = 0; r < ND; r++) dqd[r] += col[r] * sdl;
+    float rr = dl / dinv;
+    res = fmaxf(res, rr * rr);
+  }
 }
 
 template <int NBLK>
@@ -287,7 +279,7 @@ template <int NBLK>
 __device__ void solve_constraints(Env<NBLK>& e, const Frames& f, const float (*Minv)[ND]) {
   constexpr int NBA = Env<NBLK>::NBA;
   NcRows nc;
-  nc_setup_all(typename MakeSeq<2 * ND>::type(), nc, e.q, e.qd, e.mt, e.mi, Minv);
+  nc_setup(nc, e.q, e.qd, e.mt, e.mi, Minv);
   // ---- contact rows: one normal + two tangents per cached manifold point ----------------------
   ContactRows<NBLK> cr;
   cr.n = 0; cr.nrob = 0;
@@ -320,7 +312,7 @@ __device__ void solve_constraints(Env<NBLK>& e, const Frames& f, const float (*M
       if (robotA) {
         ri = cr.nrob++;
         const int fb = pi.ka == G_FINGER1 ? PMG_BODY_FINGER1 : PMG_BODY_FINGER2;
-#pragma unroll
+#pragma unroll 1
         for (int kk = 0; kk < 3; kk++) {
           V3 d = cr.dir[c][kk];
           float J[ND];
@@ -338,7 +330,7 @@ __device__ void solve_constraints(Env<NBLK>& e, const Frames& f, const float (*M
         }
       }
       cr.rob[c] = (signed char)ri;
-#pragma unroll
+#pragma unroll 1
       for (int kk = 0; kk < 3; kk++) {
         V3 d = cr.dir[c][kk];
         float denom = 0.0f;
@@ -367,10 +359,10 @@ __device__ void solve_constraints(Env<NBLK>& e, const Frames& f, const float (*M
   for (int j = 0; j < ND; j++) dqd[j] = 0.0f;
 #pragma unroll
   for (int b = 0; b < NBA; b++) { dlin[b] = v3(0, 0, 0); dang[b] = v3(0, 0, 0); }
+#pragma unroll 1
   for (int it = 0; it < SOLVER_ITERS; it++) {
     float res = 0.0f;
-    if (it & 1) nc_forward(typename MakeSeq<2 * ND>::type(), nc, Minv, dqd, res);
-    else nc_backward(typename MakeSeq<2 * ND>::type(), nc, Minv, dqd, res);
+    nc_sweep(nc, (it & 1) != 0, Minv, dqd, res);  // backwards on even iterations, forwards on odd
     for (int c = 0; c < cr.n; c++) {
       float dl = cr.rhs[c][0] - contact_row_velocity(cr, c, 0, dqd, dlin, dang) * cr.dinv[c][0];
       float sum = cr.app[c][0] + dl;

@@ -1,16 +1,31 @@
-"""GPU (fp32 CUDA kernels through the C-ABI) vs CPU oracle (double) on the same seeded inputs."""
+"""GPU parity tests: the CUDA kernels, called through the C-ABI, against the CPU oracle on the same
+seeded inputs and against the committed golden vectors (tests/golden, produced by the reference's
+unmodified Python plumbing on the oracle shim).
+
+Tolerances (north_star): state / achieved_goal within 1e-4, done / goal_achieved flags bit-exact
+(flags are compared away from the 0.05 m threshold, where a 1e-4 state difference cannot flip them).
+The kernels compute in fp32 with a CRBA + Cholesky formulation, the oracle in double with the
+articulated-body algorithm: agreement validates both.
+"""
+import os
+
 import numpy as np
 import pytest
 import torch
 
 pytestmark = pytest.mark.gpu
 
-TOL = 1e-4  # north_star: state / achieved_goal within 1e-4
+TOL = 1e-4
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
+KEYS = ("observation", "policy_state", "achieved_goal", "desired_goal")
 
 
 def _mk(task, batch, **kw):
+    import contextlib
+    import io
     import pybullet_multigoal_gym_b200 as pmg
-    return pmg.make_env(task=task, batch=batch, num_block=kw.pop("num_block", 4), **kw)
+    with contextlib.redirect_stdout(io.StringIO()):
+        return pmg.make_env(task=task, batch=batch, num_block=kw.pop("num_block", 4), **kw)
 
 
 def _oracle_env(oracle, task, seed, **kw):
@@ -19,22 +34,58 @@ def _oracle_env(oracle, task, seed, **kw):
     return e
 
 
+def _np(t):
+    return t.detach().cpu().numpy()
+
+
 @pytest.mark.parametrize("task", ["reach", "push", "pick_and_place", "block_stack"])
 def test_reset_matches_oracle_stream(oracle, task):
+    """Host MT19937 sampler + reset kernel vs the oracle, env i seeded with seed + i; two resets."""
     B = 8
     env = _mk(task, B)
+    refs = [_oracle_env(oracle, task, i, num_block=4) for i in range(B)]
+    for rep in range(2):
+        obs = env.reset()
+        for i in range(B):
+            ref = refs[i].reset()
+            for k in ref:
+                np.testing.assert_allclose(_np(obs[k][i]), ref[k], atol=2e-6, err_msg="%s env %d %s" % (task, i, k))
+
+
+@pytest.mark.parametrize("name", ["reach", "push", "pick_and_place", "block_stack"])
+def test_reset_matches_reference_plumbing_golden(name):
+    """env 0 (seed 0) reproduces the reset observations the reference's own Python produced."""
+    g = np.load(os.path.join(GOLDEN, "ref_plumbing_%s.npz" % name))
+    env = _mk(name, 2, binary_reward=(name != "push"))
     obs = env.reset()
-    for i in range(B):
-        o = _oracle_env(oracle, task, i, num_block=4)
-        ref = o.reset()
-        for k in ref:
-            np.testing.assert_allclose(obs[k][i].cpu().numpy(), ref[k], atol=2e-6, err_msg="%s env %d %s" % (task, i, k))
+    flat = np.concatenate([_np(obs[k][0]) for k in KEYS])
+    np.testing.assert_allclose(flat, g["reset_obs"][0], atol=2e-6)
+    assert [int(obs[k].shape[1]) for k in KEYS] == list(g["dims"])
+
+
+def test_reach_rollout_matches_reference_plumbing_golden():
+    """Open-loop Reach episodes (with finger-table contact) vs the golden trajectory, 1e-4."""
+    g = np.load(os.path.join(GOLDEN, "ref_plumbing_reach.npz"))
+    env = _mk("reach", 1)
+    L = int(g["episode_len"])
+    k = 0
+    for ep in range(g["reset_obs"].shape[0]):
+        obs = env.reset()
+        np.testing.assert_allclose(np.concatenate([_np(obs[key][0]) for key in KEYS]), g["reset_obs"][ep], atol=2e-6)
+        for t in range(L):
+            a = torch.from_numpy(g["actions"][k][None].astype(np.float32)).cuda()
+            obs, r, done, info = env.step(a)
+            flat = np.concatenate([_np(obs[key][0]) for key in KEYS])
+            assert np.abs(flat - g["step_obs"][k]).max() < TOL, (k, np.abs(flat - g["step_obs"][k]).max())
+            assert float(r[0]) == g["reward"][k] and bool(done[0]) == bool(g["done"][k])
+            assert bool(info["goal_achieved"][0]) == bool(g["goal_achieved"][k])
+            k += 1
 
 
 def test_reach_rollout_parity(oracle):
     B, T = 16, 50
     env = _mk("reach", B)
-    obs = env.reset()
+    env.reset()
     refs = []
     for i in range(B):
         o = _oracle_env(oracle, "reach", i)
@@ -47,56 +98,130 @@ def test_reach_rollout_parity(oracle):
         if t < 12:
             a[:, 2] = -1.0  # drive the jaws onto the table so the finger-table contacts are exercised
         obs, r, done, info = env.step(torch.from_numpy(a).cuda())
+        ag = _np(obs["achieved_goal"])
         for i in range(B):
             ro, rr, rd, ri = refs[i].step(a[i].astype(np.float64))
-            err = np.abs(obs["achieved_goal"][i].cpu().numpy() - ro["achieved_goal"]).max()
+            err = np.abs(ag[i] - ro["achieved_goal"]).max()
             worst = max(worst, err)
             assert err < TOL, (t, i, err)
             assert bool(done[i]) == rd
             d = np.linalg.norm(ro["achieved_goal"] - ro["desired_goal"])
-            if abs(d - 0.05) > 1e-4:  # flags are bit-exact away from the threshold
+            if abs(d - 0.05) > 2 * TOL:
                 assert bool(info["goal_achieved"][i]) == ri["goal_achieved"]
                 assert float(r[i]) == rr
     print("reach worst |achieved_goal| error over %d steps: %.3g" % (T, worst))
     assert env.overflow_count == 0
 
 
+def test_host_buffer_step_equals_device_step():
+    """pmg_step_host (numpy in / numpy out) and pmg_step (CUDA tensors) are the same computation."""
+    B = 32
+    e1, e2 = _mk("reach", B), _mk("reach", B)
+    e1.reset()
+    e2.reset()
+    rng = np.random.RandomState(5)
+    for t in range(3):
+        a = rng.uniform(-1, 1, size=(B, 3)).astype(np.float32)
+        o1, r1, d1, i1 = e1.step(a)
+        o2, r2, d2, i2 = e2.step(torch.from_numpy(a).cuda())
+        for k in KEYS:
+            assert np.array_equal(o1[k], _np(o2[k]))
+        assert np.array_equal(r1, _np(r2)) and np.array_equal(d1, _np(d2))
+        assert isinstance(o1["observation"], np.ndarray) and o1["observation"].shape == (B, 3)
+
+
+def test_unbatched_env_has_reference_shapes():
+    env = _mk("reach", None)
+    obs = env.reset()
+    assert obs["observation"].shape == (3,) and obs["desired_goal"].dtype == np.float64
+    obs, r, done, info = env.step(np.zeros(3))
+    assert obs["achieved_goal"].shape == (3,) and isinstance(done, bool) and set(info) >= {"goal_achieved"}
+    assert r in (-1.0, 0.0)
+    from pybullet_multigoal_gym_b200 import ActionError
+    with pytest.raises(AssertionError):   # kuka.py:168 asserts action_space.contains(a)
+        env.step(np.array([0.0, 0.0, 1.5]))
+    with pytest.raises(ActionError):
+        env.step(np.zeros(5))
+    assert env.action_space.shape == (3,) and env.observation_space["state"].shape == (3,)
+
+
+def test_compute_reward_kernel(oracle):
+    env = _mk("block_stack", 4)
+    rng = np.random.RandomState(0)
+    ag = rng.uniform(-0.1, 0.1, size=(7, 5, 12)).astype(np.float32)
+    dg = ag + rng.uniform(-0.03, 0.03, size=ag.shape).astype(np.float32)
+    r, ok = env._compute_reward(ag, dg)
+    rr, rok = oracle.compute_reward(ag.astype(np.float64), dg.astype(np.float64), 0.05, True)
+    d = np.linalg.norm(ag.astype(np.float64) - dg, axis=-1)
+    safe = np.abs(d - 0.05) > 1e-6
+    assert r.shape == (7, 5) and np.array_equal(ok[safe], rok[safe]) and np.array_equal(r[safe], rr[safe])
+    rt, okt = env._compute_reward(torch.from_numpy(ag).cuda(), torch.from_numpy(dg).cuda())
+    assert rt.is_cuda and np.array_equal(_np(rt), r)
+    assert np.array_equal(env.compute_reward(ag, dg, None), r)
+
+
+SCRIPTS = {
+    # (phase length, tip target relative to the block, grip command)
+    "push": [(12, (0.0, -0.06, 0.001), 0.0), (18, (0.0, 0.03, 0.001), 0.0)],
+    "pick_and_place": [(10, (0.0, 0.0, 0.07), -1.0), (10, (0.0, 0.0, 0.0), -1.0), (5, (0.0, 0.0, 0.0), 1.0), (12, (0.0, 0.0, 0.10), 1.0)],
+    "block_stack": [(10, (0.0, 0.0, 0.07), -1.0), (10, (0.0, 0.0, 0.0), -1.0), (5, (0.0, 0.0, 0.0), 1.0), (12, (0.0, 0.0, 0.10), 1.0)],
+}
+
+
 @pytest.mark.parametrize("task,adim", [("push", 3), ("pick_and_place", 4), ("block_stack", 4)])
-def test_teacher_forced_step_parity(oracle, task, adim):
-    """Contact-rich tasks diverge chaotically in open loop (fp32 vs double), so each env.step is
-    compared from the oracle's own state (teacher forcing, SURVEY.md 7 hard part 3)."""
-    B, T = 8, 30
+def test_teacher_forced_contact_parity(oracle, task, adim):
+    """Contact-rich tasks are chaotic in open loop (SURVEY.md 7 hard part 3), so every env.step is
+    compared from the oracle's own fp32-rounded state (teacher forcing).  Stiff contact events amplify
+    even a 1e-7 perturbation inside the double-precision oracle itself, so a perturbed twin of the
+    oracle measures that sensitivity per step: steps whose own sensitivity stays below 2e-6 must agree
+    with the GPU to 1e-4; for the others the GPU error must stay within 50x the oracle's own
+    sensitivity.  Scripted side-push / grasp-and-lift keeps the contacts realistic."""
+    B = 8
     env = _mk(task, B, binary_reward=False)
     env.reset()
     spawn = env.last_spawn()
-    refs = []
+    refs, twins = [], []
     for i in range(B):
         o = oracle.OracleEnv(task, num_block=4, binary_reward=False, seed=i)
         o.reset_with(spawn[i].astype(np.float64))
         refs.append(o)
-    # align the rest pose / ee target bookkeeping with the GPU reset
-    env.set_state(np.stack([o.get_state() for o in refs]).astype(np.float32))
+        twins.append(oracle.OracleEnv(task, num_block=4, binary_reward=False, seed=i))
     rng = np.random.RandomState(7)
-    worst = 0.0
-    for t in range(T):
-        a = rng.uniform(-1, 1, size=(B, adim)).astype(np.float32)
-        # steer towards the first block so that contacts happen
-        # both sides restart from the same fp32-rounded state with empty contact caches
-        st = np.stack([o.get_state() for o in refs]).astype(np.float32)
-        for i in range(B):
-            refs[i].set_state(st[i].astype(np.float64))
-            tip = refs[i].link_state(0)[:3]
-            blk = st[i, 46:49]
-            tgt = blk + np.array([0, 0, 0.0 if t > 8 else 0.06])
-            a[i, :3] = np.clip((tgt - tip) / 0.01, -1, 1)
-        env.set_state(st)
-        obs, r, done, info = env.step(torch.from_numpy(a).cuda())
-        for i in range(B):
-            ro, rr, rd, ri = refs[i].step(a[i].astype(np.float64))
-            for k in ("observation", "achieved_goal"):
-                got = obs[k][i].cpu().numpy()
-                # velocities are compared looser: they are one-substep quantities of a stiff contact solve
-                err = np.abs(got - ro[k]).max()
-                worst = max(worst, np.abs(obs["achieved_goal"][i].cpu().numpy() - ro["achieved_goal"]).max())
-            assert np.abs(obs["achieved_goal"][i].cpu().numpy() - ro["achieved_goal"]).max() < 5e-4, (task, t, i)
-    print("%s teacher-forced worst |achieved_goal| error: %.3g" % (task, worst))
+    n_strict = n_loose = 0
+    worst_strict = 0.0
+    t = 0
+    for length, rel, grip in SCRIPTS[task]:
+        for _ in range(length):
+            st = np.stack([o.get_state() for o in refs]).astype(np.float32)
+            a = np.zeros((B, adim), dtype=np.float32)
+            for i in range(B):
+                refs[i].set_state(st[i].astype(np.float64))
+                pert = st[i].astype(np.float64)
+                pert[:9] += 1e-7 * rng.randn(9)
+                pert[46:49] += 1e-7 * rng.randn(3)
+                twins[i].set_state(pert)
+                tip = refs[i].link_state(0)[:3]
+                a[i, :3] = np.clip((st[i, 46:49] + np.array(rel) - tip) / 0.01, -1, 1)
+                if adim == 4:
+                    a[i, 3] = grip
+            env.set_state(st)
+            obs, r, done, info = env.step(torch.from_numpy(a).cuda())
+            ag = _np(obs["achieved_goal"])
+            tipg = _np(obs["observation"])[:, :3]
+            for i in range(B):
+                ro = refs[i].step(a[i].astype(np.float64))[0]
+                rt = twins[i].step(a[i].astype(np.float64))[0]
+                sens = max(np.abs(ro["achieved_goal"] - rt["achieved_goal"]).max(), np.abs(ro["observation"][:3] - rt["observation"][:3]).max())
+                err = max(np.abs(ag[i] - ro["achieved_goal"]).max(), np.abs(tipg[i] - ro["observation"][:3]).max())
+                if sens < 2e-6:
+                    n_strict += 1
+                    worst_strict = max(worst_strict, err)
+                    assert err < TOL, (task, t, i, err, sens)
+                else:
+                    n_loose += 1
+                    assert err < max(50 * sens, 10 * TOL), (task, t, i, err, sens)
+            t += 1
+    print("%s teacher-forced: %d well-conditioned env-steps, worst error %.3g; %d ill-conditioned (oracle self-sensitivity >= 2e-6)"
+          % (task, n_strict, worst_strict, n_loose))
+    assert n_strict > 0.6 * (n_strict + n_loose)
+    assert env.overflow_count == 0

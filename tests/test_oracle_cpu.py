@@ -1,0 +1,155 @@
+"""CPU tests of the oracle: known answers derived from the reference's constants,
+the numpy-compatible RNG (bit-exact against numpy itself), and the golden vectors produced by the
+reference's own Python plumbing (tools/gen_golden.py)."""
+import os
+
+import numpy as np
+import pytest
+
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
+KEYS = ("observation", "policy_state", "achieved_goal", "desired_goal")
+
+
+def test_fk_known_answers(oracle):
+    # FK(q = 0): tip straight up at 1.381 m, identity orientation (urdf joint origins summed)
+    pos, quat = oracle.fk_tip(np.zeros(9))
+    np.testing.assert_allclose(pos, [0, 0, 1.381], atol=1e-9)
+    np.testing.assert_allclose(quat, [0, 0, 0, 1], atol=1e-9)
+    # FK(kuka_rest_pose, kuka.py:27) ~ the intended start (-0.52, 0, 0.25) / quat (0,-1,0,0) up to sign
+    pos, quat = oracle.fk_tip([0, -0.5592432, 0, 1.733180, 0, -0.8501557, 0, 0, 0])
+    np.testing.assert_allclose(pos, [-0.52292, 0, 0.25077], atol=5e-5)
+    np.testing.assert_allclose(np.abs(quat), [0, 1, 0, 0.0005], atol=5e-4)
+    # kuka_away_pose, kuka.py:28
+    pos, _ = oracle.fk_tip([0, 0.5467089, 0, 4.518901, 0, 0.828478, 0, 0, 0])
+    np.testing.assert_allclose(pos, [0.51411, 0, 0.24801], atol=5e-5)
+
+
+def test_jaw_geometry(oracle):
+    # finger_closeness = 0.07 - q1 - q2 (tabs on the inner faces, urdf:485-494)
+    e = oracle.OracleEnv("pick_and_place")
+    e.reset()
+    for q1, q2 in [(0.035, 0.035), (0.02, 0.02), (0.0, 0.0), (0.01, 0.03)]:
+        s = e.get_state()
+        s[7], s[8] = q1, q2
+        e.set_state(s)
+        d = np.linalg.norm(e.link_state(2)[:3] - e.link_state(3)[:3])
+        assert abs(d - (0.07 - q1 - q2)) < 1e-12
+
+
+def test_rng_matches_numpy_bit_exact(oracle):
+    for seed in (0, 1, 12345, 2 ** 40 + 17):
+        e = oracle.OracleEnv("reach", seed=seed)
+        rs = np.random.RandomState()
+        rs.seed(oracle.gym_seed_key(seed))
+        assert np.array_equal(e.rng_uniform(-0.64, -0.40, 50), rs.uniform(-0.64, -0.40, 50))
+        for n in (2, 4, 5, 17):
+            a = np.arange(n)
+            rs.shuffle(a)
+            assert np.array_equal(e.rng_shuffle(n), a)
+        assert np.array_equal(e.rng_uniform(0, 1, 7), rs.uniform(0, 1, 7))
+
+
+def test_ik_converges_and_is_bounded(oracle):
+    q0 = np.array([0, -0.5592432, 0, 1.733180, 0, -0.8501557, 0, 0.035, 0.035])
+    q = oracle.ik(q0, [-0.52, 0.0, 0.25])
+    pos, quat = oracle.fk_tip(q)
+    assert np.linalg.norm(pos - [-0.52, 0, 0.25]) < 2e-4
+    assert np.all(np.abs(q[7:] - 0.035) < 1e-15)  # finger columns of the Jacobian are zero
+    # a far target cannot be reached in 40 damped iterations; per-iteration step is capped at 45 deg
+    q1 = oracle.ik(q0, [-0.52, 0.0, 0.25], max_iter=1)
+    assert np.max(np.abs(q1 - q0)) <= np.pi / 4 + 1e-12
+
+
+def test_mass_matrix_inverse_is_spd(oracle):
+    e = oracle.OracleEnv("reach")
+    e.reset()
+    Mi = e.minv()
+    np.testing.assert_allclose(Mi, Mi.T, atol=1e-9)
+    assert np.all(np.linalg.eigvalsh(Mi) > 0)
+    # the two prismatic fingers carry the finger mass only along their axis: M^-1 >= 1/m
+    assert Mi[7, 7] > 1.0 / 0.636951 - 1e-9
+
+
+def test_reward_truth_table(oracle):
+    ag = np.array([[0.0, 0.0, 0.0], [0.0, 0.0, 0.0], [0.0, 0.0, 0.0]])
+    dg = np.array([[0.0, 0.0, 0.049], [0.0, 0.0, 0.05], [0.0, 0.0, 0.051]])
+    r, ok = oracle.compute_reward(ag, dg, 0.05, True)
+    assert list(ok) == [True, True, False]  # d > thr is the failure condition, d == thr succeeds
+    assert list(r) == [0.0, 0.0, -1.0] and np.signbit(r[0])  # success is -0.0 like the reference
+    r, ok = oracle.compute_reward(ag, dg, 0.05, False)
+    np.testing.assert_allclose(r, [-0.049, -0.05, -0.051])
+    # arbitrary leading axes (HER relabelling), and the 12-D block-stack distance
+    r, ok = oracle.compute_reward(np.zeros((2, 5, 12)), np.full((2, 5, 12), 0.01), 0.05, True)
+    assert r.shape == (2, 5) and ok.all()
+
+
+@pytest.mark.parametrize("task,dims,adim", [("reach", [3, 3, 3, 3], 3), ("push", [20, 7, 3, 3], 3),
+                                            ("pick_and_place", [20, 7, 3, 3], 4), ("block_stack", [72, 16, 12, 12], 4)])
+def test_dims_and_sampling_bounds(oracle, task, dims, adim):
+    e = oracle.OracleEnv(task, num_block=4, seed=3)
+    assert e.dims == dims and e.adim == adim
+    for _ in range(20):
+        o = e.reset()
+        dg = o["desired_goal"].reshape(-1, 3)
+        assert np.all(dg[:, 0] >= -0.64 - 1e-12) and np.all(dg[:, 0] <= -0.40 + 1e-12)
+        assert np.all(np.abs(dg[:, 1]) <= 0.15 + 1e-12)
+        if task == "push":
+            assert np.all(dg[:, 2] == 0.175)
+        if task == "block_stack":
+            assert sorted(np.round((dg[:, 2] - 0.175) / 0.03).astype(int)) == [0, 1, 2, 3]
+            assert np.ptp(dg[:, 0]) == 0 and np.ptp(dg[:, 1]) == 0
+            blocks = o["achieved_goal"].reshape(-1, 3)
+            for i in range(4):
+                for j in range(i + 1, 4):
+                    assert np.linalg.norm(blocks[i, :2] - blocks[j, :2]) > 0.06
+        if task != "reach":
+            blocks = o["achieved_goal"].reshape(-1, 3)
+            assert np.all(blocks[:, 2] == 0.175)
+
+
+def test_time_limit_and_elapsed(oracle):
+    e = oracle.OracleEnv("reach", max_episode_steps=5)
+    e.reset()
+    flags = [e.step(np.zeros(3))[2] for _ in range(6)]
+    assert flags == [False, False, False, False, True, True]
+    e.reset()
+    assert e.step(np.zeros(3))[2] is False
+
+
+def test_block_rests_on_table_and_arm_tracks(oracle):
+    e = oracle.OracleEnv("push", binary_reward=False)
+    o = e.reset()
+    z0 = o["achieved_goal"][2]
+    for _ in range(10):
+        o, r, d, info = e.step(np.zeros(3))
+    assert abs(o["achieved_goal"][2] - z0) < 1e-4          # resting contact holds the block
+    assert len(e.contacts()) >= 4                           # four corner points in the table manifold
+    e = oracle.OracleEnv("reach")
+    o = e.reset()
+    start = o["achieved_goal"].copy()
+    for _ in range(10):
+        o, r, d, info = e.step(np.array([1.0, 0.0, 0.0]))
+    # target moved 10 cm in +x; the motors close ~95 % of each IK step per env-step
+    assert 0.09 < o["achieved_goal"][0] - start[0] < 0.1001
+
+
+@pytest.mark.parametrize("name", ["reach", "push", "pick_and_place", "block_stack"])
+def test_oracle_reproduces_reference_plumbing_goldens(oracle, name):
+    """tests/golden/ref_plumbing_*.npz were produced by the reference's unmodified Python running on
+    the pybullet shim; the oracle's own C restatement of reset/step/obs/reward must reproduce them."""
+    g = np.load(os.path.join(GOLDEN, "ref_plumbing_%s.npz" % name))
+    binary = name != "push"
+    e = oracle.OracleEnv(name, num_block=4, binary_reward=binary, seed=0, max_episode_steps=int(g["max_episode_steps"]))
+    e.reset()  # the reference ctor's own reset (base_env.py:84)
+    L = int(g["episode_len"])
+    k = 0
+    for ep in range(g["reset_obs"].shape[0]):
+        o = e.reset()
+        flat = np.concatenate([o[key] for key in KEYS])
+        np.testing.assert_allclose(flat, g["reset_obs"][ep], atol=1e-12, rtol=0)
+        for t in range(L):
+            o, r, done, info = e.step(g["actions"][k])
+            flat = np.concatenate([o[key] for key in KEYS])
+            np.testing.assert_allclose(flat, g["step_obs"][k], atol=1e-9, rtol=0, err_msg="%s step %d" % (name, k))
+            assert r == g["reward"][k] and done == bool(g["done"][k]) and info["goal_achieved"] == bool(g["goal_achieved"][k])
+            k += 1

@@ -1,0 +1,83 @@
+#!/usr/bin/env python3
+"""Generates tests/golden/*.npz by executing the reference's UNMODIFIED Python
+(/root/reference/pybullet_multigoal_gym) on top of oracle/pybullet_shim.
+
+Runs only in the build container (it imports /root/reference).  What the vectors pin: everything the
+reference itself implements -- env-id plumbing, seeding, object/goal sampling streams, the action
+map, motor commands, call order, observation layout, clipping, reward, TimeLimit -- because that code
+runs for real.  What they do not pin: Bullet's arithmetic (the shim answers physics calls with our
+CPU oracle), see DESIGN.md.
+"""
+import contextlib
+import io
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "oracle", "pybullet_shim"))
+sys.path.insert(0, "/root/reference")
+sys.path.insert(0, ROOT)
+
+import pybullet_multigoal_gym as ref  # noqa: E402  (the reference package)
+
+OUT = os.path.join(ROOT, "tests", "golden")
+KEYS = ("observation", "policy_state", "achieved_goal", "desired_goal")
+CONFIGS = [
+    ("reach", dict(task="reach", binary_reward=True), 3, 60),
+    ("push", dict(task="push", binary_reward=False), 3, 60),
+    ("pick_and_place", dict(task="pick_and_place", binary_reward=True), 4, 60),
+    ("block_stack", dict(task="block_stack", binary_reward=True, num_block=4), 4, 60),
+]
+
+
+def pack(obs):
+    return np.concatenate([np.asarray(obs[k], dtype=np.float64).ravel() for k in KEYS])
+
+
+def scripted_actions(name, adim, T, rng):
+    """Random actions with a scripted bias towards the table / first block so that contacts occur."""
+    a = rng.uniform(-1, 1, size=(T, adim))
+    if name == "reach":
+        a[:14, 2] = -1.0
+    return a
+
+
+def main():
+    os.makedirs(OUT, exist_ok=True)
+    for name, kw, adim, T in CONFIGS:
+        with contextlib.redirect_stdout(io.StringIO()):
+            env = ref.make_env(gripper="parallel_jaw", render=False, **kw)
+        rng = np.random.RandomState(2024)
+        actions = scripted_actions(name, adim, T, rng)
+        resets, steps, rewards, dones, oks = [], [], [], [], []
+        for ep in range(2):
+            resets.append(pack(env.reset()))
+            for t in range(T // 2):
+                a = actions[ep * (T // 2) + t]
+                if name != "reach":
+                    # steer the tip to the (first) block: push from the side / descend with open jaws
+                    obs_now = steps[-1] if (steps and t > 0) else resets[-1]
+                    tip = obs_now[0:3]
+                    blk = obs_now[3:6] if name != "block_stack" else obs_now[8:11]
+                    tgt = blk + np.array([0.0, 0.0, 0.0 if (name == "push" or t > 10) else 0.07])
+                    a[:3] = np.clip((tgt - tip) / 0.01, -1, 1)
+                    if adim == 4:
+                        a[3] = -1.0 if t < 16 else 1.0
+                    actions[ep * (T // 2) + t] = a
+                obs, r, done, info = env.step(a.astype(np.float64))
+                steps.append(pack(obs))
+                rewards.append(float(r))
+                dones.append(bool(done))
+                oks.append(bool(info["goal_achieved"]))
+        np.savez_compressed(os.path.join(OUT, "ref_plumbing_%s.npz" % name), actions=actions, reset_obs=np.array(resets),
+                            step_obs=np.array(steps), reward=np.array(rewards), done=np.array(dones),
+                            goal_achieved=np.array(oks), episode_len=T // 2,
+                            dims=np.array([len(np.ravel(obs[k])) for k in KEYS]),
+                            max_episode_steps=env._max_episode_steps)
+        print("%-16s reset %s steps %s  successes %d  last reward %s" % (name, np.array(resets).shape, np.array(steps).shape, sum(oks), rewards[-1]))
+
+
+if __name__ == "__main__":
+    main()
