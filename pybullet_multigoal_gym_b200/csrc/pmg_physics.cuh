@@ -394,6 +394,124 @@ __device__ __noinline__ void mass_matrix(const Frames& f, float M[ND][ND]) {
   }
 }
 
+// ---- fused robot dynamics: two sweeps over the kinematic tree ---------------------------------
+// Outward sweep (base -> fingers): link frames, world inertia of every body and the Newton-Euler
+// velocity / acceleration recursion with qdd = 0, with the parent's state carried in registers.
+// Inward sweep (fingers -> base): accumulates subtree force/moment (-> bias forces) and subtree
+// composite inertia (-> one mass-matrix row per joint) with the same origin shifts.
+// Loops are rolled on purpose: every thread of the warp is at the same body, so the type branches
+// are uniform, and the step kernel is bound by instruction fetch + dependent-issue latency.
+struct Sym3 { float xx, xy, xz, yy, yz, zz; };
+__device__ __forceinline__ V3 mul(const Sym3& m, V3 v) {
+  return v3(m.xx * v.x + m.xy * v.y + m.xz * v.z, m.xy * v.x + m.yy * v.y + m.yz * v.z, m.xz * v.x + m.yz * v.y + m.zz * v.z);
+}
+
+__device__ __noinline__ void robot_dynamics(const float* q, const float* qd, Frames& f, float* bias, float M[ND][ND]) {
+  V3 Fb[NB], Nb[NB], rcb[NB];   // net force, net moment about the link origin, COM offset (world axes)
+  Sym3 Iwb[NB];                 // world inertia about the COM
+  {
+    M3 Rp = m3_identity();
+    V3 pp = v3(0, 0, 0), wp = v3(0, 0, 0), alp = v3(0, 0, 0), accp = v3(0, 0, GRAVITY), velp = v3(0, 0, 0);
+#pragma unroll 1
+    for (int b = 0; b < NB; b++) {
+      const int jt = body_jtype(b), dof = body_dof(b);
+      M3 Rj = mul(Rp, load_jrot(b));
+      V3 r = mul(Rp, v3(c_jxyz[b][0], c_jxyz[b][1], c_jxyz[b][2]));  // parent origin -> joint origin
+      M3 R = Rj;
+      V3 ax = v3(0, 0, 0), aq = v3(0, 0, 0);
+      if (jt == 0) {
+        float sn, cs;
+        sincosf(q[dof], &sn, &cs);
+        R.r0 = v3(cs * Rj.r0.x + sn * Rj.r0.y, -sn * Rj.r0.x + cs * Rj.r0.y, Rj.r0.z);
+        R.r1 = v3(cs * Rj.r1.x + sn * Rj.r1.y, -sn * Rj.r1.x + cs * Rj.r1.y, Rj.r1.z);
+        R.r2 = v3(cs * Rj.r2.x + sn * Rj.r2.y, -sn * Rj.r2.x + cs * Rj.r2.y, Rj.r2.z);
+        ax = col(Rj, 2);
+        aq = qd[dof] * ax;
+      } else if (jt == 1) {
+        V3 ay = col(Rj, 1);
+        ax = b == PMG_BODY_FINGER1 ? -ay : ay;
+        r += q[dof] * ax;
+        aq = qd[dof] * ax;
+      }
+      V3 p = pp + r;
+      V3 wxr = cross(wp, r);
+      V3 a_o = accp + cross(alp, r) + cross(wp, wxr);
+      V3 v_o = velp + wxr;
+      V3 w = wp, al = alp;
+      if (jt == 0) { w = wp + aq; al = alp + cross(wp, aq); }
+      else if (jt == 1) { a_o += 2.0f * cross(wp, aq); v_o += aq; }
+      // world inertia R diag(I) R^T and COM offset
+      V3 rc = mul(R, v3(c_com[b][0], c_com[b][1], c_com[b][2]));
+      const float i0 = c_inertia[b][0], i1 = c_inertia[b][1], i2 = c_inertia[b][2];
+      V3 s0 = v3(R.r0.x * i0, R.r0.y * i1, R.r0.z * i2), s1 = v3(R.r1.x * i0, R.r1.y * i1, R.r1.z * i2), s2 = v3(R.r2.x * i0, R.r2.y * i1, R.r2.z * i2);
+      Sym3 Iw;
+      Iw.xx = dot(s0, R.r0); Iw.xy = dot(s0, R.r1); Iw.xz = dot(s0, R.r2);
+      Iw.yy = dot(s1, R.r1); Iw.yz = dot(s1, R.r2); Iw.zz = dot(s2, R.r2);
+      // Newton-Euler at the COM, Bullet's per-link velocity damping as an external force
+      V3 wxrc = cross(w, rc);
+      V3 a_c = a_o + cross(al, rc) + cross(w, wxrc);
+      V3 v_c = v_o + wxrc;
+      const float m = c_mass[b];
+      const float kl = LINK_DAMPING + LINK_DAMPING * norm(v_c), ka = LINK_DAMPING + LINK_DAMPING * norm(w);
+      V3 Fc = m * a_c + (m * kl) * v_c;
+      V3 Iww = mul(Iw, w);
+      V3 Nc = mul(Iw, al) + cross(w, Iww) + ka * Iww;
+      f.R[b] = R; f.p[b] = p; f.a[b] = ax;
+      Fb[b] = Fc; Nb[b] = Nc + cross(rc, Fc); rcb[b] = rc; Iwb[b] = Iw;
+      if (b <= PMG_BODY_GBASE) { Rp = R; pp = p; wp = w; alp = al; accp = a_o; velp = v_o; }  // both fingers hang off the gripper base
+    }
+  }
+  M[8][7] = 0.0f;  // the two fingers are siblings
+  // inbox: quantities of already-visited children, expressed about the origin of their parent
+  V3 inF = v3(0, 0, 0), inN = v3(0, 0, 0), inh = v3(0, 0, 0);
+  float inm = 0.0f;
+  Sym3 inI; inI.xx = inI.xy = inI.xz = inI.yy = inI.yz = inI.zz = 0.0f;
+#pragma unroll 1
+  for (int b = NB - 1; b >= 0; b--) {
+    const int jt = body_jtype(b), dof = body_dof(b);
+    const bool leaf = b >= PMG_BODY_FINGER1;
+    const float m = c_mass[b];
+    V3 rc = rcb[b];
+    float cc = dot(rc, rc);
+    Sym3 Iw = Iwb[b];
+    // own quantities about the link origin: h = m rc, I = Iw + m (rc.rc 1 - rc rc^T)
+    V3 F = Fb[b], N = Nb[b], h = m * rc;
+    float mt = m;
+    Sym3 I;
+    I.xx = Iw.xx + m * (cc - rc.x * rc.x); I.xy = Iw.xy - m * rc.x * rc.y; I.xz = Iw.xz - m * rc.x * rc.z;
+    I.yy = Iw.yy + m * (cc - rc.y * rc.y); I.yz = Iw.yz - m * rc.y * rc.z; I.zz = Iw.zz + m * (cc - rc.z * rc.z);
+    if (!leaf) {
+      F += inF; N += inN; h += inh; mt += inm;
+      I.xx += inI.xx; I.xy += inI.xy; I.xz += inI.xz; I.yy += inI.yy; I.yz += inI.yz; I.zz += inI.zz;
+    }
+    V3 pb = f.p[b], ab = f.a[b];
+    if (jt != 2) {
+      V3 n, l;  // moment about p[b] / force caused by unit acceleration of this joint
+      if (jt == 0) { n = mul(I, ab); l = cross(ab, h); M[dof][dof] = dot(ab, n); bias[dof] = dot(ab, N); }
+      else { l = mt * ab; n = cross(h, ab); M[dof][dof] = mt; bias[dof] = dot(ab, F); }
+#pragma unroll 1
+      for (int j = (b <= 6 ? b - 1 : 6); j >= 0; j--) {  // every ancestor with a dof is a revolute arm joint, dof j == body j
+        V3 nj = n + cross(pb - f.p[j], l);
+        M[dof][j] = dot(f.a[j], nj);
+      }
+    }
+    if (b > 0) {
+      // express the subtree about the parent's origin: r = p[b] - p[parent]
+      V3 r = pb - f.p[body_parent(b)];
+      V3 sN = N + cross(r, F);
+      float hr = 2.0f * dot(h, r) + mt * dot(r, r);
+      V3 hm = h + mt * r;
+      Sym3 sI;
+      sI.xx = I.xx + hr - h.x * r.x - r.x * hm.x; sI.xy = I.xy - h.x * r.y - r.x * hm.y; sI.xz = I.xz - h.x * r.z - r.x * hm.z;
+      sI.yy = I.yy + hr - h.y * r.y - r.y * hm.y; sI.yz = I.yz - h.y * r.z - r.y * hm.z; sI.zz = I.zz + hr - h.z * r.z - r.z * hm.z;
+      if (leaf && b == PMG_BODY_FINGER1) {  // second finger: add to what finger2 already delivered
+        inF += F; inN += sN; inh += hm; inm += mt;
+        inI.xx += sI.xx; inI.xy += sI.xy; inI.xz += sI.xz; inI.yy += sI.yy; inI.yz += sI.yz; inI.zz += sI.zz;
+      } else { inF = F; inN = sN; inh = hm; inm = mt; inI = sI; }
+    }
+  }
+}
+
 // In-place Cholesky of the lower triangle, then Minv = L^-T L^-1 (full symmetric matrix out).
 __device__ __noinline__ void invert_spd9(float M[ND][ND], float Minv[ND][ND]) {
 #pragma unroll

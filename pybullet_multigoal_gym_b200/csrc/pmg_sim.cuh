@@ -166,74 +166,105 @@ __device__ void collide(Env<NBLK>& e, const Frames& f) {
 }
 
 // ---- constraint rows + projected Gauss-Seidel ------------------------------------------------
-// The 18 non-contact constraints (9 joint motors, 9 joint-limit constraints of two rows each) are
-// visited in Bullet's sorted order c_nc_order; rows live in slots 2*oi + side (motors: side 0).
-// The loops are deliberately rolled: the step kernel is instruction-fetch bound, not FLOP bound.
+// Non-contact rows.  Bullet visits the 18 constraints in its sorted order c_nc_order: with the
+// generated order that is the 9 joint motors (dofs 2,3,0,1,4,7,8,5,6) followed by the 9 joint-limit
+// constraints in the same dof order, each limit constraint contributing its lower-bound row (+1)
+// and then its upper-bound row (-1) when violated.  The motor rows are always active and are kept
+// branch-free in registers; limit rows are rare (the closed jaws sit on their upper limit) and go
+// through a small rolled loop.  The whole solver stays a few hundred instructions: the step kernel
+// is bound by instruction fetch and dependent-issue latency, not by FLOPs (profiles/).
+__host__ __device__ constexpr int nc_order(int i) {
+  constexpr int o[2 * ND] = PMG_NONCONTACT_ORDER;
+  return o[i];
+}
+__host__ __device__ constexpr bool nc_order_is_motors_then_limits() {
+  for (int i = 0; i < ND; i++)
+    if (nc_order(i) < ND || nc_order(ND + i) >= ND || nc_order(i) - ND != nc_order(ND + i)) return false;
+  return true;
+}
+static_assert(nc_order_is_motors_then_limits(), "solver layout assumes motors first, then limits, same dof order");
+__host__ __device__ constexpr int nc_dof(int k) { return nc_order(k) - ND; }  // dof of the k-th motor / limit constraint
+
 struct NcRows {
-  float rhs[4 * ND], lo[4 * ND], hi[4 * ND], app[4 * ND];
-  float dinv[ND];        // 1 / Minv[d][d]
-  unsigned active;       // bit per slot
+  float rhs[ND], lim[ND], app[ND], dinv[ND];  // motor rows, indexed by visit position k; dinv = 1 / Minv[d][d]
+  float lrhs[2 * ND], lapp[2 * ND];  // limit rows, slot 2*k + side
+  unsigned lactive;                  // bit per limit slot
 };
 
-__device__ __forceinline__ float pick9(const float* v, int d) {  // v stays in registers
-  float r = v[0];
-#pragma unroll
-  for (int k = 1; k < ND; k++) r = d == k ? v[k] : r;
-  return r;
-}
-
 __device__ __forceinline__ void nc_setup(NcRows& nc, const float* q, const float* qd, const float* mt, const float* mi, const float (*Minv)[ND]) {
-  nc.active = 0u;
+  nc.lactive = 0u;
 #pragma unroll
-  for (int d = 0; d < ND; d++) nc.dinv[d] = 1.0f / Minv[d][d];
-#pragma unroll 1
-  for (int oi = 0; oi < 2 * ND; oi++) {
-    const int id = c_nc_order[oi];
-    const int d = id >= ND ? id - ND : id;
-    const float qv = pick9(q, d), qdv = pick9(qd, d), dinv = nc.dinv[d];
-    const int s = 2 * oi;
-    if (id >= ND) {  // btMultiBodyJointMotor in POSITION_CONTROL (kuka.py:282-301)
-      float target_vel = MOTOR_KP * (pick9(mt, d) - qv) * INV_DT + qdv + MOTOR_KD * (0.0f - qdv);
-      float m = pick9(mi, d);
-      nc.active |= 1u << s;
-      nc.rhs[s] = (target_vel - qdv) * dinv; nc.lo[s] = -m; nc.hi[s] = m; nc.app[s] = 0.0f;
-    } else {         // btMultiBodyJointLimitConstraint: row 0 lower bound (+), row 1 upper bound (-)
-      float pen0 = qv - c_dof_lower[d], pen1 = c_dof_upper[d] - qv;
-      if (!(pen0 > 0.0f)) {
-        float pos_err = pen0 > SPLIT_IMPULSE_PEN_THRESHOLD ? -pen0 * CONTACT_ERP * INV_DT : 0.0f;
-        nc.active |= 1u << s;
-        nc.rhs[s] = (pos_err - qdv) * dinv; nc.lo[s] = 0.0f; nc.hi[s] = LIMIT_MAX_IMPULSE; nc.app[s] = 0.0f;
-      }
-      if (!(pen1 > 0.0f)) {
-        float pos_err = pen1 > SPLIT_IMPULSE_PEN_THRESHOLD ? -pen1 * CONTACT_ERP * INV_DT : 0.0f;
-        nc.active |= 1u << (s + 1);
-        nc.rhs[s + 1] = (pos_err + qdv) * dinv; nc.lo[s + 1] = 0.0f; nc.hi[s + 1] = LIMIT_MAX_IMPULSE; nc.app[s + 1] = 0.0f;
-      }
+  for (int k = 0; k < ND; k++) {
+    const int d = nc_dof(k);
+    const float dinv = 1.0f / Minv[d][d];
+    // btMultiBodyJointMotor in POSITION_CONTROL (kuka.py:282-301): velocity target from the position error
+    float target_vel = MOTOR_KP * (mt[d] - q[d]) * INV_DT + qd[d] + MOTOR_KD * (0.0f - qd[d]);
+    nc.rhs[k] = (target_vel - qd[d]) * dinv; nc.lim[k] = mi[d]; nc.app[k] = 0.0f; nc.dinv[k] = dinv;
+    // btMultiBodyJointLimitConstraint: row 0 lower bound (+), row 1 upper bound (-), only when violated
+    float pen0 = q[d] - c_dof_lower[d], pen1 = c_dof_upper[d] - q[d];
+    if (!(pen0 > 0.0f)) {
+      float pos_err = pen0 > SPLIT_IMPULSE_PEN_THRESHOLD ? -pen0 * CONTACT_ERP * INV_DT : 0.0f;
+      nc.lactive |= 1u << (2 * k);
+      nc.lrhs[2 * k] = (pos_err - qd[d]) * dinv; nc.lapp[2 * k] = 0.0f;
+    }
+    if (!(pen1 > 0.0f)) {
+      float pos_err = pen1 > SPLIT_IMPULSE_PEN_THRESHOLD ? -pen1 * CONTACT_ERP * INV_DT : 0.0f;
+      nc.lactive |= 1u << (2 * k + 1);
+      nc.lrhs[2 * k + 1] = (pos_err + qd[d]) * dinv; nc.lapp[2 * k + 1] = 0.0f;
     }
   }
 }
 
-// One Gauss-Seidel sweep over the non-contact rows, forwards or backwards in slot order.
-__device__ __forceinline__ void nc_sweep(NcRows& nc, bool forward, const float (*Minv)[ND], float* dqd, float& res) {
+template <int K>
+__device__ __forceinline__ void nc_motor_row(NcRows& nc, const float (*Minv)[ND], float* dqd, float& res) {
+  constexpr int d = nc_dof(K);
+  const float mdd = Minv[d][d];
+  float dl = nc.rhs[K] - dqd[d] * nc.dinv[K];
+  float sum = fminf(fmaxf(nc.app[K] + dl, -nc.lim[K]), nc.lim[K]);
+  dl = sum - nc.app[K];
+  nc.app[K] = sum;
+#pragma unroll
+  for (int r = 0; r < ND; r++) dqd[r] += Minv[d][r] * dl;
+  float rr = dl * mdd;
+  res = fmaxf(res, rr * rr);
+}
+
+__device__ __forceinline__ void nc_limit_rows(NcRows& nc, bool forward, const float (*Minv)[ND], float* dqd, float& res) {
+  unsigned todo = nc.lactive;
 #pragma unroll 1
-  for (int t = 0; t < 4 * ND; t++) {
-    const int s = forward ? t : 4 * ND - 1 - t;
-    if (!((nc.active >> s) & 1u)) continue;
-    const int id = c_nc_order[s >> 1];
-    const int d = id >= ND ? id - ND : id;
+  while (todo) {
+    const int s = forward ? __ffs(todo) - 1 : 31 - __clz(todo);
+    todo &= ~(1u << s);
+    const int d = c_nc_order[ND + (s >> 1)];
     const float sign = (s & 1) ? -1.0f : 1.0f;
-    const float dinv = nc.dinv[d];
-    float dl = nc.rhs[s] - sign * pick9(dqd, d) * dinv;
-    float app = nc.app[s], sum = app + dl;
-    if (sum < nc.lo[s]) { dl = nc.lo[s] - app; sum = nc.lo[s]; }
-    else if (sum > nc.hi[s]) { dl = nc.hi[s] - app; sum = nc.hi[s]; }
-    nc.app[s] = sum;
+    const float* col = Minv[d];  // symmetric: column d == row d
+    float cur = 0.0f;
+#pragma unroll
+    for (int r = 0; r < ND; r++) cur = r == d ? dqd[r] : cur;
+    float dl = nc.lrhs[s] - sign * cur * (1.0f / col[d]);
+    float sum = fminf(fmaxf(nc.lapp[s] + dl, 0.0f), LIMIT_MAX_IMPULSE);
+    dl = sum - nc.lapp[s];
+    nc.lapp[s] = sum;
     const float sdl = sign * dl;
-    const float* col = Minv[d];  // Minv is symmetric: column d == row d
 #pragma unroll
     for (int r = 0; r < ND; r++) dqd[r] += col[r] * sdl;
-    float rr = dl / dinv;
+    float rr = dl * col[d];
     res = fmaxf(res, rr * rr);
+  }
+}
+
+// One Gauss-Seidel sweep over the non-contact rows: backwards on even iterations, forwards on odd.
+__device__ __forceinline__ void nc_sweep(NcRows& nc, bool forward, const float (*Minv)[ND], float* dqd, float& res) {
+  if (forward) {
+    nc_motor_row<0>(nc, Minv, dqd, res); nc_motor_row<1>(nc, Minv, dqd, res); nc_motor_row<2>(nc, Minv, dqd, res);
+    nc_motor_row<3>(nc, Minv, dqd, res); nc_motor_row<4>(nc, Minv, dqd, res); nc_motor_row<5>(nc, Minv, dqd, res);
+    nc_motor_row<6>(nc, Minv, dqd, res); nc_motor_row<7>(nc, Minv, dqd, res); nc_motor_row<8>(nc, Minv, dqd, res);
+    nc_limit_rows(nc, true, Minv, dqd, res);
+  } else {
+    nc_limit_rows(nc, false, Minv, dqd, res);
+    nc_motor_row<8>(nc, Minv, dqd, res); nc_motor_row<7>(nc, Minv, dqd, res); nc_motor_row<6>(nc, Minv, dqd, res);
+    nc_motor_row<5>(nc, Minv, dqd, res); nc_motor_row<4>(nc, Minv, dqd, res); nc_motor_row<3>(nc, Minv, dqd, res);
+    nc_motor_row<2>(nc, Minv, dqd, res); nc_motor_row<1>(nc, Minv, dqd, res); nc_motor_row<0>(nc, Minv, dqd, res);
   }
 }
 
@@ -409,13 +440,11 @@ __device__ void solve_constraints(Env<NBLK>& e, const Frames& f, const float (*M
 template <int NBLK>
 __device__ void substep(Env<NBLK>& e) {
   Frames f;
-  forward_kinematics<NB>(e.q, f);
-  collide(e, f);
   float Minv[ND][ND];
   {
     float bias[ND], M[ND][ND];
-    bias_forces(f, e.qd, bias);
-    mass_matrix(f, M);
+    robot_dynamics(e.q, e.qd, f, bias, M);  // link frames first: the collision pass needs them
+    collide(e, f);
     invert_spd9(M, Minv);
 #pragma unroll
     for (int i = 0; i < ND; i++) {
