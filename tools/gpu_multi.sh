@@ -1,0 +1,3 @@
+mkdir -p gpurun_out
+python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 30 --warmup 3 --no-cpu-baseline 2>&1 | tail -2 | tee gpurun_out/bench_2gpu.json
+python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29512 bench.py --impl reference --gpus 2 --steps 5 --warmup 1 2>&1 | tail -1 | cut -c1-300
