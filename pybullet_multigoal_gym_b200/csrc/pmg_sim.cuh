@@ -268,42 +268,67 @@ __device__ __forceinline__ void nc_sweep(NcRows& nc, bool forward, const float (
   }
 }
 
+// Contact rows.  One record per row (a contact point has three: normal, tangent 1, tangent 2), sized
+// and aligned for 128-bit local-memory accesses:
+//   RowRec   : direction d, r_A x d, r_B x d (lever arms about the block centres), rhs, 1/denominator,
+//              accumulated impulse.  The cubes have isotropic inertia, so M^-1 J^T of a block endpoint is
+//              J scaled by 1/m (linear) and 1/I (angular) and needs no storage.
+//   RobotRow : J and M^-1 J^T over the 9 robot dofs, padded to 12, only for points on a finger.
+struct __align__(16) RowRec {
+  float dx, dy, dz, rhs;
+  float ax, ay, az, dinv;   // r_A x d
+  float bx, by, bz, app;    // r_B x d
+};
+struct __align__(16) RobotRow { float J[12]; float MJ[12]; };
+
 template <int NBLK>
 struct ContactRows {
   static constexpr int MP = max_points(NBLK), MR = max_robot_points(NBLK);
   int n, nrob;
   signed char rob[MP], blkA[MP], blkB[MP];  // robot-pool index / block indices, -1 = none
-  V3 dir[MP][3], rA[MP], rB[MP];            // normal + two tangents; lever arms about the block centres
-  float rhs[MP][3], dinv[MP][3], app[MP][3], mu[MP];
-  float Jr[MR][3][ND], MJr[MR][3][ND];
+  float mu[MP];
+  RowRec row[MP][3];
+  RobotRow rrow[MR][3];
 };
 
+// velocity of the row's constraint direction for the velocity (or delta-velocity) vq / vlin / vang
 template <int NBLK>
-__device__ __forceinline__ float contact_row_velocity(const ContactRows<NBLK>& cr, int c, int k, const float* vq, const V3* vlin, const V3* vang) {
+__device__ __forceinline__ float row_velocity(const ContactRows<NBLK>& cr, int c, int k, const RowRec& r, const float* vq, const V3* vlin, const V3* vang) {
   float v = 0.0f;
-  V3 d = cr.dir[c][k];
-  int ri = cr.rob[c];
+  const int ri = cr.rob[c];
   if (ri >= 0) {
+    const RobotRow& rr = cr.rrow[ri][k];
 #pragma unroll
-    for (int j = 0; j < ND; j++) v += cr.Jr[ri][k][j] * vq[j];
+    for (int j = 0; j < ND; j++) v += rr.J[j] * vq[j];
   }
-  int a = cr.blkA[c], b = cr.blkB[c];
-  if (a >= 0) v += dot(d, vlin[a] + cross(vang[a], cr.rA[c]));
-  if (b >= 0) v -= dot(d, vlin[b] + cross(vang[b], cr.rB[c]));
+  if (NBLK > 0) {
+    const int a = NBLK == 1 ? (cr.blkA[c] >= 0 ? 0 : -1) : cr.blkA[c], b = NBLK == 1 ? (cr.blkB[c] >= 0 ? 0 : -1) : cr.blkB[c];
+    if (a >= 0) { V3 l = vlin[NBLK == 1 ? 0 : a], w = vang[NBLK == 1 ? 0 : a]; v += r.dx * l.x + r.dy * l.y + r.dz * l.z + r.ax * w.x + r.ay * w.y + r.az * w.z; }
+    if (b >= 0) { V3 l = vlin[NBLK == 1 ? 0 : b], w = vang[NBLK == 1 ? 0 : b]; v -= r.dx * l.x + r.dy * l.y + r.dz * l.z + r.bx * w.x + r.by * w.y + r.bz * w.z; }
+  }
   return v;
 }
 
 template <int NBLK>
-__device__ __forceinline__ void contact_row_apply(const ContactRows<NBLK>& cr, int c, int k, float dl, float* dqd, V3* dlin, V3* dang) {
-  V3 d = cr.dir[c][k];
-  int ri = cr.rob[c];
+__device__ __forceinline__ void row_apply(const ContactRows<NBLK>& cr, int c, int k, const RowRec& r, float dl, float* dqd, V3* dlin, V3* dang) {
+  const int ri = cr.rob[c];
   if (ri >= 0) {
+    const RobotRow& rr = cr.rrow[ri][k];
 #pragma unroll
-    for (int j = 0; j < ND; j++) dqd[j] += cr.MJr[ri][k][j] * dl;
+    for (int j = 0; j < ND; j++) dqd[j] += rr.MJ[j] * dl;
   }
-  int a = cr.blkA[c], b = cr.blkB[c];
-  if (a >= 0) { dlin[a] += (dl * BLOCK_INV_MASS) * d; dang[a] += (dl * BLOCK_INV_INERTIA) * cross(cr.rA[c], d); }
-  if (b >= 0) { dlin[b] -= (dl * BLOCK_INV_MASS) * d; dang[b] -= (dl * BLOCK_INV_INERTIA) * cross(cr.rB[c], d); }
+  if (NBLK > 0) {
+    const int a = NBLK == 1 ? (cr.blkA[c] >= 0 ? 0 : -1) : cr.blkA[c], b = NBLK == 1 ? (cr.blkB[c] >= 0 ? 0 : -1) : cr.blkB[c];
+    const float lm = dl * BLOCK_INV_MASS, li = dl * BLOCK_INV_INERTIA;
+    if (a >= 0) {
+      V3& l = dlin[NBLK == 1 ? 0 : a]; V3& w = dang[NBLK == 1 ? 0 : a];
+      l.x += lm * r.dx; l.y += lm * r.dy; l.z += lm * r.dz; w.x += li * r.ax; w.y += li * r.ay; w.z += li * r.az;
+    }
+    if (b >= 0) {
+      V3& l = dlin[NBLK == 1 ? 0 : b]; V3& w = dang[NBLK == 1 ? 0 : b];
+      l.x -= lm * r.dx; l.y -= lm * r.dy; l.z -= lm * r.dz; w.x -= li * r.bx; w.y -= li * r.by; w.z -= li * r.bz;
+    }
+  }
 }
 
 template <int NBLK>
@@ -315,6 +340,7 @@ __device__ void solve_constraints(Env<NBLK>& e, const Frames& f, const float (*M
   ContactRows<NBLK> cr;
   cr.n = 0; cr.nrob = 0;
   constexpr int NP = num_pairs(NBLK);
+#pragma unroll 1
   for (int k = 0; k < NP; k++) {
     int n = __float_as_int(e.mw(k, 0));
     if (n == 0) continue;
@@ -322,64 +348,70 @@ __device__ void solve_constraints(Env<NBLK>& e, const Frames& f, const float (*M
     V3 pa, pb; M3 Ra, Rb;
     geom_pose(e, f, pi.ka, pi.ia, pa, Ra);
     geom_pose(e, f, pi.kb, pi.ib, pb, Rb);
-    float mu = geom_friction(pi.ka) * geom_friction(pi.kb);
-    bool robotA = pi.ka == G_FINGER1 || pi.ka == G_FINGER2;
+    const float mu = geom_friction(pi.ka) * geom_friction(pi.kb);
+    const bool robotA = pi.ka == G_FINGER1 || pi.ka == G_FINGER2;
+    const bool blockA = pi.ka == G_BLOCK, blockB = pi.kb == G_BLOCK;
+#pragma unroll 1
     for (int i = 0; i < n; i++) {
       if (cr.n >= ContactRows<NBLK>::MP || (robotA && cr.nrob >= ContactRows<NBLK>::MR)) { e.overflow++; continue; }
-      int c = cr.n++;
-      int o = 1 + 10 * i;
+      const int c = cr.n++;
+      const int o = 1 + 10 * i;
       V3 lA = v3(e.mw(k, o), e.mw(k, o + 1), e.mw(k, o + 2)), lB = v3(e.mw(k, o + 3), e.mw(k, o + 4), e.mw(k, o + 5));
       V3 nB = v3(e.mw(k, o + 6), e.mw(k, o + 7), e.mw(k, o + 8));
-      float dist = e.mw(k, o + 9);
+      const float dist = e.mw(k, o + 9);
       V3 wa = mul(Ra, lA) + pa, wb = mul(Rb, lB) + pb;
-      V3 t1, t2;
-      plane_space(nB, t1, t2);
-      cr.dir[c][0] = nB; cr.dir[c][1] = t1; cr.dir[c][2] = t2;
+      V3 dirs[3];
+      dirs[0] = nB;
+      plane_space(nB, dirs[1], dirs[2]);
       cr.mu[c] = mu;
-      cr.blkA[c] = pi.ka == G_BLOCK ? pi.ia : -1;
-      cr.blkB[c] = pi.kb == G_BLOCK ? pi.ib : -1;
-      cr.rA[c] = wa - pa; cr.rB[c] = wb - pb;
+      cr.blkA[c] = blockA ? pi.ia : -1;
+      cr.blkB[c] = blockB ? pi.ib : -1;
+      V3 rA = wa - pa, rB = wb - pb;
       int ri = -1;
+      V3 Jp[ND];  // velocity of the contact point per unit joint velocity
       if (robotA) {
         ri = cr.nrob++;
-        const int fb = pi.ka == G_FINGER1 ? PMG_BODY_FINGER1 : PMG_BODY_FINGER2;
-#pragma unroll 1
-        for (int kk = 0; kk < 3; kk++) {
-          V3 d = cr.dir[c][kk];
-          float J[ND];
 #pragma unroll
-          for (int j = 0; j < 7; j++) J[j] = dot(f.a[j], cross(wa - f.p[j], d));
-          J[7] = fb == PMG_BODY_FINGER1 ? dot(f.a[PMG_BODY_FINGER1], d) : 0.0f;
-          J[8] = fb == PMG_BODY_FINGER2 ? dot(f.a[PMG_BODY_FINGER2], d) : 0.0f;
-#pragma unroll
-          for (int r = 0; r < ND; r++) {
-            float s = 0.0f;
-#pragma unroll
-            for (int j = 0; j < ND; j++) s += Minv[r][j] * J[j];
-            cr.Jr[ri][kk][r] = J[r]; cr.MJr[ri][kk][r] = s;
-          }
-        }
+        for (int j = 0; j < 7; j++) Jp[j] = cross(f.a[j], wa - f.p[j]);
+        Jp[7] = pi.ka == G_FINGER1 ? f.a[PMG_BODY_FINGER1] : v3(0, 0, 0);
+        Jp[8] = pi.ka == G_FINGER2 ? f.a[PMG_BODY_FINGER2] : v3(0, 0, 0);
       }
       cr.rob[c] = (signed char)ri;
 #pragma unroll 1
       for (int kk = 0; kk < 3; kk++) {
-        V3 d = cr.dir[c][kk];
+        V3 d = dirs[kk];
+        RowRec r;
+        r.dx = d.x; r.dy = d.y; r.dz = d.z;
+        V3 xa = blockA ? cross(rA, d) : v3(0, 0, 0), xb = blockB ? cross(rB, d) : v3(0, 0, 0);
+        r.ax = xa.x; r.ay = xa.y; r.az = xa.z; r.bx = xb.x; r.by = xb.y; r.bz = xb.z;
         float denom = 0.0f;
         if (ri >= 0) {
+          RobotRow& rr = cr.rrow[ri][kk];
+          float J[ND];
 #pragma unroll
-          for (int j = 0; j < ND; j++) denom += cr.Jr[ri][kk][j] * cr.MJr[ri][kk][j];
+          for (int j = 0; j < ND; j++) { J[j] = dot(d, Jp[j]); rr.J[j] = J[j]; }
+#pragma unroll
+          for (int rr_ = 0; rr_ < ND; rr_++) {
+            float s = 0.0f;
+#pragma unroll
+            for (int j = 0; j < ND; j++) s += Minv[rr_][j] * J[j];
+            rr.MJ[rr_] = s;
+            denom += J[rr_] * s;
+          }
         }
-        if (cr.blkA[c] >= 0) { V3 x = cross(cr.rA[c], d); denom += BLOCK_INV_MASS + BLOCK_INV_INERTIA * dot(x, x); }
-        if (cr.blkB[c] >= 0) { V3 x = cross(cr.rB[c], d); denom += BLOCK_INV_MASS + BLOCK_INV_INERTIA * dot(x, x); }
-        float dinv = 1.0f / denom;
-        cr.dinv[c][kk] = dinv; cr.app[c][kk] = 0.0f;
-        float rel_vel = contact_row_velocity(cr, c, kk, e.qd, e.bv, e.bw);
+        if (blockA) denom += BLOCK_INV_MASS + BLOCK_INV_INERTIA * dot(xa, xa);
+        if (blockB) denom += BLOCK_INV_MASS + BLOCK_INV_INERTIA * dot(xb, xb);
+        r.dinv = 1.0f / denom;
+        r.app = 0.0f;
+        r.rhs = 0.0f;
+        cr.row[c][kk] = r;
+        float rel_vel = row_velocity(cr, c, kk, r, e.qd, e.bv, e.bw);
         if (kk == 0) {
           float pen = dist + LINEAR_SLOP;
           float pos_err = 0.0f, vel_err = -rel_vel;
           if (pen > 0.0f) vel_err -= pen * INV_DT; else pos_err = -pen * CONTACT_ERP * INV_DT;
-          cr.rhs[c][0] = (pos_err + vel_err) * dinv;
-        } else cr.rhs[c][kk] = -rel_vel * dinv;
+          cr.row[c][0].rhs = (pos_err + vel_err) * r.dinv;
+        } else cr.row[c][kk].rhs = -rel_vel * r.dinv;
       }
     }
   }
@@ -394,38 +426,39 @@ __device__ void solve_constraints(Env<NBLK>& e, const Frames& f, const float (*M
   for (int it = 0; it < SOLVER_ITERS; it++) {
     float res = 0.0f;
     nc_sweep(nc, (it & 1) != 0, Minv, dqd, res);  // backwards on even iterations, forwards on odd
+#pragma unroll 1
     for (int c = 0; c < cr.n; c++) {
-      float dl = cr.rhs[c][0] - contact_row_velocity(cr, c, 0, dqd, dlin, dang) * cr.dinv[c][0];
-      float sum = cr.app[c][0] + dl;
-      if (sum < 0.0f) { dl = -cr.app[c][0]; cr.app[c][0] = 0.0f; }
-      else if (sum > 1e10f) { dl = 1e10f - cr.app[c][0]; cr.app[c][0] = 1e10f; }
-      else cr.app[c][0] = sum;
-      contact_row_apply(cr, c, 0, dl, dqd, dlin, dang);
-      float rr = dl / cr.dinv[c][0];
+      RowRec r = cr.row[c][0];
+      float dl = r.rhs - row_velocity(cr, c, 0, r, dqd, dlin, dang) * r.dinv;
+      float sum = fminf(fmaxf(r.app + dl, 0.0f), 1e10f);
+      dl = sum - r.app;
+      cr.row[c][0].app = sum;
+      row_apply(cr, c, 0, r, dl, dqd, dlin, dang);
+      float rr = dl / r.dinv;
       res = fmaxf(res, rr * rr);
     }
+#pragma unroll 1
     for (int c = 0; c < cr.n; c++) {  // implicit friction cone: both tangent rows of a point together
-      float total = cr.app[c][0];
+      const float total = cr.row[c][0].app;
       if (!(total > 0.0f)) continue;
-      float lim = cr.mu[c] * total;
-      float dA = cr.rhs[c][1] - contact_row_velocity(cr, c, 1, dqd, dlin, dang) * cr.dinv[c][1];
-      float dB = cr.rhs[c][2] - contact_row_velocity(cr, c, 2, dqd, dlin, dang) * cr.dinv[c][2];
-      float sA = cr.app[c][1] + dA, sB = cr.app[c][2] + dB;
-      if (sA * sA + sB * sB >= lim * lim) {
-        float ang = atan2f(sA, sB);
-        float sn, cs;
-        sincosf(ang, &sn, &cs);
-        float cA = fabsf(lim * sn), cB = fabsf(lim * cs);
-        if (sA < -cA) { dA = -cA - cr.app[c][1]; cr.app[c][1] = -cA; }
-        else if (sA > cA) { dA = cA - cr.app[c][1]; cr.app[c][1] = cA; }
-        else cr.app[c][1] = sA;
-        if (sB < -cB) { dB = -cB - cr.app[c][2]; cr.app[c][2] = -cB; }
-        else if (sB > cB) { dB = cB - cr.app[c][2]; cr.app[c][2] = cB; }
-        else cr.app[c][2] = sB;
-      } else { cr.app[c][1] = sA; cr.app[c][2] = sB; }
-      contact_row_apply(cr, c, 1, dA, dqd, dlin, dang);
-      contact_row_apply(cr, c, 2, dB, dqd, dlin, dang);
-      float r1 = dA / cr.dinv[c][1], r2 = dB / cr.dinv[c][2];
+      const float lim = cr.mu[c] * total;
+      RowRec ra = cr.row[c][1], rb = cr.row[c][2];
+      float dA = ra.rhs - row_velocity(cr, c, 1, ra, dqd, dlin, dang) * ra.dinv;
+      float dB = rb.rhs - row_velocity(cr, c, 2, rb, dqd, dlin, dang) * rb.dinv;
+      float sA = ra.app + dA, sB = rb.app + dB;
+      const float s2 = sA * sA + sB * sB;
+      if (s2 >= lim * lim) {
+        // |lim sin(atan2(sA, sB))| = lim |sA| / sqrt(sA^2 + sB^2), likewise the cosine for sB
+        const float sc = s2 > 0.0f ? lim * rsqrtf(s2) : 0.0f;
+        const float cA = fabsf(sA) * sc, cB = s2 > 0.0f ? fabsf(sB) * sc : lim;
+        sA = fminf(fmaxf(sA, -cA), cA);
+        sB = fminf(fmaxf(sB, -cB), cB);
+        dA = sA - ra.app; dB = sB - rb.app;
+      }
+      cr.row[c][1].app = sA; cr.row[c][2].app = sB;
+      row_apply(cr, c, 1, ra, dA, dqd, dlin, dang);
+      row_apply(cr, c, 2, rb, dB, dqd, dlin, dang);
+      float r1 = dA / ra.dinv, r2 = dB / rb.dinv;
       res = fmaxf(res, fmaxf(r1 * r1, r2 * r2));
     }
     if (res <= RESIDUAL_THRESHOLD) break;
