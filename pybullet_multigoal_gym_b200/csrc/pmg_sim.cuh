@@ -16,8 +16,8 @@ constexpr int MAN_WORDS = 41;  // per pair
 constexpr int ST_Q = 0, ST_QD = 9, ST_EE = 18, ST_REST = 21, ST_MT = 28, ST_MI = 37, ST_BLK = 46;
 
 __host__ __device__ constexpr int num_pairs(int nblk) { return 2 + 4 * nblk + nblk * (nblk - 1) / 2; }
-__host__ __device__ constexpr int max_points(int nblk) { return nblk <= 1 ? 4 * num_pairs(nblk) : 64; }
-__host__ __device__ constexpr int max_robot_points(int nblk) { return nblk == 0 ? 8 : (nblk == 1 ? 16 : 24); }
+__host__ __device__ constexpr int max_points(int nblk) { return nblk <= 1 ? 4 * num_pairs(nblk) : 48; }
+__host__ __device__ constexpr int max_robot_points(int nblk) { return nblk == 0 ? 8 : 16; }
 
 // geometry endpoints of a collision pair
 enum GeomKind { G_TABLE = 0, G_FLOOR = 1, G_FINGER1 = 2, G_FINGER2 = 3, G_BLOCK = 4 };
@@ -278,15 +278,19 @@ struct __align__(16) RowRec {
   float dx, dy, dz, rhs;
   float ax, ay, az, dinv;   // r_A x d
   float bx, by, bz, app;    // r_B x d
+  float denom, mu;          // 1 / dinv; friction coefficient of the pair
+  int ends;                 // robot-pool index (bits 0..7, 0xff = none) | block A (8..15) | block B (16..23)
+  int pad;
 };
+__device__ __forceinline__ int rec_rob(int ends) { int v = ends & 0xff; return v == 0xff ? -1 : v; }
+__device__ __forceinline__ int rec_blk_a(int ends) { int v = (ends >> 8) & 0xff; return v == 0xff ? -1 : v; }
+__device__ __forceinline__ int rec_blk_b(int ends) { int v = (ends >> 16) & 0xff; return v == 0xff ? -1 : v; }
 struct __align__(16) RobotRow { float J[12]; float MJ[12]; };
 
 template <int NBLK>
 struct ContactRows {
   static constexpr int MP = max_points(NBLK), MR = max_robot_points(NBLK);
   int n, nrob;
-  signed char rob[MP], blkA[MP], blkB[MP];  // robot-pool index / block indices, -1 = none
-  float mu[MP];
   RowRec row[MP][3];
   RobotRow rrow[MR][3];
 };
@@ -295,14 +299,14 @@ struct ContactRows {
 template <int NBLK>
 __device__ __forceinline__ float row_velocity(const ContactRows<NBLK>& cr, int c, int k, const RowRec& r, const float* vq, const V3* vlin, const V3* vang) {
   float v = 0.0f;
-  const int ri = cr.rob[c];
+  const int ri = rec_rob(r.ends);
   if (ri >= 0) {
     const RobotRow& rr = cr.rrow[ri][k];
 #pragma unroll
     for (int j = 0; j < ND; j++) v += rr.J[j] * vq[j];
   }
   if (NBLK > 0) {
-    const int a = NBLK == 1 ? (cr.blkA[c] >= 0 ? 0 : -1) : cr.blkA[c], b = NBLK == 1 ? (cr.blkB[c] >= 0 ? 0 : -1) : cr.blkB[c];
+    const int a = rec_blk_a(r.ends), b = rec_blk_b(r.ends);
     if (a >= 0) { V3 l = vlin[NBLK == 1 ? 0 : a], w = vang[NBLK == 1 ? 0 : a]; v += r.dx * l.x + r.dy * l.y + r.dz * l.z + r.ax * w.x + r.ay * w.y + r.az * w.z; }
     if (b >= 0) { V3 l = vlin[NBLK == 1 ? 0 : b], w = vang[NBLK == 1 ? 0 : b]; v -= r.dx * l.x + r.dy * l.y + r.dz * l.z + r.bx * w.x + r.by * w.y + r.bz * w.z; }
   }
@@ -311,14 +315,14 @@ __device__ __forceinline__ float row_velocity(const ContactRows<NBLK>& cr, int c
 
 template <int NBLK>
 __device__ __forceinline__ void row_apply(const ContactRows<NBLK>& cr, int c, int k, const RowRec& r, float dl, float* dqd, V3* dlin, V3* dang) {
-  const int ri = cr.rob[c];
+  const int ri = rec_rob(r.ends);
   if (ri >= 0) {
     const RobotRow& rr = cr.rrow[ri][k];
 #pragma unroll
     for (int j = 0; j < ND; j++) dqd[j] += rr.MJ[j] * dl;
   }
   if (NBLK > 0) {
-    const int a = NBLK == 1 ? (cr.blkA[c] >= 0 ? 0 : -1) : cr.blkA[c], b = NBLK == 1 ? (cr.blkB[c] >= 0 ? 0 : -1) : cr.blkB[c];
+    const int a = rec_blk_a(r.ends), b = rec_blk_b(r.ends);
     const float lm = dl * BLOCK_INV_MASS, li = dl * BLOCK_INV_INERTIA;
     if (a >= 0) {
       V3& l = dlin[NBLK == 1 ? 0 : a]; V3& w = dang[NBLK == 1 ? 0 : a];
@@ -363,9 +367,6 @@ __device__ void solve_constraints(Env<NBLK>& e, const Frames& f, const float (*M
       V3 dirs[3];
       dirs[0] = nB;
       plane_space(nB, dirs[1], dirs[2]);
-      cr.mu[c] = mu;
-      cr.blkA[c] = blockA ? pi.ia : -1;
-      cr.blkB[c] = blockB ? pi.ib : -1;
       V3 rA = wa - pa, rB = wb - pb;
       int ri = -1;
       V3 Jp[ND];  // velocity of the contact point per unit joint velocity
@@ -376,11 +377,12 @@ __device__ void solve_constraints(Env<NBLK>& e, const Frames& f, const float (*M
         Jp[7] = pi.ka == G_FINGER1 ? f.a[PMG_BODY_FINGER1] : v3(0, 0, 0);
         Jp[8] = pi.ka == G_FINGER2 ? f.a[PMG_BODY_FINGER2] : v3(0, 0, 0);
       }
-      cr.rob[c] = (signed char)ri;
+      const int ends = (ri & 0xff) | (((blockA ? pi.ia : -1) & 0xff) << 8) | (((blockB ? pi.ib : -1) & 0xff) << 16);
 #pragma unroll 1
       for (int kk = 0; kk < 3; kk++) {
         V3 d = dirs[kk];
         RowRec r;
+        r.ends = ends; r.mu = mu; r.pad = 0;
         r.dx = d.x; r.dy = d.y; r.dz = d.z;
         V3 xa = blockA ? cross(rA, d) : v3(0, 0, 0), xb = blockB ? cross(rB, d) : v3(0, 0, 0);
         r.ax = xa.x; r.ay = xa.y; r.az = xa.z; r.bx = xb.x; r.by = xb.y; r.bz = xb.z;
@@ -401,6 +403,7 @@ __device__ void solve_constraints(Env<NBLK>& e, const Frames& f, const float (*M
         }
         if (blockA) denom += BLOCK_INV_MASS + BLOCK_INV_INERTIA * dot(xa, xa);
         if (blockB) denom += BLOCK_INV_MASS + BLOCK_INV_INERTIA * dot(xb, xb);
+        r.denom = denom;
         r.dinv = 1.0f / denom;
         r.app = 0.0f;
         r.rhs = 0.0f;
@@ -434,15 +437,15 @@ __device__ void solve_constraints(Env<NBLK>& e, const Frames& f, const float (*M
       dl = sum - r.app;
       cr.row[c][0].app = sum;
       row_apply(cr, c, 0, r, dl, dqd, dlin, dang);
-      float rr = dl / r.dinv;
+      float rr = dl * r.denom;
       res = fmaxf(res, rr * rr);
     }
 #pragma unroll 1
     for (int c = 0; c < cr.n; c++) {  // implicit friction cone: both tangent rows of a point together
       const float total = cr.row[c][0].app;
       if (!(total > 0.0f)) continue;
-      const float lim = cr.mu[c] * total;
       RowRec ra = cr.row[c][1], rb = cr.row[c][2];
+      const float lim = ra.mu * total;
       float dA = ra.rhs - row_velocity(cr, c, 1, ra, dqd, dlin, dang) * ra.dinv;
       float dB = rb.rhs - row_velocity(cr, c, 2, rb, dqd, dlin, dang) * rb.dinv;
       float sA = ra.app + dA, sB = rb.app + dB;
@@ -458,7 +461,7 @@ __device__ void solve_constraints(Env<NBLK>& e, const Frames& f, const float (*M
       cr.row[c][1].app = sA; cr.row[c][2].app = sB;
       row_apply(cr, c, 1, ra, dA, dqd, dlin, dang);
       row_apply(cr, c, 2, rb, dB, dqd, dlin, dang);
-      float r1 = dA / ra.dinv, r2 = dB / rb.dinv;
+      float r1 = dA * ra.denom, r2 = dB * rb.denom;
       res = fmaxf(res, fmaxf(r1 * r1, r2 * r2));
     }
     if (res <= RESIDUAL_THRESHOLD) break;

@@ -8,6 +8,8 @@ B = int(sys.argv[2]) if len(sys.argv) > 2 else 8192
 n = int(sys.argv[3]) if len(sys.argv) > 3 else 4
 env = pmg.make_env(task=task, batch=B, num_block=4, check_actions=False)
 acts = torch.rand((n, B, env.action_dim), device="cuda") * 2 - 1
+if len(sys.argv) > 4 and sys.argv[4] == "down":
+    acts[:, :, 2] = -1.0  # drive every arm onto the table: all lanes take the contact path
 out = torch.empty((B, env.row_width), device="cuda"); r = torch.empty((B,), device="cuda")
 d = torch.empty((B,), dtype=torch.uint8, device="cuda"); s = torch.empty((B,), dtype=torch.uint8, device="cuda")
 for t in range(n):
