@@ -295,6 +295,21 @@ struct ContactRows {
   RobotRow rrow[MR][3];
 };
 
+// Block-indexed access that keeps the per-block delta velocities in registers: a select chain over
+// the (few) blocks instead of a dynamically indexed local-memory array inside the sequential sweep.
+template <int N>
+__device__ __forceinline__ V3 blk_get(const V3* v, int b) {
+  V3 r = v[0];
+#pragma unroll
+  for (int k = 1; k < N; k++) { r.x = b == k ? v[k].x : r.x; r.y = b == k ? v[k].y : r.y; r.z = b == k ? v[k].z : r.z; }
+  return r;
+}
+template <int N>
+__device__ __forceinline__ void blk_add(V3* v, int b, V3 d) {
+#pragma unroll
+  for (int k = 0; k < N; k++) { const float m = b == k ? 1.0f : 0.0f; v[k].x += m * d.x; v[k].y += m * d.y; v[k].z += m * d.z; }
+}
+
 // velocity of the row's constraint direction for the velocity (or delta-velocity) vq / vlin / vang
 template <int NBLK>
 __device__ __forceinline__ float row_velocity(const ContactRows<NBLK>& cr, int c, int k, const RowRec& r, const float* vq, const V3* vlin, const V3* vang) {
@@ -307,8 +322,8 @@ __device__ __forceinline__ float row_velocity(const ContactRows<NBLK>& cr, int c
   }
   if (NBLK > 0) {
     const int a = rec_blk_a(r.ends), b = rec_blk_b(r.ends);
-    if (a >= 0) { V3 l = vlin[NBLK == 1 ? 0 : a], w = vang[NBLK == 1 ? 0 : a]; v += r.dx * l.x + r.dy * l.y + r.dz * l.z + r.ax * w.x + r.ay * w.y + r.az * w.z; }
-    if (b >= 0) { V3 l = vlin[NBLK == 1 ? 0 : b], w = vang[NBLK == 1 ? 0 : b]; v -= r.dx * l.x + r.dy * l.y + r.dz * l.z + r.bx * w.x + r.by * w.y + r.bz * w.z; }
+    if (a >= 0) { V3 l = blk_get<NBLK>(vlin, a), w = blk_get<NBLK>(vang, a); v += r.dx * l.x + r.dy * l.y + r.dz * l.z + r.ax * w.x + r.ay * w.y + r.az * w.z; }
+    if (b >= 0) { V3 l = blk_get<NBLK>(vlin, b), w = blk_get<NBLK>(vang, b); v -= r.dx * l.x + r.dy * l.y + r.dz * l.z + r.bx * w.x + r.by * w.y + r.bz * w.z; }
   }
   return v;
 }
@@ -324,14 +339,8 @@ __device__ __forceinline__ void row_apply(const ContactRows<NBLK>& cr, int c, in
   if (NBLK > 0) {
     const int a = rec_blk_a(r.ends), b = rec_blk_b(r.ends);
     const float lm = dl * BLOCK_INV_MASS, li = dl * BLOCK_INV_INERTIA;
-    if (a >= 0) {
-      V3& l = dlin[NBLK == 1 ? 0 : a]; V3& w = dang[NBLK == 1 ? 0 : a];
-      l.x += lm * r.dx; l.y += lm * r.dy; l.z += lm * r.dz; w.x += li * r.ax; w.y += li * r.ay; w.z += li * r.az;
-    }
-    if (b >= 0) {
-      V3& l = dlin[NBLK == 1 ? 0 : b]; V3& w = dang[NBLK == 1 ? 0 : b];
-      l.x -= lm * r.dx; l.y -= lm * r.dy; l.z -= lm * r.dz; w.x -= li * r.bx; w.y -= li * r.by; w.z -= li * r.bz;
-    }
+    if (a >= 0) { blk_add<NBLK>(dlin, a, v3(lm * r.dx, lm * r.dy, lm * r.dz)); blk_add<NBLK>(dang, a, v3(li * r.ax, li * r.ay, li * r.az)); }
+    if (b >= 0) { blk_add<NBLK>(dlin, b, v3(-lm * r.dx, -lm * r.dy, -lm * r.dz)); blk_add<NBLK>(dang, b, v3(-li * r.bx, -li * r.by, -li * r.bz)); }
   }
 }
 
