@@ -9,7 +9,7 @@ SO = os.path.join(HERE, "libpmg.so")
 SOURCES = ["pmg_capi.cu"]
 DEPS = ["pmg_capi.cu", "pmg_sim.cuh", "pmg_physics.cuh", "../../include/pmg.h", "../../include/pmg_model_constants.h"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-              "--expt-relaxed-constexpr", "-Xcompiler", "-fPIC", "-shared", "-Xptxas", "-v"]
+              "--expt-relaxed-constexpr", "-prec-div=false", "-prec-sqrt=false", "-Xcompiler", "-fPIC", "-shared", "-Xptxas", "-v"]
 
 
 def stale():
