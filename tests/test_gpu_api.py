@@ -1,0 +1,108 @@
+"""GPU tests of the env API surface: partial resets, seeding, determinism, TimeLimit, sharded wrapper."""
+import contextlib
+import io
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _mk(task, batch, **kw):
+    import pybullet_multigoal_gym_b200 as pmg
+    with contextlib.redirect_stdout(io.StringIO()):
+        return pmg.make_env(task=task, batch=batch, num_block=kw.pop("num_block", 4), **kw)
+
+
+def test_partial_reset_only_touches_masked_envs():
+    B = 16
+    env = _mk("push", B)
+    env.reset()
+    a = torch.rand((B, 3), device="cuda") * 2 - 1
+    for _ in range(3):
+        obs, r, d, info = env.step(a)
+    before = env.get_state()
+    mask = np.zeros(B, dtype=bool)
+    mask[[1, 5, 6]] = True
+    obs2 = env.reset(mask=mask)
+    after = env.get_state()
+    keep = ~mask
+    assert np.array_equal(before[keep], after[keep])
+    assert np.all(after[mask, -1] == 0) and np.all(after[keep, -1] == 3)          # elapsed steps
+    assert np.all(after[mask, 9:18] == 0)                                       # joint velocities zeroed
+    assert not np.array_equal(before[mask, 46:49], after[mask, 46:49])          # block respawned
+    for k in obs:
+        assert torch.equal(obs2[k][keep], obs[k][keep])
+    # done follows the per-env counter
+    for _ in range(47):
+        obs, r, d, info = env.step(a)
+    assert bool(d[keep].all()) and not bool(d[mask].any())
+
+
+def test_seed_reproducibility_and_stream_offsets():
+    e1, e2 = _mk("pick_and_place", 8, seed=11), _mk("pick_and_place", 8, seed=11)
+    o1, o2 = e1.reset(), e2.reset()
+    for k in o1:
+        assert torch.equal(o1[k], o2[k])
+    a = torch.rand((8, 4), device="cuda") * 2 - 1
+    for _ in range(3):
+        s1, s2 = e1.step(a), e2.step(a)
+        for k in s1[0]:
+            assert torch.equal(s1[0][k], s2[0][k])          # bitwise deterministic
+    # env i of a batch seeded s follows the stream of seed s + i
+    e3 = _mk("pick_and_place", 4, seed=13)
+    e4 = _mk("pick_and_place", 8, seed=11)
+    g3, g4 = e3.reset()["desired_goal"], e4.reset()["desired_goal"]
+    assert torch.equal(g3[0], g4[2]) and torch.equal(g3[1], g4[3])
+    assert e1.seed(5) == [5]
+    with pytest.raises(ValueError):
+        e1.seed(-3)
+
+
+def test_time_limit_and_info_keys():
+    env = _mk("reach", 4, max_episode_steps=3)
+    env.reset()
+    a = torch.zeros((4, 3), device="cuda")
+    flags = []
+    for _ in range(4):
+        obs, r, d, info = env.step(a)
+        flags.append(bool(d.all()))
+        assert set(info) == {"goal_achieved", "is_success", "TimeLimit.truncated"}
+        assert r.dtype == torch.float32 and set(np.unique(r.cpu().numpy())) <= {-1.0, 0.0}
+    assert flags == [False, False, True, True]
+    assert env._max_episode_steps == 3 and env.action_space.shape == (3,)
+    assert env.observation_space["state"].shape == (4, 3)
+
+
+def test_four_dim_action_on_reach_ignores_grip_column():
+    e1, e2 = _mk("reach", 4), _mk("reach", 4)
+    e1.reset()
+    e2.reset()
+    a4 = torch.rand((4, 4), device="cuda") * 2 - 1
+    o1 = e1.step(a4)[0]
+    o2 = e2.step(a4[:, :3].contiguous())[0]
+    assert torch.equal(o1["observation"], o2["observation"])
+
+
+def test_her_style_relabelling_loop():
+    """The use the reference is built for: store an episode, relabel goals with achieved goals of
+    later steps, recompute rewards with env._compute_reward on [N, G] batches."""
+    B, T = 32, 10
+    env = _mk("push", B, binary_reward=True)
+    obs = env.reset()
+    ag = [obs["achieved_goal"].clone()]
+    for t in range(T):
+        obs, r, d, info = env.step(torch.rand((B, 3), device="cuda") * 2 - 1)
+        ag.append(obs["achieved_goal"].clone())
+    ag = torch.stack(ag)                                   # [T+1, B, 3]
+    t_idx = torch.randint(0, T, (64,), device="cuda")
+    e_idx = torch.randint(0, B, (64,), device="cuda")
+    f_idx = torch.minimum(t_idx + 1 + torch.randint(0, T, (64,), device="cuda"), torch.tensor(T, device="cuda"))
+    new_goal = ag[f_idx, e_idx]
+    reward, ok = env._compute_reward(ag[t_idx + 1, e_idx], new_goal)
+    d = (ag[t_idx + 1, e_idx] - new_goal).norm(dim=-1)
+    assert torch.equal(ok, ~(d > 0.05)) or bool(((d - 0.05).abs() < 1e-6).any())
+    assert bool((reward[ok] == 0).all()) and bool((reward[~ok] == -1).all())
+    same = env._compute_reward(new_goal, new_goal)
+    assert bool(same[1].all()) and bool((same[0] == 0).all())
