@@ -25,10 +25,11 @@ import pybullet_multigoal_gym as ref  # noqa: E402  (the reference package)
 OUT = os.path.join(ROOT, "tests", "golden")
 KEYS = ("observation", "policy_state", "achieved_goal", "desired_goal")
 CONFIGS = [
-    ("reach", dict(task="reach", binary_reward=True), 3, 60),
-    ("push", dict(task="push", binary_reward=False), 3, 60),
-    ("pick_and_place", dict(task="pick_and_place", binary_reward=True), 4, 60),
-    ("block_stack", dict(task="block_stack", binary_reward=True, num_block=4), 4, 60),
+    # two full 50-step episodes each, so that gym's TimeLimit flips `done` at the last step
+    ("reach", dict(task="reach", binary_reward=True), 3, 100),
+    ("push", dict(task="push", binary_reward=False), 3, 100),
+    ("pick_and_place", dict(task="pick_and_place", binary_reward=True), 4, 100),
+    ("block_stack", dict(task="block_stack", binary_reward=True, num_block=4), 4, 100),
 ]
 
 
@@ -67,6 +68,8 @@ def main():
                         a[3] = -1.0 if t < 16 else 1.0
                     actions[ep * (T // 2) + t] = a
                 obs, r, done, info = env.step(a.astype(np.float64))
+                if t == T // 2 - 1:
+                    assert done and info.get("TimeLimit.truncated") is True
                 steps.append(pack(obs))
                 rewards.append(float(r))
                 dones.append(bool(done))
