@@ -28,6 +28,8 @@ struct StepIO {
   const float* action; float* obs; float* reward; uint8_t* done; uint8_t* success;
   float thr; int binary; int max_steps; int* overflow;
   int epw;  // environments per warp: lanes [0, epw) of every warp own one environment each
+  int bulk;         // 1: stage the state tile with TMA bulk copies (full warps only)
+  int tile_offset;  // float offset of the state tile inside dynamic shared memory
 };
 
 // env index owned by this thread, or -1 for an idle lane / past the end of the batch
@@ -49,10 +51,38 @@ template <int TASK, int NBLK> struct Dims {
 
 __device__ __forceinline__ float clip5(float v) { return fminf(fmaxf(v, -5.0f), 5.0f); }
 
+// ---- TMA engine: 1-D bulk async copies global -> shared, completion on an mbarrier -------------
+// The persistent state is [word][env]; the 32 environments of a warp are one 128-byte row per word.
+// Every lane issues the bulk copies of its share of the rows into a [word][32] shared-memory tile and
+// the warp waits once on the mbarrier, instead of ~50-130 dependent scalar global loads per thread.
+// Measured (profiles/r01_bulk_copy_carveout_ab.txt): correct, but the step is 25-30 % SLOWER with it --
+// the prologue is microseconds of a multi-millisecond latency-bound kernel and the tile costs L1
+// capacity that the per-thread scratch needs -- so it is opt-in (PMG_BULK_COPY=1), off by default.
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+template <int WORDS>
+__device__ __forceinline__ void bulk_load_state_tile(float* tile, const float* gsrc, size_t batch, uint64_t* bar) {
+  const int lane = threadIdx.x & 31;
+  const uint32_t bar_a = smem_u32(bar);
+  if (lane == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar_a), "r"(1) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_a), "r"(WORDS * 128) : "memory");
+  }
+  __syncwarp();
+  for (int w = lane; w < WORDS; w += 32)
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(tile + w * 32)), "l"(gsrc + (size_t)w * batch), "r"(128), "r"(bar_a) : "memory");
+  uint32_t done = 0;
+  while (!done)
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(done) : "r"(bar_a), "r"(0) : "memory");
+}
+
+// s points at this environment's word 0, consecutive words are `B` floats apart
+// (global state: s = state + env, B = batch; staged tile: s = tile + lane, B = 32).
 template <int TASK, int NBLK>
-__device__ void load_env(Env<NBLK>& e, const StepIO& io, int i) {
-  const size_t B = io.batch;
-  const float* s = io.state + i;
+__device__ void load_env(Env<NBLK>& e, const StepIO& io, int i, const float* s, const size_t B) {
 #pragma unroll
   for (int k = 0; k < ND; k++) {
     e.q[k] = s[(ST_Q + k) * B]; e.qd[k] = s[(ST_QD + k) * B];
@@ -67,7 +97,7 @@ __device__ void load_env(Env<NBLK>& e, const StepIO& io, int i) {
     e.bv[b] = v3(bs[7 * B], bs[8 * B], bs[9 * B]);
     e.bw[b] = v3(bs[10 * B], bs[11 * B], bs[12 * B]);
   }
-  e.man = io.manifold + i; e.stride = B; e.overflow = 0;
+  e.man = io.manifold + i; e.stride = io.batch; e.overflow = 0;
 }
 
 template <int TASK, int NBLK>
@@ -173,10 +203,25 @@ template <int TASK, int NBLK>
 __global__ void __launch_bounds__(32) step_kernel(StepIO io) {
   using D = Dims<TASK, NBLK>;
   const int i = env_of_thread(io);
-  if (i < 0) { stage_row<D::W>(nullptr, io, false); return; }  // idle lanes only help the staged store
   const size_t B = io.batch;
   Env<NBLK> e;
-  load_env<TASK, NBLK>(e, io, i);
+  float ee0[3];
+  if (io.bulk) {  // full warps only (epw == 32, batch % 32 == 0): no idle lanes on this path
+    extern __shared__ float dyn_smem[];
+    __shared__ __align__(8) uint64_t bar;
+    float* tile = dyn_smem + io.tile_offset;
+    const int env0 = (blockIdx.x * blockDim.x + threadIdx.x) & ~31;
+    bulk_load_state_tile<D::STATE>(tile, io.state + env0, B, &bar);
+    const float* ts = tile + (threadIdx.x & 31);
+    load_env<TASK, NBLK>(e, io, i, ts, 32);
+#pragma unroll
+    for (int k = 0; k < 3; k++) ee0[k] = ts[(ST_EE + k) * 32];
+  } else {
+    if (i < 0) { stage_row<D::W>(nullptr, io, false); return; }  // idle lanes only help the staged store
+    load_env<TASK, NBLK>(e, io, i, io.state + i, B);
+#pragma unroll
+    for (int k = 0; k < 3; k++) ee0[k] = io.state[(ST_EE + k) * B + i];
+  }
   float* s = io.state + i;
   // ---- Kuka.apply_action (kuka.py:167-222) ----
   float a[D::A];
@@ -189,7 +234,7 @@ __global__ void __launch_bounds__(32) step_kernel(StepIO io) {
   const float lo[3] = {-0.67f, -0.20f, 0.175f}, hi[3] = {-0.37f, 0.20f, 0.55f};  // kuka.py:40-41
   float ee[3];
 #pragma unroll
-  for (int k = 0; k < 3; k++) ee[k] = fminf(fmaxf(s[(ST_EE + k) * B] + a[k] * 0.01f, lo[k]), hi[k]);
+  for (int k = 0; k < 3; k++) ee[k] = fminf(fmaxf(ee0[k] + a[k] * 0.01f, lo[k]), hi[k]);
   {
     float qik[ND];
 #pragma unroll
@@ -228,7 +273,7 @@ __global__ void __launch_bounds__(32) reset_kernel(ResetIO r) {
   if (i < 0) { stage_row<D::W>(nullptr, io, false); return; }
   const size_t B = io.batch;
   Env<NBLK> e;
-  load_env<TASK, NBLK>(e, io, i);
+  load_env<TASK, NBLK>(e, io, i, io.state + i, B);
   float* s = io.state + i;
   const bool doit = r.mask == nullptr || r.mask[i] != 0;
   if (doit) {
@@ -362,6 +407,8 @@ struct pmg_handle {
   bool was_reset = false;
   int64_t launches = 0;
   int epw = 32;  // environments per warp (launch geometry, see pmg_create)
+  bool no_bulk = true;   // TMA staging of the state tile is opt-in (PMG_BULK_COPY=1): measured slower, see DESIGN.md
+  bool default_carveout = false;  // PMG_DEFAULT_CARVEOUT=1 keeps the driver's shared-memory carve-out
 };
 
 namespace {
@@ -427,14 +474,26 @@ StepIO make_io(pmg_handle* h, const float* action, float* obs, float* reward, ui
   io.thr = h->cfg.distance_threshold; io.binary = h->cfg.binary_reward; io.max_steps = h->cfg.max_episode_steps;
   io.overflow = h->d_overflow;
   io.epw = h->epw;
+  io.bulk = 0; io.tile_offset = 0;
   return io;
 }
 
 // one warp per block: the block scheduler then spreads the (few) warps evenly over the 148 SMs
 template <int TASK, int NBLK>
-void launch_step(pmg_handle* h, const StepIO& io, cudaStream_t st) {
+void launch_step(pmg_handle* h, const StepIO& io_in, cudaStream_t st) {
+  StepIO io = io_in;
   int warps = (h->cfg.batch + h->epw - 1) / h->epw;
-  size_t smem = (size_t)h->epw * Dims<TASK, NBLK>::W * sizeof(float);
+  size_t stage_floats = (size_t)h->epw * Dims<TASK, NBLK>::W;
+  io.bulk = (h->epw == 32 && h->cfg.batch % 32 == 0 && !h->no_bulk) ? 1 : 0;
+  io.tile_offset = (int)((stage_floats + 31) / 32 * 32);
+  size_t smem = (io.bulk ? io.tile_offset + (size_t)Dims<TASK, NBLK>::STATE * 32 : stage_floats) * sizeof(float);
+  // The per-thread scratch lives in L1-cached local memory: ask for the smallest shared-memory
+  // carve-out instead of one sized for the register-limited 8 blocks per SM.
+  static bool hinted = false;
+  if (!hinted && !h->default_carveout) {
+    cudaFuncSetAttribute(step_kernel<TASK, NBLK>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxL1);
+    hinted = true;
+  }
   step_kernel<TASK, NBLK><<<warps, 32, smem, st>>>(io);
 }
 template <int TASK, int NBLK>
@@ -513,6 +572,8 @@ int pmg_create(const pmg_config* cfg, pmg_handle** out) {
     while (epw > 1 && (long)(B + epw - 1) / epw < target_warps) epw >>= 1;
     if (const char* ev = getenv("PMG_ENVS_PER_WARP")) { int v = atoi(ev); if (v >= 1 && v <= 32) epw = v; }
     h->epw = epw;
+    if (const char* ev = getenv("PMG_BULK_COPY")) h->no_bulk = atoi(ev) == 0;
+    if (const char* ev = getenv("PMG_DEFAULT_CARVEOUT")) h->default_carveout = atoi(ev) != 0;
   }
   h->rng.resize(B);
   for (size_t i = 0; i < B; i++) h->rng[i].init_genrand(5489u + (uint32_t)i);
