@@ -1,0 +1,106 @@
+"""Task-level functional tests on the GPU: scripted controllers must solve the batched environments.
+These exercise the whole path (action map -> IK -> motors -> contacts/friction/grasp -> obs/reward)
+the way an RL agent would, on many randomised environments at once."""
+import contextlib
+import io
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _mk(task, batch, **kw):
+    import pybullet_multigoal_gym_b200 as pmg
+    with contextlib.redirect_stdout(io.StringIO()):
+        return pmg.make_env(task=task, batch=batch, num_block=kw.pop("num_block", 4), **kw)
+
+
+def _towards(target, tip, gain=1.0):
+    return torch.clamp((target - tip) / 0.01 * gain, -1.0, 1.0)
+
+
+def test_reach_scripted_policy_reaches_every_goal():
+    B = 256
+    env = _mk("reach", B)
+    obs = env.reset()
+    for t in range(50):
+        a = _towards(obs["desired_goal"], obs["achieved_goal"])
+        obs, r, done, info = env.step(a)
+    assert float(info["goal_achieved"].float().mean()) == 1.0
+    assert bool((r == 0).all()) and bool(done.all())
+    d = (obs["achieved_goal"] - obs["desired_goal"]).norm(dim=1)
+    assert float(d.max()) < 0.01      # the motors close ~95 % of the remaining error every step
+
+
+def test_push_scripted_policy_moves_blocks_to_goals():
+    """Latching state machine per env: travel above to a stand-off point behind the block, descend,
+    push along the block->goal line until the block centre reaches the goal, lift off."""
+    B, T = 256, 100
+    env = _mk("push", B, binary_reward=False, max_episode_steps=T)
+    obs = env.reset()
+    dev = obs["observation"].device
+    blk0, goal = obs["achieved_goal"].clone(), obs["desired_goal"].clone()
+    d0 = (blk0 - goal).norm(dim=1)
+    pd = torch.nn.functional.normalize(goal[:, :2] - blk0[:, :2], dim=1)
+    behind = blk0[:, :2] - 0.05 * pd
+    phase = torch.zeros(B, dtype=torch.long, device=dev)
+    hi, lo = torch.full((B, 1), 0.23, device=dev), torch.full((B, 1), 0.176, device=dev)
+    for t in range(T):
+        tip, blk = obs["observation"][:, 0:3], obs["achieved_goal"]
+        above = torch.cat([behind, hi], dim=1)
+        lift = torch.cat([tip[:, :2], hi], dim=1)
+        t0 = torch.where((tip[:, 2:3] > 0.21), above, lift)
+        t1 = torch.cat([behind, lo], dim=1)
+        remaining = ((goal[:, :2] - blk[:, :2]) * pd).sum(1)
+        t2 = torch.cat([tip[:, :2] + pd * remaining.clamp(0.0, 0.02)[:, None], lo], dim=1)
+        t3 = torch.cat([tip[:, :2], torch.full((B, 1), 0.25, device=dev)], dim=1)
+        tgt = torch.where((phase == 0)[:, None], t0, torch.where((phase == 1)[:, None], t1, torch.where((phase == 2)[:, None], t2, t3)))
+        nxt = phase.clone()   # all transitions are evaluated on the phase the step started in
+        nxt[(phase == 0) & ((tip - above).norm(dim=1) < 0.008)] = 1
+        nxt[(phase == 1) & ((tip[:, 2] - 0.176).abs() < 0.004)] = 2
+        nxt[(phase == 2) & (remaining < 0.005)] = 3
+        phase = nxt
+        obs, r, done, info = env.step(_towards(tgt, tip))
+    d1 = (obs["achieved_goal"] - goal).norm(dim=1)
+    print("push scripted: %.3f of blocks closer, success %.3f, median distance %.3f -> %.3f" % (
+        float((d1 < d0).float().mean()), float(info["goal_achieved"].float().mean()), float(d0.median()), float(d1.median())))
+    assert float((d1 < d0).float().mean()) > 0.9         # the pad pushes the blocks towards their goals
+    assert float(info["goal_achieved"].float().mean()) > 0.3
+    on_table = (obs["achieved_goal"][:, 2] - 0.175).abs() < 0.02
+    assert float(on_table.float().mean()) > 0.98           # a crude controller may pinch the odd block off the table
+    assert torch.allclose(r, -d1, atol=1e-6)              # dense reward is the negative distance
+
+
+def test_pick_and_place_scripted_grasp_and_carry():
+    B = 256
+    env = _mk("pick_and_place", B, max_episode_steps=80)
+    obs = env.reset()
+    phase = torch.zeros(B, dtype=torch.long, device="cuda")   # 0 hover, 1 descend, 2 close, 3 carry
+    timer = torch.zeros(B, dtype=torch.long, device="cuda")
+    for t in range(80):
+        tip, blk, goal = obs["observation"][:, 0:3], obs["achieved_goal"], obs["desired_goal"]
+        hover = blk + torch.tensor([0.0, 0.0, 0.06], device="cuda")
+        tgt = torch.where((phase == 0)[:, None], hover, blk)
+        tgt = torch.where((phase == 3)[:, None], goal, tgt)
+        a = torch.zeros((B, 4), device="cuda")
+        a[:, :3] = _towards(tgt, tip)
+        a[:, 3] = torch.where(phase >= 2, torch.ones(B, device="cuda"), -torch.ones(B, device="cuda"))
+        hold = phase == 2
+        a[hold, :3] = 0.0
+        err = (tgt - tip).norm(dim=1)
+        timer = torch.where(hold, timer + 1, timer)
+        nxt = phase.clone()   # one transition per step, evaluated on the phase the step started in
+        nxt[(phase == 0) & (err < 0.008)] = 1
+        nxt[(phase == 1) & (err < 0.004)] = 2
+        nxt[(phase == 2) & (timer >= 4)] = 3
+        phase = nxt
+        obs, r, done, info = env.step(a)
+    success = float(info["goal_achieved"].float().mean())
+    lifted_goals = obs["desired_goal"][:, 2] > 0.2
+    carried = (obs["achieved_goal"][:, 2] > 0.19) & lifted_goals
+    print("pick_and_place scripted success rate %.3f, in-the-air goals carried %.3f" % (success, float(carried.float().sum() / lifted_goals.float().sum().clamp(min=1))))
+    assert success > 0.8
+    # goals in the air can only be met by actually holding the block against gravity
+    assert float(carried.float().sum() / lifted_goals.float().sum().clamp(min=1)) > 0.7
+    assert float(obs["observation"][:, 6][info["goal_achieved"] & lifted_goals].mean()) == pytest.approx(0.03, abs=0.003)  # jaws closed on a 3 cm cube
