@@ -16,6 +16,7 @@
 
 #include "../../include/pmg.h"
 #include "pmg_sim.cuh"
+#include "pmg_coop.cuh"
 
 using namespace pmg;
 
@@ -23,15 +24,6 @@ using namespace pmg;
 // device: observation assembly (kuka.py:227-256, kuka_single_step_base_env.py:193-221,
 // kuka_multi_step_base_env.py:255-320) and reward (kuka_single_step_base_env.py:237-244)
 // ------------------------------------------------------------------------------------------------
-struct StepIO {
-  float* state; float* manifold; int batch; int state_words;
-  const float* action; float* obs; float* reward; uint8_t* done; uint8_t* success;
-  float thr; int binary; int max_steps; int* overflow;
-  int epw;  // environments per warp: lanes [0, epw) of every warp own one environment each
-  int bulk;         // 1: stage the state tile with TMA bulk copies (full warps only)
-  int tile_offset;  // float offset of the state tile inside dynamic shared memory
-};
-
 // env index owned by this thread, or -1 for an idle lane / past the end of the batch
 __device__ __forceinline__ int env_of_thread(const StepIO& io) {
   const int lane = threadIdx.x & 31;
@@ -39,15 +31,6 @@ __device__ __forceinline__ int env_of_thread(const StepIO& io) {
   const int i = warp * io.epw + lane;
   return (lane < io.epw && i < io.batch) ? i : -1;
 }
-
-template <int TASK, int NBLK> struct Dims {
-  static constexpr int O = TASK == 0 ? 3 : (TASK == 3 ? 8 + 16 * NBLK : 20);
-  static constexpr int P = TASK == 0 ? 3 : (TASK == 3 ? 4 + 3 * NBLK : 7);
-  static constexpr int G = TASK == 3 ? 3 * NBLK : 3;
-  static constexpr int W = O + P + 2 * G;
-  static constexpr int A = TASK >= 2 ? 4 : 3;
-  static constexpr int STATE = ST_BLK + 13 * NBLK + G + 1;
-};
 
 __device__ __forceinline__ float clip5(float v) { return fminf(fmaxf(v, -5.0f), 5.0f); }
 
@@ -263,6 +246,19 @@ __global__ void __launch_bounds__(32) step_kernel(StepIO io) {
   io.done[i] = elapsed >= io.max_steps ? 1 : 0;
 }
 
+// Lane-cooperative Reach step (pmg_coop.cuh): 8 lanes per environment, 4 environments per one-warp block.
+constexpr int COOP_MIN_BLOCKS = 14;  // batch 8192 = 2048 blocks = 13.8 per SM: keep them all resident
+__global__ void __launch_bounds__(32, COOP_MIN_BLOCKS) step_kernel_coop_reach(StepIO io) {
+  extern __shared__ __align__(16) unsigned char coop_smem[];
+  const int lane32 = threadIdx.x & 31, grp = lane32 >> 3;
+  const int env = blockIdx.x * (32 / coop::GL) + grp;
+  if (env >= io.batch) return;  // a whole octet leaves together
+  coop::Grp g;
+  g.lane = lane32 & (coop::GL - 1); g.shift = grp * coop::GL; g.mask = 0xffu << g.shift;
+  coop::EnvSmem& sm = reinterpret_cast<coop::EnvSmem*>(coop_smem)[grp];
+  coop::step_env_reach(g, sm, io, env);
+}
+
 struct ResetIO { StepIO io; const uint8_t* mask; const float* spawn; float tip_init[3]; };
 
 template <int TASK, int NBLK>
@@ -409,6 +405,7 @@ struct pmg_handle {
   int epw = 32;  // environments per warp (launch geometry, see pmg_create)
   bool no_bulk = true;   // TMA staging of the state tile is opt-in (PMG_BULK_COPY=1): measured slower, see DESIGN.md
   bool default_carveout = false;  // PMG_DEFAULT_CARVEOUT=1 keeps the driver's shared-memory carve-out
+  bool coop = true;  // Reach: lane-cooperative kernel (PMG_COOP=0 selects the thread-per-env kernel)
 };
 
 namespace {
@@ -482,6 +479,17 @@ StepIO make_io(pmg_handle* h, const float* action, float* obs, float* reward, ui
 template <int TASK, int NBLK>
 void launch_step(pmg_handle* h, const StepIO& io_in, cudaStream_t st) {
   StepIO io = io_in;
+  if (TASK == 0 && h->coop) {
+    constexpr int EPB = 32 / coop::GL;  // environments per block
+    const size_t smem = EPB * sizeof(coop::EnvSmem);
+    static bool hinted_coop = false;
+    if (!hinted_coop) {
+      cudaFuncSetAttribute(step_kernel_coop_reach, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+      hinted_coop = true;
+    }
+    step_kernel_coop_reach<<<(h->cfg.batch + EPB - 1) / EPB, 32, smem, st>>>(io);
+    return;
+  }
   int warps = (h->cfg.batch + h->epw - 1) / h->epw;
   size_t stage_floats = (size_t)h->epw * Dims<TASK, NBLK>::W;
   io.bulk = (h->epw == 32 && h->cfg.batch % 32 == 0 && !h->no_bulk) ? 1 : 0;
@@ -574,6 +582,7 @@ int pmg_create(const pmg_config* cfg, pmg_handle** out) {
     h->epw = epw;
     if (const char* ev = getenv("PMG_BULK_COPY")) h->no_bulk = atoi(ev) == 0;
     if (const char* ev = getenv("PMG_DEFAULT_CARVEOUT")) h->default_carveout = atoi(ev) != 0;
+    if (const char* ev = getenv("PMG_COOP")) h->coop = atoi(ev) != 0;
   }
   h->rng.resize(B);
   for (size_t i = 0; i < B; i++) h->rng[i].init_genrand(5489u + (uint32_t)i);

@@ -1,0 +1,622 @@
+// pmg_coop.cuh -- lane-cooperative env.step(): 8 lanes of a warp own ONE environment.
+//
+// Why: at the reference batch (8192 envs) a thread-per-env kernel is 256 warps on 592 warp schedulers,
+// each warp grinding through ~10 K dependent instructions per substep with its working set spilled to
+// L1-resident local memory (profiles/r01_*).  Here an environment is spread over the 8 lanes of an
+// "octet" (4 environments per warp, 2048 warps at batch 8192 = 3.5 warps per scheduler):
+//   * lane c = chain body c (link_1..link_7, gripper base); the link frames are an inclusive SCAN of
+//     rigid transforms over the lanes (3 shuffle levels instead of a 8-step serial recursion), the
+//     velocity / acceleration recursions are prefix sums, the composite-rigid-body inertias and the
+//     subtree wrenches are suffix sums (all about one common reference point, the gripper-base
+//     origin, so that they ARE plain sums);
+//   * the two fingers hang off the gripper base with the same orientation and are evaluated
+//     redundantly by every lane (cheaper than exchanging them);
+//   * lane r owns row r of the 9x9 joint-space inertia matrix (lane 7 owns the two finger rows); the
+//     inverse is an in-place Gauss-Jordan sweep with one row broadcast per pivot;
+//   * projected Gauss-Seidel: the delta-velocity vector is distributed over the lanes, the owner lane
+//     of a motor / limit row computes the impulse and broadcasts it (one shuffle per row); contact
+//     rows (finger-table) keep J and M^-1 J^T per lane in shared memory and reduce J.dv over the octet;
+//   * nothing lives in local memory: per-lane state is ~100 registers, exchange goes through shuffles
+//     and 3.3 KB of shared memory per environment.
+// The arithmetic is the same system the thread-per-env kernel (pmg_sim.cuh) and the oracle solve --
+// reference call sequence robots/kuka.py:167-225, envs/base_envs/base_env.py:215-219 -- organised for
+// lanes; the group primitives below are the only device-specific part, and tests/emu/ runs this very
+// source on the CPU (PMG_EMULATE) against the oracle.
+#pragma once
+
+#include "pmg_sim.cuh"
+
+namespace pmg {
+namespace coop {
+
+constexpr int GL = 8;        // lanes per environment
+constexpr int MAXPTS = 8;    // finger-table contact points: 2 pairs x 4
+constexpr int ROW_W = 24;    // floats per contact row record
+constexpr int R_J = 0, R_MJ = 9, R_RHS = 18, R_DINV = 19, R_DENOM = 20, R_APP = 21, R_MU = 22;
+constexpr int COOP_PAIRS = 2;
+
+struct __align__(16) EnvSmem {
+  float pub[7][12];                 // per arm dof: axis a, v = (p - Pref) x a, composite momentum n, l
+  float minv[84];                   // 9x9, row-major
+  float man[84];                    // persistent manifolds of the 2 finger-table pairs (2 x 41 words)
+  float rows[MAXPTS * 3][ROW_W];    // contact rows: J[9] MJ[9] rhs dinv denom app mu
+};
+
+// ---- the group (octet) interface ---------------------------------------------------------------
+struct Grp {
+  int lane;  // 0..7 inside the environment
+#ifdef PMG_EMULATE
+  __device__ float shfl(float v, int src) const { return pmg_emu::shfl(v, src); }
+  __device__ unsigned ballot(bool p) const { return pmg_emu::ballot(p); }
+  __device__ void sync() const { pmg_emu::sync(); }
+#else
+  unsigned mask;  // the octet's lanes inside the warp
+  int shift;      // first lane of the octet
+  __device__ __forceinline__ float shfl(float v, int src) const { return __shfl_sync(mask, v, src, GL); }
+  __device__ __forceinline__ unsigned ballot(bool p) const { return (__ballot_sync(mask, p) >> shift) & 0xffu; }
+  __device__ __forceinline__ void sync() const { __syncwarp(mask); }
+#endif
+  // value of lane - d (own value when there is no such lane) / lane + d / lane ^ m
+  __device__ __forceinline__ float up(float v, int d) const { return shfl(v, lane >= d ? lane - d : lane); }
+  __device__ __forceinline__ float down(float v, int d) const { return shfl(v, lane + d < GL ? lane + d : lane); }
+  __device__ __forceinline__ float bfly(float v, int m) const { return shfl(v, lane ^ m); }
+  __device__ __forceinline__ V3 shfl(V3 v, int src) const { return v3(shfl(v.x, src), shfl(v.y, src), shfl(v.z, src)); }
+  __device__ __forceinline__ V3 up(V3 v, int d) const { return v3(up(v.x, d), up(v.y, d), up(v.z, d)); }
+  __device__ __forceinline__ V3 down(V3 v, int d) const { return v3(down(v.x, d), down(v.y, d), down(v.z, d)); }
+  __device__ __forceinline__ M3 shfl(const M3& m, int src) const { M3 r; r.r0 = shfl(m.r0, src); r.r1 = shfl(m.r1, src); r.r2 = shfl(m.r2, src); return r; }
+  __device__ __forceinline__ M3 up(const M3& m, int d) const { M3 r; r.r0 = up(m.r0, d); r.r1 = up(m.r1, d); r.r2 = up(m.r2, d); return r; }
+  __device__ __forceinline__ float sum(float v) const { v += bfly(v, 4); v += bfly(v, 2); v += bfly(v, 1); return v; }
+  __device__ __forceinline__ float maxv(float v) const { v = fmaxf(v, bfly(v, 4)); v = fmaxf(v, bfly(v, 2)); v = fmaxf(v, bfly(v, 1)); return v; }
+  __device__ __forceinline__ V3 scan(V3 v) const {  // inclusive prefix sum over the lanes
+#pragma unroll
+    for (int d = 1; d < GL; d <<= 1) { V3 o = up(v, d); if (lane >= d) v += o; }
+    return v;
+  }
+  __device__ __forceinline__ float rscan(float v) const {  // inclusive suffix sum
+#pragma unroll
+    for (int d = 1; d < GL; d <<= 1) { float o = down(v, d); if (lane + d < GL) v += o; }
+    return v;
+  }
+  __device__ __forceinline__ V3 rscan(V3 v) const { return v3(rscan(v.x), rscan(v.y), rscan(v.z)); }
+};
+
+// ---- per-lane registers ----------------------------------------------------------------------------
+// Dof slots: slot 0 is arm joint `lane` on lanes 0..6 and finger1 (dof 7) on lane 7; slot 1 is finger2
+// (dof 8) on lane 7 and unused (zero) elsewhere.
+struct Lane {
+  M3 jrot; V3 jxyz, com, inertia;  // chain body `lane`: joint frame, COM, principal inertia
+  float mass, msub;                // own mass; mass of the subtree rooted here
+  float lower0, upper0, lower1, upper1, damp0;
+  float q0, q1, qd0, qd1, mt0, mt1, mi0, mi1, dtau0, dtau1;
+  int dof0;
+};
+
+__device__ __forceinline__ void load_lane_constants(const Grp& g, Lane& L) {
+  const int b = g.lane;  // chain body
+  L.jrot = load_jrot(b);
+  L.jxyz = v3(c_jxyz[b][0], c_jxyz[b][1], c_jxyz[b][2]);
+  L.com = v3(c_com[b][0], c_com[b][1], c_com[b][2]);
+  L.inertia = v3(c_inertia[b][0], c_inertia[b][1], c_inertia[b][2]);
+  L.mass = c_mass[b];
+  L.msub = g.rscan(L.mass + (b == 7 ? c_mass[PMG_BODY_FINGER1] + c_mass[PMG_BODY_FINGER2] : 0.0f));
+  L.dof0 = b;  // lane 7 -> dof 7
+  L.lower0 = c_dof_lower[b]; L.upper0 = c_dof_upper[b];
+  L.lower1 = c_dof_lower[8]; L.upper1 = c_dof_upper[8];
+  L.damp0 = c_dof_damping[b];
+}
+
+__device__ __forceinline__ Sym3 sym_add(const Sym3& a, const Sym3& b) {
+  Sym3 r; r.xx = a.xx + b.xx; r.xy = a.xy + b.xy; r.xz = a.xz + b.xz; r.yy = a.yy + b.yy; r.yz = a.yz + b.yz; r.zz = a.zz + b.zz; return r;
+}
+// R diag(i) R^T
+__device__ __forceinline__ Sym3 world_inertia(const M3& R, V3 i) {
+  V3 s0 = v3(R.r0.x * i.x, R.r0.y * i.y, R.r0.z * i.z), s1 = v3(R.r1.x * i.x, R.r1.y * i.y, R.r1.z * i.z), s2 = v3(R.r2.x * i.x, R.r2.y * i.y, R.r2.z * i.z);
+  Sym3 I;
+  I.xx = dot(s0, R.r0); I.xy = dot(s0, R.r1); I.xz = dot(s0, R.r2);
+  I.yy = dot(s1, R.r1); I.yz = dot(s1, R.r2); I.zz = dot(s2, R.r2);
+  return I;
+}
+// m (c.c 1 - c c^T)
+__device__ __forceinline__ Sym3 point_inertia(float m, V3 c) {
+  const float cc = dot(c, c);
+  Sym3 I;
+  I.xx = m * (cc - c.x * c.x); I.xy = -m * c.x * c.y; I.xz = -m * c.x * c.z;
+  I.yy = m * (cc - c.y * c.y); I.yz = -m * c.y * c.z; I.zz = m * (cc - c.z * c.z);
+  return I;
+}
+
+// Link frames of the chain: inclusive scan of (R, p) under composition.  qarm = joint angle (0 on lane 7).
+__device__ __forceinline__ void chain_fk(const Grp& g, const Lane& L, float qarm, M3& R, V3& p) {
+  float s, c;
+  sincosf(qarm, &s, &c);
+  const M3& J = L.jrot;  // J * Rz(q): new x column = c*x + s*y, new y column = -s*x + c*y
+  R.r0 = v3(c * J.r0.x + s * J.r0.y, -s * J.r0.x + c * J.r0.y, J.r0.z);
+  R.r1 = v3(c * J.r1.x + s * J.r1.y, -s * J.r1.x + c * J.r1.y, J.r1.z);
+  R.r2 = v3(c * J.r2.x + s * J.r2.y, -s * J.r2.x + c * J.r2.y, J.r2.z);
+  p = L.jxyz;
+#pragma unroll
+  for (int d = 1; d < GL; d <<= 1) {
+    M3 Ro = g.up(R, d);
+    V3 po = g.up(p, d);
+    if (g.lane >= d) { p = po + mul(Ro, p); R = mul(Ro, R); }
+  }
+}
+
+// ---- inverse kinematics (same iteration as pmg_physics.cuh::inverse_kinematics) ---------------------
+// Lane j owns column j of the tip Jacobian and row j of J^T J + 0.5 I; the 7x7 system is solved by
+// Gauss-Jordan elimination with one row broadcast per pivot.  Returns this lane's joint angle.
+__device__ float inverse_kinematics(const Grp& g, const Lane& L, float qarm, V3 target, const float tq[4]) {
+  const int lane = g.lane;
+  const bool arm = lane < 7;
+  const float t[3] = PMG_TIP_OFFSET;
+  float diff = 1e30f;
+  for (int it = 0; it < 40 && diff > 1e-5f; it++) {
+    M3 R; V3 p;
+    chain_fk(g, L, qarm, R, p);
+    M3 R6 = g.shfl(R, PMG_BODY_LINK7);
+    V3 p6 = g.shfl(p, PMG_BODY_LINK7);
+    V3 tip = p6 + mul(R6, v3(t[0], t[1], t[2]));
+    V3 ep = target - tip;
+    diff = norm(ep);
+    float qc[4];
+    m3_to_quat(R6, qc);
+    float ax = -qc[0], ay = -qc[1], az = -qc[2], aw = qc[3];
+    float dx = tq[3] * ax + tq[0] * aw + tq[1] * az - tq[2] * ay;
+    float dy = tq[3] * ay + tq[1] * aw + tq[2] * ax - tq[0] * az;
+    float dz = tq[3] * az + tq[2] * aw + tq[0] * ay - tq[1] * ax;
+    float dw = tq[3] * aw - tq[0] * ax - tq[1] * ay - tq[2] * az;
+    float vn2 = dx * dx + dy * dy + dz * dz;
+    V3 er;
+    if (vn2 < 10.0f * 2.220446049250313e-16f) {
+      float ang = 2.0f * atan2f(sqrtf(vn2), dw);
+      if (ang > PI_F) ang -= 2.0f * PI_F;
+      er = v3(ang, 0, 0);
+    } else {
+      float vn = sqrtf(vn2);
+      float ang = 2.0f * atan2f(vn, dw);
+      if (ang > PI_F) ang -= 2.0f * PI_F;
+      float sc = ang / vn;
+      er = v3(dx * sc, dy * sc, dz * sc);
+    }
+    V3 a = arm ? col(R, 2) : v3(0, 0, 0);
+    V3 Jl = cross(a, tip - p), Ja = a;
+    float A[7];
+#pragma unroll
+    for (int j = 0; j < 7; j++) {
+      V3 Jlj = g.shfl(Jl, j), Jaj = g.shfl(Ja, j);
+      A[j] = dot(Jl, Jlj) + dot(Ja, Jaj) + (j == lane ? IK_JOINT_DAMPING : 0.0f);
+    }
+    float rhs = dot(Jl, ep) + dot(Ja, er);
+#pragma unroll
+    for (int k = 0; k < 7; k++) {
+      float rk[7];
+#pragma unroll
+      for (int j = k; j < 7; j++) rk[j] = g.shfl(A[j], k);
+      const float rr = g.shfl(rhs, k);
+      const float pinv = 1.0f / rk[k];
+      const bool own = lane == k;
+      const float f = own ? -pinv : A[k] * pinv;
+#pragma unroll
+      for (int j = k + 1; j < 7; j++) A[j] = (own ? 0.0f : A[j]) - f * rk[j];
+      rhs = (own ? 0.0f : rhs) - f * rr;
+    }
+    const float mx = g.maxv(fabsf(rhs));
+    const float scale = mx > IK_MAX_STEP ? IK_MAX_STEP / mx : 1.0f;
+    if (arm) qarm += scale * rhs;
+  }
+  return qarm;
+}
+
+// ---- solver state of a lane -----------------------------------------------------------------------
+struct SolverLane {
+  float rhs0, rhs1, lim0, lim1, app0, app1, dinv0, dinv1, mdd0, mdd1;
+  float lrhs00, lrhs01, lrhs10, lrhs11;  // [slot][side]
+  float lapp00, lapp01, lapp10, lapp11;
+  float dqd0, dqd1, res;
+};
+
+template <int K>
+__device__ __forceinline__ void motor_row(const Grp& g, SolverLane& s, const float* A0, const float* A1) {
+  constexpr int d = nc_dof(K);
+  constexpr int owner = d < 8 ? d : 7;
+  constexpr bool slot1 = d == 8;
+  const float rhs = slot1 ? s.rhs1 : s.rhs0, cur = slot1 ? s.dqd1 : s.dqd0, dinv = slot1 ? s.dinv1 : s.dinv0;
+  const float app = slot1 ? s.app1 : s.app0, lim = slot1 ? s.lim1 : s.lim0, mdd = slot1 ? s.mdd1 : s.mdd0;
+  float dlc = rhs - cur * dinv;
+  const float sum = fminf(fmaxf(app + dlc, -lim), lim);
+  dlc = sum - app;
+  const bool own = g.lane == owner;
+  if (slot1) s.app1 = own ? sum : s.app1; else s.app0 = own ? sum : s.app0;
+  const float rr = dlc * mdd;
+  s.res = own ? fmaxf(s.res, rr * rr) : s.res;
+  const float dl = g.shfl(dlc, owner);
+  s.dqd0 += A0[d] * dl;
+  s.dqd1 += A1[d] * dl;
+}
+
+// limit row in slot s (visit position s>>1, side s&1); data-dependent => dynamic dof, M^-1 from shared memory
+__device__ __forceinline__ void limit_row(const Grp& g, SolverLane& s, const EnvSmem& sm, int slot_id, int dof0) {
+  const int d = c_nc_order[ND + (slot_id >> 1)];
+  const bool side = (slot_id & 1) != 0, slot1 = d == 8;
+  const int owner = d < 8 ? d : 7;
+  const float sign = side ? -1.0f : 1.0f;
+  const float lr = slot1 ? (side ? s.lrhs11 : s.lrhs10) : (side ? s.lrhs01 : s.lrhs00);
+  const float la = slot1 ? (side ? s.lapp11 : s.lapp10) : (side ? s.lapp01 : s.lapp00);
+  const float cur = slot1 ? s.dqd1 : s.dqd0, dinv = slot1 ? s.dinv1 : s.dinv0, mdd = slot1 ? s.mdd1 : s.mdd0;
+  float dlc = lr - sign * cur * dinv;
+  const float sum = fminf(fmaxf(la + dlc, 0.0f), LIMIT_MAX_IMPULSE);
+  dlc = sum - la;
+  if (g.lane == owner) {
+    if (slot1) { if (side) s.lapp11 = sum; else s.lapp10 = sum; }
+    else { if (side) s.lapp01 = sum; else s.lapp00 = sum; }
+    const float rr = dlc * mdd;
+    s.res = fmaxf(s.res, rr * rr);
+  }
+  const float sdl = sign * g.shfl(dlc, owner);
+  s.dqd0 += sm.minv[d * 9 + dof0] * sdl;
+  s.dqd1 += sm.minv[d * 9 + 8] * sdl;
+}
+
+__device__ __forceinline__ void limit_rows(const Grp& g, SolverLane& s, const EnvSmem& sm, unsigned lact, bool forward, int dof0) {
+  unsigned todo = lact;
+  while (todo) {
+    const int id = forward ? __ffs(todo) - 1 : 31 - __clz(todo);
+    todo &= ~(1u << id);
+    limit_row(g, s, sm, id, dof0);
+  }
+}
+
+// ---- one 2 ms substep ---------------------------------------------------------------------------------
+__device__ void substep(const Grp& g, EnvSmem& sm, Lane& L) {
+  const int lane = g.lane;
+  const bool arm = lane < 7, hand = lane == 7;
+  // 1. link frames (scan), joint axes
+  M3 R; V3 p;
+  chain_fk(g, L, arm ? L.q0 : 0.0f, R, p);
+  const V3 a = arm ? col(R, 2) : v3(0, 0, 0);
+  const V3 Pref = g.shfl(p, 7);  // gripper-base origin: reference point of every moment below
+  // 2. velocities and zero-qdd accelerations as prefix sums
+  const V3 aq = L.qd0 * a;
+  const V3 w = g.scan(aq), wp = w - aq;
+  const V3 tal = cross(wp, aq);
+  const V3 al = g.scan(tal), alp = al - tal;
+  V3 pprev = g.up(p, 1);
+  if (lane == 0) pprev = v3(0, 0, 0);
+  const V3 r = p - pprev;
+  const V3 wxr = cross(wp, r);
+  const V3 vo = g.scan(wxr);
+  V3 ao = g.scan(cross(alp, r) + cross(wp, wxr));
+  ao.z += GRAVITY;
+  // 3. Newton-Euler of the lane's own body about its COM (Bullet's link damping as an external force)
+  V3 Fs, Ns, hs;
+  Sym3 Is;
+  {
+    const V3 rc = mul(R, L.com);
+    const Sym3 Iw = world_inertia(R, L.inertia);
+    const V3 wxrc = cross(w, rc);
+    const V3 a_c = ao + cross(al, rc) + cross(w, wxrc);
+    const V3 v_c = vo + wxrc;
+    const float kl = LINK_DAMPING + LINK_DAMPING * norm(v_c), ka = LINK_DAMPING + LINK_DAMPING * norm(w);
+    const V3 Fc = L.mass * a_c + (L.mass * kl) * v_c;
+    const V3 Iww = mul(Iw, w);
+    const V3 Nc = mul(Iw, al) + cross(w, Iww) + ka * Iww;
+    const V3 c = (p - Pref) + rc;
+    Fs = Fc; Ns = Nc + cross(c, Fc); hs = L.mass * c;
+    Is = sym_add(Iw, point_inertia(L.mass, c));
+  }
+  // 3b. the two fingers (same orientation as the gripper base, zero COM offset), by every lane
+  const M3 Rg = g.shfl(R, 7);
+  const V3 wg = g.shfl(w, 7), alg = g.shfl(al, 7), aog = g.shfl(ao, 7), vog = g.shfl(vo, 7);
+  const float qf1 = g.shfl(L.q0, 7), qf2 = g.shfl(L.q1, 7), qdf1 = g.shfl(L.qd0, 7), qdf2 = g.shfl(L.qd1, 7);
+  const V3 ay = col(Rg, 1);
+  const V3 ax1 = -ay, ax2 = ay;  // prismatic axes (0,-1,0) / (0,+1,0) of the gripper base
+  const float mf = c_mass[PMG_BODY_FINGER1];
+  V3 r1, r2, F1, F2, nf1, lf1, nf2, lf2;
+  {
+    r1 = mul(Rg, v3(c_jxyz[PMG_BODY_FINGER1][0], c_jxyz[PMG_BODY_FINGER1][1], c_jxyz[PMG_BODY_FINGER1][2])) + qf1 * ax1;
+    r2 = mul(Rg, v3(c_jxyz[PMG_BODY_FINGER2][0], c_jxyz[PMG_BODY_FINGER2][1], c_jxyz[PMG_BODY_FINGER2][2])) + qf2 * ax2;
+    const V3 aq1 = qdf1 * ax1, aq2 = qdf2 * ax2;
+    const V3 wxr1 = cross(wg, r1), wxr2 = cross(wg, r2);
+    const V3 a1 = aog + cross(alg, r1) + cross(wg, wxr1) + 2.0f * cross(wg, aq1);
+    const V3 a2 = aog + cross(alg, r2) + cross(wg, wxr2) + 2.0f * cross(wg, aq2);
+    const V3 v1 = vog + wxr1 + aq1, v2 = vog + wxr2 + aq2;
+    const float kl1 = LINK_DAMPING + LINK_DAMPING * norm(v1), kl2 = LINK_DAMPING + LINK_DAMPING * norm(v2);
+    F1 = mf * a1 + (mf * kl1) * v1;
+    F2 = mf * a2 + (mf * kl2) * v2;
+    const Sym3 Iwf = world_inertia(Rg, v3(c_inertia[PMG_BODY_FINGER1][0], c_inertia[PMG_BODY_FINGER1][1], c_inertia[PMG_BODY_FINGER1][2]));
+    const float ka = LINK_DAMPING + LINK_DAMPING * norm(wg);
+    const V3 Iww = mul(Iwf, wg);
+    const V3 Ncf = mul(Iwf, alg) + cross(wg, Iww) + ka * Iww;
+    // momentum of a unit finger velocity about Pref: l = m ax, n = m r x ax
+    lf1 = mf * ax1; nf1 = mf * cross(r1, ax1);
+    lf2 = mf * ax2; nf2 = mf * cross(r2, ax2);
+    if (hand) {  // the gripper base carries its fingers
+      Fs += F1 + F2;
+      Ns += Ncf + Ncf + cross(r1, F1) + cross(r2, F2);
+      hs += mf * (r1 + r2);
+      Is = sym_add(Is, sym_add(sym_add(Iwf, Iwf), sym_add(point_inertia(mf, r1), point_inertia(mf, r2))));
+    }
+  }
+  const V3 pf1 = Pref + r1, pf2 = Pref + r2;
+  // collision detection of the two finger-table pairs: lane k runs pair k on the shared-memory manifold
+  if (lane < COOP_PAIRS) {
+    ManRef mr; mr.man = sm.man; mr.stride = 1;
+    const float tc[3] = PMG_TABLE_CENTER, th[3] = PMG_TABLE_HALF, fh[3] = PMG_FINGER_HALF;
+    collide_pair(mr, lane, lane == 0 ? pf1 : pf2, Rg, v3(fh[0], fh[1], fh[2]), v3(tc[0], tc[1], tc[2]), m3_identity(), v3(th[0], th[1], th[2]));
+  }
+  // 4. subtree wrenches and composite inertias: suffix sums over the chain
+  Fs = g.rscan(Fs); Ns = g.rscan(Ns); hs = g.rscan(hs);
+  Is.xx = g.rscan(Is.xx); Is.xy = g.rscan(Is.xy); Is.xz = g.rscan(Is.xz);
+  Is.yy = g.rscan(Is.yy); Is.yz = g.rscan(Is.yz); Is.zz = g.rscan(Is.zz);
+  // 5. joint-space inertia matrix rows and bias forces
+  const V3 vv = cross(p - Pref, a);  // velocity of the reference point per unit joint rate
+  const V3 n_own = arm ? mul(Is, a) + cross(hs, vv) : nf1;
+  const V3 l_own = arm ? L.msub * vv + cross(a, hs) : lf1;
+  const float b0 = arm ? dot(a, Ns) + dot(vv, Fs) : dot(ax1, F1);
+  const float b1 = dot(ax2, F2);
+  if (arm) {
+    float* pb = sm.pub[lane];
+    pb[0] = a.x; pb[1] = a.y; pb[2] = a.z; pb[3] = vv.x; pb[4] = vv.y; pb[5] = vv.z;
+    pb[6] = n_own.x; pb[7] = n_own.y; pb[8] = n_own.z; pb[9] = l_own.x; pb[10] = l_own.y; pb[11] = l_own.z;
+  }
+  g.sync();
+  float A0[ND], A1[ND];
+#pragma unroll
+  for (int j = 0; j < 7; j++) {
+    const float* pb = sm.pub[j];
+    const V3 aj = v3(pb[0], pb[1], pb[2]), vj = v3(pb[3], pb[4], pb[5]), nj = v3(pb[6], pb[7], pb[8]), lj = v3(pb[9], pb[10], pb[11]);
+    const float lo = dot(aj, n_own) + dot(vj, l_own);  // j <= own dof: the own subtree carries joint j's motion
+    const float hi = dot(a, nj) + dot(vv, lj);
+    A0[j] = j <= lane ? lo : hi;
+    A1[j] = dot(aj, nf2) + dot(vj, lf2);
+  }
+  A0[7] = arm ? dot(a, nf1) + dot(vv, lf1) : mf;
+  A0[8] = arm ? dot(a, nf2) + dot(vv, lf2) : 0.0f;  // the fingers are siblings
+  A1[7] = 0.0f; A1[8] = mf;
+  // 6. M^-1 by Gauss-Jordan sweeps, row k broadcast from its owner (lane 7 owns rows 7 and 8)
+#pragma unroll
+  for (int k = 0; k < ND; k++) {
+    const int src = k < 8 ? k : 7;
+    float rk[ND];
+#pragma unroll
+    for (int j = 0; j < ND; j++) rk[j] = g.shfl(k == 8 ? A1[j] : A0[j], src);
+    const float pinv = 1.0f / rk[k];
+    const bool own0 = lane == src && k != 8, own1 = lane == src && k == 8;
+    const float f0 = own0 ? -pinv : A0[k] * pinv, f1 = own1 ? -pinv : A1[k] * pinv;
+#pragma unroll
+    for (int j = 0; j < ND; j++) {
+      if (j == k) continue;
+      A0[j] = (own0 ? 0.0f : A0[j]) - f0 * rk[j];
+      A1[j] = (own1 ? 0.0f : A1[j]) - f1 * rk[j];
+    }
+    A0[k] = -f0; A1[k] = -f1;
+  }
+#pragma unroll
+  for (int j = 0; j < ND; j++) {
+    sm.minv[L.dof0 * 9 + j] = A0[j];
+    if (hand) sm.minv[8 * 9 + j] = A1[j];
+  }
+  // 7. unconstrained velocity update: qd += dt * M^-1 (tau_damping - bias)
+  {
+    const float t0 = L.dtau0 - b0, t1 = L.dtau1 - b1;
+    float s0 = 0.0f, s1 = 0.0f;
+#pragma unroll
+    for (int j = 0; j < ND; j++) {
+      const float tj = j < 8 ? g.shfl(t0, j) : g.shfl(t1, 7);
+      s0 += A0[j] * tj; s1 += A1[j] * tj;
+    }
+    L.qd0 = fminf(fmaxf(L.qd0 + s0 * DT, -MAX_COORD_VEL), MAX_COORD_VEL);
+    L.qd1 = hand ? fminf(fmaxf(L.qd1 + s1 * DT, -MAX_COORD_VEL), MAX_COORD_VEL) : 0.0f;
+  }
+  g.sync();  // minv and the manifolds are visible to the whole octet
+  // 8. constraint rows
+  SolverLane s;
+  unsigned lact = 0;
+  {
+    s.mdd0 = sm.minv[L.dof0 * 10]; s.mdd1 = A1[8];
+    s.dinv0 = 1.0f / s.mdd0; s.dinv1 = 1.0f / s.mdd1;
+    // btMultiBodyJointMotor in POSITION_CONTROL (kuka.py:282-301)
+    const float tv0 = MOTOR_KP * (L.mt0 - L.q0) * INV_DT + L.qd0 + MOTOR_KD * (0.0f - L.qd0);
+    const float tv1 = MOTOR_KP * (L.mt1 - L.q1) * INV_DT + L.qd1 + MOTOR_KD * (0.0f - L.qd1);
+    s.rhs0 = (tv0 - L.qd0) * s.dinv0; s.rhs1 = (tv1 - L.qd1) * s.dinv1;
+    s.lim0 = L.mi0; s.lim1 = L.mi1; s.app0 = s.app1 = 0.0f;
+    // btMultiBodyJointLimitConstraint rows, only when violated
+    const float p00 = L.q0 - L.lower0, p01 = L.upper0 - L.q0, p10 = L.q1 - L.lower1, p11 = L.upper1 - L.q1;
+    const bool v00 = !(p00 > 0.0f), v01 = !(p01 > 0.0f), v10 = hand && !(p10 > 0.0f), v11 = hand && !(p11 > 0.0f);
+    s.lrhs00 = ((p00 > SPLIT_IMPULSE_PEN_THRESHOLD ? -p00 * CONTACT_ERP * INV_DT : 0.0f) - L.qd0) * s.dinv0;
+    s.lrhs01 = ((p01 > SPLIT_IMPULSE_PEN_THRESHOLD ? -p01 * CONTACT_ERP * INV_DT : 0.0f) + L.qd0) * s.dinv0;
+    s.lrhs10 = ((p10 > SPLIT_IMPULSE_PEN_THRESHOLD ? -p10 * CONTACT_ERP * INV_DT : 0.0f) - L.qd1) * s.dinv1;
+    s.lrhs11 = ((p11 > SPLIT_IMPULSE_PEN_THRESHOLD ? -p11 * CONTACT_ERP * INV_DT : 0.0f) + L.qd1) * s.dinv1;
+    s.lapp00 = s.lapp01 = s.lapp10 = s.lapp11 = 0.0f;
+    const unsigned m00 = g.ballot(v00), m01 = g.ballot(v01), m10 = g.ballot(v10), m11 = g.ballot(v11);
+    if (m00 | m01 | m10 | m11) {
+#pragma unroll
+      for (int k = 0; k < ND; k++) {
+        const int d = nc_dof(k);
+        const unsigned lo = d < 8 ? (m00 >> d) & 1u : (m10 >> 7) & 1u, hi = d < 8 ? (m01 >> d) & 1u : (m11 >> 7) & 1u;
+        lact |= (lo << (2 * k)) | (hi << (2 * k + 1));
+      }
+    }
+    s.dqd0 = s.dqd1 = 0.0f;
+  }
+  // contact rows: one normal + two tangents per cached manifold point of the finger-table pairs
+  int nrow = 0;
+  {
+    const float tc[3] = PMG_TABLE_CENTER;
+    const float mu = (float)PMG_FINGER_FRICTION * (float)PMG_TABLE_FRICTION;
+    for (int k = 0; k < COOP_PAIRS; k++) {
+      const int n = __float_as_int(sm.man[k * MAN_WORDS]);
+      const V3 pf = k == 0 ? pf1 : pf2;
+      for (int i = 0; i < n; i++) {
+        const float* mp = sm.man + k * MAN_WORDS + 1 + 10 * i;
+        const V3 lA = v3(mp[0], mp[1], mp[2]), nB = v3(mp[6], mp[7], mp[8]);
+        const float dist = mp[9];
+        const V3 wa = mul(Rg, lA) + pf;
+        V3 dirs[3];
+        dirs[0] = nB;
+        plane_space(nB, dirs[1], dirs[2]);
+        // velocity of the contact point per unit rate of the lane's dofs
+        const V3 Jp0 = arm ? cross(a, wa - p) : (k == 0 ? ax1 : v3(0, 0, 0));
+        const V3 Jp1 = (hand && k == 1) ? ax2 : v3(0, 0, 0);
+#pragma unroll
+        for (int kk = 0; kk < 3; kk++) {
+          const V3 d = dirs[kk];
+          const float J0 = dot(d, Jp0), J1 = dot(d, Jp1);
+          float MJ0 = 0.0f, MJ1 = 0.0f;
+#pragma unroll
+          for (int j = 0; j < ND; j++) {
+            const float Jj = j < 8 ? g.shfl(J0, j) : g.shfl(J1, 7);
+            MJ0 += A0[j] * Jj; MJ1 += A1[j] * Jj;
+          }
+          if (!hand) MJ1 = 0.0f;
+          const float denom = g.sum(J0 * MJ0 + J1 * MJ1);
+          const float rel_vel = g.sum(J0 * L.qd0 + J1 * L.qd1);
+          const float dinv = 1.0f / denom;
+          float rhs;
+          if (kk == 0) {
+            const float pen = dist + LINEAR_SLOP;
+            float pos_err = 0.0f, vel_err = -rel_vel;
+            if (pen > 0.0f) vel_err -= pen * INV_DT; else pos_err = -pen * CONTACT_ERP * INV_DT;
+            rhs = (pos_err + vel_err) * dinv;
+          } else rhs = -rel_vel * dinv;
+          float* row = sm.rows[nrow * 3 + kk];
+          row[R_J + L.dof0] = J0; row[R_MJ + L.dof0] = MJ0;
+          if (hand) { row[R_J + 8] = J1; row[R_MJ + 8] = MJ1; }
+          if (lane == 0) { row[R_RHS] = rhs; row[R_DINV] = dinv; row[R_DENOM] = denom; row[R_APP] = 0.0f; row[R_MU] = mu; }
+        }
+        nrow++;
+      }
+    }
+    if (nrow) g.sync();
+  }
+  // projected Gauss-Seidel: <= 5 iterations, early exit on the largest squared velocity change
+  for (int it = 0; it < SOLVER_ITERS; it++) {
+    s.res = 0.0f;
+    if (it & 1) {  // forwards on odd iterations, backwards on even (Bullet's interleaving)
+      motor_row<0>(g, s, A0, A1); motor_row<1>(g, s, A0, A1); motor_row<2>(g, s, A0, A1);
+      motor_row<3>(g, s, A0, A1); motor_row<4>(g, s, A0, A1); motor_row<5>(g, s, A0, A1);
+      motor_row<6>(g, s, A0, A1); motor_row<7>(g, s, A0, A1); motor_row<8>(g, s, A0, A1);
+      limit_rows(g, s, sm, lact, true, L.dof0);
+    } else {
+      limit_rows(g, s, sm, lact, false, L.dof0);
+      motor_row<8>(g, s, A0, A1); motor_row<7>(g, s, A0, A1); motor_row<6>(g, s, A0, A1);
+      motor_row<5>(g, s, A0, A1); motor_row<4>(g, s, A0, A1); motor_row<3>(g, s, A0, A1);
+      motor_row<2>(g, s, A0, A1); motor_row<1>(g, s, A0, A1); motor_row<0>(g, s, A0, A1);
+    }
+    float cres = 0.0f;  // contact rows: every lane computes the same impulse
+    for (int c = 0; c < nrow; c++) {
+      float* row = sm.rows[c * 3];
+      const float v = g.sum(row[R_J + L.dof0] * s.dqd0 + (hand ? row[R_J + 8] * s.dqd1 : 0.0f));
+      const float app = row[R_APP];
+      float dl = row[R_RHS] - v * row[R_DINV];
+      const float sum = fminf(fmaxf(app + dl, 0.0f), 1e10f);
+      dl = sum - app;
+      g.sync();  // every lane has read the old impulse
+      if (lane == 0) row[R_APP] = sum;
+      s.dqd0 += row[R_MJ + L.dof0] * dl;
+      if (hand) s.dqd1 += row[R_MJ + 8] * dl;
+      const float rr = dl * row[R_DENOM];
+      cres = fmaxf(cres, rr * rr);
+    }
+    if (nrow) g.sync();
+    for (int c = 0; c < nrow; c++) {  // implicit friction cone: both tangent rows of a point together
+      const float total = sm.rows[c * 3][R_APP];
+      if (!(total > 0.0f)) continue;
+      float* ra = sm.rows[c * 3 + 1];
+      float* rb = sm.rows[c * 3 + 2];
+      const float lim = ra[R_MU] * total;
+      const float vA = g.sum(ra[R_J + L.dof0] * s.dqd0 + (hand ? ra[R_J + 8] * s.dqd1 : 0.0f));
+      const float vB = g.sum(rb[R_J + L.dof0] * s.dqd0 + (hand ? rb[R_J + 8] * s.dqd1 : 0.0f));
+      const float appA = ra[R_APP], appB = rb[R_APP];
+      float dA = ra[R_RHS] - vA * ra[R_DINV], dB = rb[R_RHS] - vB * rb[R_DINV];
+      float sA = appA + dA, sB = appB + dB;
+      const float s2 = sA * sA + sB * sB;
+      if (s2 >= lim * lim) {
+        const float sc = s2 > 0.0f ? lim * rsqrtf(s2) : 0.0f;
+        const float cA = fabsf(sA) * sc, cB = s2 > 0.0f ? fabsf(sB) * sc : lim;
+        sA = fminf(fmaxf(sA, -cA), cA);
+        sB = fminf(fmaxf(sB, -cB), cB);
+        dA = sA - appA; dB = sB - appB;
+      }
+      g.sync();
+      if (lane == 0) { ra[R_APP] = sA; rb[R_APP] = sB; }
+      s.dqd0 += ra[R_MJ + L.dof0] * dA + rb[R_MJ + L.dof0] * dB;
+      if (hand) s.dqd1 += ra[R_MJ + 8] * dA + rb[R_MJ + 8] * dB;
+      const float r1_ = dA * ra[R_DENOM], r2_ = dB * rb[R_DENOM];
+      cres = fmaxf(cres, fmaxf(r1_ * r1_, r2_ * r2_));
+    }
+    if (nrow) g.sync();
+    const float res = g.maxv(fmaxf(s.res, cres));
+    if (res <= RESIDUAL_THRESHOLD) break;
+  }
+  // 9. semi-implicit Euler
+  L.qd0 = fminf(fmaxf(L.qd0 + s.dqd0, -MAX_COORD_VEL), MAX_COORD_VEL);
+  L.qd1 = hand ? fminf(fmaxf(L.qd1 + s.dqd1, -MAX_COORD_VEL), MAX_COORD_VEL) : 0.0f;
+  L.q0 += L.qd0 * DT;
+  L.q1 += L.qd1 * DT;
+}
+
+// ---- one env.step() of a Reach environment (TASK 0, no blocks) -------------------------------------
+// `env` is the environment index, state / manifold are the same [word][env] arrays the thread-per-env
+// kernels use, so reset_kernel, pmg_get_state / pmg_set_state and the reward path are shared.
+__device__ void step_env_reach(const Grp& g, EnvSmem& sm, const StepIO& io, int env) {
+  using D = Dims<0, 0>;
+  const int lane = g.lane;
+  const bool arm = lane < 7, hand = lane == 7;
+  const size_t B = io.batch;
+  float* s = io.state + env;
+  Lane L;
+  load_lane_constants(g, L);
+  L.q0 = s[(ST_Q + lane) * B]; L.qd0 = s[(ST_QD + lane) * B]; L.mt0 = s[(ST_MT + lane) * B]; L.mi0 = s[(ST_MI + lane) * B];
+  L.q1 = hand ? s[(ST_Q + 8) * B] : 0.0f; L.qd1 = hand ? s[(ST_QD + 8) * B] : 0.0f;
+  L.mt1 = hand ? s[(ST_MT + 8) * B] : 0.0f; L.mi1 = hand ? s[(ST_MI + 8) * B] : 0.0f;
+  L.dtau0 = L.dtau1 = 0.0f;
+  for (int w = lane; w < COOP_PAIRS * MAN_WORDS; w += GL) sm.man[w] = io.manifold[(size_t)w * B + env];
+  // ---- Kuka.apply_action (kuka.py:167-222) ----
+  const float lo[3] = {-0.67f, -0.20f, 0.175f}, hi[3] = {-0.37f, 0.20f, 0.55f};  // kuka.py:40-41
+  float ee[3];
+#pragma unroll
+  for (int k = 0; k < 3; k++) ee[k] = fminf(fmaxf(s[(ST_EE + k) * B] + io.action[(size_t)env * D::A + k] * 0.01f, lo[k]), hi[k]);
+  {
+    const float tq[4] = {0.f, -1.f, 0.f, 0.f};  // kuka.py:42
+    const float qik = inverse_kinematics(g, L, arm ? L.q0 : 0.0f, v3(ee[0], ee[1], ee[2]), tq);
+    if (arm) { L.mt0 = qik; L.mi0 = ARM_FORCE * OUTER_DT; }
+  }
+  g.sync();
+  // ---- 5 x stepSimulation (kuka.py:223-225), each 20 substeps of 2 ms ----
+  for (int call = 0; call < CALLS_PER_ENV_STEP; call++) {
+    L.dtau0 = -L.damp0 * L.qd0;  // joint damping torque, sampled once per stepSimulation call
+    L.dtau1 = 0.0f;
+    for (int sub = 0; sub < SUBSTEPS_PER_CALL; sub++) substep(g, sm, L);
+  }
+  // ---- observation, reward, flags (kuka_single_step_base_env.py:193-244) ----
+  M3 R; V3 p;
+  chain_fk(g, L, arm ? L.q0 : 0.0f, R, p);
+  s[(ST_Q + lane) * B] = L.q0; s[(ST_QD + lane) * B] = L.qd0; s[(ST_MT + lane) * B] = L.mt0; s[(ST_MI + lane) * B] = L.mi0;
+  if (hand) { s[(ST_Q + 8) * B] = L.q1; s[(ST_QD + 8) * B] = L.qd1; s[(ST_MT + 8) * B] = L.mt1; s[(ST_MI + 8) * B] = L.mi1; }
+  g.sync();
+  for (int w = lane; w < COOP_PAIRS * MAN_WORDS; w += GL) io.manifold[(size_t)w * B + env] = sm.man[w];
+  if (lane == PMG_BODY_LINK7) {
+    const float t[3] = PMG_TIP_OFFSET;
+    const V3 tip = p + mul(R, v3(t[0], t[1], t[2]));
+    float* row = io.obs + (size_t)env * D::W;
+    const float* goal = io.state + (size_t)(ST_BLK) * B + env;
+    const float g0 = goal[0], g1 = goal[B], g2 = goal[2 * B];
+    row[0] = row[3] = row[6] = tip.x; row[1] = row[4] = row[7] = tip.y; row[2] = row[5] = row[8] = tip.z;
+    row[9] = g0; row[10] = g1; row[11] = g2;
+    const float dx = tip.x - g0, dy = tip.y - g1, dz = tip.z - g2;
+    const float dist = sqrtf(dx * dx + dy * dy + dz * dz);
+#pragma unroll
+    for (int k = 0; k < 3; k++) s[(ST_EE + k) * B] = ee[k];
+    float* el = s + (size_t)(D::STATE - 1) * B;
+    const int elapsed = (int)(*el) + 1;
+    *el = (float)elapsed;
+    const bool na = dist > io.thr;
+    io.reward[env] = io.binary ? -(na ? 1.0f : 0.0f) : -dist;
+    io.success[env] = na ? 0 : 1;
+    io.done[env] = elapsed >= io.max_steps ? 1 : 0;
+  }
+}
+
+}  // namespace coop
+}  // namespace pmg

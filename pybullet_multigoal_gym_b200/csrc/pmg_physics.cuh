@@ -20,7 +20,11 @@
 // blocks (the 9 motor rows, the 9x9 Cholesky) are unrolled in registers.
 #pragma once
 
+#ifdef PMG_EMULATE
+#include "pmg_emu_shim.h"  // host build of the same device code (tests/emu): CUDA keywords and intrinsics as plain C++
+#else
 #include <cuda_runtime.h>
+#endif
 #include <float.h>
 #include <math.h>
 #include <stdint.h>

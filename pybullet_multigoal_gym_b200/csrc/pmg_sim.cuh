@@ -8,6 +8,8 @@
 // or two 128-byte lines.
 #pragma once
 
+#include <stddef.h>
+
 #include "pmg_physics.cuh"
 
 namespace pmg {
@@ -55,17 +57,22 @@ __device__ __forceinline__ float geom_friction(int kind) {
   return (float)PMG_FINGER_FRICTION;
 }
 
+// Where one environment's persistent manifolds live: global memory ([word][env], stride = batch) for the
+// thread-per-env kernels, a shared-memory copy (stride 1) for the lane-cooperative kernel (pmg_coop.cuh).
+struct ManRef {
+  float* man;      // this env's first manifold word
+  size_t stride;   // distance between consecutive words
+  __device__ __forceinline__ float& mw(int pair, int w) { return man[(size_t)(pair * MAN_WORDS + w) * stride]; }
+};
+
 template <int NBLK>
-struct Env {
+struct Env : ManRef {
   static constexpr int NBA = NBLK > 0 ? NBLK : 1;
   float q[ND], qd[ND], mt[ND], mi[ND], dtau[ND];
   V3 bpos[NBA], bv[NBA], bw[NBA];
   float bquat[NBA][4];
   M3 bR[NBA];
-  float* man;      // this env's first manifold word
-  size_t stride;   // = batch
   int overflow;
-  __device__ __forceinline__ float& mw(int pair, int w) { return man[(size_t)(pair * MAN_WORDS + w) * stride]; }
 };
 
 template <int NBLK>
@@ -79,8 +86,7 @@ __device__ __forceinline__ void geom_pose(const Env<NBLK>& e, const Frames& f, i
 }
 
 // ---- collision detection + persistent manifolds (btPersistentManifold semantics) -----------
-template <int NBLK>
-__device__ void manifold_add(Env<NBLK>& e, int k, float thr, V3 lA, V3 lB, V3 nB, float dist) {
+__device__ void manifold_add(ManRef& e, int k, float thr, V3 lA, V3 lB, V3 nB, float dist) {
   int n = __float_as_int(e.mw(k, 0));
   float shortest = thr * thr;
   int nearest = -1;
@@ -115,6 +121,50 @@ __device__ void manifold_add(Env<NBLK>& e, int k, float thr, V3 lA, V3 lB, V3 nB
   e.mw(k, o + 9) = dist;
 }
 
+// btPersistentManifold::refreshContactPoints: drop points that separated or drifted, update distances
+__device__ void manifold_refresh(ManRef& e, int k, float thr, V3 pa, const M3& Ra, V3 pb, const M3& Rb) {
+  int n = __float_as_int(e.mw(k, 0));
+  for (int i = n - 1; i >= 0; i--) {
+    int o = 1 + 10 * i;
+    V3 lA = v3(e.mw(k, o), e.mw(k, o + 1), e.mw(k, o + 2)), lB = v3(e.mw(k, o + 3), e.mw(k, o + 4), e.mw(k, o + 5));
+    V3 nB = v3(e.mw(k, o + 6), e.mw(k, o + 7), e.mw(k, o + 8));
+    V3 wa = mul(Ra, lA) + pa, wb = mul(Rb, lB) + pb;
+    float dist = dot(wa - wb, nB);
+    bool drop = dist > thr;
+    if (!drop) {
+      V3 pd = wb - (wa - dist * nB);
+      drop = dot(pd, pd) > thr * thr;
+    }
+    if (drop) {
+      int last = n - 1;
+      if (i != last) for (int w = 0; w < 10; w++) e.mw(k, o + w) = e.mw(k, 1 + 10 * last + w);
+      n--;
+    } else e.mw(k, o + 9) = dist;
+  }
+  if (n != __float_as_int(e.mw(k, 0))) e.mw(k, 0) = __int_as_float(n);
+}
+
+// One collision pair: broadphase (world AABBs grown by the margin), box-box narrowphase into the
+// persistent manifold, refresh.  Boxes given by centre, orientation, half extents.
+__device__ void collide_pair(ManRef& e, int k, V3 pa, const M3& Ra, V3 ha, V3 pb, const M3& Rb, V3 hb) {
+  V3 d = pa - pb;
+  float ex = fabsf(Ra.r0.x) * ha.x + fabsf(Ra.r0.y) * ha.y + fabsf(Ra.r0.z) * ha.z + fabsf(Rb.r0.x) * hb.x + fabsf(Rb.r0.y) * hb.y + fabsf(Rb.r0.z) * hb.z + 2 * BROADPHASE_MARGIN;
+  float ey = fabsf(Ra.r1.x) * ha.x + fabsf(Ra.r1.y) * ha.y + fabsf(Ra.r1.z) * ha.z + fabsf(Rb.r1.x) * hb.x + fabsf(Rb.r1.y) * hb.y + fabsf(Rb.r1.z) * hb.z + 2 * BROADPHASE_MARGIN;
+  float ez = fabsf(Ra.r2.x) * ha.x + fabsf(Ra.r2.y) * ha.y + fabsf(Ra.r2.z) * ha.z + fabsf(Rb.r2.x) * hb.x + fabsf(Rb.r2.y) * hb.y + fabsf(Rb.r2.z) * hb.z + 2 * BROADPHASE_MARGIN;
+  if (fabsf(d.x) > ex || fabsf(d.y) > ey || fabsf(d.z) > ez) {
+    if (__float_as_int(e.mw(k, 0)) != 0) e.mw(k, 0) = __int_as_float(0);
+    return;
+  }
+  float thr = BREAKING_THRESHOLD_FACTOR * fminf(norm(ha), norm(hb));
+  Contact c[4];
+  int nc = box_box(pa, Ra, ha, pb, Rb, hb, c);
+  for (int i = 0; i < nc; i++) {
+    V3 wa = c[i].pB + c[i].dist * c[i].nB;
+    manifold_add(e, k, thr, mulT(Ra, wa - pa), mulT(Rb, c[i].pB - pb), c[i].nB, c[i].dist);
+  }
+  manifold_refresh(e, k, thr, pa, Ra, pb, Rb);
+}
+
 template <int NBLK>
 __device__ void collide(Env<NBLK>& e, const Frames& f) {
 #pragma unroll
@@ -142,26 +192,7 @@ __device__ void collide(Env<NBLK>& e, const Frames& f) {
       V3 wa = c[i].pB + c[i].dist * c[i].nB;
       manifold_add(e, k, thr, mulT(Ra, wa - pa), mulT(Rb, c[i].pB - pb), c[i].nB, c[i].dist);
     }
-    // refreshContactPoints
-    int n = __float_as_int(e.mw(k, 0));
-    for (int i = n - 1; i >= 0; i--) {
-      int o = 1 + 10 * i;
-      V3 lA = v3(e.mw(k, o), e.mw(k, o + 1), e.mw(k, o + 2)), lB = v3(e.mw(k, o + 3), e.mw(k, o + 4), e.mw(k, o + 5));
-      V3 nB = v3(e.mw(k, o + 6), e.mw(k, o + 7), e.mw(k, o + 8));
-      V3 wa = mul(Ra, lA) + pa, wb = mul(Rb, lB) + pb;
-      float dist = dot(wa - wb, nB);
-      bool drop = dist > thr;
-      if (!drop) {
-        V3 pd = wb - (wa - dist * nB);
-        drop = dot(pd, pd) > thr * thr;
-      }
-      if (drop) {
-        int last = n - 1;
-        if (i != last) for (int w = 0; w < 10; w++) e.mw(k, o + w) = e.mw(k, 1 + 10 * last + w);
-        n--;
-      } else e.mw(k, o + 9) = dist;
-    }
-    if (n != __float_as_int(e.mw(k, 0))) e.mw(k, 0) = __int_as_float(n);
+    manifold_refresh(e, k, thr, pa, Ra, pb, Rb);
   }
 }
 
@@ -524,5 +555,25 @@ __device__ void substep(Env<NBLK>& e) {
     e.bquat[b][0] = nx * inv; e.bquat[b][1] = ny * inv; e.bquat[b][2] = nz * inv; e.bquat[b][3] = nw * inv;
   }
 }
+
+// ---- kernel I/O (shared by the thread-per-env and the lane-cooperative kernels) -----------------
+struct StepIO {
+  float* state; float* manifold; int batch; int state_words;
+  const float* action; float* obs; float* reward; uint8_t* done; uint8_t* success;
+  float thr; int binary; int max_steps; int* overflow;
+  int epw;  // environments per warp: lanes [0, epw) of every warp own one environment each
+  int bulk;         // 1: stage the state tile with TMA bulk copies (full warps only)
+  int tile_offset;  // float offset of the state tile inside dynamic shared memory
+};
+
+template <int TASK, int NBLK> struct Dims {
+  static constexpr int O = TASK == 0 ? 3 : (TASK == 3 ? 8 + 16 * NBLK : 20);
+  static constexpr int P = TASK == 0 ? 3 : (TASK == 3 ? 4 + 3 * NBLK : 7);
+  static constexpr int G = TASK == 3 ? 3 * NBLK : 3;
+  static constexpr int W = O + P + 2 * G;
+  static constexpr int A = TASK >= 2 ? 4 : 3;
+  static constexpr int STATE = ST_BLK + 13 * NBLK + G + 1;
+};
+
 
 }  // namespace pmg

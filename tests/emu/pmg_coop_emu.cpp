@@ -1,0 +1,158 @@
+// pmg_coop_emu.cpp -- TEST INFRASTRUCTURE: runs the lane-cooperative device code of
+// pybullet_multigoal_gym_b200/csrc/pmg_coop.cuh on the CPU, unchanged.
+//
+// The 8 lanes of one environment are coroutines (ucontext) scheduled round-robin; every group
+// primitive (shuffle, ballot, sync) is a rendezvous: a lane publishes its operand, yields, and reads
+// the others' operands when it is resumed, i.e. exactly the lockstep semantics of __shfl_sync /
+// __syncwarp over the octet's mask.  A lane that executes a different number of rendezvous than its
+// siblings (a divergent collective, which would deadlock or corrupt on the GPU) aborts the run.
+// Built by tests/emu/build_emu.py into tests/emu/libpmg_coop_emu.so; used by tests/test_coop_emu.py
+// to compare the cooperative algorithm with the CPU oracle without a GPU.  Never loaded by the product.
+#define PMG_EMULATE 1
+#include <stdio.h>
+#include <stdlib.h>
+#include <ucontext.h>
+
+#include "../../pybullet_multigoal_gym_b200/csrc/pmg_coop.cuh"
+
+namespace pmg_emu {
+
+constexpr int NL = 8;
+constexpr size_t STACK = 1 << 20;
+
+struct Sched {
+  ucontext_t main_ctx, ctx[NL];
+  char* stack[NL];
+  bool done[NL];
+  long nsync[NL];
+  float slot[NL];
+  bool pslot[NL];
+  int cur;
+  void (*body)(int lane, void* arg);
+  void* arg;
+};
+static thread_local Sched* S = nullptr;
+
+static void yield_() {
+  S->nsync[S->cur]++;
+  swapcontext(&S->ctx[S->cur], &S->main_ctx);
+}
+int lane() { return S->cur; }
+float shfl(float v, int src) {
+  S->slot[S->cur] = v;
+  yield_();
+  float r = S->slot[src & (NL - 1)];
+  yield_();
+  return r;
+}
+unsigned ballot(bool p) {
+  S->pslot[S->cur] = p;
+  yield_();
+  unsigned m = 0;
+  for (int i = 0; i < NL; i++) m |= (S->pslot[i] ? 1u : 0u) << i;
+  yield_();
+  return m;
+}
+void sync() { yield_(); }
+
+static void trampoline(int lane_id) {
+  S->body(lane_id, S->arg);
+  S->done[lane_id] = true;
+  swapcontext(&S->ctx[lane_id], &S->main_ctx);
+}
+
+// run body(lane, arg) on 8 lockstep lanes; returns 0, or -1 when the lanes' collectives diverged
+static int run_group(void (*body)(int, void*), void* arg) {
+  Sched sch;
+  S = &sch;
+  sch.body = body; sch.arg = arg;
+  for (int i = 0; i < NL; i++) {
+    sch.stack[i] = (char*)malloc(STACK);
+    sch.done[i] = false; sch.nsync[i] = 0;
+    getcontext(&sch.ctx[i]);
+    sch.ctx[i].uc_stack.ss_sp = sch.stack[i];
+    sch.ctx[i].uc_stack.ss_size = STACK;
+    sch.ctx[i].uc_link = &sch.main_ctx;
+    makecontext(&sch.ctx[i], (void (*)())trampoline, 1, i);
+  }
+  int rc = 0;
+  for (;;) {
+    int alive = 0;
+    for (int i = 0; i < NL; i++) {
+      if (sch.done[i]) continue;
+      sch.cur = i;
+      swapcontext(&sch.main_ctx, &sch.ctx[i]);
+      if (!sch.done[i]) alive++;
+    }
+    if (alive == 0) break;
+    if (alive != NL) {  // some lanes finished while others still wait at a rendezvous
+      bool all_same = true;
+      for (int i = 1; i < NL; i++) if (sch.done[i] != sch.done[0]) all_same = false;
+      if (!all_same) { fprintf(stderr, "pmg_coop_emu: divergent collective (lanes finished at different rendezvous counts)\n"); rc = -1; break; }
+    }
+  }
+  for (int i = 1; i < NL; i++) if (sch.nsync[i] != sch.nsync[0]) { if (rc == 0) fprintf(stderr, "pmg_coop_emu: rendezvous count mismatch lane %d: %ld vs %ld\n", i, sch.nsync[i], sch.nsync[0]); rc = -1; }
+  for (int i = 0; i < NL; i++) free(sch.stack[i]);
+  S = nullptr;
+  return rc;
+}
+
+}  // namespace pmg_emu
+
+using namespace pmg;
+
+namespace {
+struct StepArgs { coop::EnvSmem* sm; StepIO io; };
+void step_body(int lane, void* arg) {
+  StepArgs* a = (StepArgs*)arg;
+  coop::Grp g; g.lane = lane;
+  coop::step_env_reach(g, *a->sm, a->io, 0);
+}
+
+struct MinvArgs { coop::EnvSmem* sm; const float* q; const float* qd; float* minv_out; float* q_out; float* qd_out; };
+void substep_body(int lane, void* arg) {
+  MinvArgs* a = (MinvArgs*)arg;
+  coop::Grp g; g.lane = lane;
+  coop::Lane L;
+  coop::load_lane_constants(g, L);
+  L.q0 = a->q[lane]; L.qd0 = a->qd[lane];
+  L.q1 = lane == 7 ? a->q[8] : 0.0f; L.qd1 = lane == 7 ? a->qd[8] : 0.0f;
+  L.mt0 = L.q0; L.mt1 = L.q1; L.mi0 = L.mi1 = 0.0f;  // motors off
+  L.dtau0 = L.dtau1 = 0.0f;
+  coop::substep(g, *a->sm, L);
+  a->q_out[lane] = L.q0; a->qd_out[lane] = L.qd0;
+  if (lane == 7) { a->q_out[8] = L.q1; a->qd_out[8] = L.qd1; }
+}
+}  // namespace
+
+extern "C" {
+
+// One env.step() of a Reach environment.  state: the Reach state words (Dims<0,0>::STATE = 50) of one
+// env; manifold: 2 x 41 words; both updated in place.  obs_row: 12 floats.
+int pmg_emu_reach_step(float* state, float* manifold, const float* action, float thr, int binary, int max_steps,
+                       float* obs_row, float* reward, uint8_t* done, uint8_t* success) {
+  static coop::EnvSmem sm;
+  memset(&sm, 0, sizeof sm);
+  StepArgs a;
+  a.sm = &sm;
+  memset(&a.io, 0, sizeof a.io);
+  a.io.state = state; a.io.manifold = manifold; a.io.batch = 1; a.io.state_words = Dims<0, 0>::STATE;
+  a.io.action = action; a.io.obs = obs_row; a.io.reward = reward; a.io.done = done; a.io.success = success;
+  a.io.thr = thr; a.io.binary = binary; a.io.max_steps = max_steps; a.io.overflow = nullptr; a.io.epw = 4;
+  return pmg_emu::run_group(step_body, &a);
+}
+
+// One free substep (motors off, no manifolds) from (q, qd); also returns M^-1 (9x9) for cross-checks.
+int pmg_emu_substep(const float* q, const float* qd, float* minv81, float* q_out, float* qd_out) {
+  static coop::EnvSmem sm;
+  memset(&sm, 0, sizeof sm);
+  MinvArgs a{&sm, q, qd, minv81, q_out, qd_out};
+  int rc = pmg_emu::run_group(substep_body, &a);
+  for (int i = 0; i < 81; i++) minv81[i] = sm.minv[i];
+  return rc;
+}
+
+int pmg_emu_state_words(void) { return Dims<0, 0>::STATE; }
+int pmg_emu_smem_bytes(void) { return (int)sizeof(coop::EnvSmem); }
+
+}  // extern "C"

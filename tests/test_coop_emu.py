@@ -1,0 +1,99 @@
+"""CPU tests of the lane-cooperative step algorithm (csrc/pmg_coop.cuh).
+
+The device source is compiled for the host with the 8 lanes of an environment emulated as lockstep
+coroutines (tests/emu/), and compared with the double-precision CPU oracle: the joint-space inertia
+inverse (lane-parallel composite-rigid-body sums + Gauss-Jordan sweeps vs the oracle's articulated-body
+impulse responses), free rollouts, and rollouts that press the closed jaws onto the table (finger-table
+manifolds, contact and friction rows).  The same kernel is checked on the GPU by tests/test_gpu_parity.py.
+"""
+import ctypes as C
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from oracle import pmg_oracle as O  # noqa: E402
+from tests.emu import build_emu  # noqa: E402
+
+FP = C.POINTER(C.c_float)
+U8 = C.POINTER(C.c_uint8)
+
+
+def _f(a):
+    return a.ctypes.data_as(FP)
+
+
+@pytest.fixture(scope="module")
+def emu():
+    O.build()
+    L = C.CDLL(build_emu.build())
+    assert L.pmg_emu_state_words() == 50
+    return L
+
+
+def test_shared_memory_budget(emu):
+    # 4 environments per one-warp block, 14 blocks per SM (batch 8192 on 148 SMs) must fit in 227 KB
+    per_block = 4 * emu.pmg_emu_smem_bytes() + 1024
+    assert 14 * per_block <= 227 * 1024
+
+
+@pytest.mark.parametrize("seed", [0, 3])
+def test_mass_matrix_inverse_matches_oracle(emu, seed):
+    o = O.OracleEnv("reach", seed=seed)
+    o.reset()
+    rng = np.random.RandomState(seed)
+    st = o.get_state()
+    st[:7] += rng.uniform(-0.3, 0.3, 7)
+    st[7:9] = rng.uniform(0.0, 0.035, 2)
+    o.set_state(st)
+    q = st[:9].astype(np.float32)
+    qd = np.zeros(9, np.float32)
+    minv, qo, qdo = np.zeros(81, np.float32), np.zeros(9, np.float32), np.zeros(9, np.float32)
+    assert emu.pmg_emu_substep(_f(q), _f(qd), _f(minv), _f(qo), _f(qdo)) == 0
+    ref = o.minv()
+    got = minv.reshape(9, 9)
+    assert np.abs(got - ref).max() <= 2e-6 * np.abs(ref).max()
+    assert np.array_equal(got, got.T) or np.abs(got - got.T).max() <= 1e-6 * np.abs(ref).max()
+
+
+def _rollout(emu, seed, nsteps, press_down):
+    o = O.OracleEnv("reach", seed=seed)
+    o.reset()
+    o.reset()
+    st = o.get_state().astype(np.float32)
+    man = np.zeros(82, np.float32)
+    rng = np.random.RandomState(seed + 100)
+    obs, rew = np.zeros(12, np.float32), np.zeros(1, np.float32)
+    dn, su = np.zeros(1, np.uint8), np.zeros(1, np.uint8)
+    worst, points = 0.0, 0
+    for t in range(nsteps):
+        a = rng.uniform(-1, 1, 3).astype(np.float32)
+        if press_down:
+            a[2] = -1.0
+        ro, rr, rd, ri = o.step(a.astype(np.float64))
+        rc = emu.pmg_emu_reach_step(_f(st), _f(man), _f(a), C.c_float(0.05), 1, 50, _f(obs), _f(rew),
+                                    dn.ctypes.data_as(U8), su.ctypes.data_as(U8))
+        assert rc == 0, "divergent collective in the cooperative kernel"
+        worst = max(worst, float(np.abs(obs[6:9] - ro["achieved_goal"]).max()))
+        assert np.array_equal(obs[0:3], obs[6:9]) and np.array_equal(obs[3:6], obs[6:9])
+        assert np.allclose(obs[9:12], ro["desired_goal"], atol=1e-7)
+        assert bool(dn[0]) == rd and bool(su[0]) == ri["goal_achieved"] and rew[0] == np.float32(rr)
+        points = max(points, int(man[0:1].view(np.int32)[0]) + int(man[41:42].view(np.int32)[0]))
+    return worst, points, st, o.get_state()
+
+
+def test_free_rollout_matches_oracle(emu):
+    worst, points, st, ost = _rollout(emu, seed=1, nsteps=12, press_down=False)
+    assert worst < 1e-5, worst  # tolerance of the path is 1e-4 (BASELINE.json north_star)
+    assert np.abs(st[:18] - ost[:18]).max() < 1e-4
+    assert st[49] == 12.0
+
+
+def test_finger_table_contact_rollout_matches_oracle(emu):
+    # tip starts at z = 0.25; 8+ steps of -1 cm reach the 0.175 clip where the closed jaws touch the table
+    worst, points, st, ost = _rollout(emu, seed=2, nsteps=14, press_down=True)
+    assert points == 8, points  # both finger-table manifolds full: 4 + 4 points
+    assert worst < 1e-4, worst

@@ -4,7 +4,10 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 import pybullet_multigoal_gym_b200 as pmg
 
-for task, B in [("reach", 8192), ("push", 4096), ("pick_and_place", 4096), ("block_stack", 2048), ("reach", 65536)]:
+CASES = [("reach", 8192), ("push", 4096), ("pick_and_place", 4096), ("block_stack", 2048), ("reach", 65536)]
+if len(sys.argv) > 1:  # e.g. quick_time.py reach:8192 reach:65536
+    CASES = [(a.split(":")[0], int(a.split(":")[1])) for a in sys.argv[1:]]
+for task, B in CASES:
     env = pmg.make_env(task=task, batch=B, num_block=4, check_actions=False)
     A = env.action_dim
     acts = torch.rand((60, B, A), device="cuda") * 2 - 1
