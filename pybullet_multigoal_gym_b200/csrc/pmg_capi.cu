@@ -247,6 +247,9 @@ __global__ void __launch_bounds__(32) step_kernel(StepIO io) {
 }
 
 // Lane-cooperative Reach step (pmg_coop.cuh): 8 lanes per environment, 4 environments per one-warp block.
+// (Packing the environments whose jaws rest on the table into the same warps was tried and measured slower:
+// the step lasts as long as its slowest warp, and four contact octets in one warp serialise their divergent
+// narrowphase branches.)
 constexpr int COOP_MIN_BLOCKS = 14;  // batch 8192 = 2048 blocks = 13.8 per SM: keep them all resident
 __global__ void __launch_bounds__(32, COOP_MIN_BLOCKS) step_kernel_coop_reach(StepIO io) {
   extern __shared__ __align__(16) unsigned char coop_smem[];

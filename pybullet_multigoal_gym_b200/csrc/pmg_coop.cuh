@@ -31,15 +31,18 @@ namespace coop {
 
 constexpr int GL = 8;        // lanes per environment
 constexpr int MAXPTS = 8;    // finger-table contact points: 2 pairs x 4
-constexpr int ROW_W = 24;    // floats per contact row record
-constexpr int R_J = 0, R_MJ = 9, R_RHS = 18, R_DINV = 19, R_DENOM = 20, R_APP = 21, R_MU = 22;
+constexpr int ROW_W = 28;    // floats per contact row record (16-byte aligned vectors)
+constexpr int R_J = 0, R_MJ = 12, R_RHS = 21, R_DINV = 22, R_DENOM = 23, R_APP = 24, R_MU = 25;
+constexpr int MINV_LD = 12;  // row stride of M^-1 in shared memory
 constexpr int COOP_PAIRS = 2;
 
+static_assert(2 * sizeof(BoxScratch) <= MAXPTS * 3 * ROW_W * sizeof(float), "narrowphase scratch must fit in the contact-row area");
 struct __align__(16) EnvSmem {
-  float pub[7][12];                 // per arm dof: axis a, v = (p - Pref) x a, composite momentum n, l
-  float minv[84];                   // 9x9, row-major
+  float pub[7][8];                  // per arm dof: axis a, v = (p - Pref) x a
+  float minv[ND * MINV_LD];         // 9x9, rows padded to 12
   float man[84];                    // persistent manifolds of the 2 finger-table pairs (2 x 41 words)
-  float rows[MAXPTS * 3][ROW_W];    // contact rows: J[9] MJ[9] rhs dinv denom app mu
+  float vq[12];                     // joint velocities (row set-up), then PGS delta velocities (contact sweeps)
+  float rows[MAXPTS * 3][ROW_W];    // contact rows: J[9] . MJ[9] rhs dinv denom app mu
 };
 
 // ---- the group (octet) interface ---------------------------------------------------------------
@@ -212,23 +215,25 @@ struct SolverLane {
   float rhs0, rhs1, lim0, lim1, app0, app1, dinv0, dinv1, mdd0, mdd1;
   float lrhs00, lrhs01, lrhs10, lrhs11;  // [slot][side]
   float lapp00, lapp01, lapp10, lapp11;
-  float dqd0, dqd1, res;
+  float dqd0, dqd1;
+  float big0, big1;  // largest |impulse change| of the lane's own rows in this sweep (convergence test)
 };
 
+// Motor row of the K-th visited dof.  Every lane evaluates the row formula on its own slot; only the
+// owner's result is kept (predicated moves) and broadcast.
 template <int K>
 __device__ __forceinline__ void motor_row(const Grp& g, SolverLane& s, const float* A0, const float* A1) {
   constexpr int d = nc_dof(K);
   constexpr int owner = d < 8 ? d : 7;
   constexpr bool slot1 = d == 8;
   const float rhs = slot1 ? s.rhs1 : s.rhs0, cur = slot1 ? s.dqd1 : s.dqd0, dinv = slot1 ? s.dinv1 : s.dinv0;
-  const float app = slot1 ? s.app1 : s.app0, lim = slot1 ? s.lim1 : s.lim0, mdd = slot1 ? s.mdd1 : s.mdd0;
+  const float app = slot1 ? s.app1 : s.app0, lim = slot1 ? s.lim1 : s.lim0;
   float dlc = rhs - cur * dinv;
   const float sum = fminf(fmaxf(app + dlc, -lim), lim);
   dlc = sum - app;
-  const bool own = g.lane == owner;
-  if (slot1) s.app1 = own ? sum : s.app1; else s.app0 = own ? sum : s.app0;
-  const float rr = dlc * mdd;
-  s.res = own ? fmaxf(s.res, rr * rr) : s.res;
+  if (g.lane == owner) {
+    if (slot1) { s.app1 = sum; s.big1 = fmaxf(s.big1, fabsf(dlc)); } else { s.app0 = sum; s.big0 = fmaxf(s.big0, fabsf(dlc)); }
+  }
   const float dl = g.shfl(dlc, owner);
   s.dqd0 += A0[d] * dl;
   s.dqd1 += A1[d] * dl;
@@ -242,28 +247,180 @@ __device__ __forceinline__ void limit_row(const Grp& g, SolverLane& s, const Env
   const float sign = side ? -1.0f : 1.0f;
   const float lr = slot1 ? (side ? s.lrhs11 : s.lrhs10) : (side ? s.lrhs01 : s.lrhs00);
   const float la = slot1 ? (side ? s.lapp11 : s.lapp10) : (side ? s.lapp01 : s.lapp00);
-  const float cur = slot1 ? s.dqd1 : s.dqd0, dinv = slot1 ? s.dinv1 : s.dinv0, mdd = slot1 ? s.mdd1 : s.mdd0;
+  const float cur = slot1 ? s.dqd1 : s.dqd0, dinv = slot1 ? s.dinv1 : s.dinv0;
   float dlc = lr - sign * cur * dinv;
   const float sum = fminf(fmaxf(la + dlc, 0.0f), LIMIT_MAX_IMPULSE);
   dlc = sum - la;
   if (g.lane == owner) {
-    if (slot1) { if (side) s.lapp11 = sum; else s.lapp10 = sum; }
-    else { if (side) s.lapp01 = sum; else s.lapp00 = sum; }
-    const float rr = dlc * mdd;
-    s.res = fmaxf(s.res, rr * rr);
+    if (slot1) { if (side) s.lapp11 = sum; else s.lapp10 = sum; s.big1 = fmaxf(s.big1, fabsf(dlc)); }
+    else { if (side) s.lapp01 = sum; else s.lapp00 = sum; s.big0 = fmaxf(s.big0, fabsf(dlc)); }
   }
   const float sdl = sign * g.shfl(dlc, owner);
-  s.dqd0 += sm.minv[d * 9 + dof0] * sdl;
-  s.dqd1 += sm.minv[d * 9 + 8] * sdl;
+  s.dqd0 += sm.minv[d * MINV_LD + dof0] * sdl;
+  s.dqd1 += sm.minv[d * MINV_LD + 8] * sdl;
 }
 
-__device__ __forceinline__ void limit_rows(const Grp& g, SolverLane& s, const EnvSmem& sm, unsigned lact, bool forward, int dof0) {
+// The closed jaws of Reach / Push sit on their upper limit, so the finger limit rows are active in most
+// substeps: static versions of exactly those rows (dof and owner known at compile time, M^-1 from registers).
+__host__ __device__ constexpr int visit_pos(int dof) {
+  for (int k = 0; k < ND; k++) if (nc_dof(k) == dof) return k;
+  return -1;
+}
+constexpr int K_F1 = visit_pos(7), K_F2 = visit_pos(8);
+static_assert(K_F1 >= 0 && K_F2 == K_F1 + 1, "finger limit fast path assumes finger1, finger2 are visited back to back");
+constexpr unsigned FINGER_LIMIT_BITS = (3u << (2 * K_F1)) | (3u << (2 * K_F2));
+
+template <int DOF, int SIDE>
+__device__ __forceinline__ void finger_limit_row(const Grp& g, SolverLane& s, const float* A0, const float* A1) {
+  constexpr bool slot1 = DOF == 8;
+  constexpr float sign = SIDE ? -1.0f : 1.0f;
+  float& lapp = slot1 ? (SIDE ? s.lapp11 : s.lapp10) : (SIDE ? s.lapp01 : s.lapp00);
+  const float lr = slot1 ? (SIDE ? s.lrhs11 : s.lrhs10) : (SIDE ? s.lrhs01 : s.lrhs00);
+  const float cur = slot1 ? s.dqd1 : s.dqd0, dinv = slot1 ? s.dinv1 : s.dinv0;
+  float dlc = lr - sign * cur * dinv;
+  const float sum = fminf(fmaxf(lapp + dlc, 0.0f), LIMIT_MAX_IMPULSE);
+  dlc = sum - lapp;
+  if (g.lane == 7) {
+    lapp = sum;
+    if (slot1) s.big1 = fmaxf(s.big1, fabsf(dlc)); else s.big0 = fmaxf(s.big0, fabsf(dlc));
+  }
+  const float sdl = sign * g.shfl(dlc, 7);
+  s.dqd0 += A0[DOF] * sdl;
+  s.dqd1 += A1[DOF] * sdl;
+}
+
+__device__ __forceinline__ void limit_rows(const Grp& g, SolverLane& s, const EnvSmem& sm, unsigned lact, bool forward, int dof0, const float* A0, const float* A1) {
+  if ((lact & ~FINGER_LIMIT_BITS) == 0u) {
+    const unsigned f = lact >> (2 * K_F1);
+    if (forward) {
+      if (f & 1u) finger_limit_row<7, 0>(g, s, A0, A1);
+      if (f & 2u) finger_limit_row<7, 1>(g, s, A0, A1);
+      if (f & 4u) finger_limit_row<8, 0>(g, s, A0, A1);
+      if (f & 8u) finger_limit_row<8, 1>(g, s, A0, A1);
+    } else {
+      if (f & 8u) finger_limit_row<8, 1>(g, s, A0, A1);
+      if (f & 4u) finger_limit_row<8, 0>(g, s, A0, A1);
+      if (f & 2u) finger_limit_row<7, 1>(g, s, A0, A1);
+      if (f & 1u) finger_limit_row<7, 0>(g, s, A0, A1);
+    }
+    return;
+  }
   unsigned todo = lact;
   while (todo) {
     const int id = forward ? __ffs(todo) - 1 : 31 - __clz(todo);
     todo &= ~(1u << id);
     limit_row(g, s, sm, id, dof0);
   }
+}
+
+// ---- finger-table contact rows -------------------------------------------------------------------------
+// Row set-up: lane c builds the three rows (normal, two tangents) of cached contact point c on its own --
+// the arm axes, M^-1 and the joint velocities are read from shared memory -- so the (up to) 8 points are set
+// up in parallel and without a single shuffle.  J of an arm joint at contact point w is
+// d . (a_j x (w - p_j)) = a_j . ((w - Pref) x d) + d . vv_j with the published vv_j = (p_j - Pref) x a_j.
+__device__ __noinline__ void contact_row_setup(EnvSmem& sm, int c, int n0, const M3& Rg, V3 pf1, V3 pf2, V3 Pref, V3 ax1, V3 ax2) {
+  const int k = c < n0 ? 0 : 1, i = k ? c - n0 : c;
+  const float* mp = sm.man + k * MAN_WORDS + 1 + 10 * i;
+  const V3 lA = v3(mp[0], mp[1], mp[2]), nB = v3(mp[6], mp[7], mp[8]);
+  const float dist = mp[9];
+  const V3 wr = mul(Rg, lA) + (k ? pf2 : pf1) - Pref;  // contact point on the finger, relative to Pref
+  V3 t1, t2;
+  plane_space(nB, t1, t2);
+  const float mu = (float)PMG_FINGER_FRICTION * (float)PMG_TABLE_FRICTION;
+#pragma unroll 1
+  for (int kk = 0; kk < 3; kk++) {
+    const V3 d = kk == 0 ? nB : (kk == 1 ? t1 : t2);
+    const V3 m = cross(wr, d);
+    float J[ND];
+#pragma unroll
+    for (int j = 0; j < 7; j++) {
+      const float* pb = sm.pub[j];
+      J[j] = pb[0] * m.x + pb[1] * m.y + pb[2] * m.z + pb[3] * d.x + pb[4] * d.y + pb[5] * d.z;
+    }
+    J[7] = k == 0 ? dot(d, ax1) : 0.0f;
+    J[8] = k == 1 ? dot(d, ax2) : 0.0f;
+    float* row = sm.rows[c * 3 + kk];
+    float denom = 0.0f, rel_vel = 0.0f;
+#pragma unroll
+    for (int r = 0; r < ND; r++) {
+      const float* mr = sm.minv + r * MINV_LD;
+      float acc = 0.0f;
+#pragma unroll
+      for (int j = 0; j < ND; j++) acc += mr[j] * J[j];
+      row[R_MJ + r] = acc; row[R_J + r] = J[r];
+      denom += J[r] * acc;
+      rel_vel += J[r] * sm.vq[r];
+    }
+    const float dinv = 1.0f / denom;
+    float rhs;
+    if (kk == 0) {
+      const float pen = dist + LINEAR_SLOP;
+      float pos_err = 0.0f, vel_err = -rel_vel;
+      if (pen > 0.0f) vel_err -= pen * INV_DT; else pos_err = -pen * CONTACT_ERP * INV_DT;
+      rhs = (pos_err + vel_err) * dinv;
+    } else rhs = -rel_vel * dinv;
+    row[R_RHS] = rhs; row[R_DINV] = dinv; row[R_DENOM] = denom; row[R_APP] = 0.0f; row[R_MU] = mu;
+  }
+}
+
+__device__ __forceinline__ float row_dot(const float* v, const float* dq) {
+  float a = v[0] * dq[0], b = v[1] * dq[1], c = v[2] * dq[2];
+  a += v[3] * dq[3]; b += v[4] * dq[4]; c += v[5] * dq[5];
+  a += v[6] * dq[6]; b += v[7] * dq[7]; c += v[8] * dq[8];
+  return a + b + c;
+}
+__device__ __forceinline__ void row_axpy(const float* v, float s, float* dq) {
+#pragma unroll
+  for (int j = 0; j < ND; j++) dq[j] += v[j] * s;
+}
+
+// One Gauss-Seidel pass over the contact rows (all normals, then the friction pairs with the implicit cone).
+// Every lane of the octet does the same arithmetic on a replicated delta-velocity vector: no shuffles on
+// this path, which is usually executed by one octet of a warp while the others wait.
+__device__ __forceinline__ float contact_sweep(const Grp& g, EnvSmem& sm, int nrow, float* dq) {
+  float cres = 0.0f;
+#pragma unroll 1
+  for (int c = 0; c < nrow; c++) {
+    float* row = sm.rows[c * 3];
+    const float app = row[R_APP];
+    float dl = row[R_RHS] - row_dot(row + R_J, dq) * row[R_DINV];
+    const float sum = fminf(fmaxf(app + dl, 0.0f), 1e10f);
+    dl = sum - app;
+    row_axpy(row + R_MJ, dl, dq);
+    const float rr = dl * row[R_DENOM];
+    cres = fmaxf(cres, rr * rr);
+    g.sync();  // every lane has read the old impulse
+    if (g.lane == 0) row[R_APP] = sum;
+  }
+  g.sync();
+#pragma unroll 1
+  for (int c = 0; c < nrow; c++) {  // implicit friction cone: both tangent rows of a point together
+    const float total = sm.rows[c * 3][R_APP];
+    if (!(total > 0.0f)) continue;
+    float* ra = sm.rows[c * 3 + 1];
+    float* rb = sm.rows[c * 3 + 2];
+    const float lim = ra[R_MU] * total;
+    const float appA = ra[R_APP], appB = rb[R_APP];
+    float dA = ra[R_RHS] - row_dot(ra + R_J, dq) * ra[R_DINV], dB = rb[R_RHS] - row_dot(rb + R_J, dq) * rb[R_DINV];
+    float sA = appA + dA, sB = appB + dB;
+    const float s2 = sA * sA + sB * sB;
+    if (s2 >= lim * lim) {
+      // |lim sin(atan2(sA, sB))| = lim |sA| / sqrt(sA^2 + sB^2), likewise the cosine for sB
+      const float sc = s2 > 0.0f ? lim * rsqrtf(s2) : 0.0f;
+      const float cA = fabsf(sA) * sc, cB = s2 > 0.0f ? fabsf(sB) * sc : lim;
+      sA = fminf(fmaxf(sA, -cA), cA);
+      sB = fminf(fmaxf(sB, -cB), cB);
+      dA = sA - appA; dB = sB - appB;
+    }
+    row_axpy(ra + R_MJ, dA, dq);
+    row_axpy(rb + R_MJ, dB, dq);
+    const float r1_ = dA * ra[R_DENOM], r2_ = dB * rb[R_DENOM];
+    cres = fmaxf(cres, fmaxf(r1_ * r1_, r2_ * r2_));
+    g.sync();
+    if (g.lane == 0) { ra[R_APP] = sA; rb[R_APP] = sB; }
+  }
+  g.sync();
+  return cres;
 }
 
 // ---- one 2 ms substep ---------------------------------------------------------------------------------
@@ -342,7 +499,9 @@ __device__ void substep(const Grp& g, EnvSmem& sm, Lane& L) {
   if (lane < COOP_PAIRS) {
     ManRef mr; mr.man = sm.man; mr.stride = 1;
     const float tc[3] = PMG_TABLE_CENTER, th[3] = PMG_TABLE_HALF, fh[3] = PMG_FINGER_HALF;
-    collide_pair(mr, lane, lane == 0 ? pf1 : pf2, Rg, v3(fh[0], fh[1], fh[2]), v3(tc[0], tc[1], tc[2]), m3_identity(), v3(th[0], th[1], th[2]));
+    // the narrowphase work arrays live in the (not yet used) contact-row area of shared memory
+    BoxScratch& scr = *reinterpret_cast<BoxScratch*>(&sm.rows[lane * (MAXPTS * 3 / 2)][0]);
+    collide_pair(mr, lane, lane == 0 ? pf1 : pf2, Rg, v3(fh[0], fh[1], fh[2]), v3(tc[0], tc[1], tc[2]), m3_identity(), v3(th[0], th[1], th[2]), scr);
   }
   // 4. subtree wrenches and composite inertias: suffix sums over the chain
   Fs = g.rscan(Fs); Ns = g.rscan(Ns); hs = g.rscan(hs);
@@ -350,30 +509,41 @@ __device__ void substep(const Grp& g, EnvSmem& sm, Lane& L) {
   Is.yy = g.rscan(Is.yy); Is.yz = g.rscan(Is.yz); Is.zz = g.rscan(Is.zz);
   // 5. joint-space inertia matrix rows and bias forces
   const V3 vv = cross(p - Pref, a);  // velocity of the reference point per unit joint rate
-  const V3 n_own = arm ? mul(Is, a) + cross(hs, vv) : nf1;
-  const V3 l_own = arm ? L.msub * vv + cross(a, hs) : lf1;
+  const V3 n_own = mul(Is, a) + cross(hs, vv);
+  const V3 l_own = L.msub * vv + cross(a, hs);
   const float b0 = arm ? dot(a, Ns) + dot(vv, Fs) : dot(ax1, F1);
   const float b1 = dot(ax2, F2);
   if (arm) {
     float* pb = sm.pub[lane];
     pb[0] = a.x; pb[1] = a.y; pb[2] = a.z; pb[3] = vv.x; pb[4] = vv.y; pb[5] = vv.z;
-    pb[6] = n_own.x; pb[7] = n_own.y; pb[8] = n_own.z; pb[9] = l_own.x; pb[10] = l_own.y; pb[11] = l_own.z;
+  }
+  g.sync();
+  // Lane i evaluates M[i][j] = s_j . (n_i, l_i) for the joints j <= i it sits below (its subtree carries
+  // their motion) and writes both triangle positions into the shared-memory matrix; the finger rows are
+  // the finger columns of the arm rows.  Then every lane reads its full row(s) back.
+  float* Ms = sm.minv;
+#pragma unroll
+  for (int j = 0; j < 7; j++) {
+    const float* pb = sm.pub[j];
+    const float val = pb[0] * n_own.x + pb[1] * n_own.y + pb[2] * n_own.z + pb[3] * l_own.x + pb[4] * l_own.y + pb[5] * l_own.z;
+    if (arm && j <= lane) { Ms[lane * MINV_LD + j] = val; Ms[j * MINV_LD + lane] = val; }
+  }
+  if (arm) {
+    const float m7 = dot(a, nf1) + dot(vv, lf1), m8 = dot(a, nf2) + dot(vv, lf2);
+    Ms[lane * MINV_LD + 7] = m7; Ms[7 * MINV_LD + lane] = m7;
+    Ms[lane * MINV_LD + 8] = m8; Ms[8 * MINV_LD + lane] = m8;
+  } else {  // the fingers are siblings: no coupling
+    Ms[7 * MINV_LD + 7] = mf; Ms[7 * MINV_LD + 8] = 0.0f; Ms[8 * MINV_LD + 7] = 0.0f; Ms[8 * MINV_LD + 8] = mf;
   }
   g.sync();
   float A0[ND], A1[ND];
 #pragma unroll
-  for (int j = 0; j < 7; j++) {
-    const float* pb = sm.pub[j];
-    const V3 aj = v3(pb[0], pb[1], pb[2]), vj = v3(pb[3], pb[4], pb[5]), nj = v3(pb[6], pb[7], pb[8]), lj = v3(pb[9], pb[10], pb[11]);
-    const float lo = dot(aj, n_own) + dot(vj, l_own);  // j <= own dof: the own subtree carries joint j's motion
-    const float hi = dot(a, nj) + dot(vv, lj);
-    A0[j] = j <= lane ? lo : hi;
-    A1[j] = dot(aj, nf2) + dot(vj, lf2);
+  for (int j = 0; j < ND; j++) {
+    A0[j] = Ms[L.dof0 * MINV_LD + j];
+    A1[j] = hand ? Ms[8 * MINV_LD + j] : (j == 8 ? 1.0f : 0.0f);  // arm lanes carry an inert second row
   }
-  A0[7] = arm ? dot(a, nf1) + dot(vv, lf1) : mf;
-  A0[8] = arm ? dot(a, nf2) + dot(vv, lf2) : 0.0f;  // the fingers are siblings
-  A1[7] = 0.0f; A1[8] = mf;
-  // 6. M^-1 by Gauss-Jordan sweeps, row k broadcast from its owner (lane 7 owns rows 7 and 8)
+  // 6. M^-1 by Gauss-Jordan sweeps, row k broadcast from its owner (lane 7 owns rows 7 and 8).  The
+  // owner's own row equals the broadcast row, so "row -= f * pivot_row" with f = 1 - 1/pivot scales it.
 #pragma unroll
   for (int k = 0; k < ND; k++) {
     const int src = k < 8 ? k : 7;
@@ -382,19 +552,19 @@ __device__ void substep(const Grp& g, EnvSmem& sm, Lane& L) {
     for (int j = 0; j < ND; j++) rk[j] = g.shfl(k == 8 ? A1[j] : A0[j], src);
     const float pinv = 1.0f / rk[k];
     const bool own0 = lane == src && k != 8, own1 = lane == src && k == 8;
-    const float f0 = own0 ? -pinv : A0[k] * pinv, f1 = own1 ? -pinv : A1[k] * pinv;
+    const float f0 = own0 ? 1.0f - pinv : A0[k] * pinv, f1 = own1 ? 1.0f - pinv : A1[k] * pinv;
 #pragma unroll
     for (int j = 0; j < ND; j++) {
       if (j == k) continue;
-      A0[j] = (own0 ? 0.0f : A0[j]) - f0 * rk[j];
-      A1[j] = (own1 ? 0.0f : A1[j]) - f1 * rk[j];
+      A0[j] -= f0 * rk[j];
+      A1[j] -= f1 * rk[j];
     }
-    A0[k] = -f0; A1[k] = -f1;
+    A0[k] = own0 ? pinv : -f0; A1[k] = own1 ? pinv : -f1;
   }
 #pragma unroll
   for (int j = 0; j < ND; j++) {
-    sm.minv[L.dof0 * 9 + j] = A0[j];
-    if (hand) sm.minv[8 * 9 + j] = A1[j];
+    sm.minv[L.dof0 * MINV_LD + j] = A0[j];
+    if (hand) sm.minv[8 * MINV_LD + j] = A1[j];
   }
   // 7. unconstrained velocity update: qd += dt * M^-1 (tau_damping - bias)
   {
@@ -408,12 +578,14 @@ __device__ void substep(const Grp& g, EnvSmem& sm, Lane& L) {
     L.qd0 = fminf(fmaxf(L.qd0 + s0 * DT, -MAX_COORD_VEL), MAX_COORD_VEL);
     L.qd1 = hand ? fminf(fmaxf(L.qd1 + s1 * DT, -MAX_COORD_VEL), MAX_COORD_VEL) : 0.0f;
   }
-  g.sync();  // minv and the manifolds are visible to the whole octet
+  sm.vq[L.dof0] = L.qd0;
+  if (hand) sm.vq[8] = L.qd1;
+  g.sync();  // minv, vq and the manifolds are visible to the whole octet
   // 8. constraint rows
   SolverLane s;
   unsigned lact = 0;
   {
-    s.mdd0 = sm.minv[L.dof0 * 10]; s.mdd1 = A1[8];
+    s.mdd0 = sm.minv[L.dof0 * (MINV_LD + 1)]; s.mdd1 = A1[8];
     s.dinv0 = 1.0f / s.mdd0; s.dinv1 = 1.0f / s.mdd1;
     // btMultiBodyJointMotor in POSITION_CONTROL (kuka.py:282-301)
     const float tv0 = MOTOR_KP * (L.mt0 - L.q0) * INV_DT + L.qd0 + MOTOR_KD * (0.0f - L.qd0);
@@ -423,13 +595,13 @@ __device__ void substep(const Grp& g, EnvSmem& sm, Lane& L) {
     // btMultiBodyJointLimitConstraint rows, only when violated
     const float p00 = L.q0 - L.lower0, p01 = L.upper0 - L.q0, p10 = L.q1 - L.lower1, p11 = L.upper1 - L.q1;
     const bool v00 = !(p00 > 0.0f), v01 = !(p01 > 0.0f), v10 = hand && !(p10 > 0.0f), v11 = hand && !(p11 > 0.0f);
-    s.lrhs00 = ((p00 > SPLIT_IMPULSE_PEN_THRESHOLD ? -p00 * CONTACT_ERP * INV_DT : 0.0f) - L.qd0) * s.dinv0;
-    s.lrhs01 = ((p01 > SPLIT_IMPULSE_PEN_THRESHOLD ? -p01 * CONTACT_ERP * INV_DT : 0.0f) + L.qd0) * s.dinv0;
-    s.lrhs10 = ((p10 > SPLIT_IMPULSE_PEN_THRESHOLD ? -p10 * CONTACT_ERP * INV_DT : 0.0f) - L.qd1) * s.dinv1;
-    s.lrhs11 = ((p11 > SPLIT_IMPULSE_PEN_THRESHOLD ? -p11 * CONTACT_ERP * INV_DT : 0.0f) + L.qd1) * s.dinv1;
-    s.lapp00 = s.lapp01 = s.lapp10 = s.lapp11 = 0.0f;
     const unsigned m00 = g.ballot(v00), m01 = g.ballot(v01), m10 = g.ballot(v10), m11 = g.ballot(v11);
+    s.lrhs00 = s.lrhs01 = s.lrhs10 = s.lrhs11 = 0.0f;
     if (m00 | m01 | m10 | m11) {
+      s.lrhs00 = ((p00 > SPLIT_IMPULSE_PEN_THRESHOLD ? -p00 * CONTACT_ERP * INV_DT : 0.0f) - L.qd0) * s.dinv0;
+      s.lrhs01 = ((p01 > SPLIT_IMPULSE_PEN_THRESHOLD ? -p01 * CONTACT_ERP * INV_DT : 0.0f) + L.qd0) * s.dinv0;
+      s.lrhs10 = ((p10 > SPLIT_IMPULSE_PEN_THRESHOLD ? -p10 * CONTACT_ERP * INV_DT : 0.0f) - L.qd1) * s.dinv1;
+      s.lrhs11 = ((p11 > SPLIT_IMPULSE_PEN_THRESHOLD ? -p11 * CONTACT_ERP * INV_DT : 0.0f) + L.qd1) * s.dinv1;
 #pragma unroll
       for (int k = 0; k < ND; k++) {
         const int d = nc_dof(k);
@@ -437,116 +609,47 @@ __device__ void substep(const Grp& g, EnvSmem& sm, Lane& L) {
         lact |= (lo << (2 * k)) | (hi << (2 * k + 1));
       }
     }
+    s.lapp00 = s.lapp01 = s.lapp10 = s.lapp11 = 0.0f;
     s.dqd0 = s.dqd1 = 0.0f;
   }
-  // contact rows: one normal + two tangents per cached manifold point of the finger-table pairs
-  int nrow = 0;
-  {
-    const float tc[3] = PMG_TABLE_CENTER;
-    const float mu = (float)PMG_FINGER_FRICTION * (float)PMG_TABLE_FRICTION;
-    for (int k = 0; k < COOP_PAIRS; k++) {
-      const int n = __float_as_int(sm.man[k * MAN_WORDS]);
-      const V3 pf = k == 0 ? pf1 : pf2;
-      for (int i = 0; i < n; i++) {
-        const float* mp = sm.man + k * MAN_WORDS + 1 + 10 * i;
-        const V3 lA = v3(mp[0], mp[1], mp[2]), nB = v3(mp[6], mp[7], mp[8]);
-        const float dist = mp[9];
-        const V3 wa = mul(Rg, lA) + pf;
-        V3 dirs[3];
-        dirs[0] = nB;
-        plane_space(nB, dirs[1], dirs[2]);
-        // velocity of the contact point per unit rate of the lane's dofs
-        const V3 Jp0 = arm ? cross(a, wa - p) : (k == 0 ? ax1 : v3(0, 0, 0));
-        const V3 Jp1 = (hand && k == 1) ? ax2 : v3(0, 0, 0);
-#pragma unroll
-        for (int kk = 0; kk < 3; kk++) {
-          const V3 d = dirs[kk];
-          const float J0 = dot(d, Jp0), J1 = dot(d, Jp1);
-          float MJ0 = 0.0f, MJ1 = 0.0f;
-#pragma unroll
-          for (int j = 0; j < ND; j++) {
-            const float Jj = j < 8 ? g.shfl(J0, j) : g.shfl(J1, 7);
-            MJ0 += A0[j] * Jj; MJ1 += A1[j] * Jj;
-          }
-          if (!hand) MJ1 = 0.0f;
-          const float denom = g.sum(J0 * MJ0 + J1 * MJ1);
-          const float rel_vel = g.sum(J0 * L.qd0 + J1 * L.qd1);
-          const float dinv = 1.0f / denom;
-          float rhs;
-          if (kk == 0) {
-            const float pen = dist + LINEAR_SLOP;
-            float pos_err = 0.0f, vel_err = -rel_vel;
-            if (pen > 0.0f) vel_err -= pen * INV_DT; else pos_err = -pen * CONTACT_ERP * INV_DT;
-            rhs = (pos_err + vel_err) * dinv;
-          } else rhs = -rel_vel * dinv;
-          float* row = sm.rows[nrow * 3 + kk];
-          row[R_J + L.dof0] = J0; row[R_MJ + L.dof0] = MJ0;
-          if (hand) { row[R_J + 8] = J1; row[R_MJ + 8] = MJ1; }
-          if (lane == 0) { row[R_RHS] = rhs; row[R_DINV] = dinv; row[R_DENOM] = denom; row[R_APP] = 0.0f; row[R_MU] = mu; }
-        }
-        nrow++;
-      }
-    }
-    if (nrow) g.sync();
+  // contact rows: one normal + two tangents per cached manifold point, point c set up by lane c
+  const int n0 = __float_as_int(sm.man[0]);
+  const int nrow = n0 + __float_as_int(sm.man[MAN_WORDS]);
+  if (nrow) {
+    if (lane < nrow) contact_row_setup(sm, lane, n0, Rg, pf1, pf2, Pref, ax1, ax2);
+    g.sync();
   }
   // projected Gauss-Seidel: <= 5 iterations, early exit on the largest squared velocity change
   for (int it = 0; it < SOLVER_ITERS; it++) {
-    s.res = 0.0f;
+    s.big0 = s.big1 = 0.0f;
     if (it & 1) {  // forwards on odd iterations, backwards on even (Bullet's interleaving)
       motor_row<0>(g, s, A0, A1); motor_row<1>(g, s, A0, A1); motor_row<2>(g, s, A0, A1);
       motor_row<3>(g, s, A0, A1); motor_row<4>(g, s, A0, A1); motor_row<5>(g, s, A0, A1);
       motor_row<6>(g, s, A0, A1); motor_row<7>(g, s, A0, A1); motor_row<8>(g, s, A0, A1);
-      limit_rows(g, s, sm, lact, true, L.dof0);
+      if (lact) limit_rows(g, s, sm, lact, true, L.dof0, A0, A1);
     } else {
-      limit_rows(g, s, sm, lact, false, L.dof0);
+      if (lact) limit_rows(g, s, sm, lact, false, L.dof0, A0, A1);
       motor_row<8>(g, s, A0, A1); motor_row<7>(g, s, A0, A1); motor_row<6>(g, s, A0, A1);
       motor_row<5>(g, s, A0, A1); motor_row<4>(g, s, A0, A1); motor_row<3>(g, s, A0, A1);
       motor_row<2>(g, s, A0, A1); motor_row<1>(g, s, A0, A1); motor_row<0>(g, s, A0, A1);
     }
-    float cres = 0.0f;  // contact rows: every lane computes the same impulse
-    for (int c = 0; c < nrow; c++) {
-      float* row = sm.rows[c * 3];
-      const float v = g.sum(row[R_J + L.dof0] * s.dqd0 + (hand ? row[R_J + 8] * s.dqd1 : 0.0f));
-      const float app = row[R_APP];
-      float dl = row[R_RHS] - v * row[R_DINV];
-      const float sum = fminf(fmaxf(app + dl, 0.0f), 1e10f);
-      dl = sum - app;
-      g.sync();  // every lane has read the old impulse
-      if (lane == 0) row[R_APP] = sum;
-      s.dqd0 += row[R_MJ + L.dof0] * dl;
-      if (hand) s.dqd1 += row[R_MJ + 8] * dl;
-      const float rr = dl * row[R_DENOM];
-      cres = fmaxf(cres, rr * rr);
-    }
-    if (nrow) g.sync();
-    for (int c = 0; c < nrow; c++) {  // implicit friction cone: both tangent rows of a point together
-      const float total = sm.rows[c * 3][R_APP];
-      if (!(total > 0.0f)) continue;
-      float* ra = sm.rows[c * 3 + 1];
-      float* rb = sm.rows[c * 3 + 2];
-      const float lim = ra[R_MU] * total;
-      const float vA = g.sum(ra[R_J + L.dof0] * s.dqd0 + (hand ? ra[R_J + 8] * s.dqd1 : 0.0f));
-      const float vB = g.sum(rb[R_J + L.dof0] * s.dqd0 + (hand ? rb[R_J + 8] * s.dqd1 : 0.0f));
-      const float appA = ra[R_APP], appB = rb[R_APP];
-      float dA = ra[R_RHS] - vA * ra[R_DINV], dB = rb[R_RHS] - vB * rb[R_DINV];
-      float sA = appA + dA, sB = appB + dB;
-      const float s2 = sA * sA + sB * sB;
-      if (s2 >= lim * lim) {
-        const float sc = s2 > 0.0f ? lim * rsqrtf(s2) : 0.0f;
-        const float cA = fabsf(sA) * sc, cB = s2 > 0.0f ? fabsf(sB) * sc : lim;
-        sA = fminf(fmaxf(sA, -cA), cA);
-        sB = fminf(fmaxf(sB, -cB), cB);
-        dA = sA - appA; dB = sB - appB;
-      }
+    const float e0 = s.big0 * s.mdd0, e1 = s.big1 * s.mdd1;
+    float res = fmaxf(e0 * e0, e1 * e1);
+    if (nrow) {
+      // gather the delta velocities, run the contact rows replicated, take the own components back
+      sm.vq[L.dof0] = s.dqd0;
+      if (hand) sm.vq[8] = s.dqd1;
       g.sync();
-      if (lane == 0) { ra[R_APP] = sA; rb[R_APP] = sB; }
-      s.dqd0 += ra[R_MJ + L.dof0] * dA + rb[R_MJ + L.dof0] * dB;
-      if (hand) s.dqd1 += ra[R_MJ + 8] * dA + rb[R_MJ + 8] * dB;
-      const float r1_ = dA * ra[R_DENOM], r2_ = dB * rb[R_DENOM];
-      cres = fmaxf(cres, fmaxf(r1_ * r1_, r2_ * r2_));
+      float dq[ND];
+#pragma unroll
+      for (int j = 0; j < ND; j++) dq[j] = sm.vq[j];
+      res = fmaxf(res, contact_sweep(g, sm, nrow, dq));
+      s.dqd0 = dq[0];
+#pragma unroll
+      for (int j = 1; j < 8; j++) s.dqd0 = lane == j ? dq[j] : s.dqd0;
+      s.dqd1 = dq[8];
     }
-    if (nrow) g.sync();
-    const float res = g.maxv(fmaxf(s.res, cres));
+    res = g.maxv(res);
     if (res <= RESIDUAL_THRESHOLD) break;
   }
   // 9. semi-implicit Euler

@@ -451,8 +451,26 @@ __device__ __noinline__ void invert_spd9(float M[ND][ND], float Minv[ND][ND]) {
 // ---- box-box contact generation (SAT + incident-face clipping, after btBoxBoxDetector) -------
 struct Contact { V3 pB, nB; float dist; };
 
-__device__ int clip_quad_to_rect(const float h[2], const float quad[8], float out[16]) {
-  float buf[2][16];
+// Dynamically indexed work arrays of the narrowphase.  The thread-per-env kernels keep them in (L1-resident)
+// local memory; the lane-cooperative kernel points them at shared memory, where its L1 share is tiny.
+struct BoxScratch {
+  float quad[8], ret[16], buf[2][16], dep[8], ang[8];
+  V3 point[8];
+  int idx[8];
+  bool avail[8];
+  Contact out[4];
+};
+
+__device__ int clip_quad_to_rect(const float h[2], const float quad[8], float out[16], float (*buf)[16]) {
+  // nothing to clip (the usual case: a small face resting inside a large one): the clipper would copy the quad
+  bool inside = true;
+#pragma unroll
+  for (int i = 0; i < 4; i++) inside = inside && fabsf(quad[2 * i]) < h[0] && fabsf(quad[2 * i + 1]) < h[1];
+  if (inside) {
+#pragma unroll
+    for (int i = 0; i < 8; i++) out[i] = quad[i];
+    return 4;
+  }
   int nq = 4, nr = 0, cur = 0;
 #pragma unroll
   for (int i = 0; i < 8; i++) buf[0][i] = quad[i];
@@ -485,7 +503,7 @@ __device__ int clip_quad_to_rect(const float h[2], const float quad[8], float ou
   return nr;
 }
 
-__device__ void cull_points(int n, const float* p, int m, int i0, int* iret) {
+__device__ void cull_points(int n, const float* p, int m, int i0, int* iret, float* A, bool* avail) {
   float a, cx, cy, q;
   if (n == 1) { cx = p[0]; cy = p[1]; }
   else if (n == 2) { cx = 0.5f * (p[0] + p[2]); cy = 0.5f * (p[1] + p[3]); }
@@ -500,7 +518,6 @@ __device__ void cull_points(int n, const float* p, int m, int i0, int* iret) {
     cx = a * (cx + q * (p[2 * n - 2] + p[0]));
     cy = a * (cy + q * (p[2 * n - 1] + p[1]));
   }
-  float A[8]; bool avail[8];
   for (int i = 0; i < n; i++) { A[i] = atan2f(p[2 * i + 1] - cy, p[2 * i] - cx); avail[i] = true; }
   avail[i0] = false; iret[0] = i0;
   for (int j = 1; j < m; j++) {
@@ -518,7 +535,8 @@ __device__ void cull_points(int n, const float* p, int m, int i0, int* iret) {
 
 // Boxes: centre p, orientation R (columns = box axes), half extents.  Up to 4 contacts out:
 // point on B, normal on B (pointing from B to A), signed distance (<= 0).
-__device__ int box_box(V3 p1, const M3& R1, V3 A, V3 p2, const M3& R2, V3 B, Contact* out) {
+__device__ int box_box(V3 p1, const M3& R1, V3 A, V3 p2, const M3& R2, V3 B, BoxScratch& scr) {
+  Contact* out = scr.out;
   V3 p = p2 - p1;
   V3 pp = mulT(R1, p);
   float R[3][3], Q[3][3];
@@ -615,7 +633,7 @@ __device__ int box_box(V3 p1, const M3& R1, V3 A, V3 p2, const M3& R2, V3 B, Con
   V3 ra1 = col(Ra, code1), ra2 = col(Ra, code2), rb1 = col(Rb, a1), rb2 = col(Rb, a2);
   float c1 = dot(center, ra1), c2 = dot(center, ra2);
   float m11 = dot(ra1, rb1), m12 = dot(ra1, rb2), m21 = dot(ra2, rb1), m22 = dot(ra2, rb2);
-  float quad[8];
+  float* quad = scr.quad;
   {
     float k1 = m11 * Sb[a1], k2 = m21 * Sb[a1], k3 = m12 * Sb[a2], k4 = m22 * Sb[a2];
     quad[0] = c1 - k1 - k3; quad[1] = c2 - k2 - k4;
@@ -623,10 +641,11 @@ __device__ int box_box(V3 p1, const M3& R1, V3 A, V3 p2, const M3& R2, V3 B, Con
     quad[4] = c1 + k1 + k3; quad[5] = c2 + k2 + k4;
     quad[6] = c1 + k1 - k3; quad[7] = c2 + k2 - k4;
   }
-  float rect[2] = {Sa[code1], Sa[code2]}, ret[16];
-  int n = clip_quad_to_rect(rect, quad, ret);
+  float rect[2] = {Sa[code1], Sa[code2]};
+  float* ret = scr.ret;
+  int n = clip_quad_to_rect(rect, quad, ret, scr.buf);
   if (n < 1) return 0;
-  V3 point[8]; float dep[8];
+  V3* point = scr.point; float* dep = scr.dep;
   float det1 = 1.0f / (m11 * m22 - m12 * m21);
   m11 *= det1; m12 *= det1; m21 *= det1; m22 *= det1;
   int cnum = 0;
@@ -638,12 +657,13 @@ __device__ int box_box(V3 p1, const M3& R1, V3 A, V3 p2, const M3& R2, V3 B, Con
     if (dp >= 0) { point[cnum] = pt; dep[cnum] = dp; ret[2 * cnum] = ret[2 * j]; ret[2 * cnum + 1] = ret[2 * j + 1]; cnum++; }
   }
   if (cnum < 1) return 0;
-  int maxc = cnum < 4 ? cnum : 4, idx[8];
+  int maxc = cnum < 4 ? cnum : 4;
+  int* idx = scr.idx;
   if (cnum <= maxc) { for (int j = 0; j < cnum; j++) idx[j] = j; }
   else {
     int i1 = 0; float maxdepth = dep[0];
     for (int i = 1; i < cnum; i++) if (dep[i] > maxdepth) { maxdepth = dep[i]; i1 = i; }
-    cull_points(cnum, ret, maxc, i1, idx);
+    cull_points(cnum, ret, maxc, i1, idx, scr.ang, scr.avail);
   }
   for (int j = 0; j < maxc; j++) {
     int k = idx[j];

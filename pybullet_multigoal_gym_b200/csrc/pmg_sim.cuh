@@ -146,7 +146,7 @@ __device__ void manifold_refresh(ManRef& e, int k, float thr, V3 pa, const M3& R
 
 // One collision pair: broadphase (world AABBs grown by the margin), box-box narrowphase into the
 // persistent manifold, refresh.  Boxes given by centre, orientation, half extents.
-__device__ void collide_pair(ManRef& e, int k, V3 pa, const M3& Ra, V3 ha, V3 pb, const M3& Rb, V3 hb) {
+__device__ void collide_pair(ManRef& e, int k, V3 pa, const M3& Ra, V3 ha, V3 pb, const M3& Rb, V3 hb, BoxScratch& scr) {
   V3 d = pa - pb;
   float ex = fabsf(Ra.r0.x) * ha.x + fabsf(Ra.r0.y) * ha.y + fabsf(Ra.r0.z) * ha.z + fabsf(Rb.r0.x) * hb.x + fabsf(Rb.r0.y) * hb.y + fabsf(Rb.r0.z) * hb.z + 2 * BROADPHASE_MARGIN;
   float ey = fabsf(Ra.r1.x) * ha.x + fabsf(Ra.r1.y) * ha.y + fabsf(Ra.r1.z) * ha.z + fabsf(Rb.r1.x) * hb.x + fabsf(Rb.r1.y) * hb.y + fabsf(Rb.r1.z) * hb.z + 2 * BROADPHASE_MARGIN;
@@ -156,8 +156,8 @@ __device__ void collide_pair(ManRef& e, int k, V3 pa, const M3& Ra, V3 ha, V3 pb
     return;
   }
   float thr = BREAKING_THRESHOLD_FACTOR * fminf(norm(ha), norm(hb));
-  Contact c[4];
-  int nc = box_box(pa, Ra, ha, pb, Rb, hb, c);
+  const Contact* c = scr.out;
+  int nc = box_box(pa, Ra, ha, pb, Rb, hb, scr);
   for (int i = 0; i < nc; i++) {
     V3 wa = c[i].pB + c[i].dist * c[i].nB;
     manifold_add(e, k, thr, mulT(Ra, wa - pa), mulT(Rb, c[i].pB - pb), c[i].nB, c[i].dist);
@@ -186,8 +186,9 @@ __device__ void collide(Env<NBLK>& e, const Frames& f) {
       continue;
     }
     float thr = BREAKING_THRESHOLD_FACTOR * fminf(norm(ha), norm(hb));
-    Contact c[4];
-    int nc = box_box(pa, Ra, ha, pb, Rb, hb, c);
+    BoxScratch scr;
+    const Contact* c = scr.out;
+    int nc = box_box(pa, Ra, ha, pb, Rb, hb, scr);
     for (int i = 0; i < nc; i++) {
       V3 wa = c[i].pB + c[i].dist * c[i].nB;
       manifold_add(e, k, thr, mulT(Ra, wa - pa), mulT(Rb, c[i].pB - pb), c[i].nB, c[i].dist);

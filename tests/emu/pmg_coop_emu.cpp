@@ -148,7 +148,7 @@ int pmg_emu_substep(const float* q, const float* qd, float* minv81, float* q_out
   memset(&sm, 0, sizeof sm);
   MinvArgs a{&sm, q, qd, minv81, q_out, qd_out};
   int rc = pmg_emu::run_group(substep_body, &a);
-  for (int i = 0; i < 81; i++) minv81[i] = sm.minv[i];
+  for (int r = 0; r < 9; r++) for (int c = 0; c < 9; c++) minv81[r * 9 + c] = sm.minv[r * coop::MINV_LD + c];
   return rc;
 }
 
