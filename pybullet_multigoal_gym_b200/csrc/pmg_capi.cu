@@ -250,16 +250,21 @@ __global__ void __launch_bounds__(32) step_kernel(StepIO io) {
 // (Packing the environments whose jaws rest on the table into the same warps was tried and measured slower:
 // the step lasts as long as its slowest warp, and four contact octets in one warp serialise their divergent
 // narrowphase branches.)
+constexpr int COOP_TABLE_BYTES = coop::GL * coop::LC_W * sizeof(float);
+static_assert(COOP_TABLE_BYTES % 16 == 0, "EnvSmem must stay 16-byte aligned behind the constant table");
 constexpr int COOP_MIN_BLOCKS = 14;  // batch 8192 = 2048 blocks = 13.8 per SM: keep them all resident
 __global__ void __launch_bounds__(32, COOP_MIN_BLOCKS) step_kernel_coop_reach(StepIO io) {
   extern __shared__ __align__(16) unsigned char coop_smem[];
   const int lane32 = threadIdx.x & 31, grp = lane32 >> 3;
+  float* lane_consts = reinterpret_cast<float*>(coop_smem);
+  if (lane32 < coop::GL) coop::fill_lane_constants(lane_consts + lane32 * coop::LC_W, lane32);
+  __syncwarp();
   const int env = blockIdx.x * (32 / coop::GL) + grp;
   if (env >= io.batch) return;  // a whole octet leaves together
   coop::Grp g;
   g.lane = lane32 & (coop::GL - 1); g.shift = grp * coop::GL; g.mask = 0xffu << g.shift;
-  coop::EnvSmem& sm = reinterpret_cast<coop::EnvSmem*>(coop_smem)[grp];
-  coop::step_env_reach(g, sm, io, env);
+  coop::EnvSmem& sm = reinterpret_cast<coop::EnvSmem*>(coop_smem + COOP_TABLE_BYTES)[grp];
+  coop::step_env_reach(g, sm, lane_consts, io, env);
 }
 
 struct ResetIO { StepIO io; const uint8_t* mask; const float* spawn; float tip_init[3]; };
@@ -484,7 +489,7 @@ void launch_step(pmg_handle* h, const StepIO& io_in, cudaStream_t st) {
   StepIO io = io_in;
   if (TASK == 0 && h->coop) {
     constexpr int EPB = 32 / coop::GL;  // environments per block
-    const size_t smem = EPB * sizeof(coop::EnvSmem);
+    const size_t smem = COOP_TABLE_BYTES + EPB * sizeof(coop::EnvSmem);
     static bool hinted_coop = false;
     if (!hinted_coop) {
       cudaFuncSetAttribute(step_kernel_coop_reach, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);

@@ -31,8 +31,8 @@ namespace coop {
 
 constexpr int GL = 8;        // lanes per environment
 constexpr int MAXPTS = 8;    // finger-table contact points: 2 pairs x 4
-constexpr int ROW_W = 28;    // floats per contact row record (16-byte aligned vectors)
-constexpr int R_J = 0, R_MJ = 12, R_RHS = 21, R_DINV = 22, R_DENOM = 23, R_APP = 24, R_MU = 25;
+constexpr int ROW_W = 24;    // floats per contact row record: J[9] rhs dinv app | MJ[9] denom mu . (16-byte aligned halves)
+constexpr int R_J = 0, R_RHS = 9, R_DINV = 10, R_APP = 11, R_MJ = 12, R_DENOM = 21, R_MU = 22;
 constexpr int MINV_LD = 12;  // row stride of M^-1 in shared memory
 constexpr int COOP_PAIRS = 2;
 
@@ -41,8 +41,9 @@ struct __align__(16) EnvSmem {
   float pub[7][8];                  // per arm dof: axis a, v = (p - Pref) x a
   float minv[ND * MINV_LD];         // 9x9, rows padded to 12
   float man[84];                    // persistent manifolds of the 2 finger-table pairs (2 x 41 words)
+  float hand[24];                   // gripper frame for the contact rows: Rg[9] pf1 pf2 Pref ax1 (kept out of registers)
   float vq[12];                     // joint velocities (row set-up), then PGS delta velocities (contact sweeps)
-  float rows[MAXPTS * 3][ROW_W];    // contact rows: J[9] . MJ[9] rhs dinv denom app mu
+  float rows[MAXPTS * 3][ROW_W];    // contact rows (layout R_* above); narrowphase scratch before they are built
 };
 
 // ---- the group (octet) interface ---------------------------------------------------------------
@@ -87,25 +88,28 @@ struct Grp {
 // Dof slots: slot 0 is arm joint `lane` on lanes 0..6 and finger1 (dof 7) on lane 7; slot 1 is finger2
 // (dof 8) on lane 7 and unused (zero) elsewhere.
 struct Lane {
-  M3 jrot; V3 jxyz, com, inertia;  // chain body `lane`: joint frame, COM, principal inertia
-  float mass, msub;                // own mass; mass of the subtree rooted here
-  float lower0, upper0, lower1, upper1, damp0;
+  const float* lc;  // this lane's row of the constant table (shared memory), see LC_* below
   float q0, q1, qd0, qd1, mt0, mt1, mi0, mi1, dtau0, dtau1;
   int dof0;
 };
 
-__device__ __forceinline__ void load_lane_constants(const Grp& g, Lane& L) {
-  const int b = g.lane;  // chain body
-  L.jrot = load_jrot(b);
-  L.jxyz = v3(c_jxyz[b][0], c_jxyz[b][1], c_jxyz[b][2]);
-  L.com = v3(c_com[b][0], c_com[b][1], c_com[b][2]);
-  L.inertia = v3(c_inertia[b][0], c_inertia[b][1], c_inertia[b][2]);
-  L.mass = c_mass[b];
-  L.msub = g.rscan(L.mass + (b == 7 ? c_mass[PMG_BODY_FINGER1] + c_mass[PMG_BODY_FINGER2] : 0.0f));
-  L.dof0 = b;  // lane 7 -> dof 7
-  L.lower0 = c_dof_lower[b]; L.upper0 = c_dof_upper[b];
-  L.lower1 = c_dof_lower[8]; L.upper1 = c_dof_upper[8];
-  L.damp0 = c_dof_damping[b];
+// Per-lane model constants of chain body `lane` (link_1..link_7, gripper base): one table per block in
+// shared memory, read where they are used instead of being held in ~25 registers through the whole substep
+// (the kernel has 128 registers per thread: 4 warps x 32 x 128 fill a scheduler's register file).
+constexpr int LC_JROT = 0, LC_JXYZ = 9, LC_COM = 12, LC_INERTIA = 15, LC_MASS = 18, LC_MSUB = 19, LC_LOWER = 20, LC_UPPER = 21, LC_DAMP = 22;
+constexpr int LC_W = 28;  // row stride: lanes 0..7 hit 8 different banks
+__device__ __forceinline__ V3 lc3(const float* lc, int o) { return v3(lc[o], lc[o + 1], lc[o + 2]); }
+
+__device__ inline void fill_lane_constants(float* row, int b) {  // b = chain body = lane
+#pragma unroll
+  for (int k = 0; k < 9; k++) row[LC_JROT + k] = c_jrot[b][k];
+#pragma unroll
+  for (int k = 0; k < 3; k++) { row[LC_JXYZ + k] = c_jxyz[b][k]; row[LC_COM + k] = c_com[b][k]; row[LC_INERTIA + k] = c_inertia[b][k]; }
+  row[LC_MASS] = c_mass[b];
+  float msub = c_mass[PMG_BODY_FINGER1] + c_mass[PMG_BODY_FINGER2];  // mass of the subtree rooted at this body
+  for (int k = 7; k >= b; k--) msub += c_mass[k];
+  row[LC_MSUB] = msub;
+  row[LC_LOWER] = c_dof_lower[b]; row[LC_UPPER] = c_dof_upper[b]; row[LC_DAMP] = c_dof_damping[b];
 }
 
 __device__ __forceinline__ Sym3 sym_add(const Sym3& a, const Sym3& b) {
@@ -132,11 +136,12 @@ __device__ __forceinline__ Sym3 point_inertia(float m, V3 c) {
 __device__ __forceinline__ void chain_fk(const Grp& g, const Lane& L, float qarm, M3& R, V3& p) {
   float s, c;
   sincosf(qarm, &s, &c);
-  const M3& J = L.jrot;  // J * Rz(q): new x column = c*x + s*y, new y column = -s*x + c*y
+  M3 J;  // J * Rz(q): new x column = c*x + s*y, new y column = -s*x + c*y
+  J.r0 = lc3(L.lc, LC_JROT); J.r1 = lc3(L.lc, LC_JROT + 3); J.r2 = lc3(L.lc, LC_JROT + 6);
   R.r0 = v3(c * J.r0.x + s * J.r0.y, -s * J.r0.x + c * J.r0.y, J.r0.z);
   R.r1 = v3(c * J.r1.x + s * J.r1.y, -s * J.r1.x + c * J.r1.y, J.r1.z);
   R.r2 = v3(c * J.r2.x + s * J.r2.y, -s * J.r2.x + c * J.r2.y, J.r2.z);
-  p = L.jxyz;
+  p = lc3(L.lc, LC_JXYZ);
 #pragma unroll
   for (int d = 1; d < GL; d <<= 1) {
     M3 Ro = g.up(R, d);
@@ -318,7 +323,12 @@ __device__ __forceinline__ void limit_rows(const Grp& g, SolverLane& s, const En
 // the arm axes, M^-1 and the joint velocities are read from shared memory -- so the (up to) 8 points are set
 // up in parallel and without a single shuffle.  J of an arm joint at contact point w is
 // d . (a_j x (w - p_j)) = a_j . ((w - Pref) x d) + d . vv_j with the published vv_j = (p_j - Pref) x a_j.
-__device__ __noinline__ void contact_row_setup(EnvSmem& sm, int c, int n0, const M3& Rg, V3 pf1, V3 pf2, V3 Pref, V3 ax1, V3 ax2) {
+__device__ __noinline__ void contact_row_setup(EnvSmem& sm, int c, int n0) {
+  const float* hd = sm.hand;
+  M3 Rg;
+  Rg.r0 = v3(hd[0], hd[1], hd[2]); Rg.r1 = v3(hd[3], hd[4], hd[5]); Rg.r2 = v3(hd[6], hd[7], hd[8]);
+  const V3 pf1 = v3(hd[9], hd[10], hd[11]), pf2 = v3(hd[12], hd[13], hd[14]), Pref = v3(hd[15], hd[16], hd[17]);
+  const V3 ax1 = v3(hd[18], hd[19], hd[20]), ax2 = -ax1;
   const int k = c < n0 ? 0 : 1, i = k ? c - n0 : c;
   const float* mp = sm.man + k * MAN_WORDS + 1 + 10 * i;
   const V3 lA = v3(mp[0], mp[1], mp[2]), nB = v3(mp[6], mp[7], mp[8]);
@@ -377,7 +387,12 @@ __device__ __forceinline__ void row_axpy(const float* v, float s, float* dq) {
 // One Gauss-Seidel pass over the contact rows (all normals, then the friction pairs with the implicit cone).
 // Every lane of the octet does the same arithmetic on a replicated delta-velocity vector: no shuffles on
 // this path, which is usually executed by one octet of a warp while the others wait.
-__device__ __forceinline__ float contact_sweep(const Grp& g, EnvSmem& sm, int nrow, float* dq) {
+// Out of line on purpose: it keeps this (rarely executed) code away from the instruction stream of the
+// contact-free solver loop.  Delta velocities come in and go out through sm.vq.
+__device__ __noinline__ float contact_sweep(Grp g, EnvSmem& sm, int nrow) {
+  float dq[ND];
+#pragma unroll
+  for (int j = 0; j < ND; j++) dq[j] = sm.vq[j];
   float cres = 0.0f;
 #pragma unroll 1
   for (int c = 0; c < nrow; c++) {
@@ -419,6 +434,11 @@ __device__ __forceinline__ float contact_sweep(const Grp& g, EnvSmem& sm, int nr
     g.sync();
     if (g.lane == 0) { ra[R_APP] = sA; rb[R_APP] = sB; }
   }
+  g.sync();  // every lane has read sm.vq (and the impulses are visible)
+  if (g.lane == 0) {
+#pragma unroll
+    for (int j = 0; j < ND; j++) sm.vq[j] = dq[j];
+  }
   g.sync();
   return cres;
 }
@@ -448,18 +468,19 @@ __device__ void substep(const Grp& g, EnvSmem& sm, Lane& L) {
   V3 Fs, Ns, hs;
   Sym3 Is;
   {
-    const V3 rc = mul(R, L.com);
-    const Sym3 Iw = world_inertia(R, L.inertia);
+    const float mass = L.lc[LC_MASS];
+    const V3 rc = mul(R, lc3(L.lc, LC_COM));
+    const Sym3 Iw = world_inertia(R, lc3(L.lc, LC_INERTIA));
     const V3 wxrc = cross(w, rc);
     const V3 a_c = ao + cross(al, rc) + cross(w, wxrc);
     const V3 v_c = vo + wxrc;
     const float kl = LINK_DAMPING + LINK_DAMPING * norm(v_c), ka = LINK_DAMPING + LINK_DAMPING * norm(w);
-    const V3 Fc = L.mass * a_c + (L.mass * kl) * v_c;
+    const V3 Fc = mass * a_c + (mass * kl) * v_c;
     const V3 Iww = mul(Iw, w);
     const V3 Nc = mul(Iw, al) + cross(w, Iww) + ka * Iww;
     const V3 c = (p - Pref) + rc;
-    Fs = Fc; Ns = Nc + cross(c, Fc); hs = L.mass * c;
-    Is = sym_add(Iw, point_inertia(L.mass, c));
+    Fs = Fc; Ns = Nc + cross(c, Fc); hs = mass * c;
+    Is = sym_add(Iw, point_inertia(mass, c));
   }
   // 3b. the two fingers (same orientation as the gripper base, zero COM offset), by every lane
   const M3 Rg = g.shfl(R, 7);
@@ -495,6 +516,13 @@ __device__ void substep(const Grp& g, EnvSmem& sm, Lane& L) {
     }
   }
   const V3 pf1 = Pref + r1, pf2 = Pref + r2;
+  if (lane == 2) {  // stash the gripper frame for the contact-row set-up (lanes 0 and 1 are about to collide)
+    float* hd = sm.hand;
+    hd[0] = Rg.r0.x; hd[1] = Rg.r0.y; hd[2] = Rg.r0.z; hd[3] = Rg.r1.x; hd[4] = Rg.r1.y; hd[5] = Rg.r1.z;
+    hd[6] = Rg.r2.x; hd[7] = Rg.r2.y; hd[8] = Rg.r2.z;
+    hd[9] = pf1.x; hd[10] = pf1.y; hd[11] = pf1.z; hd[12] = pf2.x; hd[13] = pf2.y; hd[14] = pf2.z;
+    hd[15] = Pref.x; hd[16] = Pref.y; hd[17] = Pref.z; hd[18] = ax1.x; hd[19] = ax1.y; hd[20] = ax1.z;
+  }
   // collision detection of the two finger-table pairs: lane k runs pair k on the shared-memory manifold
   if (lane < COOP_PAIRS) {
     ManRef mr; mr.man = sm.man; mr.stride = 1;
@@ -510,7 +538,7 @@ __device__ void substep(const Grp& g, EnvSmem& sm, Lane& L) {
   // 5. joint-space inertia matrix rows and bias forces
   const V3 vv = cross(p - Pref, a);  // velocity of the reference point per unit joint rate
   const V3 n_own = mul(Is, a) + cross(hs, vv);
-  const V3 l_own = L.msub * vv + cross(a, hs);
+  const V3 l_own = L.lc[LC_MSUB] * vv + cross(a, hs);
   const float b0 = arm ? dot(a, Ns) + dot(vv, Fs) : dot(ax1, F1);
   const float b1 = dot(ax2, F2);
   if (arm) {
@@ -593,7 +621,7 @@ __device__ void substep(const Grp& g, EnvSmem& sm, Lane& L) {
     s.rhs0 = (tv0 - L.qd0) * s.dinv0; s.rhs1 = (tv1 - L.qd1) * s.dinv1;
     s.lim0 = L.mi0; s.lim1 = L.mi1; s.app0 = s.app1 = 0.0f;
     // btMultiBodyJointLimitConstraint rows, only when violated
-    const float p00 = L.q0 - L.lower0, p01 = L.upper0 - L.q0, p10 = L.q1 - L.lower1, p11 = L.upper1 - L.q1;
+    const float p00 = L.q0 - L.lc[LC_LOWER], p01 = L.lc[LC_UPPER] - L.q0, p10 = L.q1 - c_dof_lower[8], p11 = c_dof_upper[8] - L.q1;
     const bool v00 = !(p00 > 0.0f), v01 = !(p01 > 0.0f), v10 = hand && !(p10 > 0.0f), v11 = hand && !(p11 > 0.0f);
     const unsigned m00 = g.ballot(v00), m01 = g.ballot(v01), m10 = g.ballot(v10), m11 = g.ballot(v11);
     s.lrhs00 = s.lrhs01 = s.lrhs10 = s.lrhs11 = 0.0f;
@@ -616,7 +644,7 @@ __device__ void substep(const Grp& g, EnvSmem& sm, Lane& L) {
   const int n0 = __float_as_int(sm.man[0]);
   const int nrow = n0 + __float_as_int(sm.man[MAN_WORDS]);
   if (nrow) {
-    if (lane < nrow) contact_row_setup(sm, lane, n0, Rg, pf1, pf2, Pref, ax1, ax2);
+    if (lane < nrow) contact_row_setup(sm, lane, n0);
     g.sync();
   }
   // projected Gauss-Seidel: <= 5 iterations, early exit on the largest squared velocity change
@@ -640,14 +668,9 @@ __device__ void substep(const Grp& g, EnvSmem& sm, Lane& L) {
       sm.vq[L.dof0] = s.dqd0;
       if (hand) sm.vq[8] = s.dqd1;
       g.sync();
-      float dq[ND];
-#pragma unroll
-      for (int j = 0; j < ND; j++) dq[j] = sm.vq[j];
-      res = fmaxf(res, contact_sweep(g, sm, nrow, dq));
-      s.dqd0 = dq[0];
-#pragma unroll
-      for (int j = 1; j < 8; j++) s.dqd0 = lane == j ? dq[j] : s.dqd0;
-      s.dqd1 = dq[8];
+      res = fmaxf(res, contact_sweep(g, sm, nrow));
+      s.dqd0 = sm.vq[L.dof0];
+      s.dqd1 = sm.vq[8];
     }
     res = g.maxv(res);
     if (res <= RESIDUAL_THRESHOLD) break;
@@ -662,14 +685,16 @@ __device__ void substep(const Grp& g, EnvSmem& sm, Lane& L) {
 // ---- one env.step() of a Reach environment (TASK 0, no blocks) -------------------------------------
 // `env` is the environment index, state / manifold are the same [word][env] arrays the thread-per-env
 // kernels use, so reset_kernel, pmg_get_state / pmg_set_state and the reward path are shared.
-__device__ void step_env_reach(const Grp& g, EnvSmem& sm, const StepIO& io, int env) {
+// `lane_consts`: the block's constant table (8 rows of LC_W floats, filled with fill_lane_constants).
+__device__ void step_env_reach(const Grp& g, EnvSmem& sm, const float* lane_consts, const StepIO& io, int env) {
   using D = Dims<0, 0>;
   const int lane = g.lane;
   const bool arm = lane < 7, hand = lane == 7;
   const size_t B = io.batch;
   float* s = io.state + env;
   Lane L;
-  load_lane_constants(g, L);
+  L.lc = lane_consts + lane * LC_W;
+  L.dof0 = lane;  // lane 7 -> dof 7 (finger1); it also owns dof 8 in slot 1
   L.q0 = s[(ST_Q + lane) * B]; L.qd0 = s[(ST_QD + lane) * B]; L.mt0 = s[(ST_MT + lane) * B]; L.mi0 = s[(ST_MI + lane) * B];
   L.q1 = hand ? s[(ST_Q + 8) * B] : 0.0f; L.qd1 = hand ? s[(ST_QD + 8) * B] : 0.0f;
   L.mt1 = hand ? s[(ST_MT + 8) * B] : 0.0f; L.mi1 = hand ? s[(ST_MI + 8) * B] : 0.0f;
@@ -688,7 +713,7 @@ __device__ void step_env_reach(const Grp& g, EnvSmem& sm, const StepIO& io, int 
   g.sync();
   // ---- 5 x stepSimulation (kuka.py:223-225), each 20 substeps of 2 ms ----
   for (int call = 0; call < CALLS_PER_ENV_STEP; call++) {
-    L.dtau0 = -L.damp0 * L.qd0;  // joint damping torque, sampled once per stepSimulation call
+    L.dtau0 = -L.lc[LC_DAMP] * L.qd0;  // joint damping torque, sampled once per stepSimulation call
     L.dtau1 = 0.0f;
     for (int sub = 0; sub < SUBSTEPS_PER_CALL; sub++) substep(g, sm, L);
   }

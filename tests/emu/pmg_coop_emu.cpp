@@ -102,11 +102,17 @@ static int run_group(void (*body)(int, void*), void* arg) {
 using namespace pmg;
 
 namespace {
+const float* lane_table() {
+  static float tab[coop::GL * coop::LC_W];
+  static bool init = false;
+  if (!init) { for (int l = 0; l < coop::GL; l++) coop::fill_lane_constants(tab + l * coop::LC_W, l); init = true; }
+  return tab;
+}
 struct StepArgs { coop::EnvSmem* sm; StepIO io; };
 void step_body(int lane, void* arg) {
   StepArgs* a = (StepArgs*)arg;
   coop::Grp g; g.lane = lane;
-  coop::step_env_reach(g, *a->sm, a->io, 0);
+  coop::step_env_reach(g, *a->sm, lane_table(), a->io, 0);
 }
 
 struct MinvArgs { coop::EnvSmem* sm; const float* q; const float* qd; float* minv_out; float* q_out; float* qd_out; };
@@ -114,7 +120,7 @@ void substep_body(int lane, void* arg) {
   MinvArgs* a = (MinvArgs*)arg;
   coop::Grp g; g.lane = lane;
   coop::Lane L;
-  coop::load_lane_constants(g, L);
+  L.lc = lane_table() + lane * coop::LC_W; L.dof0 = lane;
   L.q0 = a->q[lane]; L.qd0 = a->qd[lane];
   L.q1 = lane == 7 ? a->q[8] : 0.0f; L.qd1 = lane == 7 ? a->qd[8] : 0.0f;
   L.mt0 = L.q0; L.mt1 = L.q1; L.mi0 = L.mi1 = 0.0f;  // motors off
@@ -154,5 +160,6 @@ int pmg_emu_substep(const float* q, const float* qd, float* minv81, float* q_out
 
 int pmg_emu_state_words(void) { return Dims<0, 0>::STATE; }
 int pmg_emu_smem_bytes(void) { return (int)sizeof(coop::EnvSmem); }
+int pmg_emu_table_bytes(void) { return (int)(coop::GL * coop::LC_W * sizeof(float)); }
 
 }  // extern "C"

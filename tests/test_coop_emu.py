@@ -36,7 +36,7 @@ def emu():
 
 def test_shared_memory_budget(emu):
     # 4 environments per one-warp block, 14 blocks per SM (batch 8192 on 148 SMs) must fit in 227 KB
-    per_block = 4 * emu.pmg_emu_smem_bytes() + 1024
+    per_block = emu.pmg_emu_table_bytes() + 4 * emu.pmg_emu_smem_bytes() + 1024
     assert 14 * per_block <= 227 * 1024
 
 
