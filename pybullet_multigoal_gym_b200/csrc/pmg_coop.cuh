@@ -32,7 +32,7 @@ namespace coop {
 constexpr int GL = 8;        // lanes per environment
 constexpr int MAXPTS = 8;    // finger-table contact points: 2 pairs x 4
 constexpr int ROW_W = 24;    // floats per contact row record: J[9] rhs dinv app | MJ[9] denom mu . (16-byte aligned halves)
-constexpr int R_J = 0, R_RHS = 9, R_DINV = 10, R_APP = 11, R_MJ = 12, R_DENOM = 21, R_MU = 22;
+constexpr int R_J = 0, R_RHS = 9, R_DINV = 10, R_APP = 11, R_MJ = 12, R_DENOM = 21, R_APP2 = 22;  // impulses are double buffered
 constexpr int MINV_LD = 12;  // row stride of M^-1 in shared memory
 constexpr int COOP_PAIRS = 2;
 
@@ -336,7 +336,6 @@ __device__ __noinline__ void contact_row_setup(EnvSmem& sm, int c, int n0) {
   const V3 wr = mul(Rg, lA) + (k ? pf2 : pf1) - Pref;  // contact point on the finger, relative to Pref
   V3 t1, t2;
   plane_space(nB, t1, t2);
-  const float mu = (float)PMG_FINGER_FRICTION * (float)PMG_TABLE_FRICTION;
 #pragma unroll 1
   for (int kk = 0; kk < 3; kk++) {
     const V3 d = kk == 0 ? nB : (kk == 1 ? t1 : t2);
@@ -369,7 +368,7 @@ __device__ __noinline__ void contact_row_setup(EnvSmem& sm, int c, int n0) {
       if (pen > 0.0f) vel_err -= pen * INV_DT; else pos_err = -pen * CONTACT_ERP * INV_DT;
       rhs = (pos_err + vel_err) * dinv;
     } else rhs = -rel_vel * dinv;
-    row[R_RHS] = rhs; row[R_DINV] = dinv; row[R_DENOM] = denom; row[R_APP] = 0.0f; row[R_MU] = mu;
+    row[R_RHS] = rhs; row[R_DINV] = dinv; row[R_DENOM] = denom; row[R_APP] = 0.0f; row[R_APP2] = 0.0f;
   }
 }
 
@@ -389,7 +388,11 @@ __device__ __forceinline__ void row_axpy(const float* v, float s, float* dq) {
 // this path, which is usually executed by one octet of a warp while the others wait.
 // Out of line on purpose: it keeps this (rarely executed) code away from the instruction stream of the
 // contact-free solver loop.  Delta velocities come in and go out through sm.vq.
-__device__ __noinline__ float contact_sweep(Grp g, EnvSmem& sm, int nrow) {
+__device__ __noinline__ float contact_sweep(Grp g, EnvSmem& sm, int nrow_it) {  // nrow | (iteration parity << 8)
+  const int nrow = nrow_it & 0xff, it = nrow_it >> 8;
+  // The accumulated impulses are double buffered (read slot / write slot swap every iteration, every lane
+  // stores the same value), so no lane waits for another inside the row loops.
+  const int rd = (it & 1) ? R_APP2 : R_APP, wr = (it & 1) ? R_APP : R_APP2;
   float dq[ND];
 #pragma unroll
   for (int j = 0; j < ND; j++) dq[j] = sm.vq[j];
@@ -397,44 +400,45 @@ __device__ __noinline__ float contact_sweep(Grp g, EnvSmem& sm, int nrow) {
 #pragma unroll 1
   for (int c = 0; c < nrow; c++) {
     float* row = sm.rows[c * 3];
-    const float app = row[R_APP];
+    const float app = row[rd];
     float dl = row[R_RHS] - row_dot(row + R_J, dq) * row[R_DINV];
     const float sum = fminf(fmaxf(app + dl, 0.0f), 1e10f);
     dl = sum - app;
     row_axpy(row + R_MJ, dl, dq);
     const float rr = dl * row[R_DENOM];
     cres = fmaxf(cres, rr * rr);
-    g.sync();  // every lane has read the old impulse
-    if (g.lane == 0) row[R_APP] = sum;
+    row[wr] = sum;
   }
-  g.sync();
+  g.sync();  // the new normal impulses bound the friction rows
+  const float mu = (float)PMG_FINGER_FRICTION * (float)PMG_TABLE_FRICTION;
 #pragma unroll 1
   for (int c = 0; c < nrow; c++) {  // implicit friction cone: both tangent rows of a point together
-    const float total = sm.rows[c * 3][R_APP];
-    if (!(total > 0.0f)) continue;
     float* ra = sm.rows[c * 3 + 1];
     float* rb = sm.rows[c * 3 + 2];
-    const float lim = ra[R_MU] * total;
-    const float appA = ra[R_APP], appB = rb[R_APP];
-    float dA = ra[R_RHS] - row_dot(ra + R_J, dq) * ra[R_DINV], dB = rb[R_RHS] - row_dot(rb + R_J, dq) * rb[R_DINV];
-    float sA = appA + dA, sB = appB + dB;
-    const float s2 = sA * sA + sB * sB;
-    if (s2 >= lim * lim) {
-      // |lim sin(atan2(sA, sB))| = lim |sA| / sqrt(sA^2 + sB^2), likewise the cosine for sB
-      const float sc = s2 > 0.0f ? lim * rsqrtf(s2) : 0.0f;
-      const float cA = fabsf(sA) * sc, cB = s2 > 0.0f ? fabsf(sB) * sc : lim;
-      sA = fminf(fmaxf(sA, -cA), cA);
-      sB = fminf(fmaxf(sB, -cB), cB);
-      dA = sA - appA; dB = sB - appB;
+    const float total = sm.rows[c * 3][wr];
+    const float appA = ra[rd], appB = rb[rd];
+    float sA = appA, sB = appB;
+    if (total > 0.0f) {
+      const float lim = mu * total;
+      float dA = ra[R_RHS] - row_dot(ra + R_J, dq) * ra[R_DINV], dB = rb[R_RHS] - row_dot(rb + R_J, dq) * rb[R_DINV];
+      sA = appA + dA; sB = appB + dB;
+      const float s2 = sA * sA + sB * sB;
+      if (s2 >= lim * lim) {
+        // |lim sin(atan2(sA, sB))| = lim |sA| / sqrt(sA^2 + sB^2), likewise the cosine for sB
+        const float sc = s2 > 0.0f ? lim * rsqrtf(s2) : 0.0f;
+        const float cA = fabsf(sA) * sc, cB = s2 > 0.0f ? fabsf(sB) * sc : lim;
+        sA = fminf(fmaxf(sA, -cA), cA);
+        sB = fminf(fmaxf(sB, -cB), cB);
+        dA = sA - appA; dB = sB - appB;
+      }
+      row_axpy(ra + R_MJ, dA, dq);
+      row_axpy(rb + R_MJ, dB, dq);
+      const float r1_ = dA * ra[R_DENOM], r2_ = dB * rb[R_DENOM];
+      cres = fmaxf(cres, fmaxf(r1_ * r1_, r2_ * r2_));
     }
-    row_axpy(ra + R_MJ, dA, dq);
-    row_axpy(rb + R_MJ, dB, dq);
-    const float r1_ = dA * ra[R_DENOM], r2_ = dB * rb[R_DENOM];
-    cres = fmaxf(cres, fmaxf(r1_ * r1_, r2_ * r2_));
-    g.sync();
-    if (g.lane == 0) { ra[R_APP] = sA; rb[R_APP] = sB; }
+    ra[wr] = sA; rb[wr] = sB;  // carried over unchanged while the point is open
   }
-  g.sync();  // every lane has read sm.vq (and the impulses are visible)
+  g.sync();  // every lane has read sm.vq
   if (g.lane == 0) {
 #pragma unroll
     for (int j = 0; j < ND; j++) sm.vq[j] = dq[j];
@@ -668,7 +672,7 @@ __device__ void substep(const Grp& g, EnvSmem& sm, Lane& L) {
       sm.vq[L.dof0] = s.dqd0;
       if (hand) sm.vq[8] = s.dqd1;
       g.sync();
-      res = fmaxf(res, contact_sweep(g, sm, nrow));
+      res = fmaxf(res, contact_sweep(g, sm, nrow | ((it & 1) << 8)));
       s.dqd0 = sm.vq[L.dof0];
       s.dqd1 = sm.vq[8];
     }
