@@ -256,6 +256,7 @@ typedef struct {
 
 struct PmgoEnv {
   int task, nb, binary, max_steps, grasping, has_obj, adim;
+  int multi, grip, jc; /* multi-block obs layout (stack / rearrange); grip-informed goal; joint-space control */
   double thr;
   int dims[4];
   /* state */
@@ -1114,19 +1115,31 @@ void pmgo_step_simulation(PmgoEnv* e) {
 static void robot_reset(PmgoEnv* e);
 
 PmgoEnv* pmgo_create(int task, int num_block, int binary_reward, double thr, int max_steps) {
+  return pmgo_create_ex(task, num_block, binary_reward, thr, max_steps, 0, 0);
+}
+
+PmgoEnv* pmgo_create_ex(int task, int num_block, int binary_reward, double thr, int max_steps,
+                        int grip_informed_goal, int joint_control) {
   PmgoEnv* e = (PmgoEnv*)calloc(1, sizeof *e);
   e->task = task; e->binary = binary_reward; e->thr = thr; e->max_steps = max_steps;
   e->has_obj = task != PMGO_REACH;
+  e->multi = task == PMGO_BLOCK_STACK || task == PMGO_BLOCK_REARRANGE;
+  /* kuka_multi_step_envs.py:30 (stack: grasping) / :170 (rearrange: grasping=False, start on the table) */
   e->grasping = task == PMGO_PICK_AND_PLACE || task == PMGO_BLOCK_STACK;
-  e->nb = task == PMGO_REACH ? 0 : (task == PMGO_BLOCK_STACK ? num_block : 1);
-  e->adim = e->grasping ? 4 : 3;
+  e->grip = grip_informed_goal && task == PMGO_BLOCK_STACK; /* rearrange asserts it off (kuka_multi_step_envs.py:158) */
+  e->jc = joint_control != 0;
+  e->nb = task == PMGO_REACH ? 0 : (e->multi ? num_block : 1);
+  /* kuka.py:104-118: joint control takes 7 joint deltas (+ the grip command) */
+  e->adim = e->jc ? (e->grasping ? 8 : 7) : (e->grasping ? 4 : 3);
   e->target_in_air = task != PMGO_PUSH;
   if (task == PMGO_REACH) { e->dims[0] = 3; e->dims[1] = 3; e->dims[2] = 3; e->dims[3] = 3; }
-  else if (task == PMGO_BLOCK_STACK) { e->dims[0] = 8 + 16 * e->nb; e->dims[1] = 4 + 3 * e->nb; e->dims[2] = e->dims[3] = 3 * e->nb; }
+  else if (e->multi) { e->dims[0] = 8 + 16 * e->nb; e->dims[1] = 4 + 3 * e->nb; e->dims[2] = e->dims[3] = 3 * e->nb; }
   else { e->dims[0] = 20; e->dims[1] = 7; e->dims[2] = 3; e->dims[3] = 3; }
+  if (e->grip) { e->dims[2] += 4; e->dims[3] += 4; } /* + gripper xyz + finger closeness (kuka_multi_step_base_env.py:300-304) */
+  if (e->jc) { e->dims[0] += 7; e->dims[1] += 7; }   /* joint poses are prepended (kuka_single_step_base_env.py:214-216) */
   /* kuka.py:35-51 with each task's ctor args (obj_range = target_range = 0.15) */
   set3(e->tip_init, -0.52, 0.0, 0.25);
-  if (task == PMGO_PUSH) e->tip_init[2] = 0.175 + 0.001;
+  if (task == PMGO_PUSH || task == PMGO_BLOCK_REARRANGE) e->tip_init[2] = 0.175 + 0.001;
   for (int k = 0; k < 3; k++) {
     e->obj_lo[k] = e->tip_init[k] - 0.15; e->obj_hi[k] = e->tip_init[k] + 0.15;
     e->tgt_lo[k] = e->tip_init[k] - 0.15; e->tgt_hi[k] = e->tip_init[k] + 0.15;
@@ -1188,10 +1201,12 @@ static void write_obs(PmgoEnv* e, double* o) {
     closeness = sqrt(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]);
     finger_vel = base[7 + 1] - tab1[7 + 1];
   }
-  double* obs = o; double* pol = o + e->dims[0]; double* ag = pol + e->dims[1]; double* dg = ag + e->dims[2];
+  const int jo = e->jc ? 7 : 0;
+  double* obs = o + jo; double* pol = o + e->dims[0] + jo; double* ag = o + e->dims[0] + e->dims[1]; double* dg = ag + e->dims[2];
+  if (e->jc) { memcpy(o, e->q, sizeof(double) * 7); memcpy(o + e->dims[0], e->q, sizeof(double) * 7); }
   if (e->task == PMGO_REACH) {
     copy3(obs, tip); copy3(pol, tip); copy3(ag, tip);
-  } else if (e->task != PMGO_BLOCK_STACK) {
+  } else if (!e->multi) {
     const double* bx = e->bpos[0];
     copy3(obs, tip); copy3(obs + 3, bx); obs[6] = closeness;
     sub3(obs + 7, tip, bx);
@@ -1213,10 +1228,15 @@ static void write_obs(PmgoEnv* e, double* o) {
       sub3(pol + 4 + 3 * n, tip, e->bpos[n]);
       copy3(ag + 3 * n, e->bpos[n]);
     }
-    for (int i = 0; i < e->dims[0]; i++) obs[i] = obs[i] < -5 ? -5 : (obs[i] > 5 ? 5 : obs[i]);
-    for (int i = 0; i < e->dims[1]; i++) pol[i] = pol[i] < -5 ? -5 : (pol[i] > 5 ? 5 : pol[i]);
+    if (e->grip) { copy3(ag + 3 * e->nb, tip); ag[3 * e->nb + 3] = closeness; }
+    /* np.clip over the concatenated state / policy_state, joint poses included (:306-307) */
+    for (int i = 0; i < e->dims[0]; i++) o[i] = o[i] < -5 ? -5 : (o[i] > 5 ? 5 : o[i]);
+    for (int i = 0; i < e->dims[1]; i++) o[e->dims[0] + i] = o[e->dims[0] + i] < -5 ? -5 : (o[e->dims[0] + i] > 5 ? 5 : o[e->dims[0] + i]);
     /* _generate_goal(new_target=False): rebuild desired_goal from the cached order/targets */
-    for (int k = 0; k < e->nb; k++) copy3(e->goal + 3 * e->last_order[k], e->last_targets[k]);
+    if (e->task == PMGO_BLOCK_STACK) {
+      for (int k = 0; k < e->nb; k++) copy3(e->goal + 3 * e->last_order[k], e->last_targets[k]);
+      if (e->grip) { copy3(e->goal + 3 * e->nb, e->last_targets[e->nb - 1]); e->goal[3 * e->nb + 3] = 0.03; }
+    }
   }
   memcpy(dg, e->goal, sizeof(double) * e->dims[3]);
 }
@@ -1238,6 +1258,9 @@ static void robot_reset(PmgoEnv* e) { /* kuka.py:157-165 */
   }
   double quat[4];
   pmgo_fk_tip(e->q, e->ee_target, quat);
+  /* kuka.py:165: joint_state_target = current joint state.  It is kept in mot_target (the motor is off until
+   * the first move_arm, so the value has no effect before it is used). */
+  if (e->jc) for (int d = 0; d < 7; d++) e->mot_target[d] = e->q[d];
 }
 
 static void place_blocks(PmgoEnv* e, const double* xy) {
@@ -1252,7 +1275,7 @@ void pmgo_reset(PmgoEnv* e, double* obs_out) {
   robot_reset(e);
   e->elapsed = 0;
   double xy[2 * MAXBLK];
-  if (e->task == PMGO_BLOCK_STACK) {
+  if (e->multi) {
     /* kuka_multi_step_base_env.py:223-240 */
     for (int b = 0; b < e->nb; b++) {
       for (;;) {
@@ -1265,6 +1288,23 @@ void pmgo_reset(PmgoEnv* e, double* obs_out) {
       }
     }
     place_blocks(e, xy);
+    if (e->task == PMGO_BLOCK_REARRANGE) {
+      /* kuka_multi_step_envs.py:174-189: one table target per block, clear of every block and earlier target */
+      double txy[2 * MAXBLK];
+      for (int b = 0; b < e->nb; b++) {
+        for (;;) {
+          double x = mt_uniform(&e->rng, e->tgt_lo[0], e->tgt_hi[0]);
+          double y = mt_uniform(&e->rng, e->tgt_lo[1], e->tgt_hi[1]);
+          int ok = 1;
+          for (int k = 0; k < b; k++) if (!(hypot(x - txy[2 * k], y - txy[2 * k + 1]) > 0.06)) ok = 0;
+          for (int k = 0; k < e->nb; k++) if (!(hypot(x - xy[2 * k], y - xy[2 * k + 1]) > 0.06)) ok = 0;
+          if (ok) { txy[2 * b] = x; txy[2 * b + 1] = y; break; }
+        }
+        set3(e->goal + 3 * b, txy[2 * b], txy[2 * b + 1], 0.175);
+      }
+      write_obs(e, obs_out);
+      return;
+    }
     /* kuka_multi_step_envs.py:34-63 */
     int64_t order[MAXBLK];
     for (int k = 0; k < e->nb; k++) order[k] = k;
@@ -1282,6 +1322,7 @@ void pmgo_reset(PmgoEnv* e, double* obs_out) {
       set3(e->last_targets[k], bx, by, k == 0 ? 0.175 : 0.175 + 0.03 * k);
       copy3(e->goal + 3 * e->last_order[k], e->last_targets[k]);
     }
+    if (e->grip) { copy3(e->goal + 3 * e->nb, e->last_targets[e->nb - 1]); e->goal[3 * e->nb + 3] = 0.03; } /* :75-77 */
   } else {
     /* kuka_single_step_base_env.py:104-148 */
     double center[3];
@@ -1342,14 +1383,19 @@ void pmgo_step(PmgoEnv* e, const double* a, double* obs_out, double* reward, int
     double grip = (a[e->adim - 1] + 1.0) * (GRIPPER_ABS_LIMIT / 2);
     for (int d = 7; d < ND; d++) { e->mot_target[d] = grip; e->mot_maximp[d] = FINGER_FORCE * OUTER_DT; }
   }
-  for (int k = 0; k < 3; k++) {
-    e->ee_target[k] += a[k] * 0.01;
-    if (e->ee_target[k] < EE_LOWER[k]) e->ee_target[k] = EE_LOWER[k];
-    if (e->ee_target[k] > EE_UPPER[k]) e->ee_target[k] = EE_UPPER[k];
+  if (e->jc) {
+    /* kuka.py:204-206: joint_state_target += 0.05 a[:7], no clipping, no IK */
+    for (int d = 0; d < 7; d++) { e->mot_target[d] += a[d] * 0.05; e->mot_maximp[d] = ARM_FORCE * OUTER_DT; }
+  } else {
+    for (int k = 0; k < 3; k++) {
+      e->ee_target[k] += a[k] * 0.01;
+      if (e->ee_target[k] < EE_LOWER[k]) e->ee_target[k] = EE_LOWER[k];
+      if (e->ee_target[k] > EE_UPPER[k]) e->ee_target[k] = EE_UPPER[k];
+    }
+    double qik[ND];
+    pmgo_ik(e->q, e->ee_target, EE_FIXED_QUAT, 40, 1e-5, qik);
+    for (int d = 0; d < 7; d++) { e->mot_target[d] = qik[d]; e->mot_maximp[d] = ARM_FORCE * OUTER_DT; }
   }
-  double qik[ND];
-  pmgo_ik(e->q, e->ee_target, EE_FIXED_QUAT, 40, 1e-5, qik);
-  for (int d = 0; d < 7; d++) { e->mot_target[d] = qik[d]; e->mot_maximp[d] = ARM_FORCE * OUTER_DT; }
   for (int c = 0; c < CALLS_PER_ENV_STEP; c++) pmgo_step_simulation(e);
   write_obs(e, obs_out);
   uint8_t ok;

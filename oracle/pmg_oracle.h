@@ -29,15 +29,20 @@ extern "C" {
 #endif
 
 #define PMGO_MAX_BLOCKS 5
-#define PMGO_MAX_OBS 160 /* nb=5: 88 + 19 + 15 + 15 = 137 */
+#define PMGO_MAX_OBS 176 /* nb=5, grip goal, joint control: 95 + 26 + 19 + 19 = 159 */
 
-enum { PMGO_REACH = 0, PMGO_PUSH = 1, PMGO_PICK_AND_PLACE = 2, PMGO_BLOCK_STACK = 3 };
+enum { PMGO_REACH = 0, PMGO_PUSH = 1, PMGO_PICK_AND_PLACE = 2, PMGO_BLOCK_STACK = 3, PMGO_BLOCK_REARRANGE = 4 };
 
 typedef struct PmgoEnv PmgoEnv;
 
 /* task: enum above; num_block used by BLOCK_STACK only (1..5). */
 PmgoEnv* pmgo_create(int task, int num_block, int binary_reward, double distance_threshold,
                      int max_episode_steps);
+/* + grip_informed_goal (block_stack: goal gains gripper xyz + finger closeness, kuka_multi_step_base_env.py:
+ * 300-304, kuka_multi_step_envs.py:75-77) and joint_control (7 joint deltas instead of a tip delta,
+ * kuka.py:104-108,204-206; joint poses prepended to observation / policy_state). */
+PmgoEnv* pmgo_create_ex(int task, int num_block, int binary_reward, double distance_threshold,
+                        int max_episode_steps, int grip_informed_goal, int joint_control);
 void pmgo_destroy(PmgoEnv* e);
 
 /* dims[0..3] = observation, policy_state, achieved_goal, desired_goal lengths; returns action dim */

@@ -15,7 +15,7 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB = None
 
-TASKS = {"reach": 0, "push": 1, "pick_and_place": 2, "block_stack": 3}
+TASKS = {"reach": 0, "push": 1, "pick_and_place": 2, "block_stack": 3, "block_rearrange": 4}
 
 
 def build(force=False):
@@ -36,6 +36,8 @@ def lib():
         dp, ip = C.POINTER(C.c_double), C.POINTER(C.c_int)
         L.pmgo_create.restype = C.c_void_p
         L.pmgo_create.argtypes = [C.c_int, C.c_int, C.c_int, C.c_double, C.c_int]
+        L.pmgo_create_ex.restype = C.c_void_p
+        L.pmgo_create_ex.argtypes = [C.c_int, C.c_int, C.c_int, C.c_double, C.c_int, C.c_int, C.c_int]
         L.pmgo_destroy.argtypes = [C.c_void_p]
         L.pmgo_dims.argtypes = [C.c_void_p, ip]
         L.pmgo_dims.restype = C.c_int
@@ -95,15 +97,15 @@ class OracleEnv:
     """Single-environment CPU oracle with the reference's reset/step semantics."""
 
     def __init__(self, task="reach", num_block=4, binary_reward=True, distance_threshold=0.05,
-                 max_episode_steps=50, seed=0):
+                 max_episode_steps=50, seed=0, grip_informed_goal=False, joint_control=False):
         self.L = lib()
         self.task = task
-        self.h = self.L.pmgo_create(TASKS[task], num_block, int(binary_reward), distance_threshold,
-                                    max_episode_steps)
+        self.h = self.L.pmgo_create_ex(TASKS[task], num_block, int(binary_reward), distance_threshold,
+                                       max_episode_steps, int(grip_informed_goal), int(joint_control))
         dims = (C.c_int * 4)()
         self.adim = self.L.pmgo_dims(self.h, dims)
         self.dims = list(dims)
-        self.nb = 0 if task == "reach" else (num_block if task == "block_stack" else 1)
+        self.nb = 0 if task == "reach" else (num_block if task in ("block_stack", "block_rearrange") else 1)
         self.seed(seed)
 
     def __del__(self):

@@ -133,13 +133,23 @@ def test_block_rests_on_table_and_arm_tracks(oracle):
     assert 0.09 < o["achieved_goal"][0] - start[0] < 0.1001
 
 
-@pytest.mark.parametrize("name", ["reach", "push", "pick_and_place", "block_stack"])
+# make_env / OracleEnv keyword arguments of every golden (kept in step with tools/gen_golden.py VARIANTS)
+GOLDEN_VARIANTS = {
+    "reach": dict(task="reach"), "push": dict(task="push", binary_reward=False),
+    "pick_and_place": dict(task="pick_and_place"), "block_stack": dict(task="block_stack", num_block=4),
+    "block_rearrange": dict(task="block_rearrange", num_block=3),
+    "block_stack_grip": dict(task="block_stack", num_block=3, grip_informed_goal=True),
+    "reach_jc": dict(task="reach", joint_control=True),
+    "pick_and_place_jc": dict(task="pick_and_place", binary_reward=False, joint_control=True),
+}
+
+
+@pytest.mark.parametrize("name", sorted(GOLDEN_VARIANTS))
 def test_oracle_reproduces_reference_plumbing_goldens(oracle, name):
     """tests/golden/ref_plumbing_*.npz were produced by the reference's unmodified Python running on
     the pybullet shim; the oracle's own C restatement of reset/step/obs/reward must reproduce them."""
     g = np.load(os.path.join(GOLDEN, "ref_plumbing_%s.npz" % name))
-    binary = name != "push"
-    e = oracle.OracleEnv(name, num_block=4, binary_reward=binary, seed=0, max_episode_steps=int(g["max_episode_steps"]))
+    e = oracle.OracleEnv(seed=0, max_episode_steps=int(g["max_episode_steps"]), **GOLDEN_VARIANTS[name])
     e.reset()  # the reference ctor's own reset (base_env.py:84)
     L = int(g["episode_len"])
     k = 0

@@ -30,7 +30,21 @@ CONFIGS = [
     ("push", dict(task="push", binary_reward=False), 3, 100),
     ("pick_and_place", dict(task="pick_and_place", binary_reward=True), 4, 100),
     ("block_stack", dict(task="block_stack", binary_reward=True, num_block=4), 4, 100),
+    # "next" rows of SURVEY.md 8(f): same physics, more of the reference's plumbing
+    ("block_rearrange", dict(task="block_rearrange", binary_reward=True, num_block=3), 3, 100),
+    ("block_stack_grip", dict(task="block_stack", binary_reward=True, num_block=3, grip_informed_goal=True), 4, 100),
+    ("reach_jc", dict(task="reach", binary_reward=True, joint_control=True), 7, 100),
+    ("pick_and_place_jc", dict(task="pick_and_place", binary_reward=False, joint_control=True), 8, 100),
 ]
+# OracleEnv / make_env keyword arguments that reproduce each golden (shared with the tests)
+VARIANTS = {
+    "reach": dict(task="reach"), "push": dict(task="push", binary_reward=False),
+    "pick_and_place": dict(task="pick_and_place"), "block_stack": dict(task="block_stack", num_block=4),
+    "block_rearrange": dict(task="block_rearrange", num_block=3),
+    "block_stack_grip": dict(task="block_stack", num_block=3, grip_informed_goal=True),
+    "reach_jc": dict(task="reach", joint_control=True),
+    "pick_and_place_jc": dict(task="pick_and_place", binary_reward=False, joint_control=True),
+}
 
 
 def pack(obs):
@@ -42,12 +56,20 @@ def scripted_actions(name, adim, T, rng):
     a = rng.uniform(-1, 1, size=(T, adim))
     if name == "reach":
         a[:14, 2] = -1.0
+    if name.endswith("_jc"):
+        a[:, :7] *= 0.4      # joint-space deltas of up to 0.02 rad per step
+        a[:12, 1] = 0.5      # lean the arm forward and down: jaws / block / table contacts
+        a[:12, 3] = 0.3
     return a
 
 
 def main():
     os.makedirs(OUT, exist_ok=True)
     for name, kw, adim, T in CONFIGS:
+        # make_env registers an env id once per process and the id does not encode num_block /
+        # grip_informed_goal (__init__.py:56-85: first registration wins), so start from a clean registry
+        from gym.envs.registration import registry
+        registry.env_specs.clear()
         with contextlib.redirect_stdout(io.StringIO()):
             env = ref.make_env(gripper="parallel_jaw", render=False, **kw)
         rng = np.random.RandomState(2024)
@@ -57,12 +79,12 @@ def main():
             resets.append(pack(env.reset()))
             for t in range(T // 2):
                 a = actions[ep * (T // 2) + t]
-                if name != "reach":
+                if name not in ("reach", "reach_jc", "pick_and_place_jc"):
                     # steer the tip to the (first) block: push from the side / descend with open jaws
                     obs_now = steps[-1] if (steps and t > 0) else resets[-1]
                     tip = obs_now[0:3]
-                    blk = obs_now[3:6] if name != "block_stack" else obs_now[8:11]
-                    tgt = blk + np.array([0.0, 0.0, 0.0 if (name == "push" or t > 10) else 0.07])
+                    blk = obs_now[3:6] if not name.startswith("block_") else obs_now[8:11]
+                    tgt = blk + np.array([0.0, 0.0, 0.0 if (name in ("push", "block_rearrange") or t > 10) else 0.07])
                     a[:3] = np.clip((tgt - tip) / 0.01, -1, 1)
                     if adim == 4:
                         a[3] = -1.0 if t < 16 else 1.0
