@@ -22,7 +22,7 @@
 extern "C" {
 #endif
 
-#define PMG_ABI_VERSION 1
+#define PMG_ABI_VERSION 2
 
 typedef enum {
   PMG_OK = 0,
@@ -31,8 +31,9 @@ typedef enum {
   PMG_ERR_STATE = -3    /* call order violated (e.g. step before the first reset) */
 } pmg_status;
 
-/* task ids: envs/task_envs/kuka_single_step_envs.py:4-46, kuka_multi_step_envs.py:6-32 */
-typedef enum { PMG_REACH = 0, PMG_PUSH = 1, PMG_PICK_AND_PLACE = 2, PMG_BLOCK_STACK = 3 } pmg_task;
+/* task ids: envs/task_envs/kuka_single_step_envs.py:4-46, kuka_multi_step_envs.py:6-32 (stack),
+ * :151-189 (rearrange: the block-stack scene without grasping, one table target per block) */
+typedef enum { PMG_REACH = 0, PMG_PUSH = 1, PMG_PICK_AND_PLACE = 2, PMG_BLOCK_STACK = 3, PMG_BLOCK_REARRANGE = 4 } pmg_task;
 
 /* make_env(...) kwargs that reach the step path (__init__.py:4-11,88-131) + batch/device */
 typedef struct {
@@ -43,6 +44,11 @@ typedef struct {
   float distance_threshold;   /* default 0.05 (__init__.py:6) */
   int32_t max_episode_steps;  /* gym TimeLimit, default 50 (__init__.py:6,105) */
   int32_t device;             /* CUDA device ordinal */
+  int32_t grip_informed_goal; /* block_stack only: goal += gripper xyz + finger closeness
+                                 (kuka_multi_step_base_env.py:300-304, kuka_multi_step_envs.py:75-77) */
+  int32_t joint_control;      /* 1: actions are 7 joint deltas of 0.05 rad (+ grip command) instead of a tip delta,
+                                 joint poses are prepended to observation / policy_state (kuka.py:104-108,204-206;
+                                 kuka_single_step_base_env.py:214-216) */
 } pmg_config;
 
 typedef struct pmg_handle pmg_handle;
@@ -67,7 +73,8 @@ int pmg_seed(pmg_handle* h, const uint32_t* keys_host, const int32_t* key_lens_h
 /* replaces: env.reset() (base_env.py:124-128; kuka.py:157-165; kuka_single_step_base_env.py:
  * 104-148; kuka_multi_step_base_env.py:223-246; kuka_multi_step_envs.py:34-87).
  * mask_host: nullable [batch] bytes, non-zero = reset that env (NULL = all).
- * spawn_host: nullable [batch, spawn_width] floats = [block xy (2*nb) | desired_goal (G)];
+ * spawn_host: nullable [batch, spawn_width] floats = [block xy (2*nb) | desired_goal (G)]
+ *   (G includes the 4 gripper entries of a grip-informed goal);
  *   NULL = sample on the host from each env's numpy-compatible MT19937 stream, exactly as the
  *   reference consumes it.
  * obs_dev: [batch, packed-row width] row-major, rows of envs not reset are rewritten unchanged. */

@@ -3,20 +3,22 @@
 `make_env` keeps the reference's signature (/root/reference/pybullet_multigoal_gym/__init__.py:4-11)
 and adds `batch` (number of environments stepped in lockstep; None = one unbatched env with the
 reference's numpy shapes), `device` and `seed`.  Tasks on the accelerated path: reach, push,
-pick_and_place, block_stack with the parallel-jaw gripper and state observations.
+pick_and_place, block_stack, block_rearrange with the parallel-jaw gripper and state observations,
+including the `joint_control` and (block_stack) `grip_informed_goal` variants.
 """
-from .envs import (ActionError, KukaBlockStackEnv, KukaBulletMGEnv, KukaPickAndPlaceEnv,  # noqa: F401
-                   KukaPushEnv, KukaReachEnv)
+from .envs import (ActionError, KukaBlockRearrangeEnv, KukaBlockStackEnv, KukaBulletMGEnv,  # noqa: F401
+                   KukaPickAndPlaceEnv, KukaPushEnv, KukaReachEnv)
 
 __all__ = ["make_env", "KukaBulletMGEnv", "KukaReachEnv", "KukaPushEnv", "KukaPickAndPlaceEnv",
-           "KukaBlockStackEnv", "ActionError"]
+           "KukaBlockStackEnv", "KukaBlockRearrangeEnv", "ActionError"]
 
 _TASKS = ['push', 'reach', 'slide', 'pick_and_place',
           'block_stack', 'block_rearrange', 'chest_pick_and_place', 'chest_push',
           'primitive_push_assemble', 'primitive_push_reach', 'insertion']
-_TAGS = {'reach': 'Reach', 'push': 'Push', 'pick_and_place': 'PickAndPlace', 'block_stack': 'BlockStack'}
+_TAGS = {'reach': 'Reach', 'push': 'Push', 'pick_and_place': 'PickAndPlace', 'block_stack': 'BlockStack',
+         'block_rearrange': 'BlockRearrangeEnv'}  # __init__.py:21-40 (the rearrange tag really ends in 'Env')
 _ENTRY = {'reach': KukaReachEnv, 'push': KukaPushEnv, 'pick_and_place': KukaPickAndPlaceEnv,
-          'block_stack': KukaBlockStackEnv}
+          'block_stack': KukaBlockStackEnv, 'block_rearrange': KukaBlockRearrangeEnv}
 
 
 def make_env(task='reach', gripper='parallel_jaw', num_block=5, render=False, binary_reward=True,
@@ -37,8 +39,12 @@ def make_env(task='reach', gripper='parallel_jaw', num_block=5, render=False, bi
         unsupported.append("task=%r" % task)
     if gripper != 'parallel_jaw':
         unsupported.append("gripper=%r" % gripper)
-    for name, val in (('render', render), ('grip_informed_goal', grip_informed_goal),
-                      ('task_decomposition', task_decomposition), ('joint_control', joint_control),
+    if grip_informed_goal and task != 'block_stack':
+        if task == 'block_rearrange':  # kuka_multi_step_envs.py:158
+            raise AssertionError("Block rearranging task does not support gripper informed goal representation.")
+        grip_informed_goal = False  # the single-step tasks do not take the kwarg (__init__.py:88-106)
+    for name, val in (('render', render),
+                      ('task_decomposition', task_decomposition),
                       ('image_observation', image_observation), ('depth_image', depth_image),
                       ('goal_image', goal_image), ('point_cloud', point_cloud), ('state_noise', state_noise),
                       ('use_curriculum', use_curriculum)):
@@ -48,12 +54,14 @@ def make_env(task='reach', gripper='parallel_jaw', num_block=5, render=False, bi
         unsupported.append("primitive=%r" % primitive)
     if unsupported:
         raise NotImplementedError(
-            "outside the accelerated step path (reach/push/pick_and_place/block_stack, parallel_jaw, "
-            "state observations): " + ", ".join(unsupported))
-    if task == 'block_stack':
+            "outside the accelerated step path (reach/push/pick_and_place/block_stack/block_rearrange, "
+            "parallel_jaw, state observations): " + ", ".join(unsupported))
+    if task in ('block_stack', 'block_rearrange'):
         assert num_block <= 5, "only support up to 5 blocks"
-    env_id = 'Kuka' + _TAGS[task] + 'ParallelGrip' + ('SparseReward' if binary_reward else 'DenseReward') + '-v0'
-    print('Task id: %s' % env_id)  # __init__.py:84
+    env_id = ('Kuka' + _TAGS[task] + 'ParallelGrip' + ('SparseReward' if binary_reward else 'DenseReward') +
+              ('JointCtrl' if joint_control else '') + '-v0')
+    print('Task id: %s' % env_id)  # __init__.py:56-84
     return _ENTRY[task](batch=batch, device=device, binary_reward=binary_reward,
                         distance_threshold=distance_threshold, max_episode_steps=max_episode_steps,
-                        num_block=num_block, seed=seed, check_actions=check_actions)
+                        num_block=num_block, seed=seed, check_actions=check_actions,
+                        grip_informed_goal=grip_informed_goal, joint_control=joint_control)

@@ -10,7 +10,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 SO_PATH = os.path.join(_HERE, "libpmg.so")
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 # every symbol include/pmg.h declares
 SYMBOLS = [
@@ -24,7 +24,8 @@ SYMBOLS = [
 class PmgConfig(C.Structure):
     _fields_ = [("task", C.c_int32), ("num_block", C.c_int32), ("batch", C.c_int32),
                 ("binary_reward", C.c_int32), ("distance_threshold", C.c_float),
-                ("max_episode_steps", C.c_int32), ("device", C.c_int32)]
+                ("max_episode_steps", C.c_int32), ("device", C.c_int32),
+                ("grip_informed_goal", C.c_int32), ("joint_control", C.c_int32)]
 
 
 _lib = None

@@ -107,13 +107,12 @@ __device__ void store_env(const Env<NBLK>& e, const StepIO& io, int i) {
 // Stage the warp's rows in shared memory so that the global stores are contiguous 128-byte lines
 // (rows of consecutive envs are adjacent in the packed [batch, W] output).  Every lane of the warp
 // must call this; lanes that own no environment pass live = false.
-template <int W>
 __device__ __forceinline__ void stage_row(const float* row, const StepIO& io, bool live) {
   extern __shared__ float stage[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int W = io.row_width;
   float* ws = stage + warp * io.epw * W;
   if (live) {
-#pragma unroll
     for (int k = 0; k < W; k++) ws[lane * W + k] = row[k];
   }
   __syncwarp();
@@ -125,7 +124,8 @@ __device__ __forceinline__ void stage_row(const float* row, const StepIO& io, bo
 }
 
 // Writes the packed row [observation | policy_state | achieved_goal | desired_goal] and returns
-// the goal distance.
+// the goal distance.  Run-time variants: joint control prepends the 7 arm joint angles to observation and
+// policy_state, a grip-informed goal appends gripper xyz + finger closeness to the achieved goal.
 template <int TASK, int NBLK>
 __device__ float write_obs(const Env<NBLK>& e, const StepIO& io, int i) {
   using D = Dims<TASK, NBLK>;
@@ -135,7 +135,7 @@ __device__ float write_obs(const Env<NBLK>& e, const StepIO& io, int i) {
   V3 tip = tip_position(f), tv, tw;
   point_velocity<PMG_BODY_LINK7>(f, e.qd, tip, tv, tw);
   float closeness = 0.0f, finger_vel = 0.0f;
-  if (TASK >= 2) {
+  if (TASK >= 2 && io.grasp) {
     const float t1[3] = PMG_TAB1_OFFSET, t2[3] = PMG_TAB2_OFFSET;
     V3 tab1 = f.p[PMG_BODY_FINGER1] + mul(f.R[PMG_BODY_FINGER1], v3(t1[0], t1[1], t1[2]));
     V3 tab2 = f.p[PMG_BODY_FINGER2] + mul(f.R[PMG_BODY_FINGER2], v3(t2[0], t2[1], t2[2]));
@@ -145,11 +145,16 @@ __device__ float write_obs(const Env<NBLK>& e, const StepIO& io, int i) {
     point_velocity<PMG_BODY_FINGER1>(f, e.qd, tab1, vt, wt);
     finger_vel = vb.y - vt.y;
   }
-  float row[D::W];
-  float* obs = row; float* pol = row + D::O; float* ag = pol + D::P; float* dg = ag + D::G;
-  const float* goal = io.state + (size_t)(ST_BLK + 13 * NBLK) * B + i;
+  const int jo = io.jc ? 7 : 0, G = io.goal_dim;
+  const int O = D::O + jo, P = D::P + jo;
+  float row[D::W + 14 + 8];
+  float* obs = row + jo; float* pol = row + O + jo; float* ag = row + O + P; float* dg = ag + G;
+  if (io.jc) {
 #pragma unroll
-  for (int k = 0; k < D::G; k++) dg[k] = goal[k * B];
+    for (int k = 0; k < 7; k++) { row[k] = e.q[k]; row[O + k] = e.q[k]; }
+  }
+  const float* goal = io.state + (size_t)(ST_BLK + 13 * NBLK) * B + i;
+  for (int k = 0; k < G; k++) dg[k] = goal[k * B];
   if (TASK == 0) {
     obs[0] = pol[0] = ag[0] = tip.x; obs[1] = pol[1] = ag[1] = tip.y; obs[2] = pol[2] = ag[2] = tip.z;
   } else if (TASK != 3) {
@@ -172,13 +177,12 @@ __device__ float write_obs(const Env<NBLK>& e, const StepIO& io, int i) {
       pol[4 + 3 * n] = rel.x; pol[5 + 3 * n] = rel.y; pol[6 + 3 * n] = rel.z;
       ag[3 * n] = bx.x; ag[3 * n + 1] = bx.y; ag[3 * n + 2] = bx.z;
     }
-#pragma unroll
-    for (int k = 0; k < D::O + D::P; k++) row[k] = clip5(row[k]);
+    if (io.grip_goal) { ag[3 * NBLK] = tip.x; ag[3 * NBLK + 1] = tip.y; ag[3 * NBLK + 2] = tip.z; ag[3 * NBLK + 3] = closeness; }
+    for (int k = 0; k < O + P; k++) row[k] = clip5(row[k]);  // np.clip over the concatenated vectors, joint poses included
   }
   float d2 = 0.0f;
-#pragma unroll
-  for (int k = 0; k < D::G; k++) { float d = ag[k] - dg[k]; d2 += d * d; }
-  stage_row<D::W>(row, io, true);
+  for (int k = 0; k < G; k++) { float d = ag[k] - dg[k]; d2 += d * d; }
+  stage_row(row, io, true);
   return sqrtf(d2);
 }
 
@@ -200,22 +204,29 @@ __global__ void __launch_bounds__(32) step_kernel(StepIO io) {
 #pragma unroll
     for (int k = 0; k < 3; k++) ee0[k] = ts[(ST_EE + k) * 32];
   } else {
-    if (i < 0) { stage_row<D::W>(nullptr, io, false); return; }  // idle lanes only help the staged store
+    if (i < 0) { stage_row(nullptr, io, false); return; }  // idle lanes only help the staged store
     load_env<TASK, NBLK>(e, io, i, io.state + i, B);
 #pragma unroll
     for (int k = 0; k < 3; k++) ee0[k] = io.state[(ST_EE + k) * B + i];
   }
   float* s = io.state + i;
   // ---- Kuka.apply_action (kuka.py:167-222) ----
-  float a[D::A];
+  float a[8];
 #pragma unroll
-  for (int k = 0; k < D::A; k++) a[k] = io.action[(size_t)i * D::A + k];
-  if (TASK >= 2) {
-    float grip = (a[D::A - 1] + 1.0f) * (GRIPPER_ABS_LIMIT / 2);
+  for (int k = 0; k < 8; k++) a[k] = k < io.adim ? io.action[(size_t)i * io.adim + k] : 0.0f;
+  if (TASK >= 2 && io.grasp) {
+    float grip = ((io.jc ? a[7] : a[3]) + 1.0f) * (GRIPPER_ABS_LIMIT / 2);
     e.mt[7] = e.mt[8] = grip; e.mi[7] = e.mi[8] = FINGER_FORCE * OUTER_DT;
   }
   const float lo[3] = {-0.67f, -0.20f, 0.175f}, hi[3] = {-0.37f, 0.20f, 0.55f};  // kuka.py:40-41
   float ee[3];
+  if (io.jc) {
+    // kuka.py:204-206: joint_state_target (kept in the motor targets) += 0.05 a[:7]; no clipping, no IK
+#pragma unroll
+    for (int k = 0; k < 3; k++) ee[k] = ee0[k];
+#pragma unroll
+    for (int k = 0; k < 7; k++) { e.mt[k] += a[k] * 0.05f; e.mi[k] = ARM_FORCE * OUTER_DT; }
+  } else {
 #pragma unroll
   for (int k = 0; k < 3; k++) ee[k] = fminf(fmaxf(ee0[k] + a[k] * 0.01f, lo[k]), hi[k]);
   {
@@ -227,6 +238,7 @@ __global__ void __launch_bounds__(32) step_kernel(StepIO io) {
 #pragma unroll
     for (int k = 0; k < 7; k++) { e.mt[k] = qik[k]; e.mi[k] = ARM_FORCE * OUTER_DT; }
   }
+  }
   // ---- 5 x stepSimulation (kuka.py:223-225), each 20 substeps of 2 ms ----
   for (int call = 0; call < CALLS_PER_ENV_STEP; call++) {
 #pragma unroll
@@ -237,7 +249,7 @@ __global__ void __launch_bounds__(32) step_kernel(StepIO io) {
   store_env<TASK, NBLK>(e, io, i);
 #pragma unroll
   for (int k = 0; k < 3; k++) s[(ST_EE + k) * B] = ee[k];
-  float* el = s + (size_t)(D::STATE - 1) * B;
+  float* el = s + (size_t)(io.state_words - 1) * B;
   int elapsed = (int)(*el) + 1;
   *el = (float)elapsed;
   bool na = dist > io.thr;
@@ -274,7 +286,7 @@ __global__ void __launch_bounds__(32) reset_kernel(ResetIO r) {
   using D = Dims<TASK, NBLK>;
   const StepIO& io = r.io;
   const int i = env_of_thread(io);
-  if (i < 0) { stage_row<D::W>(nullptr, io, false); return; }
+  if (i < 0) { stage_row(nullptr, io, false); return; }
   const size_t B = io.batch;
   Env<NBLK> e;
   load_env<TASK, NBLK>(e, io, i, io.state + i, B);
@@ -290,13 +302,15 @@ __global__ void __launch_bounds__(32) reset_kernel(ResetIO r) {
     const float tq[4] = {0.f, -1.f, 0.f, 0.f};
     inverse_kinematics(qik, v3(r.tip_init[0], r.tip_init[1], r.tip_init[2]), tq);
 #pragma unroll
-    for (int k = 0; k < 7; k++) { e.q[k] = qik[k]; e.qd[k] = 0.0f; e.mt[k] = 0.0f; e.mi[k] = 0.0f; }
+    // joint control keeps joint_state_target (= the joint state after the reset, kuka.py:165) in the motor
+    // targets; the motors stay off (zero impulse limit) until the first action either way
+    for (int k = 0; k < 7; k++) { e.q[k] = qik[k]; e.qd[k] = 0.0f; e.mt[k] = io.jc ? qik[k] : 0.0f; e.mi[k] = 0.0f; }
 #pragma unroll
     for (int k = 7; k < ND; k++) { e.q[k] = GRIPPER_ABS_LIMIT; e.qd[k] = 0.0f; e.mt[k] = GRIPPER_ABS_LIMIT; e.mi[k] = FINGER_FORCE * OUTER_DT; }
     Frames f;
     forward_kinematics<7>(e.q, f);
     V3 tip = tip_position(f);
-    const float* sp = r.spawn + (size_t)i * (2 * NBLK + D::G);
+    const float* sp = r.spawn + (size_t)i * (2 * NBLK + io.goal_dim);
 #pragma unroll
     for (int b = 0; b < NBLK; b++) {
       e.bpos[b] = v3(sp[2 * b], sp[2 * b + 1], BLOCK_SPAWN_Z);
@@ -306,9 +320,8 @@ __global__ void __launch_bounds__(32) reset_kernel(ResetIO r) {
 #pragma unroll
     for (int k = 0; k < 7; k++) s[(ST_REST + k) * B] = qik[k];
     s[(ST_EE + 0) * B] = tip.x; s[(ST_EE + 1) * B] = tip.y; s[(ST_EE + 2) * B] = tip.z;
-#pragma unroll
-    for (int k = 0; k < D::G; k++) s[(size_t)(ST_BLK + 13 * NBLK + k) * B] = sp[2 * NBLK + k];
-    s[(size_t)(D::STATE - 1) * B] = 0.0f;
+    for (int k = 0; k < io.goal_dim; k++) s[(size_t)(ST_BLK + 13 * NBLK + k) * B] = sp[2 * NBLK + k];
+    s[(size_t)(io.state_words - 1) * B] = 0.0f;
     store_env<TASK, NBLK>(e, io, i);
   }
   write_obs<TASK, NBLK>(e, io, i);
@@ -403,6 +416,7 @@ int fail(int code, const char* fmt, const char* detail = "") {
 struct pmg_handle {
   pmg_config cfg;
   int nblk, O, P, G, W, A, state_words, man_words, spawn_w;
+  bool multi = false, grasp = false, grip = false, jc = false;  // task variants, see pmg_config
   float* d_state = nullptr; float* d_man = nullptr; float* d_spawn = nullptr; uint8_t* d_mask = nullptr; int* d_overflow = nullptr;
   float* d_action = nullptr; float* d_obs = nullptr; float* d_reward = nullptr; uint8_t* d_done = nullptr; uint8_t* d_success = nullptr;
   float* h_spawn = nullptr;  // pinned
@@ -424,7 +438,7 @@ void sample_spawn(pmg_handle* h, int i, float* out) {
   MT& r = h->rng[i];
   const int nb = h->nblk;
   double xy[2 * 5];
-  if (h->cfg.task == PMG_BLOCK_STACK) {
+  if (h->multi) {
     for (int b = 0; b < nb; b++) {
       for (;;) {
         double x = r.uniform(h->obj_lo[0], h->obj_hi[0]), y = r.uniform(h->obj_lo[1], h->obj_hi[1]);
@@ -433,6 +447,23 @@ void sample_spawn(pmg_handle* h, int i, float* out) {
         if (!(hypot(x - h->tip_init[0], y - h->tip_init[1]) > 0.06)) ok = false;
         if (ok) { xy[2 * b] = x; xy[2 * b + 1] = y; break; }
       }
+    }
+    for (int b = 0; b < nb; b++) { out[2 * b] = (float)xy[2 * b]; out[2 * b + 1] = (float)xy[2 * b + 1]; }
+    if (h->cfg.task == PMG_BLOCK_REARRANGE) {
+      // kuka_multi_step_envs.py:174-189: one table target per block, clear of every block and earlier target
+      double txy[2 * 5];
+      float* goal = out + 2 * nb;
+      for (int b = 0; b < nb; b++) {
+        for (;;) {
+          double x = r.uniform(h->tgt_lo[0], h->tgt_hi[0]), y = r.uniform(h->tgt_lo[1], h->tgt_hi[1]);
+          bool ok = true;
+          for (int k = 0; k < b; k++) if (!(hypot(x - txy[2 * k], y - txy[2 * k + 1]) > 0.06)) ok = false;
+          for (int k = 0; k < nb; k++) if (!(hypot(x - xy[2 * k], y - xy[2 * k + 1]) > 0.06)) ok = false;
+          if (ok) { txy[2 * b] = x; txy[2 * b + 1] = y; break; }
+        }
+        goal[3 * b] = (float)txy[2 * b]; goal[3 * b + 1] = (float)txy[2 * b + 1]; goal[3 * b + 2] = 0.175f;
+      }
+      return;
     }
     int order[5];
     for (int k = 0; k < nb; k++) order[k] = k;
@@ -444,11 +475,14 @@ void sample_spawn(pmg_handle* h, int i, float* out) {
       for (int k = 0; k < nb; k++) if (!(hypot(bx - xy[2 * k], by - xy[2 * k + 1]) > 0.08)) ok = false;
       if (ok) break;
     }
-    for (int b = 0; b < nb; b++) { out[2 * b] = (float)xy[2 * b]; out[2 * b + 1] = (float)xy[2 * b + 1]; }
     float* goal = out + 2 * nb;
     for (int k = 0; k < nb; k++) {
       goal[3 * order[k]] = (float)bx; goal[3 * order[k] + 1] = (float)by;
       goal[3 * order[k] + 2] = (float)(k == 0 ? 0.175 : 0.175 + 0.03 * k);
+    }
+    if (h->grip) {  // kuka_multi_step_envs.py:75-77: gripper above the top block, jaws at the grasp width
+      goal[3 * nb] = (float)bx; goal[3 * nb + 1] = (float)by;
+      goal[3 * nb + 2] = (float)(nb == 1 ? 0.175 : 0.175 + 0.03 * (nb - 1)); goal[3 * nb + 3] = 0.03f;
     }
     return;
   }
@@ -480,6 +514,8 @@ StepIO make_io(pmg_handle* h, const float* action, float* obs, float* reward, ui
   io.overflow = h->d_overflow;
   io.epw = h->epw;
   io.bulk = 0; io.tile_offset = 0;
+  io.grasp = h->grasp; io.jc = h->jc; io.grip_goal = h->grip;
+  io.adim = h->A; io.goal_dim = h->G; io.row_width = h->W;
   return io;
 }
 
@@ -487,7 +523,7 @@ StepIO make_io(pmg_handle* h, const float* action, float* obs, float* reward, ui
 template <int TASK, int NBLK>
 void launch_step(pmg_handle* h, const StepIO& io_in, cudaStream_t st) {
   StepIO io = io_in;
-  if (TASK == 0 && h->coop) {
+  if (TASK == 0 && h->coop && !h->jc) {
     constexpr int EPB = 32 / coop::GL;  // environments per block
     const size_t smem = COOP_TABLE_BYTES + EPB * sizeof(coop::EnvSmem);
     static bool hinted_coop = false;
@@ -499,8 +535,8 @@ void launch_step(pmg_handle* h, const StepIO& io_in, cudaStream_t st) {
     return;
   }
   int warps = (h->cfg.batch + h->epw - 1) / h->epw;
-  size_t stage_floats = (size_t)h->epw * Dims<TASK, NBLK>::W;
-  io.bulk = (h->epw == 32 && h->cfg.batch % 32 == 0 && !h->no_bulk) ? 1 : 0;
+  size_t stage_floats = (size_t)h->epw * h->W;
+  io.bulk = (h->epw == 32 && h->cfg.batch % 32 == 0 && !h->no_bulk && !h->grip) ? 1 : 0;
   io.tile_offset = (int)((stage_floats + 31) / 32 * 32);
   size_t smem = (io.bulk ? io.tile_offset + (size_t)Dims<TASK, NBLK>::STATE * 32 : stage_floats) * sizeof(float);
   // The per-thread scratch lives in L1-cached local memory: ask for the smallest shared-memory
@@ -515,7 +551,7 @@ void launch_step(pmg_handle* h, const StepIO& io_in, cudaStream_t st) {
 template <int TASK, int NBLK>
 void launch_reset(pmg_handle* h, const ResetIO& r, cudaStream_t st) {
   int warps = (h->cfg.batch + h->epw - 1) / h->epw;
-  size_t smem = (size_t)h->epw * Dims<TASK, NBLK>::W * sizeof(float);
+  size_t smem = (size_t)h->epw * h->W * sizeof(float);
   reset_kernel<TASK, NBLK><<<warps, 32, smem, st>>>(r);
 }
 
@@ -546,8 +582,10 @@ const char* pmg_last_error(void) { return g_err; }
 
 int pmg_create(const pmg_config* cfg, pmg_handle** out) {
   if (!cfg || !out) return fail(PMG_ERR_INVALID, "pmg_create: null argument%s");
-  if (cfg->task < PMG_REACH || cfg->task > PMG_BLOCK_STACK) return fail(PMG_ERR_INVALID, "pmg_create: invalid task id%s");
-  if (cfg->task == PMG_BLOCK_STACK && (cfg->num_block < 1 || cfg->num_block > 5)) return fail(PMG_ERR_INVALID, "pmg_create: only support up to 5 blocks%s");
+  if (cfg->task < PMG_REACH || cfg->task > PMG_BLOCK_REARRANGE) return fail(PMG_ERR_INVALID, "pmg_create: invalid task id%s");
+  const bool multi = cfg->task == PMG_BLOCK_STACK || cfg->task == PMG_BLOCK_REARRANGE;
+  if (multi && (cfg->num_block < 1 || cfg->num_block > 5)) return fail(PMG_ERR_INVALID, "pmg_create: only support up to 5 blocks%s");
+  if (cfg->grip_informed_goal && cfg->task != PMG_BLOCK_STACK) return fail(PMG_ERR_INVALID, "pmg_create: grip_informed_goal is a block_stack option%s");
   if (cfg->batch < 1) return fail(PMG_ERR_INVALID, "pmg_create: batch must be >= 1%s");
   if (cfg->max_episode_steps < 1 || cfg->max_episode_steps >= (1 << 24)) return fail(PMG_ERR_INVALID, "pmg_create: max_episode_steps out of range%s");
   int ndev = 0;
@@ -558,17 +596,21 @@ int pmg_create(const pmg_config* cfg, pmg_handle** out) {
   if (!h) return fail(PMG_ERR_INVALID, "pmg_create: out of host memory%s");
   h->cfg = *cfg;
   const int t = cfg->task;
-  h->nblk = t == PMG_REACH ? 0 : (t == PMG_BLOCK_STACK ? cfg->num_block : 1);
-  h->O = t == PMG_REACH ? 3 : (t == PMG_BLOCK_STACK ? 8 + 16 * h->nblk : 20);
-  h->P = t == PMG_REACH ? 3 : (t == PMG_BLOCK_STACK ? 4 + 3 * h->nblk : 7);
-  h->G = t == PMG_BLOCK_STACK ? 3 * h->nblk : 3;
+  h->multi = multi;
+  h->grasp = t == PMG_PICK_AND_PLACE || t == PMG_BLOCK_STACK;  // kuka_single_step_envs.py:16, kuka_multi_step_envs.py:30,170
+  h->grip = cfg->grip_informed_goal != 0;
+  h->jc = cfg->joint_control != 0;
+  h->nblk = t == PMG_REACH ? 0 : (multi ? cfg->num_block : 1);
+  h->O = (t == PMG_REACH ? 3 : (multi ? 8 + 16 * h->nblk : 20)) + (h->jc ? 7 : 0);
+  h->P = (t == PMG_REACH ? 3 : (multi ? 4 + 3 * h->nblk : 7)) + (h->jc ? 7 : 0);
+  h->G = (multi ? 3 * h->nblk : 3) + (h->grip ? 4 : 0);
   h->W = h->O + h->P + 2 * h->G;
-  h->A = t >= PMG_PICK_AND_PLACE ? 4 : 3;
+  h->A = h->jc ? (h->grasp ? 8 : 7) : (h->grasp ? 4 : 3);  // kuka.py:104-118
   h->state_words = ST_BLK + 13 * h->nblk + h->G + 1;
   h->man_words = num_pairs(h->nblk) * MAN_WORDS;
   h->spawn_w = 2 * h->nblk + h->G;
   // kuka.py:35-51 with obj_range = target_range = 0.15 (kuka_single_step_envs.py, kuka_multi_step_envs.py:29)
-  h->tip_init[0] = -0.52; h->tip_init[1] = 0.0; h->tip_init[2] = t == PMG_PUSH ? 0.175 + 0.001 : 0.25;
+  h->tip_init[0] = -0.52; h->tip_init[1] = 0.0; h->tip_init[2] = (t == PMG_PUSH || t == PMG_BLOCK_REARRANGE) ? 0.175 + 0.001 : 0.25;
   for (int k = 0; k < 3; k++) {
     h->obj_lo[k] = h->tip_init[k] - 0.15; h->obj_hi[k] = h->tip_init[k] + 0.15;
     h->tgt_lo[k] = h->tip_init[k] - 0.15; h->tgt_hi[k] = h->tip_init[k] + 0.15;

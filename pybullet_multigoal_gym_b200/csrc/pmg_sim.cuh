@@ -565,6 +565,11 @@ struct StepIO {
   int epw;  // environments per warp: lanes [0, epw) of every warp own one environment each
   int bulk;         // 1: stage the state tile with TMA bulk copies (full warps only)
   int tile_offset;  // float offset of the state tile inside dynamic shared memory
+  // run-time variants of a task (the block-stack kernels also serve block_rearrange):
+  int grasp;        // the last action column drives the jaws and finger_closeness / finger_vel are observed
+  int jc;           // joint-space control: 7 joint deltas (+ grip), joint poses prepended to observation / policy_state
+  int grip_goal;    // grip-informed goal: achieved / desired goal gain gripper xyz + finger closeness
+  int adim, goal_dim, row_width;  // action columns, goal length, packed row width (all after the variants above)
 };
 
 template <int TASK, int NBLK> struct Dims {

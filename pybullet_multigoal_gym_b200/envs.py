@@ -4,7 +4,9 @@ Mirrors (paths relative to /root/reference/pybullet_multigoal_gym/):
   envs/base_envs/base_env.py:120-138          seed / reset / step
   envs/base_envs/kuka_single_step_base_env.py:193-244   observation dict, _compute_reward
   envs/base_envs/kuka_multi_step_base_env.py:255-345    multi-block observation dict, reward
-  envs/task_envs/kuka_single_step_envs.py:4-46, kuka_multi_step_envs.py:6-32   task presets
+  envs/task_envs/kuka_single_step_envs.py:4-46, kuka_multi_step_envs.py:6-32,151-189   task presets
+  robots/kuka.py:104-118,204-206                joint-space control variant (joint_control=True)
+  envs/base_envs/kuka_multi_step_base_env.py:300-304   grip-informed goals (grip_informed_goal=True)
   gym 0.17.3 wrappers/time_limit.py           done = elapsed >= max_episode_steps
 
 Every array of the reference gains a leading [batch] axis (unless batch=None, which gives the
@@ -18,7 +20,7 @@ import torch
 
 from . import _lib, seeding, spaces
 
-TASK_IDS = {"reach": 0, "push": 1, "pick_and_place": 2, "block_stack": 3}
+TASK_IDS = {"reach": 0, "push": 1, "pick_and_place": 2, "block_stack": 3, "block_rearrange": 4}
 
 
 class ActionError(AssertionError, ValueError):
@@ -35,7 +37,8 @@ class KukaBulletMGEnv:
     metadata = {"render.modes": []}
 
     def __init__(self, task, batch=None, device=0, binary_reward=True, distance_threshold=0.05,
-                 max_episode_steps=50, num_block=4, seed=0, check_actions=True):
+                 max_episode_steps=50, num_block=4, seed=0, check_actions=True,
+                 grip_informed_goal=False, joint_control=False):
         if task not in TASK_IDS:
             raise ValueError("invalid task name: %s, only support: %s" % (task, sorted(TASK_IDS)))
         self._L = _lib.load()
@@ -48,12 +51,19 @@ class KukaBulletMGEnv:
         self.binary_reward = bool(binary_reward)
         self.distance_threshold = float(distance_threshold)
         self._max_episode_steps = int(max_episode_steps)
-        self.num_block = int(num_block) if task == "block_stack" else (0 if task == "reach" else 1)
+        multi = task in ("block_stack", "block_rearrange")
+        self.num_block = int(num_block) if multi else (0 if task == "reach" else 1)
         self.grasping = task in ("pick_and_place", "block_stack")
         self.has_obj = task != "reach"
+        self.joint_control = bool(joint_control)
+        self.grip_informed_goal = bool(grip_informed_goal)
+        if self.grip_informed_goal and task != "block_stack":
+            # kuka_multi_step_envs.py:158 asserts it off for rearrange; the single-step envs have no such option
+            raise AssertionError("%s does not support gripper informed goal representation." % task)
         self.check_actions = check_actions
         cfg = _lib.PmgConfig(TASK_IDS[task], int(num_block), self.batch, int(self.binary_reward),
-                             self.distance_threshold, self._max_episode_steps, self.device.index)
+                             self.distance_threshold, self._max_episode_steps, self.device.index,
+                             int(self.grip_informed_goal), int(self.joint_control))
         h = C.c_void_p()
         _lib.check(self._L.pmg_create(C.byref(cfg), C.byref(h)))
         self._h = h
@@ -287,3 +297,8 @@ class KukaPickAndPlaceEnv(KukaBulletMGEnv):  # kuka_single_step_envs.py:4-17
 class KukaBlockStackEnv(KukaBulletMGEnv):  # kuka_multi_step_envs.py:6-32
     def __init__(self, **kw):
         super().__init__("block_stack", **kw)
+
+
+class KukaBlockRearrangeEnv(KukaBulletMGEnv):  # kuka_multi_step_envs.py:151-189
+    def __init__(self, **kw):
+        super().__init__("block_rearrange", **kw)

@@ -163,3 +163,44 @@ int pmg_emu_smem_bytes(void) { return (int)sizeof(coop::EnvSmem); }
 int pmg_emu_table_bytes(void) { return (int)(coop::GL * coop::LC_W * sizeof(float)); }
 
 }  // extern "C"
+
+// ---- the thread-per-env device code (pmg_sim.cuh) on the host: plain scalar code, no lanes needed ----------
+namespace {
+template <int NBLK>
+void thread_substeps(float* st, float* man, int n_calls) {
+  Env<NBLK> e;
+  for (int k = 0; k < ND; k++) { e.q[k] = st[ST_Q + k]; e.qd[k] = st[ST_QD + k]; e.mt[k] = st[ST_MT + k]; e.mi[k] = st[ST_MI + k]; e.dtau[k] = 0; }
+  for (int b = 0; b < NBLK; b++) {
+    const float* bs = st + ST_BLK + 13 * b;
+    e.bpos[b] = v3(bs[0], bs[1], bs[2]);
+    for (int k = 0; k < 4; k++) e.bquat[b][k] = bs[3 + k];
+    e.bv[b] = v3(bs[7], bs[8], bs[9]); e.bw[b] = v3(bs[10], bs[11], bs[12]);
+  }
+  e.man = man; e.stride = 1; e.overflow = 0;
+  for (int c = 0; c < n_calls; c++) {
+    for (int k = 0; k < ND; k++) e.dtau[k] = -c_dof_damping[k] * e.qd[k];
+    for (int s = 0; s < SUBSTEPS_PER_CALL; s++) substep(e);
+  }
+  for (int k = 0; k < ND; k++) { st[ST_Q + k] = e.q[k]; st[ST_QD + k] = e.qd[k]; }
+  for (int b = 0; b < NBLK; b++) {
+    float* bs = st + ST_BLK + 13 * b;
+    bs[0] = e.bpos[b].x; bs[1] = e.bpos[b].y; bs[2] = e.bpos[b].z;
+    for (int k = 0; k < 4; k++) bs[3 + k] = e.bquat[b][k];
+    bs[7] = e.bv[b].x; bs[8] = e.bv[b].y; bs[9] = e.bv[b].z; bs[10] = e.bw[b].x; bs[11] = e.bw[b].y; bs[12] = e.bw[b].z;
+  }
+}
+}  // namespace
+
+extern "C" {
+// n_calls x 20 substeps of the thread-per-env kernel's physics on one env: state = the usual state words
+// (q qd ee rest mt mi | blocks ...), manifold = num_pairs(nblk) x 41 words, both updated in place.
+int pmg_emu_thread_substeps(int nblk, float* state, float* manifold, int n_calls) {
+  switch (nblk) {
+    case 0: thread_substeps<0>(state, manifold, n_calls); return 0;
+    case 1: thread_substeps<1>(state, manifold, n_calls); return 0;
+    case 2: thread_substeps<2>(state, manifold, n_calls); return 0;
+    case 3: thread_substeps<3>(state, manifold, n_calls); return 0;
+    default: return -1;
+  }
+}
+}
