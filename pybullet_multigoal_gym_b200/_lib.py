@@ -8,7 +8,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-SO_PATH = os.path.join(_HERE, "libpmg.so")
+SO_PATH = os.environ.get("PMG_LIBRARY") or os.path.join(_HERE, "libpmg.so")  # PMG_LIBRARY: instrumented development builds
 
 ABI_VERSION = 2
 

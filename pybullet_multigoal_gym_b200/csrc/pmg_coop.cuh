@@ -340,25 +340,28 @@ __device__ __noinline__ void contact_row_setup(EnvSmem& sm, int c, int n0) {
   for (int kk = 0; kk < 3; kk++) {
     const V3 d = kk == 0 ? nB : (kk == 1 ? t1 : t2);
     const V3 m = cross(wr, d);
-    float J[ND];
+    float J[ND];  // statically indexed everywhere below: stays in registers
 #pragma unroll
     for (int j = 0; j < 7; j++) {
-      const float* pb = sm.pub[j];
-      J[j] = pb[0] * m.x + pb[1] * m.y + pb[2] * m.z + pb[3] * d.x + pb[4] * d.y + pb[5] * d.z;
+      const float4 p0 = *reinterpret_cast<const float4*>(sm.pub[j]);
+      const float2 p1 = *reinterpret_cast<const float2*>(sm.pub[j] + 4);
+      J[j] = p0.x * m.x + p0.y * m.y + p0.z * m.z + p0.w * d.x + p1.x * d.y + p1.y * d.z;
     }
     J[7] = k == 0 ? dot(d, ax1) : 0.0f;
     J[8] = k == 1 ? dot(d, ax2) : 0.0f;
     float* row = sm.rows[c * 3 + kk];
     float denom = 0.0f, rel_vel = 0.0f;
 #pragma unroll
-    for (int r = 0; r < ND; r++) {
-      const float* mr = sm.minv + r * MINV_LD;
-      float acc = 0.0f;
-#pragma unroll
-      for (int j = 0; j < ND; j++) acc += mr[j] * J[j];
-      row[R_MJ + r] = acc; row[R_J + r] = J[r];
-      denom += J[r] * acc;
-      rel_vel += J[r] * sm.vq[r];
+    for (int j = 0; j < ND; j++) { row[R_J + j] = J[j]; rel_vel += J[j] * sm.vq[j]; }
+    // rolled on purpose: this function's register needs leak into the step kernel through the call ABI
+    // (unrolling it costs the caller 60 bytes of spills in its hot loop)
+#pragma unroll 1
+    for (int r = 0; r < ND; r++) {  // M^-1 J^T, one row of M^-1 (three 16-byte loads) per iteration
+      const float4* mr = reinterpret_cast<const float4*>(sm.minv + r * MINV_LD);
+      const float4 m0 = mr[0], m1 = mr[1], m2 = mr[2];
+      const float acc = (m0.x * J[0] + m0.y * J[1] + m0.z * J[2]) + (m0.w * J[3] + m1.x * J[4] + m1.y * J[5]) + (m1.z * J[6] + m1.w * J[7] + m2.x * J[8]);
+      row[R_MJ + r] = acc;
+      denom += row[R_J + r] * acc;
     }
     const float dinv = 1.0f / denom;
     float rhs;
@@ -372,15 +375,19 @@ __device__ __noinline__ void contact_row_setup(EnvSmem& sm, int c, int n0) {
   }
 }
 
-__device__ __forceinline__ float row_dot(const float* v, const float* dq) {
-  float a = v[0] * dq[0], b = v[1] * dq[1], c = v[2] * dq[2];
-  a += v[3] * dq[3]; b += v[4] * dq[4]; c += v[5] * dq[5];
-  a += v[6] * dq[6]; b += v[7] * dq[7]; c += v[8] * dq[8];
-  return a + b + c;
+// One contact row as six 16-byte shared-memory loads: [J0..J8 rhs dinv app] [MJ0..MJ8 denom app2 .]
+struct RowVec { float4 a, b, c; };
+__device__ __forceinline__ RowVec load3(const float* p) {
+  const float4* q = reinterpret_cast<const float4*>(p);
+  RowVec r; r.a = q[0]; r.b = q[1]; r.c = q[2];
+  return r;
 }
-__device__ __forceinline__ void row_axpy(const float* v, float s, float* dq) {
-#pragma unroll
-  for (int j = 0; j < ND; j++) dq[j] += v[j] * s;
+__device__ __forceinline__ float row_dot(const RowVec& v, const float* dq) {
+  return (v.a.x * dq[0] + v.a.y * dq[1] + v.a.z * dq[2]) + (v.a.w * dq[3] + v.b.x * dq[4] + v.b.y * dq[5]) + (v.b.z * dq[6] + v.b.w * dq[7] + v.c.x * dq[8]);
+}
+__device__ __forceinline__ void row_axpy(const RowVec& v, float s, float* dq) {
+  dq[0] += v.a.x * s; dq[1] += v.a.y * s; dq[2] += v.a.z * s; dq[3] += v.a.w * s; dq[4] += v.b.x * s;
+  dq[5] += v.b.y * s; dq[6] += v.b.z * s; dq[7] += v.b.w * s; dq[8] += v.c.x * s;
 }
 
 // One Gauss-Seidel pass over the contact rows (all normals, then the friction pairs with the implicit cone).
@@ -391,8 +398,10 @@ __device__ __forceinline__ void row_axpy(const float* v, float s, float* dq) {
 __device__ __noinline__ float contact_sweep(Grp g, EnvSmem& sm, int nrow_it) {  // nrow | (iteration parity << 8)
   const int nrow = nrow_it & 0xff, it = nrow_it >> 8;
   // The accumulated impulses are double buffered (read slot / write slot swap every iteration, every lane
-  // stores the same value), so no lane waits for another inside the row loops.
-  const int rd = (it & 1) ? R_APP2 : R_APP, wr = (it & 1) ? R_APP : R_APP2;
+  // stores the same value), so no lane waits for another inside the row loops.  Read slot: J-half .w of the
+  // third vector (R_APP) on even iterations, MJ-half .z (R_APP2) on odd ones.
+  const bool odd = (it & 1) != 0;
+  const int wr = odd ? R_APP : R_APP2;
   float dq[ND];
 #pragma unroll
   for (int j = 0; j < ND; j++) dq[j] = sm.vq[j];
@@ -400,12 +409,13 @@ __device__ __noinline__ float contact_sweep(Grp g, EnvSmem& sm, int nrow_it) {  
 #pragma unroll 1
   for (int c = 0; c < nrow; c++) {
     float* row = sm.rows[c * 3];
-    const float app = row[rd];
-    float dl = row[R_RHS] - row_dot(row + R_J, dq) * row[R_DINV];
+    const RowVec j = load3(row + R_J), mj = load3(row + R_MJ);
+    const float app = odd ? mj.c.z : j.c.w;
+    float dl = j.c.y - row_dot(j, dq) * j.c.z;   // rhs - (J . dq) dinv
     const float sum = fminf(fmaxf(app + dl, 0.0f), 1e10f);
     dl = sum - app;
-    row_axpy(row + R_MJ, dl, dq);
-    const float rr = dl * row[R_DENOM];
+    row_axpy(mj, dl, dq);
+    const float rr = dl * mj.c.y;                // denom
     cres = fmaxf(cres, rr * rr);
     row[wr] = sum;
   }
@@ -416,11 +426,13 @@ __device__ __noinline__ float contact_sweep(Grp g, EnvSmem& sm, int nrow_it) {  
     float* ra = sm.rows[c * 3 + 1];
     float* rb = sm.rows[c * 3 + 2];
     const float total = sm.rows[c * 3][wr];
-    const float appA = ra[rd], appB = rb[rd];
+    const RowVec ja = load3(ra + R_J), jb = load3(rb + R_J);
+    const float appA = odd ? ra[R_APP2] : ja.c.w, appB = odd ? rb[R_APP2] : jb.c.w;
     float sA = appA, sB = appB;
     if (total > 0.0f) {
+      const RowVec mja = load3(ra + R_MJ), mjb = load3(rb + R_MJ);
       const float lim = mu * total;
-      float dA = ra[R_RHS] - row_dot(ra + R_J, dq) * ra[R_DINV], dB = rb[R_RHS] - row_dot(rb + R_J, dq) * rb[R_DINV];
+      float dA = ja.c.y - row_dot(ja, dq) * ja.c.z, dB = jb.c.y - row_dot(jb, dq) * jb.c.z;
       sA = appA + dA; sB = appB + dB;
       const float s2 = sA * sA + sB * sB;
       if (s2 >= lim * lim) {
@@ -431,9 +443,9 @@ __device__ __noinline__ float contact_sweep(Grp g, EnvSmem& sm, int nrow_it) {  
         sB = fminf(fmaxf(sB, -cB), cB);
         dA = sA - appA; dB = sB - appB;
       }
-      row_axpy(ra + R_MJ, dA, dq);
-      row_axpy(rb + R_MJ, dB, dq);
-      const float r1_ = dA * ra[R_DENOM], r2_ = dB * rb[R_DENOM];
+      row_axpy(mja, dA, dq);
+      row_axpy(mjb, dB, dq);
+      const float r1_ = dA * mja.c.y, r2_ = dB * mjb.c.y;
       cres = fmaxf(cres, fmaxf(r1_ * r1_, r2_ * r2_));
     }
     ra[wr] = sA; rb[wr] = sB;  // carried over unchanged while the point is open
@@ -447,8 +459,24 @@ __device__ __noinline__ float contact_sweep(Grp g, EnvSmem& sm, int nrow_it) {  
   return cres;
 }
 
+// Development aid (tools/coop_timing.py builds a separate library with -DPMG_COOP_TIMING): cycles spent by
+// octets with cached contacts in [0] the whole substep, [1] narrowphase, [2] row set-up, [3] contact sweeps,
+// and [4] the number of such substeps; [5] whole substep / [6] count for contact-free octets.
+#ifdef PMG_COOP_TIMING
+__device__ unsigned long long g_coop_cycles[8];
+#define PMG_T(var) const long long var = clock64()
+#define PMG_TADD(slot, cyc) do { if (g.lane == 0) atomicAdd(&g_coop_cycles[slot], (unsigned long long)(cyc)); } while (0)
+#else
+#define PMG_T(var)
+#define PMG_TADD(slot, cyc)
+#endif
+
 // ---- one 2 ms substep ---------------------------------------------------------------------------------
 __device__ void substep(const Grp& g, EnvSmem& sm, Lane& L) {
+  PMG_T(t_begin);
+#ifdef PMG_COOP_TIMING
+  long long t_sweeps = 0;
+#endif
   const int lane = g.lane;
   const bool arm = lane < 7, hand = lane == 7;
   // 1. link frames (scan), joint axes
@@ -528,6 +556,7 @@ __device__ void substep(const Grp& g, EnvSmem& sm, Lane& L) {
     hd[15] = Pref.x; hd[16] = Pref.y; hd[17] = Pref.z; hd[18] = ax1.x; hd[19] = ax1.y; hd[20] = ax1.z;
   }
   // collision detection of the two finger-table pairs: lane k runs pair k on the shared-memory manifold
+  PMG_T(t_col0);
   if (lane < COOP_PAIRS) {
     ManRef mr; mr.man = sm.man; mr.stride = 1;
     const float tc[3] = PMG_TABLE_CENTER, th[3] = PMG_TABLE_HALF, fh[3] = PMG_FINGER_HALF;
@@ -535,6 +564,7 @@ __device__ void substep(const Grp& g, EnvSmem& sm, Lane& L) {
     BoxScratch& scr = *reinterpret_cast<BoxScratch*>(&sm.rows[lane * (MAXPTS * 3 / 2)][0]);
     collide_pair(mr, lane, lane == 0 ? pf1 : pf2, Rg, v3(fh[0], fh[1], fh[2]), v3(tc[0], tc[1], tc[2]), m3_identity(), v3(th[0], th[1], th[2]), scr);
   }
+  PMG_T(t_col1);
   // 4. subtree wrenches and composite inertias: suffix sums over the chain
   Fs = g.rscan(Fs); Ns = g.rscan(Ns); hs = g.rscan(hs);
   Is.xx = g.rscan(Is.xx); Is.xy = g.rscan(Is.xy); Is.xz = g.rscan(Is.xz);
@@ -647,10 +677,12 @@ __device__ void substep(const Grp& g, EnvSmem& sm, Lane& L) {
   // contact rows: one normal + two tangents per cached manifold point, point c set up by lane c
   const int n0 = __float_as_int(sm.man[0]);
   const int nrow = n0 + __float_as_int(sm.man[MAN_WORDS]);
+  PMG_T(t_set0);
   if (nrow) {
     if (lane < nrow) contact_row_setup(sm, lane, n0);
     g.sync();
   }
+  PMG_T(t_set1);
   // projected Gauss-Seidel: <= 5 iterations, early exit on the largest squared velocity change
   for (int it = 0; it < SOLVER_ITERS; it++) {
     s.big0 = s.big1 = 0.0f;
@@ -672,7 +704,11 @@ __device__ void substep(const Grp& g, EnvSmem& sm, Lane& L) {
       sm.vq[L.dof0] = s.dqd0;
       if (hand) sm.vq[8] = s.dqd1;
       g.sync();
+      PMG_T(t_sw0);
       res = fmaxf(res, contact_sweep(g, sm, nrow | ((it & 1) << 8)));
+#ifdef PMG_COOP_TIMING
+      t_sweeps += clock64() - t_sw0;
+#endif
       s.dqd0 = sm.vq[L.dof0];
       s.dqd1 = sm.vq[8];
     }
@@ -684,6 +720,11 @@ __device__ void substep(const Grp& g, EnvSmem& sm, Lane& L) {
   L.qd1 = hand ? fminf(fmaxf(L.qd1 + s.dqd1, -MAX_COORD_VEL), MAX_COORD_VEL) : 0.0f;
   L.q0 += L.qd0 * DT;
   L.q1 += L.qd1 * DT;
+#ifdef PMG_COOP_TIMING
+  if (nrow) {
+    PMG_TADD(0, clock64() - t_begin); PMG_TADD(1, t_col1 - t_col0); PMG_TADD(2, t_set1 - t_set0); PMG_TADD(3, t_sweeps); PMG_TADD(4, 1);
+  } else { PMG_TADD(5, clock64() - t_begin); PMG_TADD(6, 1); PMG_TADD(7, t_col1 - t_col0); }
+#endif
 }
 
 // ---- one env.step() of a Reach environment (TASK 0, no blocks) -------------------------------------

@@ -21,6 +21,8 @@
 #define __align__(n) alignas(n)
 #define __launch_bounds__(...)
 
+struct alignas(16) float4 { float x, y, z, w; };
+struct alignas(8) float2 { float x, y; };
 static inline float rsqrtf(float x) { return 1.0f / sqrtf(x); }
 static inline int __float_as_int(float f) { int i; memcpy(&i, &f, 4); return i; }
 static inline float __int_as_float(int i) { float f; memcpy(&f, &i, 4); return f; }

@@ -1,0 +1,28 @@
+"""Development aid: per-phase cycle counts of the cooperative Reach kernel for octets with / without contacts.
+
+Build (here):  nvcc ... -DPMG_COOP_TIMING -o gpurun_out/libpmg_timing.so   (see tools/gpu_timing.sh)
+Run (GPU box): PMG_LIBRARY=pybullet_multigoal_gym_b200/libpmg_timing.so python tools/coop_timing.py"""
+import ctypes as C
+import os
+import sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+import pybullet_multigoal_gym_b200 as pmg
+from pybullet_multigoal_gym_b200 import _lib
+
+B = 8192
+env = pmg.make_env(task="reach", batch=B, check_actions=False)
+L = _lib.load()
+acts = torch.rand((50, B, 3), device="cuda") * 2 - 1
+out = torch.empty((B, env.row_width), device="cuda"); r = torch.empty((B,), device="cuda")
+d = torch.empty((B,), dtype=torch.uint8, device="cuda"); s = torch.empty((B,), dtype=torch.uint8, device="cuda")
+buf = (C.c_ulonglong * 8)()
+L.pmg_debug_coop_cycles(buf)
+for t in range(50):
+    env.step_packed(acts[t], out, r, d, s)
+    if t in (5, 30, 45):
+        L.pmg_debug_coop_cycles(buf)
+        c = list(buf)
+        hot_n, cold_n = max(c[4], 1), max(c[6], 1)
+        print("after step %2d: hot octet-substeps %8d: substep %7.0f cyc = narrowphase %6.0f + row set-up %6.0f + sweeps %6.0f + rest %6.0f | cold %9d: substep %6.0f cyc (broadphase %4.0f)"
+              % (t, c[4], c[0] / hot_n, c[1] / hot_n, c[2] / hot_n, c[3] / hot_n, (c[0] - c[1] - c[2] - c[3]) / hot_n, c[6], c[5] / cold_n, c[7] / cold_n))
