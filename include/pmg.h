@@ -104,6 +104,23 @@ int pmg_step_host(pmg_handle* h, const float* action_host, float* obs_host, floa
 int pmg_compute_reward(const float* ag_dev, const float* dg_dev, int64_t n, int32_t g, float threshold,
                        int32_t binary_reward, float* reward_dev, uint8_t* achieved_dev, void* stream);
 
+/* ---- hindsight relabelling around _compute_reward ------------------------------------
+ * The reference's agents (README.md:18-20) relabel stored transitions with goals achieved later in the same
+ * episode ("future" strategy) and re-evaluate env._compute_reward on them.  Episodes live on the device:
+ *   ag_dev [n_episodes, horizon + 1, g]  achieved goals, ag[e][t + 1] = achieved goal after transition t
+ *   dg_dev [n_episodes, g]               the goals the episodes were collected with
+ * pmg_her_sample draws n transitions: episode uniform, t uniform in [0, horizon), and with probability
+ * her_prob a future index uniform in [t + 1, horizon] (else -1 = keep the original goal), from a counter-based
+ * hash of (seed, sample index) -- oracle/her_oracle.py restates it bit-exactly in numpy.
+ * pmg_her_relabel gathers the relabelled goal of every sample and evaluates _compute_reward(ag[e][t + 1], goal)
+ * (kuka_single_step_base_env.py:237-244) in the same pass. */
+int pmg_her_sample(int64_t n, int32_t n_episodes, int32_t horizon, float her_prob, uint64_t seed,
+                   int32_t* episode_dev, int32_t* t_dev, int32_t* future_dev, void* stream);
+int pmg_her_relabel(const float* ag_dev, const float* dg_dev, int32_t n_episodes, int32_t horizon, int32_t g,
+                    const int32_t* episode_dev, const int32_t* t_dev, const int32_t* future_dev, int64_t n,
+                    float threshold, int32_t binary_reward, float* goal_out_dev, float* reward_dev,
+                    uint8_t* achieved_dev, void* stream);
+
 /* State access for teacher-forced parity tests (no reference counterpart).  Row layout, floats:
  * q[9] qd[9] ee_target[3] rest_pose[7] motor_target[9] motor_max_impulse[9], then per block
  * pos[3] quat_xyzw[4] linvel[3] angvel[3], then desired_goal[G], then elapsed steps.

@@ -16,7 +16,7 @@ ABI_VERSION = 2
 SYMBOLS = [
     "pmg_abi_version", "pmg_last_error", "pmg_create", "pmg_destroy", "pmg_dims", "pmg_seed",
     "pmg_reset", "pmg_spawn_width", "pmg_last_spawn", "pmg_step", "pmg_step_host",
-    "pmg_compute_reward", "pmg_state_width", "pmg_get_state", "pmg_set_state",
+    "pmg_compute_reward", "pmg_her_sample", "pmg_her_relabel", "pmg_state_width", "pmg_get_state", "pmg_set_state",
     "pmg_launch_count", "pmg_overflow_count",
 ]
 
@@ -56,6 +56,9 @@ def load():
     L.pmg_step.argtypes = [vp, fp, fp, fp, u8p, u8p, vp]
     L.pmg_step_host.argtypes = [vp, fp, fp, fp, u8p, u8p, vp]
     L.pmg_compute_reward.argtypes = [fp, fp, C.c_int64, C.c_int32, C.c_float, C.c_int32, fp, u8p, vp]
+    L.pmg_her_sample.argtypes = [C.c_int64, C.c_int32, C.c_int32, C.c_float, C.c_uint64, vp, vp, vp, vp]
+    L.pmg_her_relabel.argtypes = [fp, fp, C.c_int32, C.c_int32, C.c_int32, vp, vp, vp, C.c_int64, C.c_float, C.c_int32,
+                                  fp, fp, u8p, vp]
     L.pmg_state_width.argtypes = [vp]
     L.pmg_get_state.argtypes = [vp, fp]
     L.pmg_set_state.argtypes = [vp, fp]

@@ -338,6 +338,40 @@ __global__ void reward_kernel(const float* ag, const float* dg, int64_t n, int g
   ok[i] = na ? 0 : 1;
 }
 
+// ---- hindsight relabelling (see include/pmg.h) ---------------------------------------------------
+__host__ __device__ inline uint64_t her_mix(uint64_t z) {  // splitmix64 finaliser
+  z = (z ^ (z >> 30)) * 0xbf58476d1ce4e5b9ull;
+  z = (z ^ (z >> 27)) * 0x94d049bb133111ebull;
+  return z ^ (z >> 31);
+}
+__global__ void her_sample_kernel(int64_t n, int n_episodes, int horizon, float her_prob, uint64_t seed,
+                                  int32_t* ep, int32_t* tt, int32_t* fut) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const uint64_t base = seed + 0x9e3779b97f4a7c15ull * (uint64_t)(3 * i + 1);
+  const uint64_t h0 = her_mix(base), h1 = her_mix(base + 0x9e3779b97f4a7c15ull), h2 = her_mix(base + 2 * 0x9e3779b97f4a7c15ull);
+  const int e = (int)((h0 >> 32) * (uint64_t)n_episodes >> 32);           // floor(u * n) on the top 32 bits
+  const int t = (int)((h1 >> 32) * (uint64_t)horizon >> 32);
+  const float u = (float)(h2 >> 40) * (1.0f / 16777216.0f);              // 24-bit uniform in [0, 1)
+  const int span = horizon - t;                                           // future indices t + 1 .. horizon
+  const int f = u < her_prob ? t + 1 + (int)((h2 & 0xffffffffull) * (uint64_t)span >> 32) : -1;
+  ep[i] = e; tt[i] = t; fut[i] = f;
+}
+__global__ void her_relabel_kernel(const float* ag, const float* dg, int horizon, int g, const int32_t* ep, const int32_t* tt,
+                                   const int32_t* fut, int64_t n, float thr, int binary, float* goal_out, float* reward, uint8_t* ok) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int e = ep[i], t = tt[i], f = fut[i];
+  const float* achieved = ag + ((size_t)e * (horizon + 1) + t + 1) * g;
+  const float* goal = f >= 0 ? ag + ((size_t)e * (horizon + 1) + f) * g : dg + (size_t)e * g;
+  float d2 = 0.0f;
+  for (int k = 0; k < g; k++) { const float gk = goal[k]; goal_out[i * g + k] = gk; const float d = achieved[k] - gk; d2 += d * d; }
+  const float d = sqrtf(d2);
+  const bool na = d > thr;
+  reward[i] = binary ? -(na ? 1.0f : 0.0f) : -d;
+  ok[i] = na ? 0 : 1;
+}
+
 // Construction-time state: BaseBulletMGEnv.__init__ resets the robot once on its own (base_env.py:41)
 // before its first self.reset(), i.e. the rest pose (kuka.py:27) gets one IK refinement here.
 __global__ void init_state_kernel(float* state, int batch, int nblk, float tx, float ty, float tz) {
@@ -751,6 +785,26 @@ int pmg_compute_reward(const float* ag, const float* dg, int64_t n, int32_t g, f
   if (!ag || !dg || !reward || !ok || n < 0 || g < 1) return fail(PMG_ERR_INVALID, "pmg_compute_reward: bad argument%s");
   if (n == 0) return PMG_OK;
   reward_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(ag, dg, n, g, thr, binary, reward, ok);
+  CUDA_TRY(cudaGetLastError());
+  return PMG_OK;
+}
+
+int pmg_her_sample(int64_t n, int32_t n_episodes, int32_t horizon, float her_prob, uint64_t seed, int32_t* ep, int32_t* tt,
+                   int32_t* fut, void* stream) {
+  if (!ep || !tt || !fut || n < 0 || n_episodes < 1 || horizon < 1) return fail(PMG_ERR_INVALID, "pmg_her_sample: bad argument%s");
+  if (n == 0) return PMG_OK;
+  her_sample_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(n, n_episodes, horizon, her_prob, seed, ep, tt, fut);
+  CUDA_TRY(cudaGetLastError());
+  return PMG_OK;
+}
+
+int pmg_her_relabel(const float* ag, const float* dg, int32_t n_episodes, int32_t horizon, int32_t g, const int32_t* ep,
+                    const int32_t* tt, const int32_t* fut, int64_t n, float thr, int32_t binary, float* goal_out, float* reward,
+                    uint8_t* ok, void* stream) {
+  if (!ag || !dg || !ep || !tt || !fut || !goal_out || !reward || !ok || n < 0 || n_episodes < 1 || horizon < 1 || g < 1)
+    return fail(PMG_ERR_INVALID, "pmg_her_relabel: bad argument%s");
+  if (n == 0) return PMG_OK;
+  her_relabel_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(ag, dg, horizon, g, ep, tt, fut, n, thr, binary, goal_out, reward, ok);
   CUDA_TRY(cudaGetLastError());
   return PMG_OK;
 }

@@ -634,13 +634,48 @@ __device__ int box_box(V3 p1, const M3& R1, V3 A, V3 p2, const M3& R2, V3 B, Box
   float c1 = dot(center, ra1), c2 = dot(center, ra2);
   float m11 = dot(ra1, rb1), m12 = dot(ra1, rb2), m21 = dot(ra2, rb1), m22 = dot(ra2, rb2);
   float* quad = scr.quad;
+  float qx[4], qy[4];  // the incident face's corners in the reference face's 2-D frame (registers)
   {
     float k1 = m11 * Sb[a1], k2 = m21 * Sb[a1], k3 = m12 * Sb[a2], k4 = m22 * Sb[a2];
-    quad[0] = c1 - k1 - k3; quad[1] = c2 - k2 - k4;
-    quad[2] = c1 - k1 + k3; quad[3] = c2 - k2 + k4;
-    quad[4] = c1 + k1 + k3; quad[5] = c2 + k2 + k4;
-    quad[6] = c1 + k1 - k3; quad[7] = c2 + k2 - k4;
+    qx[0] = c1 - k1 - k3; qy[0] = c2 - k2 - k4;
+    qx[1] = c1 - k1 + k3; qy[1] = c2 - k2 + k4;
+    qx[2] = c1 + k1 + k3; qy[2] = c2 + k2 + k4;
+    qx[3] = c1 + k1 - k3; qy[3] = c2 + k2 - k4;
   }
+  {
+    // Fast path, the usual resting contact: the incident face lies inside the reference face (nothing to
+    // clip) and all four corners touch (nothing to cull): the contacts are the four corners, in order.  The
+    // arithmetic per corner is the generic path's, so the output is bit-identical to it.
+    const float ra = Sa[code1], rb = Sa[code2], sn = Sa[codeN];
+    bool all_in = true;
+#pragma unroll
+    for (int j = 0; j < 4; j++) all_in = all_in && fabsf(qx[j]) < ra && fabsf(qy[j]) < rb;
+    if (all_in) {
+      const float det = 1.0f / (m11 * m22 - m12 * m21);
+      const float i11 = m11 * det, i12 = m12 * det, i21 = m21 * det, i22 = m22 * det;
+      V3 pt[4]; float dp[4];
+      bool all_touch = true;
+#pragma unroll
+      for (int j = 0; j < 4; j++) {
+        float k1 = i22 * (qx[j] - c1) - i12 * (qy[j] - c2);
+        float k2 = -i21 * (qx[j] - c1) + i11 * (qy[j] - c2);
+        pt[j] = center + k1 * rb1 + k2 * rb2;
+        dp[j] = sn - dot(normal2, pt[j]);
+        all_touch = all_touch && dp[j] >= 0;
+      }
+      if (all_touch) {
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+          V3 w = pt[j] + pa;
+          if (swap) w -= dp[j] * normal;  // incident face was on A: move the point onto B
+          out[j].pB = w; out[j].nB = -normal; out[j].dist = -dp[j];
+        }
+        return 4;
+      }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 4; j++) { quad[2 * j] = qx[j]; quad[2 * j + 1] = qy[j]; }
   float rect[2] = {Sa[code1], Sa[code2]};
   float* ret = scr.ret;
   int n = clip_quad_to_rect(rect, quad, ret, scr.buf);
