@@ -44,6 +44,7 @@ struct __align__(16) EnvSmem {
   float hand[24];                   // gripper frame for the contact rows: Rg[9] pf1 pf2 Pref ax1 (kept out of registers)
   float vq[12];                     // joint velocities (row set-up), then PGS delta velocities (contact sweeps)
   float rows[MAXPTS * 3][ROW_W];    // contact rows (layout R_* above); narrowphase scratch before they are built
+  float app[2][MAXPTS * 3];         // accumulated impulses of the contact rows, double buffered over the PGS iterations
 };
 
 // ---- the group (octet) interface ---------------------------------------------------------------
@@ -371,7 +372,8 @@ __device__ __noinline__ void contact_row_setup(EnvSmem& sm, int c, int n0) {
       if (pen > 0.0f) vel_err -= pen * INV_DT; else pos_err = -pen * CONTACT_ERP * INV_DT;
       rhs = (pos_err + vel_err) * dinv;
     } else rhs = -rel_vel * dinv;
-    row[R_RHS] = rhs; row[R_DINV] = dinv; row[R_DENOM] = denom; row[R_APP] = 0.0f; row[R_APP2] = 0.0f;
+    row[R_RHS] = rhs; row[R_DINV] = dinv; row[R_DENOM] = denom;
+    sm.app[0][c * 3 + kk] = 0.0f;
   }
 }
 
@@ -397,11 +399,10 @@ __device__ __forceinline__ void row_axpy(const RowVec& v, float s, float* dq) {
 // contact-free solver loop.  Delta velocities come in and go out through sm.vq.
 __device__ __noinline__ float contact_sweep(Grp g, EnvSmem& sm, int nrow_it) {  // nrow | (iteration parity << 8)
   const int nrow = nrow_it & 0xff, it = nrow_it >> 8;
-  // The accumulated impulses are double buffered (read slot / write slot swap every iteration, every lane
-  // stores the same value), so no lane waits for another inside the row loops.  Read slot: J-half .w of the
-  // third vector (R_APP) on even iterations, MJ-half .z (R_APP2) on odd ones.
-  const bool odd = (it & 1) != 0;
-  const int wr = odd ? R_APP : R_APP2;
+  // The accumulated impulses are double buffered (read buffer / write buffer swap every iteration, every lane
+  // stores the same value), so no lane waits for another inside the row loops.
+  const float* app_rd = sm.app[it & 1];
+  float* app_wr = sm.app[(it & 1) ^ 1];
   float dq[ND];
 #pragma unroll
   for (int j = 0; j < ND; j++) dq[j] = sm.vq[j];
@@ -410,14 +411,14 @@ __device__ __noinline__ float contact_sweep(Grp g, EnvSmem& sm, int nrow_it) {  
   for (int c = 0; c < nrow; c++) {
     float* row = sm.rows[c * 3];
     const RowVec j = load3(row + R_J), mj = load3(row + R_MJ);
-    const float app = odd ? mj.c.z : j.c.w;
+    const float app = app_rd[c * 3];
     float dl = j.c.y - row_dot(j, dq) * j.c.z;   // rhs - (J . dq) dinv
     const float sum = fminf(fmaxf(app + dl, 0.0f), 1e10f);
     dl = sum - app;
     row_axpy(mj, dl, dq);
     const float rr = dl * mj.c.y;                // denom
     cres = fmaxf(cres, rr * rr);
-    row[wr] = sum;
+    app_wr[c * 3] = sum;
   }
   g.sync();  // the new normal impulses bound the friction rows
   const float mu = (float)PMG_FINGER_FRICTION * (float)PMG_TABLE_FRICTION;
@@ -425,9 +426,9 @@ __device__ __noinline__ float contact_sweep(Grp g, EnvSmem& sm, int nrow_it) {  
   for (int c = 0; c < nrow; c++) {  // implicit friction cone: both tangent rows of a point together
     float* ra = sm.rows[c * 3 + 1];
     float* rb = sm.rows[c * 3 + 2];
-    const float total = sm.rows[c * 3][wr];
+    const float total = app_wr[c * 3];
     const RowVec ja = load3(ra + R_J), jb = load3(rb + R_J);
-    const float appA = odd ? ra[R_APP2] : ja.c.w, appB = odd ? rb[R_APP2] : jb.c.w;
+    const float appA = app_rd[c * 3 + 1], appB = app_rd[c * 3 + 2];
     float sA = appA, sB = appB;
     if (total > 0.0f) {
       const RowVec mja = load3(ra + R_MJ), mjb = load3(rb + R_MJ);
@@ -448,7 +449,7 @@ __device__ __noinline__ float contact_sweep(Grp g, EnvSmem& sm, int nrow_it) {  
       const float r1_ = dA * mja.c.y, r2_ = dB * mjb.c.y;
       cres = fmaxf(cres, fmaxf(r1_ * r1_, r2_ * r2_));
     }
-    ra[wr] = sA; rb[wr] = sB;  // carried over unchanged while the point is open
+    app_wr[c * 3 + 1] = sA; app_wr[c * 3 + 2] = sB;  // carried over unchanged while the point is open
   }
   g.sync();  // every lane has read sm.vq
   if (g.lane == 0) {

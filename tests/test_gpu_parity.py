@@ -266,3 +266,41 @@ def test_velocity_observations_of_resting_blocks_are_bounded(oracle):
             worst_vel = max(worst_vel, float(d[vel].max()))
     print("resting blocks: worst position-entry error %.3g, worst velocity-entry error %.3g" % (worst_pos, worst_vel))
     assert worst_pos < TOL and worst_vel < 2e-3
+
+
+def test_cooperative_and_thread_per_env_reach_kernels_agree():
+    """The two Reach step kernels (lane-cooperative: scans + Gauss-Jordan + owner-broadcast PGS; thread-per-env:
+    serial recursions + Cholesky) are different fp32 organisations of the same system: 40 open-loop steps with
+    the jaws pressed onto the table, tips within 6e-5 of each other (each is within ~1.5e-5 of the oracle on
+    this kind of rollout), flags identical away from the threshold."""
+    import os
+    B, T = 256, 40
+    old = os.environ.get("PMG_COOP")
+    try:
+        os.environ["PMG_COOP"] = "1"
+        coop = _mk("reach", B)
+        os.environ["PMG_COOP"] = "0"
+        thread = _mk("reach", B)
+    finally:
+        if old is None:
+            os.environ.pop("PMG_COOP", None)
+        else:
+            os.environ["PMG_COOP"] = old
+    o1, o2 = coop.reset(), thread.reset()
+    assert torch.equal(o1["desired_goal"], o2["desired_goal"])
+    gen = torch.Generator(device="cuda")
+    gen.manual_seed(3)
+    worst = 0.0
+    for t in range(T):
+        a = torch.rand((B, 3), device="cuda", generator=gen) * 2 - 1
+        if t < 14:
+            a[: B // 2, 2] = -1.0
+        (x1, r1, d1, i1), (x2, r2, d2, i2) = coop.step(a), thread.step(a)
+        err = float((x1["achieved_goal"] - x2["achieved_goal"]).abs().max())
+        worst = max(worst, err)
+        assert err < 6e-5, (t, err)
+        assert torch.equal(d1, d2)
+        dist = (x1["achieved_goal"] - x1["desired_goal"]).norm(dim=1)
+        clear = (dist - 0.05).abs() > 1e-4
+        assert torch.equal(i1["goal_achieved"][clear], i2["goal_achieved"][clear]) and torch.equal(r1[clear], r2[clear])
+    print("cooperative vs thread-per-env Reach kernels: worst tip difference %.3g over %d steps" % (worst, T))
