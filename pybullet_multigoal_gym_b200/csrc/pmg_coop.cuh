@@ -62,9 +62,15 @@ struct Grp {
   __device__ __forceinline__ void sync() const { __syncwarp(mask); }
 #endif
   // value of lane - d (own value when there is no such lane) / lane + d / lane ^ m
+#ifdef PMG_EMULATE
   __device__ __forceinline__ float up(float v, int d) const { return shfl(v, lane >= d ? lane - d : lane); }
   __device__ __forceinline__ float down(float v, int d) const { return shfl(v, lane + d < GL ? lane + d : lane); }
   __device__ __forceinline__ float bfly(float v, int m) const { return shfl(v, lane ^ m); }
+#else  // the native forms clamp inside the 8-lane segment themselves: no source-lane arithmetic
+  __device__ __forceinline__ float up(float v, int d) const { return __shfl_up_sync(mask, v, d, GL); }
+  __device__ __forceinline__ float down(float v, int d) const { return __shfl_down_sync(mask, v, d, GL); }
+  __device__ __forceinline__ float bfly(float v, int m) const { return __shfl_xor_sync(mask, v, m, GL); }
+#endif
   __device__ __forceinline__ V3 shfl(V3 v, int src) const { return v3(shfl(v.x, src), shfl(v.y, src), shfl(v.z, src)); }
   __device__ __forceinline__ V3 up(V3 v, int d) const { return v3(up(v.x, d), up(v.y, d), up(v.z, d)); }
   __device__ __forceinline__ V3 down(V3 v, int d) const { return v3(down(v.x, d), down(v.y, d), down(v.z, d)); }
