@@ -839,11 +839,11 @@ int64_t pmg_launch_count(const pmg_handle* h) { return h ? h->launches : 0; }
 
 #ifdef PMG_COOP_TIMING
 // development builds only (tools/coop_timing.py): read and clear the cycle counters of pmg_coop.cuh
-int pmg_debug_coop_cycles(unsigned long long* out8) {
+int pmg_debug_coop_cycles(unsigned long long* out16) {
   cudaDeviceSynchronize();
-  unsigned long long zero[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-  if (cudaMemcpyFromSymbol(out8, coop::g_coop_cycles, sizeof zero) != cudaSuccess) return -2;
-  return cudaMemcpyToSymbol(coop::g_coop_cycles, zero, sizeof zero) == cudaSuccess ? 0 : -2;
+  unsigned long long zero[16] = {0};
+  if (cudaMemcpyFromSymbol(out16, pmg::g_coop_cycles, sizeof zero) != cudaSuccess) return -2;
+  return cudaMemcpyToSymbol(pmg::g_coop_cycles, zero, sizeof zero) == cudaSuccess ? 0 : -2;
 }
 #endif
 

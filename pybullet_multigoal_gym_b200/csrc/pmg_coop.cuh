@@ -470,9 +470,8 @@ __device__ __noinline__ float contact_sweep(Grp g, EnvSmem& sm, int nrow_it) {  
 // octets with cached contacts in [0] the whole substep, [1] narrowphase, [2] row set-up, [3] contact sweeps,
 // and [4] the number of such substeps; [5] whole substep / [6] count for contact-free octets.
 #ifdef PMG_COOP_TIMING
-__device__ unsigned long long g_coop_cycles[8];
 #define PMG_T(var) const long long var = clock64()
-#define PMG_TADD(slot, cyc) do { if (g.lane == 0) atomicAdd(&g_coop_cycles[slot], (unsigned long long)(cyc)); } while (0)
+#define PMG_TADD(slot, cyc) do { if (g.lane == 0) atomicAdd(&pmg::g_coop_cycles[slot], (unsigned long long)(cyc)); } while (0)
 #else
 #define PMG_T(var)
 #define PMG_TADD(slot, cyc)

@@ -613,11 +613,13 @@ __device__ int box_box(V3 p1, const M3& R1, V3 A, V3 p2, const M3& R2, V3 B, Box
   }
   // face contact: reference face on `a`, incident face on `b`
   const bool swap = code > 3;
-  const M3& Ra = swap ? R2 : R1;
-  const M3& Rb = swap ? R1 : R2;
+  M3 Ra, Rb;  // by value, with selects: a reference picked at run time would pin R1 / R2 to local memory
+  Ra.r0 = swap ? R2.r0 : R1.r0; Ra.r1 = swap ? R2.r1 : R1.r1; Ra.r2 = swap ? R2.r2 : R1.r2;
+  Rb.r0 = swap ? R1.r0 : R2.r0; Rb.r1 = swap ? R1.r1 : R2.r1; Rb.r2 = swap ? R1.r2 : R2.r2;
   V3 pa = swap ? p2 : p1, pb = swap ? p1 : p2;
-  const float* Sa = swap ? Bh : Ah;
-  const float* Sb = swap ? Ah : Bh;
+  // half extents of the reference / incident box, picked with selects: indexing Ah / Bh dynamically would move
+  // both arrays (and every SAT read of them above) to local memory
+  const V3 SaV = swap ? B : A, SbV = swap ? A : B;
   V3 normal2 = swap ? -normal : normal;
   V3 nr = mulT(Rb, normal2);
   float anr[3] = {fabsf(nr.x), fabsf(nr.y), fabsf(nr.z)};
@@ -627,7 +629,7 @@ __device__ int box_box(V3 p1, const M3& R1, V3 A, V3 p2, const M3& R2, V3 B, Box
   } else {
     if (anr[0] > anr[2]) { lanr = 0; a1 = 1; a2 = 2; } else { a1 = 0; a2 = 1; lanr = 2; }
   }
-  V3 center = pb - pa + ((comp(nr, lanr) < 0 ? 1.0f : -1.0f) * Sb[lanr]) * col(Rb, lanr);
+  V3 center = pb - pa + ((comp(nr, lanr) < 0 ? 1.0f : -1.0f) * comp(SbV, lanr)) * col(Rb, lanr);
   int codeN = swap ? code - 4 : code - 1, code1, code2;
   if (codeN == 0) { code1 = 1; code2 = 2; } else if (codeN == 1) { code1 = 0; code2 = 2; } else { code1 = 0; code2 = 1; }
   V3 ra1 = col(Ra, code1), ra2 = col(Ra, code2), rb1 = col(Rb, a1), rb2 = col(Rb, a2);
@@ -636,7 +638,8 @@ __device__ int box_box(V3 p1, const M3& R1, V3 A, V3 p2, const M3& R2, V3 B, Box
   float* quad = scr.quad;
   float qx[4], qy[4];  // the incident face's corners in the reference face's 2-D frame (registers)
   {
-    float k1 = m11 * Sb[a1], k2 = m21 * Sb[a1], k3 = m12 * Sb[a2], k4 = m22 * Sb[a2];
+    const float sb1 = comp(SbV, a1), sb2 = comp(SbV, a2);
+    float k1 = m11 * sb1, k2 = m21 * sb1, k3 = m12 * sb2, k4 = m22 * sb2;
     qx[0] = c1 - k1 - k3; qy[0] = c2 - k2 - k4;
     qx[1] = c1 - k1 + k3; qy[1] = c2 - k2 + k4;
     qx[2] = c1 + k1 + k3; qy[2] = c2 + k2 + k4;
@@ -646,7 +649,7 @@ __device__ int box_box(V3 p1, const M3& R1, V3 A, V3 p2, const M3& R2, V3 B, Box
     // Fast path, the usual resting contact: the incident face lies inside the reference face (nothing to
     // clip) and all four corners touch (nothing to cull): the contacts are the four corners, in order.  The
     // arithmetic per corner is the generic path's, so the output is bit-identical to it.
-    const float ra = Sa[code1], rb = Sa[code2], sn = Sa[codeN];
+    const float ra = comp(SaV, code1), rb = comp(SaV, code2), sn = comp(SaV, codeN);
     bool all_in = true;
 #pragma unroll
     for (int j = 0; j < 4; j++) all_in = all_in && fabsf(qx[j]) < ra && fabsf(qy[j]) < rb;
@@ -676,7 +679,7 @@ __device__ int box_box(V3 p1, const M3& R1, V3 A, V3 p2, const M3& R2, V3 B, Box
   }
 #pragma unroll
   for (int j = 0; j < 4; j++) { quad[2 * j] = qx[j]; quad[2 * j + 1] = qy[j]; }
-  float rect[2] = {Sa[code1], Sa[code2]};
+  float rect[2] = {comp(SaV, code1), comp(SaV, code2)};
   float* ret = scr.ret;
   int n = clip_quad_to_rect(rect, quad, ret, scr.buf);
   if (n < 1) return 0;
@@ -688,7 +691,7 @@ __device__ int box_box(V3 p1, const M3& R1, V3 A, V3 p2, const M3& R2, V3 B, Box
     float k1 = m22 * (ret[2 * j] - c1) - m12 * (ret[2 * j + 1] - c2);
     float k2 = -m21 * (ret[2 * j] - c1) + m11 * (ret[2 * j + 1] - c2);
     V3 pt = center + k1 * rb1 + k2 * rb2;
-    float dp = Sa[codeN] - dot(normal2, pt);
+    float dp = comp(SaV, codeN) - dot(normal2, pt);
     if (dp >= 0) { point[cnum] = pt; dep[cnum] = dp; ret[2 * cnum] = ret[2 * j]; ret[2 * cnum + 1] = ret[2 * j + 1]; cnum++; }
   }
   if (cnum < 1) return 0;

@@ -144,6 +144,10 @@ __device__ void manifold_refresh(ManRef& e, int k, float thr, V3 pa, const M3& R
   if (n != __float_as_int(e.mw(k, 0))) e.mw(k, 0) = __int_as_float(n);
 }
 
+#ifdef PMG_COOP_TIMING
+__device__ unsigned long long g_coop_cycles[16];
+#endif
+
 // One collision pair: broadphase (world AABBs grown by the margin), box-box narrowphase into the
 // persistent manifold, refresh.  Boxes given by centre, orientation, half extents.
 __device__ void collide_pair(ManRef& e, int k, V3 pa, const M3& Ra, V3 ha, V3 pb, const M3& Rb, V3 hb, BoxScratch& scr) {
@@ -157,12 +161,27 @@ __device__ void collide_pair(ManRef& e, int k, V3 pa, const M3& Ra, V3 ha, V3 pb
   }
   float thr = BREAKING_THRESHOLD_FACTOR * fminf(norm(ha), norm(hb));
   const Contact* c = scr.out;
+#ifdef PMG_COOP_TIMING
+  const long long t0 = clock64();
+#endif
   int nc = box_box(pa, Ra, ha, pb, Rb, hb, scr);
+#ifdef PMG_COOP_TIMING
+  const long long t1 = clock64();
+#endif
   for (int i = 0; i < nc; i++) {
     V3 wa = c[i].pB + c[i].dist * c[i].nB;
     manifold_add(e, k, thr, mulT(Ra, wa - pa), mulT(Rb, c[i].pB - pb), c[i].nB, c[i].dist);
   }
+#ifdef PMG_COOP_TIMING
+  const long long t2 = clock64();
+#endif
   manifold_refresh(e, k, thr, pa, Ra, pb, Rb);
+#ifdef PMG_COOP_TIMING
+  if (k == 0 && nc > 0) {
+    atomicAdd(&g_coop_cycles[8], (unsigned long long)(t1 - t0)); atomicAdd(&g_coop_cycles[9], (unsigned long long)(t2 - t1));
+    atomicAdd(&g_coop_cycles[10], (unsigned long long)(clock64() - t2)); atomicAdd(&g_coop_cycles[11], 1ull);
+  }
+#endif
 }
 
 template <int NBLK>

@@ -16,7 +16,7 @@ L = _lib.load()
 acts = torch.rand((50, B, 3), device="cuda") * 2 - 1
 out = torch.empty((B, env.row_width), device="cuda"); r = torch.empty((B,), device="cuda")
 d = torch.empty((B,), dtype=torch.uint8, device="cuda"); s = torch.empty((B,), dtype=torch.uint8, device="cuda")
-buf = (C.c_ulonglong * 8)()
+buf = (C.c_ulonglong * 16)()
 L.pmg_debug_coop_cycles(buf)
 for t in range(50):
     env.step_packed(acts[t], out, r, d, s)
@@ -26,3 +26,5 @@ for t in range(50):
         hot_n, cold_n = max(c[4], 1), max(c[6], 1)
         print("after step %2d: hot octet-substeps %8d: substep %7.0f cyc = narrowphase %6.0f + row set-up %6.0f + sweeps %6.0f + rest %6.0f | cold %9d: substep %6.0f cyc (broadphase %4.0f)"
               % (t, c[4], c[0] / hot_n, c[1] / hot_n, c[2] / hot_n, c[3] / hot_n, (c[0] - c[1] - c[2] - c[3]) / hot_n, c[6], c[5] / cold_n, c[7] / cold_n))
+        if c[11]:
+            print("               narrowphase of a touching pair: box_box %5.0f + manifold_add %5.0f + refresh %5.0f cycles" % (c[8] / c[11], c[9] / c[11], c[10] / c[11]))
