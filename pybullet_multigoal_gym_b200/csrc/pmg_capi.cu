@@ -462,6 +462,7 @@ struct pmg_handle {
   bool no_bulk = true;   // TMA staging of the state tile is opt-in (PMG_BULK_COPY=1): measured slower, see DESIGN.md
   bool default_carveout = false;  // PMG_DEFAULT_CARVEOUT=1 keeps the driver's shared-memory carve-out
   bool coop = true;  // Reach: lane-cooperative kernel (PMG_COOP=0 selects the thread-per-env kernel)
+  bool hinted = false;  // shared-memory carve-out hint of this handle's step kernel has been set on its device
 };
 
 namespace {
@@ -560,10 +561,9 @@ void launch_step(pmg_handle* h, const StepIO& io_in, cudaStream_t st) {
   if (TASK == 0 && h->coop && !h->jc) {
     constexpr int EPB = 32 / coop::GL;  // environments per block
     const size_t smem = COOP_TABLE_BYTES + EPB * sizeof(coop::EnvSmem);
-    static bool hinted_coop = false;
-    if (!hinted_coop) {
+    if (!h->hinted) {  // per handle = per device: function attributes are per device
       cudaFuncSetAttribute(step_kernel_coop_reach, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-      hinted_coop = true;
+      h->hinted = true;
     }
     step_kernel_coop_reach<<<(h->cfg.batch + EPB - 1) / EPB, 32, smem, st>>>(io);
     return;
@@ -575,10 +575,9 @@ void launch_step(pmg_handle* h, const StepIO& io_in, cudaStream_t st) {
   size_t smem = (io.bulk ? io.tile_offset + (size_t)Dims<TASK, NBLK>::STATE * 32 : stage_floats) * sizeof(float);
   // The per-thread scratch lives in L1-cached local memory: ask for the smallest shared-memory
   // carve-out instead of one sized for the register-limited 8 blocks per SM.
-  static bool hinted = false;
-  if (!hinted && !h->default_carveout) {
+  if (!h->hinted && !h->default_carveout) {  // per handle = per device: function attributes are per device
     cudaFuncSetAttribute(step_kernel<TASK, NBLK>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxL1);
-    hinted = true;
+    h->hinted = true;
   }
   step_kernel<TASK, NBLK><<<warps, 32, smem, st>>>(io);
 }

@@ -106,3 +106,37 @@ def test_her_style_relabelling_loop():
     assert bool((reward[ok] == 0).all()) and bool((reward[~ok] == -1).all())
     same = env._compute_reward(new_goal, new_goal)
     assert bool(same[1].all()) and bool((same[0] == 0).all())
+
+
+@pytest.mark.parametrize("task", ["reach", "push"])
+def test_ragged_batches_are_independent_of_the_launch_geometry(task):
+    """An environment's trajectory depends on its seed and actions only, not on how many neighbours share its
+    warp / octet: batches of 1, 3, 5 and 33 environments (partial octets, partial warps, partial blocks of the
+    cooperative and of the thread-per-env kernels) reproduce the first rows of a 64-environment batch bit-exactly."""
+    import contextlib
+    import io
+    import pybullet_multigoal_gym_b200 as pmg
+
+    def mk(b):
+        with contextlib.redirect_stdout(io.StringIO()):
+            return pmg.make_env(task=task, batch=b, check_actions=False)
+
+    big = mk(64)
+    gen = torch.Generator(device="cuda")
+    gen.manual_seed(9)
+    acts = torch.rand((12, 64, big.action_dim), device="cuda", generator=gen) * 2 - 1
+    acts[:8, :, 2] = -1.0   # down onto the table / block: contact paths included
+    ref_reset = big.reset()
+    ref = [big.step(acts[t]) for t in range(12)]
+    for b in (1, 3, 5, 33):
+        env = mk(b)
+        o = env.reset()
+        for k in o:
+            assert torch.equal(o[k], ref_reset[k][:b]), (b, k)
+        for t in range(12):
+            obs, r, done, info = env.step(acts[t, :b].contiguous())
+            for k in obs:
+                assert torch.equal(obs[k], ref[t][0][k][:b]), (b, t, k)
+            assert torch.equal(r, ref[t][1][:b]) and torch.equal(done, ref[t][2][:b])
+            assert torch.equal(info["goal_achieved"], ref[t][3]["goal_achieved"][:b])
+        assert env.overflow_count == 0
