@@ -257,6 +257,7 @@ typedef struct {
 struct PmgoEnv {
   int task, nb, binary, max_steps, grasping, has_obj, adim;
   int multi, grip, jc; /* multi-block obs layout (stack / rearrange); grip-informed goal; joint-space control */
+  int td, sub_goal_ind; /* task decomposition (block_stack): which sub-goal is the desired goal, -1 = the last one */
   double thr;
   int dims[4];
   /* state */
@@ -1120,7 +1121,18 @@ PmgoEnv* pmgo_create(int task, int num_block, int binary_reward, double thr, int
 
 PmgoEnv* pmgo_create_ex(int task, int num_block, int binary_reward, double thr, int max_steps,
                         int grip_informed_goal, int joint_control) {
+  return pmgo_create_ex2(task, num_block, binary_reward, thr, max_steps, grip_informed_goal, joint_control, 0);
+}
+
+void pmgo_set_sub_goal(PmgoEnv* e, int ind) { if (e->td) e->sub_goal_ind = ind; }
+static void write_obs(PmgoEnv* e, double* o);
+void pmgo_observe(PmgoEnv* e, double* obs_out) { write_obs(e, obs_out); }
+
+PmgoEnv* pmgo_create_ex2(int task, int num_block, int binary_reward, double thr, int max_steps,
+                         int grip_informed_goal, int joint_control, int task_decomposition) {
   PmgoEnv* e = (PmgoEnv*)calloc(1, sizeof *e);
+  e->td = task_decomposition && task == PMGO_BLOCK_STACK;
+  e->sub_goal_ind = -1;
   e->task = task; e->binary = binary_reward; e->thr = thr; e->max_steps = max_steps;
   e->has_obj = task != PMGO_REACH;
   e->multi = task == PMGO_BLOCK_STACK || task == PMGO_BLOCK_REARRANGE;
@@ -1239,6 +1251,25 @@ static void write_obs(PmgoEnv* e, double* o) {
     }
   }
   memcpy(dg, e->goal, sizeof(double) * e->dims[3]);
+  if (e->td) {
+    /* kuka_multi_step_envs.py:88-120 + kuka_multi_step_base_env.py:159-165,311-313: the desired goal is
+     * sub_goals[sub_goal_ind], rebuilt from the current block positions every observation.  Without the grip
+     * goal sub-goal k puts the blocks of stack levels <= k on their targets and leaves the others where they
+     * are; with it there is a pick (2k) and a place (2k+1) sub-goal per level and the gripper entries name the
+     * block to pick / the target to place it on. */
+    const int nsub = e->grip ? 2 * e->nb : e->nb;
+    int ind = e->sub_goal_ind < 0 ? e->sub_goal_ind + nsub : e->sub_goal_ind; /* python list indexing */
+    const int k = e->grip ? ind >> 1 : ind, place = e->grip ? (ind & 1) : 1;
+    for (int i = 0; i < e->nb; i++) {
+      const int b = e->last_order[i];
+      const int at_target = place ? i <= k : i < k;
+      copy3(dg + 3 * b, at_target ? e->last_targets[i] : e->bpos[b]);
+    }
+    if (e->grip) {
+      copy3(dg + 3 * e->nb, place ? e->last_targets[k] : e->bpos[e->last_order[k]]);
+      dg[3 * e->nb + 3] = 0.03;
+    }
+  }
 }
 
 static void set_arm(PmgoEnv* e, const double* pose) {
@@ -1274,6 +1305,7 @@ static void place_blocks(PmgoEnv* e, const double* xy) {
 void pmgo_reset(PmgoEnv* e, double* obs_out) {
   robot_reset(e);
   e->elapsed = 0;
+  e->sub_goal_ind = -1; /* kuka_multi_step_base_env.py:247-248 */
   double xy[2 * MAXBLK];
   if (e->multi) {
     /* kuka_multi_step_base_env.py:223-240 */
@@ -1352,6 +1384,7 @@ void pmgo_reset(PmgoEnv* e, double* obs_out) {
 void pmgo_reset_with(PmgoEnv* e, const double* spawn, double* obs_out) {
   robot_reset(e);
   e->elapsed = 0;
+  e->sub_goal_ind = -1;
   place_blocks(e, spawn);
   memcpy(e->goal, spawn + 2 * e->nb, sizeof(double) * e->dims[3]);
   if (e->task == PMGO_BLOCK_STACK) {

@@ -43,6 +43,13 @@ PmgoEnv* pmgo_create(int task, int num_block, int binary_reward, double distance
  * kuka.py:104-108,204-206; joint poses prepended to observation / policy_state). */
 PmgoEnv* pmgo_create_ex(int task, int num_block, int binary_reward, double distance_threshold,
                         int max_episode_steps, int grip_informed_goal, int joint_control);
+/* + task_decomposition (block_stack: the desired goal is one of the sub-goals of kuka_multi_step_envs.py:88-120,
+ * chosen with pmgo_set_sub_goal like env.set_sub_goal, kuka_multi_step_base_env.py:159-165; reset selects -1). */
+PmgoEnv* pmgo_create_ex2(int task, int num_block, int binary_reward, double distance_threshold,
+                         int max_episode_steps, int grip_informed_goal, int joint_control, int task_decomposition);
+void pmgo_set_sub_goal(PmgoEnv* e, int sub_goal_ind);
+/* the observation of the current state, without stepping (_get_obs) */
+void pmgo_observe(PmgoEnv* e, double* obs_out);
 void pmgo_destroy(PmgoEnv* e);
 
 /* dims[0..3] = observation, policy_state, achieved_goal, desired_goal lengths; returns action dim */

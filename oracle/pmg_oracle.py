@@ -38,6 +38,10 @@ def lib():
         L.pmgo_create.argtypes = [C.c_int, C.c_int, C.c_int, C.c_double, C.c_int]
         L.pmgo_create_ex.restype = C.c_void_p
         L.pmgo_create_ex.argtypes = [C.c_int, C.c_int, C.c_int, C.c_double, C.c_int, C.c_int, C.c_int]
+        L.pmgo_create_ex2.restype = C.c_void_p
+        L.pmgo_create_ex2.argtypes = [C.c_int, C.c_int, C.c_int, C.c_double, C.c_int, C.c_int, C.c_int, C.c_int]
+        L.pmgo_set_sub_goal.argtypes = [C.c_void_p, C.c_int]
+        L.pmgo_observe.argtypes = [C.c_void_p, dp]
         L.pmgo_destroy.argtypes = [C.c_void_p]
         L.pmgo_dims.argtypes = [C.c_void_p, ip]
         L.pmgo_dims.restype = C.c_int
@@ -97,11 +101,13 @@ class OracleEnv:
     """Single-environment CPU oracle with the reference's reset/step semantics."""
 
     def __init__(self, task="reach", num_block=4, binary_reward=True, distance_threshold=0.05,
-                 max_episode_steps=50, seed=0, grip_informed_goal=False, joint_control=False):
+                 max_episode_steps=50, seed=0, grip_informed_goal=False, joint_control=False,
+                 task_decomposition=False):
         self.L = lib()
         self.task = task
-        self.h = self.L.pmgo_create_ex(TASKS[task], num_block, int(binary_reward), distance_threshold,
-                                       max_episode_steps, int(grip_informed_goal), int(joint_control))
+        self.h = self.L.pmgo_create_ex2(TASKS[task], num_block, int(binary_reward), distance_threshold,
+                                        max_episode_steps, int(grip_informed_goal), int(joint_control),
+                                        int(task_decomposition))
         dims = (C.c_int * 4)()
         self.adim = self.L.pmgo_dims(self.h, dims)
         self.dims = list(dims)
@@ -123,6 +129,14 @@ class OracleEnv:
         o, p, a, d = self.dims
         return {"observation": flat[:o].copy(), "policy_state": flat[o:o + p].copy(),
                 "achieved_goal": flat[o + p:o + p + a].copy(), "desired_goal": flat[o + p + a:o + p + a + d].copy()}
+
+    def set_sub_goal(self, ind):
+        self.L.pmgo_set_sub_goal(self.h, int(ind))
+
+    def observe(self):
+        out = np.zeros(sum(self.dims))
+        self.L.pmgo_observe(self.h, _dp(out))
+        return self._split(out)
 
     def reset(self):
         out = np.zeros(sum(self.dims))

@@ -141,6 +141,8 @@ GOLDEN_VARIANTS = {
     "block_stack_grip": dict(task="block_stack", num_block=3, grip_informed_goal=True),
     "reach_jc": dict(task="reach", joint_control=True),
     "pick_and_place_jc": dict(task="pick_and_place", binary_reward=False, joint_control=True),
+    "block_stack_td": dict(task="block_stack", num_block=3, task_decomposition=True),
+    "block_stack_td_grip": dict(task="block_stack", num_block=3, task_decomposition=True, grip_informed_goal=True),
 }
 
 
@@ -158,6 +160,10 @@ def test_oracle_reproduces_reference_plumbing_goldens(oracle, name):
         flat = np.concatenate([o[key] for key in KEYS])
         np.testing.assert_allclose(flat, g["reset_obs"][ep], atol=1e-12, rtol=0)
         for t in range(L):
+            for (at, ind), want in zip(g["sub_goal_calls"], g["sub_goal_returns"]):
+                if at == k:  # env.set_sub_goal(ind) was called before this step (kuka_multi_step_base_env.py:159-165)
+                    e.set_sub_goal(int(ind))
+                    np.testing.assert_allclose(e.observe()["desired_goal"], want, atol=1e-9, rtol=0)
             o, r, done, info = e.step(g["actions"][k])
             flat = np.concatenate([o[key] for key in KEYS])
             np.testing.assert_allclose(flat, g["step_obs"][k], atol=1e-9, rtol=0, err_msg="%s step %d" % (name, k))

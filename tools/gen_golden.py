@@ -35,7 +35,13 @@ CONFIGS = [
     ("block_stack_grip", dict(task="block_stack", binary_reward=True, num_block=3, grip_informed_goal=True), 4, 100),
     ("reach_jc", dict(task="reach", binary_reward=True, joint_control=True), 7, 100),
     ("pick_and_place_jc", dict(task="pick_and_place", binary_reward=False, joint_control=True), 8, 100),
+    # task decomposition: env.set_sub_goal(k) is called by the script below (SUB_GOAL_SCHEDULE)
+    ("block_stack_td", dict(task="block_stack", binary_reward=True, num_block=3, task_decomposition=True), 4, 100),
+    ("block_stack_td_grip", dict(task="block_stack", binary_reward=True, num_block=3, task_decomposition=True, grip_informed_goal=True), 4, 100),
 ]
+# (step within the episode) -> sub-goal index handed to env.set_sub_goal before that step; indices beyond the
+# variant's number of sub-goals are taken modulo it by the script
+SUB_GOAL_SCHEDULE = {0: 0, 10: 1, 20: 2, 30: 5, 40: -1}
 # OracleEnv / make_env keyword arguments that reproduce each golden (shared with the tests)
 VARIANTS = {
     "reach": dict(task="reach"), "push": dict(task="push", binary_reward=False),
@@ -44,6 +50,8 @@ VARIANTS = {
     "block_stack_grip": dict(task="block_stack", num_block=3, grip_informed_goal=True),
     "reach_jc": dict(task="reach", joint_control=True),
     "pick_and_place_jc": dict(task="pick_and_place", binary_reward=False, joint_control=True),
+    "block_stack_td": dict(task="block_stack", num_block=3, task_decomposition=True),
+    "block_stack_td_grip": dict(task="block_stack", num_block=3, task_decomposition=True, grip_informed_goal=True),
 }
 
 
@@ -75,6 +83,7 @@ def main():
         rng = np.random.RandomState(2024)
         actions = scripted_actions(name, adim, T, rng)
         resets, steps, rewards, dones, oks = [], [], [], [], []
+        sub_goal_calls, sub_goal_returns = [], []
         for ep in range(2):
             resets.append(pack(env.reset()))
             for t in range(T // 2):
@@ -89,6 +98,13 @@ def main():
                     if adim == 4:
                         a[3] = -1.0 if t < 16 else 1.0
                     actions[ep * (T // 2) + t] = a
+                if "_td" in name and t in SUB_GOAL_SCHEDULE:
+                    nsub = 6 if name.endswith("grip") else 3
+                    ind = SUB_GOAL_SCHEDULE[t]
+                    ind = ind if ind < 0 else ind % nsub
+                    sub = env.set_sub_goal(ind)
+                    sub_goal_calls.append((ep * (T // 2) + t, ind))
+                    sub_goal_returns.append(np.asarray(sub, dtype=np.float64))
                 obs, r, done, info = env.step(a.astype(np.float64))
                 if t == T // 2 - 1:
                     assert done and info.get("TimeLimit.truncated") is True
@@ -100,7 +116,9 @@ def main():
                             step_obs=np.array(steps), reward=np.array(rewards), done=np.array(dones),
                             goal_achieved=np.array(oks), episode_len=T // 2,
                             dims=np.array([len(np.ravel(obs[k])) for k in KEYS]),
-                            max_episode_steps=env._max_episode_steps)
+                            max_episode_steps=env._max_episode_steps,
+                            sub_goal_calls=np.array(sub_goal_calls, dtype=np.int64).reshape(-1, 2),
+                            sub_goal_returns=np.array(sub_goal_returns))
         print("%-16s reset %s steps %s  successes %d  last reward %s" % (name, np.array(resets).shape, np.array(steps).shape, sum(oks), rewards[-1]))
 
 
