@@ -22,7 +22,7 @@
 extern "C" {
 #endif
 
-#define PMG_ABI_VERSION 2
+#define PMG_ABI_VERSION 3
 
 typedef enum {
   PMG_OK = 0,
@@ -49,6 +49,8 @@ typedef struct {
   int32_t joint_control;      /* 1: actions are 7 joint deltas of 0.05 rad (+ grip command) instead of a tip delta,
                                  joint poses are prepended to observation / policy_state (kuka.py:104-108,204-206;
                                  kuka_single_step_base_env.py:214-216) */
+  int32_t task_decomposition; /* block_stack only: the desired goal is one of the sub-goals of
+                                 kuka_multi_step_envs.py:88-120, selected with pmg_set_sub_goal */
 } pmg_config;
 
 typedef struct pmg_handle pmg_handle;
@@ -82,6 +84,13 @@ int pmg_reset(pmg_handle* h, const uint8_t* mask_host, const float* spawn_host, 
 int pmg_spawn_width(const pmg_handle* h);
 /* the spawn rows used by the most recent pmg_reset, [batch, spawn_width] (for parity tests) */
 int pmg_last_spawn(const pmg_handle* h, float* spawn_host);
+
+/* replaces: env.set_sub_goal(sub_goal_ind) (kuka_multi_step_base_env.py:159-181), task decomposition only.
+ * ind_host: [batch] sub-goal index per env, python list indexing (-1 = the last sub-goal = the final goal; block
+ * stack has num_block sub-goals, 2 * num_block with grip-informed goals: pick / place per level); NULL = -1 for
+ * all.  The desired goal of the following observations is rebuilt from the current block positions
+ * (kuka_multi_step_base_env.py:311-313); every reset selects -1 again (:247-248). */
+int pmg_set_sub_goal(pmg_handle* h, const int32_t* ind_host, void* stream);
 
 /* replaces: env.step(action) (base_env.py:130-138 -> kuka.py:167-225 -> 5 x stepSimulation;
  * kuka_single_step_base_env.py:193-244; kuka_multi_step_base_env.py:255-345; gym TimeLimit).
@@ -123,7 +132,8 @@ int pmg_her_relabel(const float* ag_dev, const float* dg_dev, int32_t n_episodes
 
 /* State access for teacher-forced parity tests (no reference counterpart).  Row layout, floats:
  * q[9] qd[9] ee_target[3] rest_pose[7] motor_target[9] motor_max_impulse[9], then per block
- * pos[3] quat_xyzw[4] linvel[3] angvel[3], then desired_goal[G], then elapsed steps.
+ * pos[3] quat_xyzw[4] linvel[3] angvel[3], then desired_goal[G] (the final goal), then the sub-goal index (task
+ * decomposition only), then elapsed steps.
  * pmg_set_state also clears the contact caches. */
 int pmg_state_width(const pmg_handle* h);
 int pmg_get_state(pmg_handle* h, float* state_host);

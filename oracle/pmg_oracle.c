@@ -1442,7 +1442,7 @@ void pmgo_step(PmgoEnv* e, const double* a, double* obs_out, double* reward, int
 /* ------------------------------------------------------------------------------------------ */
 /* state access + diagnostics                                                                 */
 /* ------------------------------------------------------------------------------------------ */
-int pmgo_state_size(const PmgoEnv* e) { return 9 + 9 + 3 + 7 + 9 + 9 + 13 * e->nb + e->dims[3] + 1; }
+int pmgo_state_size(const PmgoEnv* e) { return 9 + 9 + 3 + 7 + 9 + 9 + 13 * e->nb + e->dims[3] + (e->td ? 1 : 0) + 1; }
 void pmgo_get_state(const PmgoEnv* e, double* o) {
   memcpy(o, e->q, 72); o += 9; memcpy(o, e->qd, 72); o += 9;
   memcpy(o, e->ee_target, 24); o += 3; memcpy(o, e->rest_pose, 56); o += 7;
@@ -1451,6 +1451,7 @@ void pmgo_get_state(const PmgoEnv* e, double* o) {
     copy3(o, e->bpos[b]); memcpy(o + 3, e->bquat[b], 32); copy3(o + 7, e->bv[b]); copy3(o + 10, e->bw[b]); o += 13;
   }
   memcpy(o, e->goal, sizeof(double) * e->dims[3]); o += e->dims[3];
+  if (e->td) *o++ = e->sub_goal_ind;
   *o = e->elapsed;
 }
 void pmgo_set_state(PmgoEnv* e, const double* o) {
@@ -1461,6 +1462,7 @@ void pmgo_set_state(PmgoEnv* e, const double* o) {
     copy3(e->bpos[b], o); memcpy(e->bquat[b], o + 3, 32); copy3(e->bv[b], o + 7); copy3(e->bw[b], o + 10); o += 13;
   }
   memcpy(e->goal, o, sizeof(double) * e->dims[3]); o += e->dims[3];
+  if (e->td) e->sub_goal_ind = (int)*o++;
   e->elapsed = (int)*o;
   if (e->task == PMGO_BLOCK_STACK)
     for (int b = 0; b < e->nb; b++) {

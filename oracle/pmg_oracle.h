@@ -80,8 +80,8 @@ void pmgo_compute_reward(const double* ag, const double* dg, int64_t n, int g, d
 
 /* ---- state access for teacher-forced parity tests -------------------------------------- */
 /* layout: q[9] qd[9] ee_target[3] rest_pose[7] motor_target[9] motor_maximp[9]
- *         then per block pos[3] quat[4](xyzw) linvel[3] angvel[3]; then desired_goal[G];
- *         then elapsed (as double). */
+ *         then per block pos[3] quat[4](xyzw) linvel[3] angvel[3]; then desired_goal[G] (the final goal);
+ *         then sub_goal_ind (task decomposition only); then elapsed (as double). */
 int pmgo_state_size(const PmgoEnv* e);
 void pmgo_get_state(const PmgoEnv* e, double* out);
 void pmgo_set_state(PmgoEnv* e, const double* in); /* also clears the contact caches */

@@ -4,7 +4,7 @@
 and adds `batch` (number of environments stepped in lockstep; None = one unbatched env with the
 reference's numpy shapes), `device` and `seed`.  Tasks on the accelerated path: reach, push,
 pick_and_place, block_stack, block_rearrange with the parallel-jaw gripper and state observations,
-including the `joint_control` and (block_stack) `grip_informed_goal` variants.
+including the `joint_control` and (block_stack) `grip_informed_goal` / `task_decomposition` variants.
 """
 from .envs import (ActionError, KukaBlockRearrangeEnv, KukaBlockStackEnv, KukaBulletMGEnv,  # noqa: F401
                    KukaPickAndPlaceEnv, KukaPushEnv, KukaReachEnv)
@@ -43,8 +43,12 @@ def make_env(task='reach', gripper='parallel_jaw', num_block=5, render=False, bi
         if task == 'block_rearrange':  # kuka_multi_step_envs.py:158
             raise AssertionError("Block rearranging task does not support gripper informed goal representation.")
         grip_informed_goal = False  # the single-step tasks do not take the kwarg (__init__.py:88-106)
+    if task_decomposition and task != 'block_stack':
+        if task == 'block_rearrange':  # kuka_multi_step_envs.py:159
+            raise AssertionError("Block rearranging task does not support task decomposition.")
+        if task in _TAGS:
+            task_decomposition = False  # the single-step tasks do not take the kwarg (__init__.py:88-106)
     for name, val in (('render', render),
-                      ('task_decomposition', task_decomposition),
                       ('image_observation', image_observation), ('depth_image', depth_image),
                       ('goal_image', goal_image), ('point_cloud', point_cloud), ('state_noise', state_noise),
                       ('use_curriculum', use_curriculum)):
@@ -64,4 +68,5 @@ def make_env(task='reach', gripper='parallel_jaw', num_block=5, render=False, bi
     return _ENTRY[task](batch=batch, device=device, binary_reward=binary_reward,
                         distance_threshold=distance_threshold, max_episode_steps=max_episode_steps,
                         num_block=num_block, seed=seed, check_actions=check_actions,
-                        grip_informed_goal=grip_informed_goal, joint_control=joint_control)
+                        grip_informed_goal=grip_informed_goal, joint_control=joint_control,
+                        task_decomposition=task_decomposition)

@@ -10,12 +10,12 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 SO_PATH = os.environ.get("PMG_LIBRARY") or os.path.join(_HERE, "libpmg.so")  # PMG_LIBRARY: instrumented development builds
 
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 # every symbol include/pmg.h declares
 SYMBOLS = [
     "pmg_abi_version", "pmg_last_error", "pmg_create", "pmg_destroy", "pmg_dims", "pmg_seed",
-    "pmg_reset", "pmg_spawn_width", "pmg_last_spawn", "pmg_step", "pmg_step_host",
+    "pmg_reset", "pmg_spawn_width", "pmg_last_spawn", "pmg_set_sub_goal", "pmg_step", "pmg_step_host",
     "pmg_compute_reward", "pmg_her_sample", "pmg_her_relabel", "pmg_state_width", "pmg_get_state", "pmg_set_state",
     "pmg_launch_count", "pmg_overflow_count",
 ]
@@ -25,7 +25,7 @@ class PmgConfig(C.Structure):
     _fields_ = [("task", C.c_int32), ("num_block", C.c_int32), ("batch", C.c_int32),
                 ("binary_reward", C.c_int32), ("distance_threshold", C.c_float),
                 ("max_episode_steps", C.c_int32), ("device", C.c_int32),
-                ("grip_informed_goal", C.c_int32), ("joint_control", C.c_int32)]
+                ("grip_informed_goal", C.c_int32), ("joint_control", C.c_int32), ("task_decomposition", C.c_int32)]
 
 
 _lib = None
@@ -53,6 +53,7 @@ def load():
     L.pmg_reset.argtypes = [vp, u8p, fp, fp, vp]
     L.pmg_spawn_width.argtypes = [vp]
     L.pmg_last_spawn.argtypes = [vp, fp]
+    L.pmg_set_sub_goal.argtypes = [vp, vp, vp]
     L.pmg_step.argtypes = [vp, fp, fp, fp, u8p, u8p, vp]
     L.pmg_step_host.argtypes = [vp, fp, fp, fp, u8p, u8p, vp]
     L.pmg_compute_reward.argtypes = [fp, fp, C.c_int64, C.c_int32, C.c_float, C.c_int32, fp, u8p, vp]

@@ -178,6 +178,27 @@ __device__ float write_obs(const Env<NBLK>& e, const StepIO& io, int i) {
       ag[3 * n] = bx.x; ag[3 * n + 1] = bx.y; ag[3 * n + 2] = bx.z;
     }
     if (io.grip_goal) { ag[3 * NBLK] = tip.x; ag[3 * NBLK + 1] = tip.y; ag[3 * NBLK + 2] = tip.z; ag[3 * NBLK + 3] = closeness; }
+    if (io.td) {
+      // Task decomposition (kuka_multi_step_envs.py:88-120, kuka_multi_step_base_env.py:159-165,311-313): the
+      // desired goal is sub_goals[ind], rebuilt from the current block positions.  The stored goal is the final
+      // one; a block's stack level is its target height.  Without the grip goal sub-goal k has levels <= k on
+      // their targets and the other blocks where they are; with it there is a pick (2k) / place (2k+1) pair.
+      const int nsub = io.grip_goal ? 2 * NBLK : NBLK;
+      int ind = (int)goal[(size_t)G * B];
+      if (ind < 0) ind += nsub;
+      const int k = io.grip_goal ? ind >> 1 : ind;
+      const bool place = io.grip_goal ? (ind & 1) != 0 : true;
+#pragma unroll
+      for (int n = 0; n < NBLK; n++) {
+        const int level = (int)floorf((dg[3 * n + 2] - BLOCK_SPAWN_Z) * (1.0f / 0.03f) + 0.5f);
+        const bool at_target = place ? level <= k : level < k;
+        if (io.grip_goal && level == k) {
+          dg[3 * NBLK] = place ? dg[3 * n] : e.bpos[n].x; dg[3 * NBLK + 1] = place ? dg[3 * n + 1] : e.bpos[n].y;
+          dg[3 * NBLK + 2] = place ? dg[3 * n + 2] : e.bpos[n].z;
+        }
+        if (!at_target) { dg[3 * n] = e.bpos[n].x; dg[3 * n + 1] = e.bpos[n].y; dg[3 * n + 2] = e.bpos[n].z; }
+      }
+    }
     for (int k = 0; k < O + P; k++) row[k] = clip5(row[k]);  // np.clip over the concatenated vectors, joint poses included
   }
   float d2 = 0.0f;
@@ -321,6 +342,7 @@ __global__ void __launch_bounds__(32) reset_kernel(ResetIO r) {
     for (int k = 0; k < 7; k++) s[(ST_REST + k) * B] = qik[k];
     s[(ST_EE + 0) * B] = tip.x; s[(ST_EE + 1) * B] = tip.y; s[(ST_EE + 2) * B] = tip.z;
     for (int k = 0; k < io.goal_dim; k++) s[(size_t)(ST_BLK + 13 * NBLK + k) * B] = sp[2 * NBLK + k];
+    if (io.td) s[(size_t)(ST_BLK + 13 * NBLK + io.goal_dim) * B] = -1.0f;  // kuka_multi_step_base_env.py:247-248
     s[(size_t)(io.state_words - 1) * B] = 0.0f;
     store_env<TASK, NBLK>(e, io, i);
   }
@@ -450,7 +472,7 @@ int fail(int code, const char* fmt, const char* detail = "") {
 struct pmg_handle {
   pmg_config cfg;
   int nblk, O, P, G, W, A, state_words, man_words, spawn_w;
-  bool multi = false, grasp = false, grip = false, jc = false;  // task variants, see pmg_config
+  bool multi = false, grasp = false, grip = false, jc = false, td = false;  // task variants, see pmg_config
   float* d_state = nullptr; float* d_man = nullptr; float* d_spawn = nullptr; uint8_t* d_mask = nullptr; int* d_overflow = nullptr;
   float* d_action = nullptr; float* d_obs = nullptr; float* d_reward = nullptr; uint8_t* d_done = nullptr; uint8_t* d_success = nullptr;
   float* h_spawn = nullptr;  // pinned
@@ -549,7 +571,7 @@ StepIO make_io(pmg_handle* h, const float* action, float* obs, float* reward, ui
   io.overflow = h->d_overflow;
   io.epw = h->epw;
   io.bulk = 0; io.tile_offset = 0;
-  io.grasp = h->grasp; io.jc = h->jc; io.grip_goal = h->grip;
+  io.grasp = h->grasp; io.jc = h->jc; io.grip_goal = h->grip; io.td = h->td;
   io.adim = h->A; io.goal_dim = h->G; io.row_width = h->W;
   return io;
 }
@@ -570,7 +592,7 @@ void launch_step(pmg_handle* h, const StepIO& io_in, cudaStream_t st) {
   }
   int warps = (h->cfg.batch + h->epw - 1) / h->epw;
   size_t stage_floats = (size_t)h->epw * h->W;
-  io.bulk = (h->epw == 32 && h->cfg.batch % 32 == 0 && !h->no_bulk && !h->grip) ? 1 : 0;
+  io.bulk = (h->epw == 32 && h->cfg.batch % 32 == 0 && !h->no_bulk && !h->grip && !h->td) ? 1 : 0;
   io.tile_offset = (int)((stage_floats + 31) / 32 * 32);
   size_t smem = (io.bulk ? io.tile_offset + (size_t)Dims<TASK, NBLK>::STATE * 32 : stage_floats) * sizeof(float);
   // The per-thread scratch lives in L1-cached local memory: ask for the smallest shared-memory
@@ -619,6 +641,7 @@ int pmg_create(const pmg_config* cfg, pmg_handle** out) {
   const bool multi = cfg->task == PMG_BLOCK_STACK || cfg->task == PMG_BLOCK_REARRANGE;
   if (multi && (cfg->num_block < 1 || cfg->num_block > 5)) return fail(PMG_ERR_INVALID, "pmg_create: only support up to 5 blocks%s");
   if (cfg->grip_informed_goal && cfg->task != PMG_BLOCK_STACK) return fail(PMG_ERR_INVALID, "pmg_create: grip_informed_goal is a block_stack option%s");
+  if (cfg->task_decomposition && cfg->task != PMG_BLOCK_STACK) return fail(PMG_ERR_INVALID, "pmg_create: task_decomposition is a block_stack option%s");
   if (cfg->batch < 1) return fail(PMG_ERR_INVALID, "pmg_create: batch must be >= 1%s");
   if (cfg->max_episode_steps < 1 || cfg->max_episode_steps >= (1 << 24)) return fail(PMG_ERR_INVALID, "pmg_create: max_episode_steps out of range%s");
   int ndev = 0;
@@ -633,13 +656,14 @@ int pmg_create(const pmg_config* cfg, pmg_handle** out) {
   h->grasp = t == PMG_PICK_AND_PLACE || t == PMG_BLOCK_STACK;  // kuka_single_step_envs.py:16, kuka_multi_step_envs.py:30,170
   h->grip = cfg->grip_informed_goal != 0;
   h->jc = cfg->joint_control != 0;
+  h->td = cfg->task_decomposition != 0;
   h->nblk = t == PMG_REACH ? 0 : (multi ? cfg->num_block : 1);
   h->O = (t == PMG_REACH ? 3 : (multi ? 8 + 16 * h->nblk : 20)) + (h->jc ? 7 : 0);
   h->P = (t == PMG_REACH ? 3 : (multi ? 4 + 3 * h->nblk : 7)) + (h->jc ? 7 : 0);
   h->G = (multi ? 3 * h->nblk : 3) + (h->grip ? 4 : 0);
   h->W = h->O + h->P + 2 * h->G;
   h->A = h->jc ? (h->grasp ? 8 : 7) : (h->grasp ? 4 : 3);  // kuka.py:104-118
-  h->state_words = ST_BLK + 13 * h->nblk + h->G + 1;
+  h->state_words = ST_BLK + 13 * h->nblk + h->G + (h->td ? 1 : 0) + 1;
   h->man_words = num_pairs(h->nblk) * MAN_WORDS;
   h->spawn_w = 2 * h->nblk + h->G;
   // kuka.py:35-51 with obj_range = target_range = 0.15 (kuka_single_step_envs.py, kuka_multi_step_envs.py:29)
@@ -749,6 +773,25 @@ int pmg_reset(pmg_handle* h, const uint8_t* mask_host, const float* spawn_host, 
   CUDA_TRY(cudaGetLastError());
   if (mask_host) CUDA_TRY(cudaStreamSynchronize(st));  // mask_host may be pageable caller memory
   h->was_reset = true;
+  return PMG_OK;
+}
+
+int pmg_set_sub_goal(pmg_handle* h, const int32_t* ind_host, void* stream) {
+  if (!h) return fail(PMG_ERR_INVALID, "pmg_set_sub_goal: null handle%s");
+  if (!h->td) return fail(PMG_ERR_STATE, "pmg_set_sub_goal: the handle was created without task_decomposition%s");
+  cudaStream_t st = (cudaStream_t)stream;
+  CUDA_TRY(cudaSetDevice(h->cfg.device));
+  const size_t B = h->cfg.batch;
+  const int nsub = h->grip ? 2 * h->nblk : h->nblk;
+  std::vector<float> v(B, -1.0f);
+  if (ind_host)
+    for (size_t i = 0; i < B; i++) {
+      if (ind_host[i] < -nsub || ind_host[i] >= nsub) return fail(PMG_ERR_INVALID, "pmg_set_sub_goal: list index out of range%s");
+      v[i] = (float)ind_host[i];
+    }
+  const size_t word = (size_t)ST_BLK + 13 * h->nblk + h->G;  // [word][env]: one contiguous row of the state
+  CUDA_TRY(cudaMemcpyAsync(h->d_state + word * B, v.data(), sizeof(float) * B, cudaMemcpyHostToDevice, st));
+  CUDA_TRY(cudaStreamSynchronize(st));  // v is a temporary
   return PMG_OK;
 }
 

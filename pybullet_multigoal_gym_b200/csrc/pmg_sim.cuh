@@ -588,6 +588,7 @@ struct StepIO {
   int grasp;        // the last action column drives the jaws and finger_closeness / finger_vel are observed
   int jc;           // joint-space control: 7 joint deltas (+ grip), joint poses prepended to observation / policy_state
   int grip_goal;    // grip-informed goal: achieved / desired goal gain gripper xyz + finger closeness
+  int td;           // task decomposition: desired goal = the sub-goal named by the state word behind the goal
   int adim, goal_dim, row_width;  // action columns, goal length, packed row width (all after the variants above)
 };
 

@@ -23,6 +23,40 @@ from . import _lib, seeding, spaces
 TASK_IDS = {"reach": 0, "push": 1, "pick_and_place": 2, "block_stack": 3, "block_rearrange": 4}
 
 
+class StepDemonstrator:
+    """Cycles through the sub-goal indices of a demonstration, same interface as the reference's
+    utils/demonstrator.py:1-35 (get_next_goal / manual_reset / reset_with_the_last_sub_goal_index)."""
+
+    def __init__(self, demonstrations, stick_with_final_goal=True):
+        self.demonstrations, self.demon_num = demonstrations, len(demonstrations)
+        self.demon_ind, self.current_goal, self.current_final_goal = 0, -1, 0
+        self.stick_with_final_goal, self.final = stick_with_final_goal, False
+
+    def get_next_goal(self):
+        demo = self.demonstrations[self.demon_ind]
+        if self.stick_with_final_goal and self.current_goal != -1:
+            self.final = False
+            if demo[self.current_goal] == demo[-1]:
+                self.final = True
+                return demo[self.current_goal]
+        self.current_goal = (self.current_goal + 1) % len(demo)
+        return demo[self.current_goal]
+
+    def manual_reset(self, demon_ind=None):
+        self.demon_ind = 0 if demon_ind is None else demon_ind
+        self.current_goal, self.final = -1, False
+        self.current_final_goal = self.demonstrations[self.demon_ind][-1]
+
+    def reset_with_the_last_sub_goal_index(self, ind):
+        self.current_goal = -1
+        for i, demo in enumerate(self.demonstrations):
+            if demo[-1] == ind:
+                self.demon_ind = i
+                break
+        self.current_final_goal = self.demonstrations[self.demon_ind][-1]
+        self.final = False
+
+
 class ActionError(AssertionError, ValueError):
     """Raised where the reference hits `assert self.action_space.contains(a)` (kuka.py:168)."""
 
@@ -38,7 +72,7 @@ class KukaBulletMGEnv:
 
     def __init__(self, task, batch=None, device=0, binary_reward=True, distance_threshold=0.05,
                  max_episode_steps=50, num_block=4, seed=0, check_actions=True,
-                 grip_informed_goal=False, joint_control=False):
+                 grip_informed_goal=False, joint_control=False, task_decomposition=False):
         if task not in TASK_IDS:
             raise ValueError("invalid task name: %s, only support: %s" % (task, sorted(TASK_IDS)))
         self._L = _lib.load()
@@ -60,10 +94,15 @@ class KukaBulletMGEnv:
         if self.grip_informed_goal and task != "block_stack":
             # kuka_multi_step_envs.py:158 asserts it off for rearrange; the single-step envs have no such option
             raise AssertionError("%s does not support gripper informed goal representation." % task)
+        self.task_decomposition = bool(task_decomposition) and task == "block_stack"
+        if self.task_decomposition:
+            # kuka_multi_step_envs.py:13-17, kuka_multi_step_base_env.py:116-119: demonstrations [0], [0, 1], ...
+            self.num_steps = self.num_block * (2 if self.grip_informed_goal else 1)
+            self.step_demonstrator = StepDemonstrator([list(range(i + 1)) for i in range(self.num_steps)])
         self.check_actions = check_actions
         cfg = _lib.PmgConfig(TASK_IDS[task], int(num_block), self.batch, int(self.binary_reward),
                              self.distance_threshold, self._max_episode_steps, self.device.index,
-                             int(self.grip_informed_goal), int(self.joint_control))
+                             int(self.grip_informed_goal), int(self.joint_control), int(self.task_decomposition))
         h = C.c_void_p()
         _lib.check(self._L.pmg_create(C.byref(cfg), C.byref(h)))
         self._h = h
@@ -151,6 +190,22 @@ class KukaBulletMGEnv:
             if self._squeeze:
                 self.desired_goal = host["desired_goal"]
             return host
+
+    def set_sub_goal(self, sub_goal_ind):
+        """kuka_multi_step_base_env.py:159-181.  `sub_goal_ind`: one index for every environment or a [batch]
+        array, python list indexing (-1 = the final goal).  Returns the new desired goal like the reference
+        (None, with the reference's warning, when the env was made without task_decomposition)."""
+        if not self.task_decomposition:
+            import warnings
+            warnings.warn("The set_sub_goal() method should only be called when using task decomposition,\n"
+                          "It does nothing and returns None when self.task_decomposition is False.")
+            return None
+        ind = np.ascontiguousarray(np.broadcast_to(np.asarray(sub_goal_ind.cpu() if torch.is_tensor(sub_goal_ind) else sub_goal_ind,
+                                                              dtype=np.int32), (self.batch,)))
+        with torch.cuda.device(self.device):
+            _lib.check(self._L.pmg_set_sub_goal(self._h, ind.ctypes.data_as(C.c_void_p), self._stream()))
+        obs = self.reset(mask=np.zeros((self.batch,), dtype=np.uint8))  # no env is reset: the observation rows are rebuilt
+        return obs["desired_goal"]
 
     def _check_action(self, a_np):
         if a_np.shape != (self.batch, self.action_dim) or not (np.all(a_np >= -1.0) and np.all(a_np <= 1.0)):

@@ -18,6 +18,8 @@ VARIANTS = {
     "block_stack_grip": dict(task="block_stack", num_block=3, grip_informed_goal=True),
     "reach_jc": dict(task="reach", joint_control=True),
     "pick_and_place_jc": dict(task="pick_and_place", binary_reward=False, joint_control=True),
+    "block_stack_td": dict(task="block_stack", num_block=3, task_decomposition=True),
+    "block_stack_td_grip": dict(task="block_stack", num_block=3, task_decomposition=True, grip_informed_goal=True),
 }
 
 
@@ -148,3 +150,51 @@ def test_variant_teacher_forced_steps_match_oracle(oracle, name):
           % (name, errs.size, 100 * float(np.mean(errs < TOL)), errs.max(), loose))
     assert float(np.mean(errs < TOL)) >= 0.97 and errs.size > loose
     assert env.overflow_count == 0
+
+
+@pytest.mark.parametrize("name", ["block_stack_td", "block_stack_td_grip"])
+def test_task_decomposition_sub_goals_match_oracle(oracle, name):
+    """env.set_sub_goal (kuka_multi_step_base_env.py:159-181): per-env sub-goal indices, desired goal rebuilt from
+    the current block positions each observation.  Teacher-forced against the oracle (whose sub-goal plumbing is
+    pinned by the reference goldens): desired goals within 1e-4 on every step (a sub-goal copies block positions),
+    rewards / success flags identical away from the threshold; reset selects -1 again."""
+    kw = VARIANTS[name]
+    B, nsub = 6, (6 if kw.get("grip_informed_goal") else 3)
+    env = _mk(B, **kw)
+    env.reset()
+    assert env.num_steps == nsub and env.step_demonstrator.get_next_goal() == 0
+    spawn = env.last_spawn()
+    refs = []
+    for i in range(B):
+        o = oracle.OracleEnv(seed=i, **kw)
+        o.reset_with(spawn[i].astype(np.float64))
+        refs.append(o)
+    rng = np.random.RandomState(5)
+    with pytest.raises(ValueError):
+        env.set_sub_goal(nsub)            # list index out of range
+    for t in range(16):
+        st = np.stack([o.get_state() for o in refs]).astype(np.float32)
+        inds = rng.randint(-nsub, nsub, size=B)
+        a = rng.uniform(-1, 1, size=(B, 4)).astype(np.float32)
+        for i in range(B):
+            tip = refs[i].link_state(0)[:3]
+            a[i, :3] = np.clip((st[i, 46:49] + np.array([0.0, 0.0, 0.0 if t > 8 else 0.06]) - tip) / 0.01, -1, 1)
+            a[i, 3] = -1.0
+            refs[i].set_state(st[i].astype(np.float64))
+            refs[i].set_sub_goal(int(inds[i]))
+        env.set_state(st)
+        dg_now = _np(env.set_sub_goal(inds))
+        for i in range(B):
+            np.testing.assert_allclose(dg_now[i], refs[i].observe()["desired_goal"], atol=2e-6)
+        obs, r, done, info = env.step(torch.from_numpy(a).cuda())
+        for i in range(B):
+            ro, rr, rd, ri = refs[i].step(a[i].astype(np.float64))
+            np.testing.assert_allclose(_np(obs["desired_goal"][i]), ro["desired_goal"], atol=TOL)
+            d = np.linalg.norm(ro["achieved_goal"] - ro["desired_goal"])
+            if abs(d - 0.05) > 5 * TOL:
+                assert bool(info["goal_achieved"][i]) == ri["goal_achieved"] and float(r[i]) == rr
+    o1 = env.reset()
+    st = env.get_state()
+    assert np.all(st[:, -2] == -1.0)      # sub-goal index word sits in front of the elapsed-steps word
+    final = o1["desired_goal"]
+    assert torch.equal(env.set_sub_goal(-1), final) and torch.equal(env.set_sub_goal(nsub - 1), final)
