@@ -258,6 +258,8 @@ struct PmgoEnv {
   int task, nb, binary, max_steps, grasping, has_obj, adim;
   int multi, grip, jc; /* multi-block obs layout (stack / rearrange); grip-informed goal; joint-space control */
   int td, sub_goal_ind; /* task decomposition (block_stack): which sub-goal is the desired goal, -1 = the last one */
+  /* curriculum (block_stack, kuka_multi_step_base_env.py:122-140,350-379): goal difficulty drawn per reset */
+  int cur, cur_update, cur_level; double cur_prob[MAXBLK], cur_count[MAXBLK], cur_goals_per;
   double thr;
   int dims[4];
   /* state */
@@ -1130,9 +1132,44 @@ void pmgo_observe(PmgoEnv* e, double* obs_out) { write_obs(e, obs_out); }
 
 PmgoEnv* pmgo_create_ex2(int task, int num_block, int binary_reward, double thr, int max_steps,
                          int grip_informed_goal, int joint_control, int task_decomposition) {
+  return pmgo_create_ex3(task, num_block, binary_reward, thr, max_steps, grip_informed_goal, joint_control, task_decomposition, 0, 0);
+}
+
+void pmgo_set_curriculum_update(PmgoEnv* e, int on) { if (e->cur) e->cur_update = on != 0; }
+int pmgo_get_curriculum(const PmgoEnv* e, double* prob_out) {
+  for (int k = 0; k < e->nb; k++) prob_out[k] = e->cur_prob[k];
+  return e->cur_level;
+}
+
+/* kuka_multi_step_base_env.py:350-379, statement by statement (numpy negative indexing included) */
+static void update_curriculum_prob(PmgoEnv* e) {
+  const int n = e->nb;
+  int fin[MAXBLK], half[MAXBLK];
+  for (int i = 0; i < n; i++) {
+    fin[i] = e->cur_count[i] >= e->cur_goals_per;
+    half[i] = e->cur_count[i] >= e->cur_goals_per / 2;
+    if (fin[i]) e->cur_prob[i] = 0.0;
+  }
+  if (half[0] && !fin[0]) { e->cur_prob[0] = 0.5; e->cur_prob[1] = 0.5; }
+  for (int i = 1; i < n - 1; i++)
+    if (fin[i - 1] && !fin[i]) {
+      if (half[i]) { e->cur_prob[i] = 0.5; e->cur_prob[i + 1] = 0.5; }
+      else e->cur_prob[i] = 1.0;
+    }
+  if (fin[n - 2]) e->cur_prob[n - 1] = 1.0;
+}
+
+PmgoEnv* pmgo_create_ex3(int task, int num_block, int binary_reward, double thr, int max_steps,
+                         int grip_informed_goal, int joint_control, int task_decomposition,
+                         int use_curriculum, long num_goals_to_generate) {
   PmgoEnv* e = (PmgoEnv*)calloc(1, sizeof *e);
   e->td = task_decomposition && task == PMGO_BLOCK_STACK;
   e->sub_goal_ind = -1;
+  e->cur = use_curriculum && task == PMGO_BLOCK_STACK && !e->td; /* mutually exclusive (:113,121) */
+  if (e->cur) {
+    e->cur_prob[0] = 1.0;
+    e->cur_goals_per = (double)(num_goals_to_generate / num_block); /* floor division (:138) */
+  }
   e->task = task; e->binary = binary_reward; e->thr = thr; e->max_steps = max_steps;
   e->has_obj = task != PMGO_REACH;
   e->multi = task == PMGO_BLOCK_STACK || task == PMGO_BLOCK_REARRANGE;
@@ -1251,7 +1288,9 @@ static void write_obs(PmgoEnv* e, double* o) {
     }
   }
   memcpy(dg, e->goal, sizeof(double) * e->dims[3]);
-  if (e->td) {
+  if (e->td || e->cur) {
+    /* The curriculum goal of level L (kuka_multi_step_envs.py:124-148) is the "place" sub-goal of level L;
+     * e->sub_goal_ind holds the equivalent sub-goal index in that mode. */
     /* kuka_multi_step_envs.py:88-120 + kuka_multi_step_base_env.py:159-165,311-313: the desired goal is
      * sub_goals[sub_goal_ind], rebuilt from the current block positions every observation.  Without the grip
      * goal sub-goal k puts the blocks of stack levels <= k on their targets and leaves the others where they
@@ -1305,7 +1344,7 @@ static void place_blocks(PmgoEnv* e, const double* xy) {
 void pmgo_reset(PmgoEnv* e, double* obs_out) {
   robot_reset(e);
   e->elapsed = 0;
-  e->sub_goal_ind = -1; /* kuka_multi_step_base_env.py:247-248 */
+  if (!e->cur) e->sub_goal_ind = -1; /* kuka_multi_step_base_env.py:247-248 */
   double xy[2 * MAXBLK];
   if (e->multi) {
     /* kuka_multi_step_base_env.py:223-240 */
@@ -1355,6 +1394,19 @@ void pmgo_reset(PmgoEnv* e, double* obs_out) {
       copy3(e->goal + 3 * e->last_order[k], e->last_targets[k]);
     }
     if (e->grip) { copy3(e->goal + 3 * e->nb, e->last_targets[e->nb - 1]); e->goal[3 * e->nb + 3] = 0.03; } /* :75-77 */
+    if (e->cur) {
+      /* kuka_multi_step_envs.py:127-134: level = np_random.choice(num_curriculum, p=curriculum_prob), i.e.
+       * cdf.searchsorted(random_sample(), side='right') in numpy's legacy RandomState */
+      double cdf[MAXBLK], acc = 0;
+      for (int k = 0; k < e->nb; k++) { acc += e->cur_prob[k]; cdf[k] = acc; }
+      for (int k = 0; k < e->nb; k++) cdf[k] /= acc;
+      const double u = mt_double(&e->rng);
+      int level = 0;
+      while (level < e->nb && cdf[level] <= u) level++;
+      e->cur_level = level;
+      e->sub_goal_ind = e->grip ? 2 * level + 1 : level;
+      if (e->cur_update) { e->cur_count[level] += 1; update_curriculum_prob(e); }
+    }
   } else {
     /* kuka_single_step_base_env.py:104-148 */
     double center[3];
@@ -1384,7 +1436,9 @@ void pmgo_reset(PmgoEnv* e, double* obs_out) {
 void pmgo_reset_with(PmgoEnv* e, const double* spawn, double* obs_out) {
   robot_reset(e);
   e->elapsed = 0;
-  e->sub_goal_ind = -1;
+  /* spawn rows of a curriculum env carry the sub-goal index behind the goal */
+  e->sub_goal_ind = e->cur ? (int)spawn[2 * e->nb + e->dims[3]] : -1;
+  if (e->cur) e->cur_level = e->grip ? e->sub_goal_ind >> 1 : e->sub_goal_ind;
   place_blocks(e, spawn);
   memcpy(e->goal, spawn + 2 * e->nb, sizeof(double) * e->dims[3]);
   if (e->task == PMGO_BLOCK_STACK) {
@@ -1442,7 +1496,7 @@ void pmgo_step(PmgoEnv* e, const double* a, double* obs_out, double* reward, int
 /* ------------------------------------------------------------------------------------------ */
 /* state access + diagnostics                                                                 */
 /* ------------------------------------------------------------------------------------------ */
-int pmgo_state_size(const PmgoEnv* e) { return 9 + 9 + 3 + 7 + 9 + 9 + 13 * e->nb + e->dims[3] + (e->td ? 1 : 0) + 1; }
+int pmgo_state_size(const PmgoEnv* e) { return 9 + 9 + 3 + 7 + 9 + 9 + 13 * e->nb + e->dims[3] + ((e->td || e->cur) ? 1 : 0) + 1; }
 void pmgo_get_state(const PmgoEnv* e, double* o) {
   memcpy(o, e->q, 72); o += 9; memcpy(o, e->qd, 72); o += 9;
   memcpy(o, e->ee_target, 24); o += 3; memcpy(o, e->rest_pose, 56); o += 7;
@@ -1451,7 +1505,7 @@ void pmgo_get_state(const PmgoEnv* e, double* o) {
     copy3(o, e->bpos[b]); memcpy(o + 3, e->bquat[b], 32); copy3(o + 7, e->bv[b]); copy3(o + 10, e->bw[b]); o += 13;
   }
   memcpy(o, e->goal, sizeof(double) * e->dims[3]); o += e->dims[3];
-  if (e->td) *o++ = e->sub_goal_ind;
+  if (e->td || e->cur) *o++ = e->sub_goal_ind;
   *o = e->elapsed;
 }
 void pmgo_set_state(PmgoEnv* e, const double* o) {
@@ -1462,7 +1516,7 @@ void pmgo_set_state(PmgoEnv* e, const double* o) {
     copy3(e->bpos[b], o); memcpy(e->bquat[b], o + 3, 32); copy3(e->bv[b], o + 7); copy3(e->bw[b], o + 10); o += 13;
   }
   memcpy(e->goal, o, sizeof(double) * e->dims[3]); o += e->dims[3];
-  if (e->td) e->sub_goal_ind = (int)*o++;
+  if (e->td || e->cur) e->sub_goal_ind = (int)*o++;
   e->elapsed = (int)*o;
   if (e->task == PMGO_BLOCK_STACK)
     for (int b = 0; b < e->nb; b++) {

@@ -47,6 +47,14 @@ PmgoEnv* pmgo_create_ex(int task, int num_block, int binary_reward, double dista
  * chosen with pmgo_set_sub_goal like env.set_sub_goal, kuka_multi_step_base_env.py:159-165; reset selects -1). */
 PmgoEnv* pmgo_create_ex2(int task, int num_block, int binary_reward, double distance_threshold,
                          int max_episode_steps, int grip_informed_goal, int joint_control, int task_decomposition);
+/* + use_curriculum (block_stack; kuka_multi_step_base_env.py:122-140,350-379, kuka_multi_step_envs.py:124-148): every
+ * reset draws a difficulty level from curriculum_prob (np_random.choice) and only the stack levels <= it have to
+ * be built; with updates activated the probabilities follow the number of generated goals per level. */
+PmgoEnv* pmgo_create_ex3(int task, int num_block, int binary_reward, double distance_threshold, int max_episode_steps,
+                         int grip_informed_goal, int joint_control, int task_decomposition, int use_curriculum,
+                         long num_goals_to_generate);
+void pmgo_set_curriculum_update(PmgoEnv* e, int on); /* activate_ / deactivate_curriculum_update */
+int pmgo_get_curriculum(const PmgoEnv* e, double* prob_out /*[num_block]*/); /* returns the current level */
 void pmgo_set_sub_goal(PmgoEnv* e, int sub_goal_ind);
 /* the observation of the current state, without stepping (_get_obs) */
 void pmgo_observe(PmgoEnv* e, double* obs_out);
@@ -81,7 +89,7 @@ void pmgo_compute_reward(const double* ag, const double* dg, int64_t n, int g, d
 /* ---- state access for teacher-forced parity tests -------------------------------------- */
 /* layout: q[9] qd[9] ee_target[3] rest_pose[7] motor_target[9] motor_maximp[9]
  *         then per block pos[3] quat[4](xyzw) linvel[3] angvel[3]; then desired_goal[G] (the final goal);
- *         then sub_goal_ind (task decomposition only); then elapsed (as double). */
+ *         then sub_goal_ind (task decomposition / curriculum only); then elapsed (as double). */
 int pmgo_state_size(const PmgoEnv* e);
 void pmgo_get_state(const PmgoEnv* e, double* out);
 void pmgo_set_state(PmgoEnv* e, const double* in); /* also clears the contact caches */

@@ -40,6 +40,11 @@ def lib():
         L.pmgo_create_ex.argtypes = [C.c_int, C.c_int, C.c_int, C.c_double, C.c_int, C.c_int, C.c_int]
         L.pmgo_create_ex2.restype = C.c_void_p
         L.pmgo_create_ex2.argtypes = [C.c_int, C.c_int, C.c_int, C.c_double, C.c_int, C.c_int, C.c_int, C.c_int]
+        L.pmgo_create_ex3.restype = C.c_void_p
+        L.pmgo_create_ex3.argtypes = [C.c_int, C.c_int, C.c_int, C.c_double, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_long]
+        L.pmgo_set_curriculum_update.argtypes = [C.c_void_p, C.c_int]
+        L.pmgo_get_curriculum.argtypes = [C.c_void_p, dp]
+        L.pmgo_get_curriculum.restype = C.c_int
         L.pmgo_set_sub_goal.argtypes = [C.c_void_p, C.c_int]
         L.pmgo_observe.argtypes = [C.c_void_p, dp]
         L.pmgo_destroy.argtypes = [C.c_void_p]
@@ -102,12 +107,12 @@ class OracleEnv:
 
     def __init__(self, task="reach", num_block=4, binary_reward=True, distance_threshold=0.05,
                  max_episode_steps=50, seed=0, grip_informed_goal=False, joint_control=False,
-                 task_decomposition=False):
+                 task_decomposition=False, use_curriculum=False, num_goals_to_generate=10 ** 6):
         self.L = lib()
         self.task = task
-        self.h = self.L.pmgo_create_ex2(TASKS[task], num_block, int(binary_reward), distance_threshold,
+        self.h = self.L.pmgo_create_ex3(TASKS[task], num_block, int(binary_reward), distance_threshold,
                                         max_episode_steps, int(grip_informed_goal), int(joint_control),
-                                        int(task_decomposition))
+                                        int(task_decomposition), int(use_curriculum), int(num_goals_to_generate))
         dims = (C.c_int * 4)()
         self.adim = self.L.pmgo_dims(self.h, dims)
         self.dims = list(dims)
@@ -132,6 +137,14 @@ class OracleEnv:
 
     def set_sub_goal(self, ind):
         self.L.pmgo_set_sub_goal(self.h, int(ind))
+
+    def set_curriculum_update(self, on):
+        self.L.pmgo_set_curriculum_update(self.h, int(on))
+
+    def curriculum(self):
+        p = np.zeros(self.nb)
+        level = self.L.pmgo_get_curriculum(self.h, _dp(p))
+        return p, level
 
     def observe(self):
         out = np.zeros(sum(self.dims))

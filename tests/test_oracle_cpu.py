@@ -143,6 +143,8 @@ GOLDEN_VARIANTS = {
     "pick_and_place_jc": dict(task="pick_and_place", binary_reward=False, joint_control=True),
     "block_stack_td": dict(task="block_stack", num_block=3, task_decomposition=True),
     "block_stack_td_grip": dict(task="block_stack", num_block=3, task_decomposition=True, grip_informed_goal=True),
+    "block_stack_cur": dict(task="block_stack", num_block=3, use_curriculum=True, num_goals_to_generate=12),
+    "block_stack_cur_grip": dict(task="block_stack", num_block=3, use_curriculum=True, grip_informed_goal=True, num_goals_to_generate=12),
 }
 
 
@@ -153,12 +155,18 @@ def test_oracle_reproduces_reference_plumbing_goldens(oracle, name):
     g = np.load(os.path.join(GOLDEN, "ref_plumbing_%s.npz" % name))
     e = oracle.OracleEnv(seed=0, max_episode_steps=int(g["max_episode_steps"]), **GOLDEN_VARIANTS[name])
     e.reset()  # the reference ctor's own reset (base_env.py:84)
+    if "_cur" in name:
+        e.set_curriculum_update(True)  # env.activate_curriculum_update() (kuka_multi_step_base_env.py:147-151)
     L = int(g["episode_len"])
     k = 0
     for ep in range(g["reset_obs"].shape[0]):
         o = e.reset()
         flat = np.concatenate([o[key] for key in KEYS])
         np.testing.assert_allclose(flat, g["reset_obs"][ep], atol=1e-12, rtol=0)
+        if "_cur" in name:  # level drawn with np_random.choice, probabilities after _update_curriculum_prob
+            prob, level = e.curriculum()
+            assert level == int(g["curriculum_level"][ep])
+            np.testing.assert_allclose(prob, g["curriculum_prob"][ep], atol=0, rtol=0)
         for t in range(L):
             for (at, ind), want in zip(g["sub_goal_calls"], g["sub_goal_returns"]):
                 if at == k:  # env.set_sub_goal(ind) was called before this step (kuka_multi_step_base_env.py:159-165)

@@ -38,6 +38,10 @@ CONFIGS = [
     # task decomposition: env.set_sub_goal(k) is called by the script below (SUB_GOAL_SCHEDULE)
     ("block_stack_td", dict(task="block_stack", binary_reward=True, num_block=3, task_decomposition=True), 4, 100),
     ("block_stack_td_grip", dict(task="block_stack", binary_reward=True, num_block=3, task_decomposition=True, grip_informed_goal=True), 4, 100),
+    # curriculum: 24 short episodes with updates activated and 4 goals per level, so that curriculum_prob walks
+    # through its whole schedule (kuka_multi_step_base_env.py:350-379); max_episode_steps = 2
+    ("block_stack_cur", dict(task="block_stack", binary_reward=True, num_block=3, use_curriculum=True, num_goals_to_generate=12, max_episode_steps=2), 4, 48),
+    ("block_stack_cur_grip", dict(task="block_stack", binary_reward=True, num_block=3, use_curriculum=True, grip_informed_goal=True, num_goals_to_generate=12, max_episode_steps=2), 4, 48),
 ]
 # (step within the episode) -> sub-goal index handed to env.set_sub_goal before that step; indices beyond the
 # variant's number of sub-goals are taken modulo it by the script
@@ -52,6 +56,8 @@ VARIANTS = {
     "pick_and_place_jc": dict(task="pick_and_place", binary_reward=False, joint_control=True),
     "block_stack_td": dict(task="block_stack", num_block=3, task_decomposition=True),
     "block_stack_td_grip": dict(task="block_stack", num_block=3, task_decomposition=True, grip_informed_goal=True),
+    "block_stack_cur": dict(task="block_stack", num_block=3, use_curriculum=True, num_goals_to_generate=12, max_episode_steps=2),
+    "block_stack_cur_grip": dict(task="block_stack", num_block=3, use_curriculum=True, grip_informed_goal=True, num_goals_to_generate=12, max_episode_steps=2),
 }
 
 
@@ -84,10 +90,23 @@ def main():
         actions = scripted_actions(name, adim, T, rng)
         resets, steps, rewards, dones, oks = [], [], [], [], []
         sub_goal_calls, sub_goal_returns = [], []
-        for ep in range(2):
+        cur_prob, cur_level, cur_goal_step = [], [], []
+        L = T // 2
+        if "_cur" in name:
+            L = 2
+            import warnings
+            with warnings.catch_warnings():
+                warnings.simplefilter("ignore")
+                env.activate_curriculum_update()
+        for ep in range(T // L):
             resets.append(pack(env.reset()))
-            for t in range(T // 2):
-                a = actions[ep * (T // 2) + t]
+            if "_cur" in name:
+                inner = env.unwrapped if hasattr(env, "unwrapped") else env.env
+                cur_prob.append(np.array(inner.curriculum_prob, dtype=np.float64))
+                cur_level.append(int(inner.last_curriculum_level))
+                cur_goal_step.append(int(inner.curriculum_goal_step))
+            for t in range(L):
+                a = actions[ep * L + t]
                 if name not in ("reach", "reach_jc", "pick_and_place_jc"):
                     # steer the tip to the (first) block: push from the side / descend with open jaws
                     obs_now = steps[-1] if (steps and t > 0) else resets[-1]
@@ -97,16 +116,16 @@ def main():
                     a[:3] = np.clip((tgt - tip) / 0.01, -1, 1)
                     if adim == 4:
                         a[3] = -1.0 if t < 16 else 1.0
-                    actions[ep * (T // 2) + t] = a
+                    actions[ep * L + t] = a
                 if "_td" in name and t in SUB_GOAL_SCHEDULE:
                     nsub = 6 if name.endswith("grip") else 3
                     ind = SUB_GOAL_SCHEDULE[t]
                     ind = ind if ind < 0 else ind % nsub
                     sub = env.set_sub_goal(ind)
-                    sub_goal_calls.append((ep * (T // 2) + t, ind))
+                    sub_goal_calls.append((ep * L + t, ind))
                     sub_goal_returns.append(np.asarray(sub, dtype=np.float64))
                 obs, r, done, info = env.step(a.astype(np.float64))
-                if t == T // 2 - 1:
+                if t == L - 1:
                     assert done and info.get("TimeLimit.truncated") is True
                 steps.append(pack(obs))
                 rewards.append(float(r))
@@ -114,7 +133,9 @@ def main():
                 oks.append(bool(info["goal_achieved"]))
         np.savez_compressed(os.path.join(OUT, "ref_plumbing_%s.npz" % name), actions=actions, reset_obs=np.array(resets),
                             step_obs=np.array(steps), reward=np.array(rewards), done=np.array(dones),
-                            goal_achieved=np.array(oks), episode_len=T // 2,
+                            goal_achieved=np.array(oks), episode_len=L,
+                            curriculum_prob=np.array(cur_prob), curriculum_level=np.array(cur_level, dtype=np.int64),
+                            curriculum_goal_step=np.array(cur_goal_step, dtype=np.int64),
                             dims=np.array([len(np.ravel(obs[k])) for k in KEYS]),
                             max_episode_steps=env._max_episode_steps,
                             sub_goal_calls=np.array(sub_goal_calls, dtype=np.int64).reshape(-1, 2),
