@@ -22,7 +22,7 @@
 extern "C" {
 #endif
 
-#define PMG_ABI_VERSION 3
+#define PMG_ABI_VERSION 4
 
 typedef enum {
   PMG_OK = 0,
@@ -51,6 +51,10 @@ typedef struct {
                                  kuka_single_step_base_env.py:214-216) */
   int32_t task_decomposition; /* block_stack only: the desired goal is one of the sub-goals of
                                  kuka_multi_step_envs.py:88-120, selected with pmg_set_sub_goal */
+  int32_t use_curriculum;     /* block_stack only (exclusive with task_decomposition): every reset draws a goal
+                                 difficulty level from a per-env probability schedule
+                                 (kuka_multi_step_base_env.py:122-140,350-379; kuka_multi_step_envs.py:124-148) */
+  int32_t num_goals_to_generate; /* make_env(num_goals_to_generate=...): goals per level = this // num_block */
 } pmg_config;
 
 typedef struct pmg_handle pmg_handle;
@@ -76,7 +80,8 @@ int pmg_seed(pmg_handle* h, const uint32_t* keys_host, const int32_t* key_lens_h
  * 104-148; kuka_multi_step_base_env.py:223-246; kuka_multi_step_envs.py:34-87).
  * mask_host: nullable [batch] bytes, non-zero = reset that env (NULL = all).
  * spawn_host: nullable [batch, spawn_width] floats = [block xy (2*nb) | desired_goal (G)]
- *   (G includes the 4 gripper entries of a grip-informed goal);
+ *   (G includes the 4 gripper entries of a grip-informed goal; curriculum handles append the sub-goal index
+ *   equivalent to the drawn level: level, or 2 * level + 1 with grip-informed goals);
  *   NULL = sample on the host from each env's numpy-compatible MT19937 stream, exactly as the
  *   reference consumes it.
  * obs_dev: [batch, packed-row width] row-major, rows of envs not reset are rewritten unchanged. */
@@ -84,6 +89,13 @@ int pmg_reset(pmg_handle* h, const uint8_t* mask_host, const float* spawn_host, 
 int pmg_spawn_width(const pmg_handle* h);
 /* the spawn rows used by the most recent pmg_reset, [batch, spawn_width] (for parity tests) */
 int pmg_last_spawn(const pmg_handle* h, float* spawn_host);
+
+/* replaces: env.activate_curriculum_update() / env.deactivate_curriculum_update()
+ * (kuka_multi_step_base_env.py:147-157); curriculum handles only. */
+int pmg_set_curriculum_update(pmg_handle* h, int32_t on);
+/* curriculum state of every env: prob_host [batch, num_block] (curriculum_prob), level_host [batch] (the level drawn
+ * by the most recent reset; env.curriculum_goal_step = level * 25 + 50).  Either pointer may be NULL. */
+int pmg_get_curriculum(const pmg_handle* h, float* prob_host, int32_t* level_host);
 
 /* replaces: env.set_sub_goal(sub_goal_ind) (kuka_multi_step_base_env.py:159-181), task decomposition only.
  * ind_host: [batch] sub-goal index per env, python list indexing (-1 = the last sub-goal = the final goal; block

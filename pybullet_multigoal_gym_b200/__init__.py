@@ -4,7 +4,7 @@
 and adds `batch` (number of environments stepped in lockstep; None = one unbatched env with the
 reference's numpy shapes), `device` and `seed`.  Tasks on the accelerated path: reach, push,
 pick_and_place, block_stack, block_rearrange with the parallel-jaw gripper and state observations,
-including the `joint_control` and (block_stack) `grip_informed_goal` / `task_decomposition` variants.
+including the `joint_control` and (block_stack) `grip_informed_goal` / `task_decomposition` / `use_curriculum` variants.
 """
 from .envs import (ActionError, KukaBlockRearrangeEnv, KukaBlockStackEnv, KukaBulletMGEnv,  # noqa: F401
                    KukaPickAndPlaceEnv, KukaPushEnv, KukaReachEnv)
@@ -48,10 +48,13 @@ def make_env(task='reach', gripper='parallel_jaw', num_block=5, render=False, bi
             raise AssertionError("Block rearranging task does not support task decomposition.")
         if task in _TAGS:
             task_decomposition = False  # the single-step tasks do not take the kwarg (__init__.py:88-106)
+    if use_curriculum and task != 'block_stack':
+        if task in ('reach', 'push', 'pick_and_place'):
+            use_curriculum = False  # the single-step tasks do not take the kwarg (__init__.py:88-106)
     for name, val in (('render', render),
                       ('image_observation', image_observation), ('depth_image', depth_image),
                       ('goal_image', goal_image), ('point_cloud', point_cloud), ('state_noise', state_noise),
-                      ('use_curriculum', use_curriculum)):
+                      ('use_curriculum', use_curriculum and task != 'block_stack')):
         if val:
             unsupported.append("%s=True" % name)
     if primitive is not None:
@@ -69,4 +72,5 @@ def make_env(task='reach', gripper='parallel_jaw', num_block=5, render=False, bi
                         distance_threshold=distance_threshold, max_episode_steps=max_episode_steps,
                         num_block=num_block, seed=seed, check_actions=check_actions,
                         grip_informed_goal=grip_informed_goal, joint_control=joint_control,
-                        task_decomposition=task_decomposition)
+                        task_decomposition=task_decomposition,
+                        use_curriculum=use_curriculum, num_goals_to_generate=num_goals_to_generate)

@@ -10,12 +10,12 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 SO_PATH = os.environ.get("PMG_LIBRARY") or os.path.join(_HERE, "libpmg.so")  # PMG_LIBRARY: instrumented development builds
 
-ABI_VERSION = 3
+ABI_VERSION = 4
 
 # every symbol include/pmg.h declares
 SYMBOLS = [
     "pmg_abi_version", "pmg_last_error", "pmg_create", "pmg_destroy", "pmg_dims", "pmg_seed",
-    "pmg_reset", "pmg_spawn_width", "pmg_last_spawn", "pmg_set_sub_goal", "pmg_step", "pmg_step_host",
+    "pmg_reset", "pmg_spawn_width", "pmg_last_spawn", "pmg_set_curriculum_update", "pmg_get_curriculum", "pmg_set_sub_goal", "pmg_step", "pmg_step_host",
     "pmg_compute_reward", "pmg_her_sample", "pmg_her_relabel", "pmg_state_width", "pmg_get_state", "pmg_set_state",
     "pmg_launch_count", "pmg_overflow_count",
 ]
@@ -25,7 +25,8 @@ class PmgConfig(C.Structure):
     _fields_ = [("task", C.c_int32), ("num_block", C.c_int32), ("batch", C.c_int32),
                 ("binary_reward", C.c_int32), ("distance_threshold", C.c_float),
                 ("max_episode_steps", C.c_int32), ("device", C.c_int32),
-                ("grip_informed_goal", C.c_int32), ("joint_control", C.c_int32), ("task_decomposition", C.c_int32)]
+                ("grip_informed_goal", C.c_int32), ("joint_control", C.c_int32), ("task_decomposition", C.c_int32),
+                ("use_curriculum", C.c_int32), ("num_goals_to_generate", C.c_int32)]
 
 
 _lib = None
@@ -53,6 +54,8 @@ def load():
     L.pmg_reset.argtypes = [vp, u8p, fp, fp, vp]
     L.pmg_spawn_width.argtypes = [vp]
     L.pmg_last_spawn.argtypes = [vp, fp]
+    L.pmg_set_curriculum_update.argtypes = [vp, C.c_int32]
+    L.pmg_get_curriculum.argtypes = [vp, fp, vp]
     L.pmg_set_sub_goal.argtypes = [vp, vp, vp]
     L.pmg_step.argtypes = [vp, fp, fp, fp, u8p, u8p, vp]
     L.pmg_step_host.argtypes = [vp, fp, fp, fp, u8p, u8p, vp]

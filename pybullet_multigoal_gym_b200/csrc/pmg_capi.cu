@@ -331,7 +331,7 @@ __global__ void __launch_bounds__(32) reset_kernel(ResetIO r) {
     Frames f;
     forward_kinematics<7>(e.q, f);
     V3 tip = tip_position(f);
-    const float* sp = r.spawn + (size_t)i * (2 * NBLK + io.goal_dim);
+    const float* sp = r.spawn + (size_t)i * (2 * NBLK + io.goal_dim + (io.cur ? 1 : 0));
 #pragma unroll
     for (int b = 0; b < NBLK; b++) {
       e.bpos[b] = v3(sp[2 * b], sp[2 * b + 1], BLOCK_SPAWN_Z);
@@ -342,7 +342,9 @@ __global__ void __launch_bounds__(32) reset_kernel(ResetIO r) {
     for (int k = 0; k < 7; k++) s[(ST_REST + k) * B] = qik[k];
     s[(ST_EE + 0) * B] = tip.x; s[(ST_EE + 1) * B] = tip.y; s[(ST_EE + 2) * B] = tip.z;
     for (int k = 0; k < io.goal_dim; k++) s[(size_t)(ST_BLK + 13 * NBLK + k) * B] = sp[2 * NBLK + k];
-    if (io.td) s[(size_t)(ST_BLK + 13 * NBLK + io.goal_dim) * B] = -1.0f;  // kuka_multi_step_base_env.py:247-248
+    // task decomposition selects the last sub-goal again (kuka_multi_step_base_env.py:247-248); a curriculum reset
+    // carries the sub-goal index of the level it drew behind the goal of its spawn row
+    if (io.td) s[(size_t)(ST_BLK + 13 * NBLK + io.goal_dim) * B] = io.cur ? sp[2 * NBLK + io.goal_dim] : -1.0f;
     s[(size_t)(io.state_words - 1) * B] = 0.0f;
     store_env<TASK, NBLK>(e, io, i);
   }
@@ -472,7 +474,12 @@ int fail(int code, const char* fmt, const char* detail = "") {
 struct pmg_handle {
   pmg_config cfg;
   int nblk, O, P, G, W, A, state_words, man_words, spawn_w;
-  bool multi = false, grasp = false, grip = false, jc = false, td = false;  // task variants, see pmg_config
+  bool multi = false, grasp = false, grip = false, jc = false, td = false, cur = false;  // task variants, see pmg_config
+  // curriculum state, one reference env's worth per environment (kuka_multi_step_base_env.py:122-140)
+  bool cur_update = false;
+  double cur_goals_per = 0;
+  std::vector<double> cur_prob, cur_count;  // [batch][nblk]
+  std::vector<int32_t> cur_level;           // [batch]
   float* d_state = nullptr; float* d_man = nullptr; float* d_spawn = nullptr; uint8_t* d_mask = nullptr; int* d_overflow = nullptr;
   float* d_action = nullptr; float* d_obs = nullptr; float* d_reward = nullptr; uint8_t* d_done = nullptr; uint8_t* d_success = nullptr;
   float* h_spawn = nullptr;  // pinned
@@ -541,6 +548,34 @@ void sample_spawn(pmg_handle* h, int i, float* out) {
       goal[3 * nb] = (float)bx; goal[3 * nb + 1] = (float)by;
       goal[3 * nb + 2] = (float)(nb == 1 ? 0.175 : 0.175 + 0.03 * (nb - 1)); goal[3 * nb + 3] = 0.03f;
     }
+    if (h->cur) {
+      // kuka_multi_step_envs.py:127-134: level = np_random.choice(num_curriculum, p=curriculum_prob), which is
+      // cdf.searchsorted(random_sample(), side='right') in numpy's legacy RandomState; then
+      // _update_curriculum_prob (kuka_multi_step_base_env.py:350-379), statement by statement
+      double* prob = &h->cur_prob[(size_t)i * nb];
+      double* count = &h->cur_count[(size_t)i * nb];
+      double cdf[5], acc = 0;
+      for (int k = 0; k < nb; k++) { acc += prob[k]; cdf[k] = acc; }
+      const double u = r.random_sample();
+      int level = 0;
+      while (level < nb && cdf[level] / acc <= u) level++;
+      h->cur_level[i] = level;
+      goal[h->G] = (float)(h->grip ? 2 * level + 1 : level);  // the equivalent sub-goal index, consumed by reset_kernel
+      if (h->cur_update) {
+        count[level] += 1;
+        bool fin[5], half[5];
+        for (int k = 0; k < nb; k++) {
+          fin[k] = count[k] >= h->cur_goals_per; half[k] = count[k] >= h->cur_goals_per / 2;
+          if (fin[k]) prob[k] = 0.0;
+        }
+        if (half[0] && !fin[0]) { prob[0] = 0.5; prob[1] = 0.5; }
+        for (int k = 1; k < nb - 1; k++)
+          if (fin[k - 1] && !fin[k]) {
+            if (half[k]) { prob[k] = 0.5; prob[k + 1] = 0.5; } else prob[k] = 1.0;
+          }
+        if (fin[nb - 2]) prob[nb - 1] = 1.0;
+      }
+    }
     return;
   }
   double center[3] = {h->tip_init[0], h->tip_init[1], h->tip_init[2]};
@@ -571,7 +606,7 @@ StepIO make_io(pmg_handle* h, const float* action, float* obs, float* reward, ui
   io.overflow = h->d_overflow;
   io.epw = h->epw;
   io.bulk = 0; io.tile_offset = 0;
-  io.grasp = h->grasp; io.jc = h->jc; io.grip_goal = h->grip; io.td = h->td;
+  io.grasp = h->grasp; io.jc = h->jc; io.grip_goal = h->grip; io.td = h->td || h->cur; io.cur = h->cur;
   io.adim = h->A; io.goal_dim = h->G; io.row_width = h->W;
   return io;
 }
@@ -592,7 +627,7 @@ void launch_step(pmg_handle* h, const StepIO& io_in, cudaStream_t st) {
   }
   int warps = (h->cfg.batch + h->epw - 1) / h->epw;
   size_t stage_floats = (size_t)h->epw * h->W;
-  io.bulk = (h->epw == 32 && h->cfg.batch % 32 == 0 && !h->no_bulk && !h->grip && !h->td) ? 1 : 0;
+  io.bulk = (h->epw == 32 && h->cfg.batch % 32 == 0 && !h->no_bulk && !h->grip && !h->td && !h->cur) ? 1 : 0;
   io.tile_offset = (int)((stage_floats + 31) / 32 * 32);
   size_t smem = (io.bulk ? io.tile_offset + (size_t)Dims<TASK, NBLK>::STATE * 32 : stage_floats) * sizeof(float);
   // The per-thread scratch lives in L1-cached local memory: ask for the smallest shared-memory
@@ -642,6 +677,8 @@ int pmg_create(const pmg_config* cfg, pmg_handle** out) {
   if (multi && (cfg->num_block < 1 || cfg->num_block > 5)) return fail(PMG_ERR_INVALID, "pmg_create: only support up to 5 blocks%s");
   if (cfg->grip_informed_goal && cfg->task != PMG_BLOCK_STACK) return fail(PMG_ERR_INVALID, "pmg_create: grip_informed_goal is a block_stack option%s");
   if (cfg->task_decomposition && cfg->task != PMG_BLOCK_STACK) return fail(PMG_ERR_INVALID, "pmg_create: task_decomposition is a block_stack option%s");
+  if (cfg->use_curriculum && (cfg->task != PMG_BLOCK_STACK || cfg->num_block < 2)) return fail(PMG_ERR_INVALID, "pmg_create: use_curriculum needs block_stack with at least 2 blocks%s");
+  if (cfg->use_curriculum && cfg->task_decomposition) return fail(PMG_ERR_INVALID, "pmg_create: if using curriculum, task decomposition should be False, vice versa%s");
   if (cfg->batch < 1) return fail(PMG_ERR_INVALID, "pmg_create: batch must be >= 1%s");
   if (cfg->max_episode_steps < 1 || cfg->max_episode_steps >= (1 << 24)) return fail(PMG_ERR_INVALID, "pmg_create: max_episode_steps out of range%s");
   int ndev = 0;
@@ -657,15 +694,16 @@ int pmg_create(const pmg_config* cfg, pmg_handle** out) {
   h->grip = cfg->grip_informed_goal != 0;
   h->jc = cfg->joint_control != 0;
   h->td = cfg->task_decomposition != 0;
+  h->cur = cfg->use_curriculum != 0;
   h->nblk = t == PMG_REACH ? 0 : (multi ? cfg->num_block : 1);
   h->O = (t == PMG_REACH ? 3 : (multi ? 8 + 16 * h->nblk : 20)) + (h->jc ? 7 : 0);
   h->P = (t == PMG_REACH ? 3 : (multi ? 4 + 3 * h->nblk : 7)) + (h->jc ? 7 : 0);
   h->G = (multi ? 3 * h->nblk : 3) + (h->grip ? 4 : 0);
   h->W = h->O + h->P + 2 * h->G;
   h->A = h->jc ? (h->grasp ? 8 : 7) : (h->grasp ? 4 : 3);  // kuka.py:104-118
-  h->state_words = ST_BLK + 13 * h->nblk + h->G + (h->td ? 1 : 0) + 1;
+  h->state_words = ST_BLK + 13 * h->nblk + h->G + ((h->td || h->cur) ? 1 : 0) + 1;
   h->man_words = num_pairs(h->nblk) * MAN_WORDS;
-  h->spawn_w = 2 * h->nblk + h->G;
+  h->spawn_w = 2 * h->nblk + h->G + (h->cur ? 1 : 0);
   // kuka.py:35-51 with obj_range = target_range = 0.15 (kuka_single_step_envs.py, kuka_multi_step_envs.py:29)
   h->tip_init[0] = -0.52; h->tip_init[1] = 0.0; h->tip_init[2] = (t == PMG_PUSH || t == PMG_BLOCK_REARRANGE) ? 0.175 + 0.001 : 0.25;
   for (int k = 0; k < 3; k++) {
@@ -690,6 +728,13 @@ int pmg_create(const pmg_config* cfg, pmg_handle** out) {
     if (const char* ev = getenv("PMG_BULK_COPY")) h->no_bulk = atoi(ev) == 0;
     if (const char* ev = getenv("PMG_DEFAULT_CARVEOUT")) h->default_carveout = atoi(ev) != 0;
     if (const char* ev = getenv("PMG_COOP")) h->coop = atoi(ev) != 0;
+  }
+  if (h->cur) {
+    h->cur_goals_per = (double)(cfg->num_goals_to_generate / h->nblk);  // floor division (kuka_multi_step_base_env.py:138)
+    h->cur_prob.assign(B * h->nblk, 0.0);
+    h->cur_count.assign(B * h->nblk, 0.0);
+    h->cur_level.assign(B, 0);
+    for (size_t i = 0; i < B; i++) h->cur_prob[i * h->nblk] = 1.0;  // the easiest goal is the only possible one at first
   }
   h->rng.resize(B);
   for (size_t i = 0; i < B; i++) h->rng[i].init_genrand(5489u + (uint32_t)i);
@@ -758,7 +803,10 @@ int pmg_reset(pmg_handle* h, const uint8_t* mask_host, const float* spawn_host, 
   CUDA_TRY(cudaStreamSynchronize(st));
   for (size_t i = 0; i < B; i++) {
     if (mask_host && !mask_host[i]) continue;
-    if (spawn_host) memcpy(h->h_spawn + i * h->spawn_w, spawn_host + i * h->spawn_w, sizeof(float) * h->spawn_w);
+    if (spawn_host) {
+      memcpy(h->h_spawn + i * h->spawn_w, spawn_host + i * h->spawn_w, sizeof(float) * h->spawn_w);
+      if (h->cur) { const int ind = (int)spawn_host[i * h->spawn_w + h->spawn_w - 1]; h->cur_level[i] = h->grip ? ind >> 1 : ind; }
+    }
     else sample_spawn(h, (int)i, h->h_spawn + i * h->spawn_w);
   }
   CUDA_TRY(cudaMemcpyAsync(h->d_spawn, h->h_spawn, sizeof(float) * h->spawn_w * B, cudaMemcpyHostToDevice, st));
@@ -773,6 +821,21 @@ int pmg_reset(pmg_handle* h, const uint8_t* mask_host, const float* spawn_host, 
   CUDA_TRY(cudaGetLastError());
   if (mask_host) CUDA_TRY(cudaStreamSynchronize(st));  // mask_host may be pageable caller memory
   h->was_reset = true;
+  return PMG_OK;
+}
+
+int pmg_set_curriculum_update(pmg_handle* h, int32_t on) {
+  if (!h) return fail(PMG_ERR_INVALID, "pmg_set_curriculum_update: null handle%s");
+  if (!h->cur) return fail(PMG_ERR_STATE, "pmg_set_curriculum_update: the handle was created without use_curriculum%s");
+  h->cur_update = on != 0;
+  return PMG_OK;
+}
+
+int pmg_get_curriculum(const pmg_handle* h, float* prob_host, int32_t* level_host) {
+  if (!h) return fail(PMG_ERR_INVALID, "pmg_get_curriculum: null handle%s");
+  if (!h->cur) return fail(PMG_ERR_STATE, "pmg_get_curriculum: the handle was created without use_curriculum%s");
+  if (prob_host) for (size_t k = 0; k < h->cur_prob.size(); k++) prob_host[k] = (float)h->cur_prob[k];
+  if (level_host) memcpy(level_host, h->cur_level.data(), sizeof(int32_t) * h->cur_level.size());
   return PMG_OK;
 }
 

@@ -72,7 +72,8 @@ class KukaBulletMGEnv:
 
     def __init__(self, task, batch=None, device=0, binary_reward=True, distance_threshold=0.05,
                  max_episode_steps=50, num_block=4, seed=0, check_actions=True,
-                 grip_informed_goal=False, joint_control=False, task_decomposition=False):
+                 grip_informed_goal=False, joint_control=False, task_decomposition=False,
+                 use_curriculum=False, num_goals_to_generate=1e6):
         if task not in TASK_IDS:
             raise ValueError("invalid task name: %s, only support: %s" % (task, sorted(TASK_IDS)))
         self._L = _lib.load()
@@ -99,10 +100,22 @@ class KukaBulletMGEnv:
             # kuka_multi_step_envs.py:13-17, kuka_multi_step_base_env.py:116-119: demonstrations [0], [0, 1], ...
             self.num_steps = self.num_block * (2 if self.grip_informed_goal else 1)
             self.step_demonstrator = StepDemonstrator([list(range(i + 1)) for i in range(self.num_steps)])
+        self.curriculum = bool(use_curriculum) and task == "block_stack"
+        if self.curriculum:
+            # kuka_multi_step_base_env.py:112-140
+            assert not self.task_decomposition, 'if using curriculum, task decomposition should be False, vice versa'
+            import warnings
+            warnings.warn("You will need to call env.activate_curriculum_update() before your training phase, "
+                          "and env.deactivate_curriculum_update() before your evaluation phase.")
+            self.curriculum_update = False
+            self.num_curriculum = self.num_block
+            self.base_curriculum_episode_steps = 50
+            self.num_goals_per_curriculum = int(num_goals_to_generate) // self.num_curriculum
         self.check_actions = check_actions
         cfg = _lib.PmgConfig(TASK_IDS[task], int(num_block), self.batch, int(self.binary_reward),
                              self.distance_threshold, self._max_episode_steps, self.device.index,
-                             int(self.grip_informed_goal), int(self.joint_control), int(self.task_decomposition))
+                             int(self.grip_informed_goal), int(self.joint_control), int(self.task_decomposition),
+                             int(self.curriculum), int(min(int(num_goals_to_generate), 2 ** 31 - 1)))
         h = C.c_void_p()
         _lib.check(self._L.pmg_create(C.byref(cfg), C.byref(h)))
         self._h = h
@@ -190,6 +203,43 @@ class KukaBulletMGEnv:
             if self._squeeze:
                 self.desired_goal = host["desired_goal"]
             return host
+
+    # ---- curriculum (kuka_multi_step_base_env.py:147-157, 350-379) -------------------------------------
+    def _curriculum_toggle(self, on):
+        if not self.curriculum:
+            import warnings
+            warnings.warn("This method should not be called while not using curriculum.")
+            return
+        self.curriculum_update = on
+        _lib.check(self._L.pmg_set_curriculum_update(self._h, int(on)))
+
+    def activate_curriculum_update(self):
+        self._curriculum_toggle(True)
+
+    def deactivate_curriculum_update(self):
+        self._curriculum_toggle(False)
+
+    def _curriculum_state(self):
+        prob = np.zeros((self.batch, self.num_block), dtype=np.float32)
+        level = np.zeros((self.batch,), dtype=np.int32)
+        _lib.check(self._L.pmg_get_curriculum(self._h, prob.ctypes.data_as(C.c_void_p), level.ctypes.data_as(C.c_void_p)))
+        return prob, level
+
+    @property
+    def curriculum_prob(self):
+        """[batch, num_curriculum]: every environment runs its own schedule, like separate reference envs."""
+        p = self._curriculum_state()[0]
+        return p[0].astype(np.float64) if self._squeeze else p
+
+    @property
+    def last_curriculum_level(self):
+        lv = self._curriculum_state()[1]
+        return int(lv[0]) if self._squeeze else lv
+
+    @property
+    def curriculum_goal_step(self):
+        """kuka_multi_step_envs.py:128: the number of episode steps the reference suggests for the drawn level."""
+        return self.last_curriculum_level * 25 + self.base_curriculum_episode_steps
 
     def set_sub_goal(self, sub_goal_ind):
         """kuka_multi_step_base_env.py:159-181.  `sub_goal_ind`: one index for every environment or a [batch]

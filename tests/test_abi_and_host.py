@@ -27,7 +27,7 @@ def test_library_exports_every_declared_symbol():
     missing = [s for s in declared if not hasattr(L, s)]
     assert not missing, "libpmg.so lacks: %s" % missing
     assert sorted(_lib.SYMBOLS) == declared
-    assert _lib.load().pmg_abi_version() == 3
+    assert _lib.load().pmg_abi_version() == 4
     # the library is sm_100a SASS produced by our own sources (kept in-tree, not in site-packages)
     assert os.path.dirname(_lib.SO_PATH) == os.path.join(ROOT, "pybullet_multigoal_gym_b200")
 
@@ -39,15 +39,15 @@ def test_c_abi_rejects_bad_arguments_without_touching_the_gpu():
     L = _lib.load()
     h = C.c_void_p()
     assert L.pmg_create(None, C.byref(h)) == -1
-    cfg = _lib.PmgConfig(7, 4, 8, 1, 0.05, 50, 0, 0, 0, 0)
+    cfg = _lib.PmgConfig(7, 4, 8, 1, 0.05, 50, 0, 0, 0, 0, 0, 0)
     assert L.pmg_create(C.byref(cfg), C.byref(h)) == -1 and b"task" in L.pmg_last_error()
-    cfg = _lib.PmgConfig(3, 6, 8, 1, 0.05, 50, 0, 0, 0, 0)
+    cfg = _lib.PmgConfig(3, 6, 8, 1, 0.05, 50, 0, 0, 0, 0, 0, 0)
     assert L.pmg_create(C.byref(cfg), C.byref(h)) == -1 and b"5 blocks" in L.pmg_last_error()
-    cfg = _lib.PmgConfig(4, 6, 8, 1, 0.05, 50, 0, 0, 0, 0)
+    cfg = _lib.PmgConfig(4, 6, 8, 1, 0.05, 50, 0, 0, 0, 0, 0, 0)
     assert L.pmg_create(C.byref(cfg), C.byref(h)) == -1 and b"5 blocks" in L.pmg_last_error()
-    cfg = _lib.PmgConfig(4, 3, 8, 1, 0.05, 50, 0, 1, 0, 0)  # grip-informed goals are a block_stack option
+    cfg = _lib.PmgConfig(4, 3, 8, 1, 0.05, 50, 0, 1, 0, 0, 0, 0)  # grip-informed goals are a block_stack option
     assert L.pmg_create(C.byref(cfg), C.byref(h)) == -1 and b"grip_informed_goal" in L.pmg_last_error()
-    cfg = _lib.PmgConfig(0, 0, 0, 1, 0.05, 50, 0, 0, 0, 0)
+    cfg = _lib.PmgConfig(0, 0, 0, 1, 0.05, 50, 0, 0, 0, 0, 0, 0)
     assert L.pmg_create(C.byref(cfg), C.byref(h)) == -1
     with pytest.raises(ValueError):
         _lib.check(-1)
@@ -66,7 +66,7 @@ def test_make_env_validation_matches_reference():
     with pytest.raises(AssertionError):      # kuka_multi_step_envs.py:159
         pmg.make_env(task="block_rearrange", num_block=3, task_decomposition=True)
     for kw in (dict(task="insertion"), dict(task="slide"), dict(task="reach", gripper="robotiq85"),
-               dict(task="push", image_observation=True), dict(task="block_stack", num_block=4, use_curriculum=True)):
+               dict(task="push", image_observation=True), dict(task="block_rearrange", num_block=4, use_curriculum=True)):
         with pytest.raises(NotImplementedError):
             pmg.make_env(**kw)
 

@@ -198,3 +198,57 @@ def test_task_decomposition_sub_goals_match_oracle(oracle, name):
     assert np.all(st[:, -2] == -1.0)      # sub-goal index word sits in front of the elapsed-steps word
     final = o1["desired_goal"]
     assert torch.equal(env.set_sub_goal(-1), final) and torch.equal(env.set_sub_goal(nsub - 1), final)
+
+
+@pytest.mark.parametrize("name,grip", [("block_stack_cur", False), ("block_stack_cur_grip", True)])
+def test_curriculum_schedule_matches_reference_plumbing_golden(oracle, name, grip):
+    """use_curriculum=True (kuka_multi_step_base_env.py:122-157,350-379; kuka_multi_step_envs.py:124-148): every
+    environment draws its goal level with np_random.choice from its own probability schedule.  Env 0 (seed 0)
+    reproduces the reference golden -- levels, curriculum_prob after every reset, reset observations -- and every
+    env i follows the oracle seeded with seed + i; desired goals after a step track the current block positions."""
+    import warnings
+    g = np.load(os.path.join(GOLDEN, "ref_plumbing_%s.npz" % name))
+    kw = dict(task="block_stack", num_block=3, use_curriculum=True, num_goals_to_generate=12, grip_informed_goal=grip)
+    B = 4
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        env = _mk(B, max_episode_steps=2, **kw)
+        refs = [oracle.OracleEnv(seed=i, max_episode_steps=2, **kw) for i in range(B)]
+    for o in refs:
+        o.reset()
+        o.set_curriculum_update(True)
+    env.activate_curriculum_update()
+    assert [int(env.reset()[k].shape[1]) for k in KEYS] == list(g["dims"])
+    env = None
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        env = _mk(B, max_episode_steps=2, **kw)   # a fresh env: the dims check above consumed one reset
+    env.activate_curriculum_update()
+    k = 0
+    for ep in range(g["reset_obs"].shape[0]):
+        obs = env.reset()
+        flat0 = np.concatenate([_np(obs[key][0]) for key in KEYS])
+        np.testing.assert_allclose(flat0, g["reset_obs"][ep], atol=2e-6)
+        assert int(env.last_curriculum_level[0]) == int(g["curriculum_level"][ep])
+        np.testing.assert_allclose(env.curriculum_prob[0], g["curriculum_prob"][ep], atol=0)
+        assert int(env.curriculum_goal_step[0]) == int(g["curriculum_goal_step"][ep])
+        for i in range(B):
+            ro = refs[i].reset()
+            prob, level = refs[i].curriculum()
+            assert int(env.last_curriculum_level[i]) == level
+            np.testing.assert_allclose(env.curriculum_prob[i], prob, atol=0)
+            np.testing.assert_allclose(_np(obs["desired_goal"][i]), ro["desired_goal"], atol=2e-6)
+        for t in range(int(g["episode_len"])):
+            a = torch.from_numpy(np.repeat(g["actions"][k][None].astype(np.float32), B, axis=0)).cuda()
+            obs, r, done, info = env.step(a)
+            flat0 = np.concatenate([_np(obs[key][0]) for key in KEYS])
+            pos = np.r_[0:3, flat0.size - 2 * env.goal_dim:flat0.size]
+            assert np.abs(flat0 - g["step_obs"][k])[pos].max() < TOL
+            assert bool(done[0]) == bool(g["done"][k]) and float(r[0]) == g["reward"][k]
+            for i in range(B):
+                refs[i].step(g["actions"][k])
+            k += 1
+    env.deactivate_curriculum_update()
+    before = env.curriculum_prob.copy()
+    env.reset()
+    assert np.array_equal(env.curriculum_prob, before)   # frozen while updates are off
