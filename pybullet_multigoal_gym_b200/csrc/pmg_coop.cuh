@@ -568,7 +568,8 @@ __device__ void substep(const Grp& g, EnvSmem& sm, Lane& L) {
     const float tc[3] = PMG_TABLE_CENTER, th[3] = PMG_TABLE_HALF, fh[3] = PMG_FINGER_HALF;
     // the narrowphase work arrays live in the (not yet used) contact-row area of shared memory
     BoxScratch& scr = *reinterpret_cast<BoxScratch*>(&sm.rows[lane * (MAXPTS * 3 / 2)][0]);
-    collide_pair(mr, lane, lane == 0 ? pf1 : pf2, Rg, v3(fh[0], fh[1], fh[2]), v3(tc[0], tc[1], tc[2]), m3_identity(), v3(th[0], th[1], th[2]), scr);
+    collide_pair(mr, lane, lane == 0 ? pf1 : pf2, Rg, v3(fh[0], fh[1], fh[2]), v3(0, 0, 0), false,
+                 v3(tc[0], tc[1], tc[2]), m3_identity(), v3(th[0], th[1], th[2]), geom_anchor(G_TABLE), scr);
   }
   PMG_T(t_col1);
   // 4. subtree wrenches and composite inertias: suffix sums over the chain

@@ -634,6 +634,14 @@ __device__ int box_box(V3 p1, const M3& R1, V3 A, V3 p2, const M3& R2, V3 B, Box
   if (codeN == 0) { code1 = 1; code2 = 2; } else if (codeN == 1) { code1 = 0; code2 = 2; } else { code1 = 0; code2 = 1; }
   V3 ra1 = col(Ra, code1), ra2 = col(Ra, code2), rb1 = col(Rb, a1), rb2 = col(Rb, a2);
   float c1 = dot(center, ra1), c2 = dot(center, ra2);
+  // Depths and contact points are evaluated relative to the centre of the REFERENCE FACE, not of the reference
+  // box: the large terms (half extent against centre distance) cancel once, here, with a rounding error that is
+  // common to all corners of the contact, and the per-corner terms are then added to a small number.  With
+  // everything relative to the box centre the four corners of a block resting on the table differ by fp32
+  // rounding of a 0.08 m coordinate (7e-9 m), which the contact ERP (450 1/s) turns into visible spin.
+  const float sa_n = comp(SaV, codeN);
+  const V3 centerf = center - sa_n * normal2;   // incident face centre relative to the reference face centre
+  const V3 face_c = pa + sa_n * normal2;        // reference face centre, in the caller's coordinates
   float m11 = dot(ra1, rb1), m12 = dot(ra1, rb2), m21 = dot(ra2, rb1), m22 = dot(ra2, rb2);
   float* quad = scr.quad;
   float qx[4], qy[4];  // the incident face's corners in the reference face's 2-D frame (registers)
@@ -649,7 +657,7 @@ __device__ int box_box(V3 p1, const M3& R1, V3 A, V3 p2, const M3& R2, V3 B, Box
     // Fast path, the usual resting contact: the incident face lies inside the reference face (nothing to
     // clip) and all four corners touch (nothing to cull): the contacts are the four corners, in order.  The
     // arithmetic per corner is the generic path's, so the output is bit-identical to it.
-    const float ra = comp(SaV, code1), rb = comp(SaV, code2), sn = comp(SaV, codeN);
+    const float ra = comp(SaV, code1), rb = comp(SaV, code2);
     bool all_in = true;
 #pragma unroll
     for (int j = 0; j < 4; j++) all_in = all_in && fabsf(qx[j]) < ra && fabsf(qy[j]) < rb;
@@ -662,14 +670,14 @@ __device__ int box_box(V3 p1, const M3& R1, V3 A, V3 p2, const M3& R2, V3 B, Box
       for (int j = 0; j < 4; j++) {
         float k1 = i22 * (qx[j] - c1) - i12 * (qy[j] - c2);
         float k2 = -i21 * (qx[j] - c1) + i11 * (qy[j] - c2);
-        pt[j] = center + k1 * rb1 + k2 * rb2;
-        dp[j] = sn - dot(normal2, pt[j]);
+        pt[j] = centerf + k1 * rb1 + k2 * rb2;
+        dp[j] = -dot(normal2, pt[j]);
         all_touch = all_touch && dp[j] >= 0;
       }
       if (all_touch) {
 #pragma unroll
         for (int j = 0; j < 4; j++) {
-          V3 w = pt[j] + pa;
+          V3 w = pt[j] + face_c;
           if (swap) w -= dp[j] * normal;  // incident face was on A: move the point onto B
           out[j].pB = w; out[j].nB = -normal; out[j].dist = -dp[j];
         }
@@ -690,8 +698,8 @@ __device__ int box_box(V3 p1, const M3& R1, V3 A, V3 p2, const M3& R2, V3 B, Box
   for (int j = 0; j < n; j++) {
     float k1 = m22 * (ret[2 * j] - c1) - m12 * (ret[2 * j + 1] - c2);
     float k2 = -m21 * (ret[2 * j] - c1) + m11 * (ret[2 * j + 1] - c2);
-    V3 pt = center + k1 * rb1 + k2 * rb2;
-    float dp = comp(SaV, codeN) - dot(normal2, pt);
+    V3 pt = centerf + k1 * rb1 + k2 * rb2;
+    float dp = -dot(normal2, pt);
     if (dp >= 0) { point[cnum] = pt; dep[cnum] = dp; ret[2 * cnum] = ret[2 * j]; ret[2 * cnum + 1] = ret[2 * j + 1]; cnum++; }
   }
   if (cnum < 1) return 0;
@@ -705,7 +713,7 @@ __device__ int box_box(V3 p1, const M3& R1, V3 A, V3 p2, const M3& R2, V3 B, Box
   }
   for (int j = 0; j < maxc; j++) {
     int k = idx[j];
-    V3 w = point[k] + pa;
+    V3 w = point[k] + face_c;
     if (swap) w -= dep[k] * normal;  // incident face was on A: move the point onto B
     out[j].pB = w; out[j].nB = -normal; out[j].dist = -dep[k];
   }

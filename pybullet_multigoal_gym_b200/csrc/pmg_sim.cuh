@@ -65,6 +65,17 @@ struct ManRef {
   __device__ __forceinline__ float& mw(int pair, int w) { return man[(size_t)(pair * MAN_WORDS + w) * stride]; }
 };
 
+// Manifold-local coordinates of a static box refer to the centre of its TOP FACE, not to its centre: contact
+// points on the table are then small numbers (see box_box: the fp32 rounding of a 0.08 m coordinate would
+// otherwise show up as spin of resting blocks).  Dynamic bodies are small; theirs refer to the body centre.
+__device__ __forceinline__ V3 geom_anchor(int kind) {
+  const float th[3] = PMG_TABLE_HALF, fh[3] = PMG_FLOOR_HALF;
+  if (kind == G_TABLE) return v3(0.0f, 0.0f, th[2]);
+  if (kind == G_FLOOR) return v3(0.0f, 0.0f, fh[2]);
+  return v3(0.0f, 0.0f, 0.0f);
+}
+__device__ __forceinline__ bool geom_static(int kind) { return kind == G_TABLE || kind == G_FLOOR; }
+
 template <int NBLK>
 struct Env : ManRef {
   static constexpr int NBA = NBLK > 0 ? NBLK : 1;
@@ -149,8 +160,11 @@ __device__ unsigned long long g_coop_cycles[16];
 #endif
 
 // One collision pair: broadphase (world AABBs grown by the margin), box-box narrowphase into the
-// persistent manifold, refresh.  Boxes given by centre, orientation, half extents.
-__device__ void collide_pair(ManRef& e, int k, V3 pa, const M3& Ra, V3 ha, V3 pb, const M3& Rb, V3 hb, BoxScratch& scr) {
+// persistent manifold, refresh.  Boxes given by centre, orientation, half extents; aA / aB are the anchors
+// (geom_anchor, world axes: static boxes are axis aligned) the manifold-local coordinates refer to.  The
+// narrowphase and the manifold run in coordinates relative to the static box's anchor (else to B's centre),
+// so that penetration depths are differences of small numbers.
+__device__ void collide_pair(ManRef& e, int k, V3 pa, const M3& Ra, V3 ha, V3 aA, bool a_static, V3 pb, const M3& Rb, V3 hb, V3 aB, BoxScratch& scr) {
   V3 d = pa - pb;
   float ex = fabsf(Ra.r0.x) * ha.x + fabsf(Ra.r0.y) * ha.y + fabsf(Ra.r0.z) * ha.z + fabsf(Rb.r0.x) * hb.x + fabsf(Rb.r0.y) * hb.y + fabsf(Rb.r0.z) * hb.z + 2 * BROADPHASE_MARGIN;
   float ey = fabsf(Ra.r1.x) * ha.x + fabsf(Ra.r1.y) * ha.y + fabsf(Ra.r1.z) * ha.z + fabsf(Rb.r1.x) * hb.x + fabsf(Rb.r1.y) * hb.y + fabsf(Rb.r1.z) * hb.z + 2 * BROADPHASE_MARGIN;
@@ -160,22 +174,25 @@ __device__ void collide_pair(ManRef& e, int k, V3 pa, const M3& Ra, V3 ha, V3 pb
     return;
   }
   float thr = BREAKING_THRESHOLD_FACTOR * fminf(norm(ha), norm(hb));
+  const V3 O = a_static ? pa + aA : pb + aB;            // origin of the relative coordinates
+  const V3 a0 = pa - O, b0 = pb - O;                     // box centres
+  const V3 a1 = a0 + aA, b1 = b0 + aB;                   // anchors of the manifold-local coordinates
   const Contact* c = scr.out;
 #ifdef PMG_COOP_TIMING
   const long long t0 = clock64();
 #endif
-  int nc = box_box(pa, Ra, ha, pb, Rb, hb, scr);
+  int nc = box_box(a0, Ra, ha, b0, Rb, hb, scr);
 #ifdef PMG_COOP_TIMING
   const long long t1 = clock64();
 #endif
   for (int i = 0; i < nc; i++) {
     V3 wa = c[i].pB + c[i].dist * c[i].nB;
-    manifold_add(e, k, thr, mulT(Ra, wa - pa), mulT(Rb, c[i].pB - pb), c[i].nB, c[i].dist);
+    manifold_add(e, k, thr, mulT(Ra, wa - a1), mulT(Rb, c[i].pB - b1), c[i].nB, c[i].dist);
   }
 #ifdef PMG_COOP_TIMING
   const long long t2 = clock64();
 #endif
-  manifold_refresh(e, k, thr, pa, Ra, pb, Rb);
+  manifold_refresh(e, k, thr, a1, Ra, b1, Rb);
 #ifdef PMG_COOP_TIMING
   if (k == 0 && nc > 0) {
     atomicAdd(&g_coop_cycles[8], (unsigned long long)(t1 - t0)); atomicAdd(&g_coop_cycles[9], (unsigned long long)(t2 - t1));
@@ -205,14 +222,18 @@ __device__ void collide(Env<NBLK>& e, const Frames& f) {
       continue;
     }
     float thr = BREAKING_THRESHOLD_FACTOR * fminf(norm(ha), norm(hb));
+    // narrowphase and manifold in coordinates relative to the static box's anchor (else B's centre), see collide_pair
+    const V3 aA = geom_anchor(pi.ka), aB = geom_anchor(pi.kb);
+    const V3 O = geom_static(pi.ka) ? pa + aA : pb + aB;
+    const V3 a0 = pa - O, b0 = pb - O, a1 = a0 + aA, b1 = b0 + aB;
     BoxScratch scr;
     const Contact* c = scr.out;
-    int nc = box_box(pa, Ra, ha, pb, Rb, hb, scr);
+    int nc = box_box(a0, Ra, ha, b0, Rb, hb, scr);
     for (int i = 0; i < nc; i++) {
       V3 wa = c[i].pB + c[i].dist * c[i].nB;
-      manifold_add(e, k, thr, mulT(Ra, wa - pa), mulT(Rb, c[i].pB - pb), c[i].nB, c[i].dist);
+      manifold_add(e, k, thr, mulT(Ra, wa - a1), mulT(Rb, c[i].pB - b1), c[i].nB, c[i].dist);
     }
-    manifold_refresh(e, k, thr, pa, Ra, pb, Rb);
+    manifold_refresh(e, k, thr, a1, Ra, b1, Rb);
   }
 }
 
@@ -412,6 +433,7 @@ __device__ void solve_constraints(Env<NBLK>& e, const Frames& f, const float (*M
     V3 pa, pb; M3 Ra, Rb;
     geom_pose(e, f, pi.ka, pi.ia, pa, Ra);
     geom_pose(e, f, pi.kb, pi.ib, pb, Rb);
+    const V3 pa_anchor = pa + geom_anchor(pi.ka), pb_anchor = pb + geom_anchor(pi.kb);  // what lA / lB refer to
     const float mu = geom_friction(pi.ka) * geom_friction(pi.kb);
     const bool robotA = pi.ka == G_FINGER1 || pi.ka == G_FINGER2;
     const bool blockA = pi.ka == G_BLOCK, blockB = pi.kb == G_BLOCK;
@@ -423,7 +445,7 @@ __device__ void solve_constraints(Env<NBLK>& e, const Frames& f, const float (*M
       V3 lA = v3(e.mw(k, o), e.mw(k, o + 1), e.mw(k, o + 2)), lB = v3(e.mw(k, o + 3), e.mw(k, o + 4), e.mw(k, o + 5));
       V3 nB = v3(e.mw(k, o + 6), e.mw(k, o + 7), e.mw(k, o + 8));
       const float dist = e.mw(k, o + 9);
-      V3 wa = mul(Ra, lA) + pa, wb = mul(Rb, lB) + pb;
+      V3 wa = mul(Ra, lA) + pa_anchor, wb = mul(Rb, lB) + pb_anchor;
       V3 dirs[3];
       dirs[0] = nB;
       plane_space(nB, dirs[1], dirs[2]);

@@ -103,8 +103,9 @@ def test_finger_table_contact_rollout_matches_oracle(emu):
 def test_thread_per_env_physics_on_host_matches_oracle(emu, task, nb):
     """The thread-per-env device code (csrc/pmg_sim.cuh: robot dynamics, box-box manifolds, contact / friction
     rows, PGS) compiled for the host, stepped from the oracle's state with blocks resting on the table and the
-    closed jaws descending onto it: positions agree with the double-precision oracle to 1e-5 over 0.2 s; the
-    angular velocity of a resting block shows the documented fp32 contact-depth noise (< 2e-3 rad/s)."""
+    closed jaws descending onto it: positions agree with the double-precision oracle to 1e-5 over 0.2 s, velocities
+    to 1e-4 (contact depths are evaluated relative to the reference face / the static box's anchor, so a resting
+    block does not pick up fp32 rounding of table-sized coordinates as spin: 3e-4 rad/s before that change)."""
     o = O.OracleEnv(task, num_block=nb, seed=4)
     o.reset()
     o.reset()
@@ -124,6 +125,6 @@ def test_thread_per_env_physics_on_host_matches_oracle(emu, task, nb):
         for b in range(nb):
             got, want = s2[46 + 13 * b:59 + 13 * b], ref[46 + 13 * b:59 + 13 * b]
             assert np.abs(got[:7] - want[:7]).max() < 1e-5               # block position + quaternion
-            assert np.abs(got[7:10] - want[7:10]).max() < 2e-4           # linear velocity
-            assert np.abs(got[10:13] - want[10:13]).max() < 2e-3         # angular velocity (fp32 contact noise)
+            assert np.abs(got[7:10] - want[7:10]).max() < 1e-4           # linear velocity
+            assert np.abs(got[10:13] - want[10:13]).max() < 1e-4         # angular velocity
     assert sum(int(man[41 * k:41 * k + 1].view(np.int32)[0]) for k in range(npairs)) >= 4 * nb  # blocks rest on 4 points

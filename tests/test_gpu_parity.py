@@ -231,11 +231,12 @@ def test_teacher_forced_contact_parity(oracle, task, adim):
 
 
 def test_velocity_observations_of_resting_blocks_are_bounded(oracle):
-    """Known deviation: the stiff contact ERP term (0.9 / 2 ms) amplifies the fp32 rounding of the
-    cached contact depths (ulp(0.08 m) = 7e-9 m) into ~3e-4 rad/s of angular-velocity noise on a block that
-    rests on the table; the double-precision oracle sits at 1e-10.  Positions are unaffected (< 1e-6 per
-    step).  This test pins the size of that noise: velocity entries of the observation within 2e-3 of the
-    oracle, position entries within 1e-4, on a scene where nothing touches the blocks."""
+    """The stiff contact ERP term (0.9 / 2 ms) amplifies any rounding of the contact depths 450-fold into velocity.
+    With depths taken as differences of table-sized fp32 coordinates a block resting on the table showed
+    ~3e-4 rad/s of angular-velocity noise against 1e-10 in the double-precision oracle; the narrowphase and the
+    manifolds now work relative to the reference face / the static box's anchor.  This test pins the
+    result: on a scene where nothing touches the blocks every entry of the observation, velocities included,
+    stays within 1e-4 of the oracle."""
     B = 4
     env = _mk("block_stack", B, num_block=3)
     env.reset()
@@ -265,7 +266,7 @@ def test_velocity_observations_of_resting_blocks_are_bounded(oracle):
             worst_pos = max(worst_pos, float(d[~vel].max()))
             worst_vel = max(worst_vel, float(d[vel].max()))
     print("resting blocks: worst position-entry error %.3g, worst velocity-entry error %.3g" % (worst_pos, worst_vel))
-    assert worst_pos < TOL and worst_vel < 2e-3
+    assert worst_pos < TOL and worst_vel < TOL
 
 
 def test_cooperative_and_thread_per_env_reach_kernels_agree():
