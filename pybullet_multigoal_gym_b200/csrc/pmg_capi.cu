@@ -482,7 +482,10 @@ struct pmg_handle {
   std::vector<int32_t> cur_level;           // [batch]
   float* d_state = nullptr; float* d_man = nullptr; float* d_spawn = nullptr; uint8_t* d_mask = nullptr; int* d_overflow = nullptr;
   float* d_action = nullptr; float* d_obs = nullptr; float* d_reward = nullptr; uint8_t* d_done = nullptr; uint8_t* d_success = nullptr;
-  float* h_spawn = nullptr;  // pinned
+  float* h_spawn = nullptr;  // pinned; the spawn row every env was last reset with
+  float* h_stage[2] = {nullptr, nullptr};  // pinned DMA staging, alternating, so that sampling overlaps the GPU
+  cudaEvent_t stage_done[2] = {nullptr, nullptr};
+  int stage_cur = 0;
   std::vector<MT> rng;
   double tip_init[3], obj_lo[3], obj_hi[3], tgt_lo[3], tgt_hi[3];
   bool was_reset = false;
@@ -751,6 +754,10 @@ int pmg_create(const pmg_config* cfg, pmg_handle** out) {
   ALLOC(h->d_success, B);
 #undef ALLOC
   if (cudaMallocHost((void**)&h->h_spawn, sizeof(float) * h->spawn_w * B) != cudaSuccess) { pmg_destroy(h); return fail(PMG_ERR_CUDA, "cudaMallocHost failed%s"); }
+  for (int k = 0; k < 2; k++)
+    if (cudaMallocHost((void**)&h->h_stage[k], sizeof(float) * h->spawn_w * B) != cudaSuccess ||
+        cudaEventCreateWithFlags(&h->stage_done[k], cudaEventDisableTiming) != cudaSuccess) { pmg_destroy(h); return fail(PMG_ERR_CUDA, "cudaMallocHost failed%s"); }
+  memset(h->h_spawn, 0, sizeof(float) * h->spawn_w * B);
   cudaMemset(h->d_state, 0, sizeof(float) * h->state_words * B);
   cudaMemset(h->d_man, 0, sizeof(float) * h->man_words * B);
   cudaMemset(h->d_overflow, 0, sizeof(int));
@@ -767,6 +774,7 @@ int pmg_destroy(pmg_handle* h) {
   cudaFree(h->d_state); cudaFree(h->d_man); cudaFree(h->d_spawn); cudaFree(h->d_mask); cudaFree(h->d_overflow);
   cudaFree(h->d_action); cudaFree(h->d_obs); cudaFree(h->d_reward); cudaFree(h->d_done); cudaFree(h->d_success);
   if (h->h_spawn) cudaFreeHost(h->h_spawn);
+  for (int k = 0; k < 2; k++) { if (h->h_stage[k]) cudaFreeHost(h->h_stage[k]); if (h->stage_done[k]) cudaEventDestroy(h->stage_done[k]); }
   delete h;
   return PMG_OK;
 }
@@ -799,8 +807,7 @@ int pmg_reset(pmg_handle* h, const uint8_t* mask_host, const float* spawn_host, 
   cudaStream_t st = (cudaStream_t)stream;
   CUDA_TRY(cudaSetDevice(h->cfg.device));
   const size_t B = h->cfg.batch;
-  // the pinned staging buffer is reused: wait for the previous reset's copy to have been consumed
-  CUDA_TRY(cudaStreamSynchronize(st));
+  // host sampling runs while the GPU is still busy with the step kernel enqueued before this reset
   for (size_t i = 0; i < B; i++) {
     if (mask_host && !mask_host[i]) continue;
     if (spawn_host) {
@@ -809,7 +816,13 @@ int pmg_reset(pmg_handle* h, const uint8_t* mask_host, const float* spawn_host, 
     }
     else sample_spawn(h, (int)i, h->h_spawn + i * h->spawn_w);
   }
-  CUDA_TRY(cudaMemcpyAsync(h->d_spawn, h->h_spawn, sizeof(float) * h->spawn_w * B, cudaMemcpyHostToDevice, st));
+  // two pinned staging buffers alternate; one is reused only after the copy that last read it has completed
+  float* stage = h->h_stage[h->stage_cur];
+  CUDA_TRY(cudaEventSynchronize(h->stage_done[h->stage_cur]));
+  memcpy(stage, h->h_spawn, sizeof(float) * h->spawn_w * B);
+  CUDA_TRY(cudaMemcpyAsync(h->d_spawn, stage, sizeof(float) * h->spawn_w * B, cudaMemcpyHostToDevice, st));
+  CUDA_TRY(cudaEventRecord(h->stage_done[h->stage_cur], st));
+  h->stage_cur ^= 1;
   if (mask_host) CUDA_TRY(cudaMemcpyAsync(h->d_mask, mask_host, B, cudaMemcpyHostToDevice, st));
   ResetIO r;
   r.io = make_io(h, nullptr, obs_dev, nullptr, nullptr, nullptr);
