@@ -11,7 +11,7 @@ observation batch).
   value        device-timed (CUDA events around every step, L2 flushed between steps outside the
                events), inputs resident in HBM, max over ranks
   e2e          the same metric through the public API with HOST buffers: env.step(numpy actions)
-               -> pmg_step_host: H2D of the actions, the kernel, D2H of obs/reward/flags
+               -> pmg_step_host_blocks: H2D of the actions, the kernel, D2H of obs/reward/flags
   roofline     HBM roofline of the step kernel: algorithmic bytes per launch (SURVEY.md 8d, 282 B per
                Reach env-step) / mean kernel duration vs MEASURED_PEAKS.json hbm_gbs.  The path is
                bound by FP32 issue / dependency latency, not HBM; `fp32_frac` is
@@ -286,7 +286,7 @@ def main():
                          "note": "latency/FP32-issue bound path: 100 dependent substeps per env-step, ~0.3 KB of compulsory HBM traffic (SURVEY.md 0.5)",
                          "fp32_frac": FLOP_PER_ENV_STEP[task] * B / (kernel_ms / 1e3) / fp32_peak},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": B * A * 4, "d2h_bytes_per_step": B * Wd * 4 + B * 4 + 2 * B,
-                    "steps": int(host_tape.shape[0]), "api": "env.step(numpy) -> pmg_step_host"},
+                    "steps": int(host_tape.shape[0]), "api": "env.step(numpy) -> pmg_step_host_blocks"},
             "gpu_launches": int(launches),
             "clocks": sampler.summary(),
         }

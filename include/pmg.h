@@ -22,7 +22,7 @@
 extern "C" {
 #endif
 
-#define PMG_ABI_VERSION 4
+#define PMG_ABI_VERSION 5
 
 typedef enum {
   PMG_OK = 0,
@@ -118,6 +118,13 @@ int pmg_step(pmg_handle* h, const float* action_dev, float* obs_dev, float* rewa
  * reference-side binding calls once per env.step(). */
 int pmg_step_host(pmg_handle* h, const float* action_host, float* obs_host, float* reward_host,
                   uint8_t* done_host, uint8_t* success_host, void* stream);
+
+/* pmg_step_host with the observation delivered as four contiguous blocks instead of packed rows:
+ * blocks_host = [observation [batch, O] | policy_state [batch, P] | achieved_goal [batch, G] | desired_goal [batch, G]],
+ * each block row-major and contiguous -- the arrays of the reference's observation dict, ready to hand out without a
+ * strided de-interleave on the host (which costs more than the PCIe transfer at batch 8192). */
+int pmg_step_host_blocks(pmg_handle* h, const float* action_host, float* blocks_host, float* reward_host,
+                         uint8_t* done_host, uint8_t* success_host, void* stream);
 
 /* replaces: env._compute_reward(achieved_goal, desired_goal) on arbitrary leading axes
  * (kuka_single_step_base_env.py:237-244; kuka_multi_step_base_env.py:338-345), e.g. HER relabelling.

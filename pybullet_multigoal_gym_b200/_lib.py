@@ -10,12 +10,12 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 SO_PATH = os.environ.get("PMG_LIBRARY") or os.path.join(_HERE, "libpmg.so")  # PMG_LIBRARY: instrumented development builds
 
-ABI_VERSION = 4
+ABI_VERSION = 5
 
 # every symbol include/pmg.h declares
 SYMBOLS = [
     "pmg_abi_version", "pmg_last_error", "pmg_create", "pmg_destroy", "pmg_dims", "pmg_seed",
-    "pmg_reset", "pmg_spawn_width", "pmg_last_spawn", "pmg_set_curriculum_update", "pmg_get_curriculum", "pmg_set_sub_goal", "pmg_step", "pmg_step_host",
+    "pmg_reset", "pmg_spawn_width", "pmg_last_spawn", "pmg_set_curriculum_update", "pmg_get_curriculum", "pmg_set_sub_goal", "pmg_step", "pmg_step_host", "pmg_step_host_blocks",
     "pmg_compute_reward", "pmg_her_sample", "pmg_her_relabel", "pmg_state_width", "pmg_get_state", "pmg_set_state",
     "pmg_launch_count", "pmg_overflow_count",
 ]
@@ -59,6 +59,7 @@ def load():
     L.pmg_set_sub_goal.argtypes = [vp, vp, vp]
     L.pmg_step.argtypes = [vp, fp, fp, fp, u8p, u8p, vp]
     L.pmg_step_host.argtypes = [vp, fp, fp, fp, u8p, u8p, vp]
+    L.pmg_step_host_blocks.argtypes = [vp, fp, fp, fp, u8p, u8p, vp]
     L.pmg_compute_reward.argtypes = [fp, fp, C.c_int64, C.c_int32, C.c_float, C.c_int32, fp, u8p, vp]
     L.pmg_her_sample.argtypes = [C.c_int64, C.c_int32, C.c_int32, C.c_float, C.c_uint64, vp, vp, vp, vp]
     L.pmg_her_relabel.argtypes = [fp, fp, C.c_int32, C.c_int32, C.c_int32, vp, vp, vp, C.c_int64, C.c_float, C.c_int32,

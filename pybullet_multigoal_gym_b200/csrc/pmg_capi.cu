@@ -351,6 +351,19 @@ __global__ void __launch_bounds__(32) reset_kernel(ResetIO r) {
   write_obs<TASK, NBLK>(e, io, i);
 }
 
+// packed rows [B, W] -> four contiguous blocks [B, O] [B, P] [B, G] [B, G] (pmg_step_host_blocks)
+__global__ void split_rows_kernel(const float* packed, int B, int W, int O, int P, int G, float* blocks) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B * W) return;
+  const int env = i / W, c = i - env * W;
+  size_t dst;
+  if (c < O) dst = (size_t)env * O + c;
+  else if (c < O + P) dst = (size_t)B * O + (size_t)env * P + (c - O);
+  else if (c < O + P + G) dst = (size_t)B * (O + P) + (size_t)env * G + (c - O - P);
+  else dst = (size_t)B * (O + P + G) + (size_t)env * G + (c - O - P - G);
+  blocks[dst] = packed[i];
+}
+
 __global__ void reward_kernel(const float* ag, const float* dg, int64_t n, int g, float thr, int binary, float* reward, uint8_t* ok) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
@@ -481,6 +494,7 @@ struct pmg_handle {
   std::vector<double> cur_prob, cur_count;  // [batch][nblk]
   std::vector<int32_t> cur_level;           // [batch]
   float* d_state = nullptr; float* d_man = nullptr; float* d_spawn = nullptr; uint8_t* d_mask = nullptr; int* d_overflow = nullptr;
+  float* d_blocks = nullptr;
   float* d_action = nullptr; float* d_obs = nullptr; float* d_reward = nullptr; uint8_t* d_done = nullptr; uint8_t* d_success = nullptr;
   float* h_spawn = nullptr;  // pinned; the spawn row every env was last reset with
   float* h_stage[2] = {nullptr, nullptr};  // pinned DMA staging, alternating, so that sampling overlaps the GPU
@@ -749,6 +763,7 @@ int pmg_create(const pmg_config* cfg, pmg_handle** out) {
   ALLOC(h->d_overflow, sizeof(int));
   ALLOC(h->d_action, sizeof(float) * h->A * B);
   ALLOC(h->d_obs, sizeof(float) * h->W * B);
+  ALLOC(h->d_blocks, sizeof(float) * h->W * B);
   ALLOC(h->d_reward, sizeof(float) * B);
   ALLOC(h->d_done, B);
   ALLOC(h->d_success, B);
@@ -772,7 +787,7 @@ int pmg_destroy(pmg_handle* h) {
   if (!h) return PMG_OK;
   cudaSetDevice(h->cfg.device);
   cudaFree(h->d_state); cudaFree(h->d_man); cudaFree(h->d_spawn); cudaFree(h->d_mask); cudaFree(h->d_overflow);
-  cudaFree(h->d_action); cudaFree(h->d_obs); cudaFree(h->d_reward); cudaFree(h->d_done); cudaFree(h->d_success);
+  cudaFree(h->d_action); cudaFree(h->d_obs); cudaFree(h->d_blocks); cudaFree(h->d_reward); cudaFree(h->d_done); cudaFree(h->d_success);
   if (h->h_spawn) cudaFreeHost(h->h_spawn);
   for (int k = 0; k < 2; k++) { if (h->h_stage[k]) cudaFreeHost(h->h_stage[k]); if (h->stage_done[k]) cudaEventDestroy(h->stage_done[k]); }
   delete h;
@@ -892,6 +907,26 @@ int pmg_step_host(pmg_handle* h, const float* action_host, float* obs_host, floa
   int rc = pmg_step(h, h->d_action, h->d_obs, h->d_reward, h->d_done, h->d_success, stream);
   if (rc != PMG_OK) return rc;
   CUDA_TRY(cudaMemcpyAsync(obs_host, h->d_obs, sizeof(float) * h->W * B, cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaMemcpyAsync(reward_host, h->d_reward, sizeof(float) * B, cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaMemcpyAsync(done_host, h->d_done, B, cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaMemcpyAsync(success_host, h->d_success, B, cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaStreamSynchronize(st));
+  return PMG_OK;
+}
+
+int pmg_step_host_blocks(pmg_handle* h, const float* action_host, float* blocks_host, float* reward_host, uint8_t* done_host,
+                         uint8_t* success_host, void* stream) {
+  if (!h || !action_host || !blocks_host || !reward_host || !done_host || !success_host) return fail(PMG_ERR_INVALID, "pmg_step_host_blocks: null argument%s");
+  cudaStream_t st = (cudaStream_t)stream;
+  CUDA_TRY(cudaSetDevice(h->cfg.device));
+  const size_t B = h->cfg.batch;
+  CUDA_TRY(cudaMemcpyAsync(h->d_action, action_host, sizeof(float) * h->A * B, cudaMemcpyHostToDevice, st));
+  int rc = pmg_step(h, h->d_action, h->d_obs, h->d_reward, h->d_done, h->d_success, stream);
+  if (rc != PMG_OK) return rc;
+  const int n = (int)(B * h->W);
+  split_rows_kernel<<<(n + 255) / 256, 256, 0, st>>>(h->d_obs, (int)B, h->W, h->O, h->P, h->G, h->d_blocks);
+  h->launches++;
+  CUDA_TRY(cudaMemcpyAsync(blocks_host, h->d_blocks, sizeof(float) * h->W * B, cudaMemcpyDeviceToHost, st));
   CUDA_TRY(cudaMemcpyAsync(reward_host, h->d_reward, sizeof(float) * B, cudaMemcpyDeviceToHost, st));
   CUDA_TRY(cudaMemcpyAsync(done_host, h->d_done, B, cudaMemcpyDeviceToHost, st));
   CUDA_TRY(cudaMemcpyAsync(success_host, h->d_success, B, cudaMemcpyDeviceToHost, st));

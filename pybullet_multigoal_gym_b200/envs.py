@@ -135,6 +135,18 @@ class KukaBulletMGEnv:
         self._h_reward = torch.empty((B,), dtype=torch.float32).pin_memory()
         self._h_done = torch.empty((B,), dtype=torch.uint8).pin_memory()
         self._h_success = torch.empty((B,), dtype=torch.uint8).pin_memory()
+        self._h_blocks = torch.empty((B * self.row_width,), dtype=torch.float32).pin_memory()
+        # numpy views and raw pointers of the pinned staging buffers, built once (env.step is called at kHz rates)
+        self._np_action, self._np_reward = self._h_action.numpy(), self._h_reward.numpy()
+        self._np_done, self._np_success = self._h_done.numpy(), self._h_success.numpy()
+        blocks, off = self._h_blocks.numpy(), 0
+        self._np_blocks = {}
+        for key, dim in (("observation", self.obs_dim), ("policy_state", self.policy_dim),
+                         ("achieved_goal", self.goal_dim), ("desired_goal", self.goal_dim)):
+            self._np_blocks[key] = blocks[off:off + B * dim].reshape(B, dim)
+            off += B * dim
+        self._p_action, self._p_blocks, self._p_reward = _ptr(self._h_action), _ptr(self._h_blocks), _ptr(self._h_reward)
+        self._p_done, self._p_success = _ptr(self._h_done), _ptr(self._h_success)
         self.action_space = spaces.Box(-np.ones([self.action_dim]), np.ones([self.action_dim]))  # kuka.py:109-118
         self.desired_goal = None
         self.seed(seed)
@@ -275,14 +287,18 @@ class KukaBulletMGEnv:
             a = a[:, :3]  # BASELINE config "4-dim action" on a non-grasping task: the grip column is ignored
         if self.check_actions or a.shape != (self.batch, self.action_dim):
             self._check_action(a)
-        self._h_action.numpy()[...] = a
+        self._np_action[...] = a
+        # one C-ABI call: H2D of the actions, the step kernel, D2H of the four observation blocks (contiguous per
+        # key, so handing them out is four memcpy-speed copies instead of strided de-interleaving) and the flags
         with torch.cuda.device(self.device):
-            _lib.check(self._L.pmg_step_host(self._h, _ptr(self._h_action), _ptr(self._h_obs), _ptr(self._h_reward),
-                                             _ptr(self._h_done), _ptr(self._h_success), self._stream()))
-        obs = self._to_host_obs(self._h_obs.numpy())
-        reward = self._h_reward.numpy().copy()
-        done = self._h_done.numpy().astype(bool)
-        ok = self._h_success.numpy().astype(bool)
+            _lib.check(self._L.pmg_step_host_blocks(self._h, self._p_action, self._p_blocks, self._p_reward,
+                                                    self._p_done, self._p_success, self._stream()))
+        obs = {k: v.copy() for k, v in self._np_blocks.items()}
+        if self._squeeze:
+            obs = {k: v[0].astype(np.float64) for k, v in obs.items()}
+        reward = self._np_reward.copy()
+        done = self._np_done.view(np.bool_).copy()
+        ok = self._np_success.view(np.bool_).copy()
         if not self.binary_reward:
             reward = reward.astype(np.float64)
         if self._squeeze:

@@ -140,3 +140,28 @@ def test_ragged_batches_are_independent_of_the_launch_geometry(task):
             assert torch.equal(r, ref[t][1][:b]) and torch.equal(done, ref[t][2][:b])
             assert torch.equal(info["goal_achieved"], ref[t][3]["goal_achieved"][:b])
         assert env.overflow_count == 0
+
+
+def test_both_host_buffer_entry_points_agree():
+    """pmg_step_host (packed rows, the entry INTEGRATION.md's stub binds) and pmg_step_host_blocks (what env.step
+    uses) deliver the same numbers."""
+    import ctypes as C
+    from pybullet_multigoal_gym_b200 import _lib
+    B = 33
+    e1, e2 = _mk("push", B), _mk("push", B)
+    e1.reset()
+    e2.reset()
+    L = _lib.load()
+    rng = np.random.RandomState(1)
+    packed = np.zeros((B, e1.row_width), np.float32)
+    r = np.zeros(B, np.float32)
+    d, s = np.zeros(B, np.uint8), np.zeros(B, np.uint8)
+    vp = lambda a: a.ctypes.data_as(C.c_void_p)
+    for t in range(3):
+        a = rng.uniform(-1, 1, size=(B, 3)).astype(np.float32)
+        _lib.check(L.pmg_step_host(e1._h, vp(a), vp(packed), vp(r), vp(d), vp(s), None))
+        obs, r2, d2, info = e2.step(a)
+        O, P, G = e1.obs_dim, e1.policy_dim, e1.goal_dim
+        assert np.array_equal(obs["observation"], packed[:, :O]) and np.array_equal(obs["policy_state"], packed[:, O:O + P])
+        assert np.array_equal(obs["achieved_goal"], packed[:, O + P:O + P + G]) and np.array_equal(obs["desired_goal"], packed[:, O + P + G:])
+        assert np.array_equal(r2.astype(np.float32), r) and np.array_equal(d2, d.astype(bool)) and np.array_equal(info["goal_achieved"], s.astype(bool))
