@@ -53,12 +53,18 @@ struct Grp {
 #ifdef PMG_EMULATE
   __device__ float shfl(float v, int src) const { return pmg_emu::shfl(v, src); }
   __device__ unsigned ballot(bool p) const { return pmg_emu::ballot(p); }
+  __device__ unsigned reduce_or(unsigned v) const {  // bitwise OR over the octet
+    unsigned r = 0;
+    for (int b = 0; b < 32; b++) if (pmg_emu::ballot(((v >> b) & 1u) != 0)) r |= 1u << b;
+    return r;
+  }
   __device__ void sync() const { pmg_emu::sync(); }
 #else
   unsigned mask;  // the octet's lanes inside the warp
   int shift;      // first lane of the octet
   __device__ __forceinline__ float shfl(float v, int src) const { return __shfl_sync(mask, v, src, GL); }
   __device__ __forceinline__ unsigned ballot(bool p) const { return (__ballot_sync(mask, p) >> shift) & 0xffu; }
+  __device__ __forceinline__ unsigned reduce_or(unsigned v) const { return __reduce_or_sync(mask, v); }  // one REDUX
   __device__ __forceinline__ void sync() const { __syncwarp(mask); }
 #endif
   // value of lane - d (own value when there is no such lane) / lane + d / lane ^ m
@@ -664,9 +670,12 @@ __device__ void substep(const Grp& g, EnvSmem& sm, Lane& L) {
     // btMultiBodyJointLimitConstraint rows, only when violated
     const float p00 = L.q0 - L.lc[LC_LOWER], p01 = L.lc[LC_UPPER] - L.q0, p10 = L.q1 - c_dof_lower[8], p11 = c_dof_upper[8] - L.q1;
     const bool v00 = !(p00 > 0.0f), v01 = !(p01 > 0.0f), v10 = hand && !(p10 > 0.0f), v11 = hand && !(p11 > 0.0f);
-    const unsigned m00 = g.ballot(v00), m01 = g.ballot(v01), m10 = g.ballot(v10), m11 = g.ballot(v11);
+    // the four violation flags of every lane, gathered with one warp reduction (a partial-mask vote per flag
+    // was the most expensive instruction of the contact-free path): lane l owns bits 4l .. 4l+3
+    const unsigned mine = ((v00 ? 1u : 0u) | (v01 ? 2u : 0u) | (v10 ? 4u : 0u) | (v11 ? 8u : 0u)) << (4 * lane);
+    const unsigned viol = g.reduce_or(mine);
     s.lrhs00 = s.lrhs01 = s.lrhs10 = s.lrhs11 = 0.0f;
-    if (m00 | m01 | m10 | m11) {
+    if (viol) {
       s.lrhs00 = ((p00 > SPLIT_IMPULSE_PEN_THRESHOLD ? -p00 * CONTACT_ERP * INV_DT : 0.0f) - L.qd0) * s.dinv0;
       s.lrhs01 = ((p01 > SPLIT_IMPULSE_PEN_THRESHOLD ? -p01 * CONTACT_ERP * INV_DT : 0.0f) + L.qd0) * s.dinv0;
       s.lrhs10 = ((p10 > SPLIT_IMPULSE_PEN_THRESHOLD ? -p10 * CONTACT_ERP * INV_DT : 0.0f) - L.qd1) * s.dinv1;
@@ -674,7 +683,7 @@ __device__ void substep(const Grp& g, EnvSmem& sm, Lane& L) {
 #pragma unroll
       for (int k = 0; k < ND; k++) {
         const int d = nc_dof(k);
-        const unsigned lo = d < 8 ? (m00 >> d) & 1u : (m10 >> 7) & 1u, hi = d < 8 ? (m01 >> d) & 1u : (m11 >> 7) & 1u;
+        const unsigned lo = d < 8 ? (viol >> (4 * d)) & 1u : (viol >> 30) & 1u, hi = d < 8 ? (viol >> (4 * d + 1)) & 1u : (viol >> 31) & 1u;
         lact |= (lo << (2 * k)) | (hi << (2 * k + 1));
       }
     }
