@@ -167,3 +167,21 @@ def test_single_all_gather_of_the_flat_step_output_gloo_world2():
         assert col0 == [0.0, 6.0, 12.0, 18.0, 1000.0, 1006.0, 1012.0, 1018.0]
         assert reward == [0.0] * 4 + [-1.0] * 4
         assert done == [False] * 4 + [True] * 4
+
+
+def test_step_demonstrator_matches_reference_golden():
+    """envs.StepDemonstrator against a trace of the reference's utils/demonstrator.py (tools/gen_demonstrator_golden.py)."""
+    import json
+    from pybullet_multigoal_gym_b200.envs import StepDemonstrator
+    g = json.load(open(os.path.join(ROOT, "tests", "golden", "step_demonstrator.json")))
+    for run in g["runs"]:
+        d = StepDemonstrator(g["demonstrations"], stick_with_final_goal=run["stick_with_final_goal"])
+        for rec in run["trace"]:
+            if rec[0] == "next":
+                assert [d.get_next_goal(), bool(d.final), d.current_goal, d.demon_ind] == rec[1:]
+            elif rec[0] == "manual_reset":
+                d.manual_reset(rec[1])
+                assert [bool(d.final), d.current_goal, d.demon_ind, d.current_final_goal] == rec[2:]
+            else:
+                d.reset_with_the_last_sub_goal_index(rec[1])
+                assert [bool(d.final), d.current_goal, d.demon_ind, d.current_final_goal] == rec[2:]
