@@ -14,6 +14,8 @@ B = 8192
 env = pmg.make_env(task="reach", batch=B, check_actions=False)
 L = _lib.load()
 acts = torch.rand((50, B, 3), device="cuda") * 2 - 1
+if len(sys.argv) > 1 and sys.argv[1] == "down":
+    acts[:, :, 2] = -1.0  # every arm onto the table: all octets run the contact path together
 out = torch.empty((B, env.row_width), device="cuda"); r = torch.empty((B,), device="cuda")
 d = torch.empty((B,), dtype=torch.uint8, device="cuda"); s = torch.empty((B,), dtype=torch.uint8, device="cuda")
 buf = (C.c_ulonglong * 16)()
