@@ -300,6 +300,23 @@ __global__ void __launch_bounds__(32, COOP_MIN_BLOCKS) step_kernel_coop_reach(St
   coop::step_env_reach(g, sm, lane_consts, io, env);
 }
 
+// Lane-cooperative Push / PickAndPlace step: the same octet layout with the block and its manifolds in shared memory
+// (8.4 KB per environment: 6 one-warp blocks per SM, so registers are not the constraint here).
+template <int TASK>
+__global__ void __launch_bounds__(32, 6) step_kernel_coop_block(StepIO io) {
+  extern __shared__ __align__(16) unsigned char coop_smem[];
+  const int lane32 = threadIdx.x & 31, grp = lane32 >> 3;
+  float* lane_consts = reinterpret_cast<float*>(coop_smem);
+  if (lane32 < coop::GL) coop::fill_lane_constants(lane_consts + lane32 * coop::LC_W, lane32);
+  __syncwarp();
+  const int env = blockIdx.x * (32 / coop::GL) + grp;
+  if (env >= io.batch) return;  // a whole octet leaves together
+  coop::Grp g;
+  g.lane = lane32 & (coop::GL - 1); g.shift = grp * coop::GL; g.mask = 0xffu << g.shift;
+  coop::EnvSmemT<1>& sm = reinterpret_cast<coop::EnvSmemT<1>*>(coop_smem + COOP_TABLE_BYTES)[grp];
+  coop::step_env_block<TASK>(g, sm, lane_consts, io, env);
+}
+
 struct ResetIO { StepIO io; const uint8_t* mask; const float* spawn; float tip_init[3]; };
 
 template <int TASK, int NBLK>
@@ -508,6 +525,7 @@ struct pmg_handle {
   bool no_bulk = true;   // TMA staging of the state tile is opt-in (PMG_BULK_COPY=1): measured slower, see DESIGN.md
   bool default_carveout = false;  // PMG_DEFAULT_CARVEOUT=1 keeps the driver's shared-memory carve-out
   bool coop = true;  // Reach: lane-cooperative kernel (PMG_COOP=0 selects the thread-per-env kernel)
+  bool coop_block = true;  // Push / PickAndPlace: lane-cooperative kernel (PMG_COOP_BLOCK=0 selects the thread-per-env kernel)
   bool hinted = false;  // shared-memory carve-out hint of this handle's step kernel has been set on its device
 };
 
@@ -647,6 +665,16 @@ void launch_step(pmg_handle* h, const StepIO& io_in, cudaStream_t st) {
   io.bulk = (h->epw == 32 && h->cfg.batch % 32 == 0 && !h->no_bulk && !h->grip && !h->td && !h->cur) ? 1 : 0;
   io.tile_offset = (int)((stage_floats + 31) / 32 * 32);
   size_t smem = (io.bulk ? io.tile_offset + (size_t)Dims<TASK, NBLK>::STATE * 32 : stage_floats) * sizeof(float);
+  if ((TASK == 1 || TASK == 2) && h->coop_block && !h->jc) {
+    constexpr int EPB = 32 / coop::GL;
+    const size_t smem = COOP_TABLE_BYTES + EPB * sizeof(coop::EnvSmemT<1>);
+    if (!h->hinted) {
+      cudaFuncSetAttribute(step_kernel_coop_block<TASK == 2 ? 2 : 1>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+      h->hinted = true;
+    }
+    step_kernel_coop_block<TASK == 2 ? 2 : 1><<<(h->cfg.batch + EPB - 1) / EPB, 32, smem, st>>>(io);
+    return;
+  }
   // The per-thread scratch lives in L1-cached local memory: ask for the smallest shared-memory
   // carve-out instead of one sized for the register-limited 8 blocks per SM.
   if (!h->hinted && !h->default_carveout) {  // per handle = per device: function attributes are per device
@@ -745,6 +773,7 @@ int pmg_create(const pmg_config* cfg, pmg_handle** out) {
     if (const char* ev = getenv("PMG_BULK_COPY")) h->no_bulk = atoi(ev) == 0;
     if (const char* ev = getenv("PMG_DEFAULT_CARVEOUT")) h->default_carveout = atoi(ev) != 0;
     if (const char* ev = getenv("PMG_COOP")) h->coop = atoi(ev) != 0;
+    if (const char* ev = getenv("PMG_COOP_BLOCK")) h->coop_block = atoi(ev) != 0;
   }
   if (h->cur) {
     h->cur_goals_per = (double)(cfg->num_goals_to_generate / h->nblk);  // floor division (kuka_multi_step_base_env.py:138)

@@ -30,22 +30,31 @@ namespace pmg {
 namespace coop {
 
 constexpr int GL = 8;        // lanes per environment
-constexpr int MAXPTS = 8;    // finger-table contact points: 2 pairs x 4
-constexpr int ROW_W = 24;    // floats per contact row record: J[9] rhs dinv app | MJ[9] denom mu . (16-byte aligned halves)
-constexpr int R_J = 0, R_RHS = 9, R_DINV = 10, R_APP = 11, R_MJ = 12, R_DENOM = 21, R_APP2 = 22;  // impulses are double buffered
+constexpr int R_J = 0, R_RHS = 9, R_DINV = 10, R_MJ = 12, R_DENOM = 21, R_MU = 22;  // contact row record, robot part
+constexpr int R_BD = 24, R_BA = 28;  // block part (NBLK > 0): direction d[3] . | lever arm r_B x d [3] has_block
 constexpr int MINV_LD = 12;  // row stride of M^-1 in shared memory
-constexpr int COOP_PAIRS = 2;
 
-static_assert(2 * sizeof(BoxScratch) <= MAXPTS * 3 * ROW_W * sizeof(float), "narrowphase scratch must fit in the contact-row area");
-struct __align__(16) EnvSmem {
+// Shared memory of one environment.  NBLK = 0: Reach (two finger-table pairs, <= 8 contact points);
+// NBLK = 1: Push / PickAndPlace (+ table-block, floor-block, finger-block pairs; <= 16 points are kept, further
+// ones are counted as overflow like the pools of the thread-per-env kernels).
+template <int NBLK>
+struct __align__(16) EnvSmemT {
+  static constexpr int NB = NBLK;
+  static constexpr int NPAIRS = num_pairs(NBLK);                // 2 / 6
+  static constexpr int MAXPTS = NBLK == 0 ? 8 : 16;
+  static constexpr int ROW_W = NBLK == 0 ? 24 : 32;             // floats per contact row record (16-byte aligned thirds)
   float pub[7][8];                  // per arm dof: axis a, v = (p - Pref) x a
   float minv[ND * MINV_LD];         // 9x9, rows padded to 12
-  float man[84];                    // persistent manifolds of the 2 finger-table pairs (2 x 41 words)
+  float man[(NPAIRS * MAN_WORDS + 3) / 4 * 4];  // persistent manifolds (41 words per pair)
   float hand[24];                   // gripper frame for the contact rows: Rg[9] pf1 pf2 Pref ax1 (kept out of registers)
-  float vq[12];                     // joint velocities (row set-up), then PGS delta velocities (contact sweeps)
+  float vq[NBLK == 0 ? 12 : 16];    // joint (+ block) velocities for the row set-up, then the PGS delta velocities
   float rows[MAXPTS * 3][ROW_W];    // contact rows (layout R_* above); narrowphase scratch before they are built
   float app[2][MAXPTS * 3];         // accumulated impulses of the contact rows, double buffered over the PGS iterations
+  float blk[NBLK > 0 ? 24 : 1];     // block: pos[3] quat[4] v[3] w[3] R[9]
+  static_assert(NPAIRS * sizeof(BoxScratch) <= MAXPTS * 3 * ROW_W * sizeof(float), "narrowphase scratch must fit in the contact-row area");
 };
+using EnvSmem = EnvSmemT<0>;
+constexpr int BK_POS = 0, BK_QUAT = 3, BK_V = 7, BK_W = 10, BK_R = 13;
 
 // ---- the group (octet) interface ---------------------------------------------------------------
 struct Grp {
@@ -258,7 +267,8 @@ __device__ __forceinline__ void motor_row(const Grp& g, SolverLane& s, const flo
 }
 
 // limit row in slot s (visit position s>>1, side s&1); data-dependent => dynamic dof, M^-1 from shared memory
-__device__ __forceinline__ void limit_row(const Grp& g, SolverLane& s, const EnvSmem& sm, int slot_id, int dof0) {
+template <class SM>
+__device__ __forceinline__ void limit_row(const Grp& g, SolverLane& s, const SM& sm, int slot_id, int dof0) {
   const int d = c_nc_order[ND + (slot_id >> 1)];
   const bool side = (slot_id & 1) != 0, slot1 = d == 8;
   const int owner = d < 8 ? d : 7;
@@ -307,7 +317,8 @@ __device__ __forceinline__ void finger_limit_row(const Grp& g, SolverLane& s, co
   s.dqd1 += A1[DOF] * sdl;
 }
 
-__device__ __forceinline__ void limit_rows(const Grp& g, SolverLane& s, const EnvSmem& sm, unsigned lact, bool forward, int dof0, const float* A0, const float* A1) {
+template <class SM>
+__device__ __forceinline__ void limit_rows(const Grp& g, SolverLane& s, const SM& sm, unsigned lact, bool forward, int dof0, const float* A0, const float* A1) {
   if ((lact & ~FINGER_LIMIT_BITS) == 0u) {
     const unsigned f = lact >> (2 * K_F1);
     if (forward) {
@@ -389,6 +400,82 @@ __device__ __noinline__ void contact_row_setup(EnvSmem& sm, int c, int n0) {
   }
 }
 
+// Row set-up of the one-block tasks: lane c (and again lane c for point c + 8) builds the three rows of cached
+// point c.  Pairs in manifold order (pmg_sim.cuh pair_info<1>): finger1-table, finger2-table, table-block,
+// floor-block, finger1-block, finger2-block; body A is a finger (robot end: J over the 9 dofs) or a static box
+// (no end), body B is the table (no end) or the block (end: d and r_B x d).
+template <class SM>
+__device__ __noinline__ void contact_row_setup_blk(SM& sm, int c) {
+  // which pair / which point of it
+  int k = 0, i = c;
+#pragma unroll 1
+  for (; k < SM::NPAIRS; k++) {
+    const int n = __float_as_int(sm.man[k * MAN_WORDS]);
+    if (i < n) break;
+    i -= n;
+  }
+  const PairInfo pi = pair_info<SM::NB>(k);
+  const bool robotA = pi.ka == G_FINGER1 || pi.ka == G_FINGER2, blockB = pi.kb == G_BLOCK;
+  const float* hd = sm.hand;
+  M3 Rg;
+  Rg.r0 = v3(hd[0], hd[1], hd[2]); Rg.r1 = v3(hd[3], hd[4], hd[5]); Rg.r2 = v3(hd[6], hd[7], hd[8]);
+  const V3 pf1 = v3(hd[9], hd[10], hd[11]), pf2 = v3(hd[12], hd[13], hd[14]), Pref = v3(hd[15], hd[16], hd[17]);
+  const V3 ax1 = v3(hd[18], hd[19], hd[20]), ax2 = -ax1;
+  const float* bk = sm.blk;
+  const float* mp = sm.man + k * MAN_WORDS + 1 + 10 * i;
+  const V3 lA = v3(mp[0], mp[1], mp[2]), lB = v3(mp[3], mp[4], mp[5]), nB = v3(mp[6], mp[7], mp[8]);
+  const float dist = mp[9];
+  // contact point on A relative to Pref (robot end) and on B relative to the block centre (block end)
+  const V3 wr = robotA ? mul(Rg, lA) + (pi.ka == G_FINGER1 ? pf1 : pf2) - Pref : v3(0, 0, 0);
+  M3 Rb;
+  Rb.r0 = v3(bk[BK_R], bk[BK_R + 1], bk[BK_R + 2]); Rb.r1 = v3(bk[BK_R + 3], bk[BK_R + 4], bk[BK_R + 5]); Rb.r2 = v3(bk[BK_R + 6], bk[BK_R + 7], bk[BK_R + 8]);
+  const V3 rB = blockB ? mul(Rb, lB) : v3(0, 0, 0);
+  const V3 bv = v3(bk[BK_V], bk[BK_V + 1], bk[BK_V + 2]), bw = v3(bk[BK_W], bk[BK_W + 1], bk[BK_W + 2]);
+  V3 t1, t2;
+  plane_space(nB, t1, t2);
+  const float mu = geom_friction(pi.ka) * geom_friction(pi.kb);
+#pragma unroll 1
+  for (int kk = 0; kk < 3; kk++) {
+    const V3 d = kk == 0 ? nB : (kk == 1 ? t1 : t2);
+    const V3 m = cross(wr, d);
+    float J[ND];  // statically indexed everywhere below: stays in registers
+#pragma unroll
+    for (int j = 0; j < 7; j++) {
+      const float4 p0 = *reinterpret_cast<const float4*>(sm.pub[j]);
+      const float2 p1 = *reinterpret_cast<const float2*>(sm.pub[j] + 4);
+      J[j] = robotA ? p0.x * m.x + p0.y * m.y + p0.z * m.z + p0.w * d.x + p1.x * d.y + p1.y * d.z : 0.0f;
+    }
+    J[7] = pi.ka == G_FINGER1 ? dot(d, ax1) : 0.0f;
+    J[8] = pi.ka == G_FINGER2 ? dot(d, ax2) : 0.0f;
+    float* row = sm.rows[c * 3 + kk];
+    const V3 ang = cross(rB, d);
+    float denom = blockB ? BLOCK_INV_MASS + BLOCK_INV_INERTIA * dot(ang, ang) : 0.0f;
+    float rel_vel = blockB ? -(dot(d, bv) + dot(ang, bw)) : 0.0f;
+#pragma unroll
+    for (int j = 0; j < ND; j++) { row[R_J + j] = J[j]; rel_vel += J[j] * sm.vq[j]; }
+#pragma unroll 1
+    for (int r = 0; r < ND; r++) {  // M^-1 J^T, one row of M^-1 (three 16-byte loads) per iteration
+      const float4* mr = reinterpret_cast<const float4*>(sm.minv + r * MINV_LD);
+      const float4 m0 = mr[0], m1 = mr[1], m2 = mr[2];
+      const float acc = (m0.x * J[0] + m0.y * J[1] + m0.z * J[2]) + (m0.w * J[3] + m1.x * J[4] + m1.y * J[5]) + (m1.z * J[6] + m1.w * J[7] + m2.x * J[8]);
+      row[R_MJ + r] = acc;
+      denom += row[R_J + r] * acc;
+    }
+    const float dinv = 1.0f / denom;
+    float rhs;
+    if (kk == 0) {
+      const float pen = dist + LINEAR_SLOP;
+      float pos_err = 0.0f, vel_err = -rel_vel;
+      if (pen > 0.0f) vel_err -= pen * INV_DT; else pos_err = -pen * CONTACT_ERP * INV_DT;
+      rhs = (pos_err + vel_err) * dinv;
+    } else rhs = -rel_vel * dinv;
+    row[R_RHS] = rhs; row[R_DINV] = dinv; row[R_DENOM] = denom; row[R_MU] = mu;
+    row[R_BD] = d.x; row[R_BD + 1] = d.y; row[R_BD + 2] = d.z; row[R_BD + 3] = 0.0f;
+    row[R_BA] = ang.x; row[R_BA + 1] = ang.y; row[R_BA + 2] = ang.z; row[R_BA + 3] = blockB ? 1.0f : 0.0f;
+    sm.app[0][c * 3 + kk] = 0.0f;
+  }
+}
+
 // One contact row as six 16-byte shared-memory loads: [J0..J8 rhs dinv app] [MJ0..MJ8 denom app2 .]
 struct RowVec { float4 a, b, c; };
 __device__ __forceinline__ RowVec load3(const float* p) {
@@ -409,31 +496,56 @@ __device__ __forceinline__ void row_axpy(const RowVec& v, float s, float* dq) {
 // this path, which is usually executed by one octet of a warp while the others wait.
 // Out of line on purpose: it keeps this (rarely executed) code away from the instruction stream of the
 // contact-free solver loop.  Delta velocities come in and go out through sm.vq.
-__device__ __noinline__ float contact_sweep(Grp g, EnvSmem& sm, int nrow_it) {  // nrow | (iteration parity << 8)
+// Block end point of a contact row (NBLK > 0): the block is always body B of its pairs, so it sees the
+// impulse with the opposite sign; the cubes have isotropic inertia, so M^-1 J^T of the block end is J scaled by
+// 1/m (linear) and 1/I (angular) and needs no storage (as in the thread-per-env kernels).
+struct BlkVec { float4 d, a; };  // d = (dx dy dz .), a = (r_B x d, has_block)
+__device__ __forceinline__ BlkVec load_blk(const float* row) {
+  const float4* q = reinterpret_cast<const float4*>(row + R_BD);
+  BlkVec r; r.d = q[0]; r.a = q[1];
+  return r;
+}
+__device__ __forceinline__ float blk_dot(const BlkVec& b, const float* dv) {  // dv = block delta (lin[3], ang[3])
+  return b.a.w * ((b.d.x * dv[0] + b.d.y * dv[1] + b.d.z * dv[2]) + (b.a.x * dv[3] + b.a.y * dv[4] + b.a.z * dv[5]));
+}
+__device__ __forceinline__ void blk_axpy(const BlkVec& b, float lam, float* dv) {
+  const float lm = lam * b.a.w * BLOCK_INV_MASS, li = lam * b.a.w * BLOCK_INV_INERTIA;
+  dv[0] -= lm * b.d.x; dv[1] -= lm * b.d.y; dv[2] -= lm * b.d.z;
+  dv[3] -= li * b.a.x; dv[4] -= li * b.a.y; dv[5] -= li * b.a.z;
+}
+
+template <class SM>
+__device__ __noinline__ float contact_sweep(Grp g, SM& sm, int nrow_it) {  // nrow | (iteration parity << 8)
+  constexpr bool BLK = SM::NB > 0;  // rows may have a block end point: the vector gains the block's delta velocities
   const int nrow = nrow_it & 0xff, it = nrow_it >> 8;
   // The accumulated impulses are double buffered (read buffer / write buffer swap every iteration, every lane
   // stores the same value), so no lane waits for another inside the row loops.
   const float* app_rd = sm.app[it & 1];
   float* app_wr = sm.app[(it & 1) ^ 1];
-  float dq[ND];
+  float dq[ND], dv[6];
 #pragma unroll
   for (int j = 0; j < ND; j++) dq[j] = sm.vq[j];
+#pragma unroll
+  for (int j = 0; j < 6; j++) dv[j] = BLK ? sm.vq[(BLK ? ND : 0) + j] : 0.0f;
   float cres = 0.0f;
 #pragma unroll 1
   for (int c = 0; c < nrow; c++) {
     float* row = sm.rows[c * 3];
     const RowVec j = load3(row + R_J), mj = load3(row + R_MJ);
     const float app = app_rd[c * 3];
-    float dl = j.c.y - row_dot(j, dq) * j.c.z;   // rhs - (J . dq) dinv
+    float v = row_dot(j, dq);
+    BlkVec bk;
+    if (BLK) { bk = load_blk(row); v -= blk_dot(bk, dv); }
+    float dl = j.c.y - v * j.c.z;   // rhs - (J . dq) dinv
     const float sum = fminf(fmaxf(app + dl, 0.0f), 1e10f);
     dl = sum - app;
     row_axpy(mj, dl, dq);
+    if (BLK) blk_axpy(bk, dl, dv);
     const float rr = dl * mj.c.y;                // denom
     cres = fmaxf(cres, rr * rr);
     app_wr[c * 3] = sum;
   }
   g.sync();  // the new normal impulses bound the friction rows
-  const float mu = (float)PMG_FINGER_FRICTION * (float)PMG_TABLE_FRICTION;
 #pragma unroll 1
   for (int c = 0; c < nrow; c++) {  // implicit friction cone: both tangent rows of a point together
     float* ra = sm.rows[c * 3 + 1];
@@ -444,8 +556,12 @@ __device__ __noinline__ float contact_sweep(Grp g, EnvSmem& sm, int nrow_it) {  
     float sA = appA, sB = appB;
     if (total > 0.0f) {
       const RowVec mja = load3(ra + R_MJ), mjb = load3(rb + R_MJ);
+      const float mu = BLK ? mja.c.z : (float)PMG_FINGER_FRICTION * (float)PMG_TABLE_FRICTION;  // R_MU
       const float lim = mu * total;
-      float dA = ja.c.y - row_dot(ja, dq) * ja.c.z, dB = jb.c.y - row_dot(jb, dq) * jb.c.z;
+      float vA = row_dot(ja, dq), vB = row_dot(jb, dq);
+      BlkVec bka, bkb;
+      if (BLK) { bka = load_blk(ra); bkb = load_blk(rb); vA -= blk_dot(bka, dv); vB -= blk_dot(bkb, dv); }
+      float dA = ja.c.y - vA * ja.c.z, dB = jb.c.y - vB * jb.c.z;
       sA = appA + dA; sB = appB + dB;
       const float s2 = sA * sA + sB * sB;
       if (s2 >= lim * lim) {
@@ -458,6 +574,7 @@ __device__ __noinline__ float contact_sweep(Grp g, EnvSmem& sm, int nrow_it) {  
       }
       row_axpy(mja, dA, dq);
       row_axpy(mjb, dB, dq);
+      if (BLK) { blk_axpy(bka, dA, dv); blk_axpy(bkb, dB, dv); }
       const float r1_ = dA * mja.c.y, r2_ = dB * mjb.c.y;
       cres = fmaxf(cres, fmaxf(r1_ * r1_, r2_ * r2_));
     }
@@ -467,6 +584,10 @@ __device__ __noinline__ float contact_sweep(Grp g, EnvSmem& sm, int nrow_it) {  
   if (g.lane == 0) {
 #pragma unroll
     for (int j = 0; j < ND; j++) sm.vq[j] = dq[j];
+    if (BLK) {
+#pragma unroll
+      for (int j = 0; j < 6; j++) sm.vq[(BLK ? ND : 0) + j] = dv[j];
+    }
   }
   g.sync();
   return cres;
@@ -484,13 +605,21 @@ __device__ __noinline__ float contact_sweep(Grp g, EnvSmem& sm, int nrow_it) {  
 #endif
 
 // ---- one 2 ms substep ---------------------------------------------------------------------------------
-__device__ void substep(const Grp& g, EnvSmem& sm, Lane& L) {
+template <class SM>
+__device__ void substep(const Grp& g, SM& sm, Lane& L) {
+  constexpr bool BLK = SM::NB > 0;
   PMG_T(t_begin);
 #ifdef PMG_COOP_TIMING
   long long t_sweeps = 0;
 #endif
   const int lane = g.lane;
   const bool arm = lane < 7, hand = lane == 7;
+  if (BLK && lane == 0) {  // the block's orientation matrix for the narrowphase and the rows (visible after the sync below)
+    float* bk = sm.blk;
+    const M3 Rb = quat_to_m3(bk[BK_QUAT], bk[BK_QUAT + 1], bk[BK_QUAT + 2], bk[BK_QUAT + 3]);
+    bk[BK_R] = Rb.r0.x; bk[BK_R + 1] = Rb.r0.y; bk[BK_R + 2] = Rb.r0.z; bk[BK_R + 3] = Rb.r1.x; bk[BK_R + 4] = Rb.r1.y;
+    bk[BK_R + 5] = Rb.r1.z; bk[BK_R + 6] = Rb.r2.x; bk[BK_R + 7] = Rb.r2.y; bk[BK_R + 8] = Rb.r2.z;
+  }
   // 1. link frames (scan), joint axes
   M3 R; V3 p;
   chain_fk(g, L, arm ? L.q0 : 0.0f, R, p);
@@ -569,13 +698,31 @@ __device__ void substep(const Grp& g, EnvSmem& sm, Lane& L) {
   }
   // collision detection of the two finger-table pairs: lane k runs pair k on the shared-memory manifold
   PMG_T(t_col0);
-  if (lane < COOP_PAIRS) {
+  if (BLK) g.sync();  // block pose of this substep (integration of the last one, orientation matrix above)
+  if (lane < SM::NPAIRS) {
     ManRef mr; mr.man = sm.man; mr.stride = 1;
     const float tc[3] = PMG_TABLE_CENTER, th[3] = PMG_TABLE_HALF, fh[3] = PMG_FINGER_HALF;
     // the narrowphase work arrays live in the (not yet used) contact-row area of shared memory
-    BoxScratch& scr = *reinterpret_cast<BoxScratch*>(&sm.rows[lane * (MAXPTS * 3 / 2)][0]);
-    collide_pair(mr, lane, lane == 0 ? pf1 : pf2, Rg, v3(fh[0], fh[1], fh[2]), v3(0, 0, 0), false,
-                 v3(tc[0], tc[1], tc[2]), m3_identity(), v3(th[0], th[1], th[2]), geom_anchor(G_TABLE), scr);
+    constexpr int SCR_STRIDE = SM::MAXPTS * 3 * SM::ROW_W / SM::NPAIRS / 4 * 4;
+    BoxScratch& scr = *reinterpret_cast<BoxScratch*>(&sm.rows[0][0] + lane * SCR_STRIDE);
+    if constexpr (!BLK) {
+      collide_pair(mr, lane, lane == 0 ? pf1 : pf2, Rg, v3(fh[0], fh[1], fh[2]), v3(0, 0, 0), false,
+                   v3(tc[0], tc[1], tc[2]), m3_identity(), v3(th[0], th[1], th[2]), geom_anchor(G_TABLE), scr);
+    } else {
+      // lane k runs pair k: finger1-table, finger2-table, table-block, floor-block, finger1-block, finger2-block
+      const PairInfo pi = pair_info<SM::NB>(lane);
+      const float fc[3] = PMG_FLOOR_CENTER;
+      const float* bk = sm.blk;
+      const bool fingerA = pi.ka == G_FINGER1 || pi.ka == G_FINGER2;
+      V3 pa = fingerA ? (pi.ka == G_FINGER1 ? pf1 : pf2) : (pi.ka == G_TABLE ? v3(tc[0], tc[1], tc[2]) : v3(fc[0], fc[1], fc[2]));
+      M3 Ra = fingerA ? Rg : m3_identity();
+      V3 pb = pi.kb == G_TABLE ? v3(tc[0], tc[1], tc[2]) : v3(bk[BK_POS], bk[BK_POS + 1], bk[BK_POS + 2]);
+      M3 Rb = m3_identity();
+      if (pi.kb == G_BLOCK) {
+        Rb.r0 = v3(bk[BK_R], bk[BK_R + 1], bk[BK_R + 2]); Rb.r1 = v3(bk[BK_R + 3], bk[BK_R + 4], bk[BK_R + 5]); Rb.r2 = v3(bk[BK_R + 6], bk[BK_R + 7], bk[BK_R + 8]);
+      }
+      collide_pair(mr, lane, pa, Ra, geom_half(pi.ka), geom_anchor(pi.ka), geom_static(pi.ka), pb, Rb, geom_half(pi.kb), geom_anchor(pi.kb), scr);
+    }
   }
   PMG_T(t_col1);
   // 4. subtree wrenches and composite inertias: suffix sums over the chain
@@ -655,7 +802,17 @@ __device__ void substep(const Grp& g, EnvSmem& sm, Lane& L) {
   }
   sm.vq[L.dof0] = L.qd0;
   if (hand) sm.vq[8] = L.qd1;
-  g.sync();  // minv, vq and the manifolds are visible to the whole octet
+  if (BLK && lane == 0) {  // free cube: gravity + Bullet's velocity damping; isotropic inertia => no gyro term
+    float* bk = sm.blk;
+    V3 bv = v3(bk[BK_V], bk[BK_V + 1], bk[BK_V + 2]), bw = v3(bk[BK_W], bk[BK_W + 1], bk[BK_W + 2]);
+    const float kl = LINK_DAMPING + LINK_DAMPING * norm(bv), ka = LINK_DAMPING + LINK_DAMPING * norm(bw);
+    bv += DT * (v3(0, 0, -GRAVITY) - kl * bv);
+    bw -= (DT * ka) * bw;
+    bk[BK_V] = bv.x; bk[BK_V + 1] = bv.y; bk[BK_V + 2] = bv.z; bk[BK_W] = bw.x; bk[BK_W + 1] = bw.y; bk[BK_W + 2] = bw.z;
+#pragma unroll
+    for (int j = 0; j < 6; j++) sm.vq[(BLK ? ND : 0) + j] = 0.0f;  // the block's PGS delta velocities
+  }
+  g.sync();  // minv, vq, the block velocity and the manifolds are visible to the whole octet
   // 8. constraint rows
   SolverLane s;
   unsigned lact = 0;
@@ -692,10 +849,22 @@ __device__ void substep(const Grp& g, EnvSmem& sm, Lane& L) {
   }
   // contact rows: one normal + two tangents per cached manifold point, point c set up by lane c
   const int n0 = __float_as_int(sm.man[0]);
-  const int nrow = n0 + __float_as_int(sm.man[MAN_WORDS]);
+  int nrow = n0 + __float_as_int(sm.man[MAN_WORDS]);  // number of cached contact points (3 rows each)
+  if (BLK) {
+#pragma unroll
+    for (int k = 2; k < SM::NPAIRS; k++) nrow += __float_as_int(sm.man[k * MAN_WORDS]);
+    if (nrow > SM::MAXPTS) {  // points beyond the pool are dropped and counted (pmg_overflow_count)
+      if (lane == 0) sm.blk[23] += (float)(nrow - SM::MAXPTS);
+      nrow = SM::MAXPTS;
+    }
+  }
   PMG_T(t_set0);
   if (nrow) {
-    if (lane < nrow) contact_row_setup(sm, lane, n0);
+    if constexpr (!BLK) {
+      if (lane < nrow) contact_row_setup(sm, lane, n0);
+    } else {
+      for (int c = lane; c < nrow; c += GL) contact_row_setup_blk(sm, c);
+    }
     g.sync();
   }
   PMG_T(t_set1);
@@ -736,6 +905,25 @@ __device__ void substep(const Grp& g, EnvSmem& sm, Lane& L) {
   L.qd1 = hand ? fminf(fmaxf(L.qd1 + s.dqd1, -MAX_COORD_VEL), MAX_COORD_VEL) : 0.0f;
   L.q0 += L.qd0 * DT;
   L.q1 += L.qd1 * DT;
+  if (BLK && lane == 0) {  // block: add the solver's delta velocities, integrate (exponential map for the orientation)
+    float* bk = sm.blk;
+    const float* dv = sm.vq + (BLK ? ND : 0);
+    V3 bv = v3(bk[BK_V] + dv[0], bk[BK_V + 1] + dv[1], bk[BK_V + 2] + dv[2]);
+    V3 bw = v3(bk[BK_W] + dv[3], bk[BK_W + 1] + dv[4], bk[BK_W + 2] + dv[5]);
+    bk[BK_V] = bv.x; bk[BK_V + 1] = bv.y; bk[BK_V + 2] = bv.z; bk[BK_W] = bw.x; bk[BK_W + 1] = bw.y; bk[BK_W + 2] = bw.z;
+    bk[BK_POS] += DT * bv.x; bk[BK_POS + 1] += DT * bv.y; bk[BK_POS + 2] += DT * bv.z;
+    float w = norm(bw);
+    if (w * DT > 0.25f * PI_F) w = 0.25f * PI_F / DT;  // ANGULAR_MOTION_THRESHOLD
+    const float sn = w < 0.001f ? 0.5f * DT - DT * DT * DT * 0.020833333333f * w * w : sinf(0.5f * w * DT) / w;
+    const float ax = bw.x * sn, ay = bw.y * sn, az = bw.z * sn, aw = cosf(0.5f * w * DT);
+    const float bx = bk[BK_QUAT], by = bk[BK_QUAT + 1], bz = bk[BK_QUAT + 2], bw_ = bk[BK_QUAT + 3];
+    const float nx = aw * bx + ax * bw_ + ay * bz - az * by;
+    const float ny = aw * by + ay * bw_ + az * bx - ax * bz;
+    const float nz = aw * bz + az * bw_ + ax * by - ay * bx;
+    const float nw = aw * bw_ - ax * bx - ay * by - az * bz;
+    const float inv = 1.0f / sqrtf(nx * nx + ny * ny + nz * nz + nw * nw);
+    bk[BK_QUAT] = nx * inv; bk[BK_QUAT + 1] = ny * inv; bk[BK_QUAT + 2] = nz * inv; bk[BK_QUAT + 3] = nw * inv;
+  }
 #ifdef PMG_COOP_TIMING
   if (nrow) {
     PMG_TADD(0, clock64() - t_begin); PMG_TADD(1, t_col1 - t_col0); PMG_TADD(2, t_set1 - t_set0); PMG_TADD(3, t_sweeps); PMG_TADD(4, 1);
@@ -760,7 +948,7 @@ __device__ void step_env_reach(const Grp& g, EnvSmem& sm, const float* lane_cons
   L.q1 = hand ? s[(ST_Q + 8) * B] : 0.0f; L.qd1 = hand ? s[(ST_QD + 8) * B] : 0.0f;
   L.mt1 = hand ? s[(ST_MT + 8) * B] : 0.0f; L.mi1 = hand ? s[(ST_MI + 8) * B] : 0.0f;
   L.dtau0 = L.dtau1 = 0.0f;
-  for (int w = lane; w < COOP_PAIRS * MAN_WORDS; w += GL) sm.man[w] = io.manifold[(size_t)w * B + env];
+  for (int w = lane; w < EnvSmem::NPAIRS * MAN_WORDS; w += GL) sm.man[w] = io.manifold[(size_t)w * B + env];
   // ---- Kuka.apply_action (kuka.py:167-222) ----
   const float lo[3] = {-0.67f, -0.20f, 0.175f}, hi[3] = {-0.37f, 0.20f, 0.55f};  // kuka.py:40-41
   float ee[3];
@@ -784,7 +972,7 @@ __device__ void step_env_reach(const Grp& g, EnvSmem& sm, const float* lane_cons
   s[(ST_Q + lane) * B] = L.q0; s[(ST_QD + lane) * B] = L.qd0; s[(ST_MT + lane) * B] = L.mt0; s[(ST_MI + lane) * B] = L.mi0;
   if (hand) { s[(ST_Q + 8) * B] = L.q1; s[(ST_QD + 8) * B] = L.qd1; s[(ST_MT + 8) * B] = L.mt1; s[(ST_MI + 8) * B] = L.mi1; }
   g.sync();
-  for (int w = lane; w < COOP_PAIRS * MAN_WORDS; w += GL) io.manifold[(size_t)w * B + env] = sm.man[w];
+  for (int w = lane; w < EnvSmem::NPAIRS * MAN_WORDS; w += GL) io.manifold[(size_t)w * B + env] = sm.man[w];
   if (lane == PMG_BODY_LINK7) {
     const float t[3] = PMG_TIP_OFFSET;
     const V3 tip = p + mul(R, v3(t[0], t[1], t[2]));
@@ -794,6 +982,110 @@ __device__ void step_env_reach(const Grp& g, EnvSmem& sm, const float* lane_cons
     row[0] = row[3] = row[6] = tip.x; row[1] = row[4] = row[7] = tip.y; row[2] = row[5] = row[8] = tip.z;
     row[9] = g0; row[10] = g1; row[11] = g2;
     const float dx = tip.x - g0, dy = tip.y - g1, dz = tip.z - g2;
+    const float dist = sqrtf(dx * dx + dy * dy + dz * dz);
+#pragma unroll
+    for (int k = 0; k < 3; k++) s[(ST_EE + k) * B] = ee[k];
+    float* el = s + (size_t)(D::STATE - 1) * B;
+    const int elapsed = (int)(*el) + 1;
+    *el = (float)elapsed;
+    const bool na = dist > io.thr;
+    io.reward[env] = io.binary ? -(na ? 1.0f : 0.0f) : -dist;
+    io.success[env] = na ? 0 : 1;
+    io.done[env] = elapsed >= io.max_steps ? 1 : 0;
+  }
+}
+
+// ---- one env.step() of a one-block environment: Push (TASK 1) / PickAndPlace (TASK 2) -----------------------
+// Same structure as step_env_reach; the block's state and its four extra manifolds live in shared memory for
+// the whole step.  Cartesian control only (joint control runs on the thread-per-env kernel).
+template <int TASK>
+__device__ void step_env_block(const Grp& g, EnvSmemT<1>& sm, const float* lane_consts, const StepIO& io, int env) {
+  using SM = EnvSmemT<1>;
+  using D = Dims<TASK, 1>;
+  const int lane = g.lane;
+  const bool arm = lane < 7, hand = lane == 7;
+  const size_t B = io.batch;
+  float* s = io.state + env;
+  Lane L;
+  L.lc = lane_consts + lane * LC_W;
+  L.dof0 = lane;
+  L.q0 = s[(ST_Q + lane) * B]; L.qd0 = s[(ST_QD + lane) * B]; L.mt0 = s[(ST_MT + lane) * B]; L.mi0 = s[(ST_MI + lane) * B];
+  L.q1 = hand ? s[(ST_Q + 8) * B] : 0.0f; L.qd1 = hand ? s[(ST_QD + 8) * B] : 0.0f;
+  L.mt1 = hand ? s[(ST_MT + 8) * B] : 0.0f; L.mi1 = hand ? s[(ST_MI + 8) * B] : 0.0f;
+  L.dtau0 = L.dtau1 = 0.0f;
+  for (int w = lane; w < SM::NPAIRS * MAN_WORDS; w += GL) sm.man[w] = io.manifold[(size_t)w * B + env];
+  for (int w = lane; w < 13; w += GL) sm.blk[w] = s[(size_t)(ST_BLK + w) * B];
+  if (lane == 0) sm.blk[23] = 0.0f;  // contact points dropped because the row pool was full
+  // ---- Kuka.apply_action (kuka.py:167-222) ----
+  const float* act = io.action + (size_t)env * D::A;
+  if (TASK == 2 && hand) {  // grasping: the last action column drives both jaws (kuka.py:169-172)
+    const float grip = (act[3] + 1.0f) * (GRIPPER_ABS_LIMIT / 2);
+    L.mt0 = L.mt1 = grip; L.mi0 = L.mi1 = FINGER_FORCE * OUTER_DT;
+  }
+  const float lo[3] = {-0.67f, -0.20f, 0.175f}, hi[3] = {-0.37f, 0.20f, 0.55f};  // kuka.py:40-41
+  float ee[3];
+#pragma unroll
+  for (int k = 0; k < 3; k++) ee[k] = fminf(fmaxf(s[(ST_EE + k) * B] + act[k] * 0.01f, lo[k]), hi[k]);
+  {
+    const float tq[4] = {0.f, -1.f, 0.f, 0.f};  // kuka.py:42
+    const float qik = inverse_kinematics(g, L, arm ? L.q0 : 0.0f, v3(ee[0], ee[1], ee[2]), tq);
+    if (arm) { L.mt0 = qik; L.mi0 = ARM_FORCE * OUTER_DT; }
+  }
+  g.sync();
+  // ---- 5 x stepSimulation (kuka.py:223-225), each 20 substeps of 2 ms ----
+  for (int call = 0; call < CALLS_PER_ENV_STEP; call++) {
+    L.dtau0 = -L.lc[LC_DAMP] * L.qd0;  // joint damping torque, sampled once per stepSimulation call
+    L.dtau1 = 0.0f;
+    for (int sub = 0; sub < SUBSTEPS_PER_CALL; sub++) substep(g, sm, L);
+  }
+  // ---- observation, reward, flags (kuka.py:227-256, kuka_single_step_base_env.py:193-244) ----
+  M3 R; V3 p;
+  chain_fk(g, L, arm ? L.q0 : 0.0f, R, p);
+  const V3 a = arm ? col(R, 2) : v3(0, 0, 0);
+  const V3 aq = L.qd0 * a;
+  const V3 w = g.scan(aq), wp = w - aq;
+  V3 pprev = g.up(p, 1);
+  if (lane == 0) pprev = v3(0, 0, 0);
+  const V3 vo = g.scan(cross(wp, p - pprev));
+  s[(ST_Q + lane) * B] = L.q0; s[(ST_QD + lane) * B] = L.qd0; s[(ST_MT + lane) * B] = L.mt0; s[(ST_MI + lane) * B] = L.mi0;
+  if (hand) { s[(ST_Q + 8) * B] = L.q1; s[(ST_QD + 8) * B] = L.qd1; s[(ST_MT + 8) * B] = L.mt1; s[(ST_MI + 8) * B] = L.mi1; }
+  g.sync();  // the block state of the last substep
+  for (int wd = lane; wd < SM::NPAIRS * MAN_WORDS; wd += GL) io.manifold[(size_t)wd * B + env] = sm.man[wd];
+  for (int wd = lane; wd < 13; wd += GL) s[(size_t)(ST_BLK + wd) * B] = sm.blk[wd];
+  if (lane == 0 && sm.blk[23] > 0.0f && io.overflow) atomicAdd(io.overflow, (int)sm.blk[23]);
+  // tip pose / velocity from lane 6 (link_7); jaw quantities on lane 7 (gripper base), which writes the row
+  const float t[3] = PMG_TIP_OFFSET;
+  const V3 tip_own = p + mul(R, v3(t[0], t[1], t[2]));
+  const V3 tip = g.shfl(tip_own, PMG_BODY_LINK7);
+  const V3 tv = g.shfl(vo + cross(w, tip_own - p), PMG_BODY_LINK7), tw = g.shfl(w, PMG_BODY_LINK7);
+  if (hand) {
+    float closeness = 0.0f, finger_vel = 0.0f;
+    if (TASK == 2) {
+      const float t1[3] = PMG_TAB1_OFFSET, t2[3] = PMG_TAB2_OFFSET;
+      const V3 ay = col(R, 1);  // R = gripper-base frame on this lane; fingers slide along -/+ its y axis
+      const V3 j1 = v3(c_jxyz[PMG_BODY_FINGER1][0], c_jxyz[PMG_BODY_FINGER1][1], c_jxyz[PMG_BODY_FINGER1][2]);
+      const V3 j2 = v3(c_jxyz[PMG_BODY_FINGER2][0], c_jxyz[PMG_BODY_FINGER2][1], c_jxyz[PMG_BODY_FINGER2][2]);
+      const V3 tab1 = mul(R, j1 + v3(t1[0], t1[1], t1[2])) - L.q0 * ay;   // relative to the gripper-base origin
+      const V3 tab2 = mul(R, j2 + v3(t2[0], t2[1], t2[2])) + L.q1 * ay;
+      closeness = norm(tab1 - tab2);
+      // finger_vel = (v_base - v_tab1).y with v_tab1 = v_base + w x (tab1 - p_base) + qd_finger1 * axis1 (kuka.py:240-242)
+      const V3 rel = cross(w, tab1) - L.qd0 * ay;
+      finger_vel = -rel.y;
+    }
+    const float* bk = sm.blk;
+    const V3 bx = v3(bk[BK_POS], bk[BK_POS + 1], bk[BK_POS + 2]), bv = v3(bk[BK_V], bk[BK_V + 1], bk[BK_V + 2]), bw = v3(bk[BK_W], bk[BK_W + 1], bk[BK_W + 2]);
+    const V3 rel = tip - bx, rv = tv - bv, rw = tw - bw;
+    float* row = io.obs + (size_t)env * D::W;
+    float* obs = row; float* pol = row + D::O; float* ag = pol + D::P; float* dg = ag + D::G;
+    obs[0] = tip.x; obs[1] = tip.y; obs[2] = tip.z; obs[3] = bx.x; obs[4] = bx.y; obs[5] = bx.z; obs[6] = closeness;
+    obs[7] = rel.x; obs[8] = rel.y; obs[9] = rel.z; obs[10] = tv.x; obs[11] = tv.y; obs[12] = tv.z; obs[13] = finger_vel;
+    obs[14] = rv.x; obs[15] = rv.y; obs[16] = rv.z; obs[17] = rw.x; obs[18] = rw.y; obs[19] = rw.z;
+    pol[0] = tip.x; pol[1] = tip.y; pol[2] = tip.z; pol[3] = closeness; pol[4] = rel.x; pol[5] = rel.y; pol[6] = rel.z;
+    ag[0] = bx.x; ag[1] = bx.y; ag[2] = bx.z;
+    const float* goal = io.state + (size_t)(ST_BLK + 13) * B + env;
+    const float g0 = goal[0], g1 = goal[B], g2 = goal[2 * B];
+    dg[0] = g0; dg[1] = g1; dg[2] = g2;
+    const float dx = bx.x - g0, dy = bx.y - g1, dz = bx.z - g2;
     const float dist = sqrtf(dx * dx + dy * dy + dz * dz);
 #pragma unroll
     for (int k = 0; k < 3; k++) s[(ST_EE + k) * B] = ee[k];

@@ -204,3 +204,33 @@ int pmg_emu_thread_substeps(int nblk, float* state, float* manifold, int n_calls
   }
 }
 }
+
+// ---- the one-block cooperative step (Push / PickAndPlace) ------------------------------------------------------
+namespace {
+struct BlkArgs { coop::EnvSmemT<1>* sm; StepIO io; int task; };
+void blk_body(int lane, void* arg) {
+  BlkArgs* a = (BlkArgs*)arg;
+  coop::Grp g; g.lane = lane;
+  if (a->task == 1) coop::step_env_block<1>(g, *a->sm, lane_table(), a->io, 0);
+  else coop::step_env_block<2>(g, *a->sm, lane_table(), a->io, 0);
+}
+}  // namespace
+
+extern "C" {
+// One env.step() of a Push (task 1, 3 action columns) / PickAndPlace (task 2, 4 columns) environment.  state:
+// Dims<TASK,1>::STATE = 63 words of one env; manifold: 6 x 41 words; obs_row: 33 floats.
+int pmg_emu_block_step(int task, float* state, float* manifold, const float* action, float thr, int binary, int max_steps,
+                       float* obs_row, float* reward, uint8_t* done, uint8_t* success) {
+  static coop::EnvSmemT<1> sm;
+  memset(&sm, 0, sizeof sm);
+  BlkArgs a;
+  a.sm = &sm; a.task = task;
+  memset(&a.io, 0, sizeof a.io);
+  a.io.state = state; a.io.manifold = manifold; a.io.batch = 1; a.io.state_words = Dims<1, 1>::STATE;
+  a.io.action = action; a.io.obs = obs_row; a.io.reward = reward; a.io.done = done; a.io.success = success;
+  a.io.thr = thr; a.io.binary = binary; a.io.max_steps = max_steps; a.io.overflow = nullptr; a.io.epw = 4;
+  a.io.grasp = task == 2; a.io.adim = task == 2 ? 4 : 3; a.io.goal_dim = 3; a.io.row_width = 33;
+  return pmg_emu::run_group(blk_body, &a);
+}
+int pmg_emu_block_smem_bytes(void) { return (int)sizeof(coop::EnvSmemT<1>); }
+}

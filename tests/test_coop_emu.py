@@ -128,3 +128,38 @@ def test_thread_per_env_physics_on_host_matches_oracle(emu, task, nb):
             assert np.abs(got[7:10] - want[7:10]).max() < 1e-4           # linear velocity
             assert np.abs(got[10:13] - want[10:13]).max() < 1e-4         # angular velocity
     assert sum(int(man[41 * k:41 * k + 1].view(np.int32)[0]) for k in range(npairs)) >= 4 * nb  # blocks rest on 4 points
+
+
+@pytest.mark.parametrize("task,tid,adim,nsteps", [("push", 1, 3, 16), ("pick_and_place", 2, 4, 22)])
+def test_cooperative_block_step_matches_oracle(emu, task, tid, adim, nsteps):
+    """The lane-cooperative Push / PickAndPlace step (block + six manifolds in shared memory, rows with a block end
+    point, lanes over pairs for the narrowphase and over contact points for the row set-up) against the oracle,
+    one env.step at a time from the oracle's fp32-rounded state (contact-rich rollouts are chaotic in open loop):
+    scripted side push / descend-and-grasp, every position entry of the packed row within 1e-4."""
+    assert 6 * (emu.pmg_emu_table_bytes() + 4 * emu.pmg_emu_block_smem_bytes() + 1024) <= 227 * 1024  # 6 blocks per SM
+    o = O.OracleEnv(task, seed=1, binary_reward=False)
+    o.reset()
+    o.reset()
+    obs, rew = np.zeros(33, np.float32), np.zeros(1, np.float32)
+    dn, su = np.zeros(1, np.uint8), np.zeros(1, np.uint8)
+    worst, touched = 0.0, 0
+    for t in range(nsteps):
+        st = o.get_state().astype(np.float32)
+        o.set_state(st.astype(np.float64))     # both sides start the step from the same state, contact caches empty
+        man = np.zeros(6 * 41, np.float32)
+        tip = o.link_state(0)[:3]
+        a = np.zeros(adim, np.float32)
+        a[:3] = np.clip((st[46:49] + np.array([0.0, 0.0, 0.0 if (task == "push" or t > 10) else 0.07]) - tip) / 0.01, -1, 1)
+        if adim == 4:
+            a[3] = -1.0 if t < 16 else 1.0
+        ro, rr, rd, ri = o.step(a.astype(np.float64))
+        rc = emu.pmg_emu_block_step(tid, _f(st), _f(man), _f(a), C.c_float(0.05), 0, 50, _f(obs), _f(rew),
+                                    dn.ctypes.data_as(U8), su.ctypes.data_as(U8))
+        assert rc == 0, "divergent collective in the cooperative kernel"
+        want = np.concatenate([ro[k] for k in ("observation", "policy_state", "achieved_goal", "desired_goal")])
+        pos = np.r_[0:10, 20:33]               # everything but the velocity entries of the observation
+        worst = max(worst, float(np.abs(obs - want)[pos].max()))
+        assert abs(float(rew[0]) - rr) < 1e-4 and bool(dn[0]) == rd
+        touched = max(touched, sum(int(man[41 * k:41 * k + 1].view(np.int32)[0]) for k in (4, 5)))
+    assert worst < 1e-4, worst
+    assert touched > 0                         # the jaws did reach the block (finger-block manifolds in use)
