@@ -301,9 +301,9 @@ __global__ void __launch_bounds__(32, COOP_MIN_BLOCKS) step_kernel_coop_reach(St
 }
 
 // Lane-cooperative Push / PickAndPlace step: the same octet layout with the block and its manifolds in shared memory
-// (8.4 KB per environment: 6 one-warp blocks per SM, so registers are not the constraint here).
+// (11.6 KB per environment, 4 one-warp blocks per SM: shared memory, not registers, limits residency here).
 template <int TASK>
-__global__ void __launch_bounds__(32, 6) step_kernel_coop_block(StepIO io) {
+__global__ void __launch_bounds__(32, 4) step_kernel_coop_block(StepIO io) {
   extern __shared__ __align__(16) unsigned char coop_smem[];
   const int lane32 = threadIdx.x & 31, grp = lane32 >> 3;
   float* lane_consts = reinterpret_cast<float*>(coop_smem);

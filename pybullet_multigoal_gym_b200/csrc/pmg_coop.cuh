@@ -35,13 +35,13 @@ constexpr int R_BD = 24, R_BA = 28;  // block part (NBLK > 0): direction d[3] . 
 constexpr int MINV_LD = 12;  // row stride of M^-1 in shared memory
 
 // Shared memory of one environment.  NBLK = 0: Reach (two finger-table pairs, <= 8 contact points);
-// NBLK = 1: Push / PickAndPlace (+ table-block, floor-block, finger-block pairs; <= 16 points are kept, further
-// ones are counted as overflow like the pools of the thread-per-env kernels).
+// NBLK = 1: Push / PickAndPlace (+ table-block, floor-block, finger-block pairs: 6 pairs x 4 points, the same pool
+// as the thread-per-env kernels; a grasp on the table really uses 20 of them).
 template <int NBLK>
 struct __align__(16) EnvSmemT {
   static constexpr int NB = NBLK;
   static constexpr int NPAIRS = num_pairs(NBLK);                // 2 / 6
-  static constexpr int MAXPTS = NBLK == 0 ? 8 : 16;
+  static constexpr int MAXPTS = NBLK == 0 ? 8 : 24;
   static constexpr int ROW_W = NBLK == 0 ? 24 : 32;             // floats per contact row record (16-byte aligned thirds)
   float pub[7][8];                  // per arm dof: axis a, v = (p - Pref) x a
   float minv[ND * MINV_LD];         // 9x9, rows padded to 12

@@ -32,8 +32,8 @@ def test_partial_reset_only_touches_masked_envs():
     assert np.all(after[mask, -1] == 0) and np.all(after[keep, -1] == 3)          # elapsed steps
     assert np.all(after[mask, 9:18] == 0)                                       # joint velocities zeroed
     assert not np.array_equal(before[mask, 46:49], after[mask, 46:49])          # block respawned
-    for k in obs:
-        assert torch.equal(obs2[k][keep], obs[k][keep])
+    for k in obs:  # rewritten by the reset kernel's own observation code: same numbers up to fp32 rounding
+        assert torch.allclose(obs2[k][keep], obs[k][keep], rtol=0, atol=2e-6)
     # done follows the per-env counter
     for _ in range(47):
         obs, r, d, info = env.step(a)
