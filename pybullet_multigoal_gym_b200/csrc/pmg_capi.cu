@@ -301,9 +301,10 @@ __global__ void __launch_bounds__(32, COOP_MIN_BLOCKS) step_kernel_coop_reach(St
 }
 
 // Lane-cooperative Push / PickAndPlace step: the same octet layout with the block and its manifolds in shared memory
-// (11.6 KB per environment, 4 one-warp blocks per SM: shared memory, not registers, limits residency here).
+// (7.1 KB per environment with the first 12 contact points' rows; 7 one-warp blocks = 28 environments per SM, so a
+// 4096-environment batch is one wave of 1024 blocks on 148 SMs).
 template <int TASK>
-__global__ void __launch_bounds__(32, 4) step_kernel_coop_block(StepIO io) {
+__global__ void __launch_bounds__(32, 7) step_kernel_coop_block(StepIO io) {
   extern __shared__ __align__(16) unsigned char coop_smem[];
   const int lane32 = threadIdx.x & 31, grp = lane32 >> 3;
   float* lane_consts = reinterpret_cast<float*>(coop_smem);
@@ -510,7 +511,7 @@ struct pmg_handle {
   double cur_goals_per = 0;
   std::vector<double> cur_prob, cur_count;  // [batch][nblk]
   std::vector<int32_t> cur_level;           // [batch]
-  float* d_state = nullptr; float* d_man = nullptr; float* d_spawn = nullptr; uint8_t* d_mask = nullptr; int* d_overflow = nullptr;
+  float* d_state = nullptr; float* d_man = nullptr; float* d_spawn = nullptr; uint8_t* d_mask = nullptr; int* d_overflow = nullptr; float* d_row_spill = nullptr;
   float* d_blocks = nullptr;
   float* d_action = nullptr; float* d_obs = nullptr; float* d_reward = nullptr; uint8_t* d_done = nullptr; uint8_t* d_success = nullptr;
   float* h_spawn = nullptr;  // pinned; the spawn row every env was last reset with
@@ -638,7 +639,7 @@ StepIO make_io(pmg_handle* h, const float* action, float* obs, float* reward, ui
   io.state = h->d_state; io.manifold = h->d_man; io.batch = h->cfg.batch; io.state_words = h->state_words;
   io.action = action; io.obs = obs; io.reward = reward; io.done = done; io.success = success;
   io.thr = h->cfg.distance_threshold; io.binary = h->cfg.binary_reward; io.max_steps = h->cfg.max_episode_steps;
-  io.overflow = h->d_overflow;
+  io.overflow = h->d_overflow; io.row_spill = h->d_row_spill;
   io.epw = h->epw;
   io.bulk = 0; io.tile_offset = 0;
   io.grasp = h->grasp; io.jc = h->jc; io.grip_goal = h->grip; io.td = h->td || h->cur; io.cur = h->cur;
@@ -790,6 +791,8 @@ int pmg_create(const pmg_config* cfg, pmg_handle** out) {
   ALLOC(h->d_spawn, sizeof(float) * h->spawn_w * B);
   ALLOC(h->d_mask, B);
   ALLOC(h->d_overflow, sizeof(int));
+  if ((h->cfg.task == PMG_PUSH || h->cfg.task == PMG_PICK_AND_PLACE) && h->coop_block && !h->jc)
+    ALLOC(h->d_row_spill, sizeof(float) * coop::EnvSmemT<1>::SPILL_WORDS * B);
   ALLOC(h->d_action, sizeof(float) * h->A * B);
   ALLOC(h->d_obs, sizeof(float) * h->W * B);
   ALLOC(h->d_blocks, sizeof(float) * h->W * B);
@@ -815,7 +818,7 @@ int pmg_create(const pmg_config* cfg, pmg_handle** out) {
 int pmg_destroy(pmg_handle* h) {
   if (!h) return PMG_OK;
   cudaSetDevice(h->cfg.device);
-  cudaFree(h->d_state); cudaFree(h->d_man); cudaFree(h->d_spawn); cudaFree(h->d_mask); cudaFree(h->d_overflow);
+  cudaFree(h->d_state); cudaFree(h->d_man); cudaFree(h->d_spawn); cudaFree(h->d_mask); cudaFree(h->d_overflow); cudaFree(h->d_row_spill);
   cudaFree(h->d_action); cudaFree(h->d_obs); cudaFree(h->d_blocks); cudaFree(h->d_reward); cudaFree(h->d_done); cudaFree(h->d_success);
   if (h->h_spawn) cudaFreeHost(h->h_spawn);
   for (int k = 0; k < 2; k++) { if (h->h_stage[k]) cudaFreeHost(h->h_stage[k]); if (h->stage_done[k]) cudaEventDestroy(h->stage_done[k]); }

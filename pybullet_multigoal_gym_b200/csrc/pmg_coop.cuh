@@ -36,22 +36,29 @@ constexpr int MINV_LD = 12;  // row stride of M^-1 in shared memory
 
 // Shared memory of one environment.  NBLK = 0: Reach (two finger-table pairs, <= 8 contact points);
 // NBLK = 1: Push / PickAndPlace (+ table-block, floor-block, finger-block pairs: 6 pairs x 4 points, the same pool
-// as the thread-per-env kernels; a grasp on the table really uses 20 of them).
+// as the thread-per-env kernels; a grasp on the table really uses 20 of them).  Only the records of the first
+// SPTS points live in shared memory; the rarely used rest goes to a per-environment global scratch (`spill`, L1/L2
+// resident, read as warp-uniform broadcasts), which is what lets 7 blocks = 28 environments share one SM.
+template <int NBLK> struct RowSpill { float* spill; float spill_pad_[2]; };
+template <> struct RowSpill<0> {};
 template <int NBLK>
-struct __align__(16) EnvSmemT {
+struct __align__(16) EnvSmemT : RowSpill<NBLK> {
   static constexpr int NB = NBLK;
   static constexpr int NPAIRS = num_pairs(NBLK);                // 2 / 6
-  static constexpr int MAXPTS = NBLK == 0 ? 8 : 24;
+  static constexpr int MAXPTS = NBLK == 0 ? 8 : 24;             // cached contact points that get rows
+  static constexpr int SPTS = NBLK == 0 ? 8 : 12;               // ... of which in shared memory
   static constexpr int ROW_W = NBLK == 0 ? 24 : 32;             // floats per contact row record (16-byte aligned thirds)
   float pub[7][8];                  // per arm dof: axis a, v = (p - Pref) x a
   float minv[ND * MINV_LD];         // 9x9, rows padded to 12
   float man[(NPAIRS * MAN_WORDS + 3) / 4 * 4];  // persistent manifolds (41 words per pair)
   float hand[24];                   // gripper frame for the contact rows: Rg[9] pf1 pf2 Pref ax1 (kept out of registers)
   float vq[NBLK == 0 ? 12 : 16];    // joint (+ block) velocities for the row set-up, then the PGS delta velocities
-  float rows[MAXPTS * 3][ROW_W];    // contact rows (layout R_* above); narrowphase scratch before they are built
+  float rows[SPTS * 3][ROW_W];      // contact rows (layout R_* above); narrowphase scratch before they are built
   float app[2][MAXPTS * 3];         // accumulated impulses of the contact rows, double buffered over the PGS iterations
   float blk[NBLK > 0 ? 24 : 1];     // block: pos[3] quat[4] v[3] w[3] R[9]
-  static_assert(NPAIRS * sizeof(BoxScratch) <= MAXPTS * 3 * ROW_W * sizeof(float), "narrowphase scratch must fit in the contact-row area");
+  static_assert(NPAIRS * sizeof(BoxScratch) <= SPTS * 3 * ROW_W * sizeof(float), "narrowphase scratch must fit in the contact-row area");
+  static constexpr int SPILL_WORDS = (MAXPTS - SPTS) * 3 * ROW_W;  // global scratch per environment
+  __device__ __forceinline__ float* spill_row(int r) { return this->spill + (r - SPTS * 3) * ROW_W; }  // r >= 3 SPTS
 };
 using EnvSmem = EnvSmemT<0>;
 constexpr int BK_POS = 0, BK_QUAT = 3, BK_V = 7, BK_W = 10, BK_R = 13;
@@ -404,7 +411,9 @@ __device__ __noinline__ void contact_row_setup(EnvSmem& sm, int c, int n0) {
 // point c.  Pairs in manifold order (pmg_sim.cuh pair_info<1>): finger1-table, finger2-table, table-block,
 // floor-block, finger1-block, finger2-block; body A is a finger (robot end: J over the 9 dofs) or a static box
 // (no end), body B is the table (no end) or the block (end: d and r_B x d).
-template <class SM>
+// SPILL: the point's records go to the global scratch (c >= SPTS); its own copy of the code, so that the usual
+// points keep shared-memory stores and loads.
+template <bool SPILL, class SM>
 __device__ __noinline__ void contact_row_setup_blk(SM& sm, int c) {
   // which pair / which point of it
   int k = 0, i = c;
@@ -447,7 +456,7 @@ __device__ __noinline__ void contact_row_setup_blk(SM& sm, int c) {
     }
     J[7] = pi.ka == G_FINGER1 ? dot(d, ax1) : 0.0f;
     J[8] = pi.ka == G_FINGER2 ? dot(d, ax2) : 0.0f;
-    float* row = sm.rows[c * 3 + kk];
+    float* row = SPILL ? sm.spill_row(c * 3 + kk) : sm.rows[SPILL ? 0 : c * 3 + kk];
     const V3 ang = cross(rB, d);
     float denom = blockB ? BLOCK_INV_MASS + BLOCK_INV_INERTIA * dot(ang, ang) : 0.0f;
     float rel_vel = blockB ? -(dot(d, bv) + dot(ang, bw)) : 0.0f;
@@ -528,9 +537,9 @@ __device__ __noinline__ float contact_sweep(Grp g, SM& sm, int nrow_it) {  // nr
 #pragma unroll
   for (int j = 0; j < 6; j++) dv[j] = BLK ? sm.vq[(BLK ? ND : 0) + j] : 0.0f;
   float cres = 0.0f;
-#pragma unroll 1
-  for (int c = 0; c < nrow; c++) {
-    float* row = sm.rows[c * 3];
+  // (the loop bodies are lambdas so that the shared-memory rows and the spilled ones get their own loops: a
+  // pointer selected per row would turn every row load into a generic-address load)
+  auto normal_row = [&](const float* row, int c) {
     const RowVec j = load3(row + R_J), mj = load3(row + R_MJ);
     const float app = app_rd[c * 3];
     float v = row_dot(j, dq);
@@ -544,12 +553,16 @@ __device__ __noinline__ float contact_sweep(Grp g, SM& sm, int nrow_it) {  // nr
     const float rr = dl * mj.c.y;                // denom
     cres = fmaxf(cres, rr * rr);
     app_wr[c * 3] = sum;
+  };
+  const int nsh = nrow < SM::SPTS ? nrow : SM::SPTS;  // points whose rows are in shared memory
+#pragma unroll 1
+  for (int c = 0; c < nsh; c++) normal_row(sm.rows[c * 3], c);
+  if constexpr (SM::MAXPTS > SM::SPTS) {
+#pragma unroll 1
+    for (int c = SM::SPTS; c < nrow; c++) normal_row(sm.spill_row(c * 3), c);
   }
   g.sync();  // the new normal impulses bound the friction rows
-#pragma unroll 1
-  for (int c = 0; c < nrow; c++) {  // implicit friction cone: both tangent rows of a point together
-    float* ra = sm.rows[c * 3 + 1];
-    float* rb = sm.rows[c * 3 + 2];
+  auto friction_rows = [&](const float* ra, const float* rb, int c) {  // implicit friction cone: both tangent rows of a point together
     const float total = app_wr[c * 3];
     const RowVec ja = load3(ra + R_J), jb = load3(rb + R_J);
     const float appA = app_rd[c * 3 + 1], appB = app_rd[c * 3 + 2];
@@ -579,6 +592,12 @@ __device__ __noinline__ float contact_sweep(Grp g, SM& sm, int nrow_it) {  // nr
       cres = fmaxf(cres, fmaxf(r1_ * r1_, r2_ * r2_));
     }
     app_wr[c * 3 + 1] = sA; app_wr[c * 3 + 2] = sB;  // carried over unchanged while the point is open
+  };
+#pragma unroll 1
+  for (int c = 0; c < nsh; c++) friction_rows(sm.rows[c * 3 + 1], sm.rows[c * 3 + 2], c);
+  if constexpr (SM::MAXPTS > SM::SPTS) {
+#pragma unroll 1
+    for (int c = SM::SPTS; c < nrow; c++) friction_rows(sm.spill_row(c * 3 + 1), sm.spill_row(c * 3 + 2), c);
   }
   g.sync();  // every lane has read sm.vq
   if (g.lane == 0) {
@@ -703,7 +722,7 @@ __device__ void substep(const Grp& g, SM& sm, Lane& L) {
     ManRef mr; mr.man = sm.man; mr.stride = 1;
     const float tc[3] = PMG_TABLE_CENTER, th[3] = PMG_TABLE_HALF, fh[3] = PMG_FINGER_HALF;
     // the narrowphase work arrays live in the (not yet used) contact-row area of shared memory
-    constexpr int SCR_STRIDE = SM::MAXPTS * 3 * SM::ROW_W / SM::NPAIRS / 4 * 4;
+    constexpr int SCR_STRIDE = SM::SPTS * 3 * SM::ROW_W / SM::NPAIRS / 4 * 4;
     BoxScratch& scr = *reinterpret_cast<BoxScratch*>(&sm.rows[0][0] + lane * SCR_STRIDE);
     if constexpr (!BLK) {
       collide_pair(mr, lane, lane == 0 ? pf1 : pf2, Rg, v3(fh[0], fh[1], fh[2]), v3(0, 0, 0), false,
@@ -863,7 +882,10 @@ __device__ void substep(const Grp& g, SM& sm, Lane& L) {
     if constexpr (!BLK) {
       if (lane < nrow) contact_row_setup(sm, lane, n0);
     } else {
-      for (int c = lane; c < nrow; c += GL) contact_row_setup_blk(sm, c);
+      for (int c = lane; c < nrow; c += GL) {
+        if (c < SM::SPTS) contact_row_setup_blk<false>(sm, c);
+        else contact_row_setup_blk<true>(sm, c);
+      }
     }
     g.sync();
   }
@@ -1015,7 +1037,10 @@ __device__ void step_env_block(const Grp& g, EnvSmemT<1>& sm, const float* lane_
   L.dtau0 = L.dtau1 = 0.0f;
   for (int w = lane; w < SM::NPAIRS * MAN_WORDS; w += GL) sm.man[w] = io.manifold[(size_t)w * B + env];
   for (int w = lane; w < 13; w += GL) sm.blk[w] = s[(size_t)(ST_BLK + w) * B];
-  if (lane == 0) sm.blk[23] = 0.0f;  // contact points dropped because the row pool was full
+  if (lane == 0) {
+    sm.blk[23] = 0.0f;  // contact points dropped because the row pool was full
+    sm.spill = io.row_spill + (size_t)env * SM::SPILL_WORDS;
+  }
   // ---- Kuka.apply_action (kuka.py:167-222) ----
   const float* act = io.action + (size_t)env * D::A;
   if (TASK == 2 && hand) {  // grasping: the last action column drives both jaws (kuka.py:169-172)

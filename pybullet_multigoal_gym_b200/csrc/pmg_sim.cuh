@@ -613,6 +613,7 @@ struct StepIO {
   int td;           // task decomposition / curriculum: desired goal = the sub-goal named by the state word behind the goal
   int cur;          // curriculum: that word is set by the reset (from the spawn row) instead of -1
   int adim, goal_dim, row_width;  // action columns, goal length, packed row width (all after the variants above)
+  float* row_spill;               // cooperative block kernel: contact-row records beyond the shared-memory ones
 };
 
 template <int TASK, int NBLK> struct Dims {

@@ -230,6 +230,8 @@ int pmg_emu_block_step(int task, float* state, float* manifold, const float* act
   a.io.action = action; a.io.obs = obs_row; a.io.reward = reward; a.io.done = done; a.io.success = success;
   a.io.thr = thr; a.io.binary = binary; a.io.max_steps = max_steps; a.io.overflow = nullptr; a.io.epw = 4;
   a.io.grasp = task == 2; a.io.adim = task == 2 ? 4 : 3; a.io.goal_dim = 3; a.io.row_width = 33;
+  static float spill[coop::EnvSmemT<1>::SPILL_WORDS];
+  a.io.row_spill = spill;
   return pmg_emu::run_group(blk_body, &a);
 }
 int pmg_emu_block_smem_bytes(void) { return (int)sizeof(coop::EnvSmemT<1>); }
