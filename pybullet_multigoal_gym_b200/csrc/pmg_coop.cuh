@@ -24,6 +24,8 @@
 // source on the CPU (PMG_EMULATE) against the oracle.
 #pragma once
 
+#include <type_traits>
+
 #include "pmg_sim.cuh"
 
 namespace pmg {
@@ -446,29 +448,35 @@ __device__ __noinline__ void contact_row_setup_blk(SM& sm, int c) {
 #pragma unroll 1
   for (int kk = 0; kk < 3; kk++) {
     const V3 d = kk == 0 ? nB : (kk == 1 ? t1 : t2);
-    const V3 m = cross(wr, d);
-    float J[ND];  // statically indexed everywhere below: stays in registers
-#pragma unroll
-    for (int j = 0; j < 7; j++) {
-      const float4 p0 = *reinterpret_cast<const float4*>(sm.pub[j]);
-      const float2 p1 = *reinterpret_cast<const float2*>(sm.pub[j] + 4);
-      J[j] = robotA ? p0.x * m.x + p0.y * m.y + p0.z * m.z + p0.w * d.x + p1.x * d.y + p1.y * d.z : 0.0f;
-    }
-    J[7] = pi.ka == G_FINGER1 ? dot(d, ax1) : 0.0f;
-    J[8] = pi.ka == G_FINGER2 ? dot(d, ax2) : 0.0f;
     float* row = SPILL ? sm.spill_row(c * 3 + kk) : sm.rows[SPILL ? 0 : c * 3 + kk];
     const V3 ang = cross(rB, d);
     float denom = blockB ? BLOCK_INV_MASS + BLOCK_INV_INERTIA * dot(ang, ang) : 0.0f;
     float rel_vel = blockB ? -(dot(d, bv) + dot(ang, bw)) : 0.0f;
+    if (robotA) {
+      const V3 m = cross(wr, d);
+      float J[ND];  // statically indexed everywhere below: stays in registers
 #pragma unroll
-    for (int j = 0; j < ND; j++) { row[R_J + j] = J[j]; rel_vel += J[j] * sm.vq[j]; }
+      for (int j = 0; j < 7; j++) {
+        const float4 p0 = *reinterpret_cast<const float4*>(sm.pub[j]);
+        const float2 p1 = *reinterpret_cast<const float2*>(sm.pub[j] + 4);
+        J[j] = p0.x * m.x + p0.y * m.y + p0.z * m.z + p0.w * d.x + p1.x * d.y + p1.y * d.z;
+      }
+      J[7] = pi.ka == G_FINGER1 ? dot(d, ax1) : 0.0f;
+      J[8] = pi.ka == G_FINGER2 ? dot(d, ax2) : 0.0f;
+#pragma unroll
+      for (int j = 0; j < ND; j++) { row[R_J + j] = J[j]; rel_vel += J[j] * sm.vq[j]; }
 #pragma unroll 1
-    for (int r = 0; r < ND; r++) {  // M^-1 J^T, one row of M^-1 (three 16-byte loads) per iteration
-      const float4* mr = reinterpret_cast<const float4*>(sm.minv + r * MINV_LD);
-      const float4 m0 = mr[0], m1 = mr[1], m2 = mr[2];
-      const float acc = (m0.x * J[0] + m0.y * J[1] + m0.z * J[2]) + (m0.w * J[3] + m1.x * J[4] + m1.y * J[5]) + (m1.z * J[6] + m1.w * J[7] + m2.x * J[8]);
-      row[R_MJ + r] = acc;
-      denom += row[R_J + r] * acc;
+      for (int r = 0; r < ND; r++) {  // M^-1 J^T, one row of M^-1 (three 16-byte loads) per iteration
+        const float4* mr = reinterpret_cast<const float4*>(sm.minv + r * MINV_LD);
+        const float4 m0 = mr[0], m1 = mr[1], m2 = mr[2];
+        const float acc = (m0.x * J[0] + m0.y * J[1] + m0.z * J[2]) + (m0.w * J[3] + m1.x * J[4] + m1.y * J[5]) + (m1.z * J[6] + m1.w * J[7] + m2.x * J[8]);
+        row[R_MJ + r] = acc;
+        denom += row[R_J + r] * acc;
+      }
+    } else {  // static box against the block: no robot end (the sweeps skip this part of the record; zeros for the spilled form)
+      const float4 z = {0.0f, 0.0f, 0.0f, 0.0f};
+#pragma unroll
+      for (int j = 0; j < 6; j++) reinterpret_cast<float4*>(row)[j] = z;
     }
     const float dinv = 1.0f / denom;
     float rhs;
@@ -524,7 +532,7 @@ __device__ __forceinline__ void blk_axpy(const BlkVec& b, float lam, float* dv) 
 }
 
 template <class SM>
-__device__ __noinline__ float contact_sweep(Grp g, SM& sm, int nrow_it) {  // nrow | (iteration parity << 8)
+__device__ __noinline__ float contact_sweep(Grp g, SM& sm, int nrow_it) {  // nrow | iteration parity << 8 | c1 << 16 | c2 << 24
   constexpr bool BLK = SM::NB > 0;  // rows may have a block end point: the vector gains the block's delta velocities
   const int nrow = nrow_it & 0xff, it = nrow_it >> 8;
   // The accumulated impulses are double buffered (read buffer / write buffer swap every iteration, every lane
@@ -537,44 +545,49 @@ __device__ __noinline__ float contact_sweep(Grp g, SM& sm, int nrow_it) {  // nr
 #pragma unroll
   for (int j = 0; j < 6; j++) dv[j] = BLK ? sm.vq[(BLK ? ND : 0) + j] : 0.0f;
   float cres = 0.0f;
-  // (the loop bodies are lambdas so that the shared-memory rows and the spilled ones get their own loops: a
-  // pointer selected per row would turn every row load into a generic-address load)
-  auto normal_row = [&](const float* row, int c) {
-    const RowVec j = load3(row + R_J), mj = load3(row + R_MJ);
-    const float app = app_rd[c * 3];
-    float v = row_dot(j, dq);
+  // The loop bodies are lambdas with compile-time flags for the two ends of a row: points come in pair order, so the
+  // first c1 have a robot end only (finger-table), those up to c2 a block end only (table-block, floor-block), the
+  // rest both (finger-block); a resting block costs 12 instead of 30 multiply-adds per row.  Spilled rows (their own
+  // loop: a pointer selected per row would make every row load a generic-address load) take the general form.
+  const int c1 = BLK ? (nrow_it >> 16) & 0xff : nrow, c2 = BLK ? (nrow_it >> 24) & 0xff : nrow;
+  auto ld4 = [](const float* p) { return *reinterpret_cast<const float4*>(p); };
+  auto normal_row = [&](auto robot, auto block, const float* row, int c) {
+    constexpr bool RB = decltype(robot)::value, BK = decltype(block)::value;
+    const float4 jc = ld4(row + R_J + 8), mc = ld4(row + R_MJ + 8);  // (J8 rhs dinv .) (MJ8 denom mu .)
+    RowVec j, mj;
     BlkVec bk;
-    if (BLK) { bk = load_blk(row); v -= blk_dot(bk, dv); }
-    float dl = j.c.y - v * j.c.z;   // rhs - (J . dq) dinv
+    float v = 0.0f;
+    if (RB) { j.a = ld4(row + R_J); j.b = ld4(row + R_J + 4); j.c = jc; mj.a = ld4(row + R_MJ); mj.b = ld4(row + R_MJ + 4); mj.c = mc; v = row_dot(j, dq); }
+    if (BK) { bk = load_blk(row); v -= blk_dot(bk, dv); }
+    const float app = app_rd[c * 3];
+    float dl = jc.y - v * jc.z;   // rhs - (J . dq) dinv
     const float sum = fminf(fmaxf(app + dl, 0.0f), 1e10f);
     dl = sum - app;
-    row_axpy(mj, dl, dq);
-    if (BLK) blk_axpy(bk, dl, dv);
-    const float rr = dl * mj.c.y;                // denom
+    if (RB) row_axpy(mj, dl, dq);
+    if (BK) blk_axpy(bk, dl, dv);
+    const float rr = dl * mc.y;                // denom
     cres = fmaxf(cres, rr * rr);
     app_wr[c * 3] = sum;
   };
-  const int nsh = nrow < SM::SPTS ? nrow : SM::SPTS;  // points whose rows are in shared memory
-#pragma unroll 1
-  for (int c = 0; c < nsh; c++) normal_row(sm.rows[c * 3], c);
-  if constexpr (SM::MAXPTS > SM::SPTS) {
-#pragma unroll 1
-    for (int c = SM::SPTS; c < nrow; c++) normal_row(sm.spill_row(c * 3), c);
-  }
-  g.sync();  // the new normal impulses bound the friction rows
-  auto friction_rows = [&](const float* ra, const float* rb, int c) {  // implicit friction cone: both tangent rows of a point together
+  auto friction_rows = [&](auto robot, auto block, const float* ra, const float* rb, int c) {  // implicit friction cone: both tangent rows of a point together
+    constexpr bool RB = decltype(robot)::value, BK = decltype(block)::value;
     const float total = app_wr[c * 3];
-    const RowVec ja = load3(ra + R_J), jb = load3(rb + R_J);
     const float appA = app_rd[c * 3 + 1], appB = app_rd[c * 3 + 2];
     float sA = appA, sB = appB;
     if (total > 0.0f) {
-      const RowVec mja = load3(ra + R_MJ), mjb = load3(rb + R_MJ);
-      const float mu = BLK ? mja.c.z : (float)PMG_FINGER_FRICTION * (float)PMG_TABLE_FRICTION;  // R_MU
-      const float lim = mu * total;
-      float vA = row_dot(ja, dq), vB = row_dot(jb, dq);
+      const float4 jca = ld4(ra + R_J + 8), jcb = ld4(rb + R_J + 8), mca = ld4(ra + R_MJ + 8), mcb = ld4(rb + R_MJ + 8);
+      RowVec ja, jb, mja, mjb;
       BlkVec bka, bkb;
-      if (BLK) { bka = load_blk(ra); bkb = load_blk(rb); vA -= blk_dot(bka, dv); vB -= blk_dot(bkb, dv); }
-      float dA = ja.c.y - vA * ja.c.z, dB = jb.c.y - vB * jb.c.z;
+      float vA = 0.0f, vB = 0.0f;
+      if (RB) {
+        ja.a = ld4(ra + R_J); ja.b = ld4(ra + R_J + 4); ja.c = jca; jb.a = ld4(rb + R_J); jb.b = ld4(rb + R_J + 4); jb.c = jcb;
+        mja.a = ld4(ra + R_MJ); mja.b = ld4(ra + R_MJ + 4); mja.c = mca; mjb.a = ld4(rb + R_MJ); mjb.b = ld4(rb + R_MJ + 4); mjb.c = mcb;
+        vA = row_dot(ja, dq); vB = row_dot(jb, dq);
+      }
+      if (BK) { bka = load_blk(ra); bkb = load_blk(rb); vA -= blk_dot(bka, dv); vB -= blk_dot(bkb, dv); }
+      const float mu = BLK ? mca.z : (float)PMG_FINGER_FRICTION * (float)PMG_TABLE_FRICTION;  // R_MU
+      const float lim = mu * total;
+      float dA = jca.y - vA * jca.z, dB = jcb.y - vB * jcb.z;
       sA = appA + dA; sB = appB + dB;
       const float s2 = sA * sA + sB * sB;
       if (s2 >= lim * lim) {
@@ -585,19 +598,43 @@ __device__ __noinline__ float contact_sweep(Grp g, SM& sm, int nrow_it) {  // nr
         sB = fminf(fmaxf(sB, -cB), cB);
         dA = sA - appA; dB = sB - appB;
       }
-      row_axpy(mja, dA, dq);
-      row_axpy(mjb, dB, dq);
-      if (BLK) { blk_axpy(bka, dA, dv); blk_axpy(bkb, dB, dv); }
-      const float r1_ = dA * mja.c.y, r2_ = dB * mjb.c.y;
+      if (RB) { row_axpy(mja, dA, dq); row_axpy(mjb, dB, dq); }
+      if (BK) { blk_axpy(bka, dA, dv); blk_axpy(bkb, dB, dv); }
+      const float r1_ = dA * mca.y, r2_ = dB * mcb.y;
       cres = fmaxf(cres, fmaxf(r1_ * r1_, r2_ * r2_));
     }
     app_wr[c * 3 + 1] = sA; app_wr[c * 3 + 2] = sB;  // carried over unchanged while the point is open
   };
+  using T = std::true_type;
+  using F = std::false_type;
+  const int nsh = nrow < SM::SPTS ? nrow : SM::SPTS;  // points whose rows are in shared memory
+  // one loop per kind (not one loop with a three-way branch): the four environments of a warp then run the same
+  // form together even when their point counts differ
+  const int e1 = c1 < nsh ? c1 : nsh, e2 = c2 < nsh ? c2 : nsh;
 #pragma unroll 1
-  for (int c = 0; c < nsh; c++) friction_rows(sm.rows[c * 3 + 1], sm.rows[c * 3 + 2], c);
+  for (int c = 0; c < e1; c++) normal_row(T(), F(), sm.rows[c * 3], c);
+  if constexpr (BLK) {
+#pragma unroll 1
+    for (int c = e1; c < e2; c++) normal_row(F(), T(), sm.rows[c * 3], c);
+#pragma unroll 1
+    for (int c = e2; c < nsh; c++) normal_row(T(), T(), sm.rows[c * 3], c);
+  }
   if constexpr (SM::MAXPTS > SM::SPTS) {
 #pragma unroll 1
-    for (int c = SM::SPTS; c < nrow; c++) friction_rows(sm.spill_row(c * 3 + 1), sm.spill_row(c * 3 + 2), c);
+    for (int c = SM::SPTS; c < nrow; c++) normal_row(T(), T(), sm.spill_row(c * 3), c);
+  }
+  g.sync();  // the new normal impulses bound the friction rows
+#pragma unroll 1
+  for (int c = 0; c < e1; c++) friction_rows(T(), F(), sm.rows[c * 3 + 1], sm.rows[c * 3 + 2], c);
+  if constexpr (BLK) {
+#pragma unroll 1
+    for (int c = e1; c < e2; c++) friction_rows(F(), T(), sm.rows[c * 3 + 1], sm.rows[c * 3 + 2], c);
+#pragma unroll 1
+    for (int c = e2; c < nsh; c++) friction_rows(T(), T(), sm.rows[c * 3 + 1], sm.rows[c * 3 + 2], c);
+  }
+  if constexpr (SM::MAXPTS > SM::SPTS) {
+#pragma unroll 1
+    for (int c = SM::SPTS; c < nrow; c++) friction_rows(T(), T(), sm.spill_row(c * 3 + 1), sm.spill_row(c * 3 + 2), c);
   }
   g.sync();  // every lane has read sm.vq
   if (g.lane == 0) {
@@ -869,9 +906,14 @@ __device__ void substep(const Grp& g, SM& sm, Lane& L) {
   // contact rows: one normal + two tangents per cached manifold point, point c set up by lane c
   const int n0 = __float_as_int(sm.man[0]);
   int nrow = n0 + __float_as_int(sm.man[MAN_WORDS]);  // number of cached contact points (3 rows each)
+  int row_kinds = 0;                                  // (first point with a block end) << 16 | (first with both ends) << 24
   if (BLK) {
+    row_kinds = nrow << 16;
 #pragma unroll
-    for (int k = 2; k < SM::NPAIRS; k++) nrow += __float_as_int(sm.man[k * MAN_WORDS]);
+    for (int k = 2; k < SM::NPAIRS; k++) {
+      if (k == 4) row_kinds |= nrow << 24;
+      nrow += __float_as_int(sm.man[k * MAN_WORDS]);
+    }
     if (nrow > SM::MAXPTS) {  // points beyond the pool are dropped and counted (pmg_overflow_count)
       if (lane == 0) sm.blk[23] += (float)(nrow - SM::MAXPTS);
       nrow = SM::MAXPTS;
@@ -912,7 +954,7 @@ __device__ void substep(const Grp& g, SM& sm, Lane& L) {
       if (hand) sm.vq[8] = s.dqd1;
       g.sync();
       PMG_T(t_sw0);
-      res = fmaxf(res, contact_sweep(g, sm, nrow | ((it & 1) << 8)));
+      res = fmaxf(res, contact_sweep(g, sm, nrow | ((it & 1) << 8) | row_kinds));
 #ifdef PMG_COOP_TIMING
       t_sweeps += clock64() - t_sw0;
 #endif

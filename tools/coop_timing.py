@@ -1,4 +1,5 @@
-"""Development aid: per-phase cycle counts of the cooperative Reach kernel for octets with / without contacts.
+"""Development aid: per-phase cycle counts of the cooperative kernels for octets with / without contacts.
+Usage: coop_timing.py [down] [task[:batch]]   (default reach:8192)
 
 Build (here):  nvcc ... -DPMG_COOP_TIMING -o gpurun_out/libpmg_timing.so   (see tools/gpu_timing.sh)
 Run (GPU box): PMG_LIBRARY=pybullet_multigoal_gym_b200/libpmg_timing.so python tools/coop_timing.py"""
@@ -10,11 +11,16 @@ import torch
 import pybullet_multigoal_gym_b200 as pmg
 from pybullet_multigoal_gym_b200 import _lib
 
-B = 8192
-env = pmg.make_env(task="reach", batch=B, check_actions=False)
+args = sys.argv[1:]
+down = "down" in args
+args = [a for a in args if a != "down"]
+task, _, bs = (args[0] if args else "reach:8192").partition(":")
+B = int(bs or 8192)
+env = pmg.make_env(task=task, batch=B, check_actions=False)
 L = _lib.load()
-acts = torch.rand((50, B, 3), device="cuda") * 2 - 1
-if len(sys.argv) > 1 and sys.argv[1] == "down":
+torch.manual_seed(0)
+acts = torch.rand((50, B, env.action_dim), device="cuda") * 2 - 1
+if down:
     acts[:, :, 2] = -1.0  # every arm onto the table: all octets run the contact path together
 out = torch.empty((B, env.row_width), device="cuda"); r = torch.empty((B,), device="cuda")
 d = torch.empty((B,), dtype=torch.uint8, device="cuda"); s = torch.empty((B,), dtype=torch.uint8, device="cuda")
