@@ -277,7 +277,9 @@ def main():
             "config": {"workload": WORKLOAD if task == TASK else "task=%s batch=%d per GPU" % (task, B),
                        "global_batch": B * world, "parallelism": "env-sharded x%d, one all-gather of the obs batch per step" % world,
                        "l2": "flushed between timed steps (256 MiB memset outside the per-step CUDA events); working set 1.6 MB",
-                       "kernel": ("lane-cooperative step kernel: 8 lanes per env, 4 envs per one-warp block" if (task == "reach" and os.environ.get("PMG_COOP", "1") != "0")
+                       "kernel": ("lane-cooperative step kernel: 8 lanes per env, 4 envs per one-warp block"
+                                  if ((task == "reach" and os.environ.get("PMG_COOP", "1") != "0") or
+                                      (task in ("push", "pick_and_place") and os.environ.get("PMG_COOP_BLOCK", "1") != "0"))
                                   else "thread-per-env step kernel: 32 envs per warp"),
                        "contact_pool_overflows": overflow},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,

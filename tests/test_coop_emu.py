@@ -142,7 +142,7 @@ def test_cooperative_block_step_matches_oracle(emu, task, tid, adim, nsteps):
     o.reset()
     obs, rew = np.zeros(33, np.float32), np.zeros(1, np.float32)
     dn, su = np.zeros(1, np.uint8), np.zeros(1, np.uint8)
-    worst, touched = 0.0, 0
+    worst, touched, most = 0.0, 0, 0
     for t in range(nsteps):
         st = o.get_state().astype(np.float32)
         o.set_state(st.astype(np.float64))     # both sides start the step from the same state, contact caches empty
@@ -161,5 +161,9 @@ def test_cooperative_block_step_matches_oracle(emu, task, tid, adim, nsteps):
         worst = max(worst, float(np.abs(obs - want)[pos].max()))
         assert abs(float(rew[0]) - rr) < 1e-4 and bool(dn[0]) == rd
         touched = max(touched, sum(int(man[41 * k:41 * k + 1].view(np.int32)[0]) for k in (4, 5)))
+        most = max(most, sum(int(man[41 * k:41 * k + 1].view(np.int32)[0]) for k in range(6)))
     assert worst < 1e-4, worst
     assert touched > 0                         # the jaws did reach the block (finger-block manifolds in use)
+    print("%s: most cached contact points in one step: %d" % (task, most))
+    if task == "push":
+        assert most > 12                       # rows beyond the 12 shared-memory points: the global spill path ran

@@ -1,6 +1,6 @@
 #!/usr/bin/env python3
 """Condenses `ncu --set full` captures of the step kernel into profiles/r01_step_kernel_ncu_summary.json
-(read by bench.py for roofline.traffic).  usage: ncu_summary.py out.json name=capture.ncu-rep[:note] ..."""
+(read by bench.py for roofline.traffic).  usage: ncu_summary.py out.json name=capture.ncu-rep|capture_raw.csv[:note] ..."""
 import csv
 import json
 import subprocess
@@ -19,7 +19,10 @@ out = {}
 for arg in sys.argv[2:]:
     name, rest = arg.split("=", 1)
     path, _, note = rest.partition(":")
-    txt = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    if path.endswith(".csv"):  # `ncu -i X.ncu-rep --page raw --csv` already exported on the GPU box
+        txt = open(path, errors="replace").read()
+    else:
+        txt = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(txt.splitlines()))
     hdr, units, vals = rows[0], rows[1], rows[2]
     m = {}
