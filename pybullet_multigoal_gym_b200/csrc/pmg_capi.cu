@@ -286,6 +286,7 @@ __global__ void __launch_bounds__(32) step_kernel(StepIO io) {
 constexpr int COOP_TABLE_BYTES = coop::GL * coop::LC_W * sizeof(float);
 static_assert(COOP_TABLE_BYTES % 16 == 0, "EnvSmem must stay 16-byte aligned behind the constant table");
 constexpr int COOP_MIN_BLOCKS = 14;  // batch 8192 = 2048 blocks = 13.8 per SM: keep them all resident
+template <bool JC>
 __global__ void __launch_bounds__(32, COOP_MIN_BLOCKS) step_kernel_coop_reach(StepIO io) {
   extern __shared__ __align__(16) unsigned char coop_smem[];
   const int lane32 = threadIdx.x & 31, grp = lane32 >> 3;
@@ -297,7 +298,7 @@ __global__ void __launch_bounds__(32, COOP_MIN_BLOCKS) step_kernel_coop_reach(St
   coop::Grp g;
   g.lane = lane32 & (coop::GL - 1); g.shift = grp * coop::GL; g.mask = 0xffu << g.shift;
   coop::EnvSmem& sm = reinterpret_cast<coop::EnvSmem*>(coop_smem + COOP_TABLE_BYTES)[grp];
-  coop::step_env_reach(g, sm, lane_consts, io, env);
+  coop::step_env_reach<JC>(g, sm, lane_consts, io, env);
 }
 
 // Lane-cooperative Push / PickAndPlace step: the same octet layout with the block and its manifolds in shared memory
@@ -651,14 +652,17 @@ StepIO make_io(pmg_handle* h, const float* action, float* obs, float* reward, ui
 template <int TASK, int NBLK>
 void launch_step(pmg_handle* h, const StepIO& io_in, cudaStream_t st) {
   StepIO io = io_in;
-  if (TASK == 0 && h->coop && !h->jc) {
+  if (TASK == 0 && h->coop) {
     constexpr int EPB = 32 / coop::GL;  // environments per block
     const size_t smem = COOP_TABLE_BYTES + EPB * sizeof(coop::EnvSmem);
+    const int blocks = (h->cfg.batch + EPB - 1) / EPB;
     if (!h->hinted) {  // per handle = per device: function attributes are per device
-      cudaFuncSetAttribute(step_kernel_coop_reach, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+      if (h->jc) cudaFuncSetAttribute(step_kernel_coop_reach<true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+      else cudaFuncSetAttribute(step_kernel_coop_reach<false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
       h->hinted = true;
     }
-    step_kernel_coop_reach<<<(h->cfg.batch + EPB - 1) / EPB, 32, smem, st>>>(io);
+    if (h->jc) step_kernel_coop_reach<true><<<blocks, 32, smem, st>>>(io);
+    else step_kernel_coop_reach<false><<<blocks, 32, smem, st>>>(io);
     return;
   }
   int warps = (h->cfg.batch + h->epw - 1) / h->epw;
@@ -666,7 +670,7 @@ void launch_step(pmg_handle* h, const StepIO& io_in, cudaStream_t st) {
   io.bulk = (h->epw == 32 && h->cfg.batch % 32 == 0 && !h->no_bulk && !h->grip && !h->td && !h->cur) ? 1 : 0;
   io.tile_offset = (int)((stage_floats + 31) / 32 * 32);
   size_t smem = (io.bulk ? io.tile_offset + (size_t)Dims<TASK, NBLK>::STATE * 32 : stage_floats) * sizeof(float);
-  if ((TASK == 1 || TASK == 2) && h->coop_block && !h->jc) {
+  if ((TASK == 1 || TASK == 2) && h->coop_block) {
     constexpr int EPB = 32 / coop::GL;
     const size_t smem = COOP_TABLE_BYTES + EPB * sizeof(coop::EnvSmemT<1>);
     if (!h->hinted) {
@@ -791,7 +795,7 @@ int pmg_create(const pmg_config* cfg, pmg_handle** out) {
   ALLOC(h->d_spawn, sizeof(float) * h->spawn_w * B);
   ALLOC(h->d_mask, B);
   ALLOC(h->d_overflow, sizeof(int));
-  if ((h->cfg.task == PMG_PUSH || h->cfg.task == PMG_PICK_AND_PLACE) && h->coop_block && !h->jc)
+  if ((h->cfg.task == PMG_PUSH || h->cfg.task == PMG_PICK_AND_PLACE) && h->coop_block)
     ALLOC(h->d_row_spill, sizeof(float) * coop::EnvSmemT<1>::SPILL_WORDS * B);
   ALLOC(h->d_action, sizeof(float) * h->A * B);
   ALLOC(h->d_obs, sizeof(float) * h->W * B);

@@ -999,6 +999,8 @@ __device__ void substep(const Grp& g, SM& sm, Lane& L) {
 // `env` is the environment index, state / manifold are the same [word][env] arrays the thread-per-env
 // kernels use, so reset_kernel, pmg_get_state / pmg_set_state and the reward path are shared.
 // `lane_consts`: the block's constant table (8 rows of LC_W floats, filled with fill_lane_constants).
+// JC: joint control (a compile-time variant, so that the default kernel keeps its register allocation)
+template <bool JC>
 __device__ void step_env_reach(const Grp& g, EnvSmem& sm, const float* lane_consts, const StepIO& io, int env) {
   using D = Dims<0, 0>;
   const int lane = g.lane;
@@ -1016,9 +1018,14 @@ __device__ void step_env_reach(const Grp& g, EnvSmem& sm, const float* lane_cons
   // ---- Kuka.apply_action (kuka.py:167-222) ----
   const float lo[3] = {-0.67f, -0.20f, 0.175f}, hi[3] = {-0.37f, 0.20f, 0.55f};  // kuka.py:40-41
   float ee[3];
+  if (JC) {
+    // kuka.py:204-206: joint_state_target (kept in the motor targets) += 0.05 a[:7]; no clipping, no IK
 #pragma unroll
-  for (int k = 0; k < 3; k++) ee[k] = fminf(fmaxf(s[(ST_EE + k) * B] + io.action[(size_t)env * D::A + k] * 0.01f, lo[k]), hi[k]);
-  {
+    for (int k = 0; k < 3; k++) ee[k] = s[(ST_EE + k) * B];
+    if (arm) { L.mt0 += io.action[(size_t)env * io.adim + lane] * 0.05f; L.mi0 = ARM_FORCE * OUTER_DT; }
+  } else {
+#pragma unroll
+    for (int k = 0; k < 3; k++) ee[k] = fminf(fmaxf(s[(ST_EE + k) * B] + io.action[(size_t)env * D::A + k] * 0.01f, lo[k]), hi[k]);
     const float tq[4] = {0.f, -1.f, 0.f, 0.f};  // kuka.py:42
     const float qik = inverse_kinematics(g, L, arm ? L.q0 : 0.0f, v3(ee[0], ee[1], ee[2]), tq);
     if (arm) { L.mt0 = qik; L.mi0 = ARM_FORCE * OUTER_DT; }
@@ -1037,14 +1044,21 @@ __device__ void step_env_reach(const Grp& g, EnvSmem& sm, const float* lane_cons
   if (hand) { s[(ST_Q + 8) * B] = L.q1; s[(ST_QD + 8) * B] = L.qd1; s[(ST_MT + 8) * B] = L.mt1; s[(ST_MI + 8) * B] = L.mi1; }
   g.sync();
   for (int w = lane; w < EnvSmem::NPAIRS * MAN_WORDS; w += GL) io.manifold[(size_t)w * B + env] = sm.man[w];
+  // joint control prepends the 7 joint positions to observation and policy_state (kuka_single_step_base_env.py:214-216)
+  constexpr int jo = JC ? 7 : 0;
+  if (JC && arm) {
+    float* row = io.obs + (size_t)env * io.row_width;
+    row[lane] = L.q0; row[3 + jo + lane] = L.q0;
+  }
   if (lane == PMG_BODY_LINK7) {
     const float t[3] = PMG_TIP_OFFSET;
     const V3 tip = p + mul(R, v3(t[0], t[1], t[2]));
-    float* row = io.obs + (size_t)env * D::W;
+    float* row = io.obs + (size_t)env * (D::W + 2 * jo);
     const float* goal = io.state + (size_t)(ST_BLK) * B + env;
     const float g0 = goal[0], g1 = goal[B], g2 = goal[2 * B];
-    row[0] = row[3] = row[6] = tip.x; row[1] = row[4] = row[7] = tip.y; row[2] = row[5] = row[8] = tip.z;
-    row[9] = g0; row[10] = g1; row[11] = g2;
+    float* ob = row + jo; float* pol = row + 3 + 2 * jo; float* ag = row + 6 + 2 * jo;
+    ob[0] = pol[0] = ag[0] = tip.x; ob[1] = pol[1] = ag[1] = tip.y; ob[2] = pol[2] = ag[2] = tip.z;
+    ag[3] = g0; ag[4] = g1; ag[5] = g2;
     const float dx = tip.x - g0, dy = tip.y - g1, dz = tip.z - g2;
     const float dist = sqrtf(dx * dx + dy * dy + dz * dz);
 #pragma unroll
@@ -1084,16 +1098,21 @@ __device__ void step_env_block(const Grp& g, EnvSmemT<1>& sm, const float* lane_
     sm.spill = io.row_spill + (size_t)env * SM::SPILL_WORDS;
   }
   // ---- Kuka.apply_action (kuka.py:167-222) ----
-  const float* act = io.action + (size_t)env * D::A;
+  const float* act = io.action + (size_t)env * (io.jc ? io.adim : D::A);
   if (TASK == 2 && hand) {  // grasping: the last action column drives both jaws (kuka.py:169-172)
-    const float grip = (act[3] + 1.0f) * (GRIPPER_ABS_LIMIT / 2);
+    const float grip = (act[io.jc ? 7 : 3] + 1.0f) * (GRIPPER_ABS_LIMIT / 2);
     L.mt0 = L.mt1 = grip; L.mi0 = L.mi1 = FINGER_FORCE * OUTER_DT;
   }
   const float lo[3] = {-0.67f, -0.20f, 0.175f}, hi[3] = {-0.37f, 0.20f, 0.55f};  // kuka.py:40-41
   float ee[3];
+  if (io.jc) {
+    // kuka.py:204-206: joint_state_target (kept in the motor targets) += 0.05 a[:7]; no clipping, no IK
 #pragma unroll
-  for (int k = 0; k < 3; k++) ee[k] = fminf(fmaxf(s[(ST_EE + k) * B] + act[k] * 0.01f, lo[k]), hi[k]);
-  {
+    for (int k = 0; k < 3; k++) ee[k] = s[(ST_EE + k) * B];
+    if (arm) { L.mt0 += act[lane] * 0.05f; L.mi0 = ARM_FORCE * OUTER_DT; }
+  } else {
+#pragma unroll
+    for (int k = 0; k < 3; k++) ee[k] = fminf(fmaxf(s[(ST_EE + k) * B] + act[k] * 0.01f, lo[k]), hi[k]);
     const float tq[4] = {0.f, -1.f, 0.f, 0.f};  // kuka.py:42
     const float qik = inverse_kinematics(g, L, arm ? L.q0 : 0.0f, v3(ee[0], ee[1], ee[2]), tq);
     if (arm) { L.mt0 = qik; L.mi0 = ARM_FORCE * OUTER_DT; }
@@ -1125,6 +1144,12 @@ __device__ void step_env_block(const Grp& g, EnvSmemT<1>& sm, const float* lane_
   const V3 tip_own = p + mul(R, v3(t[0], t[1], t[2]));
   const V3 tip = g.shfl(tip_own, PMG_BODY_LINK7);
   const V3 tv = g.shfl(vo + cross(w, tip_own - p), PMG_BODY_LINK7), tw = g.shfl(w, PMG_BODY_LINK7);
+  // joint control prepends the 7 joint positions to observation and policy_state (kuka_single_step_base_env.py:214-216)
+  const int jo = io.jc ? 7 : 0;
+  if (io.jc && arm) {
+    float* row = io.obs + (size_t)env * io.row_width;
+    row[lane] = L.q0; row[D::O + jo + lane] = L.q0;
+  }
   if (hand) {
     float closeness = 0.0f, finger_vel = 0.0f;
     if (TASK == 2) {
@@ -1142,8 +1167,8 @@ __device__ void step_env_block(const Grp& g, EnvSmemT<1>& sm, const float* lane_
     const float* bk = sm.blk;
     const V3 bx = v3(bk[BK_POS], bk[BK_POS + 1], bk[BK_POS + 2]), bv = v3(bk[BK_V], bk[BK_V + 1], bk[BK_V + 2]), bw = v3(bk[BK_W], bk[BK_W + 1], bk[BK_W + 2]);
     const V3 rel = tip - bx, rv = tv - bv, rw = tw - bw;
-    float* row = io.obs + (size_t)env * D::W;
-    float* obs = row; float* pol = row + D::O; float* ag = pol + D::P; float* dg = ag + D::G;
+    float* row = io.obs + (size_t)env * (D::W + 2 * jo);
+    float* obs = row + jo; float* pol = row + D::O + 2 * jo; float* ag = pol + D::P; float* dg = ag + D::G;
     obs[0] = tip.x; obs[1] = tip.y; obs[2] = tip.z; obs[3] = bx.x; obs[4] = bx.y; obs[5] = bx.z; obs[6] = closeness;
     obs[7] = rel.x; obs[8] = rel.y; obs[9] = rel.z; obs[10] = tv.x; obs[11] = tv.y; obs[12] = tv.z; obs[13] = finger_vel;
     obs[14] = rv.x; obs[15] = rv.y; obs[16] = rv.z; obs[17] = rw.x; obs[18] = rw.y; obs[19] = rw.z;

@@ -112,7 +112,7 @@ struct StepArgs { coop::EnvSmem* sm; StepIO io; };
 void step_body(int lane, void* arg) {
   StepArgs* a = (StepArgs*)arg;
   coop::Grp g; g.lane = lane;
-  coop::step_env_reach(g, *a->sm, lane_table(), a->io, 0);
+  coop::step_env_reach<false>(g, *a->sm, lane_table(), a->io, 0);
 }
 
 struct MinvArgs { coop::EnvSmem* sm; const float* q; const float* qd; float* minv_out; float* q_out; float* qd_out; };

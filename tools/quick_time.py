@@ -5,10 +5,11 @@ import torch
 import pybullet_multigoal_gym_b200 as pmg
 
 CASES = [("reach", 8192), ("push", 4096), ("pick_and_place", 4096), ("block_stack", 2048), ("reach", 65536)]
-if len(sys.argv) > 1:  # e.g. quick_time.py reach:8192 reach:65536
-    CASES = [(a.split(":")[0], int(a.split(":")[1])) for a in sys.argv[1:]]
-for task, B in CASES:
-    env = pmg.make_env(task=task, batch=B, num_block=4, check_actions=False)
+if len(sys.argv) > 1:  # e.g. quick_time.py reach:8192 reach:65536 pick_and_place:4096:jc
+    CASES = [tuple(a.split(":")) for a in sys.argv[1:]]
+for case in CASES:
+    task, B, jc = case[0], int(case[1]), len(case) > 2 and case[2] == "jc"
+    env = pmg.make_env(task=task, batch=B, num_block=4, check_actions=False, joint_control=jc)
     A = env.action_dim
     acts = torch.rand((60, B, A), device="cuda") * 2 - 1
     out = torch.empty((B, env.row_width), device="cuda"); r = torch.empty((B,), device="cuda")
@@ -23,5 +24,5 @@ for task, B in CASES:
         env.step_packed(acts[5 + t], out, r, d, s)
     e1.record(); torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / n
-    print("%-16s B=%6d  %.3f ms/step  %.3f M env-steps/s  overflow=%d" % (task, B, ms, B / ms / 1e3, env.overflow_count), flush=True)
+    print("%-16s" % (task + ("_jc" if jc else "")) + " B=%6d  %.3f ms/step  %.3f M env-steps/s  overflow=%d" % (B, ms, B / ms / 1e3, env.overflow_count), flush=True)
     env.close()
