@@ -15,9 +15,12 @@
 //     inverse is an in-place Gauss-Jordan sweep with one row broadcast per pivot;
 //   * projected Gauss-Seidel: the delta-velocity vector is distributed over the lanes, the owner lane
 //     of a motor / limit row computes the impulse and broadcasts it (one shuffle per row); contact
-//     rows (finger-table) keep J and M^-1 J^T per lane in shared memory and reduce J.dv over the octet;
+//     rows are built with lanes over contact points (J, M^-1 J^T records in shared memory) and swept
+//     replicated on a gathered delta-velocity vector (no shuffles on a path that usually runs diverged);
+//   * narrowphase: lanes over collision pairs; Push / PickAndPlace (EnvSmemT<1>) add the block body, four
+//     more pairs and rows with a block end point, specialised by which ends a row has;
 //   * nothing lives in local memory: per-lane state is ~100 registers, exchange goes through shuffles
-//     and 3.3 KB of shared memory per environment.
+//     and 3.3 KB (Reach) / 7.1 KB (one block) of shared memory per environment.
 // The arithmetic is the same system the thread-per-env kernel (pmg_sim.cuh) and the oracle solve --
 // reference call sequence robots/kuka.py:167-225, envs/base_envs/base_env.py:215-219 -- organised for
 // lanes; the group primitives below are the only device-specific part, and tests/emu/ runs this very

@@ -235,4 +235,32 @@ int pmg_emu_block_step(int task, float* state, float* manifold, const float* act
   return pmg_emu::run_group(blk_body, &a);
 }
 int pmg_emu_block_smem_bytes(void) { return (int)sizeof(coop::EnvSmemT<1>); }
+
+// The joint-control variants (kuka.py:204-206): task 0 Reach (7 action columns, row of 26 floats), 1 Push (7, 47),
+// 2 PickAndPlace (8, 47).
+int pmg_emu_step_jc(int task, float* state, float* manifold, const float* action, float thr, int binary, int max_steps,
+                    float* obs_row, float* reward, uint8_t* done, uint8_t* success) {
+  StepIO io;
+  memset(&io, 0, sizeof io);
+  io.state = state; io.manifold = manifold; io.batch = 1; io.state_words = task == 0 ? Dims<0, 0>::STATE : Dims<1, 1>::STATE;
+  io.action = action; io.obs = obs_row; io.reward = reward; io.done = done; io.success = success;
+  io.thr = thr; io.binary = binary; io.max_steps = max_steps; io.overflow = nullptr; io.epw = 4;
+  io.jc = 1; io.grasp = task == 2; io.adim = task == 2 ? 8 : 7; io.goal_dim = 3; io.row_width = task == 0 ? 26 : 47;
+  if (task == 0) {
+    static coop::EnvSmem sm;
+    memset(&sm, 0, sizeof sm);
+    StepArgs a; a.sm = &sm; a.io = io;
+    return pmg_emu::run_group([](int lane, void* arg) {
+      StepArgs* a = (StepArgs*)arg;
+      coop::Grp g; g.lane = lane;
+      coop::step_env_reach<true>(g, *a->sm, lane_table(), a->io, 0);
+    }, &a);
+  }
+  static coop::EnvSmemT<1> sm;
+  static float spill[coop::EnvSmemT<1>::SPILL_WORDS];
+  memset(&sm, 0, sizeof sm);
+  io.row_spill = spill;
+  BlkArgs a; a.sm = &sm; a.io = io; a.task = task;
+  return pmg_emu::run_group(blk_body, &a);
+}
 }

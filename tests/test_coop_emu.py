@@ -167,3 +167,33 @@ def test_cooperative_block_step_matches_oracle(emu, task, tid, adim, nsteps):
     print("%s: most cached contact points in one step: %d" % (task, most))
     if task == "push":
         assert most > 12                       # rows beyond the 12 shared-memory points: the global spill path ran
+
+
+@pytest.mark.parametrize("task,tid,adim,width", [("reach", 0, 7, 26), ("push", 1, 7, 47), ("pick_and_place", 2, 8, 47)])
+def test_cooperative_joint_control_step_matches_oracle(emu, task, tid, adim, width):
+    """joint_control=True on the cooperative kernels (kuka.py:204-206: motor targets += 0.05 a, no IK; the 7 joint
+    positions prepended to observation and policy_state), one env.step at a time from the oracle's state."""
+    o = O.OracleEnv(task, seed=3, binary_reward=False, joint_control=True)
+    o.reset()
+    o.reset()
+    rng = np.random.RandomState(11)
+    obs, rew = np.zeros(width, np.float32), np.zeros(1, np.float32)
+    dn, su = np.zeros(1, np.uint8), np.zeros(1, np.uint8)
+    nman = 2 if tid == 0 else 6
+    worst = 0.0
+    for t in range(6):
+        st = o.get_state().astype(np.float32)
+        o.set_state(st.astype(np.float64))
+        man = np.zeros(nman * 41, np.float32)
+        a = rng.uniform(-1, 1, adim).astype(np.float32)
+        ro, rr, rd, ri = o.step(a.astype(np.float64))
+        rc = emu.pmg_emu_step_jc(tid, _f(st), _f(man), _f(a), C.c_float(0.05), 0, 50, _f(obs), _f(rew),
+                                 dn.ctypes.data_as(U8), su.ctypes.data_as(U8))
+        assert rc == 0, "divergent collective in the cooperative kernel"
+        want = np.concatenate([ro[k] for k in ("observation", "policy_state", "achieved_goal", "desired_goal")])
+        assert want.shape == (width,)
+        # everything but the velocity entries of the (prefixed) block observation
+        pos = np.arange(width) if tid == 0 else np.r_[0:17, 27:47]
+        worst = max(worst, float(np.abs(obs - want)[pos].max()))
+        assert abs(float(rew[0]) - rr) < 1e-4 and bool(dn[0]) == rd
+    assert worst < 1e-4, worst
