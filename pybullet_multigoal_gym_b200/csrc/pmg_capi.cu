@@ -394,6 +394,70 @@ __global__ void reward_kernel(const float* ag, const float* dg, int64_t n, int g
   ok[i] = na ? 0 : 1;
 }
 
+// The same computation through shared memory, for goal widths whose rows are a power-of-two number of bytes.
+// Measured on the B200 (tools/reward_bw.py, profiles/r01_reward_kernel_bandwidth.txt; algorithmic bytes 8g + 5 per row,
+// inputs of 2-3 GB): the row-per-thread kernel above streams at 94 % (g = 3) and 101 % (g = 12) of the measured copy
+// bandwidth -- its g strided loads hit the lines the first one brought into L1 -- but only 36 % at g = 16 (64-byte
+// rows: the warp's lines fall into a few L1 sets and are evicted before they are re-used).  Here a block walks tiles of
+// 256 x RPT rows: the tile is one contiguous run of floats, read with 16-byte loads by all threads, the differences go
+// to shared memory (row stride g|1 words: odd, so the per-row sums below are bank-conflict free), then thread r
+// accumulates row r in the same order as reward_kernel (bit-identical results): 76 % at g = 16, 69-80 % at g = 3 / 12.
+// Used when g is a multiple of 16 (<= 32) and both arrays are 16-byte aligned.
+constexpr int REWARD_THREADS = 256;
+template <int RPT>  // rows per thread: 256 * RPT rows per tile (small g needs more bytes in flight per block)
+__global__ void __launch_bounds__(REWARD_THREADS) reward_kernel_tiled(const float* __restrict__ ag, const float* __restrict__ dg, int64_t n, int g,
+                                                                      float thr, int binary, float* __restrict__ reward, uint8_t* __restrict__ ok) {
+  constexpr int TILE = REWARD_THREADS * RPT;
+  extern __shared__ float diff[];  // TILE * (g | 1)
+  const int gp = g | 1;
+  const int64_t ntiles = (n + TILE - 1) / TILE;
+  for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int64_t row0 = tile * TILE;
+    const int rows = (int)(n - row0 < TILE ? n - row0 : TILE);
+    const int cnt = rows * g;
+    const float* a = ag + row0 * g;  // row0 * g is a multiple of 256 floats: as aligned as the arrays
+    const float* b = dg + row0 * g;
+    const float4* a4 = reinterpret_cast<const float4*>(a);
+    const float4* b4 = reinterpret_cast<const float4*>(b);
+    for (int v = threadIdx.x; v < (cnt >> 2); v += REWARD_THREADS) {
+      const float4 x = __ldcs(a4 + v), y = __ldcs(b4 + v);
+      int r = (4 * v) / g, k = 4 * v - r * g;
+      const float d[4] = {x.x - y.x, x.y - y.y, x.z - y.z, x.w - y.w};
+#pragma unroll
+      for (int j = 0; j < 4; j++) {
+        diff[r * gp + k] = d[j];
+        if (++k == g) { k = 0; r++; }
+      }
+    }
+    for (int e = (cnt & ~3) + threadIdx.x; e < cnt; e += REWARD_THREADS) {  // the last tile may end inside a 16-byte group
+      const int r = e / g;
+      diff[r * gp + (e - r * g)] = a[e] - b[e];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < RPT; j++) {
+      const int r = threadIdx.x + j * REWARD_THREADS;
+      if (r < rows) {
+        const float* dr = diff + r * gp;
+        float d2 = 0.0f;
+        for (int k = 0; k < g; k++) { const float d = dr[k]; d2 += d * d; }
+        const float d = sqrtf(d2);
+        const bool na = d > thr;
+        reward[row0 + r] = binary ? -(na ? 1.0f : 0.0f) : -d;
+        ok[row0 + r] = na ? 0 : 1;
+      }
+    }
+    __syncthreads();
+  }
+}
+template <int RPT>
+void launch_reward_tiled(const float* ag, const float* dg, int64_t n, int g, float thr, int binary, float* reward, uint8_t* ok, cudaStream_t st) {
+  constexpr int TILE = REWARD_THREADS * RPT;
+  const int64_t ntiles = (n + TILE - 1) / TILE;
+  const unsigned grid = (unsigned)(ntiles < 148 * 8 ? ntiles : 148 * 8);  // 8 resident blocks of 256 threads per SM
+  reward_kernel_tiled<RPT><<<grid, REWARD_THREADS, sizeof(float) * TILE * (g | 1), st>>>(ag, dg, n, g, thr, binary, reward, ok);
+}
+
 // ---- hindsight relabelling (see include/pmg.h) ---------------------------------------------------
 __host__ __device__ inline uint64_t her_mix(uint64_t z) {  // splitmix64 finaliser
   z = (z ^ (z >> 30)) * 0xbf58476d1ce4e5b9ull;
@@ -973,7 +1037,18 @@ int pmg_step_host_blocks(pmg_handle* h, const float* action_host, float* blocks_
 int pmg_compute_reward(const float* ag, const float* dg, int64_t n, int32_t g, float thr, int32_t binary, float* reward, uint8_t* ok, void* stream) {
   if (!ag || !dg || !reward || !ok || n < 0 || g < 1) return fail(PMG_ERR_INVALID, "pmg_compute_reward: bad argument%s");
   if (n == 0) return PMG_OK;
-  reward_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(ag, dg, n, g, thr, binary, reward, ok);
+  // A/B runs: PMG_REWARD_SIMPLE=1 / PMG_REWARD_TILED=1 force one kernel wherever it applies
+  static const bool simple_only = [] { const char* ev = getenv("PMG_REWARD_SIMPLE"); return ev && atoi(ev) != 0; }();
+  static const bool tiled_always = [] { const char* ev = getenv("PMG_REWARD_TILED"); return ev && atoi(ev) != 0; }();
+  const bool aligned = (((uintptr_t)ag | (uintptr_t)dg) & 15u) == 0;
+  if (aligned && g <= 32 && !simple_only && (g % 16 == 0 || tiled_always)) {
+    // <= 27 KB of shared memory per block either way (8 blocks per SM)
+    if (g <= 4) launch_reward_tiled<4>(ag, dg, n, g, thr, binary, reward, ok, (cudaStream_t)stream);
+    else if (g <= 12) launch_reward_tiled<2>(ag, dg, n, g, thr, binary, reward, ok, (cudaStream_t)stream);
+    else launch_reward_tiled<1>(ag, dg, n, g, thr, binary, reward, ok, (cudaStream_t)stream);
+  } else {
+    reward_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(ag, dg, n, g, thr, binary, reward, ok);
+  }
   CUDA_TRY(cudaGetLastError());
   return PMG_OK;
 }

@@ -356,3 +356,21 @@ def test_cooperative_and_thread_per_env_block_kernels_agree(task, adim):
     print("cooperative vs thread-per-env %s kernels: %.2f%% of env-steps within 1e-4, worst %.3g" % (task, 100.0 * good / total, worst))
     assert good >= 0.99 * total and worst < 5e-3
     assert coop.overflow_count == 0 and thread.overflow_count == 0
+
+
+@pytest.mark.parametrize("n,g", [(1, 3), (1025, 3), (513, 12), (257, 16), (4099, 16), (33, 32), (40, 33)])
+def test_compute_reward_kernels_on_ragged_shapes(n, g):
+    """`_compute_reward` over [n, g] rows for both kernels behind pmg_compute_reward (row per thread; tiled through
+    shared memory when g is a multiple of 16) against float64 torch: flags away from the threshold, dense rewards
+    to 1e-6."""
+    env = _mk("reach", 2, binary_reward=False)
+    gen = torch.Generator(device="cuda")
+    gen.manual_seed(n * 100 + g)
+    ag = torch.rand((n, g), device="cuda", generator=gen) * 0.1
+    dg = ag + (torch.rand((n, g), device="cuda", generator=gen) - 0.5) * 0.08
+    r, ok = env._compute_reward(ag, dg)
+    d = (ag.double() - dg.double()).norm(dim=1)
+    safe = (d - 0.05).abs() > 1e-6
+    assert r.shape == (n,) and ok.shape == (n,)
+    assert torch.equal(ok[safe], (d <= 0.05)[safe])
+    assert float((r.double() + d).abs().max()) < 1e-6
