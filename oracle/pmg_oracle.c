@@ -1144,7 +1144,8 @@ int pmgo_get_curriculum(const PmgoEnv* e, double* prob_out) {
 /* kuka_multi_step_base_env.py:350-379, statement by statement (numpy negative indexing included) */
 static void update_curriculum_prob(PmgoEnv* e) {
   const int n = e->nb;
-  int fin[MAXBLK], half[MAXBLK];
+  int fin[MAXBLK] = {0}, half[MAXBLK] = {0};
+  if (n < 2) return; /* the reference raises IndexError on mask_finished[-2] here; pmg_create rejects the combination */
   for (int i = 0; i < n; i++) {
     fin[i] = e->cur_count[i] >= e->cur_goals_per;
     half[i] = e->cur_count[i] >= e->cur_goals_per / 2;
@@ -1345,7 +1346,7 @@ void pmgo_reset(PmgoEnv* e, double* obs_out) {
   robot_reset(e);
   e->elapsed = 0;
   if (!e->cur) e->sub_goal_ind = -1; /* kuka_multi_step_base_env.py:247-248 */
-  double xy[2 * MAXBLK];
+  double xy[2 * MAXBLK] = {0};
   if (e->multi) {
     /* kuka_multi_step_base_env.py:223-240 */
     for (int b = 0; b < e->nb; b++) {
