@@ -130,7 +130,7 @@ def test_thread_per_env_physics_on_host_matches_oracle(emu, task, nb):
     assert sum(int(man[41 * k:41 * k + 1].view(np.int32)[0]) for k in range(npairs)) >= 4 * nb  # blocks rest on 4 points
 
 
-@pytest.mark.parametrize("task,tid,adim,nsteps", [("push", 1, 3, 16), ("pick_and_place", 2, 4, 22)])
+@pytest.mark.parametrize("task,tid,adim,nsteps", [("push", 1, 3, 16), ("pick_and_place", 2, 4, 30)])
 def test_cooperative_block_step_matches_oracle(emu, task, tid, adim, nsteps):
     """The lane-cooperative Push / PickAndPlace step (block + six manifolds in shared memory, rows with a block end
     point, lanes over pairs for the narrowphase and over contact points for the row set-up) against the oracle,
@@ -149,7 +149,9 @@ def test_cooperative_block_step_matches_oracle(emu, task, tid, adim, nsteps):
         man = np.zeros(6 * 41, np.float32)
         tip = o.link_state(0)[:3]
         a = np.zeros(adim, np.float32)
-        a[:3] = np.clip((st[46:49] + np.array([0.0, 0.0, 0.0 if (task == "push" or t > 10) else 0.07]) - tip) / 0.01, -1, 1)
+        # push: straight at the block; pick and place: hover, descend, close the jaws (t >= 16), lift (t >= 22)
+        dz = 0.0 if task == "push" else (0.07 if t <= 10 else (0.0 if t < 22 else 0.08))
+        a[:3] = np.clip((st[46:49] + np.array([0.0, 0.0, dz]) - tip) / 0.01, -1, 1)
         if adim == 4:
             a[3] = -1.0 if t < 16 else 1.0
         ro, rr, rd, ri = o.step(a.astype(np.float64))
@@ -165,6 +167,9 @@ def test_cooperative_block_step_matches_oracle(emu, task, tid, adim, nsteps):
     assert worst < 1e-4, worst
     assert touched > 0                         # the jaws did reach the block (finger-block manifolds in use)
     print("%s: most cached contact points in one step: %d" % (task, most))
+    if task == "pick_and_place":
+        print("pick_and_place: block height after the lift %.4f (oracle %.4f)" % (obs[5], ro["observation"][5]))
+        assert obs[5] > 0.19 and ro["observation"][5] > 0.19   # carried by the friction rows with both end points
     if task == "push":
         assert most > 12                       # rows beyond the 12 shared-memory points: the global spill path ran
 
