@@ -71,7 +71,7 @@ def test_push_scripted_policy_moves_blocks_to_goals():
     # a crude controller pushes the odd block over the table edge (4-6 of 256 end on the floor under either kernel;
     # which of the marginal ones go is chaotic), none may leave the scene
     assert float(on_table.float().mean()) > 0.96
-    assert float(obs["achieved_goal"][:, 2].min()) > 0.01 and float(obs["achieved_goal"][:, 2].max()) < 0.3
+    assert float(obs["achieved_goal"][:, 2].min()) > 0.0 and float(obs["achieved_goal"][:, 2].max()) < 0.3   # on the floor (z = 0.021) at worst
     assert torch.allclose(r, -d1, atol=1e-6)              # dense reward is the negative distance
 
 
