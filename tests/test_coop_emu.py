@@ -202,3 +202,59 @@ def test_cooperative_joint_control_step_matches_oracle(emu, task, tid, adim, wid
         worst = max(worst, float(np.abs(obs - want)[pos].max()))
         assert abs(float(rew[0]) - rr) < 1e-4 and bool(dn[0]) == rd
     assert worst < 1e-4, worst
+
+
+def _block_scenario(emu, task, tid, adim, nsteps, init, policy):
+    """Teacher-forced cooperative block steps against the oracle; returns (worst position-entry error, set of
+    collision pairs that held contact points at a step end, most points at a step end)."""
+    o = O.OracleEnv(task, seed=4, binary_reward=False)
+    o.reset()
+    o.reset()
+    st = o.get_state()
+    init(st)
+    o.set_state(st)
+    obs, rew = np.zeros(33, np.float32), np.zeros(1, np.float32)
+    dn, su = np.zeros(1, np.uint8), np.zeros(1, np.uint8)
+    worst, most, pairs = 0.0, 0, set()
+    pos = np.r_[0:10, 20:33]
+    for t in range(nsteps):
+        st = o.get_state().astype(np.float32)
+        o.set_state(st.astype(np.float64))
+        man = np.zeros(6 * 41, np.float32)
+        a = policy(t, st, o.link_state(0)[:3]).astype(np.float32)
+        ro, rr, rd, ri = o.step(a.astype(np.float64))
+        rc = emu.pmg_emu_block_step(tid, _f(st), _f(man), _f(a), C.c_float(0.05), 0, 50, _f(obs), _f(rew),
+                                    dn.ctypes.data_as(U8), su.ctypes.data_as(U8))
+        assert rc == 0, "divergent collective in the cooperative kernel"
+        want = np.concatenate([ro[k] for k in ("observation", "policy_state", "achieved_goal", "desired_goal")])
+        worst = max(worst, float(np.abs(obs - want)[pos].max()))
+        cnt = [int(man[41 * k:41 * k + 1].view(np.int32)[0]) for k in range(6)]
+        most = max(most, sum(cnt))
+        pairs |= {k for k in range(6) if cnt[k]}
+    return worst, pairs, most, float(obs[5])
+
+
+def test_cooperative_block_falls_to_the_floor_like_the_oracle(emu):
+    """A block released beyond the table edge: free fall, impact on the floor box (pair 3), bounce from the
+    penetration recovery, rest -- the floor-block rows of the cooperative kernel."""
+    def init(st):
+        st[46:49] = [-0.52, 0.37, 0.30]
+        st[53:59] = 0.0
+    worst, pairs, most, z = _block_scenario(emu, "push", 1, 3, 9, init, lambda t, st, tip: np.zeros(3))
+    assert worst < 1e-4, worst
+    assert 3 in pairs and z < 0.03   # on the floor at the end
+
+
+def test_cooperative_closed_jaws_press_on_the_block_like_the_oracle(emu):
+    """Hover over the block, then drive the closed jaws down onto it: finger-block rows loaded against the table-block
+    rows (pairs 2, 4, 5 together)."""
+    def policy(t, st, tip):
+        a = np.zeros(4)
+        a[:3] = np.clip((st[46:49] + np.array([0.0, 0.0, 0.08 if t <= 6 else 0.0]) - tip) / 0.01, -1, 1)
+        if t > 12:
+            a[2] = -1.0
+        a[3] = 1.0
+        return a
+    worst, pairs, most, z = _block_scenario(emu, "pick_and_place", 2, 4, 16, lambda st: None, policy)
+    assert worst < 1e-4, worst
+    assert {2, 4, 5} <= pairs and most >= 10
