@@ -36,7 +36,8 @@ namespace coop {
 
 constexpr int GL = 8;        // lanes per environment
 constexpr int R_J = 0, R_RHS = 9, R_DINV = 10, R_MJ = 12, R_DENOM = 21, R_MU = 22;  // contact row record, robot part
-constexpr int R_BD = 24, R_BA = 28;  // block part (NBLK > 0): direction d[3] . | lever arm r_B x d [3] has_block
+constexpr int R_BD = 24, R_BA = 28;  // block part (NBLK > 0): direction d[3] has_robot | lever arm r_B x d [3] has_block
+constexpr int R_AA = 32, R_IDX = 36;  // NBLK > 1: lever arm r_A x d [3] . | block index of end A, of end B (-1: none)
 constexpr int MINV_LD = 12;  // row stride of M^-1 in shared memory
 
 // Shared memory of one environment.  NBLK = 0: Reach (two finger-table pairs, <= 8 contact points);
@@ -50,18 +51,19 @@ template <int NBLK>
 struct __align__(16) EnvSmemT : RowSpill<NBLK> {
   static constexpr int NB = NBLK;
   static constexpr int NPAIRS = num_pairs(NBLK);                // 2 / 6
-  static constexpr int MAXPTS = NBLK == 0 ? 8 : 24;             // cached contact points that get rows
+  static constexpr int MAXPTS = NBLK == 0 ? 8 : (NBLK == 1 ? 24 : 48);  // cached contact points that get rows
   static constexpr int SPTS = NBLK == 0 ? 8 : 12;               // ... of which in shared memory
-  static constexpr int ROW_W = NBLK == 0 ? 24 : 32;             // floats per contact row record (16-byte aligned thirds)
+  static constexpr int ROW_W = NBLK == 0 ? 24 : (NBLK == 1 ? 32 : 40);  // floats per contact row record (16-byte aligned parts)
+  static constexpr int NSCR = NPAIRS < GL ? NPAIRS : GL;        // narrowphase scratch areas (one per lane that runs pairs)
   float pub[7][8];                  // per arm dof: axis a, v = (p - Pref) x a
   float minv[ND * MINV_LD];         // 9x9, rows padded to 12
   float man[(NPAIRS * MAN_WORDS + 3) / 4 * 4];  // persistent manifolds (41 words per pair)
   float hand[24];                   // gripper frame for the contact rows: Rg[9] pf1 pf2 Pref ax1 (kept out of registers)
-  float vq[NBLK == 0 ? 12 : 16];    // joint (+ block) velocities for the row set-up, then the PGS delta velocities
+  float vq[NBLK == 0 ? 12 : (ND + 6 * NBLK + 3) / 4 * 4];  // joint (+ block) velocities for the row set-up, then the PGS delta velocities
   float rows[SPTS * 3][ROW_W];      // contact rows (layout R_* above); narrowphase scratch before they are built
   float app[2][MAXPTS * 3];         // accumulated impulses of the contact rows, double buffered over the PGS iterations
-  float blk[NBLK > 0 ? 24 : 1];     // block: pos[3] quat[4] v[3] w[3] R[9]
-  static_assert(NPAIRS * sizeof(BoxScratch) <= SPTS * 3 * ROW_W * sizeof(float), "narrowphase scratch must fit in the contact-row area");
+  float blk[NBLK > 0 ? 24 * NBLK : 1];  // per block: pos[3] quat[4] v[3] w[3] R[9] (+ 2 spare words)
+  static_assert(NSCR * sizeof(BoxScratch) <= SPTS * 3 * ROW_W * sizeof(float), "narrowphase scratch must fit in the contact-row area");
   static constexpr int SPILL_WORDS = (MAXPTS - SPTS) * 3 * ROW_W;  // global scratch per environment
   __device__ __forceinline__ float* spill_row(int r) { return this->spill + (r - SPTS * 3) * ROW_W; }  // r >= 3 SPTS
 };
@@ -652,6 +654,210 @@ __device__ __noinline__ float contact_sweep(Grp g, SM& sm, int nrow_it) {  // nr
   return cres;
 }
 
+// ---- multi-block environments (BlockStack / BlockRearrange, NBLK > 1) ------------------------------------------------
+// Row set-up: as contact_row_setup_blk, but either end may be a block (block-block pairs have two) and the blocks are
+// looked up by index.  Signs as in the thread-per-env kernels (pmg_sim.cuh row_velocity / row_apply): end A sees
+// +impulse, end B -impulse.
+template <bool SPILL, class SM>
+__device__ __noinline__ void contact_row_setup_multi(SM& sm, int c) {
+  int k = 0, i = c;
+#pragma unroll 1
+  for (; k < SM::NPAIRS; k++) {
+    const int n = __float_as_int(sm.man[k * MAN_WORDS]);
+    if (i < n) break;
+    i -= n;
+  }
+  const PairInfo pi = pair_info<SM::NB>(k);
+  const bool robotA = pi.ka == G_FINGER1 || pi.ka == G_FINGER2, blockA = pi.ka == G_BLOCK, blockB = pi.kb == G_BLOCK;
+  const float* hd = sm.hand;
+  M3 Rg;
+  Rg.r0 = v3(hd[0], hd[1], hd[2]); Rg.r1 = v3(hd[3], hd[4], hd[5]); Rg.r2 = v3(hd[6], hd[7], hd[8]);
+  const V3 pf1 = v3(hd[9], hd[10], hd[11]), pf2 = v3(hd[12], hd[13], hd[14]), Pref = v3(hd[15], hd[16], hd[17]);
+  const V3 ax1 = v3(hd[18], hd[19], hd[20]), ax2 = -ax1;
+  const float* mp = sm.man + k * MAN_WORDS + 1 + 10 * i;
+  const V3 lA = v3(mp[0], mp[1], mp[2]), lB = v3(mp[3], mp[4], mp[5]), nB = v3(mp[6], mp[7], mp[8]);
+  const float dist = mp[9];
+  const V3 wr = robotA ? mul(Rg, lA) + (pi.ka == G_FINGER1 ? pf1 : pf2) - Pref : v3(0, 0, 0);
+  V3 rA = v3(0, 0, 0), rB = v3(0, 0, 0), av = v3(0, 0, 0), aw = v3(0, 0, 0), bv = v3(0, 0, 0), bw = v3(0, 0, 0);
+  if (blockA) {
+    const float* bk = sm.blk + 24 * pi.ia;
+    M3 R;
+    R.r0 = v3(bk[BK_R], bk[BK_R + 1], bk[BK_R + 2]); R.r1 = v3(bk[BK_R + 3], bk[BK_R + 4], bk[BK_R + 5]); R.r2 = v3(bk[BK_R + 6], bk[BK_R + 7], bk[BK_R + 8]);
+    rA = mul(R, lA);
+    av = v3(bk[BK_V], bk[BK_V + 1], bk[BK_V + 2]); aw = v3(bk[BK_W], bk[BK_W + 1], bk[BK_W + 2]);
+  }
+  if (blockB) {
+    const float* bk = sm.blk + 24 * pi.ib;
+    M3 R;
+    R.r0 = v3(bk[BK_R], bk[BK_R + 1], bk[BK_R + 2]); R.r1 = v3(bk[BK_R + 3], bk[BK_R + 4], bk[BK_R + 5]); R.r2 = v3(bk[BK_R + 6], bk[BK_R + 7], bk[BK_R + 8]);
+    rB = mul(R, lB);
+    bv = v3(bk[BK_V], bk[BK_V + 1], bk[BK_V + 2]); bw = v3(bk[BK_W], bk[BK_W + 1], bk[BK_W + 2]);
+  }
+  V3 t1, t2;
+  plane_space(nB, t1, t2);
+  const float mu = geom_friction(pi.ka) * geom_friction(pi.kb);
+#pragma unroll 1
+  for (int kk = 0; kk < 3; kk++) {
+    const V3 d = kk == 0 ? nB : (kk == 1 ? t1 : t2);
+    float* row = SPILL ? sm.spill_row(c * 3 + kk) : sm.rows[SPILL ? 0 : c * 3 + kk];
+    const V3 xa = cross(rA, d), xb = cross(rB, d);
+    float denom = 0.0f, rel_vel = 0.0f;
+    if (blockA) { denom += BLOCK_INV_MASS + BLOCK_INV_INERTIA * dot(xa, xa); rel_vel += dot(d, av) + dot(xa, aw); }
+    if (blockB) { denom += BLOCK_INV_MASS + BLOCK_INV_INERTIA * dot(xb, xb); rel_vel -= dot(d, bv) + dot(xb, bw); }
+    if (robotA) {
+      const V3 m = cross(wr, d);
+      float J[ND];
+#pragma unroll
+      for (int j = 0; j < 7; j++) {
+        const float4 p0 = *reinterpret_cast<const float4*>(sm.pub[j]);
+        const float2 p1 = *reinterpret_cast<const float2*>(sm.pub[j] + 4);
+        J[j] = p0.x * m.x + p0.y * m.y + p0.z * m.z + p0.w * d.x + p1.x * d.y + p1.y * d.z;
+      }
+      J[7] = pi.ka == G_FINGER1 ? dot(d, ax1) : 0.0f;
+      J[8] = pi.ka == G_FINGER2 ? dot(d, ax2) : 0.0f;
+#pragma unroll
+      for (int j = 0; j < ND; j++) { row[R_J + j] = J[j]; rel_vel += J[j] * sm.vq[j]; }
+#pragma unroll 1
+      for (int r = 0; r < ND; r++) {
+        const float4* mr = reinterpret_cast<const float4*>(sm.minv + r * MINV_LD);
+        const float4 m0 = mr[0], m1 = mr[1], m2 = mr[2];
+        const float acc = (m0.x * J[0] + m0.y * J[1] + m0.z * J[2]) + (m0.w * J[3] + m1.x * J[4] + m1.y * J[5]) + (m1.z * J[6] + m1.w * J[7] + m2.x * J[8]);
+        row[R_MJ + r] = acc;
+        denom += row[R_J + r] * acc;
+      }
+    } else {
+      const float4 z = {0.0f, 0.0f, 0.0f, 0.0f};
+#pragma unroll
+      for (int j = 0; j < 6; j++) reinterpret_cast<float4*>(row)[j] = z;
+    }
+    const float dinv = 1.0f / denom;
+    float rhs;
+    if (kk == 0) {
+      const float pen = dist + LINEAR_SLOP;
+      float pos_err = 0.0f, vel_err = -rel_vel;
+      if (pen > 0.0f) vel_err -= pen * INV_DT; else pos_err = -pen * CONTACT_ERP * INV_DT;
+      rhs = (pos_err + vel_err) * dinv;
+    } else rhs = -rel_vel * dinv;
+    row[R_RHS] = rhs; row[R_DINV] = dinv; row[R_DENOM] = denom; row[R_MU] = mu;
+    row[R_BD] = d.x; row[R_BD + 1] = d.y; row[R_BD + 2] = d.z; row[R_BD + 3] = robotA ? 1.0f : 0.0f;
+    row[R_BA] = xb.x; row[R_BA + 1] = xb.y; row[R_BA + 2] = xb.z; row[R_BA + 3] = blockB ? 1.0f : 0.0f;
+    row[R_AA] = xa.x; row[R_AA + 1] = xa.y; row[R_AA + 2] = xa.z; row[R_AA + 3] = blockA ? 1.0f : 0.0f;
+    row[R_IDX] = __int_as_float(blockA ? pi.ia : -1); row[R_IDX + 1] = __int_as_float(blockB ? pi.ib : -1);
+    sm.app[0][c * 3 + kk] = 0.0f;
+  }
+}
+
+// One Gauss-Seidel pass for multi-block environments.  The joint delta velocities are replicated as in contact_sweep;
+// the blocks' are not (a register array cannot be indexed by a run-time block number): LANE b KEEPS BLOCK b's six
+// deltas, a row fetches its one or two blocks with run-time-source shuffles inside the octet (the whole octet is on
+// this path, so the shuffles are legal although the warp has diverged) and the owner lanes apply the impulse.
+template <class SM>
+__device__ __noinline__ float contact_sweep_multi(Grp g, SM& sm, int nrow_it) {  // nrow | iteration parity << 8
+  const int nrow = nrow_it & 0xff, it = nrow_it >> 8;
+  const int lane = g.lane;
+  const float* app_rd = sm.app[it & 1];
+  float* app_wr = sm.app[(it & 1) ^ 1];
+  float dq[ND], bd[6];
+#pragma unroll
+  for (int j = 0; j < ND; j++) dq[j] = sm.vq[j];
+#pragma unroll
+  for (int j = 0; j < 6; j++) bd[j] = lane < SM::NB ? sm.vq[ND + 6 * lane + j] : 0.0f;
+  float cres = 0.0f;
+  auto ld4 = [](const float* p) { return *reinterpret_cast<const float4*>(p); };
+  // velocity of the row's block ends: + end A, - end B
+  auto block_vel = [&](const float4& d, const float4& xa, const float4& xb, int ia, int ib) {
+    float v = 0.0f;
+    if (ia >= 0) {
+      const float l0 = g.shfl(bd[0], ia), l1 = g.shfl(bd[1], ia), l2 = g.shfl(bd[2], ia), w0 = g.shfl(bd[3], ia), w1 = g.shfl(bd[4], ia), w2 = g.shfl(bd[5], ia);
+      v += (d.x * l0 + d.y * l1 + d.z * l2) + (xa.x * w0 + xa.y * w1 + xa.z * w2);
+    }
+    if (ib >= 0) {
+      const float l0 = g.shfl(bd[0], ib), l1 = g.shfl(bd[1], ib), l2 = g.shfl(bd[2], ib), w0 = g.shfl(bd[3], ib), w1 = g.shfl(bd[4], ib), w2 = g.shfl(bd[5], ib);
+      v -= (d.x * l0 + d.y * l1 + d.z * l2) + (xb.x * w0 + xb.y * w1 + xb.z * w2);
+    }
+    return v;
+  };
+  auto block_apply = [&](const float4& d, const float4& xa, const float4& xb, int ia, int ib, float dl) {
+    const float lm = dl * BLOCK_INV_MASS, li = dl * BLOCK_INV_INERTIA;
+    if (lane == ia) { bd[0] += lm * d.x; bd[1] += lm * d.y; bd[2] += lm * d.z; bd[3] += li * xa.x; bd[4] += li * xa.y; bd[5] += li * xa.z; }
+    if (lane == ib) { bd[0] -= lm * d.x; bd[1] -= lm * d.y; bd[2] -= lm * d.z; bd[3] -= li * xb.x; bd[4] -= li * xb.y; bd[5] -= li * xb.z; }
+  };
+  auto normal_row = [&](const float* row, int c) {
+    const float4 jc = ld4(row + R_J + 8), mc = ld4(row + R_MJ + 8), d = ld4(row + R_BD), xb = ld4(row + R_BA), xa = ld4(row + R_AA);
+    const int ia = __float_as_int(row[R_IDX]), ib = __float_as_int(row[R_IDX + 1]);
+    const bool rob = d.w != 0.0f;
+    RowVec j, mj;
+    float v = 0.0f;
+    if (rob) { j.a = ld4(row + R_J); j.b = ld4(row + R_J + 4); j.c = jc; mj.a = ld4(row + R_MJ); mj.b = ld4(row + R_MJ + 4); mj.c = mc; v = row_dot(j, dq); }
+    v += block_vel(d, xa, xb, ia, ib);
+    const float app = app_rd[c * 3];
+    float dl = jc.y - v * jc.z;
+    const float sum = fminf(fmaxf(app + dl, 0.0f), 1e10f);
+    dl = sum - app;
+    if (rob) row_axpy(mj, dl, dq);
+    block_apply(d, xa, xb, ia, ib, dl);
+    const float rr = dl * mc.y;
+    cres = fmaxf(cres, rr * rr);
+    app_wr[c * 3] = sum;
+  };
+  auto friction_rows = [&](const float* ra, const float* rb, int c) {
+    const float total = app_wr[c * 3];
+    const float appA = app_rd[c * 3 + 1], appB = app_rd[c * 3 + 2];
+    float sA = appA, sB = appB;
+    if (total > 0.0f) {  // uniform over the octet: every lane holds the same impulses
+      const float4 jca = ld4(ra + R_J + 8), jcb = ld4(rb + R_J + 8), mca = ld4(ra + R_MJ + 8), mcb = ld4(rb + R_MJ + 8);
+      const float4 da = ld4(ra + R_BD), xba = ld4(ra + R_BA), xaa = ld4(ra + R_AA), db = ld4(rb + R_BD), xbb = ld4(rb + R_BA), xab = ld4(rb + R_AA);
+      const int ia = __float_as_int(ra[R_IDX]), ib = __float_as_int(ra[R_IDX + 1]);
+      const bool rob = da.w != 0.0f;
+      RowVec ja, jb, mja, mjb;
+      float vA = 0.0f, vB = 0.0f;
+      if (rob) {
+        ja.a = ld4(ra + R_J); ja.b = ld4(ra + R_J + 4); ja.c = jca; jb.a = ld4(rb + R_J); jb.b = ld4(rb + R_J + 4); jb.c = jcb;
+        mja.a = ld4(ra + R_MJ); mja.b = ld4(ra + R_MJ + 4); mja.c = mca; mjb.a = ld4(rb + R_MJ); mjb.b = ld4(rb + R_MJ + 4); mjb.c = mcb;
+        vA = row_dot(ja, dq); vB = row_dot(jb, dq);
+      }
+      vA += block_vel(da, xaa, xba, ia, ib); vB += block_vel(db, xab, xbb, ia, ib);
+      const float lim = mca.z * total;  // R_MU
+      float dA = jca.y - vA * jca.z, dB = jcb.y - vB * jcb.z;
+      sA = appA + dA; sB = appB + dB;
+      const float s2 = sA * sA + sB * sB;
+      if (s2 >= lim * lim) {
+        const float sc = s2 > 0.0f ? lim * rsqrtf(s2) : 0.0f;
+        const float cA = fabsf(sA) * sc, cB = s2 > 0.0f ? fabsf(sB) * sc : lim;
+        sA = fminf(fmaxf(sA, -cA), cA);
+        sB = fminf(fmaxf(sB, -cB), cB);
+        dA = sA - appA; dB = sB - appB;
+      }
+      if (rob) { row_axpy(mja, dA, dq); row_axpy(mjb, dB, dq); }
+      block_apply(da, xaa, xba, ia, ib, dA); block_apply(db, xab, xbb, ia, ib, dB);
+      const float r1_ = dA * mca.y, r2_ = dB * mcb.y;
+      cres = fmaxf(cres, fmaxf(r1_ * r1_, r2_ * r2_));
+    }
+    app_wr[c * 3 + 1] = sA; app_wr[c * 3 + 2] = sB;
+  };
+  const int nsh = nrow < SM::SPTS ? nrow : SM::SPTS;
+#pragma unroll 1
+  for (int c = 0; c < nsh; c++) normal_row(sm.rows[c * 3], c);
+#pragma unroll 1
+  for (int c = SM::SPTS; c < nrow; c++) normal_row(sm.spill_row(c * 3), c);
+  g.sync();
+#pragma unroll 1
+  for (int c = 0; c < nsh; c++) friction_rows(sm.rows[c * 3 + 1], sm.rows[c * 3 + 2], c);
+#pragma unroll 1
+  for (int c = SM::SPTS; c < nrow; c++) friction_rows(sm.spill_row(c * 3 + 1), sm.spill_row(c * 3 + 2), c);
+  g.sync();  // every lane has read sm.vq
+  if (lane == 0) {
+#pragma unroll
+    for (int j = 0; j < ND; j++) sm.vq[j] = dq[j];
+  }
+  if (lane < SM::NB) {
+#pragma unroll
+    for (int j = 0; j < 6; j++) sm.vq[ND + 6 * lane + j] = bd[j];
+  }
+  g.sync();
+  return cres;
+}
+
 // Development aid (tools/coop_timing.py builds a separate library with -DPMG_COOP_TIMING): cycles spent by
 // octets with cached contacts in [0] the whole substep, [1] narrowphase, [2] row set-up, [3] contact sweeps,
 // and [4] the number of such substeps; [5] whole substep / [6] count for contact-free octets.
@@ -667,14 +873,15 @@ __device__ __noinline__ float contact_sweep(Grp g, SM& sm, int nrow_it) {  // nr
 template <class SM>
 __device__ void substep(const Grp& g, SM& sm, Lane& L) {
   constexpr bool BLK = SM::NB > 0;
+  constexpr bool MULTI = SM::NB > 1;  // BlockStack / BlockRearrange: lane b owns block b
   PMG_T(t_begin);
 #ifdef PMG_COOP_TIMING
   long long t_sweeps = 0;
 #endif
   const int lane = g.lane;
   const bool arm = lane < 7, hand = lane == 7;
-  if (BLK && lane == 0) {  // the block's orientation matrix for the narrowphase and the rows (visible after the sync below)
-    float* bk = sm.blk;
+  if (BLK && (MULTI ? lane < SM::NB : lane == 0)) {  // the block's orientation matrix for the narrowphase and the rows (visible after the sync below)
+    float* bk = sm.blk + (MULTI ? 24 * lane : 0);
     const M3 Rb = quat_to_m3(bk[BK_QUAT], bk[BK_QUAT + 1], bk[BK_QUAT + 2], bk[BK_QUAT + 3]);
     bk[BK_R] = Rb.r0.x; bk[BK_R + 1] = Rb.r0.y; bk[BK_R + 2] = Rb.r0.z; bk[BK_R + 3] = Rb.r1.x; bk[BK_R + 4] = Rb.r1.y;
     bk[BK_R + 5] = Rb.r1.z; bk[BK_R + 6] = Rb.r2.x; bk[BK_R + 7] = Rb.r2.y; bk[BK_R + 8] = Rb.r2.z;
@@ -758,11 +965,38 @@ __device__ void substep(const Grp& g, SM& sm, Lane& L) {
   // collision detection of the two finger-table pairs: lane k runs pair k on the shared-memory manifold
   PMG_T(t_col0);
   if (BLK) g.sync();  // block pose of this substep (integration of the last one, orientation matrix above)
-  if (lane < SM::NPAIRS) {
+  if constexpr (MULTI) {
+    // lane k runs pairs k, k + 8, ...: the same geometry look-up as the thread-per-env kernels, blocks from shared memory
+    ManRef mr; mr.man = sm.man; mr.stride = 1;
+    constexpr int SCR_STRIDE = SM::SPTS * 3 * SM::ROW_W / SM::NSCR / 4 * 4;
+    BoxScratch& scr = *reinterpret_cast<BoxScratch*>(&sm.rows[0][0] + lane * SCR_STRIDE);
+    const float tc[3] = PMG_TABLE_CENTER, fc[3] = PMG_FLOOR_CENTER;
+#pragma unroll 1
+    for (int k = lane; k < SM::NPAIRS; k += GL) {
+      const PairInfo pi = pair_info<SM::NB>(k);
+      V3 pa, pb;
+      M3 Ra = m3_identity(), Rb = m3_identity();
+      if (pi.ka == G_FINGER1 || pi.ka == G_FINGER2) { pa = pi.ka == G_FINGER1 ? pf1 : pf2; Ra = Rg; }
+      else if (pi.ka == G_TABLE) pa = v3(tc[0], tc[1], tc[2]);
+      else if (pi.ka == G_FLOOR) pa = v3(fc[0], fc[1], fc[2]);
+      else {
+        const float* bk = sm.blk + 24 * pi.ia;
+        pa = v3(bk[BK_POS], bk[BK_POS + 1], bk[BK_POS + 2]);
+        Ra.r0 = v3(bk[BK_R], bk[BK_R + 1], bk[BK_R + 2]); Ra.r1 = v3(bk[BK_R + 3], bk[BK_R + 4], bk[BK_R + 5]); Ra.r2 = v3(bk[BK_R + 6], bk[BK_R + 7], bk[BK_R + 8]);
+      }
+      if (pi.kb == G_TABLE) pb = v3(tc[0], tc[1], tc[2]);
+      else {
+        const float* bk = sm.blk + 24 * pi.ib;
+        pb = v3(bk[BK_POS], bk[BK_POS + 1], bk[BK_POS + 2]);
+        Rb.r0 = v3(bk[BK_R], bk[BK_R + 1], bk[BK_R + 2]); Rb.r1 = v3(bk[BK_R + 3], bk[BK_R + 4], bk[BK_R + 5]); Rb.r2 = v3(bk[BK_R + 6], bk[BK_R + 7], bk[BK_R + 8]);
+      }
+      collide_pair(mr, k, pa, Ra, geom_half(pi.ka), geom_anchor(pi.ka), geom_static(pi.ka), pb, Rb, geom_half(pi.kb), geom_anchor(pi.kb), scr);
+    }
+  } else if (lane < SM::NPAIRS) {
     ManRef mr; mr.man = sm.man; mr.stride = 1;
     const float tc[3] = PMG_TABLE_CENTER, th[3] = PMG_TABLE_HALF, fh[3] = PMG_FINGER_HALF;
     // the narrowphase work arrays live in the (not yet used) contact-row area of shared memory
-    constexpr int SCR_STRIDE = SM::SPTS * 3 * SM::ROW_W / SM::NPAIRS / 4 * 4;
+    constexpr int SCR_STRIDE = SM::SPTS * 3 * SM::ROW_W / SM::NSCR / 4 * 4;
     BoxScratch& scr = *reinterpret_cast<BoxScratch*>(&sm.rows[0][0] + lane * SCR_STRIDE);
     if constexpr (!BLK) {
       collide_pair(mr, lane, lane == 0 ? pf1 : pf2, Rg, v3(fh[0], fh[1], fh[2]), v3(0, 0, 0), false,
@@ -861,15 +1095,15 @@ __device__ void substep(const Grp& g, SM& sm, Lane& L) {
   }
   sm.vq[L.dof0] = L.qd0;
   if (hand) sm.vq[8] = L.qd1;
-  if (BLK && lane == 0) {  // free cube: gravity + Bullet's velocity damping; isotropic inertia => no gyro term
-    float* bk = sm.blk;
+  if (BLK && (MULTI ? lane < SM::NB : lane == 0)) {  // free cube: gravity + Bullet's velocity damping; isotropic inertia => no gyro term
+    float* bk = sm.blk + (MULTI ? 24 * lane : 0);
     V3 bv = v3(bk[BK_V], bk[BK_V + 1], bk[BK_V + 2]), bw = v3(bk[BK_W], bk[BK_W + 1], bk[BK_W + 2]);
     const float kl = LINK_DAMPING + LINK_DAMPING * norm(bv), ka = LINK_DAMPING + LINK_DAMPING * norm(bw);
     bv += DT * (v3(0, 0, -GRAVITY) - kl * bv);
     bw -= (DT * ka) * bw;
     bk[BK_V] = bv.x; bk[BK_V + 1] = bv.y; bk[BK_V + 2] = bv.z; bk[BK_W] = bw.x; bk[BK_W + 1] = bw.y; bk[BK_W + 2] = bw.z;
 #pragma unroll
-    for (int j = 0; j < 6; j++) sm.vq[(BLK ? ND : 0) + j] = 0.0f;  // the block's PGS delta velocities
+    for (int j = 0; j < 6; j++) sm.vq[(BLK ? ND : 0) + (MULTI ? 6 * lane : 0) + j] = 0.0f;  // the block's PGS delta velocities
   }
   g.sync();  // minv, vq, the block velocity and the manifolds are visible to the whole octet
   // 8. constraint rows
@@ -928,8 +1162,13 @@ __device__ void substep(const Grp& g, SM& sm, Lane& L) {
       if (lane < nrow) contact_row_setup(sm, lane, n0);
     } else {
       for (int c = lane; c < nrow; c += GL) {
-        if (c < SM::SPTS) contact_row_setup_blk<false>(sm, c);
-        else contact_row_setup_blk<true>(sm, c);
+        if constexpr (MULTI) {
+          if (c < SM::SPTS) contact_row_setup_multi<false>(sm, c);
+          else contact_row_setup_multi<true>(sm, c);
+        } else {
+          if (c < SM::SPTS) contact_row_setup_blk<false>(sm, c);
+          else contact_row_setup_blk<true>(sm, c);
+        }
       }
     }
     g.sync();
@@ -957,7 +1196,8 @@ __device__ void substep(const Grp& g, SM& sm, Lane& L) {
       if (hand) sm.vq[8] = s.dqd1;
       g.sync();
       PMG_T(t_sw0);
-      res = fmaxf(res, contact_sweep(g, sm, nrow | ((it & 1) << 8) | row_kinds));
+      if constexpr (MULTI) res = fmaxf(res, contact_sweep_multi(g, sm, nrow | ((it & 1) << 8)));
+      else res = fmaxf(res, contact_sweep(g, sm, nrow | ((it & 1) << 8) | row_kinds));
 #ifdef PMG_COOP_TIMING
       t_sweeps += clock64() - t_sw0;
 #endif
@@ -972,9 +1212,9 @@ __device__ void substep(const Grp& g, SM& sm, Lane& L) {
   L.qd1 = hand ? fminf(fmaxf(L.qd1 + s.dqd1, -MAX_COORD_VEL), MAX_COORD_VEL) : 0.0f;
   L.q0 += L.qd0 * DT;
   L.q1 += L.qd1 * DT;
-  if (BLK && lane == 0) {  // block: add the solver's delta velocities, integrate (exponential map for the orientation)
-    float* bk = sm.blk;
-    const float* dv = sm.vq + (BLK ? ND : 0);
+  if (BLK && (MULTI ? lane < SM::NB : lane == 0)) {  // block: add the solver's delta velocities, integrate (exponential map for the orientation)
+    float* bk = sm.blk + (MULTI ? 24 * lane : 0);
+    const float* dv = sm.vq + (BLK ? ND : 0) + (MULTI ? 6 * lane : 0);
     V3 bv = v3(bk[BK_V] + dv[0], bk[BK_V + 1] + dv[1], bk[BK_V + 2] + dv[2]);
     V3 bw = v3(bk[BK_W] + dv[3], bk[BK_W + 1] + dv[4], bk[BK_W + 2] + dv[5]);
     bk[BK_V] = bv.x; bk[BK_V + 1] = bv.y; bk[BK_V + 2] = bv.z; bk[BK_W] = bw.x; bk[BK_W + 1] = bw.y; bk[BK_W + 2] = bw.z;
@@ -1191,6 +1431,63 @@ __device__ void step_env_block(const Grp& g, EnvSmemT<1>& sm, const float* lane_
     io.reward[env] = io.binary ? -(na ? 1.0f : 0.0f) : -dist;
     io.success[env] = na ? 0 : 1;
     io.done[env] = elapsed >= io.max_steps ? 1 : 0;
+  }
+}
+
+// ---- multi-block environments: physics of one env.step() ---------------------------------------------------------
+// BlockStack / BlockRearrange with NBLK blocks (4-column action, grasping).  State in / state out only: the
+// observation and sub-goal assembly of the multi-step tasks (8 + 16 NBLK entries, grip goal, task decomposition) still
+// lives in the thread-per-env kernel's write_obs, so this step is not wired into libpmg.so yet -- tests/emu runs it
+// against the oracle.
+template <int NBLK>
+__device__ void step_env_multi_physics(const Grp& g, EnvSmemT<NBLK>& sm, const float* lane_consts, const StepIO& io, int env) {
+  using SM = EnvSmemT<NBLK>;
+  const int lane = g.lane;
+  const bool arm = lane < 7, hand = lane == 7;
+  const size_t B = io.batch;
+  float* s = io.state + env;
+  Lane L;
+  L.lc = lane_consts + lane * LC_W;
+  L.dof0 = lane;
+  L.q0 = s[(ST_Q + lane) * B]; L.qd0 = s[(ST_QD + lane) * B]; L.mt0 = s[(ST_MT + lane) * B]; L.mi0 = s[(ST_MI + lane) * B];
+  L.q1 = hand ? s[(ST_Q + 8) * B] : 0.0f; L.qd1 = hand ? s[(ST_QD + 8) * B] : 0.0f;
+  L.mt1 = hand ? s[(ST_MT + 8) * B] : 0.0f; L.mi1 = hand ? s[(ST_MI + 8) * B] : 0.0f;
+  L.dtau0 = L.dtau1 = 0.0f;
+  for (int w = lane; w < SM::NPAIRS * MAN_WORDS; w += GL) sm.man[w] = io.manifold[(size_t)w * B + env];
+  for (int w = lane; w < 13 * NBLK; w += GL) sm.blk[24 * (w / 13) + w % 13] = s[(size_t)(ST_BLK + w) * B];
+  if (lane == 0) {
+    sm.blk[23] = 0.0f;
+    sm.spill = io.row_spill + (size_t)env * SM::SPILL_WORDS;
+  }
+  const float* act = io.action + (size_t)env * 4;
+  if (hand) {  // kuka.py:169-172
+    const float grip = (act[3] + 1.0f) * (GRIPPER_ABS_LIMIT / 2);
+    L.mt0 = L.mt1 = grip; L.mi0 = L.mi1 = FINGER_FORCE * OUTER_DT;
+  }
+  const float lo[3] = {-0.67f, -0.20f, 0.175f}, hi[3] = {-0.37f, 0.20f, 0.55f};  // kuka.py:40-41
+  float ee[3];
+#pragma unroll
+  for (int k = 0; k < 3; k++) ee[k] = fminf(fmaxf(s[(ST_EE + k) * B] + act[k] * 0.01f, lo[k]), hi[k]);
+  {
+    const float tq[4] = {0.f, -1.f, 0.f, 0.f};  // kuka.py:42
+    const float qik = inverse_kinematics(g, L, arm ? L.q0 : 0.0f, v3(ee[0], ee[1], ee[2]), tq);
+    if (arm) { L.mt0 = qik; L.mi0 = ARM_FORCE * OUTER_DT; }
+  }
+  g.sync();
+  for (int call = 0; call < CALLS_PER_ENV_STEP; call++) {
+    L.dtau0 = -L.lc[LC_DAMP] * L.qd0;
+    L.dtau1 = 0.0f;
+    for (int sub = 0; sub < SUBSTEPS_PER_CALL; sub++) substep(g, sm, L);
+  }
+  s[(ST_Q + lane) * B] = L.q0; s[(ST_QD + lane) * B] = L.qd0; s[(ST_MT + lane) * B] = L.mt0; s[(ST_MI + lane) * B] = L.mi0;
+  if (hand) { s[(ST_Q + 8) * B] = L.q1; s[(ST_QD + 8) * B] = L.qd1; s[(ST_MT + 8) * B] = L.mt1; s[(ST_MI + 8) * B] = L.mi1; }
+  g.sync();
+  for (int w = lane; w < SM::NPAIRS * MAN_WORDS; w += GL) io.manifold[(size_t)w * B + env] = sm.man[w];
+  for (int w = lane; w < 13 * NBLK; w += GL) s[(size_t)(ST_BLK + w) * B] = sm.blk[24 * (w / 13) + w % 13];
+  if (lane == 0) {
+#pragma unroll
+    for (int k = 0; k < 3; k++) s[(ST_EE + k) * B] = ee[k];
+    if (sm.blk[23] > 0.0f && io.overflow) atomicAdd(io.overflow, (int)sm.blk[23]);
   }
 }
 

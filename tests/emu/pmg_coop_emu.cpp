@@ -236,6 +236,40 @@ int pmg_emu_block_step(int task, float* state, float* manifold, const float* act
 }
 int pmg_emu_block_smem_bytes(void) { return (int)sizeof(coop::EnvSmemT<1>); }
 
+}  // extern "C"
+
+// Physics of one env.step() of a multi-block environment (BlockStack layout, nb = 2..5 blocks, 4 action columns):
+// state (Dims<3, nb>::STATE words) and manifolds (num_pairs(nb) x 41 words) updated in place.
+template <int NB>
+static int multi_step(float* state, float* manifold, const float* action, int* overflow) {
+  static coop::EnvSmemT<NB> sm;
+  static float spill[coop::EnvSmemT<NB>::SPILL_WORDS];
+  memset(&sm, 0, sizeof sm);
+  struct Args { coop::EnvSmemT<NB>* sm; StepIO io; } a;
+  a.sm = &sm;
+  memset(&a.io, 0, sizeof a.io);
+  a.io.state = state; a.io.manifold = manifold; a.io.batch = 1; a.io.state_words = Dims<3, NB>::STATE;
+  a.io.action = action; a.io.overflow = overflow; a.io.epw = 4; a.io.grasp = 1; a.io.adim = 4; a.io.row_spill = spill;
+  return pmg_emu::run_group([](int lane, void* arg) {
+    Args* a = (Args*)arg;
+    coop::Grp g; g.lane = lane;
+    coop::step_env_multi_physics<NB>(g, *a->sm, lane_table(), a->io, 0);
+  }, &a);
+}
+extern "C" {
+int pmg_emu_multi_step(int nb, float* state, float* manifold, const float* action, int* overflow) {
+  switch (nb) {
+    case 2: return multi_step<2>(state, manifold, action, overflow);
+    case 3: return multi_step<3>(state, manifold, action, overflow);
+    case 4: return multi_step<4>(state, manifold, action, overflow);
+    case 5: return multi_step<5>(state, manifold, action, overflow);
+  }
+  return -1;
+}
+int pmg_emu_multi_smem_bytes(int nb) {
+  return nb == 2 ? (int)sizeof(coop::EnvSmemT<2>) : nb == 3 ? (int)sizeof(coop::EnvSmemT<3>) : nb == 4 ? (int)sizeof(coop::EnvSmemT<4>) : (int)sizeof(coop::EnvSmemT<5>);
+}
+
 // The joint-control variants (kuka.py:204-206): task 0 Reach (7 action columns, row of 26 floats), 1 Push (7, 47),
 // 2 PickAndPlace (8, 47).
 int pmg_emu_step_jc(int task, float* state, float* manifold, const float* action, float thr, int binary, int max_steps,

@@ -278,3 +278,78 @@ def test_cooperative_tumbling_block_matches_oracle(emu, seed):
     worst, pairs, most, z = _block_scenario(emu, "push", 1, 3, 8, init, lambda t, st, tip: np.zeros(3))
     assert worst < 3e-4, worst
     assert pairs == {2} and most == 4 and abs(z - 0.175) < 1e-3   # flat on the table at the end
+
+
+def _multi_scenario(emu, nb, nsteps, window, init, policy, seed=4):
+    """Teacher-forced cooperative multi-block steps (physics only: state in, state out) against the oracle; the
+    emulator runs only for t in `window` (the oracle alone drives the approach).  Returns worst joint/block pose error,
+    worst block velocity error, the collision pairs that held points at a step end, most points at a step end."""
+    o = O.OracleEnv("block_stack", num_block=nb, seed=seed)
+    o.reset()
+    o.reset()
+    st = o.get_state()
+    init(st)
+    o.set_state(st)
+    npairs = 2 + 4 * nb + nb * (nb - 1) // 2
+    ovf = (C.c_int * 1)(0)
+    worst_p, worst_v, pairs, most = 0.0, 0.0, set(), 0
+    for t in range(nsteps):
+        st = o.get_state().astype(np.float32)
+        o.set_state(st.astype(np.float64))
+        a = policy(t, st, o.link_state(0)[:3]).astype(np.float32)
+        o.step(a.astype(np.float64))
+        if t not in window:
+            continue
+        man = np.zeros(41 * npairs, np.float32)
+        s2 = st.copy()
+        assert emu.pmg_emu_multi_step(nb, _f(s2), _f(man), _f(a), ovf) == 0, "divergent collective in the cooperative kernel"
+        ref = o.get_state()
+        worst_p = max(worst_p, float(np.abs(s2[:9] - ref[:9]).max()))
+        for b in range(nb):
+            worst_p = max(worst_p, float(np.abs(s2[46 + 13 * b:53 + 13 * b] - ref[46 + 13 * b:53 + 13 * b]).max()))
+            worst_v = max(worst_v, float(np.abs(s2[53 + 13 * b:59 + 13 * b] - ref[53 + 13 * b:59 + 13 * b]).max()))
+        cnt = [int(man[41 * k:41 * k + 1].view(np.int32)[0]) for k in range(npairs)]
+        pairs |= {k for k in range(npairs) if cnt[k]}
+        most = max(most, sum(cnt))
+    assert ovf[0] == 0
+    return worst_p, worst_v, pairs, most
+
+
+def test_cooperative_multi_block_grasp_matches_oracle(emu):
+    """Multi-block cooperative step (lane b owns block b, lanes stride over the 17 collision pairs, rows with up to two
+    block ends, block deltas fetched by run-time-source shuffles): descend onto block 0 of three, close the jaws, start
+    the lift, the other two blocks resting beside it.  Shared memory: 4 environments x 4 blocks per SM fit."""
+    assert 4 * (emu.pmg_emu_table_bytes() + 4 * emu.pmg_emu_multi_smem_bytes(4) + 1024) <= 227 * 1024
+
+    def policy(t, st, tip):
+        b0 = st[46:49]
+        tgt = b0 + [0, 0, 0.07] if t <= 8 else (b0 if t <= 16 else (tip if t <= 20 else np.array([tip[0], tip[1], 0.27])))
+        a = np.zeros(4)
+        a[:3] = np.clip((tgt - tip) / 0.01, -1, 1)
+        a[3] = -1.0 if t <= 16 else 1.0
+        return a
+    worst_p, worst_v, pairs, most = _multi_scenario(emu, 3, 24, range(15, 24), lambda st: None, policy)
+    assert worst_p < 1e-4 and worst_v < 1e-3, (worst_p, worst_v)
+    assert {4, 5, 6, 10} <= pairs and most >= 16   # both jaws on block 0, blocks 1 and 2 on the table
+
+
+def test_cooperative_multi_block_stack_matches_oracle(emu):
+    """Block 0 released 2 mm above block 1 (block-block pair: rows with two block ends), then the closed jaws are
+    lowered gently onto the stack (finger-block, block-block and table-block rows loaded in series)."""
+    def init(st):
+        st[46:49] = st[59:62] + [0.0, 0.0, 0.032]
+        st[49:53] = [0, 0, 0, 1]
+        st[53:59] = 0.0
+
+    def policy(t, st, tip):
+        top = st[46:49]
+        tgt = top + [0, 0, 0.08] if t <= 6 else top + [0, 0, 0.035]
+        a = np.zeros(4)
+        a[:3] = np.clip((tgt - tip) / 0.01, -1, 1)
+        if t > 12:
+            a[2] = -0.4
+        a[3] = 1.0
+        return a
+    worst_p, worst_v, pairs, most = _multi_scenario(emu, 2, 17, [0, 1, 2, 13, 14, 15, 16], init, policy)
+    assert worst_p < 1e-4 and worst_v < 1e-3, (worst_p, worst_v)
+    assert {4, 5, 6, 10} <= pairs and most >= 16   # pair 2 + 4 * 2 = 10: block 0 on block 1; both jaws on block 0
