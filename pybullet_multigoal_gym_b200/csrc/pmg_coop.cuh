@@ -1434,14 +1434,15 @@ __device__ void step_env_block(const Grp& g, EnvSmemT<1>& sm, const float* lane_
   }
 }
 
-// ---- multi-block environments: physics of one env.step() ---------------------------------------------------------
-// BlockStack / BlockRearrange with NBLK blocks (4-column action, grasping).  State in / state out only: the
-// observation and sub-goal assembly of the multi-step tasks (8 + 16 NBLK entries, grip goal, task decomposition) still
-// lives in the thread-per-env kernel's write_obs, so this step is not wired into libpmg.so yet -- tests/emu runs it
-// against the oracle.
+// ---- multi-block environments: one env.step() -------------------------------------------------------------------
+// BlockStack / BlockRearrange with NBLK blocks (4-column Cartesian action, grasping), including the grip-informed goal
+// and the task-decomposition / curriculum sub-goals (kuka_multi_step_base_env.py:255-345, the same assembly as
+// write_obs<3, NBLK> of the thread-per-env kernel).  Verified against the oracle on the CPU (tests/emu); not yet
+// instantiated in libpmg.so -- dispatch and GPU measurement are the next step.
 template <int NBLK>
-__device__ void step_env_multi_physics(const Grp& g, EnvSmemT<NBLK>& sm, const float* lane_consts, const StepIO& io, int env) {
+__device__ void step_env_multi(const Grp& g, EnvSmemT<NBLK>& sm, const float* lane_consts, const StepIO& io, int env) {
   using SM = EnvSmemT<NBLK>;
+  using D = Dims<3, NBLK>;
   const int lane = g.lane;
   const bool arm = lane < 7, hand = lane == 7;
   const size_t B = io.batch;
@@ -1456,9 +1457,10 @@ __device__ void step_env_multi_physics(const Grp& g, EnvSmemT<NBLK>& sm, const f
   for (int w = lane; w < SM::NPAIRS * MAN_WORDS; w += GL) sm.man[w] = io.manifold[(size_t)w * B + env];
   for (int w = lane; w < 13 * NBLK; w += GL) sm.blk[24 * (w / 13) + w % 13] = s[(size_t)(ST_BLK + w) * B];
   if (lane == 0) {
-    sm.blk[23] = 0.0f;
+    sm.blk[23] = 0.0f;  // contact points dropped because the row pool was full
     sm.spill = io.row_spill + (size_t)env * SM::SPILL_WORDS;
   }
+  // ---- Kuka.apply_action (kuka.py:167-222) ----
   const float* act = io.action + (size_t)env * 4;
   if (hand) {  // kuka.py:169-172
     const float grip = (act[3] + 1.0f) * (GRIPPER_ABS_LIMIT / 2);
@@ -1474,20 +1476,91 @@ __device__ void step_env_multi_physics(const Grp& g, EnvSmemT<NBLK>& sm, const f
     if (arm) { L.mt0 = qik; L.mi0 = ARM_FORCE * OUTER_DT; }
   }
   g.sync();
+  // ---- 5 x stepSimulation (kuka.py:223-225), each 20 substeps of 2 ms ----
   for (int call = 0; call < CALLS_PER_ENV_STEP; call++) {
     L.dtau0 = -L.lc[LC_DAMP] * L.qd0;
     L.dtau1 = 0.0f;
     for (int sub = 0; sub < SUBSTEPS_PER_CALL; sub++) substep(g, sm, L);
   }
+  // ---- observation, reward, flags ----
+  M3 R; V3 p;
+  chain_fk(g, L, arm ? L.q0 : 0.0f, R, p);
+  const V3 a = arm ? col(R, 2) : v3(0, 0, 0);
+  const V3 aq = L.qd0 * a;
+  const V3 w = g.scan(aq), wp = w - aq;
+  V3 pprev = g.up(p, 1);
+  if (lane == 0) pprev = v3(0, 0, 0);
+  const V3 vo = g.scan(cross(wp, p - pprev));
   s[(ST_Q + lane) * B] = L.q0; s[(ST_QD + lane) * B] = L.qd0; s[(ST_MT + lane) * B] = L.mt0; s[(ST_MI + lane) * B] = L.mi0;
   if (hand) { s[(ST_Q + 8) * B] = L.q1; s[(ST_QD + 8) * B] = L.qd1; s[(ST_MT + 8) * B] = L.mt1; s[(ST_MI + 8) * B] = L.mi1; }
-  g.sync();
-  for (int w = lane; w < SM::NPAIRS * MAN_WORDS; w += GL) io.manifold[(size_t)w * B + env] = sm.man[w];
-  for (int w = lane; w < 13 * NBLK; w += GL) s[(size_t)(ST_BLK + w) * B] = sm.blk[24 * (w / 13) + w % 13];
-  if (lane == 0) {
+  g.sync();  // the block states of the last substep
+  for (int wd = lane; wd < SM::NPAIRS * MAN_WORDS; wd += GL) io.manifold[(size_t)wd * B + env] = sm.man[wd];
+  for (int wd = lane; wd < 13 * NBLK; wd += GL) s[(size_t)(ST_BLK + wd) * B] = sm.blk[24 * (wd / 13) + wd % 13];
+  if (lane == 0 && sm.blk[23] > 0.0f && io.overflow) atomicAdd(io.overflow, (int)sm.blk[23]);
+  const float t[3] = PMG_TIP_OFFSET;
+  const V3 tip_own = p + mul(R, v3(t[0], t[1], t[2]));
+  const V3 tip = g.shfl(tip_own, PMG_BODY_LINK7);
+  const V3 tv = g.shfl(vo + cross(w, tip_own - p), PMG_BODY_LINK7), tw = g.shfl(w, PMG_BODY_LINK7);
+  if (hand) {
+    const float t1[3] = PMG_TAB1_OFFSET, t2[3] = PMG_TAB2_OFFSET;
+    const V3 ay = col(R, 1);  // R = gripper-base frame on this lane; fingers slide along -/+ its y axis
+    const V3 j1 = v3(c_jxyz[PMG_BODY_FINGER1][0], c_jxyz[PMG_BODY_FINGER1][1], c_jxyz[PMG_BODY_FINGER1][2]);
+    const V3 j2 = v3(c_jxyz[PMG_BODY_FINGER2][0], c_jxyz[PMG_BODY_FINGER2][1], c_jxyz[PMG_BODY_FINGER2][2]);
+    const V3 tab1 = mul(R, j1 + v3(t1[0], t1[1], t1[2])) - L.q0 * ay;
+    const V3 tab2 = mul(R, j2 + v3(t2[0], t2[1], t2[2])) + L.q1 * ay;
+    const float closeness = norm(tab1 - tab2);
+    const float finger_vel = -(cross(w, tab1) - L.qd0 * ay).y;
+    const int G = io.goal_dim;  // 3 NBLK, + 4 with the grip-informed goal
+    float* row = io.obs + (size_t)env * io.row_width;
+    float* obs = row; float* pol = row + D::O; float* ag = pol + D::P; float* dg = ag + G;
+    obs[0] = tip.x; obs[1] = tip.y; obs[2] = tip.z; obs[3] = closeness; obs[4] = tv.x; obs[5] = tv.y; obs[6] = tv.z; obs[7] = finger_vel;
+    pol[0] = tip.x; pol[1] = tip.y; pol[2] = tip.z; pol[3] = closeness;
+#pragma unroll 1
+    for (int n = 0; n < NBLK; n++) {
+      const float* bk = sm.blk + 24 * n;
+      float* bs = obs + 8 + 16 * n;
+      const V3 bx = v3(bk[BK_POS], bk[BK_POS + 1], bk[BK_POS + 2]), bv = v3(bk[BK_V], bk[BK_V + 1], bk[BK_V + 2]), bw = v3(bk[BK_W], bk[BK_W + 1], bk[BK_W + 2]);
+      const V3 rel = tip - bx, rv = tv - bv, rw = tw - bw;
+      bs[0] = bx.x; bs[1] = bx.y; bs[2] = bx.z; bs[3] = rel.x; bs[4] = rel.y; bs[5] = rel.z;
+      bs[6] = bk[BK_QUAT]; bs[7] = bk[BK_QUAT + 1]; bs[8] = bk[BK_QUAT + 2]; bs[9] = bk[BK_QUAT + 3];
+      bs[10] = rv.x; bs[11] = rv.y; bs[12] = rv.z; bs[13] = rw.x; bs[14] = rw.y; bs[15] = rw.z;
+      pol[4 + 3 * n] = rel.x; pol[5 + 3 * n] = rel.y; pol[6 + 3 * n] = rel.z;
+      ag[3 * n] = bx.x; ag[3 * n + 1] = bx.y; ag[3 * n + 2] = bx.z;
+    }
+    if (io.grip_goal) { ag[3 * NBLK] = tip.x; ag[3 * NBLK + 1] = tip.y; ag[3 * NBLK + 2] = tip.z; ag[3 * NBLK + 3] = closeness; }
+    const float* goal = io.state + (size_t)(ST_BLK + 13 * NBLK) * B + env;
+    for (int k = 0; k < G; k++) dg[k] = goal[(size_t)k * B];
+    if (io.td) {  // sub-goal rebuilt from the current block positions (see write_obs in pmg_capi.cu)
+      const int nsub = io.grip_goal ? 2 * NBLK : NBLK;
+      int ind = (int)goal[(size_t)G * B];
+      if (ind < 0) ind += nsub;
+      const int k = io.grip_goal ? ind >> 1 : ind;
+      const bool place = io.grip_goal ? (ind & 1) != 0 : true;
+#pragma unroll 1
+      for (int n = 0; n < NBLK; n++) {
+        const float* bk = sm.blk + 24 * n;
+        const int level = (int)floorf((dg[3 * n + 2] - BLOCK_SPAWN_Z) * (1.0f / 0.03f) + 0.5f);
+        const bool at_target = place ? level <= k : level < k;
+        if (io.grip_goal && level == k) {
+          dg[3 * NBLK] = place ? dg[3 * n] : bk[BK_POS]; dg[3 * NBLK + 1] = place ? dg[3 * n + 1] : bk[BK_POS + 1];
+          dg[3 * NBLK + 2] = place ? dg[3 * n + 2] : bk[BK_POS + 2];
+        }
+        if (!at_target) { dg[3 * n] = bk[BK_POS]; dg[3 * n + 1] = bk[BK_POS + 1]; dg[3 * n + 2] = bk[BK_POS + 2]; }
+      }
+    }
+    for (int k = 0; k < D::O + D::P; k++) row[k] = fminf(fmaxf(row[k], -5.0f), 5.0f);  // np.clip of observation and policy_state
+    float d2 = 0.0f;
+    for (int k = 0; k < G; k++) { const float d = ag[k] - dg[k]; d2 += d * d; }
+    const float dist = sqrtf(d2);
 #pragma unroll
     for (int k = 0; k < 3; k++) s[(ST_EE + k) * B] = ee[k];
-    if (sm.blk[23] > 0.0f && io.overflow) atomicAdd(io.overflow, (int)sm.blk[23]);
+    float* el = s + (size_t)(io.state_words - 1) * B;
+    const int elapsed = (int)(*el) + 1;
+    *el = (float)elapsed;
+    const bool na = dist > io.thr;
+    io.reward[env] = io.binary ? -(na ? 1.0f : 0.0f) : -dist;
+    io.success[env] = na ? 0 : 1;
+    io.done[env] = elapsed >= io.max_steps ? 1 : 0;
   }
 }
 

@@ -238,31 +238,38 @@ int pmg_emu_block_smem_bytes(void) { return (int)sizeof(coop::EnvSmemT<1>); }
 
 }  // extern "C"
 
-// Physics of one env.step() of a multi-block environment (BlockStack layout, nb = 2..5 blocks, 4 action columns):
-// state (Dims<3, nb>::STATE words) and manifolds (num_pairs(nb) x 41 words) updated in place.
+// One env.step() of a multi-block environment (BlockStack layout, nb = 2..5 blocks, 4 action columns): state
+// (state_words of one env) and manifolds (num_pairs(nb) x 41 words) updated in place, packed row out.
+// grip: grip-informed goal (goal_dim 3 nb + 4); td: task decomposition / curriculum (sub-goal word in the state).
 template <int NB>
-static int multi_step(float* state, float* manifold, const float* action, int* overflow) {
+static int multi_step(float* state, float* manifold, const float* action, int* overflow, int grip, int td, float thr, int binary,
+                      int max_steps, float* obs_row, float* reward, uint8_t* done, uint8_t* success) {
   static coop::EnvSmemT<NB> sm;
   static float spill[coop::EnvSmemT<NB>::SPILL_WORDS];
   memset(&sm, 0, sizeof sm);
   struct Args { coop::EnvSmemT<NB>* sm; StepIO io; } a;
   a.sm = &sm;
   memset(&a.io, 0, sizeof a.io);
-  a.io.state = state; a.io.manifold = manifold; a.io.batch = 1; a.io.state_words = Dims<3, NB>::STATE;
-  a.io.action = action; a.io.overflow = overflow; a.io.epw = 4; a.io.grasp = 1; a.io.adim = 4; a.io.row_spill = spill;
+  const int G = 3 * NB + (grip ? 4 : 0);
+  a.io.state = state; a.io.manifold = manifold; a.io.batch = 1; a.io.state_words = ST_BLK + 13 * NB + G + (td ? 1 : 0) + 1;
+  a.io.action = action; a.io.obs = obs_row; a.io.reward = reward; a.io.done = done; a.io.success = success;
+  a.io.thr = thr; a.io.binary = binary; a.io.max_steps = max_steps;
+  a.io.overflow = overflow; a.io.epw = 4; a.io.grasp = 1; a.io.adim = 4; a.io.row_spill = spill;
+  a.io.grip_goal = grip; a.io.td = td; a.io.goal_dim = G; a.io.row_width = Dims<3, NB>::O + Dims<3, NB>::P + 2 * G;
   return pmg_emu::run_group([](int lane, void* arg) {
     Args* a = (Args*)arg;
     coop::Grp g; g.lane = lane;
-    coop::step_env_multi_physics<NB>(g, *a->sm, lane_table(), a->io, 0);
+    coop::step_env_multi<NB>(g, *a->sm, lane_table(), a->io, 0);
   }, &a);
 }
 extern "C" {
-int pmg_emu_multi_step(int nb, float* state, float* manifold, const float* action, int* overflow) {
+int pmg_emu_multi_step(int nb, float* state, float* manifold, const float* action, int* overflow, int grip, int td, float thr,
+                       int binary, int max_steps, float* obs_row, float* reward, uint8_t* done, uint8_t* success) {
   switch (nb) {
-    case 2: return multi_step<2>(state, manifold, action, overflow);
-    case 3: return multi_step<3>(state, manifold, action, overflow);
-    case 4: return multi_step<4>(state, manifold, action, overflow);
-    case 5: return multi_step<5>(state, manifold, action, overflow);
+    case 2: return multi_step<2>(state, manifold, action, overflow, grip, td, thr, binary, max_steps, obs_row, reward, done, success);
+    case 3: return multi_step<3>(state, manifold, action, overflow, grip, td, thr, binary, max_steps, obs_row, reward, done, success);
+    case 4: return multi_step<4>(state, manifold, action, overflow, grip, td, thr, binary, max_steps, obs_row, reward, done, success);
+    case 5: return multi_step<5>(state, manifold, action, overflow, grip, td, thr, binary, max_steps, obs_row, reward, done, success);
   }
   return -1;
 }

@@ -280,39 +280,57 @@ def test_cooperative_tumbling_block_matches_oracle(emu, seed):
     assert pairs == {2} and most == 4 and abs(z - 0.175) < 1e-3   # flat on the table at the end
 
 
-def _multi_scenario(emu, nb, nsteps, window, init, policy, seed=4):
-    """Teacher-forced cooperative multi-block steps (physics only: state in, state out) against the oracle; the
+def _multi_scenario(emu, nb, nsteps, window, init, policy, seed=4, grip=False, td=False, sub_goal=None):
+    """Teacher-forced cooperative multi-block steps against the oracle (state and packed observation row); the
     emulator runs only for t in `window` (the oracle alone drives the approach).  Returns worst joint/block pose error,
-    worst block velocity error, the collision pairs that held points at a step end, most points at a step end."""
-    o = O.OracleEnv("block_stack", num_block=nb, seed=seed)
+    worst block velocity error, worst observation-row error away from the velocity entries, the collision pairs that
+    held points at a step end, most points at a step end."""
+    o = O.OracleEnv("block_stack", num_block=nb, seed=seed, binary_reward=False, grip_informed_goal=grip, task_decomposition=td)
     o.reset()
     o.reset()
+    if sub_goal is not None:
+        o.set_sub_goal(sub_goal)
     st = o.get_state()
     init(st)
     o.set_state(st)
     npairs = 2 + 4 * nb + nb * (nb - 1) // 2
+    G = 3 * nb + (4 if grip else 0)
+    width = (8 + 16 * nb) + (4 + 3 * nb) + 2 * G
     ovf = (C.c_int * 1)(0)
-    worst_p, worst_v, pairs, most = 0.0, 0.0, set(), 0
+    obs, rew = np.zeros(width, np.float32), np.zeros(1, np.float32)
+    dn, su = np.zeros(1, np.uint8), np.zeros(1, np.uint8)
+    vel_cols = set(range(4, 8))
+    for b in range(nb):
+        vel_cols |= set(range(8 + 16 * b + 10, 8 + 16 * b + 16))
+    pos_cols = np.array([c for c in range(width) if c not in vel_cols])
+    worst_p, worst_v, worst_o, pairs, most = 0.0, 0.0, 0.0, set(), 0
     for t in range(nsteps):
         st = o.get_state().astype(np.float32)
         o.set_state(st.astype(np.float64))
         a = policy(t, st, o.link_state(0)[:3]).astype(np.float32)
-        o.step(a.astype(np.float64))
+        ro, rr, rd, ri = o.step(a.astype(np.float64))
         if t not in window:
             continue
         man = np.zeros(41 * npairs, np.float32)
         s2 = st.copy()
-        assert emu.pmg_emu_multi_step(nb, _f(s2), _f(man), _f(a), ovf) == 0, "divergent collective in the cooperative kernel"
+        rc = emu.pmg_emu_multi_step(nb, _f(s2), _f(man), _f(a), ovf, int(grip), int(td), C.c_float(0.05), 0, 50, _f(obs), _f(rew),
+                                    dn.ctypes.data_as(U8), su.ctypes.data_as(U8))
+        assert rc == 0, "divergent collective in the cooperative kernel"
         ref = o.get_state()
         worst_p = max(worst_p, float(np.abs(s2[:9] - ref[:9]).max()))
         for b in range(nb):
             worst_p = max(worst_p, float(np.abs(s2[46 + 13 * b:53 + 13 * b] - ref[46 + 13 * b:53 + 13 * b]).max()))
             worst_v = max(worst_v, float(np.abs(s2[53 + 13 * b:59 + 13 * b] - ref[53 + 13 * b:59 + 13 * b]).max()))
+        want = np.concatenate([ro[k] for k in ("observation", "policy_state", "achieved_goal", "desired_goal")])
+        assert want.shape == (width,)
+        worst_o = max(worst_o, float(np.abs(obs - want)[pos_cols].max()))
+        assert abs(float(rew[0]) - rr) < 2e-4 and bool(dn[0]) == rd
+        assert s2[-1] == ref[-1]                                   # elapsed steps
         cnt = [int(man[41 * k:41 * k + 1].view(np.int32)[0]) for k in range(npairs)]
         pairs |= {k for k in range(npairs) if cnt[k]}
         most = max(most, sum(cnt))
     assert ovf[0] == 0
-    return worst_p, worst_v, pairs, most
+    return worst_p, worst_v, worst_o, pairs, most
 
 
 def test_cooperative_multi_block_grasp_matches_oracle(emu):
@@ -328,8 +346,8 @@ def test_cooperative_multi_block_grasp_matches_oracle(emu):
         a[:3] = np.clip((tgt - tip) / 0.01, -1, 1)
         a[3] = -1.0 if t <= 16 else 1.0
         return a
-    worst_p, worst_v, pairs, most = _multi_scenario(emu, 3, 24, range(15, 24), lambda st: None, policy)
-    assert worst_p < 1e-4 and worst_v < 1e-3, (worst_p, worst_v)
+    worst_p, worst_v, worst_o, pairs, most = _multi_scenario(emu, 3, 24, range(15, 24), lambda st: None, policy)
+    assert worst_p < 1e-4 and worst_v < 1e-3 and worst_o < 1e-4, (worst_p, worst_v, worst_o)
     assert {4, 5, 6, 10} <= pairs and most >= 16   # both jaws on block 0, blocks 1 and 2 on the table
 
 
@@ -350,6 +368,16 @@ def test_cooperative_multi_block_stack_matches_oracle(emu):
             a[2] = -0.4
         a[3] = 1.0
         return a
-    worst_p, worst_v, pairs, most = _multi_scenario(emu, 2, 17, [0, 1, 2, 13, 14, 15, 16], init, policy)
-    assert worst_p < 1e-4 and worst_v < 1e-3, (worst_p, worst_v)
+    worst_p, worst_v, worst_o, pairs, most = _multi_scenario(emu, 2, 17, [0, 1, 2, 13, 14, 15, 16], init, policy)
+    assert worst_p < 1e-4 and worst_v < 1e-3 and worst_o < 1e-4, (worst_p, worst_v, worst_o)
     assert {4, 5, 6, 10} <= pairs and most >= 16   # pair 2 + 4 * 2 = 10: block 0 on block 1; both jaws on block 0
+
+
+@pytest.mark.parametrize("grip,td,sub_goal", [(True, False, None), (False, True, 1), (True, True, 2)])
+def test_cooperative_multi_block_goal_variants_match_oracle(emu, grip, td, sub_goal):
+    """Observation assembly of the multi-block cooperative step for the grip-informed goal and the task-decomposition
+    sub-goals (desired goal rebuilt from the current block positions), three resting blocks, arm moving."""
+    def policy(t, st, tip):
+        return np.array([0.5, -0.5, -0.3, -1.0])
+    worst_p, worst_v, worst_o, pairs, most = _multi_scenario(emu, 3, 2, range(0, 2), lambda st: None, policy, grip=grip, td=td, sub_goal=sub_goal)
+    assert worst_p < 1e-4 and worst_o < 1e-4, (worst_p, worst_o)
