@@ -319,6 +319,23 @@ __global__ void __launch_bounds__(32, 7) step_kernel_coop_block(StepIO io) {
   coop::step_env_block<TASK>(g, sm, lane_consts, io, env);
 }
 
+// Lane-cooperative BlockStack / BlockRearrange step (NBLK = 2..5).  OPT-IN (PMG_COOP_STACK=1): verified against the
+// oracle on the CPU emulator only so far, not yet run or measured on the GPU.
+template <int NBLK>
+__global__ void __launch_bounds__(32, 3) step_kernel_coop_multi(StepIO io) {
+  extern __shared__ __align__(16) unsigned char coop_smem[];
+  const int lane32 = threadIdx.x & 31, grp = lane32 >> 3;
+  float* lane_consts = reinterpret_cast<float*>(coop_smem);
+  if (lane32 < coop::GL) coop::fill_lane_constants(lane_consts + lane32 * coop::LC_W, lane32);
+  __syncwarp();
+  const int env = blockIdx.x * (32 / coop::GL) + grp;
+  if (env >= io.batch) return;  // a whole octet leaves together
+  coop::Grp g;
+  g.lane = lane32 & (coop::GL - 1); g.shift = grp * coop::GL; g.mask = 0xffu << g.shift;
+  coop::EnvSmemT<NBLK>& sm = reinterpret_cast<coop::EnvSmemT<NBLK>*>(coop_smem + COOP_TABLE_BYTES)[grp];
+  coop::step_env_multi<NBLK>(g, sm, lane_consts, io, env);
+}
+
 struct ResetIO { StepIO io; const uint8_t* mask; const float* spawn; float tip_init[3]; };
 
 template <int TASK, int NBLK>
@@ -592,6 +609,7 @@ struct pmg_handle {
   bool default_carveout = false;  // PMG_DEFAULT_CARVEOUT=1 keeps the driver's shared-memory carve-out
   bool coop = true;  // Reach: lane-cooperative kernel (PMG_COOP=0 selects the thread-per-env kernel)
   bool coop_block = true;  // Push / PickAndPlace: lane-cooperative kernel (PMG_COOP_BLOCK=0 selects the thread-per-env kernel)
+  bool coop_stack = false; // BlockStack / BlockRearrange with >= 2 blocks: opt-in lane-cooperative kernel (PMG_COOP_STACK=1)
   bool hinted = false;  // shared-memory carve-out hint of this handle's step kernel has been set on its device
 };
 
@@ -729,6 +747,19 @@ void launch_step(pmg_handle* h, const StepIO& io_in, cudaStream_t st) {
     else step_kernel_coop_reach<false><<<blocks, 32, smem, st>>>(io);
     return;
   }
+  if constexpr (TASK == 3 && NBLK >= 2) {
+    if (h->coop_stack && !h->jc) {
+      constexpr int EPB = 32 / coop::GL;
+      const size_t smem = COOP_TABLE_BYTES + EPB * sizeof(coop::EnvSmemT<NBLK>);
+      if (!h->hinted) {
+        cudaFuncSetAttribute(step_kernel_coop_multi<NBLK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaFuncSetAttribute(step_kernel_coop_multi<NBLK>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        h->hinted = true;
+      }
+      step_kernel_coop_multi<NBLK><<<(h->cfg.batch + EPB - 1) / EPB, 32, smem, st>>>(io);
+      return;
+    }
+  }
   int warps = (h->cfg.batch + h->epw - 1) / h->epw;
   size_t stage_floats = (size_t)h->epw * h->W;
   io.bulk = (h->epw == 32 && h->cfg.batch % 32 == 0 && !h->no_bulk && !h->grip && !h->td && !h->cur) ? 1 : 0;
@@ -843,6 +874,7 @@ int pmg_create(const pmg_config* cfg, pmg_handle** out) {
     if (const char* ev = getenv("PMG_DEFAULT_CARVEOUT")) h->default_carveout = atoi(ev) != 0;
     if (const char* ev = getenv("PMG_COOP")) h->coop = atoi(ev) != 0;
     if (const char* ev = getenv("PMG_COOP_BLOCK")) h->coop_block = atoi(ev) != 0;
+    if (const char* ev = getenv("PMG_COOP_STACK")) h->coop_stack = atoi(ev) != 0;
   }
   if (h->cur) {
     h->cur_goals_per = (double)(cfg->num_goals_to_generate / h->nblk);  // floor division (kuka_multi_step_base_env.py:138)
@@ -861,6 +893,8 @@ int pmg_create(const pmg_config* cfg, pmg_handle** out) {
   ALLOC(h->d_overflow, sizeof(int));
   if ((h->cfg.task == PMG_PUSH || h->cfg.task == PMG_PICK_AND_PLACE) && h->coop_block)
     ALLOC(h->d_row_spill, sizeof(float) * coop::EnvSmemT<1>::SPILL_WORDS * B);
+  if (h->multi && h->nblk >= 2 && h->coop_stack && !h->jc)
+    ALLOC(h->d_row_spill, sizeof(float) * coop::EnvSmemT<2>::SPILL_WORDS * B);  // the same for every NBLK >= 2
   ALLOC(h->d_action, sizeof(float) * h->A * B);
   ALLOC(h->d_obs, sizeof(float) * h->W * B);
   ALLOC(h->d_blocks, sizeof(float) * h->W * B);
