@@ -381,3 +381,14 @@ def test_cooperative_multi_block_goal_variants_match_oracle(emu, grip, td, sub_g
         return np.array([0.5, -0.5, -0.3, -1.0])
     worst_p, worst_v, worst_o, pairs, most = _multi_scenario(emu, 3, 2, range(0, 2), lambda st: None, policy, grip=grip, td=td, sub_goal=sub_goal)
     assert worst_p < 1e-4 and worst_o < 1e-4, (worst_p, worst_o)
+
+
+@pytest.mark.parametrize("nb", [4, 5])
+def test_cooperative_multi_block_larger_scenes_match_oracle(emu, nb):
+    """The 4- and 5-block instantiations (24 / 32 collision pairs: lanes run up to four pairs each; 16 / 20 resting
+    contact points, i.e. spilled rows): two steps with the arm moving over resting blocks."""
+    def policy(t, st, tip):
+        return np.array([-0.5, 0.5, -0.5, 1.0])
+    worst_p, worst_v, worst_o, pairs, most = _multi_scenario(emu, nb, 2, range(0, 2), lambda st: None, policy)
+    assert worst_p < 1e-4 and worst_v < 1e-3 and worst_o < 1e-4, (worst_p, worst_v, worst_o)
+    assert most == 4 * nb and pairs == {2 + 4 * b for b in range(nb)}
