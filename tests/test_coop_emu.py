@@ -392,3 +392,30 @@ def test_cooperative_multi_block_larger_scenes_match_oracle(emu, nb):
     worst_p, worst_v, worst_o, pairs, most = _multi_scenario(emu, nb, 2, range(0, 2), lambda st: None, policy)
     assert worst_p < 1e-4 and worst_v < 1e-3 and worst_o < 1e-4, (worst_p, worst_v, worst_o)
     assert most == 4 * nb and pairs == {2 + 4 * b for b in range(nb)}
+
+
+def test_cooperative_multi_block_pick_carry_release_matches_oracle(emu):
+    """The whole stacking move on three blocks -- hover, descend, grasp, lift, carry over block 1, lower, open the jaws
+    -- driven by the oracle; the cooperative step is checked while carrying (block held by friction rows only), at the
+    release and with block 0 resting on block 1 (block-block pair 14)."""
+    def policy(t, st, tip):
+        b0, b1 = st[46:49], st[59:62]
+        if t <= 8:
+            tgt = b0 + [0, 0, 0.07]
+        elif t <= 16:
+            tgt = b0
+        elif t <= 20:
+            tgt = tip.copy()
+        elif t <= 28:
+            tgt = np.array([tip[0], tip[1], 0.27])
+        elif t <= 44:
+            tgt = np.array([b1[0], b1[1], 0.27])
+        else:
+            tgt = np.array([b1[0], b1[1], 0.175 + 0.03 + 0.004])
+        a = np.zeros(4)
+        a[:3] = np.clip((tgt - tip) / 0.01, -1, 1)
+        a[3] = -1.0 if (t <= 16 or t > 56) else 1.0
+        return a
+    worst_p, worst_v, worst_o, pairs, most = _multi_scenario(emu, 3, 60, [36, 50, 56, 57, 59], lambda st: None, policy)
+    assert worst_p < 1e-4 and worst_v < 1e-3 and worst_o < 1e-4, (worst_p, worst_v, worst_o)
+    assert {4, 5, 14} <= pairs   # both jaws on block 0 while carrying; block 0 on block 1 at the end
