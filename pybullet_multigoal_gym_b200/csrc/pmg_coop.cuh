@@ -1435,7 +1435,7 @@ __device__ void step_env_block(const Grp& g, EnvSmemT<1>& sm, const float* lane_
 }
 
 // ---- multi-block environments: one env.step() -------------------------------------------------------------------
-// BlockStack / BlockRearrange with NBLK blocks (4-column Cartesian action, grasping), including the grip-informed goal
+// BlockStack (4-column Cartesian action, grasping) / BlockRearrange (3 columns) with NBLK blocks, including the grip-informed goal
 // and the task-decomposition / curriculum sub-goals (kuka_multi_step_base_env.py:255-345, the same assembly as
 // write_obs<3, NBLK> of the thread-per-env kernel).  Verified against the oracle on the CPU (tests/emu); not yet
 // instantiated in libpmg.so -- dispatch and GPU measurement are the next step.
@@ -1461,8 +1461,8 @@ __device__ void step_env_multi(const Grp& g, EnvSmemT<NBLK>& sm, const float* la
     sm.spill = io.row_spill + (size_t)env * SM::SPILL_WORDS;
   }
   // ---- Kuka.apply_action (kuka.py:167-222) ----
-  const float* act = io.action + (size_t)env * 4;
-  if (hand) {  // kuka.py:169-172
+  const float* act = io.action + (size_t)env * io.adim;  // 4 columns (BlockStack: grasping) or 3 (BlockRearrange)
+  if (hand && io.grasp) {  // kuka.py:169-172
     const float grip = (act[3] + 1.0f) * (GRIPPER_ABS_LIMIT / 2);
     L.mt0 = L.mt1 = grip; L.mi0 = L.mi1 = FINGER_FORCE * OUTER_DT;
   }
@@ -1508,8 +1508,8 @@ __device__ void step_env_multi(const Grp& g, EnvSmemT<NBLK>& sm, const float* la
     const V3 j2 = v3(c_jxyz[PMG_BODY_FINGER2][0], c_jxyz[PMG_BODY_FINGER2][1], c_jxyz[PMG_BODY_FINGER2][2]);
     const V3 tab1 = mul(R, j1 + v3(t1[0], t1[1], t1[2])) - L.q0 * ay;
     const V3 tab2 = mul(R, j2 + v3(t2[0], t2[1], t2[2])) + L.q1 * ay;
-    const float closeness = norm(tab1 - tab2);
-    const float finger_vel = -(cross(w, tab1) - L.qd0 * ay).y;
+    const float closeness = io.grasp ? norm(tab1 - tab2) : 0.0f;   // kuka.py:245-246: [0.0] without grasping
+    const float finger_vel = io.grasp ? -(cross(w, tab1) - L.qd0 * ay).y : 0.0f;
     const int G = io.goal_dim;  // 3 NBLK, + 4 with the grip-informed goal
     float* row = io.obs + (size_t)env * io.row_width;
     float* obs = row; float* pol = row + D::O; float* ag = pol + D::P; float* dg = ag + G;

@@ -240,7 +240,8 @@ int pmg_emu_block_smem_bytes(void) { return (int)sizeof(coop::EnvSmemT<1>); }
 
 // One env.step() of a multi-block environment (BlockStack layout, nb = 2..5 blocks, 4 action columns): state
 // (state_words of one env) and manifolds (num_pairs(nb) x 41 words) updated in place, packed row out.
-// grip: grip-informed goal (goal_dim 3 nb + 4); td: task decomposition / curriculum (sub-goal word in the state).
+// grip: 1 = grip-informed goal (goal_dim 3 nb + 4), -1 = BlockRearrange (no grasping, 3 action columns);
+// td: task decomposition / curriculum (sub-goal word in the state).
 template <int NB>
 static int multi_step(float* state, float* manifold, const float* action, int* overflow, int grip, int td, float thr, int binary,
                       int max_steps, float* obs_row, float* reward, uint8_t* done, uint8_t* success) {
@@ -250,11 +251,12 @@ static int multi_step(float* state, float* manifold, const float* action, int* o
   struct Args { coop::EnvSmemT<NB>* sm; StepIO io; } a;
   a.sm = &sm;
   memset(&a.io, 0, sizeof a.io);
-  const int G = 3 * NB + (grip ? 4 : 0);
+  const int G = 3 * NB + (grip > 0 ? 4 : 0);
   a.io.state = state; a.io.manifold = manifold; a.io.batch = 1; a.io.state_words = ST_BLK + 13 * NB + G + (td ? 1 : 0) + 1;
   a.io.action = action; a.io.obs = obs_row; a.io.reward = reward; a.io.done = done; a.io.success = success;
   a.io.thr = thr; a.io.binary = binary; a.io.max_steps = max_steps;
-  a.io.overflow = overflow; a.io.epw = 4; a.io.grasp = 1; a.io.adim = 4; a.io.row_spill = spill;
+  a.io.overflow = overflow; a.io.epw = 4; a.io.grasp = grip >= 0; a.io.adim = grip >= 0 ? 4 : 3; a.io.row_spill = spill;
+  if (grip < 0) grip = 0;  // grip = -1: BlockRearrange (no grasping, 3 action columns)
   a.io.grip_goal = grip; a.io.td = td; a.io.goal_dim = G; a.io.row_width = Dims<3, NB>::O + Dims<3, NB>::P + 2 * G;
   return pmg_emu::run_group([](int lane, void* arg) {
     Args* a = (Args*)arg;

@@ -280,12 +280,12 @@ def test_cooperative_tumbling_block_matches_oracle(emu, seed):
     assert pairs == {2} and most == 4 and abs(z - 0.175) < 1e-3   # flat on the table at the end
 
 
-def _multi_scenario(emu, nb, nsteps, window, init, policy, seed=4, grip=False, td=False, sub_goal=None):
+def _multi_scenario(emu, nb, nsteps, window, init, policy, seed=4, grip=False, td=False, sub_goal=None, task="block_stack"):
     """Teacher-forced cooperative multi-block steps against the oracle (state and packed observation row); the
     emulator runs only for t in `window` (the oracle alone drives the approach).  Returns worst joint/block pose error,
     worst block velocity error, worst observation-row error away from the velocity entries, the collision pairs that
     held points at a step end, most points at a step end."""
-    o = O.OracleEnv("block_stack", num_block=nb, seed=seed, binary_reward=False, grip_informed_goal=grip, task_decomposition=td)
+    o = O.OracleEnv(task, num_block=nb, seed=seed, binary_reward=False, grip_informed_goal=grip, task_decomposition=td)
     o.reset()
     o.reset()
     if sub_goal is not None:
@@ -313,7 +313,7 @@ def _multi_scenario(emu, nb, nsteps, window, init, policy, seed=4, grip=False, t
             continue
         man = np.zeros(41 * npairs, np.float32)
         s2 = st.copy()
-        rc = emu.pmg_emu_multi_step(nb, _f(s2), _f(man), _f(a), ovf, int(grip), int(td), C.c_float(0.05), 0, 50, _f(obs), _f(rew),
+        rc = emu.pmg_emu_multi_step(nb, _f(s2), _f(man), _f(a), ovf, -1 if task == "block_rearrange" else int(grip), int(td), C.c_float(0.05), 0, 50, _f(obs), _f(rew),
                                     dn.ctypes.data_as(U8), su.ctypes.data_as(U8))
         assert rc == 0, "divergent collective in the cooperative kernel"
         ref = o.get_state()
@@ -419,3 +419,12 @@ def test_cooperative_multi_block_pick_carry_release_matches_oracle(emu):
     worst_p, worst_v, worst_o, pairs, most = _multi_scenario(emu, 3, 60, [36, 50, 56, 57, 59], lambda st: None, policy)
     assert worst_p < 1e-4 and worst_v < 1e-3 and worst_o < 1e-4, (worst_p, worst_v, worst_o)
     assert {4, 5, 14} <= pairs   # both jaws on block 0 while carrying; block 0 on block 1 at the end
+
+
+def test_cooperative_multi_block_rearrange_matches_oracle(emu):
+    """BlockRearrange runs on the same multi-block step (3 action columns, jaws kept closed, table targets instead of a
+    stack as the desired goal, zero finger entries in the observation)."""
+    def policy(t, st, tip):
+        return np.array([0.3, 0.6, -0.4])
+    worst_p, worst_v, worst_o, pairs, most = _multi_scenario(emu, 3, 2, range(0, 2), lambda st: None, policy, task="block_rearrange")
+    assert worst_p < 1e-4 and worst_v < 1e-3 and worst_o < 1e-4, (worst_p, worst_v, worst_o)
