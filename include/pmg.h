@@ -22,7 +22,7 @@
 extern "C" {
 #endif
 
-#define PMG_ABI_VERSION 5
+#define PMG_ABI_VERSION 6
 
 typedef enum {
   PMG_OK = 0,
@@ -87,8 +87,27 @@ int pmg_seed(pmg_handle* h, const uint32_t* keys_host, const int32_t* key_lens_h
  * obs_dev: [batch, packed-row width] row-major, rows of envs not reset are rewritten unchanged. */
 int pmg_reset(pmg_handle* h, const uint8_t* mask_host, const float* spawn_host, float* obs_dev, void* stream);
 int pmg_spawn_width(const pmg_handle* h);
-/* the spawn rows used by the most recent pmg_reset, [batch, spawn_width] (for parity tests) */
+/* the spawn rows every env was last reset with, [batch, spawn_width] (for parity tests); after a device-sampled
+ * reset (pmg_reset_device / auto-reset) the rows the reset kernel drew */
 int pmg_last_spawn(const pmg_handle* h, float* spawn_host);
+
+/* ---- device-side reset sampling and auto-reset ("spawn NULL => device Philox") ----------------
+ * pmg_reset samples on ONE host thread from the reference's MT19937 streams (seed parity with the reference).  For
+ * throughput runs the same sampling rules (kuka_single_step_base_env.py:104-148, kuka_multi_step_base_env.py:223-240,
+ * kuka_multi_step_envs.py:34-87,174-189) are applied inside the reset kernel to a Philox4x32-10 stream per
+ * (seed, env_index_base + env, episode number): no host work, no host<->device traffic, asynchronous on `stream`.
+ * It is a different random stream from the reference's; oracle/device_rng_oracle.py restates it bit-exactly.
+ * env_index_base: global index of this handle's env 0, so that a sharded batch draws the same rows whatever the
+ * sharding.  Not available for curriculum handles (their schedule lives on the host). */
+int pmg_set_device_rng(pmg_handle* h, uint64_t seed, int64_t env_index_base);
+/* pmg_reset with device sampling; mask_dev: nullable [batch] bytes ON THE DEVICE (non-zero = reset that env). */
+int pmg_reset_device(pmg_handle* h, const uint8_t* mask_dev, float* obs_dev, void* stream);
+/* Auto-reset (gym VectorEnv semantics; the reference's single env leaves this to the caller's `if done: reset()`):
+ * when on, every pmg_step / pmg_step_host* is followed on the same stream by a reset pass over the environments
+ * whose `done` flag that step raised; their rows of obs_dev become the first observation of the new episode, while
+ * reward / done / success stay those of the terminal step.  terminal_obs_dev: nullable [batch, W]; rows of the
+ * environments that reset receive their terminal observation (the other rows are not written). */
+int pmg_set_auto_reset(pmg_handle* h, int32_t on, float* terminal_obs_dev);
 
 /* replaces: env.activate_curriculum_update() / env.deactivate_curriculum_update()
  * (kuka_multi_step_base_env.py:147-157); curriculum handles only. */
@@ -112,6 +131,28 @@ int pmg_set_sub_goal(pmg_handle* h, const int32_t* ind_host, void* stream);
  * success = info['goal_achieved']).  One kernel launch, asynchronous on `stream`. */
 int pmg_step(pmg_handle* h, const float* action_dev, float* obs_dev, float* reward_dev,
              uint8_t* done_dev, uint8_t* success_dev, void* stream);
+
+/* ---- multi-GPU: the batch sharded over ranks, the returned batch gathered over peer memory -------
+ * One process per GPU, rank r owns environments [r * batch, (r + 1) * batch) of a global batch of world * batch.
+ * Environments share nothing, so the only exchange is the returned batch.  Instead of an all-gather launched behind
+ * the step kernel, the kernel's epilogue stores every finished environment's row, reward and flags straight into
+ * slice r of EVERY rank's gather buffer (peer-mapped memory: the stores travel over NVLink / NVSwitch while the other
+ * warps are still computing); the launch's last arrival publishes a per-rank sequence flag to all ranks and waits
+ * for theirs, so the kernel's completion means "my buffer holds the global batch of this step".  (With auto-reset on,
+ * the reset pass that follows the step kernel rewrites the rows of the finished environments and does the push.)
+ *
+ * pmg_gather_create allocates this rank's buffer and returns its 64-byte cudaIpcMemHandle; the caller exchanges the
+ * handles of all ranks (any host channel, e.g. torch.distributed.all_gather_object) and passes the world x 64 bytes
+ * to pmg_gather_connect.  world <= 8.  The buffer holds two copies (by step parity) of
+ *   [obs f32 world*batch x W | reward f32 world*batch | done u8 world*batch | success u8 world*batch]
+ * i.e. the global arrays, contiguous; pmg_gather_layout returns {bytes per parity copy, offsets of obs / reward /
+ * done / success inside a copy, total bytes}.  pmg_step_gather returns the four device pointers of the copy this
+ * step filled; they stay valid until the step after the next one (a peer may run at most one step ahead).
+ * Every rank must call pmg_step_gather the same number of times. */
+int pmg_gather_create(pmg_handle* h, int32_t rank, int32_t world, void* ipc_handle_out);
+int pmg_gather_connect(pmg_handle* h, const void* ipc_handles);
+int pmg_gather_layout(const pmg_handle* h, int64_t layout[6]);
+int pmg_step_gather(pmg_handle* h, const float* action_dev, void** gathered_dev_out, void* stream);
 
 /* Same call with HOST buffers (pinned or pageable): H2D of the actions, the step kernel, D2H of
  * obs / reward / done / success, then a stream synchronise.  This is the end-to-end entry a

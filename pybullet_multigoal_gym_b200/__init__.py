@@ -2,7 +2,9 @@
 
 `make_env` keeps the reference's signature (/root/reference/pybullet_multigoal_gym/__init__.py:4-11)
 and adds `batch` (number of environments stepped in lockstep; None = one unbatched env with the
-reference's numpy shapes), `device` and `seed`.  Tasks on the accelerated path: reach, push,
+reference's numpy shapes), `device`, `seed`, and the throughput options `device_sampling` (resets drawn on the
+device from Philox streams instead of the reference's host MT19937 streams) / `auto_reset` (environments reset
+themselves on the device when their episode ends).  Tasks on the accelerated path: reach, push,
 pick_and_place, block_stack, block_rearrange with the parallel-jaw gripper and state observations,
 including the `joint_control` and (block_stack) `grip_informed_goal` / `task_decomposition` / `use_curriculum` variants.
 """
@@ -29,7 +31,8 @@ def make_env(task='reach', gripper='parallel_jaw', num_block=5, render=False, bi
              visualize_target=True,
              camera_setup=None, observation_cam_id=None, goal_cam_id=0,
              use_curriculum=False, num_goals_to_generate=1e6,
-             batch=None, device=0, seed=0, check_actions=True):
+             batch=None, device=0, seed=0, check_actions=True, device_sampling=False, auto_reset=False,
+             env_index_base=0):
     grippers = ['robotiq85', 'parallel_jaw']
     assert gripper in grippers, 'invalid gripper: {}, only support: {}'.format(gripper, grippers)
     if task not in _TASKS:
@@ -73,4 +76,5 @@ def make_env(task='reach', gripper='parallel_jaw', num_block=5, render=False, bi
                         num_block=num_block, seed=seed, check_actions=check_actions,
                         grip_informed_goal=grip_informed_goal, joint_control=joint_control,
                         task_decomposition=task_decomposition,
-                        use_curriculum=use_curriculum, num_goals_to_generate=num_goals_to_generate)
+                        use_curriculum=use_curriculum, num_goals_to_generate=num_goals_to_generate,
+                        device_sampling=device_sampling, auto_reset=auto_reset, env_index_base=env_index_base)

@@ -10,12 +10,12 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 SO_PATH = os.environ.get("PMG_LIBRARY") or os.path.join(_HERE, "libpmg.so")  # PMG_LIBRARY: instrumented development builds
 
-ABI_VERSION = 5
+ABI_VERSION = 6
 
 # every symbol include/pmg.h declares
 SYMBOLS = [
     "pmg_abi_version", "pmg_last_error", "pmg_create", "pmg_destroy", "pmg_dims", "pmg_seed",
-    "pmg_reset", "pmg_spawn_width", "pmg_last_spawn", "pmg_set_curriculum_update", "pmg_get_curriculum", "pmg_set_sub_goal", "pmg_step", "pmg_step_host", "pmg_step_host_blocks",
+    "pmg_reset", "pmg_set_device_rng", "pmg_reset_device", "pmg_set_auto_reset", "pmg_spawn_width", "pmg_last_spawn", "pmg_set_curriculum_update", "pmg_get_curriculum", "pmg_set_sub_goal", "pmg_step", "pmg_gather_create", "pmg_gather_connect", "pmg_gather_layout", "pmg_step_gather", "pmg_step_host", "pmg_step_host_blocks",
     "pmg_compute_reward", "pmg_her_sample", "pmg_her_relabel", "pmg_state_width", "pmg_get_state", "pmg_set_state",
     "pmg_launch_count", "pmg_overflow_count",
 ]
@@ -52,12 +52,19 @@ def load():
     L.pmg_dims.argtypes = [vp, C.POINTER(C.c_int32)]
     L.pmg_seed.argtypes = [vp, vp, vp, C.c_int32]
     L.pmg_reset.argtypes = [vp, u8p, fp, fp, vp]
+    L.pmg_set_device_rng.argtypes = [vp, C.c_uint64, C.c_int64]
+    L.pmg_reset_device.argtypes = [vp, u8p, fp, vp]
+    L.pmg_set_auto_reset.argtypes = [vp, C.c_int32, fp]
     L.pmg_spawn_width.argtypes = [vp]
     L.pmg_last_spawn.argtypes = [vp, fp]
     L.pmg_set_curriculum_update.argtypes = [vp, C.c_int32]
     L.pmg_get_curriculum.argtypes = [vp, fp, vp]
     L.pmg_set_sub_goal.argtypes = [vp, vp, vp]
     L.pmg_step.argtypes = [vp, fp, fp, fp, u8p, u8p, vp]
+    L.pmg_gather_create.argtypes = [vp, C.c_int32, C.c_int32, vp]
+    L.pmg_gather_connect.argtypes = [vp, vp]
+    L.pmg_gather_layout.argtypes = [vp, C.POINTER(C.c_int64)]
+    L.pmg_step_gather.argtypes = [vp, fp, C.POINTER(vp), vp]
     L.pmg_step_host.argtypes = [vp, fp, fp, fp, u8p, u8p, vp]
     L.pmg_step_host_blocks.argtypes = [vp, fp, fp, fp, u8p, u8p, vp]
     L.pmg_compute_reward.argtypes = [fp, fp, C.c_int64, C.c_int32, C.c_float, C.c_int32, fp, u8p, vp]

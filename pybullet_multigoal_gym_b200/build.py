@@ -7,7 +7,15 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 SO = os.path.join(HERE, "libpmg.so")
 SOURCES = ["pmg_capi.cu"]
-DEPS = ["pmg_capi.cu", "pmg_sim.cuh", "pmg_physics.cuh", "../../include/pmg.h", "../../include/pmg_model_constants.h"]
+
+
+def _deps():
+    """Every source the library is built from: all of csrc/ and include/ (a stale libpmg.so must never be measured)."""
+    inc = os.path.join(HERE, "..", "include")
+    return ([os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC)) if f.endswith((".cu", ".cuh", ".h"))]
+            + [os.path.join(inc, f) for f in sorted(os.listdir(inc)) if f.endswith(".h")] + [os.path.abspath(__file__)])
+
+
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "--expt-relaxed-constexpr", "-prec-div=false", "-prec-sqrt=false", "-Xcompiler", "-fPIC", "-shared", "-Xptxas", "-v"]
 
@@ -16,7 +24,7 @@ def stale():
     if not os.path.exists(SO):
         return True
     t = os.path.getmtime(SO)
-    return any(os.path.getmtime(os.path.join(CSRC, d)) > t for d in DEPS)
+    return any(os.path.getmtime(d) > t for d in _deps())
 
 
 def build(force=False, verbose=False):

@@ -17,6 +17,7 @@
 #include "../../include/pmg.h"
 #include "pmg_sim.cuh"
 #include "pmg_coop.cuh"
+#include "pmg_spawn.cuh"
 
 using namespace pmg;
 
@@ -120,13 +121,27 @@ __device__ __forceinline__ void stage_row(const float* row, const StepIO& io, bo
   const int nvalid = max(0, min(io.epw, io.batch - env0)) * W;
   float* out = io.obs + (size_t)env0 * W;
   for (int k = lane; k < nvalid; k += 32) out[k] = ws[k];
+  if (io.g_n && io.g_in_step)  // fused gather: the same lines go to this rank's slice of every peer's buffer
+    for (int d = 0; d < io.g_n; d++) {
+      float* rout = io.g_obs[d] + (size_t)env0 * W;
+      for (int k = lane; k < nvalid; k += 32) rout[k] = ws[k];
+    }
+  if (io.g_n && io.g_in_step) __threadfence_system();  // idle lanes store too but never arrive: order their stores here
   __syncwarp();
+}
+
+// thread-per-env kernels: reward and flags of environment i to the peers, then sign it off
+__device__ __forceinline__ void gather_finish_thread(const StepIO& io, int i) {
+  if (io.g_n == 0 || !io.g_in_step) return;
+  for (int d = 0; d < io.g_n; d++) { io.g_reward[d][i] = io.reward[i]; io.g_done[d][i] = io.done[i]; io.g_success[d][i] = io.success[i]; }
+  gather_arrive(io);
 }
 
 // Writes the packed row [observation | policy_state | achieved_goal | desired_goal] and returns
 // the goal distance.  Run-time variants: joint control prepends the 7 arm joint angles to observation and
 // policy_state, a grip-informed goal appends gripper xyz + finger closeness to the achieved goal.
-template <int TASK, int NBLK>
+// DIRECT: the thread stores its row itself (the auto-reset path, where only some lanes of a warp have a row to write).
+template <int TASK, int NBLK, bool DIRECT = false>
 __device__ float write_obs(const Env<NBLK>& e, const StepIO& io, int i) {
   using D = Dims<TASK, NBLK>;
   const size_t B = io.batch;
@@ -203,7 +218,12 @@ __device__ float write_obs(const Env<NBLK>& e, const StepIO& io, int i) {
   }
   float d2 = 0.0f;
   for (int k = 0; k < G; k++) { float d = ag[k] - dg[k]; d2 += d * d; }
-  stage_row(row, io, true);
+  if (DIRECT) {
+    float* out = io.obs + (size_t)i * io.row_width;
+    for (int k = 0; k < io.row_width; k++) out[k] = row[k];
+  } else {
+    stage_row(row, io, true);
+  }
   return sqrtf(d2);
 }
 
@@ -277,6 +297,7 @@ __global__ void __launch_bounds__(32) step_kernel(StepIO io) {
   io.reward[i] = io.binary ? -(na ? 1.0f : 0.0f) : -dist;
   io.success[i] = na ? 0 : 1;
   io.done[i] = elapsed >= io.max_steps ? 1 : 0;
+  gather_finish_thread(io, i);
 }
 
 // Lane-cooperative Reach step (pmg_coop.cuh): 8 lanes per environment, 4 environments per one-warp block.
@@ -319,8 +340,8 @@ __global__ void __launch_bounds__(32, 7) step_kernel_coop_block(StepIO io) {
   coop::step_env_block<TASK>(g, sm, lane_consts, io, env);
 }
 
-// Lane-cooperative BlockStack / BlockRearrange step (NBLK = 2..5).  OPT-IN (PMG_COOP_STACK=1): verified against the
-// oracle on the CPU emulator only so far, not yet run or measured on the GPU.
+// Lane-cooperative BlockStack / BlockRearrange step (NBLK = 2..5), the default for these tasks since round 2: it passes
+// the same GPU parity tests as the thread-per-env kernel (PMG_COOP_STACK=0), racecheck-clean, 1.9x its rate at B = 2048.
 template <int NBLK>
 __global__ void __launch_bounds__(32, 3) step_kernel_coop_multi(StepIO io) {
   extern __shared__ __align__(16) unsigned char coop_smem[];
@@ -336,19 +357,31 @@ __global__ void __launch_bounds__(32, 3) step_kernel_coop_multi(StepIO io) {
   coop::step_env_multi<NBLK>(g, sm, lane_consts, io, env);
 }
 
-struct ResetIO { StepIO io; const uint8_t* mask; const float* spawn; float tip_init[3]; };
+// mask / spawn are device pointers.  spawn == nullptr: the row is sampled here from the environment's Philox stream
+// (pmg_spawn.cuh) and recorded in spawn_out.  auto_rows: the auto-reset pass behind a step -- mask is that step's
+// `done` flags, only the rows of the environments that reset are rewritten (with their first observation of the new
+// episode; the terminal row is copied to `terminal` first when given), reward / done / success stay the terminal ones.
+struct ResetIO {
+  StepIO io; const uint8_t* mask; const float* spawn; float tip_init[3];
+  int task, auto_rows; unsigned long long seed; long long env_base; uint32_t* episode; float* spawn_out; float* terminal;
+  spawn::Bounds bounds;
+};
 
+// Reset (doit) and observation of environment i.  Auto-reset pass: called for the finished environments only, the row
+// is stored by the thread itself and the terminal row is saved first when asked for.
 template <int TASK, int NBLK>
-__global__ void __launch_bounds__(32) reset_kernel(ResetIO r) {
-  using D = Dims<TASK, NBLK>;
+__device__ void reset_env(const ResetIO& r, int i, bool doit) {
   const StepIO& io = r.io;
-  const int i = env_of_thread(io);
-  if (i < 0) { stage_row(nullptr, io, false); return; }
   const size_t B = io.batch;
+  if (r.auto_rows && r.terminal) {
+    const float* src = io.obs + (size_t)i * io.row_width;
+    float* dst = r.terminal + (size_t)i * io.row_width;
+    for (int k = 0; k < io.row_width; k++) dst[k] = src[k];
+  }
+
   Env<NBLK> e;
   load_env<TASK, NBLK>(e, io, i, io.state + i, B);
   float* s = io.state + i;
-  const bool doit = r.mask == nullptr || r.mask[i] != 0;
   if (doit) {
     // Kuka.robot_specific_reset (kuka.py:157-165): joints to the rest pose, rest pose <- IK(start
     // position) seeded there, joints to the new rest pose, jaws closed with their motor on.
@@ -367,7 +400,19 @@ __global__ void __launch_bounds__(32) reset_kernel(ResetIO r) {
     Frames f;
     forward_kinematics<7>(e.q, f);
     V3 tip = tip_position(f);
-    const float* sp = r.spawn + (size_t)i * (2 * NBLK + io.goal_dim + (io.cur ? 1 : 0));
+    const int spawn_w = 2 * NBLK + io.goal_dim + (io.cur ? 1 : 0);
+    float sampled[2 * 5 + 3 * 5 + 4 + 1];
+    const float* sp;
+    if (r.spawn) sp = r.spawn + (size_t)i * spawn_w;
+    else {
+      spawn::Philox rng;
+      const uint32_t ep = r.episode[i];
+      r.episode[i] = ep + 1;
+      spawn::stream_init(rng, r.seed, r.env_base + i, ep);
+      spawn::sample_row(rng, r.task, NBLK, io.grip_goal, r.bounds, sampled);
+      for (int k = 0; k < spawn_w; k++) r.spawn_out[(size_t)i * spawn_w + k] = sampled[k];
+      sp = sampled;
+    }
 #pragma unroll
     for (int b = 0; b < NBLK; b++) {
       e.bpos[b] = v3(sp[2 * b], sp[2 * b + 1], BLOCK_SPAWN_Z);
@@ -384,8 +429,39 @@ __global__ void __launch_bounds__(32) reset_kernel(ResetIO r) {
     s[(size_t)(io.state_words - 1) * B] = 0.0f;
     store_env<TASK, NBLK>(e, io, i);
   }
-  write_obs<TASK, NBLK>(e, io, i);
+  if (r.auto_rows) write_obs<TASK, NBLK, true>(e, io, i);
+  else write_obs<TASK, NBLK>(e, io, i);
 }
+
+template <int TASK, int NBLK>
+__global__ void __launch_bounds__(32) reset_kernel(ResetIO r) {
+  using D = Dims<TASK, NBLK>;
+  const StepIO& io = r.io;
+  const int i = env_of_thread(io);
+  if (r.auto_rows) {  // auto-reset pass: only the environments that just finished an episode do anything ...
+    const bool mine = i >= 0 && r.mask[i] != 0;
+    if (mine) reset_env<TASK, NBLK>(r, i, true);
+    if (io.g_n) {  // ... and, when the batch is sharded, the warp then pushes its (final) rows to the peers
+      __syncwarp();
+      const int lane = threadIdx.x & 31, W = io.row_width;
+      const int env0 = ((blockIdx.x * blockDim.x + threadIdx.x) >> 5) * io.epw;
+      const int nenv = max(0, min(io.epw, io.batch - env0));
+      const float* rows = io.obs + (size_t)env0 * W;
+      for (int d = 0; d < io.g_n; d++) {
+        float* rout = io.g_obs[d] + (size_t)env0 * W;
+        for (int k = lane; k < nenv * W; k += 32) rout[k] = rows[k];
+        if (lane < nenv) { io.g_reward[d][env0 + lane] = io.reward[env0 + lane]; io.g_done[d][env0 + lane] = io.done[env0 + lane]; io.g_success[d][env0 + lane] = io.success[env0 + lane]; }
+      }
+      __threadfence_system();  // every lane stored (idle ones included): order the stores before any arrival of the warp
+      __syncwarp();
+      if (i >= 0) gather_arrive(io);
+    }
+    return;
+  }
+  if (i < 0) { stage_row(nullptr, io, false); return; }
+  reset_env<TASK, NBLK>(r, i, r.mask == nullptr || r.mask[i] != 0);
+}
+
 
 // packed rows [B, W] -> four contiguous blocks [B, O] [B, P] [B, G] [B, G] (pmg_step_host_blocks)
 __global__ void split_rows_kernel(const float* packed, int B, int W, int O, int P, int G, float* blocks) {
@@ -609,8 +685,20 @@ struct pmg_handle {
   bool default_carveout = false;  // PMG_DEFAULT_CARVEOUT=1 keeps the driver's shared-memory carve-out
   bool coop = true;  // Reach: lane-cooperative kernel (PMG_COOP=0 selects the thread-per-env kernel)
   bool coop_block = true;  // Push / PickAndPlace: lane-cooperative kernel (PMG_COOP_BLOCK=0 selects the thread-per-env kernel)
-  bool coop_stack = false; // BlockStack / BlockRearrange with >= 2 blocks: opt-in lane-cooperative kernel (PMG_COOP_STACK=1)
+  bool coop_stack = true;  // BlockStack / BlockRearrange with >= 2 blocks: lane-cooperative kernel (PMG_COOP_STACK=0 selects the thread-per-env kernel)
   bool hinted = false;  // shared-memory carve-out hint of this handle's step kernel has been set on its device
+  // device-side reset sampling (pmg_spawn.cuh) and auto-reset
+  bool dev_rng = false, auto_reset = false, last_spawn_on_device = false;
+  uint64_t rng_seed = 0; int64_t env_base = 0;
+  uint32_t* d_episode = nullptr; float* d_spawn_dev = nullptr; float* terminal_obs = nullptr;
+  // gather over peer memory (pmg_gather_*): this rank's buffer, the peers' mapped buffers, layout
+  int g_world = 0, g_rank = 0;
+  char* g_buf[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};  // [rank] = own allocation
+  bool g_connected = false;
+  unsigned g_seq = 0;
+  unsigned* d_g_counter = nullptr;
+  int* g_err_host = nullptr; int* g_err_dev = nullptr;
+  size_t g_parity_bytes = 0, g_off_reward = 0, g_off_done = 0, g_off_success = 0, g_flags_off = 0, g_total = 0;
 };
 
 namespace {
@@ -727,6 +815,7 @@ StepIO make_io(pmg_handle* h, const float* action, float* obs, float* reward, ui
   io.bulk = 0; io.tile_offset = 0;
   io.grasp = h->grasp; io.jc = h->jc; io.grip_goal = h->grip; io.td = h->td || h->cur; io.cur = h->cur;
   io.adim = h->A; io.goal_dim = h->G; io.row_width = h->W;
+  io.g_n = 0; io.g_in_step = 0; io.g_world = 0; io.g_seq = 0; io.g_flags_local = nullptr; io.g_counter = nullptr; io.g_err = nullptr;
   return io;
 }
 
@@ -805,6 +894,21 @@ void launch_reset(pmg_handle* h, const ResetIO& r, cudaStream_t st) {
       }                                                                              \
   }
 
+// Enqueues the reset kernel.  spawn_dev == nullptr: rows sampled on the device.  auto_rows: see ResetIO.
+void enqueue_reset(pmg_handle* h, const uint8_t* mask_dev, const float* spawn_dev, float* obs_dev, int auto_rows, cudaStream_t st,
+                   const StepIO* step_io = nullptr) {
+  ResetIO r;
+  r.io = step_io ? *step_io : make_io(h, nullptr, obs_dev, nullptr, nullptr, nullptr);
+  r.mask = mask_dev;
+  r.spawn = spawn_dev;
+  for (int k = 0; k < 3; k++) r.tip_init[k] = (float)h->tip_init[k];
+  r.task = h->cfg.task; r.auto_rows = auto_rows; r.seed = h->rng_seed; r.env_base = h->env_base;
+  r.episode = h->d_episode; r.spawn_out = h->d_spawn_dev; r.terminal = auto_rows ? h->terminal_obs : nullptr;
+  r.bounds = spawn::to_bounds(h->tip_init, h->obj_lo, h->obj_hi, h->tgt_lo, h->tgt_hi);
+  PMG_DISPATCH(launch_reset, h, r, st);
+  h->launches++;
+}
+
 }  // namespace
 
 // ------------------------------------------------------------------------------------------------
@@ -850,13 +954,7 @@ int pmg_create(const pmg_config* cfg, pmg_handle** out) {
   h->man_words = num_pairs(h->nblk) * MAN_WORDS;
   h->spawn_w = 2 * h->nblk + h->G + (h->cur ? 1 : 0);
   // kuka.py:35-51 with obj_range = target_range = 0.15 (kuka_single_step_envs.py, kuka_multi_step_envs.py:29)
-  h->tip_init[0] = -0.52; h->tip_init[1] = 0.0; h->tip_init[2] = (t == PMG_PUSH || t == PMG_BLOCK_REARRANGE) ? 0.175 + 0.001 : 0.25;
-  for (int k = 0; k < 3; k++) {
-    h->obj_lo[k] = h->tip_init[k] - 0.15; h->obj_hi[k] = h->tip_init[k] + 0.15;
-    h->tgt_lo[k] = h->tip_init[k] - 0.15; h->tgt_hi[k] = h->tip_init[k] + 0.15;
-  }
-  h->obj_lo[0] += 0.03; h->obj_hi[0] -= 0.03;
-  h->tgt_lo[0] += 0.03; h->tgt_lo[2] = 0.175; h->tgt_hi[0] -= 0.03;
+  spawn::task_bounds(t, h->tip_init, h->obj_lo, h->obj_hi, h->tgt_lo, h->tgt_hi);
   const size_t B = cfg->batch;
   {
     // Launch geometry: lanes [0, epw) of every warp own one environment.  Spreading a batch over
@@ -891,6 +989,8 @@ int pmg_create(const pmg_config* cfg, pmg_handle** out) {
   ALLOC(h->d_spawn, sizeof(float) * h->spawn_w * B);
   ALLOC(h->d_mask, B);
   ALLOC(h->d_overflow, sizeof(int));
+  ALLOC(h->d_episode, sizeof(uint32_t) * B);
+  ALLOC(h->d_spawn_dev, sizeof(float) * h->spawn_w * B);
   if ((h->cfg.task == PMG_PUSH || h->cfg.task == PMG_PICK_AND_PLACE) && h->coop_block)
     ALLOC(h->d_row_spill, sizeof(float) * coop::EnvSmemT<1>::SPILL_WORDS * B);
   if (h->multi && h->nblk >= 2 && h->coop_stack && !h->jc)
@@ -910,6 +1010,8 @@ int pmg_create(const pmg_config* cfg, pmg_handle** out) {
   cudaMemset(h->d_state, 0, sizeof(float) * h->state_words * B);
   cudaMemset(h->d_man, 0, sizeof(float) * h->man_words * B);
   cudaMemset(h->d_overflow, 0, sizeof(int));
+  cudaMemset(h->d_episode, 0, sizeof(uint32_t) * B);
+  cudaMemset(h->d_spawn_dev, 0, sizeof(float) * h->spawn_w * B);
   init_state_kernel<<<(int)((B + 31) / 32), 32>>>(h->d_state, (int)B, h->nblk, (float)h->tip_init[0], (float)h->tip_init[1], (float)h->tip_init[2]);
   h->launches++;
   CUDA_TRY(cudaDeviceSynchronize());
@@ -921,6 +1023,13 @@ int pmg_destroy(pmg_handle* h) {
   if (!h) return PMG_OK;
   cudaSetDevice(h->cfg.device);
   cudaFree(h->d_state); cudaFree(h->d_man); cudaFree(h->d_spawn); cudaFree(h->d_mask); cudaFree(h->d_overflow); cudaFree(h->d_row_spill);
+  cudaFree(h->d_episode); cudaFree(h->d_spawn_dev);
+  for (int d = 0; d < h->g_world; d++) {
+    if (!h->g_buf[d]) continue;
+    if (d == h->g_rank) cudaFree(h->g_buf[d]); else cudaIpcCloseMemHandle(h->g_buf[d]);
+  }
+  cudaFree(h->d_g_counter);
+  if (h->g_err_host) cudaFreeHost(h->g_err_host);
   cudaFree(h->d_action); cudaFree(h->d_obs); cudaFree(h->d_blocks); cudaFree(h->d_reward); cudaFree(h->d_done); cudaFree(h->d_success);
   if (h->h_spawn) cudaFreeHost(h->h_spawn);
   for (int k = 0; k < 2; k++) { if (h->h_stage[k]) cudaFreeHost(h->h_stage[k]); if (h->stage_done[k]) cudaEventDestroy(h->stage_done[k]); }
@@ -947,6 +1056,12 @@ int pmg_spawn_width(const pmg_handle* h) { return h ? h->spawn_w : PMG_ERR_INVAL
 
 int pmg_last_spawn(const pmg_handle* h, float* spawn_host) {
   if (!h || !spawn_host) return fail(PMG_ERR_INVALID, "pmg_last_spawn: null argument%s");
+  if (h->last_spawn_on_device) {  // rows sampled by the reset kernel (pmg_reset_device / auto-reset)
+    CUDA_TRY(cudaSetDevice(h->cfg.device));
+    CUDA_TRY(cudaDeviceSynchronize());
+    CUDA_TRY(cudaMemcpy(spawn_host, h->d_spawn_dev, sizeof(float) * h->spawn_w * h->cfg.batch, cudaMemcpyDeviceToHost));
+    return PMG_OK;
+  }
   memcpy(spawn_host, h->h_spawn, sizeof(float) * h->spawn_w * h->cfg.batch);
   return PMG_OK;
 }
@@ -973,16 +1088,40 @@ int pmg_reset(pmg_handle* h, const uint8_t* mask_host, const float* spawn_host, 
   CUDA_TRY(cudaEventRecord(h->stage_done[h->stage_cur], st));
   h->stage_cur ^= 1;
   if (mask_host) CUDA_TRY(cudaMemcpyAsync(h->d_mask, mask_host, B, cudaMemcpyHostToDevice, st));
-  ResetIO r;
-  r.io = make_io(h, nullptr, obs_dev, nullptr, nullptr, nullptr);
-  r.mask = mask_host ? h->d_mask : nullptr;
-  r.spawn = h->d_spawn;
-  for (int k = 0; k < 3; k++) r.tip_init[k] = (float)h->tip_init[k];
-  PMG_DISPATCH(launch_reset, h, r, st);
-  h->launches++;
+  enqueue_reset(h, mask_host ? h->d_mask : nullptr, h->d_spawn, obs_dev, 0, st);
   CUDA_TRY(cudaGetLastError());
   if (mask_host) CUDA_TRY(cudaStreamSynchronize(st));  // mask_host may be pageable caller memory
   h->was_reset = true;
+  h->last_spawn_on_device = false;
+  return PMG_OK;
+}
+
+int pmg_set_device_rng(pmg_handle* h, uint64_t seed, int64_t env_index_base) {
+  if (!h) return fail(PMG_ERR_INVALID, "pmg_set_device_rng: null handle%s");
+  if (h->cur) return fail(PMG_ERR_STATE, "pmg_set_device_rng: curriculum resets are sampled on the host (their schedule lives there)%s");
+  CUDA_TRY(cudaSetDevice(h->cfg.device));
+  h->dev_rng = true; h->rng_seed = seed; h->env_base = env_index_base;
+  CUDA_TRY(cudaDeviceSynchronize());
+  CUDA_TRY(cudaMemset(h->d_episode, 0, sizeof(uint32_t) * h->cfg.batch));
+  return PMG_OK;
+}
+
+int pmg_reset_device(pmg_handle* h, const uint8_t* mask_dev, float* obs_dev, void* stream) {
+  if (!h || !obs_dev) return fail(PMG_ERR_INVALID, "pmg_reset_device: null argument%s");
+  if (!h->dev_rng) return fail(PMG_ERR_STATE, "pmg_reset_device: call pmg_set_device_rng first%s");
+  CUDA_TRY(cudaSetDevice(h->cfg.device));
+  enqueue_reset(h, mask_dev, nullptr, obs_dev, 0, (cudaStream_t)stream);
+  CUDA_TRY(cudaGetLastError());
+  h->was_reset = true;
+  h->last_spawn_on_device = true;
+  return PMG_OK;
+}
+
+int pmg_set_auto_reset(pmg_handle* h, int32_t on, float* terminal_obs_dev) {
+  if (!h) return fail(PMG_ERR_INVALID, "pmg_set_auto_reset: null handle%s");
+  if (on && !h->dev_rng) return fail(PMG_ERR_STATE, "pmg_set_auto_reset: call pmg_set_device_rng first%s");
+  h->auto_reset = on != 0;
+  h->terminal_obs = on ? terminal_obs_dev : nullptr;
   return PMG_OK;
 }
 
@@ -1028,7 +1167,105 @@ int pmg_step(pmg_handle* h, const float* action_dev, float* obs_dev, float* rewa
   StepIO io = make_io(h, action_dev, obs_dev, reward_dev, done_dev, success_dev);
   PMG_DISPATCH(launch_step, h, io, st);
   h->launches++;
+  if (h->auto_reset) {  // environments whose episode just ended reset themselves; their rows become the new episode's first observation
+    enqueue_reset(h, done_dev, nullptr, obs_dev, 1, st);
+    h->last_spawn_on_device = true;
+  }
   CUDA_TRY(cudaGetLastError());
+  return PMG_OK;
+}
+
+// ---- multi-GPU gather over peer memory ----------------------------------------------------------------------------
+int pmg_gather_create(pmg_handle* h, int32_t rank, int32_t world, void* ipc_handle_out) {
+  if (!h || !ipc_handle_out) return fail(PMG_ERR_INVALID, "pmg_gather_create: null argument%s");
+  if (world < 1 || world > 8 || rank < 0 || rank >= world) return fail(PMG_ERR_INVALID, "pmg_gather_create: 1 <= world <= 8, 0 <= rank < world%s");
+  if (h->g_world) return fail(PMG_ERR_STATE, "pmg_gather_create: the handle already has a gather buffer%s");
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "include/pmg.h documents 64-byte IPC handles");
+  CUDA_TRY(cudaSetDevice(h->cfg.device));
+  const size_t Bg = (size_t)h->cfg.batch * world;
+  auto up = [](size_t v) { return (v + 255) / 256 * 256; };
+  h->g_off_reward = up(Bg * h->W * sizeof(float));
+  h->g_off_done = h->g_off_reward + up(Bg * sizeof(float));
+  h->g_off_success = h->g_off_done + up(Bg);
+  h->g_parity_bytes = h->g_off_success + up(Bg);
+  h->g_flags_off = 2 * h->g_parity_bytes;
+  h->g_total = h->g_flags_off + 256;
+  char* buf = nullptr;
+  CUDA_TRY(cudaMalloc((void**)&buf, h->g_total));
+  CUDA_TRY(cudaMemset(buf, 0, h->g_total));
+  CUDA_TRY(cudaMalloc((void**)&h->d_g_counter, sizeof(unsigned)));
+  CUDA_TRY(cudaMemset(h->d_g_counter, 0, sizeof(unsigned)));
+  CUDA_TRY(cudaHostAlloc((void**)&h->g_err_host, sizeof(int), cudaHostAllocMapped));
+  *h->g_err_host = 0;
+  CUDA_TRY(cudaHostGetDevicePointer((void**)&h->g_err_dev, h->g_err_host, 0));
+  CUDA_TRY(cudaDeviceSynchronize());
+  h->g_world = world; h->g_rank = rank; h->g_buf[rank] = buf; h->g_seq = 0;
+  h->g_connected = world == 1;
+  CUDA_TRY(cudaIpcGetMemHandle((cudaIpcMemHandle_t*)ipc_handle_out, buf));
+  return PMG_OK;
+}
+
+int pmg_gather_connect(pmg_handle* h, const void* ipc_handles) {
+  if (!h || !ipc_handles) return fail(PMG_ERR_INVALID, "pmg_gather_connect: null argument%s");
+  if (!h->g_world) return fail(PMG_ERR_STATE, "pmg_gather_connect: call pmg_gather_create first%s");
+  CUDA_TRY(cudaSetDevice(h->cfg.device));
+  const cudaIpcMemHandle_t* hs = (const cudaIpcMemHandle_t*)ipc_handles;
+  for (int d = 0; d < h->g_world; d++) {
+    if (d == h->g_rank || h->g_buf[d]) continue;
+    void* p = nullptr;
+    CUDA_TRY(cudaIpcOpenMemHandle(&p, hs[d], cudaIpcMemLazyEnablePeerAccess));
+    h->g_buf[d] = (char*)p;
+  }
+  h->g_connected = true;
+  return PMG_OK;
+}
+
+int pmg_gather_layout(const pmg_handle* h, int64_t layout[6]) {
+  if (!h || !layout) return fail(PMG_ERR_INVALID, "pmg_gather_layout: null argument%s");
+  if (!h->g_world) return fail(PMG_ERR_STATE, "pmg_gather_layout: call pmg_gather_create first%s");
+  layout[0] = (int64_t)h->g_parity_bytes; layout[1] = 0; layout[2] = (int64_t)h->g_off_reward; layout[3] = (int64_t)h->g_off_done;
+  layout[4] = (int64_t)h->g_off_success; layout[5] = (int64_t)h->g_total;
+  return PMG_OK;
+}
+
+int pmg_step_gather(pmg_handle* h, const float* action_dev, void** gathered_dev_out, void* stream) {
+  if (!h || !action_dev || !gathered_dev_out) return fail(PMG_ERR_INVALID, "pmg_step_gather: null argument%s");
+  if (!h->was_reset) return fail(PMG_ERR_STATE, "pmg_step_gather: call pmg_reset first%s");
+  if (!h->g_connected) return fail(PMG_ERR_STATE, "pmg_step_gather: call pmg_gather_create and pmg_gather_connect first%s");
+  if (*h->g_err_host) return fail(PMG_ERR_CUDA, "pmg_step_gather: a peer rank did not publish its step within 5 s%s");
+  cudaStream_t st = (cudaStream_t)stream;
+  CUDA_TRY(cudaSetDevice(h->cfg.device));
+  const unsigned seq = ++h->g_seq;
+  const size_t par = (size_t)(seq & 1u) * h->g_parity_bytes;
+  const size_t B = h->cfg.batch, row0 = B * h->g_rank;
+  auto slice = [&](int d, float*& obs, float*& rew, uint8_t*& dn, uint8_t*& su) {
+    char* base = h->g_buf[d] + par;
+    obs = (float*)base + row0 * h->W; rew = (float*)(base + h->g_off_reward) + row0;
+    dn = (uint8_t*)(base + h->g_off_done) + row0; su = (uint8_t*)(base + h->g_off_success) + row0;
+  };
+  float *obs, *rew; uint8_t *dn, *su;
+  slice(h->g_rank, obs, rew, dn, su);
+  StepIO io = make_io(h, action_dev, obs, rew, dn, su);
+  int n = 0;
+  for (int d = 0; d < h->g_world; d++) {
+    io.g_flag[d] = (unsigned*)(h->g_buf[d] + h->g_flags_off) + h->g_rank;
+    if (d == h->g_rank) continue;
+    slice(d, io.g_obs[n], io.g_reward[n], io.g_done[n], io.g_success[n]);
+    n++;
+  }
+  io.g_n = n; io.g_world = h->g_world; io.g_seq = seq; io.g_in_step = h->auto_reset ? 0 : 1;
+  io.g_flags_local = (const unsigned*)(h->g_buf[h->g_rank] + h->g_flags_off);
+  io.g_counter = h->d_g_counter; io.g_err = h->g_err_dev;
+  if (n == 0) io.g_in_step = 0;  // world 1: nothing to push, nothing to wait for
+  PMG_DISPATCH(launch_step, h, io, st);
+  h->launches++;
+  if (h->auto_reset) {  // the reset pass rewrites the rows of the finished environments, then pushes and publishes
+    enqueue_reset(h, dn, nullptr, obs, 1, st, &io);
+    h->last_spawn_on_device = true;
+  }
+  CUDA_TRY(cudaGetLastError());
+  char* base = h->g_buf[h->g_rank] + par;
+  gathered_dev_out[0] = base; gathered_dev_out[1] = base + h->g_off_reward; gathered_dev_out[2] = base + h->g_off_done; gathered_dev_out[3] = base + h->g_off_success;
   return PMG_OK;
 }
 

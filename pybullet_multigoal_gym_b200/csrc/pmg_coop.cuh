@@ -1238,6 +1238,25 @@ __device__ void substep(const Grp& g, SM& sm, Lane& L) {
 #endif
 }
 
+// ---- fused gather: the octet copies its finished row, reward and flags to the peers' gather buffers -------------
+// (multi-GPU sharding, include/pmg.h pmg_step_gather).  The row was just written to this rank's own buffer by lanes
+// of this octet; after the octet barrier the 8 lanes copy it with 32-byte segments to every peer over NVLink, then
+// lane 0 signs the environment off (gather_arrive).  Nothing happens when no gather is attached (g_n == 0).
+__device__ __forceinline__ void gather_push(const Grp& g, const StepIO& io, int env) {
+  if (io.g_n == 0 || !io.g_in_step) return;
+  g.sync();
+  const int W = io.row_width;
+  const float* row = io.obs + (size_t)env * W;
+  for (int d = 0; d < io.g_n; d++) {
+    float* dst = io.g_obs[d] + (size_t)env * W;
+    for (int k = g.lane; k < W; k += GL) dst[k] = row[k];
+    if (g.lane == 0) { io.g_reward[d][env] = io.reward[env]; io.g_done[d][env] = io.done[env]; io.g_success[d][env] = io.success[env]; }
+  }
+  __threadfence_system();
+  g.sync();
+  if (g.lane == 0) gather_arrive(io);
+}
+
 // ---- one env.step() of a Reach environment (TASK 0, no blocks) -------------------------------------
 // `env` is the environment index, state / manifold are the same [word][env] arrays the thread-per-env
 // kernels use, so reset_kernel, pmg_get_state / pmg_set_state and the reward path are shared.
@@ -1314,6 +1333,7 @@ __device__ void step_env_reach(const Grp& g, EnvSmem& sm, const float* lane_cons
     io.success[env] = na ? 0 : 1;
     io.done[env] = elapsed >= io.max_steps ? 1 : 0;
   }
+  gather_push(g, io, env);
 }
 
 // ---- one env.step() of a one-block environment: Push (TASK 1) / PickAndPlace (TASK 2) -----------------------
@@ -1432,6 +1452,7 @@ __device__ void step_env_block(const Grp& g, EnvSmemT<1>& sm, const float* lane_
     io.success[env] = na ? 0 : 1;
     io.done[env] = elapsed >= io.max_steps ? 1 : 0;
   }
+  gather_push(g, io, env);
 }
 
 // ---- multi-block environments: one env.step() -------------------------------------------------------------------
@@ -1562,6 +1583,7 @@ __device__ void step_env_multi(const Grp& g, EnvSmemT<NBLK>& sm, const float* la
     io.success[env] = na ? 0 : 1;
     io.done[env] = elapsed >= io.max_steps ? 1 : 0;
   }
+  gather_push(g, io, env);
 }
 
 }  // namespace coop

@@ -614,7 +614,48 @@ struct StepIO {
   int cur;          // curriculum: that word is set by the reset (from the spawn row) instead of -1
   int adim, goal_dim, row_width;  // action columns, goal length, packed row width (all after the variants above)
   float* row_spill;               // cooperative block kernel: contact-row records beyond the shared-memory ones
+  // ---- multi-GPU gather over peer memory (pmg_step_gather; include/pmg.h) ----
+  // obs / reward / done / success above point at this rank's slice of its OWN gather buffer; g_* are the same slices
+  // of the g_n peers' buffers (peer-mapped device pointers: plain stores travel over NVLink).
+  int g_n;               // number of remote destinations, 0 = no gather
+  int g_in_step;         // 1: the step kernel pushes and publishes; 0: the auto-reset pass behind it does
+  int g_world;           // ranks (flags to publish / wait for)
+  unsigned g_seq;        // sequence number of this step
+  float* g_obs[7]; float* g_reward[7]; uint8_t* g_done[7]; uint8_t* g_success[7];
+  unsigned* g_flag[8];   // this rank's flag word in every rank's buffer (own buffer included)
+  const unsigned* g_flags_local;  // the world flag words of the own buffer
+  unsigned* g_counter;   // arrivals of this launch (one per environment), reset by the last one
+  int* g_err;            // mapped host word: set when a peer's flag did not arrive in time
 };
+
+#ifndef PMG_EMULATE
+// Called once per environment after its row, reward and flags are stored locally AND on the peers.  The last arrival
+// of the launch publishes this rank's sequence number to every rank and then waits for theirs, so that the kernel's
+// completion means "the local gather buffer holds the whole global batch of this step".  Peers never wait for this
+// kernel to finish, only for the flag it has already published, so there is no cyclic wait.  The data buffers are
+// double-buffered by the parity of g_seq (a peer can be at most one step ahead).
+__device__ __forceinline__ void gather_arrive(const StepIO& io) {
+  __threadfence_system();  // this environment's peer stores are ordered before the arrival
+  const unsigned old = atomicAdd(io.g_counter, 1u);
+  if (old != (unsigned)io.batch - 1u) return;
+  atomicExch(io.g_counter, 0u);
+  __threadfence_system();  // every environment's stores (observed through the counter) before the flags
+  for (int d = 0; d < io.g_world; d++) *(volatile unsigned*)io.g_flag[d] = io.g_seq;
+  unsigned long long t0, t1;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+  for (int src = 0; src < io.g_world; src++) {
+    const volatile unsigned* f = io.g_flags_local + src;
+    while ((int)(*f - io.g_seq) < 0) {
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+      if (t1 - t0 > 5000000000ull) { *(volatile int*)io.g_err = 1 + src; return; }  // 5 s: a peer died; report, do not hang the GPU
+      __nanosleep(200);
+    }
+  }
+  __threadfence_system();
+}
+#else
+__device__ __forceinline__ void gather_arrive(const StepIO&) {}
+#endif
 
 template <int TASK, int NBLK> struct Dims {
   static constexpr int O = TASK == 0 ? 3 : (TASK == 3 ? 8 + 16 * NBLK : 20);

@@ -73,7 +73,8 @@ class KukaBulletMGEnv:
     def __init__(self, task, batch=None, device=0, binary_reward=True, distance_threshold=0.05,
                  max_episode_steps=50, num_block=4, seed=0, check_actions=True,
                  grip_informed_goal=False, joint_control=False, task_decomposition=False,
-                 use_curriculum=False, num_goals_to_generate=1e6):
+                 use_curriculum=False, num_goals_to_generate=1e6, device_sampling=False, auto_reset=False,
+                 env_index_base=0):
         if task not in TASK_IDS:
             raise ValueError("invalid task name: %s, only support: %s" % (task, sorted(TASK_IDS)))
         self._L = _lib.load()
@@ -149,8 +150,14 @@ class KukaBulletMGEnv:
         self._p_done, self._p_success = _ptr(self._h_done), _ptr(self._h_success)
         self.action_space = spaces.Box(-np.ones([self.action_dim]), np.ones([self.action_dim]))  # kuka.py:109-118
         self.desired_goal = None
+        self.device_sampling = self.auto_reset = False
+        self._terminal = None
         self.seed(seed)
+        if device_sampling or auto_reset:
+            self.enable_device_sampling(seed=seed, env_index_base=env_index_base)
         obs = self.reset()  # the reference ctor resets once (base_env.py:84) and so consumes the RNG
+        if auto_reset:
+            self.set_auto_reset(True)
         shp = (lambda k: tuple(obs[k].shape))
         self.observation_space = spaces.Dict(dict(  # base_env.py:86-92 (note: 'state', not 'observation')
             state=spaces.Box(-np.inf, np.inf, shape=shp("observation"), dtype="float32"),
@@ -191,6 +198,8 @@ class KukaBulletMGEnv:
         """base_env.py:124-128.  `mask` ([batch] bool) resets a subset; `spawn` ([batch, 2*nb+G])
         overrides the sampled block xy / goal.  Returns torch CUDA tensors when the env is batched
         (numpy for batch=None) unless device_output says otherwise."""
+        if self.device_sampling and spawn is None:
+            return self._reset_device(mask, device_output)
         with torch.cuda.device(self.device):
             out = torch.empty((self.batch, self.row_width), dtype=torch.float32, device=self.device)
             m = None
@@ -205,6 +214,47 @@ class KukaBulletMGEnv:
                     raise ValueError("spawn must have shape (%d, %d)" % (self.batch, self._L.pmg_spawn_width(self._h)))
             _lib.check(self._L.pmg_reset(self._h, m.ctypes.data_as(C.c_void_p) if m is not None else None,
                                          sp.ctypes.data_as(C.c_void_p) if sp is not None else None, _ptr(out), self._stream()))
+            obs = self._split(out)
+            self.desired_goal = obs["desired_goal"]
+            if device_output is None:
+                device_output = not self._squeeze
+            if device_output:
+                return obs
+            host = self._to_host_obs(out.cpu().numpy())
+            if self._squeeze:
+                self.desired_goal = host["desired_goal"]
+            return host
+
+    # ---- device-side sampling / auto-reset (no reference counterpart; include/pmg.h) -------------------
+    def enable_device_sampling(self, seed=0, env_index_base=0):
+        """Resets are sampled inside the reset kernel from Philox streams keyed by (seed, env_index_base + i, episode)
+        instead of on the host from the reference's MT19937 streams: same sampling rules, different random numbers,
+        no host work and no synchronisation (pmg_set_device_rng)."""
+        _lib.check(self._L.pmg_set_device_rng(self._h, int(seed) & (2 ** 64 - 1), int(env_index_base)))
+        self.device_sampling = True
+
+    def set_auto_reset(self, on=True, keep_terminal_observation=False):
+        """gym VectorEnv-style auto-reset on the device: after every step the environments whose episode ended
+        (`done`) reset themselves and their observation rows are those of the new episode; reward / done / info are the
+        terminal step's.  With keep_terminal_observation the terminal rows are returned in
+        info['terminal_observation'] (valid where done)."""
+        if on and not self.device_sampling:
+            self.enable_device_sampling()
+        self._terminal = None
+        if on and keep_terminal_observation:
+            self._terminal = torch.zeros((self.batch, self.row_width), dtype=torch.float32, device=self.device)
+        _lib.check(self._L.pmg_set_auto_reset(self._h, int(bool(on)), _ptr(self._terminal) if self._terminal is not None else None))
+        self.auto_reset = bool(on)
+
+    def _reset_device(self, mask, device_output):
+        with torch.cuda.device(self.device):
+            out = torch.empty((self.batch, self.row_width), dtype=torch.float32, device=self.device)
+            m = None
+            if mask is not None:
+                m = torch.as_tensor(mask).to(self.device).ne(0).to(torch.uint8).contiguous()
+                if tuple(m.shape) != (self.batch,):
+                    raise ValueError("mask must have shape (%d,)" % self.batch)
+            _lib.check(self._L.pmg_reset_device(self._h, _ptr(m) if m is not None else None, _ptr(out), self._stream()))
             obs = self._split(out)
             self.desired_goal = obs["desired_goal"]
             if device_output is None:
@@ -274,8 +324,9 @@ class KukaBulletMGEnv:
             raise ActionError("action outside the action space Box(-1, 1, (%d,))" % self.action_dim)
 
     def step(self, action):
-        """base_env.py:130-138 + TimeLimit.  CUDA tensor in -> CUDA tensors out (asynchronous on the
-        current stream); numpy / CPU tensor in -> numpy out through the host-buffer C-ABI call."""
+        """base_env.py:130-138 + TimeLimit.  CUDA tensor in -> CUDA tensors out (asynchronous on the current stream
+        when the env was made with check_actions=False; the range check of the default reads a flag back, i.e.
+        synchronises); numpy / CPU tensor in -> numpy out through the host-buffer C-ABI call."""
         if torch.is_tensor(action) and action.is_cuda:
             return self._step_device(action)
         a = np.asarray(action.numpy() if torch.is_tensor(action) else action, dtype=np.float32)
@@ -301,11 +352,16 @@ class KukaBulletMGEnv:
         ok = self._np_success.view(np.bool_).copy()
         if not self.binary_reward:
             reward = reward.astype(np.float64)
+        self.desired_goal = obs["desired_goal"]
         if self._squeeze:
-            self.desired_goal = obs["desired_goal"]
-            info = {"goal_achieved": bool(ok[0]), "is_success": bool(ok[0]), "TimeLimit.truncated": bool(done[0])}
+            info = {"goal_achieved": bool(ok[0]), "is_success": bool(ok[0])}
+            if done[0]:
+                info["TimeLimit.truncated"] = True  # gym's TimeLimit sets the key only when the limit ends the episode
             return obs, reward[0], bool(done[0]), info
+        # batched: the key is an array, True where the limit ended the episode
         info = {"goal_achieved": ok, "is_success": ok, "TimeLimit.truncated": done.copy()}
+        if self._terminal is not None:
+            info["terminal_observation"] = self._split(self._terminal)
         return obs, reward, done, info
 
     def _step_device(self, action):
@@ -314,7 +370,7 @@ class KukaBulletMGEnv:
         if tuple(action.shape) != (self.batch, self.action_dim):
             raise ActionError("action must have shape (%d, %d)" % (self.batch, self.action_dim))
         action = action.to(dtype=torch.float32).contiguous()
-        if self.check_actions and bool((action.abs() > 1.0).any()):
+        if self.check_actions and not bool(((action >= -1.0) & (action <= 1.0)).all()):  # NaN fails the test, like Box.contains
             raise ActionError("action outside the action space Box(-1, 1, (%d,))" % self.action_dim)
         with torch.cuda.device(self.device):
             out = torch.empty((self.batch, self.row_width), dtype=torch.float32, device=self.device)
@@ -324,7 +380,10 @@ class KukaBulletMGEnv:
         obs = self._split(out)
         self.desired_goal = obs["desired_goal"]
         done, ok = flags[0].bool(), flags[1].bool()
-        return obs, reward, done, {"goal_achieved": ok, "is_success": ok, "TimeLimit.truncated": done}
+        info = {"goal_achieved": ok, "is_success": ok, "TimeLimit.truncated": done}
+        if self._terminal is not None:
+            info["terminal_observation"] = self._split(self._terminal)
+        return obs, reward, done, info
 
     def step_packed(self, action, out, reward, done, success):
         """Zero-allocation device path: caller-owned CUDA buffers (used by bench.py and the sharded env)."""

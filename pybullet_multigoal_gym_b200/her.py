@@ -33,13 +33,17 @@ def sample(n, n_episodes, horizon, her_prob=0.8, seed=0, device=0):
 def relabel(achieved_goals, desired_goals, episode, t, future, distance_threshold=0.05, binary_reward=True):
     """achieved_goals [E, T + 1, G], desired_goals [E, G] (CUDA float32) -> (goals [n, G], reward [n], achieved [n])."""
     L = _lib.load()
-    ag = achieved_goals.contiguous()
-    dg = desired_goals.contiguous()
+    ag = achieved_goals.to(torch.float32).contiguous()
+    dg = desired_goals.to(torch.float32).contiguous()
     E, T1, G = ag.shape
     if tuple(dg.shape) != (E, G):
         raise AssertionError("desired_goals must have shape (%d, %d)" % (E, G))
     n = int(episode.numel())
     dev = ag.device
+    # the kernel reads int32 indices: convert (int64 tensors would be misread) and keep them on the goals' device
+    episode, t, future = (x.to(device=dev, dtype=torch.int32).contiguous() for x in (episode, t, future))
+    if not (t.numel() == n and future.numel() == n):
+        raise ValueError("episode, t and future must have the same length")
     with torch.cuda.device(dev):
         goals = torch.empty((n, G), dtype=torch.float32, device=dev)
         reward = torch.empty((n,), dtype=torch.float32, device=dev)

@@ -14,6 +14,7 @@
 #include <ucontext.h>
 
 #include "../../pybullet_multigoal_gym_b200/csrc/pmg_coop.cuh"
+#include "../../pybullet_multigoal_gym_b200/csrc/pmg_spawn.cuh"
 
 namespace pmg_emu {
 
@@ -307,3 +308,15 @@ int pmg_emu_step_jc(int task, float* state, float* manifold, const float* action
   return pmg_emu::run_group(blk_body, &a);
 }
 }
+
+// the device-side reset sampler (csrc/pmg_spawn.cuh) on the host, for the bit-exact comparison with
+// oracle/device_rng_oracle.py in the CPU test suite
+extern "C" void pmg_emu_device_spawn(int task, int nb, int grip, unsigned long long seed, long long env, unsigned episode, float* out) {
+  double tip[3], ol[3], oh[3], tl[3], th[3];
+  pmg::spawn::task_bounds(task, tip, ol, oh, tl, th);
+  const pmg::spawn::Bounds b = pmg::spawn::to_bounds(tip, ol, oh, tl, th);
+  pmg::spawn::Philox r;
+  pmg::spawn::stream_init(r, seed, env, episode);
+  pmg::spawn::sample_row(r, task, nb, grip, b, out);
+}
+extern "C" void pmg_emu_philox(const unsigned* ctr, const unsigned* key, unsigned* out) { pmg::spawn::philox_block(ctr, key, out); }

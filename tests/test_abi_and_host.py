@@ -27,7 +27,7 @@ def test_library_exports_every_declared_symbol():
     missing = [s for s in declared if not hasattr(L, s)]
     assert not missing, "libpmg.so lacks: %s" % missing
     assert sorted(_lib.SYMBOLS) == declared
-    assert _lib.load().pmg_abi_version() == 5
+    assert _lib.load().pmg_abi_version() == _lib.ABI_VERSION == 6
     # the library is sm_100a SASS produced by our own sources (kept in-tree, not in site-packages)
     assert os.path.dirname(_lib.SO_PATH) == os.path.join(ROOT, "pybullet_multigoal_gym_b200")
 

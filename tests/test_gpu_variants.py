@@ -86,14 +86,12 @@ def test_reach_joint_control_rollout_matches_golden():
 
 @pytest.mark.parametrize("name", ["block_rearrange", "block_stack_grip", "pick_and_place_jc"])
 def test_variant_teacher_forced_steps_match_oracle(oracle, name):
-    """One env.step at a time from the oracle's own fp32-rounded state (contact-rich rollouts are chaotic in
-    open loop, tests/test_gpu_parity.py): positions of the packed row (tip, joint poses, achieved / desired
-    goal incl. the grip entries) within 1e-4 on >= 97 % of the well-conditioned steps, judged by a
-    1e-7-perturbed twin of the oracle as in test_teacher_forced_contact_parity.  The physics is the one those
-    tests cover; this test is about the variants' plumbing, so a jaw landing on a block edge (a discrete
-    contact decision fp32 may take differently) is only bounded at 1 cm instead of failing the run.
-    Velocity entries are not compared at 1e-4: the relative angular velocity of a resting block carries
-    ~3e-4 rad/s of fp32 contact-depth noise (known deviations; test_gpu_parity.py bounds it)."""
+    """One env.step at a time from the oracle's own fp32-rounded state (tests/_teacher.py): every entry of the packed
+    row, joint poses and grip-goal entries included.  On the steps the oracle is well-conditioned on (4 perturbed
+    twins; a single twin missed the tri-modal jaw-on-block-edge steps of env 2 here about one time in five, which is
+    why this test used to carry a 1 cm escape hatch) position entries are within 1e-4 on >= 97 % of the env-steps and
+    within 5e-4 on all of them; velocity entries are bounded and their within-1e-4 fraction is printed."""
+    from tests import _teacher
     kw = VARIANTS[name]
     B = 6
     env = _mk(B, **kw)
@@ -104,51 +102,23 @@ def test_variant_teacher_forced_steps_match_oracle(oracle, name):
         o = oracle.OracleEnv(seed=i, **kw)
         o.reset_with(spawn[i].astype(np.float64))
         refs.append(o)
-        twins.append(oracle.OracleEnv(seed=i, **kw))
-    rng = np.random.RandomState(11)
-    A = env.action_dim
-    errs, loose = [], 0
-    for t in range(24):
-        st = np.stack([o.get_state() for o in refs]).astype(np.float32)
-        a = rng.uniform(-1, 1, size=(B, A)).astype(np.float32)
-        for i in range(B):
-            refs[i].set_state(st[i].astype(np.float64))
-            pert = st[i].astype(np.float64)
-            pert[:9] += 1e-7 * rng.randn(9)
-            twins[i].set_state(pert)
-            if kw.get("joint_control"):
-                a[i, :7] *= 0.3
-                a[i, 1] = 0.4 if t < 10 else a[i, 1]   # lean forward / down towards the table and the block
-            else:
-                tip = refs[i].link_state(0)[:3]
-                a[i, :3] = np.clip((st[i, 46:49] + np.array([0.0, 0.0, 0.0 if name == "block_rearrange" or t > 8 else 0.06]) - tip) / 0.01, -1, 1)
-                if A == 4:
-                    a[i, 3] = -1.0 if t < 14 else 1.0
-        env.set_state(st)
-        obs, r, done, info = env.step(torch.from_numpy(a).cuda())
-        got = np.concatenate([_np(obs[k]) for k in KEYS], axis=1)
-        for i in range(B):
-            ro = refs[i].step(a[i].astype(np.float64))[0]
-            rt = twins[i].step(a[i].astype(np.float64))[0]
-            want = np.concatenate([ro[k] for k in KEYS])
-            twin = np.concatenate([rt[k] for k in KEYS])
-            # positions only: tip, joint poses, achieved goal (velocities are compared in test_gpu_parity.py's
-            # criteria through achieved_goal of the next step)
-            jo = 7 if kw.get("joint_control") else 0
-            cols = np.r_[jo:jo + 3, want.size - 2 * env.goal_dim:want.size]  # tip xyz + achieved / desired goal
-            if jo:
-                cols = np.r_[0:7, cols]                                      # + the prepended joint poses
-            err = float(np.abs(got[i] - want)[cols].max())
-            sens = float(np.abs(twin - want)[cols].max())
-            if sens < 2e-6:
-                errs.append(err)
-                assert err < 100 * TOL, (name, t, i, err, sens)
-            else:
-                loose += 1
-    errs = np.array(errs)
-    print("%s teacher-forced: %d well-conditioned env-steps, %.1f%% within 1e-4, worst %.3g; %d ill-conditioned"
-          % (name, errs.size, 100 * float(np.mean(errs < TOL)), errs.max(), loose))
-    assert float(np.mean(errs < TOL)) >= 0.97 and errs.size > loose
+        twins.append([oracle.OracleEnv(seed=i, **kw) for _ in range(_teacher.N_TWINS)])
+    jc = bool(kw.get("joint_control"))
+
+    def fn(t, j, st, tip, a):
+        if jc:
+            a[:7] *= 0.3
+            if t < 10:
+                a[1] = 0.4   # lean forward / down towards the table and the block
+        else:
+            a[:3] = np.clip((st[46:49] + np.array([0.0, 0.0, 0.0 if name == "block_rearrange" or t > 8 else 0.06]) - tip) / 0.01, -1, 1)
+            if a.size == 4:
+                a[3] = -1.0 if t < 14 else 1.0
+        return a
+    vel = _teacher.velocity_mask(kw["task"], env.num_block, env.row_width, joint_control=jc)
+    stats = _teacher.run(env, oracle, refs, twins, 24, fn, vel, np.random.RandomState(11), name)
+    pos, _ = stats.report()
+    assert float(np.mean(pos < TOL)) >= 0.97 and pos.size > stats.loose
     assert env.overflow_count == 0
 
 
