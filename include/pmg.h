@@ -199,6 +199,13 @@ int pmg_state_width(const pmg_handle* h);
 int pmg_get_state(pmg_handle* h, float* state_host);
 int pmg_set_state(pmg_handle* h, const float* state_host);
 
+/* Measurement aid (bench.py's roofline): while on, every pmg_step / pmg_step_gather brackets its STEP KERNEL alone
+ * (not the auto-reset pass, not the caller's copies) with CUDA events on the launch stream; pmg_kernel_time_ms
+ * synchronises the device and returns the summed duration and the number of launches covered (a ring of the first
+ * 2048 since the last pmg_kernel_timing call). */
+int pmg_kernel_timing(pmg_handle* h, int32_t on);
+int pmg_kernel_time_ms(pmg_handle* h, double* total_ms, int64_t* count);
+
 /* number of kernels this library has launched on the handle since creation */
 int64_t pmg_launch_count(const pmg_handle* h);
 /* contact points dropped because a per-env scratch pool overflowed (0 in every shipped config) */

@@ -26,10 +26,35 @@ def build(force=False):
     return so
 
 
+_NATIVE_SO = None
+
+
+def use_native():
+    """CPU-baseline runs (bench.py): compile the same source on THIS machine with -O3 -march=native (still
+    -fno-fast-math -ffp-contract=off, so the arithmetic is unchanged) into oracle/_native/ and load that build
+    instead of the portable -O2 one.  Falls back to the portable build when no compiler is available.  Returns the
+    flags in use."""
+    global _NATIVE_SO
+    if _LIB is not None:
+        return "already loaded"
+    out_dir = os.path.join(_HERE, "_native")
+    so = os.path.join(out_dir, "libpmg_oracle_native.so")
+    flags = ["-O3", "-march=native", "-fPIC", "-std=gnu11", "-fno-fast-math", "-ffp-contract=off"]
+    try:
+        os.makedirs(out_dir, exist_ok=True)
+        subprocess.check_call(["gcc"] + flags + ["-shared", "-o", so, os.path.join(_HERE, "pmg_oracle.c"), "-lm", "-lpthread"],
+                              stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+        _NATIVE_SO = so
+        return " ".join(flags)
+    except Exception:
+        build()
+        return "-O2 (portable build; native compile failed)"
+
+
 def lib():
     global _LIB
     if _LIB is None:
-        so = os.path.join(_HERE, "libpmg_oracle.so")
+        so = _NATIVE_SO or os.path.join(_HERE, "libpmg_oracle.so")
         if not os.path.exists(so):
             build()
         L = C.CDLL(so)

@@ -17,7 +17,7 @@ SYMBOLS = [
     "pmg_abi_version", "pmg_last_error", "pmg_create", "pmg_destroy", "pmg_dims", "pmg_seed",
     "pmg_reset", "pmg_set_device_rng", "pmg_reset_device", "pmg_set_auto_reset", "pmg_spawn_width", "pmg_last_spawn", "pmg_set_curriculum_update", "pmg_get_curriculum", "pmg_set_sub_goal", "pmg_step", "pmg_gather_create", "pmg_gather_connect", "pmg_gather_layout", "pmg_step_gather", "pmg_step_host", "pmg_step_host_blocks",
     "pmg_compute_reward", "pmg_her_sample", "pmg_her_relabel", "pmg_state_width", "pmg_get_state", "pmg_set_state",
-    "pmg_launch_count", "pmg_overflow_count",
+    "pmg_kernel_timing", "pmg_kernel_time_ms", "pmg_launch_count", "pmg_overflow_count",
 ]
 
 
@@ -74,6 +74,8 @@ def load():
     L.pmg_state_width.argtypes = [vp]
     L.pmg_get_state.argtypes = [vp, fp]
     L.pmg_set_state.argtypes = [vp, fp]
+    L.pmg_kernel_timing.argtypes = [vp, C.c_int32]
+    L.pmg_kernel_time_ms.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_int64)]
     L.pmg_launch_count.argtypes = [vp]
     L.pmg_launch_count.restype = C.c_int64
     L.pmg_overflow_count.argtypes = [vp]

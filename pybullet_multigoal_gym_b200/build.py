@@ -43,6 +43,22 @@ def build(force=False, verbose=False):
     return SO
 
 
+def build_timing():
+    """Development build with per-phase cycle counters in the cooperative kernels (tools/coop_timing.py):
+    libpmg_timing.so, selected with PMG_LIBRARY; never loaded by default."""
+    nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+    out = os.path.join(HERE, "libpmg_timing.so")
+    cmd = [nvcc] + NVCC_FLAGS + ["-DPMG_COOP_TIMING", "-o", out] + [os.path.join(CSRC, s) for s in SOURCES]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode != 0:
+        sys.stderr.write(res.stdout + res.stderr)
+        raise RuntimeError("nvcc failed building libpmg_timing.so")
+    return out
+
+
 if __name__ == "__main__":
-    build(force=True, verbose="-v" in sys.argv)
-    print(SO)
+    if "--timing" in sys.argv:
+        print(build_timing())
+    else:
+        build(force=True, verbose="-v" in sys.argv)
+        print(SO)

@@ -699,7 +699,12 @@ struct pmg_handle {
   unsigned* d_g_counter = nullptr;
   int* g_err_host = nullptr; int* g_err_dev = nullptr;
   size_t g_parity_bytes = 0, g_off_reward = 0, g_off_done = 0, g_off_success = 0, g_flags_off = 0, g_total = 0;
+  // optional CUDA-event timing of the step kernel alone (pmg_kernel_timing): a ring of event pairs on the launch stream
+  bool timing = false;
+  std::vector<cudaEvent_t> t_ev;  // 2 * TIMING_RING events, created on first use
+  int64_t t_count = 0;
 };
+constexpr int TIMING_RING = 2048;
 
 namespace {
 
@@ -1030,6 +1035,7 @@ int pmg_destroy(pmg_handle* h) {
   }
   cudaFree(h->d_g_counter);
   if (h->g_err_host) cudaFreeHost(h->g_err_host);
+  for (auto& e : h->t_ev) cudaEventDestroy(e);
   cudaFree(h->d_action); cudaFree(h->d_obs); cudaFree(h->d_blocks); cudaFree(h->d_reward); cudaFree(h->d_done); cudaFree(h->d_success);
   if (h->h_spawn) cudaFreeHost(h->h_spawn);
   for (int k = 0; k < 2; k++) { if (h->h_stage[k]) cudaFreeHost(h->h_stage[k]); if (h->stage_done[k]) cudaEventDestroy(h->stage_done[k]); }
@@ -1165,7 +1171,9 @@ int pmg_step(pmg_handle* h, const float* action_dev, float* obs_dev, float* rewa
   cudaStream_t st = (cudaStream_t)stream;
   CUDA_TRY(cudaSetDevice(h->cfg.device));
   StepIO io = make_io(h, action_dev, obs_dev, reward_dev, done_dev, success_dev);
+  if (h->timing) cudaEventRecord(h->t_ev[2 * (h->t_count % TIMING_RING)], st);
   PMG_DISPATCH(launch_step, h, io, st);
+  if (h->timing) { cudaEventRecord(h->t_ev[2 * (h->t_count % TIMING_RING) + 1], st); h->t_count++; }
   h->launches++;
   if (h->auto_reset) {  // environments whose episode just ended reset themselves; their rows become the new episode's first observation
     enqueue_reset(h, done_dev, nullptr, obs_dev, 1, st);
@@ -1257,7 +1265,9 @@ int pmg_step_gather(pmg_handle* h, const float* action_dev, void** gathered_dev_
   io.g_flags_local = (const unsigned*)(h->g_buf[h->g_rank] + h->g_flags_off);
   io.g_counter = h->d_g_counter; io.g_err = h->g_err_dev;
   if (n == 0) io.g_in_step = 0;  // world 1: nothing to push, nothing to wait for
+  if (h->timing) cudaEventRecord(h->t_ev[2 * (h->t_count % TIMING_RING)], st);
   PMG_DISPATCH(launch_step, h, io, st);
+  if (h->timing) { cudaEventRecord(h->t_ev[2 * (h->t_count % TIMING_RING) + 1], st); h->t_count++; }
   h->launches++;
   if (h->auto_reset) {  // the reset pass rewrites the rows of the finished environments, then pushes and publishes
     enqueue_reset(h, dn, nullptr, obs, 1, st, &io);
@@ -1371,6 +1381,33 @@ int pmg_set_state(pmg_handle* h, const float* in) {
 }
 
 int64_t pmg_launch_count(const pmg_handle* h) { return h ? h->launches : 0; }
+
+int pmg_kernel_timing(pmg_handle* h, int32_t on) {
+  if (!h) return fail(PMG_ERR_INVALID, "pmg_kernel_timing: null handle%s");
+  CUDA_TRY(cudaSetDevice(h->cfg.device));
+  if (on && h->t_ev.empty()) {
+    h->t_ev.resize(2 * TIMING_RING);
+    for (auto& e : h->t_ev) CUDA_TRY(cudaEventCreate(&e));
+  }
+  h->timing = on != 0;
+  h->t_count = 0;
+  return PMG_OK;
+}
+
+int pmg_kernel_time_ms(pmg_handle* h, double* total_ms, int64_t* count) {
+  if (!h || !total_ms || !count) return fail(PMG_ERR_INVALID, "pmg_kernel_time_ms: null argument%s");
+  CUDA_TRY(cudaSetDevice(h->cfg.device));
+  CUDA_TRY(cudaDeviceSynchronize());
+  const int64_t n = h->t_count < TIMING_RING ? h->t_count : TIMING_RING;
+  double sum = 0.0;
+  for (int64_t k = 0; k < n; k++) {
+    float ms = 0.0f;
+    CUDA_TRY(cudaEventElapsedTime(&ms, h->t_ev[2 * k], h->t_ev[2 * k + 1]));
+    sum += ms;
+  }
+  *total_ms = sum; *count = n;
+  return PMG_OK;
+}
 
 #ifdef PMG_COOP_TIMING
 // development builds only (tools/coop_timing.py): read and clear the cycle counters of pmg_coop.cuh

@@ -52,18 +52,23 @@ struct __align__(16) EnvSmemT : RowSpill<NBLK> {
   static constexpr int NB = NBLK;
   static constexpr int NPAIRS = num_pairs(NBLK);                // 2 / 6
   static constexpr int MAXPTS = NBLK == 0 ? 8 : (NBLK == 1 ? 24 : 48);  // cached contact points that get rows
-  static constexpr int SPTS = NBLK == 0 ? 8 : 12;               // ... of which in shared memory
+  static constexpr int SPTS = NBLK == 0 ? 8 : (NBLK == 1 ? 12 : 8);  // ... of which in shared memory (NBLK > 1: of the points that are not static)
   static constexpr int ROW_W = NBLK == 0 ? 24 : (NBLK == 1 ? 32 : 40);  // floats per contact row record (16-byte aligned parts)
+  static constexpr int SROWS = NBLK > 1 ? NBLK * 4 * 3 : 0;     // NBLK > 1: compact rows of the static points (table / floor against a block), 4 points per block
+  static constexpr int SROW_W = 12;                             // d[3] rhs | r_B x d [3] dinv | denom mu . .
+  static constexpr int SROWS_AS_ROWS = (SROWS * SROW_W + ROW_W - 1) / ROW_W;  // ... stored behind the general rows
   static constexpr int NSCR = NPAIRS < GL ? NPAIRS : GL;        // narrowphase scratch areas (one per lane that runs pairs)
   float pub[7][8];                  // per arm dof: axis a, v = (p - Pref) x a
   float minv[ND * MINV_LD];         // 9x9, rows padded to 12
   float man[(NPAIRS * MAN_WORDS + 3) / 4 * 4];  // persistent manifolds (41 words per pair)
   float hand[24];                   // gripper frame for the contact rows: Rg[9] pf1 pf2 Pref ax1 (kept out of registers)
   float vq[NBLK == 0 ? 12 : (ND + 6 * NBLK + 3) / 4 * 4];  // joint (+ block) velocities for the row set-up, then the PGS delta velocities
-  float rows[SPTS * 3][ROW_W];      // contact rows (layout R_* above); narrowphase scratch before they are built
+  float rows[SPTS * 3 + SROWS_AS_ROWS][ROW_W];  // contact rows (layout R_* above), then the compact static rows; narrowphase scratch before they are built
   float app[2][MAXPTS * 3];         // accumulated impulses of the contact rows, double buffered over the PGS iterations
   float blk[NBLK > 0 ? 24 * NBLK : 1];  // per block: pos[3] quat[4] v[3] w[3] R[9] (+ 2 spare words)
-  static_assert(NSCR * sizeof(BoxScratch) <= SPTS * 3 * ROW_W * sizeof(float), "narrowphase scratch must fit in the contact-row area");
+  static constexpr int SCRATCH_FLOATS = (SPTS * 3 + SROWS_AS_ROWS) * ROW_W;
+  __device__ __forceinline__ float* srow(int r) { return &rows[0][0] + SPTS * 3 * ROW_W + r * SROW_W; }  // compact static row r
+  static_assert(NSCR * sizeof(BoxScratch) <= SCRATCH_FLOATS * sizeof(float), "narrowphase scratch must fit in the contact-row area");
   static constexpr int SPILL_WORDS = (MAXPTS - SPTS) * 3 * ROW_W;  // global scratch per environment
   __device__ __forceinline__ float* spill_row(int r) { return this->spill + (r - SPTS * 3) * ROW_W; }  // r >= 3 SPTS
 };
@@ -658,34 +663,31 @@ __device__ __noinline__ float contact_sweep(Grp g, SM& sm, int nrow_it) {  // nr
 // Row set-up: as contact_row_setup_blk, but either end may be a block (block-block pairs have two) and the blocks are
 // looked up by index.  Signs as in the thread-per-env kernels (pmg_sim.cuh row_velocity / row_apply): end A sees
 // +impulse, end B -impulse.
-template <bool SPILL, class SM>
+// Static points (table / floor against block b) get a compact record in sm.srows[b]: their rows touch that block only.
+// The other points -- "general": a finger or a second block at the other end -- keep the 40-float record, the first
+// SPTS of them in shared memory, the rest in the global spill.
+template <int NB>
+__device__ __forceinline__ bool static_pair(int k) { return k >= 2 && k < 2 + 4 * NB && ((k - 2) & 3) < 2; }
+
+template <class SM>
 __device__ __noinline__ void contact_row_setup_multi(SM& sm, int c) {
-  int k = 0, i = c;
+  int k = 0, i = c, gidx = c;  // pair, point inside the pair, index among the general points
 #pragma unroll 1
   for (; k < SM::NPAIRS; k++) {
     const int n = __float_as_int(sm.man[k * MAN_WORDS]);
     if (i < n) break;
     i -= n;
+    if (static_pair<SM::NB>(k)) gidx -= n;
   }
   const PairInfo pi = pair_info<SM::NB>(k);
   const bool robotA = pi.ka == G_FINGER1 || pi.ka == G_FINGER2, blockA = pi.ka == G_BLOCK, blockB = pi.kb == G_BLOCK;
-  const float* hd = sm.hand;
-  M3 Rg;
-  Rg.r0 = v3(hd[0], hd[1], hd[2]); Rg.r1 = v3(hd[3], hd[4], hd[5]); Rg.r2 = v3(hd[6], hd[7], hd[8]);
-  const V3 pf1 = v3(hd[9], hd[10], hd[11]), pf2 = v3(hd[12], hd[13], hd[14]), Pref = v3(hd[15], hd[16], hd[17]);
-  const V3 ax1 = v3(hd[18], hd[19], hd[20]), ax2 = -ax1;
   const float* mp = sm.man + k * MAN_WORDS + 1 + 10 * i;
   const V3 lA = v3(mp[0], mp[1], mp[2]), lB = v3(mp[3], mp[4], mp[5]), nB = v3(mp[6], mp[7], mp[8]);
   const float dist = mp[9];
-  const V3 wr = robotA ? mul(Rg, lA) + (pi.ka == G_FINGER1 ? pf1 : pf2) - Pref : v3(0, 0, 0);
-  V3 rA = v3(0, 0, 0), rB = v3(0, 0, 0), av = v3(0, 0, 0), aw = v3(0, 0, 0), bv = v3(0, 0, 0), bw = v3(0, 0, 0);
-  if (blockA) {
-    const float* bk = sm.blk + 24 * pi.ia;
-    M3 R;
-    R.r0 = v3(bk[BK_R], bk[BK_R + 1], bk[BK_R + 2]); R.r1 = v3(bk[BK_R + 3], bk[BK_R + 4], bk[BK_R + 5]); R.r2 = v3(bk[BK_R + 6], bk[BK_R + 7], bk[BK_R + 8]);
-    rA = mul(R, lA);
-    av = v3(bk[BK_V], bk[BK_V + 1], bk[BK_V + 2]); aw = v3(bk[BK_W], bk[BK_W + 1], bk[BK_W + 2]);
-  }
+  V3 t1, t2;
+  plane_space(nB, t1, t2);
+  const float mu = geom_friction(pi.ka) * geom_friction(pi.kb);
+  V3 rB = v3(0, 0, 0), bv = v3(0, 0, 0), bw = v3(0, 0, 0);
   if (blockB) {
     const float* bk = sm.blk + 24 * pi.ib;
     M3 R;
@@ -693,13 +695,50 @@ __device__ __noinline__ void contact_row_setup_multi(SM& sm, int c) {
     rB = mul(R, lB);
     bv = v3(bk[BK_V], bk[BK_V + 1], bk[BK_V + 2]); bw = v3(bk[BK_W], bk[BK_W + 1], bk[BK_W + 2]);
   }
-  V3 t1, t2;
-  plane_space(nB, t1, t2);
-  const float mu = geom_friction(pi.ka) * geom_friction(pi.kb);
+  if (static_pair<SM::NB>(k)) {
+    // the 4-point manifolds of the table and the floor pair of one block: points beyond the 4 slots are dropped (a 3 cm
+    // cube cannot rest on both) and counted like the pool overflow
+    const int slot = i + ((k - 2) & 3 ? __float_as_int(sm.man[(k - 1) * MAN_WORDS]) : 0);
+    if (slot >= 4) return;
+#pragma unroll 1
+    for (int kk = 0; kk < 3; kk++) {
+      const V3 d = kk == 0 ? nB : (kk == 1 ? t1 : t2);
+      float* row = sm.srow((pi.ib * 4 + slot) * 3 + kk);
+      const V3 xb = cross(rB, d);
+      const float denom = BLOCK_INV_MASS + BLOCK_INV_INERTIA * dot(xb, xb);
+      const float rel_vel = -(dot(d, bv) + dot(xb, bw));
+      const float dinv = 1.0f / denom;
+      float rhs;
+      if (kk == 0) {
+        const float pen = dist + LINEAR_SLOP;
+        float pos_err = 0.0f, vel_err = -rel_vel;
+        if (pen > 0.0f) vel_err -= pen * INV_DT; else pos_err = -pen * CONTACT_ERP * INV_DT;
+        rhs = (pos_err + vel_err) * dinv;
+      } else rhs = -rel_vel * dinv;
+      row[0] = d.x; row[1] = d.y; row[2] = d.z; row[3] = rhs; row[4] = xb.x; row[5] = xb.y; row[6] = xb.z; row[7] = dinv;
+      row[8] = denom; row[9] = mu;
+      sm.app[0][c * 3 + kk] = 0.0f;
+    }
+    return;
+  }
+  const float* hd = sm.hand;
+  M3 Rg;
+  Rg.r0 = v3(hd[0], hd[1], hd[2]); Rg.r1 = v3(hd[3], hd[4], hd[5]); Rg.r2 = v3(hd[6], hd[7], hd[8]);
+  const V3 pf1 = v3(hd[9], hd[10], hd[11]), pf2 = v3(hd[12], hd[13], hd[14]), Pref = v3(hd[15], hd[16], hd[17]);
+  const V3 ax1 = v3(hd[18], hd[19], hd[20]), ax2 = -ax1;
+  const V3 wr = robotA ? mul(Rg, lA) + (pi.ka == G_FINGER1 ? pf1 : pf2) - Pref : v3(0, 0, 0);
+  V3 rA = v3(0, 0, 0), av = v3(0, 0, 0), aw = v3(0, 0, 0);
+  if (blockA) {
+    const float* bk = sm.blk + 24 * pi.ia;
+    M3 R;
+    R.r0 = v3(bk[BK_R], bk[BK_R + 1], bk[BK_R + 2]); R.r1 = v3(bk[BK_R + 3], bk[BK_R + 4], bk[BK_R + 5]); R.r2 = v3(bk[BK_R + 6], bk[BK_R + 7], bk[BK_R + 8]);
+    rA = mul(R, lA);
+    av = v3(bk[BK_V], bk[BK_V + 1], bk[BK_V + 2]); aw = v3(bk[BK_W], bk[BK_W + 1], bk[BK_W + 2]);
+  }
 #pragma unroll 1
   for (int kk = 0; kk < 3; kk++) {
     const V3 d = kk == 0 ? nB : (kk == 1 ? t1 : t2);
-    float* row = SPILL ? sm.spill_row(c * 3 + kk) : sm.rows[SPILL ? 0 : c * 3 + kk];
+    float* row = gidx < SM::SPTS ? sm.rows[gidx * 3 + kk] : sm.spill_row(gidx * 3 + kk);
     const V3 xa = cross(rA, d), xb = cross(rB, d);
     float denom = 0.0f, rel_vel = 0.0f;
     if (blockA) { denom += BLOCK_INV_MASS + BLOCK_INV_INERTIA * dot(xa, xa); rel_vel += dot(d, av) + dot(xa, aw); }
@@ -725,11 +764,7 @@ __device__ __noinline__ void contact_row_setup_multi(SM& sm, int c) {
         row[R_MJ + r] = acc;
         denom += row[R_J + r] * acc;
       }
-    } else {
-      const float4 z = {0.0f, 0.0f, 0.0f, 0.0f};
-#pragma unroll
-      for (int j = 0; j < 6; j++) reinterpret_cast<float4*>(row)[j] = z;
-    }
+    }  // rows without a robot end leave J / M^-1 J^T unwritten: the sweeps only read them when R_BD + 3 says so
     const float dinv = 1.0f / denom;
     float rhs;
     if (kk == 0) {
@@ -749,10 +784,21 @@ __device__ __noinline__ void contact_row_setup_multi(SM& sm, int c) {
 
 // One Gauss-Seidel pass for multi-block environments.  The joint delta velocities are replicated as in contact_sweep;
 // the blocks' are not (a register array cannot be indexed by a run-time block number): LANE b KEEPS BLOCK b's six
-// deltas, a row fetches its one or two blocks with run-time-source shuffles inside the octet (the whole octet is on
-// this path, so the shuffles are legal although the warp has diverged) and the owner lanes apply the impulse.
+// deltas.
+//   * STATIC rows (table / floor against block b) involve block b only, so LANE b SOLVES THEM ON ITS OWN, the blocks in
+//     parallel: a stack scene at rest is 16 such points = 48 rows per iteration, formerly swept one after the other by
+//     the whole octet (76 % of the substep, 430 cycles per row with two run-time-source shuffle groups each).
+//     Gauss-Seidel visits rows in Bullet's order -- all normal rows in pair order, then all friction rows -- and two
+//     rows commute when they share no velocity; block b's static pairs precede every other pair that touches block b
+//     (its finger pairs, the block-block pairs), and they share nothing with the static rows of other blocks or with
+//     the finger-table rows, so "static rows of all blocks side by side, then the remaining rows in order" produces the
+//     same iterates.
+//   * the remaining rows (a finger or a second block at the other end) are visited by the whole octet in pair order: a
+//     row fetches its one or two blocks with run-time-source shuffles (legal on the diverged path: the whole octet
+//     takes it) and the owner lanes apply the impulse.
 template <class SM>
 __device__ __noinline__ float contact_sweep_multi(Grp g, SM& sm, int nrow_it) {  // nrow | iteration parity << 8
+  constexpr int NB = SM::NB;
   const int nrow = nrow_it & 0xff, it = nrow_it >> 8;
   const int lane = g.lane;
   const float* app_rd = sm.app[it & 1];
@@ -761,10 +807,37 @@ __device__ __noinline__ float contact_sweep_multi(Grp g, SM& sm, int nrow_it) { 
 #pragma unroll
   for (int j = 0; j < ND; j++) dq[j] = sm.vq[j];
 #pragma unroll
-  for (int j = 0; j < 6; j++) bd[j] = lane < SM::NB ? sm.vq[ND + 6 * lane + j] : 0.0f;
+  for (int j = 0; j < 6; j++) bd[j] = lane < NB ? sm.vq[ND + 6 * lane + j] : 0.0f;
   float cres = 0.0f;
   auto ld4 = [](const float* p) { return *reinterpret_cast<const float4*>(p); };
-  // velocity of the row's block ends: + end A, - end B
+  // this lane's static points: a contiguous run of the pair-ordered point list (table-block, then floor-block)
+  int s0 = 0, s1 = 0;
+  if (lane < NB) {
+#pragma unroll 1
+    for (int k = 0; k < 2 + 4 * lane; k++) s0 += __float_as_int(sm.man[k * MAN_WORDS]);
+    s1 = s0 + __float_as_int(sm.man[(2 + 4 * lane) * MAN_WORDS]) + __float_as_int(sm.man[(3 + 4 * lane) * MAN_WORDS]);
+    if (s1 > s0 + 4) s1 = s0 + 4;                             // 4 static slots per block (see contact_row_setup_multi)
+    s0 = s0 < nrow ? s0 : nrow; s1 = s1 < nrow ? s1 : nrow;  // points beyond the pool were dropped
+  }
+  const float* srow = sm.srow((lane < NB ? lane : 0) * 12);  // this lane's compact static rows: [slot * 3 + kk][12]
+  // ---- normal rows ----
+#pragma unroll 1
+  for (int c = s0; c < s1; c++) {  // static: the block is end B (it sees -impulse)
+    const float* row = srow + (c - s0) * 3 * SM::SROW_W;
+    const float4 d = ld4(row), xb = ld4(row + 4);  // d.w = rhs, xb.w = 1 / denominator
+    const float denom = row[8];
+    const float v = -((d.x * bd[0] + d.y * bd[1] + d.z * bd[2]) + (xb.x * bd[3] + xb.y * bd[4] + xb.z * bd[5]));
+    const float app = app_rd[c * 3];
+    float dl = d.w - v * xb.w;
+    const float sum = fminf(fmaxf(app + dl, 0.0f), 1e10f);
+    dl = sum - app;
+    const float lm = dl * BLOCK_INV_MASS, li = dl * BLOCK_INV_INERTIA;
+    bd[0] -= lm * d.x; bd[1] -= lm * d.y; bd[2] -= lm * d.z; bd[3] -= li * xb.x; bd[4] -= li * xb.y; bd[5] -= li * xb.z;
+    const float rr = dl * denom;
+    cres = fmaxf(cres, rr * rr);
+    app_wr[c * 3] = sum;
+  }
+  // velocity of a general row's block ends: + end A, - end B
   auto block_vel = [&](const float4& d, const float4& xa, const float4& xb, int ia, int ib) {
     float v = 0.0f;
     if (ia >= 0) {
@@ -835,22 +908,75 @@ __device__ __noinline__ float contact_sweep_multi(Grp g, SM& sm, int nrow_it) { 
     }
     app_wr[c * 3 + 1] = sA; app_wr[c * 3 + 2] = sB;
   };
-  const int nsh = nrow < SM::SPTS ? nrow : SM::SPTS;
+  // the other rows, in pair order, by the whole octet (the pair counts are uniform over the octet)
+  {
+    int c = 0, gi = 0;  // point index in pair order (impulse arrays), index among the general points (row records)
 #pragma unroll 1
-  for (int c = 0; c < nsh; c++) normal_row(sm.rows[c * 3], c);
+    for (int k = 0; k < SM::NPAIRS && c < nrow; k++) {
+      const int n = __float_as_int(sm.man[k * MAN_WORDS]);
+      if (static_pair<NB>(k)) { c += n; continue; }
+      const int e = c + n < nrow ? c + n : nrow;
 #pragma unroll 1
-  for (int c = SM::SPTS; c < nrow; c++) normal_row(sm.spill_row(c * 3), c);
-  g.sync();
+      for (; c < e; c++, gi++) {
+        if (gi < SM::SPTS) normal_row(sm.rows[gi * 3], c);
+        else normal_row(sm.spill_row(gi * 3), c);
+      }
+    }
+  }
+  g.sync();  // app_wr of the normal rows is read (by other lanes too) below
+  // ---- friction rows: the two tangent rows of a point projected together onto the cone ----
 #pragma unroll 1
-  for (int c = 0; c < nsh; c++) friction_rows(sm.rows[c * 3 + 1], sm.rows[c * 3 + 2], c);
+  for (int c = s0; c < s1; c++) {
+    const float total = app_wr[c * 3];
+    const float appA = app_rd[c * 3 + 1], appB = app_rd[c * 3 + 2];
+    float sA = appA, sB = appB;
+    if (total > 0.0f) {
+      const float* ra = srow + ((c - s0) * 3 + 1) * SM::SROW_W;
+      const float* rb = ra + SM::SROW_W;
+      const float4 da = ld4(ra), xba = ld4(ra + 4), db = ld4(rb), xbb = ld4(rb + 4);
+      const float2 ma = *reinterpret_cast<const float2*>(ra + 8);  // denominator, friction coefficient
+      const float denB = rb[8];
+      const float vA = -((da.x * bd[0] + da.y * bd[1] + da.z * bd[2]) + (xba.x * bd[3] + xba.y * bd[4] + xba.z * bd[5]));
+      const float vB = -((db.x * bd[0] + db.y * bd[1] + db.z * bd[2]) + (xbb.x * bd[3] + xbb.y * bd[4] + xbb.z * bd[5]));
+      const float lim = ma.y * total;
+      float dA = da.w - vA * xba.w, dB = db.w - vB * xbb.w;
+      sA = appA + dA; sB = appB + dB;
+      const float s2 = sA * sA + sB * sB;
+      if (s2 >= lim * lim) {
+        const float sc = s2 > 0.0f ? lim * rsqrtf(s2) : 0.0f;
+        const float cA = fabsf(sA) * sc, cB = s2 > 0.0f ? fabsf(sB) * sc : lim;
+        sA = fminf(fmaxf(sA, -cA), cA);
+        sB = fminf(fmaxf(sB, -cB), cB);
+        dA = sA - appA; dB = sB - appB;
+      }
+      const float lmA = dA * BLOCK_INV_MASS, liA = dA * BLOCK_INV_INERTIA, lmB = dB * BLOCK_INV_MASS, liB = dB * BLOCK_INV_INERTIA;
+      bd[0] -= lmA * da.x; bd[1] -= lmA * da.y; bd[2] -= lmA * da.z; bd[3] -= liA * xba.x; bd[4] -= liA * xba.y; bd[5] -= liA * xba.z;
+      bd[0] -= lmB * db.x; bd[1] -= lmB * db.y; bd[2] -= lmB * db.z; bd[3] -= liB * xbb.x; bd[4] -= liB * xbb.y; bd[5] -= liB * xbb.z;
+      const float r1_ = dA * ma.x, r2_ = dB * denB;
+      cres = fmaxf(cres, fmaxf(r1_ * r1_, r2_ * r2_));
+    }
+    app_wr[c * 3 + 1] = sA; app_wr[c * 3 + 2] = sB;
+  }
+  {
+    int c = 0, gi = 0;
 #pragma unroll 1
-  for (int c = SM::SPTS; c < nrow; c++) friction_rows(sm.spill_row(c * 3 + 1), sm.spill_row(c * 3 + 2), c);
+    for (int k = 0; k < SM::NPAIRS && c < nrow; k++) {
+      const int n = __float_as_int(sm.man[k * MAN_WORDS]);
+      if (static_pair<NB>(k)) { c += n; continue; }
+      const int e = c + n < nrow ? c + n : nrow;
+#pragma unroll 1
+      for (; c < e; c++, gi++) {
+        if (gi < SM::SPTS) friction_rows(sm.rows[gi * 3 + 1], sm.rows[gi * 3 + 2], c);
+        else friction_rows(sm.spill_row(gi * 3 + 1), sm.spill_row(gi * 3 + 2), c);
+      }
+    }
+  }
   g.sync();  // every lane has read sm.vq
   if (lane == 0) {
 #pragma unroll
     for (int j = 0; j < ND; j++) sm.vq[j] = dq[j];
   }
-  if (lane < SM::NB) {
+  if (lane < NB) {
 #pragma unroll
     for (int j = 0; j < 6; j++) sm.vq[ND + 6 * lane + j] = bd[j];
   }
@@ -968,11 +1094,26 @@ __device__ void substep(const Grp& g, SM& sm, Lane& L) {
   if constexpr (MULTI) {
     // lane k runs pairs k, k + 8, ...: the same geometry look-up as the thread-per-env kernels, blocks from shared memory
     ManRef mr; mr.man = sm.man; mr.stride = 1;
-    constexpr int SCR_STRIDE = SM::SPTS * 3 * SM::ROW_W / SM::NSCR / 4 * 4;
+    constexpr int SCR_STRIDE = SM::SCRATCH_FLOATS / SM::NSCR / 4 * 4;
+    static_assert(SCR_STRIDE * sizeof(float) >= sizeof(BoxScratch), "one narrowphase scratch area per lane");
     BoxScratch& scr = *reinterpret_cast<BoxScratch*>(&sm.rows[0][0] + lane * SCR_STRIDE);
     const float tc[3] = PMG_TABLE_CENTER, fc[3] = PMG_FLOOR_CENTER;
+    // Position p of the schedule -> pair: the table-block pairs (always touching in a scene at rest: a full SAT +
+    // clipping each) come first, one per lane, then finger-table, finger-block, block-block, floor-block.
+    auto scheduled_pair = [](int p) {
+      constexpr int NB = SM::NB, NBB = NB * (NB - 1) / 2;
+      if (p < NB) return 2 + 4 * p;
+      p -= NB;
+      if (p < 2) return p;
+      p -= 2;
+      if (p < 2 * NB) return 2 + 4 * (p >> 1) + 2 + (p & 1);
+      p -= 2 * NB;
+      if (p < NBB) return 2 + 4 * NB + p;
+      return 2 + 4 * (p - NBB) + 1;
+    };
 #pragma unroll 1
-    for (int k = lane; k < SM::NPAIRS; k += GL) {
+    for (int pos = lane; pos < SM::NPAIRS; pos += GL) {
+      const int k = scheduled_pair(pos);
       const PairInfo pi = pair_info<SM::NB>(k);
       V3 pa, pb;
       M3 Ra = m3_identity(), Rb = m3_identity();
@@ -1155,6 +1296,15 @@ __device__ void substep(const Grp& g, SM& sm, Lane& L) {
       if (lane == 0) sm.blk[23] += (float)(nrow - SM::MAXPTS);
       nrow = SM::MAXPTS;
     }
+    if constexpr (MULTI) {  // ... and so are static points beyond a block's 4 compact slots (table and floor at once)
+      if (lane == 0) {
+#pragma unroll 1
+        for (int b = 0; b < SM::NB; b++) {
+          const int n = __float_as_int(sm.man[(2 + 4 * b) * MAN_WORDS]) + __float_as_int(sm.man[(3 + 4 * b) * MAN_WORDS]);
+          if (n > 4) sm.blk[23] += (float)(n - 4);
+        }
+      }
+    }
   }
   PMG_T(t_set0);
   if (nrow) {
@@ -1163,8 +1313,7 @@ __device__ void substep(const Grp& g, SM& sm, Lane& L) {
     } else {
       for (int c = lane; c < nrow; c += GL) {
         if constexpr (MULTI) {
-          if (c < SM::SPTS) contact_row_setup_multi<false>(sm, c);
-          else contact_row_setup_multi<true>(sm, c);
+          contact_row_setup_multi(sm, c);
         } else {
           if (c < SM::SPTS) contact_row_setup_blk<false>(sm, c);
           else contact_row_setup_blk<true>(sm, c);

@@ -29,6 +29,7 @@ static inline float __int_as_float(int i) { float f; memcpy(&f, &i, 4); return f
 static inline int __ffs(unsigned v) { return v ? __builtin_ctz(v) + 1 : 0; }
 static inline int __clz(unsigned v) { return v ? __builtin_clz(v) : 32; }
 static inline int atomicAdd(int* p, int v) { int o = *p; *p += v; return o; }
+static inline void __threadfence_system() {}
 static inline int min(int a, int b) { return a < b ? a : b; }
 static inline int max(int a, int b) { return a > b ? a : b; }
 

@@ -450,6 +450,16 @@ class KukaBulletMGEnv:
         _lib.check(self._L.pmg_last_spawn(self._h, out.ctypes.data_as(C.c_void_p)))
         return out
 
+    def kernel_timing(self, on=True):
+        """Bracket every step kernel with CUDA events inside the library (bench.py's roofline measurement)."""
+        _lib.check(self._L.pmg_kernel_timing(self._h, int(bool(on))))
+
+    def kernel_time_ms(self):
+        """-> (summed step-kernel milliseconds, launches covered) since kernel_timing(True); synchronises."""
+        ms, n = C.c_double(), C.c_int64()
+        _lib.check(self._L.pmg_kernel_time_ms(self._h, C.byref(ms), C.byref(n)))
+        return ms.value, n.value
+
     @property
     def launch_count(self):
         return int(self._L.pmg_launch_count(self._h))

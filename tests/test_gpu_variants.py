@@ -118,7 +118,7 @@ def test_variant_teacher_forced_steps_match_oracle(oracle, name):
     vel = _teacher.velocity_mask(kw["task"], env.num_block, env.row_width, joint_control=jc)
     stats = _teacher.run(env, oracle, refs, twins, 24, fn, vel, np.random.RandomState(11), name)
     pos, _ = stats.report()
-    assert float(np.mean(pos < TOL)) >= 0.97 and pos.size > stats.loose
+    assert float(np.mean(pos < TOL)) >= 0.97 and pos.size >= 40
     assert env.overflow_count == 0
 
 

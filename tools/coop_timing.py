@@ -16,7 +16,7 @@ down = "down" in args
 args = [a for a in args if a != "down"]
 task, _, bs = (args[0] if args else "reach:8192").partition(":")
 B = int(bs or 8192)
-env = pmg.make_env(task=task, batch=B, check_actions=False)
+env = pmg.make_env(task=task, batch=B, num_block=4, check_actions=False)
 L = _lib.load()
 torch.manual_seed(0)
 acts = torch.rand((50, B, env.action_dim), device="cuda") * 2 - 1
