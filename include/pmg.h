@@ -33,7 +33,8 @@ typedef enum {
 
 /* task ids: envs/task_envs/kuka_single_step_envs.py:4-46, kuka_multi_step_envs.py:6-32 (stack),
  * :151-189 (rearrange: the block-stack scene without grasping, one table target per block) */
-typedef enum { PMG_REACH = 0, PMG_PUSH = 1, PMG_PICK_AND_PLACE = 2, PMG_BLOCK_STACK = 3, PMG_BLOCK_REARRANGE = 4 } pmg_task;
+typedef enum { PMG_REACH = 0, PMG_PUSH = 1, PMG_PICK_AND_PLACE = 2, PMG_BLOCK_STACK = 3, PMG_BLOCK_REARRANGE = 4,
+               PMG_SLIDE = 5 /* kuka_single_step_envs.py:49-59: Push on the long low-friction table with a puck, goals beyond reach */ } pmg_task;
 
 /* make_env(...) kwargs that reach the step path (__init__.py:4-11,88-131) + batch/device */
 typedef struct {

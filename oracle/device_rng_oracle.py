@@ -53,18 +53,22 @@ def _d2(ax, ay, bx, by):
 
 def bounds(task):
     """kuka.py:35-51 with obj_range = target_range = 0.15 (as pmg_create computes them, in double, then float32)."""
-    tz = 0.175 + 0.001 if task in ("push", "block_rearrange") else 0.25
+    tz = 0.175 + 0.001 if task in ("push", "block_rearrange", "slide") else 0.25
     tip = [-0.52, 0.0, tz]
-    obj_lo = [tip[k] - 0.15 for k in range(3)]
-    obj_hi = [tip[k] + 0.15 for k in range(3)]
-    tgt_lo, tgt_hi = list(obj_lo), list(obj_hi)
+    obj_range, target_range = (0.1, 0.2) if task == "slide" else (0.15, 0.15)   # kuka_single_step_envs.py:49-59
+    obj_lo = [tip[k] - obj_range for k in range(3)]
+    obj_hi = [tip[k] + obj_range for k in range(3)]
+    tgt_lo = [tip[k] - target_range for k in range(3)]
+    tgt_hi = [tip[k] + target_range for k in range(3)]
     obj_lo[0] += 0.03; obj_hi[0] -= 0.03
     tgt_lo[0] += 0.03; tgt_lo[2] = 0.175; tgt_hi[0] -= 0.03
+    if task == "slide":
+        tgt_lo[0] -= 0.4; tgt_hi[0] -= 0.4                                       # kuka_single_step_base_env.py:66-69
     c = lambda v: [f32(x) for x in v]
     return dict(tip=c(tip), obj_lo=c(obj_lo[:2]), obj_hi=c(obj_hi[:2]), tgt_lo=c(tgt_lo), tgt_hi=c(tgt_hi))
 
 
-TASK_IDS = {"reach": 0, "push": 1, "pick_and_place": 2, "block_stack": 3, "block_rearrange": 4}
+TASK_IDS = {"reach": 0, "push": 1, "pick_and_place": 2, "block_stack": 3, "block_rearrange": 4, "slide": 5}
 
 
 def sample_row(task, num_block, grip, seed, env, episode):
@@ -72,11 +76,12 @@ def sample_row(task, num_block, grip, seed, env, episode):
     b = bounds(task)
     r = Stream(seed, env, episode)
     t = TASK_IDS[task]
-    nb = 0 if t == 0 else (1 if t < 3 else num_block)
-    G = 3 * nb + (4 if grip else 0) if t >= 3 else 3
+    multi = t in (3, 4)
+    nb = 0 if t == 0 else (num_block if multi else 1)
+    G = 3 * nb + (4 if grip else 0) if multi else 3
     out = np.zeros(2 * nb + G, dtype=np.float32)
-    R01, R006, R008, Z0 = f32(0.01), f32(0.0036), f32(0.0064), f32(0.175)
-    if t >= 3:
+    R01, R006, R008, Z0 = f32(0.01), f32(0.0036), f32(0.0064), (f32(0.17) if t == 5 else f32(0.175))
+    if multi:
         for k in range(nb):
             for _ in range(MAX_TRIES):
                 x, y = r.uniform(b["obj_lo"][0], b["obj_hi"][0]), r.uniform(b["obj_lo"][1], b["obj_hi"][1])
@@ -126,7 +131,7 @@ def sample_row(task, num_block, grip, seed, env, episode):
         dz = f32(g[2]) - f32(cz)
         if _d2(g[0], g[1], cx, cy) + dz * dz > R01:
             break
-    if t == 1:
+    if t in (1, 5):
         g[2] = Z0
     elif t == 2:
         if r.uniform(0.0, 1.0) >= f32(0.5):

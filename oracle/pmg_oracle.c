@@ -79,6 +79,10 @@ static const double TABLE_HALF[3] = PMG_TABLE_HALF;
 static const double FLOOR_CENTER[3] = PMG_FLOOR_CENTER;
 static const double FLOOR_HALF[3] = PMG_FLOOR_HALF;
 static const int NONCONTACT_ORDER[2 * ND] = PMG_NONCONTACT_ORDER;
+/* Slide (kuka_single_step_envs.py:49-59, kuka_single_step_base_env.py:53-56,66-69,89-93) */
+static const double LONG_TABLE_CENTER[3] = PMG_LONG_TABLE_CENTER;
+static const double LONG_TABLE_HALF[3] = PMG_LONG_TABLE_HALF;
+static const double PUCK_INERTIA[3] = PMG_PUCK_INERTIA;
 
 /* kuka.py:27 */
 static const double KUKA_REST_POSE[7] = {0, -0.5592432, 0, 1.733180, 0, -0.8501557, 0};
@@ -242,7 +246,7 @@ typedef struct {
 } Manifold;
 
 /* collision endpoints: kind 0 static box, 1 robot body, 2 block */
-typedef struct { int kind, index; double half[3]; double friction; double radius; } Geom;
+typedef struct { int kind, index; double half[3]; double friction; double radius; int cylinder; } Geom; /* cylinder: axis z, half = (r, r, h) */
 typedef struct { Geom a, b; } Pair;
 
 typedef struct {
@@ -277,6 +281,9 @@ struct PmgoEnv {
   MT rng;
   /* contacts */
   int npair; Pair pairs[MAX_PAIRS]; Manifold man[MAX_PAIRS];
+  /* free-body parameters (cubes: isotropic; the Slide puck: a cylinder about its z axis) and the scene's table */
+  double blk_mass, blk_inertia[3], blk_spawn_z; int puck;
+  double table_center[3];
   /* per-substep kinematics / ABA cache */
   double bR[NB][9], bp[NB][3], S[NB][6], U[NB][6], Dinv[NB], vel[NB][6];
   double blkR[MAXBLK][9];
@@ -754,23 +761,153 @@ static int box_box(const double* p1, const double* R1, const double* A, const do
 /* ------------------------------------------------------------------------------------------ */
 /* collision pairs and persistent manifolds                                                   */
 /* ------------------------------------------------------------------------------------------ */
+/* ------------------------------------------------------------------------------------------ */
+/* box (A) against a cylinder (B, axis = its local z): the Slide puck                         */
+/* ------------------------------------------------------------------------------------------ */
+/* Bullet runs GJK/EPA + a persistent manifold for this pair; the single closest-point pair it returns per call on
+ * a flat-on-flat contact depends on the simplex history and cannot be restated without Bullet itself.  This is a
+ * MODEL of the pair (Slide): a separating-axis choice between the cylinder axis (cap against a box face)
+ * and the radial direction (curved side against the box), then
+ *   cap - face : the rim points of that cap at four azimuths fixed in the cylinder (+-x, +-y) plus the deepest rim
+ *                point, kept when they lie over the face and penetrate it, and the corners of the face that lie
+ *                inside the cap disc (a finger pressing on the puck); normal = the face normal; <= 4 points
+ *                (the deepest first, then the ones that spread the patch);
+ *   side       : the closest points of the box to the cylinder axis at the two ends of their common height range.
+ * Output convention of box_box: point on B, normal on B (pointing from B towards A), signed distance (<= 0). */
+static int box_cyl(const double* pa, const double* Ra, const double* ha, const double* pb, const double* Rb,
+                   double r, double h, ContactOut* out) {
+  double ax[3] = {Rb[2], Rb[5], Rb[8]};                     /* cylinder axis in world */
+  double d[3], cb[3];                                       /* box centre in the cylinder frame */
+  sub3(d, pa, pb); matTvec3(Rb, d, cb);
+  double Aq[3][3];                                          /* box axes in the cylinder frame: Aq[k] = Rb^T Ra[:,k] */
+  for (int k = 0; k < 3; k++) { double col[3] = {Ra[k], Ra[3 + k], Ra[6 + k]}; matTvec3(Rb, col, Aq[k]); }
+  double ez = ha[0] * fabs(Aq[0][2]) + ha[1] * fabs(Aq[1][2]) + ha[2] * fabs(Aq[2][2]);   /* box extent along the axis */
+  /* axial separation for the two caps: cap s faces the box when the box lies on its side */
+  int scap = cb[2] >= 0 ? 1 : -1;
+  double sep_cap = scap * cb[2] - ez - h;
+  if (sep_cap > 0) return 0;
+  /* radial: closest point of the box to the axis at the two ends of the common height range */
+  double z0 = cb[2] - ez > -h ? cb[2] - ez : -h, z1 = cb[2] + ez < h ? cb[2] + ez : h;
+  double zs[2] = {z0 + 0.05 * (z1 - z0), z1 - 0.05 * (z1 - z0)};
+  double qs[2][3], rho[2];
+  double sep_rad = 1e30;
+  for (int i = 0; i < 2; i++) {
+    double rel[3] = {-cb[0], -cb[1], zs[i] - cb[2]}, loc[3], q[3] = {cb[0], cb[1], cb[2]};
+    for (int k = 0; k < 3; k++) {                           /* clamp in the box frame */
+      loc[k] = rel[0] * Aq[k][0] + rel[1] * Aq[k][1] + rel[2] * Aq[k][2];
+      if (loc[k] > ha[k]) loc[k] = ha[k];
+      if (loc[k] < -ha[k]) loc[k] = -ha[k];
+      q[0] += loc[k] * Aq[k][0]; q[1] += loc[k] * Aq[k][1]; q[2] += loc[k] * Aq[k][2];
+    }
+    copy3(qs[i], q);
+    rho[i] = sqrt(q[0] * q[0] + q[1] * q[1]);
+    if (rho[i] - r < sep_rad) sep_rad = rho[i] - r;
+  }
+  if (sep_rad > 0) return 0;
+  int n = 0;
+  if (sep_cap >= sep_rad) {
+    /* ---- cap against the box face whose outward normal opposes the cap normal most ---- */
+    int fj = 0; double best = -1;
+    for (int k = 0; k < 3; k++) if (fabs(Aq[k][2]) > best) { best = fabs(Aq[k][2]); fj = k; }
+    double sig = Aq[fj][2] * scap > 0 ? -1.0 : 1.0;         /* the face looks against the cap normal */
+    double nf[3] = {sig * Aq[fj][0], sig * Aq[fj][1], sig * Aq[fj][2]};   /* outward face normal, cylinder frame */
+    int k1 = (fj + 1) % 3, k2 = (fj + 2) % 3;
+    double cand[9][7]; int nc = 0;                          /* point on B (cyl frame), distance, point on A */
+    /* rim points of the cap */
+    double u[5][2] = {{1, 0}, {-1, 0}, {0, 1}, {0, -1}, {0, 0}};
+    double tx = -nf[0], ty = -nf[1], tn = sqrt(tx * tx + ty * ty);
+    int nu = 4;
+    if (tn > 0.02) { u[4][0] = tx / tn; u[4][1] = ty / tn; nu = 5; }   /* tilted by more than ~1 degree: the lowest rim point matters */
+    for (int i = 0; i < nu; i++) {
+      double p[3] = {r * u[i][0], r * u[i][1], scap * h}, rel[3], loc[3];
+      sub3(rel, p, cb);
+      for (int k = 0; k < 3; k++) loc[k] = rel[0] * Aq[k][0] + rel[1] * Aq[k][1] + rel[2] * Aq[k][2];
+      if (fabs(loc[k1]) > ha[k1] || fabs(loc[k2]) > ha[k2]) continue;
+      double dist = sig * loc[fj] - ha[fj];
+      if (dist > 0) continue;
+      copy3(cand[nc], p); cand[nc][3] = dist;
+      nc++;
+    }
+    /* corners of the face inside the cap disc */
+    double ncn = -(nf[2] * scap);                           /* n . cap normal with n = -nf */
+    if (ncn > 1e-6)
+      for (int i = 0; i < 4; i++) {
+        double loc[3]; loc[fj] = sig * ha[fj]; loc[k1] = (i & 1 ? 1 : -1) * ha[k1]; loc[k2] = (i & 2 ? 1 : -1) * ha[k2];
+        double v[3] = {cb[0], cb[1], cb[2]};
+        for (int k = 0; k < 3; k++) { v[0] += loc[k] * Aq[k][0]; v[1] += loc[k] * Aq[k][1]; v[2] += loc[k] * Aq[k][2]; }
+        double dcap = (v[2] - scap * h) * scap;             /* height of the corner above the cap plane */
+        double dist = dcap / ncn;                            /* along n = -nf */
+        if (dist > 0) continue;
+        double pB[3] = {v[0] + dist * nf[0], v[1] + dist * nf[1], v[2] + dist * nf[2]};   /* pB = pA - dist n */
+        if (pB[0] * pB[0] + pB[1] * pB[1] > r * r) continue;
+        copy3(cand[nc], pB); cand[nc][3] = dist;
+        nc++;
+      }
+    /* keep <= 4: the deepest, then the candidates farthest from the ones already kept */
+    int used[9] = {0}, keep[4];
+    for (int m = 0; m < 4 && m < nc; m++) {
+      int bi = -1; double bv = -1e30;
+      for (int i = 0; i < nc; i++) {
+        if (used[i]) continue;
+        double score;
+        if (m == 0) score = -cand[i][3];
+        else {
+          score = 1e30;
+          for (int j = 0; j < m; j++) {
+            double e0 = cand[i][0] - cand[keep[j]][0], e1 = cand[i][1] - cand[keep[j]][1], e2 = cand[i][2] - cand[keep[j]][2];
+            double dd = e0 * e0 + e1 * e1 + e2 * e2;
+            if (dd < score) score = dd;
+          }
+          if (score < 1e-10) continue;                      /* coincides with a kept point (deepest rim point = a fixed one) */
+        }
+        if (score > bv) { bv = score; bi = i; }
+      }
+      if (bi < 0) break;
+      used[bi] = 1; keep[m] = bi;
+      double nw[3] = {-nf[0], -nf[1], -nf[2]}, pw[3];
+      matvec3(Rb, cand[bi], pw); add3(out[n].pB, pw, pb);
+      matvec3(Rb, nw, out[n].nB);
+      out[n].dist = cand[bi][3];
+      n++;
+    }
+    return n;
+  }
+  /* ---- curved side against the box ---- */
+  for (int i = 0; i < 2; i++) {
+    if (rho[i] - r > 0 || rho[i] < 1e-9) continue;
+    if (i == 1 && fabs(zs[1] - zs[0]) < 1e-6) break;
+    double nl[3] = {qs[i][0] / rho[i], qs[i][1] / rho[i], 0}, pl[3] = {nl[0] * r, nl[1] * r, qs[i][2]}, pw[3];
+    matvec3(Rb, pl, pw); add3(out[n].pB, pw, pb);
+    matvec3(Rb, nl, out[n].nB);
+    out[n].dist = rho[i] - r;
+    n++;
+  }
+  (void)ax;
+  return n;
+}
+
 static double box_radius(const double* h) { return sqrt(h[0] * h[0] + h[1] * h[1] + h[2] * h[2]); }
 
 static Geom make_geom(int kind, int index, const double* half, double friction) {
   Geom g;
-  g.kind = kind; g.index = index; copy3(g.half, half); g.friction = friction; g.radius = box_radius(half);
+  g.kind = kind; g.index = index; copy3(g.half, half); g.friction = friction; g.radius = box_radius(half); g.cylinder = 0;
   return g;
 }
 
 static void build_pairs(PmgoEnv* e) {
-  const double bh[3] = {PMG_BLOCK_HALF, PMG_BLOCK_HALF, PMG_BLOCK_HALF};
+  double bh[3] = {PMG_BLOCK_HALF, PMG_BLOCK_HALF, PMG_BLOCK_HALF};
   Geom table = make_geom(0, 0, TABLE_HALF, PMG_TABLE_FRICTION), floor_ = make_geom(0, 1, FLOOR_HALF, PMG_FLOOR_FRICTION);
+  if (e->puck) {
+    table = make_geom(0, 0, LONG_TABLE_HALF, PMG_LONG_TABLE_FRICTION);
+    set3(bh, PMG_PUCK_RADIUS, PMG_PUCK_RADIUS, PMG_PUCK_HALF_LEN);
+  }
   Geom f1 = make_geom(1, PMG_BODY_FINGER1, FINGER_HALF, PMG_FINGER_FRICTION), f2 = make_geom(1, PMG_BODY_FINGER2, FINGER_HALF, PMG_FINGER_FRICTION);
   int n = 0;
   e->pairs[n].a = f1; e->pairs[n++].b = table;
   e->pairs[n].a = f2; e->pairs[n++].b = table;
   for (int i = 0; i < e->nb; i++) {
-    Geom blk = make_geom(2, i, bh, PMG_BLOCK_FRICTION);
+    Geom blk = make_geom(2, i, bh, e->puck ? PMG_PUCK_FRICTION : PMG_BLOCK_FRICTION);
+    blk.cylinder = e->puck;
     e->pairs[n].a = table; e->pairs[n++].b = blk;
     e->pairs[n].a = floor_; e->pairs[n++].b = blk;
     e->pairs[n].a = f1; e->pairs[n++].b = blk;
@@ -787,7 +924,7 @@ static void build_pairs(PmgoEnv* e) {
 
 static const double I3c[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
 static void geom_pose(const PmgoEnv* e, const Geom* g, const double** p, const double** R) {
-  if (g->kind == 0) { *p = g->index == 0 ? TABLE_CENTER : FLOOR_CENTER; *R = I3c; }
+  if (g->kind == 0) { *p = g->index == 0 ? e->table_center : FLOOR_CENTER; *R = I3c; }
   else if (g->kind == 1) { *p = e->bp[g->index]; *R = e->bR[g->index]; }
   else { *p = e->bpos[g->index]; *R = e->blkR[g->index]; }
 }
@@ -846,7 +983,8 @@ static void collide(PmgoEnv* e) {
     if (!overlap) { m->n = 0; continue; }
     double thr = BREAKING_THRESHOLD_FACTOR * (pr->a.radius < pr->b.radius ? pr->a.radius : pr->b.radius);
     ContactOut c[4];
-    int nc = box_box(pa, Ra, pr->a.half, pb, Rb, pr->b.half, c);
+    int nc = pr->b.cylinder ? box_cyl(pa, Ra, pr->a.half, pb, Rb, pr->b.half[0], pr->b.half[2], c)
+                            : box_box(pa, Ra, pr->a.half, pb, Rb, pr->b.half, c);
     for (int i = 0; i < nc; i++) {
       double wa[3], lA[3], lB[3], t[3];
       copy3(wa, c[i].pB);
@@ -894,9 +1032,9 @@ static void block_jac(const PmgoEnv* e, int blk, const double* pw, const double*
   /* world inverse inertia R diag(1/I) R^T; the blocks are cubes so this is isotropic */
   double t[3], u[3];
   matTvec3(e->blkR[blk], J, t);
-  for (int k = 0; k < 3; k++) t[k] /= PMG_BLOCK_INERTIA;
+  for (int k = 0; k < 3; k++) t[k] /= e->blk_inertia[k];
   matvec3(e->blkR[blk], t, u);
-  for (int k = 0; k < 3; k++) { MJ[k] = u[k]; MJ[3 + k] = J[3 + k] / PMG_BLOCK_MASS; }
+  for (int k = 0; k < 3; k++) { MJ[k] = u[k]; MJ[3 + k] = J[3 + k] / e->blk_mass; }
 }
 
 static double row_velocity(const PmgoEnv* e, const Row* r, const double* qd, double bvel[MAXBLK][6]) {
@@ -1080,6 +1218,15 @@ static void substep(PmgoEnv* e) {
     if (e->qd[d] < -MAX_COORD_VEL) e->qd[d] = -MAX_COORD_VEL;
   }
   for (int b = 0; b < e->nb; b++) { /* free bodies: gravity + damping; cube => no gyroscopic term */
+    if (e->puck) { /* anisotropic inertia: alpha = -I^-1 (w x I w), I = R diag(I) R^T (btMultiBody's gyroscopic term) */
+      double wl[3], Iw[3], g[3], gw[3];
+      matTvec3(e->blkR[b], e->bw[b], wl);
+      for (int k = 0; k < 3; k++) Iw[k] = e->blk_inertia[k] * wl[k];
+      cross3(wl, Iw, g);
+      for (int k = 0; k < 3; k++) g[k] /= e->blk_inertia[k];
+      matvec3(e->blkR[b], g, gw);
+      for (int k = 0; k < 3; k++) e->bw[b][k] -= gw[k] * DT;
+    }
     double kl = LINK_DAMPING + LINK_DAMPING * norm3(e->bv[b]), ka = LINK_DAMPING + LINK_DAMPING * norm3(e->bw[b]);
     for (int k = 0; k < 3; k++) {
       double acc = -e->bv[b][k] * kl + (k == 2 ? GRAVITY_Z : 0.0);
@@ -1181,7 +1328,13 @@ PmgoEnv* pmgo_create_ex3(int task, int num_block, int binary_reward, double thr,
   e->nb = task == PMGO_REACH ? 0 : (e->multi ? num_block : 1);
   /* kuka.py:104-118: joint control takes 7 joint deltas (+ the grip command) */
   e->adim = e->jc ? (e->grasping ? 8 : 7) : (e->grasping ? 4 : 3);
-  e->target_in_air = task != PMGO_PUSH;
+  e->target_in_air = task != PMGO_PUSH && task != PMGO_SLIDE;
+  /* Slide (kuka_single_step_envs.py:49-59): long low-friction table, a 2 kg puck instead of the cube */
+  e->puck = task == PMGO_SLIDE;
+  e->blk_mass = e->puck ? PMG_PUCK_MASS : PMG_BLOCK_MASS;
+  for (int k = 0; k < 3; k++) e->blk_inertia[k] = e->puck ? PUCK_INERTIA[k] : PMG_BLOCK_INERTIA;
+  e->blk_spawn_z = e->puck ? PMG_PUCK_SPAWN_Z : BLOCK_SPAWN_Z;
+  copy3(e->table_center, e->puck ? LONG_TABLE_CENTER : TABLE_CENTER);
   if (task == PMGO_REACH) { e->dims[0] = 3; e->dims[1] = 3; e->dims[2] = 3; e->dims[3] = 3; }
   else if (e->multi) { e->dims[0] = 8 + 16 * e->nb; e->dims[1] = 4 + 3 * e->nb; e->dims[2] = e->dims[3] = 3 * e->nb; }
   else { e->dims[0] = 20; e->dims[1] = 7; e->dims[2] = 3; e->dims[3] = 3; }
@@ -1189,13 +1342,15 @@ PmgoEnv* pmgo_create_ex3(int task, int num_block, int binary_reward, double thr,
   if (e->jc) { e->dims[0] += 7; e->dims[1] += 7; }   /* joint poses are prepended (kuka_single_step_base_env.py:214-216) */
   /* kuka.py:35-51 with each task's ctor args (obj_range = target_range = 0.15) */
   set3(e->tip_init, -0.52, 0.0, 0.25);
-  if (task == PMGO_PUSH || task == PMGO_BLOCK_REARRANGE) e->tip_init[2] = 0.175 + 0.001;
+  if (task == PMGO_PUSH || task == PMGO_BLOCK_REARRANGE || task == PMGO_SLIDE) e->tip_init[2] = 0.175 + 0.001;
+  const double obj_range = task == PMGO_SLIDE ? 0.1 : 0.15, target_range = task == PMGO_SLIDE ? 0.2 : 0.15;
   for (int k = 0; k < 3; k++) {
-    e->obj_lo[k] = e->tip_init[k] - 0.15; e->obj_hi[k] = e->tip_init[k] + 0.15;
-    e->tgt_lo[k] = e->tip_init[k] - 0.15; e->tgt_hi[k] = e->tip_init[k] + 0.15;
+    e->obj_lo[k] = e->tip_init[k] - obj_range; e->obj_hi[k] = e->tip_init[k] + obj_range;
+    e->tgt_lo[k] = e->tip_init[k] - target_range; e->tgt_hi[k] = e->tip_init[k] + target_range;
   }
   e->obj_lo[0] += 0.03; e->obj_hi[0] -= 0.03;
   e->tgt_lo[0] += 0.03; e->tgt_lo[2] = EE_LOWER[2]; e->tgt_hi[0] -= 0.03;
+  if (task == PMGO_SLIDE) { e->tgt_lo[0] -= 0.4; e->tgt_hi[0] -= 0.4; } /* kuka_single_step_base_env.py:66-69 */
   memcpy(e->rest_pose, KUKA_REST_POSE, sizeof e->rest_pose);
   for (int b = 0; b < MAXBLK; b++) { e->bquat[b][3] = 1.0; }
   build_pairs(e);
@@ -1336,7 +1491,7 @@ static void robot_reset(PmgoEnv* e) { /* kuka.py:157-165 */
 
 static void place_blocks(PmgoEnv* e, const double* xy) {
   for (int b = 0; b < e->nb; b++) {
-    set3(e->bpos[b], xy[2 * b], xy[2 * b + 1], BLOCK_SPAWN_Z);
+    set3(e->bpos[b], xy[2 * b], xy[2 * b + 1], e->blk_spawn_z);
     e->bquat[b][0] = e->bquat[b][1] = e->bquat[b][2] = 0; e->bquat[b][3] = 1;
     set3(e->bv[b], 0, 0, 0); set3(e->bw[b], 0, 0, 0);
   }
@@ -1420,7 +1575,7 @@ void pmgo_reset(PmgoEnv* e, double* obs_out) {
       }
       xy[0] = x; xy[1] = y;
       place_blocks(e, xy);
-      set3(center, x, y, BLOCK_SPAWN_Z);
+      set3(center, x, y, e->blk_spawn_z);
     }
     for (;;) {
       for (int k = 0; k < 3; k++) e->goal[k] = mt_uniform(&e->rng, e->tgt_lo[k], e->tgt_hi[k]);
@@ -1428,8 +1583,8 @@ void pmgo_reset(PmgoEnv* e, double* obs_out) {
       sub3(d, e->goal, center);
       if (sqrt(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]) > 0.1) break;
     }
-    if (!e->target_in_air) e->goal[2] = BLOCK_SPAWN_Z;
-    else if (e->grasping) { if (mt_uniform(&e->rng, 0, 1) >= 0.5) e->goal[2] = BLOCK_SPAWN_Z; }
+    if (!e->target_in_air) e->goal[2] = e->blk_spawn_z;
+    else if (e->grasping) { if (mt_uniform(&e->rng, 0, 1) >= 0.5) e->goal[2] = e->blk_spawn_z; }
   }
   write_obs(e, obs_out);
 }

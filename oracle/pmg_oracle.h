@@ -31,7 +31,7 @@ extern "C" {
 #define PMGO_MAX_BLOCKS 5
 #define PMGO_MAX_OBS 176 /* nb=5, grip goal, joint control: 95 + 26 + 19 + 19 = 159 */
 
-enum { PMGO_REACH = 0, PMGO_PUSH = 1, PMGO_PICK_AND_PLACE = 2, PMGO_BLOCK_STACK = 3, PMGO_BLOCK_REARRANGE = 4 };
+enum { PMGO_REACH = 0, PMGO_PUSH = 1, PMGO_PICK_AND_PLACE = 2, PMGO_BLOCK_STACK = 3, PMGO_BLOCK_REARRANGE = 4, PMGO_SLIDE = 5 };
 
 typedef struct PmgoEnv PmgoEnv;
 

@@ -56,6 +56,7 @@ class _World(object):
         self.mot_target = np.zeros(9)
         self.mot_maximp = np.zeros(9)
         self.blocks = []          # body ids of the dynamic blocks, in load order
+        self.slide = False        # long_table.urdf + cylinder_bulk.urdf: the Slide scene (one puck instead of a cube)
         self.oracle = None
         self.scratch = _O.OracleEnv("reach")
 
@@ -73,7 +74,11 @@ class _World(object):
     def _ensure_oracle(self):
         nb = len(self.blocks)
         if self.oracle is None or self.oracle.nb != nb:
-            self.oracle = _O.OracleEnv("block_stack", num_block=nb) if nb else _O.OracleEnv("reach")
+            if self.slide:
+                assert nb == 1
+                self.oracle = _O.OracleEnv("slide")
+            else:
+                self.oracle = _O.OracleEnv("block_stack", num_block=nb) if nb else _O.OracleEnv("reach")
         return self.oracle
 
     def step(self):
@@ -161,6 +166,13 @@ def loadURDF(world, path, basePosition=(0, 0, 0), baseOrientation=(0, 0, 0, 1), 
     elif name in ("table.urdf",):
         body["kind"] = "static"
         assert np.allclose(basePosition, [-0.52, 0.0, 0.08])
+    elif name == "long_table.urdf":  # Slide (kuka_single_step_base_env.py:53-56)
+        body["kind"] = "static"
+        assert np.allclose(basePosition, [-0.70, 0.0, 0.08])
+        world.slide = True
+    elif name == "cylinder_bulk.urdf":
+        body["kind"] = "block"
+        assert world.slide, "the puck only exists on the long table"
     elif name.startswith("block"):
         body["kind"] = "block"
     elif name.startswith("target"):

@@ -5,21 +5,21 @@ and adds `batch` (number of environments stepped in lockstep; None = one unbatch
 reference's numpy shapes), `device`, `seed`, and the throughput options `device_sampling` (resets drawn on the
 device from Philox streams instead of the reference's host MT19937 streams) / `auto_reset` (environments reset
 themselves on the device when their episode ends).  Tasks on the accelerated path: reach, push,
-pick_and_place, block_stack, block_rearrange with the parallel-jaw gripper and state observations,
+pick_and_place, slide, block_stack, block_rearrange with the parallel-jaw gripper and state observations,
 including the `joint_control` and (block_stack) `grip_informed_goal` / `task_decomposition` / `use_curriculum` variants.
 """
 from .envs import (ActionError, KukaBlockRearrangeEnv, KukaBlockStackEnv, KukaBulletMGEnv,  # noqa: F401
-                   KukaPickAndPlaceEnv, KukaPushEnv, KukaReachEnv)
+                   KukaPickAndPlaceEnv, KukaPushEnv, KukaReachEnv, KukaSlideEnv)
 
-__all__ = ["make_env", "KukaBulletMGEnv", "KukaReachEnv", "KukaPushEnv", "KukaPickAndPlaceEnv",
+__all__ = ["make_env", "KukaBulletMGEnv", "KukaReachEnv", "KukaPushEnv", "KukaPickAndPlaceEnv", "KukaSlideEnv",
            "KukaBlockStackEnv", "KukaBlockRearrangeEnv", "ActionError"]
 
 _TASKS = ['push', 'reach', 'slide', 'pick_and_place',
           'block_stack', 'block_rearrange', 'chest_pick_and_place', 'chest_push',
           'primitive_push_assemble', 'primitive_push_reach', 'insertion']
-_TAGS = {'reach': 'Reach', 'push': 'Push', 'pick_and_place': 'PickAndPlace', 'block_stack': 'BlockStack',
+_TAGS = {'reach': 'Reach', 'push': 'Push', 'pick_and_place': 'PickAndPlace', 'slide': 'Slide', 'block_stack': 'BlockStack',
          'block_rearrange': 'BlockRearrangeEnv'}  # __init__.py:21-40 (the rearrange tag really ends in 'Env')
-_ENTRY = {'reach': KukaReachEnv, 'push': KukaPushEnv, 'pick_and_place': KukaPickAndPlaceEnv,
+_ENTRY = {'reach': KukaReachEnv, 'push': KukaPushEnv, 'pick_and_place': KukaPickAndPlaceEnv, 'slide': KukaSlideEnv,
           'block_stack': KukaBlockStackEnv, 'block_rearrange': KukaBlockRearrangeEnv}
 
 
@@ -52,7 +52,7 @@ def make_env(task='reach', gripper='parallel_jaw', num_block=5, render=False, bi
         if task in _TAGS:
             task_decomposition = False  # the single-step tasks do not take the kwarg (__init__.py:88-106)
     if use_curriculum and task != 'block_stack':
-        if task in ('reach', 'push', 'pick_and_place'):
+        if task in ('reach', 'push', 'pick_and_place', 'slide'):
             use_curriculum = False  # the single-step tasks do not take the kwarg (__init__.py:88-106)
     for name, val in (('render', render),
                       ('image_observation', image_observation), ('depth_image', depth_image),
@@ -64,7 +64,7 @@ def make_env(task='reach', gripper='parallel_jaw', num_block=5, render=False, bi
         unsupported.append("primitive=%r" % primitive)
     if unsupported:
         raise NotImplementedError(
-            "outside the accelerated step path (reach/push/pick_and_place/block_stack/block_rearrange, "
+            "outside the accelerated step path (reach/push/pick_and_place/slide/block_stack/block_rearrange, "
             "parallel_jaw, state observations): " + ", ".join(unsupported))
     if task in ('block_stack', 'block_rearrange'):
         assert num_block <= 5, "only support up to 5 blocks"

@@ -314,8 +314,8 @@ __global__ void __launch_bounds__(32, COOP_MIN_BLOCKS) step_kernel_coop_reach(St
   float* lane_consts = reinterpret_cast<float*>(coop_smem);
   if (lane32 < coop::GL) coop::fill_lane_constants(lane_consts + lane32 * coop::LC_W, lane32);
   __syncwarp();
-  const int env = blockIdx.x * (32 / coop::GL) + grp;
-  if (env >= io.batch) return;  // a whole octet leaves together
+  const int env = blockIdx.x * io.epb + grp;      // io.epb environments per one-warp block (octets beyond it stay idle)
+  if (grp >= io.epb || env >= io.batch) return;   // a whole octet leaves together
   coop::Grp g;
   g.lane = lane32 & (coop::GL - 1); g.shift = grp * coop::GL; g.mask = 0xffu << g.shift;
   coop::EnvSmem& sm = reinterpret_cast<coop::EnvSmem*>(coop_smem + COOP_TABLE_BYTES)[grp];
@@ -332,11 +332,11 @@ __global__ void __launch_bounds__(32, 7) step_kernel_coop_block(StepIO io) {
   float* lane_consts = reinterpret_cast<float*>(coop_smem);
   if (lane32 < coop::GL) coop::fill_lane_constants(lane_consts + lane32 * coop::LC_W, lane32);
   __syncwarp();
-  const int env = blockIdx.x * (32 / coop::GL) + grp;
-  if (env >= io.batch) return;  // a whole octet leaves together
+  const int env = blockIdx.x * io.epb + grp;      // io.epb environments per one-warp block (octets beyond it stay idle)
+  if (grp >= io.epb || env >= io.batch) return;   // a whole octet leaves together
   coop::Grp g;
   g.lane = lane32 & (coop::GL - 1); g.shift = grp * coop::GL; g.mask = 0xffu << g.shift;
-  coop::EnvSmemT<1>& sm = reinterpret_cast<coop::EnvSmemT<1>*>(coop_smem + COOP_TABLE_BYTES)[grp];
+  coop::EnvSmemT<1, TASK == 5>& sm = reinterpret_cast<coop::EnvSmemT<1, TASK == 5>*>(coop_smem + COOP_TABLE_BYTES)[grp];
   coop::step_env_block<TASK>(g, sm, lane_consts, io, env);
 }
 
@@ -349,8 +349,8 @@ __global__ void __launch_bounds__(32, 3) step_kernel_coop_multi(StepIO io) {
   float* lane_consts = reinterpret_cast<float*>(coop_smem);
   if (lane32 < coop::GL) coop::fill_lane_constants(lane_consts + lane32 * coop::LC_W, lane32);
   __syncwarp();
-  const int env = blockIdx.x * (32 / coop::GL) + grp;
-  if (env >= io.batch) return;  // a whole octet leaves together
+  const int env = blockIdx.x * io.epb + grp;      // io.epb environments per one-warp block (octets beyond it stay idle)
+  if (grp >= io.epb || env >= io.batch) return;   // a whole octet leaves together
   coop::Grp g;
   g.lane = lane32 & (coop::GL - 1); g.shift = grp * coop::GL; g.mask = 0xffu << g.shift;
   coop::EnvSmemT<NBLK>& sm = reinterpret_cast<coop::EnvSmemT<NBLK>*>(coop_smem + COOP_TABLE_BYTES)[grp];
@@ -363,6 +363,7 @@ __global__ void __launch_bounds__(32, 3) step_kernel_coop_multi(StepIO io) {
 // episode; the terminal row is copied to `terminal` first when given), reward / done / success stay the terminal ones.
 struct ResetIO {
   StepIO io; const uint8_t* mask; const float* spawn; float tip_init[3];
+  float spawn_z;  // height the objects are placed at: cubes 0.175, Slide's puck 0.170
   int task, auto_rows; unsigned long long seed; long long env_base; uint32_t* episode; float* spawn_out; float* terminal;
   spawn::Bounds bounds;
 };
@@ -415,7 +416,7 @@ __device__ void reset_env(const ResetIO& r, int i, bool doit) {
     }
 #pragma unroll
     for (int b = 0; b < NBLK; b++) {
-      e.bpos[b] = v3(sp[2 * b], sp[2 * b + 1], BLOCK_SPAWN_Z);
+      e.bpos[b] = v3(sp[2 * b], sp[2 * b + 1], r.spawn_z);
       e.bquat[b][0] = e.bquat[b][1] = e.bquat[b][2] = 0.0f; e.bquat[b][3] = 1.0f;
       e.bv[b] = v3(0, 0, 0); e.bw[b] = v3(0, 0, 0);
     }
@@ -678,6 +679,7 @@ struct pmg_handle {
   int stage_cur = 0;
   std::vector<MT> rng;
   double tip_init[3], obj_lo[3], obj_hi[3], tgt_lo[3], tgt_hi[3];
+  double spawn_z = 0.175;  // kuka_single_step_base_env.py:50 (cube) / :56 (Slide's puck: 0.170)
   bool was_reset = false;
   int64_t launches = 0;
   int epw = 32;  // environments per warp (launch geometry, see pmg_create)
@@ -687,6 +689,7 @@ struct pmg_handle {
   bool coop_block = true;  // Push / PickAndPlace: lane-cooperative kernel (PMG_COOP_BLOCK=0 selects the thread-per-env kernel)
   bool coop_stack = true;  // BlockStack / BlockRearrange with >= 2 blocks: lane-cooperative kernel (PMG_COOP_STACK=0 selects the thread-per-env kernel)
   bool hinted = false;  // shared-memory carve-out hint of this handle's step kernel has been set on its device
+  int epb = 0;          // lane-cooperative kernels: environments per one-warp block, chosen at the first launch (coop_geometry)
   // device-side reset sampling (pmg_spawn.cuh) and auto-reset
   bool dev_rng = false, auto_reset = false, last_spawn_on_device = false;
   uint64_t rng_seed = 0; int64_t env_base = 0;
@@ -797,7 +800,7 @@ void sample_spawn(pmg_handle* h, int i, float* out) {
       x = r.uniform(h->obj_lo[0], h->obj_hi[0]); y = r.uniform(h->obj_lo[1], h->obj_hi[1]);
     }
     out[0] = (float)x; out[1] = (float)y;
-    center[0] = x; center[1] = y; center[2] = 0.175;
+    center[0] = x; center[1] = y; center[2] = h->spawn_z;
   }
   double g[3];
   for (;;) {
@@ -805,7 +808,7 @@ void sample_spawn(pmg_handle* h, int i, float* out) {
     double dx = g[0] - center[0], dy = g[1] - center[1], dz = g[2] - center[2];
     if (sqrt(dx * dx + dy * dy + dz * dz) > 0.1) break;
   }
-  if (h->cfg.task == PMG_PUSH) g[2] = 0.175;
+  if (h->cfg.task == PMG_PUSH || h->cfg.task == PMG_SLIDE) g[2] = h->spawn_z;
   else if (h->cfg.task == PMG_PICK_AND_PLACE) { if (r.uniform(0, 1) >= 0.5) g[2] = 0.175; }
   for (int k = 0; k < 3; k++) out[2 * nb + k] = (float)g[k];
 }
@@ -816,7 +819,7 @@ StepIO make_io(pmg_handle* h, const float* action, float* obs, float* reward, ui
   io.action = action; io.obs = obs; io.reward = reward; io.done = done; io.success = success;
   io.thr = h->cfg.distance_threshold; io.binary = h->cfg.binary_reward; io.max_steps = h->cfg.max_episode_steps;
   io.overflow = h->d_overflow; io.row_spill = h->d_row_spill;
-  io.epw = h->epw;
+  io.epw = h->epw; io.epb = 32 / coop::GL;
   io.bulk = 0; io.tile_offset = 0;
   io.grasp = h->grasp; io.jc = h->jc; io.grip_goal = h->grip; io.td = h->td || h->cur; io.cur = h->cur;
   io.adim = h->A; io.goal_dim = h->G; io.row_width = h->W;
@@ -824,32 +827,64 @@ StepIO make_io(pmg_handle* h, const float* action, float* obs, float* reward, ui
   return io;
 }
 
+// Launch geometry of a lane-cooperative kernel: environments per one-warp block.  A warp of four octets runs as long
+// as the union of its octets' paths, and at the configs' batches the kernels are latency-bound (one warp issues every
+// 4-5 cycles), so FEWER environments per warp -- more, emptier warps -- is faster as long as (a) every block is still
+// resident at once (registers / shared memory: asked from the occupancy API for this kernel and block size) and (b) there
+// is at most one warp per scheduler (4 per SM).  Measured (profiles/r02_envs_per_block.txt): pick_and_place at 512
+// environments 2.10 -> 1.86 ms with 1 per warp, block_stack at 256: 2.91 -> 2.74 ms; but block_stack at 2048 with 2 per
+// warp (7 warps per SM) is SLOWER than 4 per warp (3.71 vs 3.45 ms): more warps in different phases of a loop body larger
+// than the instruction cache.  So the shards of the 8-GPU configs (256 - 1024 environments) get emptier warps, the
+// single-GPU configs keep 4 per warp.  PMG_COOP_EPB overrides.
+template <class K>
+int coop_geometry(pmg_handle* h, K kernel, size_t table_bytes, size_t env_bytes) {
+  if (h->epb) return h->epb;
+  int sms = 148;
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->cfg.device);
+  int best = 32 / coop::GL;
+  for (int epb = best; epb >= 1; epb >>= 1) {
+    const size_t smem = table_bytes + (size_t)epb * env_bytes;
+    int per_sm = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, 32, smem) != cudaSuccess) break;
+    const long blocks = ((long)h->cfg.batch + epb - 1) / epb;
+    if (blocks > (long)per_sm * sms) break;          // (a) one wave
+    if (blocks > 4L * sms) break;                    // (b) <= 1 warp per scheduler
+    best = epb;
+  }
+  if (const char* ev = getenv("PMG_COOP_EPB")) { const int v = atoi(ev); if (v == 1 || v == 2 || v == 4) best = v; }
+  h->epb = best;
+  return best;
+}
+
 // one warp per block: the block scheduler then spreads the (few) warps evenly over the 148 SMs
 template <int TASK, int NBLK>
 void launch_step(pmg_handle* h, const StepIO& io_in, cudaStream_t st) {
   StepIO io = io_in;
   if (TASK == 0 && h->coop) {
-    constexpr int EPB = 32 / coop::GL;  // environments per block
-    const size_t smem = COOP_TABLE_BYTES + EPB * sizeof(coop::EnvSmem);
-    const int blocks = (h->cfg.batch + EPB - 1) / EPB;
     if (!h->hinted) {  // per handle = per device: function attributes are per device
       if (h->jc) cudaFuncSetAttribute(step_kernel_coop_reach<true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
       else cudaFuncSetAttribute(step_kernel_coop_reach<false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
       h->hinted = true;
     }
+    const int EPB = h->jc ? coop_geometry(h, step_kernel_coop_reach<true>, COOP_TABLE_BYTES, sizeof(coop::EnvSmem))
+                          : coop_geometry(h, step_kernel_coop_reach<false>, COOP_TABLE_BYTES, sizeof(coop::EnvSmem));
+    io.epb = EPB;
+    const size_t smem = COOP_TABLE_BYTES + EPB * sizeof(coop::EnvSmem);
+    const int blocks = (h->cfg.batch + EPB - 1) / EPB;
     if (h->jc) step_kernel_coop_reach<true><<<blocks, 32, smem, st>>>(io);
     else step_kernel_coop_reach<false><<<blocks, 32, smem, st>>>(io);
     return;
   }
   if constexpr (TASK == 3 && NBLK >= 2) {
     if (h->coop_stack && !h->jc) {
-      constexpr int EPB = 32 / coop::GL;
-      const size_t smem = COOP_TABLE_BYTES + EPB * sizeof(coop::EnvSmemT<NBLK>);
       if (!h->hinted) {
-        cudaFuncSetAttribute(step_kernel_coop_multi<NBLK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaFuncSetAttribute(step_kernel_coop_multi<NBLK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(COOP_TABLE_BYTES + 4 * sizeof(coop::EnvSmemT<NBLK>)));
         cudaFuncSetAttribute(step_kernel_coop_multi<NBLK>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
         h->hinted = true;
       }
+      const int EPB = coop_geometry(h, step_kernel_coop_multi<NBLK>, COOP_TABLE_BYTES, sizeof(coop::EnvSmemT<NBLK>));
+      io.epb = EPB;
+      const size_t smem = COOP_TABLE_BYTES + EPB * sizeof(coop::EnvSmemT<NBLK>);
       step_kernel_coop_multi<NBLK><<<(h->cfg.batch + EPB - 1) / EPB, 32, smem, st>>>(io);
       return;
     }
@@ -860,12 +895,20 @@ void launch_step(pmg_handle* h, const StepIO& io_in, cudaStream_t st) {
   io.tile_offset = (int)((stage_floats + 31) / 32 * 32);
   size_t smem = (io.bulk ? io.tile_offset + (size_t)Dims<TASK, NBLK>::STATE * 32 : stage_floats) * sizeof(float);
   if ((TASK == 1 || TASK == 2) && h->coop_block) {
-    constexpr int EPB = 32 / coop::GL;
-    const size_t smem = COOP_TABLE_BYTES + EPB * sizeof(coop::EnvSmemT<1>);
     if (!h->hinted) {
-      cudaFuncSetAttribute(step_kernel_coop_block<TASK == 2 ? 2 : 1>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+      if (h->cfg.task == PMG_SLIDE) cudaFuncSetAttribute(step_kernel_coop_block<5>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+      else cudaFuncSetAttribute(step_kernel_coop_block<TASK == 2 ? 2 : 1>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
       h->hinted = true;
     }
+    if (h->cfg.task == PMG_SLIDE) {  // Push's layout with the long table and the puck (EnvSmemT<1, true>)
+      const int EPB = coop_geometry(h, step_kernel_coop_block<5>, COOP_TABLE_BYTES, sizeof(coop::EnvSmemT<1, true>));
+      io.epb = EPB;
+      step_kernel_coop_block<5><<<(h->cfg.batch + EPB - 1) / EPB, 32, COOP_TABLE_BYTES + EPB * sizeof(coop::EnvSmemT<1, true>), st>>>(io);
+      return;
+    }
+    const int EPB = coop_geometry(h, step_kernel_coop_block<TASK == 2 ? 2 : 1>, COOP_TABLE_BYTES, sizeof(coop::EnvSmemT<1>));
+    io.epb = EPB;
+    const size_t smem = COOP_TABLE_BYTES + EPB * sizeof(coop::EnvSmemT<1>);
     step_kernel_coop_block<TASK == 2 ? 2 : 1><<<(h->cfg.batch + EPB - 1) / EPB, 32, smem, st>>>(io);
     return;
   }
@@ -887,7 +930,7 @@ void launch_reset(pmg_handle* h, const ResetIO& r, cudaStream_t st) {
 #define PMG_DISPATCH(FN, ...)                                                        \
   switch (h->cfg.task) {                                                             \
     case PMG_REACH: FN<0, 0>(__VA_ARGS__); break;                                    \
-    case PMG_PUSH: FN<1, 1>(__VA_ARGS__); break;                                     \
+    case PMG_PUSH: case PMG_SLIDE: FN<1, 1>(__VA_ARGS__); break;                     \
     case PMG_PICK_AND_PLACE: FN<2, 1>(__VA_ARGS__); break;                           \
     default:                                                                         \
       switch (h->nblk) {                                                             \
@@ -907,6 +950,7 @@ void enqueue_reset(pmg_handle* h, const uint8_t* mask_dev, const float* spawn_de
   r.mask = mask_dev;
   r.spawn = spawn_dev;
   for (int k = 0; k < 3; k++) r.tip_init[k] = (float)h->tip_init[k];
+  r.spawn_z = (float)h->spawn_z;
   r.task = h->cfg.task; r.auto_rows = auto_rows; r.seed = h->rng_seed; r.env_base = h->env_base;
   r.episode = h->d_episode; r.spawn_out = h->d_spawn_dev; r.terminal = auto_rows ? h->terminal_obs : nullptr;
   r.bounds = spawn::to_bounds(h->tip_init, h->obj_lo, h->obj_hi, h->tgt_lo, h->tgt_hi);
@@ -926,7 +970,7 @@ const char* pmg_last_error(void) { return g_err; }
 
 int pmg_create(const pmg_config* cfg, pmg_handle** out) {
   if (!cfg || !out) return fail(PMG_ERR_INVALID, "pmg_create: null argument%s");
-  if (cfg->task < PMG_REACH || cfg->task > PMG_BLOCK_REARRANGE) return fail(PMG_ERR_INVALID, "pmg_create: invalid task id%s");
+  if (cfg->task < PMG_REACH || cfg->task > PMG_SLIDE) return fail(PMG_ERR_INVALID, "pmg_create: invalid task id%s");
   const bool multi = cfg->task == PMG_BLOCK_STACK || cfg->task == PMG_BLOCK_REARRANGE;
   if (multi && (cfg->num_block < 1 || cfg->num_block > 5)) return fail(PMG_ERR_INVALID, "pmg_create: only support up to 5 blocks%s");
   if (cfg->grip_informed_goal && cfg->task != PMG_BLOCK_STACK) return fail(PMG_ERR_INVALID, "pmg_create: grip_informed_goal is a block_stack option%s");
@@ -960,6 +1004,7 @@ int pmg_create(const pmg_config* cfg, pmg_handle** out) {
   h->spawn_w = 2 * h->nblk + h->G + (h->cur ? 1 : 0);
   // kuka.py:35-51 with obj_range = target_range = 0.15 (kuka_single_step_envs.py, kuka_multi_step_envs.py:29)
   spawn::task_bounds(t, h->tip_init, h->obj_lo, h->obj_hi, h->tgt_lo, h->tgt_hi);
+  if (t == PMG_SLIDE) h->spawn_z = PMG_PUCK_SPAWN_Z;
   const size_t B = cfg->batch;
   {
     // Launch geometry: lanes [0, epw) of every warp own one environment.  Spreading a batch over
@@ -996,7 +1041,8 @@ int pmg_create(const pmg_config* cfg, pmg_handle** out) {
   ALLOC(h->d_overflow, sizeof(int));
   ALLOC(h->d_episode, sizeof(uint32_t) * B);
   ALLOC(h->d_spawn_dev, sizeof(float) * h->spawn_w * B);
-  if ((h->cfg.task == PMG_PUSH || h->cfg.task == PMG_PICK_AND_PLACE) && h->coop_block)
+  if (h->cfg.task == PMG_SLIDE && !h->coop_block) { pmg_destroy(h); return fail(PMG_ERR_INVALID, "pmg_create: slide runs on the lane-cooperative kernel only (PMG_COOP_BLOCK=0 is set)%s"); }
+  if ((h->cfg.task == PMG_PUSH || h->cfg.task == PMG_PICK_AND_PLACE || h->cfg.task == PMG_SLIDE) && h->coop_block)
     ALLOC(h->d_row_spill, sizeof(float) * coop::EnvSmemT<1>::SPILL_WORDS * B);
   if (h->multi && h->nblk >= 2 && h->coop_stack && !h->jc)
     ALLOC(h->d_row_spill, sizeof(float) * coop::EnvSmemT<2>::SPILL_WORDS * B);  // the same for every NBLK >= 2

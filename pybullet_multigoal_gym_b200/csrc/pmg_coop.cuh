@@ -47,9 +47,15 @@ constexpr int MINV_LD = 12;  // row stride of M^-1 in shared memory
 // resident, read as warp-uniform broadcasts), which is what lets 7 blocks = 28 environments share one SM.
 template <int NBLK> struct RowSpill { float* spill; float spill_pad_[2]; };
 template <> struct RowSpill<0> {};
-template <int NBLK>
-struct __align__(16) EnvSmemT : RowSpill<NBLK> {
+// NBLK > 1: the points that are not static, in pair order (point index into the impulse arrays), built once per substep
+// (glist: point index into the impulse arrays), with each one's pair and its index inside the pair's manifold
+template <int NBLK> struct GenList { unsigned char glist[48], ppair[48], pidx[48]; };
+template <> struct GenList<0> {};
+template <> struct GenList<1> {};
+template <int NBLK, bool PUCK_ = false>
+struct __align__(16) EnvSmemT : RowSpill<NBLK>, GenList<NBLK> {
   static constexpr int NB = NBLK;
+  static constexpr bool PUCK = PUCK_;  // Slide: long table, the block is a cylinder with an anisotropic inertia
   static constexpr int NPAIRS = num_pairs(NBLK);                // 2 / 6
   static constexpr int MAXPTS = NBLK == 0 ? 8 : (NBLK == 1 ? 24 : 48);  // cached contact points that get rows
   static constexpr int SPTS = NBLK == 0 ? 8 : (NBLK == 1 ? 12 : 8);  // ... of which in shared memory (NBLK > 1: of the points that are not static)
@@ -425,6 +431,14 @@ __device__ __noinline__ void contact_row_setup(EnvSmem& sm, int c, int n0) {
 // (no end), body B is the table (no end) or the block (end: d and r_B x d).
 // SPILL: the point's records go to the global scratch (c >= SPTS); its own copy of the code, so that the usual
 // points keep shared-memory stores and loads.
+// S x with S = I_world^-1/2 = R diag(1/sqrt(I)) R^T = k1 + (k3 - k1) a a^T for a body of revolution about its axis a
+static_assert(PMG_PUCK_MASS == PMG_BLOCK_MASS, "the puck reuses BLOCK_INV_MASS");
+__device__ __forceinline__ V3 puck_scale(V3 x, V3 a) {
+  const float pin[3] = PMG_PUCK_INERTIA;
+  const float k1 = rsqrtf(pin[0]), k3 = rsqrtf(pin[2]);
+  return k1 * x + ((k3 - k1) * dot(a, x)) * a;
+}
+
 template <bool SPILL, class SM>
 __device__ __noinline__ void contact_row_setup_blk(SM& sm, int c) {
   // which pair / which point of it
@@ -454,14 +468,18 @@ __device__ __noinline__ void contact_row_setup_blk(SM& sm, int c) {
   const V3 bv = v3(bk[BK_V], bk[BK_V + 1], bk[BK_V + 2]), bw = v3(bk[BK_W], bk[BK_W + 1], bk[BK_W + 2]);
   V3 t1, t2;
   plane_space(nB, t1, t2);
-  const float mu = geom_friction(pi.ka) * geom_friction(pi.kb);
+  const float mu = geom_friction(pi.ka, SM::PUCK) * geom_friction(pi.kb, SM::PUCK);
+  const V3 axb = v3(bk[BK_R + 2], bk[BK_R + 5], bk[BK_R + 8]);  // the puck's axis (third column of its orientation)
 #pragma unroll 1
   for (int kk = 0; kk < 3; kk++) {
     const V3 d = kk == 0 ? nB : (kk == 1 ? t1 : t2);
     float* row = SPILL ? sm.spill_row(c * 3 + kk) : sm.rows[SPILL ? 0 : c * 3 + kk];
-    const V3 ang = cross(rB, d);
-    float denom = blockB ? BLOCK_INV_MASS + BLOCK_INV_INERTIA * dot(ang, ang) : 0.0f;
-    float rel_vel = blockB ? -(dot(d, bv) + dot(ang, bw)) : 0.0f;
+    const V3 ang0 = cross(rB, d);
+    // Puck: rows carry S (r_B x d) with S = I_world^-1/2 and the sweeps solve for S^-1 dw (puck_scale), which keeps
+    // the record and the isotropic update of the cubes: (r x d) . dw = (S r x d) . (S^-1 dw), dw += lam I^-1 (r x d).
+    const V3 ang = SM::PUCK ? puck_scale(ang0, axb) : ang0;
+    float denom = blockB ? BLOCK_INV_MASS + (SM::PUCK ? 1.0f : BLOCK_INV_INERTIA) * dot(ang, ang) : 0.0f;
+    float rel_vel = blockB ? -(dot(d, bv) + dot(ang0, bw)) : 0.0f;
     if (robotA) {
       const V3 m = cross(wr, d);
       float J[ND];  // statically indexed everywhere below: stays in registers
@@ -535,8 +553,9 @@ __device__ __forceinline__ BlkVec load_blk(const float* row) {
 __device__ __forceinline__ float blk_dot(const BlkVec& b, const float* dv) {  // dv = block delta (lin[3], ang[3])
   return b.a.w * ((b.d.x * dv[0] + b.d.y * dv[1] + b.d.z * dv[2]) + (b.a.x * dv[3] + b.a.y * dv[4] + b.a.z * dv[5]));
 }
+template <bool PUCK>  // the puck's rows carry the inertia in their scaled lever arm (contact_row_setup_blk)
 __device__ __forceinline__ void blk_axpy(const BlkVec& b, float lam, float* dv) {
-  const float lm = lam * b.a.w * BLOCK_INV_MASS, li = lam * b.a.w * BLOCK_INV_INERTIA;
+  const float lm = lam * b.a.w * BLOCK_INV_MASS, li = lam * b.a.w * (PUCK ? 1.0f : BLOCK_INV_INERTIA);
   dv[0] -= lm * b.d.x; dv[1] -= lm * b.d.y; dv[2] -= lm * b.d.z;
   dv[3] -= li * b.a.x; dv[4] -= li * b.a.y; dv[5] -= li * b.a.z;
 }
@@ -574,7 +593,7 @@ __device__ __noinline__ float contact_sweep(Grp g, SM& sm, int nrow_it) {  // nr
     const float sum = fminf(fmaxf(app + dl, 0.0f), 1e10f);
     dl = sum - app;
     if (RB) row_axpy(mj, dl, dq);
-    if (BK) blk_axpy(bk, dl, dv);
+    if (BK) blk_axpy<SM::PUCK>(bk, dl, dv);
     const float rr = dl * mc.y;                // denom
     cres = fmaxf(cres, rr * rr);
     app_wr[c * 3] = sum;
@@ -609,7 +628,7 @@ __device__ __noinline__ float contact_sweep(Grp g, SM& sm, int nrow_it) {  // nr
         dA = sA - appA; dB = sB - appB;
       }
       if (RB) { row_axpy(mja, dA, dq); row_axpy(mjb, dB, dq); }
-      if (BK) { blk_axpy(bka, dA, dv); blk_axpy(bkb, dB, dv); }
+      if (BK) { blk_axpy<SM::PUCK>(bka, dA, dv); blk_axpy<SM::PUCK>(bkb, dB, dv); }
       const float r1_ = dA * mca.y, r2_ = dB * mcb.y;
       cres = fmaxf(cres, fmaxf(r1_ * r1_, r2_ * r2_));
     }
@@ -669,16 +688,46 @@ __device__ __noinline__ float contact_sweep(Grp g, SM& sm, int nrow_it) {  // nr
 template <int NB>
 __device__ __forceinline__ bool static_pair(int k) { return k >= 2 && k < 2 + 4 * NB && ((k - 2) & 3) < 2; }
 
+// Static point `slot` (0..3: the table points, then the floor points) of block b: pair k, point i of its manifold,
+// point c of the pair-ordered list (impulse arrays).
 template <class SM>
-__device__ __noinline__ void contact_row_setup_multi(SM& sm, int c) {
-  int k = 0, i = c, gidx = c;  // pair, point inside the pair, index among the general points
+__device__ __noinline__ void contact_row_setup_static(SM& sm, int c, int b, int slot, int k, int i) {
+  const float* mp = sm.man + k * MAN_WORDS + 1 + 10 * i;
+  const V3 lB = v3(mp[3], mp[4], mp[5]), nB = v3(mp[6], mp[7], mp[8]);
+  const float dist = mp[9];
+  V3 t1, t2;
+  plane_space(nB, t1, t2);
+  const float mu = geom_friction((k - 2) & 3 ? G_FLOOR : G_TABLE) * geom_friction(G_BLOCK);
+  const float* bk = sm.blk + 24 * b;
+  M3 R;
+  R.r0 = v3(bk[BK_R], bk[BK_R + 1], bk[BK_R + 2]); R.r1 = v3(bk[BK_R + 3], bk[BK_R + 4], bk[BK_R + 5]); R.r2 = v3(bk[BK_R + 6], bk[BK_R + 7], bk[BK_R + 8]);
+  const V3 rB = mul(R, lB);
+  const V3 bv = v3(bk[BK_V], bk[BK_V + 1], bk[BK_V + 2]), bw = v3(bk[BK_W], bk[BK_W + 1], bk[BK_W + 2]);
 #pragma unroll 1
-  for (; k < SM::NPAIRS; k++) {
-    const int n = __float_as_int(sm.man[k * MAN_WORDS]);
-    if (i < n) break;
-    i -= n;
-    if (static_pair<SM::NB>(k)) gidx -= n;
+  for (int kk = 0; kk < 3; kk++) {
+    const V3 d = kk == 0 ? nB : (kk == 1 ? t1 : t2);
+    float* row = sm.srow((b * 4 + slot) * 3 + kk);
+    const V3 xb = cross(rB, d);
+    const float denom = BLOCK_INV_MASS + BLOCK_INV_INERTIA * dot(xb, xb);
+    const float rel_vel = -(dot(d, bv) + dot(xb, bw));
+    const float dinv = 1.0f / denom;
+    float rhs;
+    if (kk == 0) {
+      const float pen = dist + LINEAR_SLOP;
+      float pos_err = 0.0f, vel_err = -rel_vel;
+      if (pen > 0.0f) vel_err -= pen * INV_DT; else pos_err = -pen * CONTACT_ERP * INV_DT;
+      rhs = (pos_err + vel_err) * dinv;
+    } else rhs = -rel_vel * dinv;
+    row[0] = d.x; row[1] = d.y; row[2] = d.z; row[3] = rhs; row[4] = xb.x; row[5] = xb.y; row[6] = xb.z; row[7] = dinv;
+    row[8] = denom; row[9] = mu;
+    sm.app[0][c * 3 + kk] = 0.0f;
   }
+}
+
+// General point gi (a finger or a second block at the other end): the 40-float record, the first SPTS in shared memory.
+template <class SM>
+__device__ __noinline__ void contact_row_setup_general(SM& sm, int gidx) {
+  const int c = sm.glist[gidx], k = sm.ppair[gidx], i = sm.pidx[gidx];
   const PairInfo pi = pair_info<SM::NB>(k);
   const bool robotA = pi.ka == G_FINGER1 || pi.ka == G_FINGER2, blockA = pi.ka == G_BLOCK, blockB = pi.kb == G_BLOCK;
   const float* mp = sm.man + k * MAN_WORDS + 1 + 10 * i;
@@ -694,32 +743,6 @@ __device__ __noinline__ void contact_row_setup_multi(SM& sm, int c) {
     R.r0 = v3(bk[BK_R], bk[BK_R + 1], bk[BK_R + 2]); R.r1 = v3(bk[BK_R + 3], bk[BK_R + 4], bk[BK_R + 5]); R.r2 = v3(bk[BK_R + 6], bk[BK_R + 7], bk[BK_R + 8]);
     rB = mul(R, lB);
     bv = v3(bk[BK_V], bk[BK_V + 1], bk[BK_V + 2]); bw = v3(bk[BK_W], bk[BK_W + 1], bk[BK_W + 2]);
-  }
-  if (static_pair<SM::NB>(k)) {
-    // the 4-point manifolds of the table and the floor pair of one block: points beyond the 4 slots are dropped (a 3 cm
-    // cube cannot rest on both) and counted like the pool overflow
-    const int slot = i + ((k - 2) & 3 ? __float_as_int(sm.man[(k - 1) * MAN_WORDS]) : 0);
-    if (slot >= 4) return;
-#pragma unroll 1
-    for (int kk = 0; kk < 3; kk++) {
-      const V3 d = kk == 0 ? nB : (kk == 1 ? t1 : t2);
-      float* row = sm.srow((pi.ib * 4 + slot) * 3 + kk);
-      const V3 xb = cross(rB, d);
-      const float denom = BLOCK_INV_MASS + BLOCK_INV_INERTIA * dot(xb, xb);
-      const float rel_vel = -(dot(d, bv) + dot(xb, bw));
-      const float dinv = 1.0f / denom;
-      float rhs;
-      if (kk == 0) {
-        const float pen = dist + LINEAR_SLOP;
-        float pos_err = 0.0f, vel_err = -rel_vel;
-        if (pen > 0.0f) vel_err -= pen * INV_DT; else pos_err = -pen * CONTACT_ERP * INV_DT;
-        rhs = (pos_err + vel_err) * dinv;
-      } else rhs = -rel_vel * dinv;
-      row[0] = d.x; row[1] = d.y; row[2] = d.z; row[3] = rhs; row[4] = xb.x; row[5] = xb.y; row[6] = xb.z; row[7] = dinv;
-      row[8] = denom; row[9] = mu;
-      sm.app[0][c * 3 + kk] = 0.0f;
-    }
-    return;
   }
   const float* hd = sm.hand;
   M3 Rg;
@@ -796,46 +819,58 @@ __device__ __noinline__ void contact_row_setup_multi(SM& sm, int c) {
 //   * the remaining rows (a finger or a second block at the other end) are visited by the whole octet in pair order: a
 //     row fetches its one or two blocks with run-time-source shuffles (legal on the diverged path: the whole octet
 //     takes it) and the owner lanes apply the impulse.
+// nrow_it: iteration parity << 8 | number of general points << 16; srange: this lane's static points [s0, s1) as
+// s0 | s1 << 8 (a contiguous run of the pair-ordered point list: table-block, then floor-block), both from the substep.
 template <class SM>
-__device__ __noinline__ float contact_sweep_multi(Grp g, SM& sm, int nrow_it) {  // nrow | iteration parity << 8
+__device__ __noinline__ float contact_sweep_multi(Grp g, SM& sm, int nrow_it, int srange) {
   constexpr int NB = SM::NB;
-  const int nrow = nrow_it & 0xff, it = nrow_it >> 8;
+  const int it = (nrow_it >> 8) & 1, ngen = (nrow_it >> 16) & 0xff;
   const int lane = g.lane;
   const float* app_rd = sm.app[it & 1];
   float* app_wr = sm.app[(it & 1) ^ 1];
   float dq[ND], bd[6];
+  if (ngen) {  // only rows with a robot end read the joint delta velocities (uniform over the octet)
 #pragma unroll
-  for (int j = 0; j < ND; j++) dq[j] = sm.vq[j];
+    for (int j = 0; j < ND; j++) dq[j] = sm.vq[j];
+  }
 #pragma unroll
   for (int j = 0; j < 6; j++) bd[j] = lane < NB ? sm.vq[ND + 6 * lane + j] : 0.0f;
   float cres = 0.0f;
   auto ld4 = [](const float* p) { return *reinterpret_cast<const float4*>(p); };
-  // this lane's static points: a contiguous run of the pair-ordered point list (table-block, then floor-block)
-  int s0 = 0, s1 = 0;
-  if (lane < NB) {
-#pragma unroll 1
-    for (int k = 0; k < 2 + 4 * lane; k++) s0 += __float_as_int(sm.man[k * MAN_WORDS]);
-    s1 = s0 + __float_as_int(sm.man[(2 + 4 * lane) * MAN_WORDS]) + __float_as_int(sm.man[(3 + 4 * lane) * MAN_WORDS]);
-    if (s1 > s0 + 4) s1 = s0 + 4;                             // 4 static slots per block (see contact_row_setup_multi)
-    s0 = s0 < nrow ? s0 : nrow; s1 = s1 < nrow ? s1 : nrow;  // points beyond the pool were dropped
-  }
+  const int s0 = srange & 0xff, s1 = srange >> 8;
+  float sn[4];  // normal impulses of this lane's static points after the normal pass
   const float* srow = sm.srow((lane < NB ? lane : 0) * 12);  // this lane's compact static rows: [slot * 3 + kk][12]
   // ---- normal rows ----
-#pragma unroll 1
-  for (int c = s0; c < s1; c++) {  // static: the block is end B (it sees -impulse)
-    const float* row = srow + (c - s0) * 3 * SM::SROW_W;
-    const float4 d = ld4(row), xb = ld4(row + 4);  // d.w = rhs, xb.w = 1 / denominator
-    const float denom = row[8];
-    const float v = -((d.x * bd[0] + d.y * bd[1] + d.z * bd[2]) + (xb.x * bd[3] + xb.y * bd[4] + xb.z * bd[5]));
-    const float app = app_rd[c * 3];
-    float dl = d.w - v * xb.w;
-    const float sum = fminf(fmaxf(app + dl, 0.0f), 1e10f);
-    dl = sum - app;
-    const float lm = dl * BLOCK_INV_MASS, li = dl * BLOCK_INV_INERTIA;
-    bd[0] -= lm * d.x; bd[1] -= lm * d.y; bd[2] -= lm * d.z; bd[3] -= li * xb.x; bd[4] -= li * xb.y; bd[5] -= li * xb.z;
-    const float rr = dl * denom;
-    cres = fmaxf(cres, rr * rr);
-    app_wr[c * 3] = sum;
+  // static: the block is end B (it sees -impulse).  At most 4 points per block (contact_row_setup_static): the records
+  // are fetched up front -- they do not depend on the velocities -- so that only the arithmetic sits on the dependent
+  // chain from one row to the next.
+  {
+    float4 D[4], X[4];
+    float den[4], ap[4];
+#pragma unroll
+    for (int i = 0; i < 4; i++)
+      if (s0 + i < s1) {
+        const float* row = srow + i * 3 * SM::SROW_W;
+        D[i] = ld4(row); X[i] = ld4(row + 4); den[i] = row[8]; ap[i] = app_rd[(s0 + i) * 3];  // D.w = rhs, X.w = 1 / denominator
+      }
+#pragma unroll
+    for (int i = 0; i < 4; i++)
+      if (s0 + i < s1) {
+        const float4 d = D[i], xb = X[i];
+        const float v = -((d.x * bd[0] + d.y * bd[1] + d.z * bd[2]) + (xb.x * bd[3] + xb.y * bd[4] + xb.z * bd[5]));
+        float dl = d.w - v * xb.w;
+        const float sum = fminf(fmaxf(ap[i] + dl, 0.0f), 1e10f);
+        dl = sum - ap[i];
+        const float lm = dl * BLOCK_INV_MASS, li = dl * BLOCK_INV_INERTIA;
+        bd[0] -= lm * d.x; bd[1] -= lm * d.y; bd[2] -= lm * d.z; bd[3] -= li * xb.x; bd[4] -= li * xb.y; bd[5] -= li * xb.z;
+        const float rr = dl * den[i];
+        cres = fmaxf(cres, rr * rr);
+        app_wr[(s0 + i) * 3] = sum;
+        ap[i] = sum;  // the normal impulse the friction rows of this point are bounded by
+      }
+    // the friction records of the static points, fetched while the general normal rows run
+#pragma unroll
+    for (int i = 0; i < 4; i++) { sn[i] = s0 + i < s1 ? ap[i] : 0.0f; }
   }
   // velocity of a general row's block ends: + end A, - end B
   auto block_vel = [&](const float4& d, const float4& xa, const float4& xb, int ia, int ib) {
@@ -910,77 +945,76 @@ __device__ __noinline__ float contact_sweep_multi(Grp g, SM& sm, int nrow_it) { 
   };
   // the other rows, in pair order, by the whole octet (the pair counts are uniform over the octet)
   {
-    int c = 0, gi = 0;  // point index in pair order (impulse arrays), index among the general points (row records)
+    const int nsh = ngen < SM::SPTS ? ngen : SM::SPTS;
 #pragma unroll 1
-    for (int k = 0; k < SM::NPAIRS && c < nrow; k++) {
-      const int n = __float_as_int(sm.man[k * MAN_WORDS]);
-      if (static_pair<NB>(k)) { c += n; continue; }
-      const int e = c + n < nrow ? c + n : nrow;
+    for (int gi = 0; gi < nsh; gi++) normal_row(sm.rows[gi * 3], sm.glist[gi]);  // glist: point index (impulse arrays)
 #pragma unroll 1
-      for (; c < e; c++, gi++) {
-        if (gi < SM::SPTS) normal_row(sm.rows[gi * 3], c);
-        else normal_row(sm.spill_row(gi * 3), c);
-      }
-    }
+    for (int gi = SM::SPTS; gi < ngen; gi++) normal_row(sm.spill_row(gi * 3), sm.glist[gi]);
   }
-  g.sync();  // app_wr of the normal rows is read (by other lanes too) below
+  // (no barrier: a static point's impulses are private to its lane, a general point's are written identically by all)
   // ---- friction rows: the two tangent rows of a point projected together onto the cone ----
-#pragma unroll 1
-  for (int c = s0; c < s1; c++) {
-    const float total = app_wr[c * 3];
-    const float appA = app_rd[c * 3 + 1], appB = app_rd[c * 3 + 2];
-    float sA = appA, sB = appB;
-    if (total > 0.0f) {
-      const float* ra = srow + ((c - s0) * 3 + 1) * SM::SROW_W;
-      const float* rb = ra + SM::SROW_W;
-      const float4 da = ld4(ra), xba = ld4(ra + 4), db = ld4(rb), xbb = ld4(rb + 4);
-      const float2 ma = *reinterpret_cast<const float2*>(ra + 8);  // denominator, friction coefficient
-      const float denB = rb[8];
-      const float vA = -((da.x * bd[0] + da.y * bd[1] + da.z * bd[2]) + (xba.x * bd[3] + xba.y * bd[4] + xba.z * bd[5]));
-      const float vB = -((db.x * bd[0] + db.y * bd[1] + db.z * bd[2]) + (xbb.x * bd[3] + xbb.y * bd[4] + xbb.z * bd[5]));
-      const float lim = ma.y * total;
-      float dA = da.w - vA * xba.w, dB = db.w - vB * xbb.w;
-      sA = appA + dA; sB = appB + dB;
-      const float s2 = sA * sA + sB * sB;
-      if (s2 >= lim * lim) {
-        const float sc = s2 > 0.0f ? lim * rsqrtf(s2) : 0.0f;
-        const float cA = fabsf(sA) * sc, cB = s2 > 0.0f ? fabsf(sB) * sc : lim;
-        sA = fminf(fmaxf(sA, -cA), cA);
-        sB = fminf(fmaxf(sB, -cB), cB);
-        dA = sA - appA; dB = sB - appB;
+  {
+    float4 DA[4], XA[4], DB[4], XB[4];
+    float2 MA[4];
+    float denB[4], apA[4], apB[4];
+#pragma unroll
+    for (int i = 0; i < 4; i++)
+      if (s0 + i < s1) {
+        const float* ra = srow + (i * 3 + 1) * SM::SROW_W;
+        const float* rb = ra + SM::SROW_W;
+        DA[i] = ld4(ra); XA[i] = ld4(ra + 4); DB[i] = ld4(rb); XB[i] = ld4(rb + 4);
+        MA[i] = *reinterpret_cast<const float2*>(ra + 8);  // denominator, friction coefficient
+        denB[i] = rb[8];
+        apA[i] = app_rd[(s0 + i) * 3 + 1]; apB[i] = app_rd[(s0 + i) * 3 + 2];
       }
-      const float lmA = dA * BLOCK_INV_MASS, liA = dA * BLOCK_INV_INERTIA, lmB = dB * BLOCK_INV_MASS, liB = dB * BLOCK_INV_INERTIA;
-      bd[0] -= lmA * da.x; bd[1] -= lmA * da.y; bd[2] -= lmA * da.z; bd[3] -= liA * xba.x; bd[4] -= liA * xba.y; bd[5] -= liA * xba.z;
-      bd[0] -= lmB * db.x; bd[1] -= lmB * db.y; bd[2] -= lmB * db.z; bd[3] -= liB * xbb.x; bd[4] -= liB * xbb.y; bd[5] -= liB * xbb.z;
-      const float r1_ = dA * ma.x, r2_ = dB * denB;
-      cres = fmaxf(cres, fmaxf(r1_ * r1_, r2_ * r2_));
-    }
-    app_wr[c * 3 + 1] = sA; app_wr[c * 3 + 2] = sB;
+#pragma unroll
+    for (int i = 0; i < 4; i++)
+      if (s0 + i < s1) {
+        const float total = sn[i];
+        float sA = apA[i], sB = apB[i];
+        if (total > 0.0f) {
+          const float4 da = DA[i], xba = XA[i], db = DB[i], xbb = XB[i];
+          const float vA = -((da.x * bd[0] + da.y * bd[1] + da.z * bd[2]) + (xba.x * bd[3] + xba.y * bd[4] + xba.z * bd[5]));
+          const float vB = -((db.x * bd[0] + db.y * bd[1] + db.z * bd[2]) + (xbb.x * bd[3] + xbb.y * bd[4] + xbb.z * bd[5]));
+          const float lim = MA[i].y * total;
+          float dA = da.w - vA * xba.w, dB = db.w - vB * xbb.w;
+          sA = apA[i] + dA; sB = apB[i] + dB;
+          const float s2 = sA * sA + sB * sB;
+          if (s2 >= lim * lim) {
+            const float sc = s2 > 0.0f ? lim * rsqrtf(s2) : 0.0f;
+            const float cA = fabsf(sA) * sc, cB = s2 > 0.0f ? fabsf(sB) * sc : lim;
+            sA = fminf(fmaxf(sA, -cA), cA);
+            sB = fminf(fmaxf(sB, -cB), cB);
+            dA = sA - apA[i]; dB = sB - apB[i];
+          }
+          const float lmA = dA * BLOCK_INV_MASS, liA = dA * BLOCK_INV_INERTIA, lmB = dB * BLOCK_INV_MASS, liB = dB * BLOCK_INV_INERTIA;
+          bd[0] -= lmA * da.x; bd[1] -= lmA * da.y; bd[2] -= lmA * da.z; bd[3] -= liA * xba.x; bd[4] -= liA * xba.y; bd[5] -= liA * xba.z;
+          bd[0] -= lmB * db.x; bd[1] -= lmB * db.y; bd[2] -= lmB * db.z; bd[3] -= liB * xbb.x; bd[4] -= liB * xbb.y; bd[5] -= liB * xbb.z;
+          const float r1_ = dA * MA[i].x, r2_ = dB * denB[i];
+          cres = fmaxf(cres, fmaxf(r1_ * r1_, r2_ * r2_));
+        }
+        app_wr[(s0 + i) * 3 + 1] = sA; app_wr[(s0 + i) * 3 + 2] = sB;
+      }
   }
   {
-    int c = 0, gi = 0;
+    const int nsh = ngen < SM::SPTS ? ngen : SM::SPTS;
 #pragma unroll 1
-    for (int k = 0; k < SM::NPAIRS && c < nrow; k++) {
-      const int n = __float_as_int(sm.man[k * MAN_WORDS]);
-      if (static_pair<NB>(k)) { c += n; continue; }
-      const int e = c + n < nrow ? c + n : nrow;
+    for (int gi = 0; gi < nsh; gi++) friction_rows(sm.rows[gi * 3 + 1], sm.rows[gi * 3 + 2], sm.glist[gi]);
 #pragma unroll 1
-      for (; c < e; c++, gi++) {
-        if (gi < SM::SPTS) friction_rows(sm.rows[gi * 3 + 1], sm.rows[gi * 3 + 2], c);
-        else friction_rows(sm.spill_row(gi * 3 + 1), sm.spill_row(gi * 3 + 2), c);
-      }
-    }
+    for (int gi = SM::SPTS; gi < ngen; gi++) friction_rows(sm.spill_row(gi * 3 + 1), sm.spill_row(gi * 3 + 2), sm.glist[gi]);
   }
-  g.sync();  // every lane has read sm.vq
-  if (lane == 0) {
-#pragma unroll
-    for (int j = 0; j < ND; j++) sm.vq[j] = dq[j];
-  }
-  if (lane < NB) {
+  if (lane < NB) {  // private to the lane: read back by the same lane in the next iteration / at the integration
 #pragma unroll
     for (int j = 0; j < 6; j++) sm.vq[ND + 6 * lane + j] = bd[j];
   }
-  g.sync();
+  if (ngen) {
+    g.sync();  // every lane has read sm.vq
+    if (lane == 0) {
+#pragma unroll
+      for (int j = 0; j < ND; j++) sm.vq[j] = dq[j];
+    }
+    g.sync();
+  }
   return cres;
 }
 
@@ -1148,14 +1182,16 @@ __device__ void substep(const Grp& g, SM& sm, Lane& L) {
       const float fc[3] = PMG_FLOOR_CENTER;
       const float* bk = sm.blk;
       const bool fingerA = pi.ka == G_FINGER1 || pi.ka == G_FINGER2;
-      V3 pa = fingerA ? (pi.ka == G_FINGER1 ? pf1 : pf2) : (pi.ka == G_TABLE ? v3(tc[0], tc[1], tc[2]) : v3(fc[0], fc[1], fc[2]));
+      const V3 tcv = table_center(SM::PUCK);  // Slide: the long table
+      V3 pa = fingerA ? (pi.ka == G_FINGER1 ? pf1 : pf2) : (pi.ka == G_TABLE ? tcv : v3(fc[0], fc[1], fc[2]));
       M3 Ra = fingerA ? Rg : m3_identity();
-      V3 pb = pi.kb == G_TABLE ? v3(tc[0], tc[1], tc[2]) : v3(bk[BK_POS], bk[BK_POS + 1], bk[BK_POS + 2]);
+      V3 pb = pi.kb == G_TABLE ? tcv : v3(bk[BK_POS], bk[BK_POS + 1], bk[BK_POS + 2]);
       M3 Rb = m3_identity();
       if (pi.kb == G_BLOCK) {
         Rb.r0 = v3(bk[BK_R], bk[BK_R + 1], bk[BK_R + 2]); Rb.r1 = v3(bk[BK_R + 3], bk[BK_R + 4], bk[BK_R + 5]); Rb.r2 = v3(bk[BK_R + 6], bk[BK_R + 7], bk[BK_R + 8]);
       }
-      collide_pair(mr, lane, pa, Ra, geom_half(pi.ka), geom_anchor(pi.ka), geom_static(pi.ka), pb, Rb, geom_half(pi.kb), geom_anchor(pi.kb), scr);
+      collide_pair(mr, lane, pa, Ra, geom_half(pi.ka, SM::PUCK), geom_anchor(pi.ka), geom_static(pi.ka), pb, Rb, geom_half(pi.kb, SM::PUCK), geom_anchor(pi.kb), scr,
+                   SM::PUCK && pi.kb == G_BLOCK);
     }
   }
   PMG_T(t_col1);
@@ -1239,6 +1275,14 @@ __device__ void substep(const Grp& g, SM& sm, Lane& L) {
   if (BLK && (MULTI ? lane < SM::NB : lane == 0)) {  // free cube: gravity + Bullet's velocity damping; isotropic inertia => no gyro term
     float* bk = sm.blk + (MULTI ? 24 * lane : 0);
     V3 bv = v3(bk[BK_V], bk[BK_V + 1], bk[BK_V + 2]), bw = v3(bk[BK_W], bk[BK_W + 1], bk[BK_W + 2]);
+    if constexpr (SM::PUCK) {
+      // anisotropic inertia: the gyroscopic term alpha = -I^-1 (w x I w), I = i1 + (i3 - i1) a a^T about the puck's axis a
+      // (w x I w = (i3 - i1)(a.w) w x a; I^-1 y = y / i1 + (1/i3 - 1/i1)(a.y) a and a . (w x a) = 0)
+      const float pin[3] = PMG_PUCK_INERTIA;
+      const V3 axb = v3(bk[BK_R + 2], bk[BK_R + 5], bk[BK_R + 8]);
+      const V3 g = ((pin[2] - pin[0]) * dot(axb, bw)) * cross(bw, axb);
+      bw -= (DT / pin[0]) * g;
+    }
     const float kl = LINK_DAMPING + LINK_DAMPING * norm(bv), ka = LINK_DAMPING + LINK_DAMPING * norm(bw);
     bv += DT * (v3(0, 0, -GRAVITY) - kl * bv);
     bw -= (DT * ka) * bw;
@@ -1285,6 +1329,8 @@ __device__ void substep(const Grp& g, SM& sm, Lane& L) {
   const int n0 = __float_as_int(sm.man[0]);
   int nrow = n0 + __float_as_int(sm.man[MAN_WORDS]);  // number of cached contact points (3 rows each)
   int row_kinds = 0;                                  // (first point with a block end) << 16 | (first with both ends) << 24
+  int ngen = 0, srange = 0;                           // multi-block scenes: general points, this lane's static points
+  int st0[SM::NB > 1 ? SM::NB : 1], ntab[SM::NB > 1 ? SM::NB : 1], nst[SM::NB > 1 ? SM::NB : 1];  // per block: first static point, table points, static points kept
   if (BLK) {
     row_kinds = nrow << 16;
 #pragma unroll
@@ -1296,13 +1342,48 @@ __device__ void substep(const Grp& g, SM& sm, Lane& L) {
       if (lane == 0) sm.blk[23] += (float)(nrow - SM::MAXPTS);
       nrow = SM::MAXPTS;
     }
-    if constexpr (MULTI) {  // ... and so are static points beyond a block's 4 compact slots (table and floor at once)
-      if (lane == 0) {
+    if constexpr (MULTI) {
+      // Point classes, once per substep, in registers: per block the run of its STATIC points (table-block, then
+      // floor-block; at most 4 slots -- points beyond them, i.e. table and floor at once, are dropped and counted
+      // like the pool overflow) and the number of the other ("general") points.
+      constexpr int NBK = SM::NB;
+      int c = 0;
+#pragma unroll
+      for (int b = 0; b < NBK; b++) { st0[b] = 0; ntab[b] = 0; nst[b] = 0; }
+#pragma unroll
+      for (int k = 0; k < SM::NPAIRS; k++) {
+        const int n = __float_as_int(sm.man[k * MAN_WORDS]);
+        int ne = nrow - c;  // points beyond the pool were dropped
+        ne = ne < 0 ? 0 : (ne < n ? ne : n);
+        if (static_pair<NBK>(k)) {
+          const int b = (k - 2) >> 2;
+          if (((k - 2) & 3) == 0) { st0[b] = c; ntab[b] = ne; nst[b] = ne; }
+          else {
+            if (lane == 0 && nst[b] + ne > 4) sm.blk[23] += (float)(nst[b] + ne - 4);
+            nst[b] = nst[b] + ne < 4 ? nst[b] + ne : 4;
+          }
+        } else ngen += ne;
+        c += n;
+      }
+      int s0 = 0, s1 = 0;
+#pragma unroll
+      for (int b = 0; b < NBK; b++) if (lane == b) { s0 = st0[b]; s1 = st0[b] + nst[b]; }
+      srange = s0 | (s1 << 8);
+      if (ngen) {  // rare in a scene at rest: a finger on a block or on the table, stacked blocks
+        if (lane == 0) {
+          int c2 = 0, g2 = 0;
 #pragma unroll 1
-        for (int b = 0; b < SM::NB; b++) {
-          const int n = __float_as_int(sm.man[(2 + 4 * b) * MAN_WORDS]) + __float_as_int(sm.man[(3 + 4 * b) * MAN_WORDS]);
-          if (n > 4) sm.blk[23] += (float)(n - 4);
+          for (int k = 0; k < SM::NPAIRS; k++) {
+            const int n = __float_as_int(sm.man[k * MAN_WORDS]);
+            if (!static_pair<NBK>(k))
+              for (int i = 0; i < n && c2 + i < nrow; i++) {
+                sm.glist[g2] = (unsigned char)(c2 + i); sm.ppair[g2] = (unsigned char)k; sm.pidx[g2] = (unsigned char)i;
+                g2++;
+              }
+            c2 += n;
+          }
         }
+        g.sync();  // the general-point tables are read by the row set-up of every lane
       }
     }
   }
@@ -1311,10 +1392,18 @@ __device__ void substep(const Grp& g, SM& sm, Lane& L) {
     if constexpr (!BLK) {
       if (lane < nrow) contact_row_setup(sm, lane, n0);
     } else {
-      for (int c = lane; c < nrow; c += GL) {
-        if constexpr (MULTI) {
-          contact_row_setup_multi(sm, c);
-        } else {
+      if constexpr (MULTI) {
+        // static slot s = 4 b + slot over the lanes (a scene at rest: 16 slots, two per lane), then the general points
+        for (int sidx = lane; sidx < SM::NB * 4; sidx += GL) {
+          const int b = sidx >> 2, slot = sidx & 3;
+          int b0 = 0, nt = 0, ns = 0;
+#pragma unroll
+          for (int bb = 0; bb < SM::NB; bb++) if (bb == b) { b0 = st0[bb]; nt = ntab[bb]; ns = nst[bb]; }
+          if (slot < ns) contact_row_setup_static(sm, b0 + slot, b, slot, slot < nt ? 2 + 4 * b : 3 + 4 * b, slot < nt ? slot : slot - nt);
+        }
+        for (int gi = lane; gi < ngen; gi += GL) contact_row_setup_general(sm, gi);
+      } else {
+        for (int c = lane; c < nrow; c += GL) {
           if (c < SM::SPTS) contact_row_setup_blk<false>(sm, c);
           else contact_row_setup_blk<true>(sm, c);
         }
@@ -1340,18 +1429,24 @@ __device__ void substep(const Grp& g, SM& sm, Lane& L) {
     const float e0 = s.big0 * s.mdd0, e1 = s.big1 * s.mdd1;
     float res = fmaxf(e0 * e0, e1 * e1);
     if (nrow) {
-      // gather the delta velocities, run the contact rows replicated, take the own components back
-      sm.vq[L.dof0] = s.dqd0;
-      if (hand) sm.vq[8] = s.dqd1;
-      g.sync();
+      // gather the delta velocities, run the contact rows replicated, take the own components back (multi-block scenes
+      // whose points are all static leave the joints alone: no exchange, no barriers)
+      const bool joints = !MULTI || ngen != 0;
+      if (joints) {
+        sm.vq[L.dof0] = s.dqd0;
+        if (hand) sm.vq[8] = s.dqd1;
+        g.sync();
+      }
       PMG_T(t_sw0);
-      if constexpr (MULTI) res = fmaxf(res, contact_sweep_multi(g, sm, nrow | ((it & 1) << 8)));
+      if constexpr (MULTI) res = fmaxf(res, contact_sweep_multi(g, sm, ((it & 1) << 8) | (ngen << 16), srange));
       else res = fmaxf(res, contact_sweep(g, sm, nrow | ((it & 1) << 8) | row_kinds));
 #ifdef PMG_COOP_TIMING
       t_sweeps += clock64() - t_sw0;
 #endif
-      s.dqd0 = sm.vq[L.dof0];
-      s.dqd1 = sm.vq[8];
+      if (joints) {
+        s.dqd0 = sm.vq[L.dof0];
+        s.dqd1 = sm.vq[8];
+      }
     }
     res = g.maxv(res);
     if (res <= RESIDUAL_THRESHOLD) break;
@@ -1365,7 +1460,9 @@ __device__ void substep(const Grp& g, SM& sm, Lane& L) {
     float* bk = sm.blk + (MULTI ? 24 * lane : 0);
     const float* dv = sm.vq + (BLK ? ND : 0) + (MULTI ? 6 * lane : 0);
     V3 bv = v3(bk[BK_V] + dv[0], bk[BK_V + 1] + dv[1], bk[BK_V + 2] + dv[2]);
-    V3 bw = v3(bk[BK_W] + dv[3], bk[BK_W + 1] + dv[4], bk[BK_W + 2] + dv[5]);
+    V3 dw = v3(dv[3], dv[4], dv[5]);
+    if constexpr (SM::PUCK) dw = puck_scale(dw, v3(bk[BK_R + 2], bk[BK_R + 5], bk[BK_R + 8]));  // the sweeps solved for S^-1 dw
+    V3 bw = v3(bk[BK_W] + dw.x, bk[BK_W + 1] + dw.y, bk[BK_W + 2] + dw.z);
     bk[BK_V] = bv.x; bk[BK_V + 1] = bv.y; bk[BK_V + 2] = bv.z; bk[BK_W] = bw.x; bk[BK_W + 1] = bw.y; bk[BK_W + 2] = bw.z;
     bk[BK_POS] += DT * bv.x; bk[BK_POS + 1] += DT * bv.y; bk[BK_POS + 2] += DT * bv.z;
     float w = norm(bw);
@@ -1485,13 +1582,14 @@ __device__ void step_env_reach(const Grp& g, EnvSmem& sm, const float* lane_cons
   gather_push(g, io, env);
 }
 
-// ---- one env.step() of a one-block environment: Push (TASK 1) / PickAndPlace (TASK 2) -----------------------
+// ---- one env.step() of a one-block environment: Push (TASK 1) / PickAndPlace (TASK 2) / Slide (TASK 5) -----
 // Same structure as step_env_reach; the block's state and its four extra manifolds live in shared memory for
-// the whole step.  Cartesian control only (joint control runs on the thread-per-env kernel).
+// the whole step.  Slide (kuka_single_step_envs.py:49-59) is Push on the long table with the puck: the same
+// action map, observation and reward, EnvSmemT<1, true> selects its geometry and inertia.
 template <int TASK>
-__device__ void step_env_block(const Grp& g, EnvSmemT<1>& sm, const float* lane_consts, const StepIO& io, int env) {
-  using SM = EnvSmemT<1>;
-  using D = Dims<TASK, 1>;
+__device__ void step_env_block(const Grp& g, EnvSmemT<1, TASK == 5>& sm, const float* lane_consts, const StepIO& io, int env) {
+  using SM = EnvSmemT<1, TASK == 5>;
+  using D = Dims<TASK == 5 ? 1 : TASK, 1>;
   const int lane = g.lane;
   const bool arm = lane < 7, hand = lane == 7;
   const size_t B = io.batch;

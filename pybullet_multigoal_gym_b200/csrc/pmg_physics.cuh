@@ -720,6 +720,130 @@ __device__ int box_box(V3 p1, const M3& R1, V3 A, V3 p2, const M3& R2, V3 B, Box
   return maxc;
 }
 
+// ---- box (A) against a cylinder (B, axis = its local z): the Slide puck -----------------------------------------
+// A model of the pair, not a restatement of Bullet's GJK/EPA path (see DESIGN.md on the puck model,
+// Slide): separating-axis choice between the cylinder axis (a cap against a box face) and the radial direction (the
+// curved side against the box), then
+//   cap - face : the rim points of that cap at four azimuths fixed in the cylinder (+-x, +-y), plus the deepest rim
+//                point once the cap is tilted by more than ~1 degree, kept when they lie over the face and penetrate
+//                it, and the corners of the face inside the cap disc; normal = the face normal; <= 4 points (the
+//                deepest, then the ones farthest from those already kept);
+//   side       : the closest points of the box to the cylinder axis at the two ends of their common height range.
+// Depths are taken relative to the centre of the box face (one rounding common to all points, as in box_box).
+// Output convention of box_box: point on B, normal on B (pointing from B towards A), signed distance (<= 0).
+__device__ int box_cyl(V3 pa, const M3& Ra, V3 ha, V3 pb, const M3& Rb, float r, float h, Contact* out) {
+  const V3 cb = mulT(Rb, pa - pb);                           // box centre in the cylinder frame
+  V3 Aq[3];                                                  // box axes in the cylinder frame
+  Aq[0] = mulT(Rb, col(Ra, 0)); Aq[1] = mulT(Rb, col(Ra, 1)); Aq[2] = mulT(Rb, col(Ra, 2));
+  const float hav[3] = {ha.x, ha.y, ha.z};
+  const float ez = ha.x * fabsf(Aq[0].z) + ha.y * fabsf(Aq[1].z) + ha.z * fabsf(Aq[2].z);   // box extent along the axis
+  const float scap = cb.z >= 0.0f ? 1.0f : -1.0f;            // the cap on the box's side
+  const float sep_cap = scap * cb.z - ez - h;
+  if (sep_cap > 0.0f) return 0;
+  const float z0 = fmaxf(cb.z - ez, -h), z1 = fminf(cb.z + ez, h);
+  const float zs[2] = {z0 + 0.05f * (z1 - z0), z1 - 0.05f * (z1 - z0)};
+  V3 qs[2];
+  float rho[2], sep_rad = 1e30f;
+#pragma unroll
+  for (int i = 0; i < 2; i++) {
+    const V3 rel = v3(-cb.x, -cb.y, zs[i] - cb.z);
+    V3 q = cb;
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+      const float loc = fminf(fmaxf(dot(rel, Aq[k]), -hav[k]), hav[k]);   // clamp in the box frame
+      q += loc * Aq[k];
+    }
+    qs[i] = q;
+    rho[i] = sqrtf(q.x * q.x + q.y * q.y);
+    sep_rad = fminf(sep_rad, rho[i] - r);
+  }
+  if (sep_rad > 0.0f) return 0;
+  int n = 0;
+  if (sep_cap >= sep_rad) {
+    // ---- cap against the box face whose outward normal opposes the cap normal most ----
+    int fj = 0;
+    float best = fabsf(Aq[0].z);
+    if (fabsf(Aq[1].z) > best) { best = fabsf(Aq[1].z); fj = 1; }
+    if (fabsf(Aq[2].z) > best) { best = fabsf(Aq[2].z); fj = 2; }
+    const int k1 = (fj + 1) % 3, k2 = (fj + 2) % 3;
+    const V3 af = fj == 0 ? Aq[0] : (fj == 1 ? Aq[1] : Aq[2]);
+    const V3 a1 = k1 == 0 ? Aq[0] : (k1 == 1 ? Aq[1] : Aq[2]), a2 = k2 == 0 ? Aq[0] : (k2 == 1 ? Aq[1] : Aq[2]);
+    const float hf = hav[fj], h1 = hav[k1], h2 = hav[k2];
+    const float sig = af.z * scap > 0.0f ? -1.0f : 1.0f;     // the face looks against the cap normal
+    const V3 nf = sig * af;                                  // outward face normal, cylinder frame
+    const V3 fc = cb + (sig * hf) * af;                      // centre of that face
+    float cand[9][4];                                        // point on B (cylinder frame), distance
+    int nc = 0;
+    const float tx = -nf.x, ty = -nf.y, tn = sqrtf(tx * tx + ty * ty);
+    const int nu = tn > 0.02f ? 5 : 4;                       // tilted by more than ~1 degree: the lowest rim point matters
+#pragma unroll 1
+    for (int i = 0; i < nu; i++) {
+      const float ux = i == 0 ? 1.0f : (i == 1 ? -1.0f : (i < 4 ? 0.0f : tx / tn));
+      const float uy = i < 2 ? 0.0f : (i == 2 ? 1.0f : (i == 3 ? -1.0f : ty / tn));
+      const V3 p = v3(r * ux, r * uy, scap * h), rel = p - fc;
+      if (fabsf(dot(rel, a1)) > h1 || fabsf(dot(rel, a2)) > h2) continue;
+      const float dist = dot(rel, nf);
+      if (dist > 0.0f) continue;
+      cand[nc][0] = p.x; cand[nc][1] = p.y; cand[nc][2] = p.z; cand[nc][3] = dist;
+      nc++;
+    }
+    const float ncn = -(nf.z * scap);                        // n . cap normal with n = -nf
+    if (ncn > 1e-6f) {
+#pragma unroll 1
+      for (int i = 0; i < 4; i++) {                          // corners of the face inside the cap disc
+        const V3 v = fc + ((i & 1) ? h1 : -h1) * a1 + ((i & 2) ? h2 : -h2) * a2;
+        const float dist = (v.z - scap * h) * scap / ncn;    // along n = -nf
+        if (dist > 0.0f) continue;
+        const V3 pB = v + dist * nf;                         // pB = pA - dist n
+        if (pB.x * pB.x + pB.y * pB.y > r * r) continue;
+        cand[nc][0] = pB.x; cand[nc][1] = pB.y; cand[nc][2] = pB.z; cand[nc][3] = dist;
+        nc++;
+      }
+    }
+    int keep[4];
+    unsigned used = 0;
+#pragma unroll 1
+    for (int m = 0; m < 4 && m < nc; m++) {
+      int bi = -1;
+      float bv = -1e30f;
+#pragma unroll 1
+      for (int i = 0; i < nc; i++) {
+        if (used & (1u << i)) continue;
+        float score;
+        if (m == 0) score = -cand[i][3];
+        else {
+          score = 1e30f;
+          for (int j = 0; j < m; j++) {
+            const float e0 = cand[i][0] - cand[keep[j]][0], e1 = cand[i][1] - cand[keep[j]][1], e2 = cand[i][2] - cand[keep[j]][2];
+            score = fminf(score, e0 * e0 + e1 * e1 + e2 * e2);
+          }
+          if (score < 1e-10f) continue;                      // coincides with a kept point
+        }
+        if (score > bv) { bv = score; bi = i; }
+      }
+      if (bi < 0) break;
+      used |= 1u << bi; keep[m] = bi;
+      out[n].pB = pb + mul(Rb, v3(cand[bi][0], cand[bi][1], cand[bi][2]));
+      out[n].nB = mul(Rb, -nf);
+      out[n].dist = cand[bi][3];
+      n++;
+    }
+    return n;
+  }
+  // ---- curved side against the box ----
+#pragma unroll
+  for (int i = 0; i < 2; i++) {
+    if (rho[i] - r > 0.0f || rho[i] < 1e-9f) continue;
+    if (i == 1 && fabsf(zs[1] - zs[0]) < 1e-6f) break;
+    const V3 nl = v3(qs[i].x / rho[i], qs[i].y / rho[i], 0.0f);
+    out[n].pB = pb + mul(Rb, v3(nl.x * r, nl.y * r, qs[i].z));
+    out[n].nB = mul(Rb, nl);
+    out[n].dist = rho[i] - r;
+    n++;
+  }
+  return n;
+}
+
 __device__ __forceinline__ void plane_space(V3 n, V3& p, V3& q) {  // btPlaneSpace1
   if (fabsf(n.z) > 0.70710678118654752440f) {
     float a = n.y * n.y + n.z * n.z, k = 1.0f / sqrtf(a);

@@ -43,15 +43,21 @@ __device__ __forceinline__ PairInfo pair_info(int k) {
   return p;
 }
 
-__device__ __forceinline__ V3 geom_half(int kind) {
-  const float th[3] = PMG_TABLE_HALF, fh[3] = PMG_FLOOR_HALF, gh[3] = PMG_FINGER_HALF;
-  if (kind == G_TABLE) return v3(th[0], th[1], th[2]);
+// puck: the Slide scene (long low-friction table, the block is a cylinder about its z axis: half = (r, r, h))
+__device__ __forceinline__ V3 geom_half(int kind, bool puck = false) {
+  const float th[3] = PMG_TABLE_HALF, lh[3] = PMG_LONG_TABLE_HALF, fh[3] = PMG_FLOOR_HALF, gh[3] = PMG_FINGER_HALF;
+  if (kind == G_TABLE) return puck ? v3(lh[0], lh[1], lh[2]) : v3(th[0], th[1], th[2]);
   if (kind == G_FLOOR) return v3(fh[0], fh[1], fh[2]);
-  if (kind == G_BLOCK) return v3(BLOCK_HALF, BLOCK_HALF, BLOCK_HALF);
+  if (kind == G_BLOCK) return puck ? v3((float)PMG_PUCK_RADIUS, (float)PMG_PUCK_RADIUS, (float)PMG_PUCK_HALF_LEN) : v3(BLOCK_HALF, BLOCK_HALF, BLOCK_HALF);
   return v3(gh[0], gh[1], gh[2]);
 }
-__device__ __forceinline__ float geom_friction(int kind) {
-  if (kind == G_TABLE) return (float)PMG_TABLE_FRICTION;
+__device__ __forceinline__ V3 table_center(bool puck = false) {
+  const float tc[3] = PMG_TABLE_CENTER, lc[3] = PMG_LONG_TABLE_CENTER;
+  return puck ? v3(lc[0], lc[1], lc[2]) : v3(tc[0], tc[1], tc[2]);
+}
+__device__ __forceinline__ float geom_friction(int kind, bool puck = false) {
+  if (kind == G_TABLE) return puck ? (float)PMG_LONG_TABLE_FRICTION : (float)PMG_TABLE_FRICTION;
+  if (kind == G_BLOCK && puck) return (float)PMG_PUCK_FRICTION;
   if (kind == G_FLOOR) return (float)PMG_FLOOR_FRICTION;
   if (kind == G_BLOCK) return (float)PMG_BLOCK_FRICTION;
   return (float)PMG_FINGER_FRICTION;
@@ -164,7 +170,9 @@ __device__ unsigned long long g_coop_cycles[16];
 // (geom_anchor, world axes: static boxes are axis aligned) the manifold-local coordinates refer to.  The
 // narrowphase and the manifold run in coordinates relative to the static box's anchor (else to B's centre),
 // so that penetration depths are differences of small numbers.
-__device__ void collide_pair(ManRef& e, int k, V3 pa, const M3& Ra, V3 ha, V3 aA, bool a_static, V3 pb, const M3& Rb, V3 hb, V3 aB, BoxScratch& scr) {
+// cylB: body B is the Slide puck (a cylinder about its z axis, hb = (r, r, h)): box_cyl instead of box_box.
+__device__ void collide_pair(ManRef& e, int k, V3 pa, const M3& Ra, V3 ha, V3 aA, bool a_static, V3 pb, const M3& Rb, V3 hb, V3 aB, BoxScratch& scr,
+                             bool cylB = false) {
   V3 d = pa - pb;
   float ex = fabsf(Ra.r0.x) * ha.x + fabsf(Ra.r0.y) * ha.y + fabsf(Ra.r0.z) * ha.z + fabsf(Rb.r0.x) * hb.x + fabsf(Rb.r0.y) * hb.y + fabsf(Rb.r0.z) * hb.z + 2 * BROADPHASE_MARGIN;
   float ey = fabsf(Ra.r1.x) * ha.x + fabsf(Ra.r1.y) * ha.y + fabsf(Ra.r1.z) * ha.z + fabsf(Rb.r1.x) * hb.x + fabsf(Rb.r1.y) * hb.y + fabsf(Rb.r1.z) * hb.z + 2 * BROADPHASE_MARGIN;
@@ -181,7 +189,7 @@ __device__ void collide_pair(ManRef& e, int k, V3 pa, const M3& Ra, V3 ha, V3 aA
 #ifdef PMG_COOP_TIMING
   const long long t0 = clock64();
 #endif
-  int nc = box_box(a0, Ra, ha, b0, Rb, hb, scr);
+  int nc = cylB ? box_cyl(a0, Ra, ha, b0, Rb, hb.x, hb.z, scr.out) : box_box(a0, Ra, ha, b0, Rb, hb, scr);
 #ifdef PMG_COOP_TIMING
   const long long t1 = clock64();
 #endif
@@ -604,6 +612,7 @@ struct StepIO {
   const float* action; float* obs; float* reward; uint8_t* done; uint8_t* success;
   float thr; int binary; int max_steps; int* overflow;
   int epw;  // environments per warp: lanes [0, epw) of every warp own one environment each
+  int epb;  // lane-cooperative kernels: environments (octets) per one-warp block, 4 / 2 / 1 (see coop_geometry)
   int bulk;         // 1: stage the state tile with TMA bulk copies (full warps only)
   int tile_offset;  // float offset of the state tile inside dynamic shared memory
   // run-time variants of a task (the block-stack kernels also serve block_rearrange):

@@ -68,14 +68,18 @@ struct Bounds { float tip[3], obj_lo[2], obj_hi[2], tgt_lo[3], tgt_hi[3]; };  //
 
 // Sampling boxes of a task: kuka.py:35-51 with obj_range = target_range = 0.15 (kuka_single_step_envs.py,
 // kuka_multi_step_envs.py:29), tip start 1 mm above the table for Push / BlockRearrange (kuka.py:37-38).  Host only.
+// Slide (task 5, kuka_single_step_envs.py:49-59, kuka_single_step_base_env.py:66-69): obj_range 0.1, target_range 0.2,
+// targets 0.4 further along -x (beyond the arm's reach).
 inline void task_bounds(int task, double tip[3], double obj_lo[3], double obj_hi[3], double tgt_lo[3], double tgt_hi[3]) {
-  tip[0] = -0.52; tip[1] = 0.0; tip[2] = (task == 1 || task == 4) ? 0.175 + 0.001 : 0.25;
+  tip[0] = -0.52; tip[1] = 0.0; tip[2] = (task == 1 || task == 4 || task == 5) ? 0.175 + 0.001 : 0.25;
+  const double obj_range = task == 5 ? 0.1 : 0.15, target_range = task == 5 ? 0.2 : 0.15;
   for (int k = 0; k < 3; k++) {
-    obj_lo[k] = tip[k] - 0.15; obj_hi[k] = tip[k] + 0.15;
-    tgt_lo[k] = tip[k] - 0.15; tgt_hi[k] = tip[k] + 0.15;
+    obj_lo[k] = tip[k] - obj_range; obj_hi[k] = tip[k] + obj_range;
+    tgt_lo[k] = tip[k] - target_range; tgt_hi[k] = tip[k] + target_range;
   }
   obj_lo[0] += 0.03; obj_hi[0] -= 0.03;
   tgt_lo[0] += 0.03; tgt_lo[2] = 0.175; tgt_hi[0] -= 0.03;
+  if (task == 5) { tgt_lo[0] -= 0.4; tgt_hi[0] -= 0.4; }
 }
 inline Bounds to_bounds(const double tip[3], const double obj_lo[3], const double obj_hi[3], const double tgt_lo[3], const double tgt_hi[3]) {
   Bounds b;
@@ -90,8 +94,8 @@ constexpr int MAX_TRIES = 64;  // rejection loops are bounded on the device; the
 // grip: grip-informed goal (block_stack).  Curriculum resets are host-only (their schedule lives on the host).
 PMG_HD void sample_row(Philox& r, int task, int nb, int grip, const Bounds& b, float* out) {
   const float R01 = 0.01f, R006 = 0.0036f, R008 = 0.0064f;  // 0.1^2, 0.06^2, 0.08^2 as float32 literals
-  const float Z0 = 0.175f;
-  if (task >= 3) {  // block_stack / block_rearrange
+  const float Z0 = task == 5 ? 0.17f : 0.175f;  // spawn height of the object: cube 0.175, Slide's puck 0.170 (kuka_single_step_base_env.py:50,56)
+  if (task == 3 || task == 4) {  // block_stack / block_rearrange
     for (int k = 0; k < nb; k++) {  // kuka_multi_step_base_env.py:223-240
       float x = 0.0f, y = 0.0f;
       for (int tries = 0; tries < MAX_TRIES; tries++) {
@@ -155,7 +159,7 @@ PMG_HD void sample_row(Philox& r, int task, int nb, int grip, const Bounds& b, f
     const float dz = PMG_FADD(g2, -cz);
     if (PMG_FADD(dist2(g0, g1, cx, cy), PMG_FMUL(dz, dz)) > R01) break;
   }
-  if (task == 1) g2 = Z0;                                   // push: on the table (:138-139)
+  if (task == 1 || task == 5) g2 = Z0;                      // push / slide: on the table (:138-139)
   else if (task == 2) { if (uniform(r, 0.0f, 1.0f) >= 0.5f) g2 = Z0; }  // pick_and_place: half of the goals on the table (:140-143)
   out[2 * nb] = g0; out[2 * nb + 1] = g1; out[2 * nb + 2] = g2;
 }

@@ -4,7 +4,7 @@ Mirrors (paths relative to /root/reference/pybullet_multigoal_gym/):
   envs/base_envs/base_env.py:120-138          seed / reset / step
   envs/base_envs/kuka_single_step_base_env.py:193-244   observation dict, _compute_reward
   envs/base_envs/kuka_multi_step_base_env.py:255-345    multi-block observation dict, reward
-  envs/task_envs/kuka_single_step_envs.py:4-46, kuka_multi_step_envs.py:6-32,151-189   task presets
+  envs/task_envs/kuka_single_step_envs.py:4-59, kuka_multi_step_envs.py:6-32,151-189   task presets
   robots/kuka.py:104-118,204-206                joint-space control variant (joint_control=True)
   envs/base_envs/kuka_multi_step_base_env.py:300-304   grip-informed goals (grip_informed_goal=True)
   gym 0.17.3 wrappers/time_limit.py           done = elapsed >= max_episode_steps
@@ -20,7 +20,7 @@ import torch
 
 from . import _lib, seeding, spaces
 
-TASK_IDS = {"reach": 0, "push": 1, "pick_and_place": 2, "block_stack": 3, "block_rearrange": 4}
+TASK_IDS = {"reach": 0, "push": 1, "pick_and_place": 2, "block_stack": 3, "block_rearrange": 4, "slide": 5}
 
 
 class StepDemonstrator:
@@ -482,6 +482,11 @@ class KukaPushEnv(KukaBulletMGEnv):  # kuka_single_step_envs.py:20-32
 class KukaPickAndPlaceEnv(KukaBulletMGEnv):  # kuka_single_step_envs.py:4-17
     def __init__(self, **kw):
         super().__init__("pick_and_place", **kw)
+
+
+class KukaSlideEnv(KukaBulletMGEnv):  # kuka_single_step_envs.py:49-59
+    def __init__(self, **kw):
+        super().__init__("slide", **kw)
 
 
 class KukaBlockStackEnv(KukaBulletMGEnv):  # kuka_multi_step_envs.py:6-32

@@ -35,7 +35,7 @@ def velocity_mask(task, num_block, row_width, joint_control=False):
     kuka_multi_step_base_env.py:276-283; joint control prepends the 7 joint poses, :214-216)."""
     vel = np.zeros(row_width, dtype=bool)
     jo = 7 if joint_control else 0
-    if task in ("push", "pick_and_place"):
+    if task in ("push", "pick_and_place", "slide"):
         vel[jo + 10:jo + 20] = True          # tip vel 3, finger vel 1, rel lin vel 3, rel ang vel 3
     elif task in ("block_stack", "block_rearrange"):
         vel[jo + 4:jo + 8] = True            # tip vel 3, finger vel 1

@@ -208,11 +208,12 @@ int pmg_emu_thread_substeps(int nblk, float* state, float* manifold, int n_calls
 
 // ---- the one-block cooperative step (Push / PickAndPlace) ------------------------------------------------------
 namespace {
-struct BlkArgs { coop::EnvSmemT<1>* sm; StepIO io; int task; };
+struct BlkArgs { coop::EnvSmemT<1>* sm; coop::EnvSmemT<1, true>* smp; StepIO io; int task; };
 void blk_body(int lane, void* arg) {
   BlkArgs* a = (BlkArgs*)arg;
   coop::Grp g; g.lane = lane;
   if (a->task == 1) coop::step_env_block<1>(g, *a->sm, lane_table(), a->io, 0);
+  else if (a->task == 5) coop::step_env_block<5>(g, *a->smp, lane_table(), a->io, 0);   // Slide: long table + puck
   else coop::step_env_block<2>(g, *a->sm, lane_table(), a->io, 0);
 }
 }  // namespace
@@ -223,9 +224,11 @@ extern "C" {
 int pmg_emu_block_step(int task, float* state, float* manifold, const float* action, float thr, int binary, int max_steps,
                        float* obs_row, float* reward, uint8_t* done, uint8_t* success) {
   static coop::EnvSmemT<1> sm;
+  static coop::EnvSmemT<1, true> smp;
   memset(&sm, 0, sizeof sm);
+  memset(&smp, 0, sizeof smp);
   BlkArgs a;
-  a.sm = &sm; a.task = task;
+  a.sm = &sm; a.smp = &smp; a.task = task;
   memset(&a.io, 0, sizeof a.io);
   a.io.state = state; a.io.manifold = manifold; a.io.batch = 1; a.io.state_words = Dims<1, 1>::STATE;
   a.io.action = action; a.io.obs = obs_row; a.io.reward = reward; a.io.done = done; a.io.success = success;

@@ -428,3 +428,46 @@ def test_cooperative_multi_block_rearrange_matches_oracle(emu):
         return np.array([0.3, 0.6, -0.4])
     worst_p, worst_v, worst_o, pairs, most = _multi_scenario(emu, 3, 2, range(0, 2), lambda st: None, policy, task="block_rearrange")
     assert worst_p < 1e-4 and worst_v < 1e-3 and worst_o < 1e-4, (worst_p, worst_v, worst_o)
+
+
+@pytest.mark.parametrize("seed", [0, 1])
+def test_cooperative_slide_step_matches_oracle(emu, seed):
+    """Slide: the one-block cooperative step instantiated with the long table and the puck
+    (cylinder-box narrowphase: cap rim points on the table, curved side against the jaws, a jaw face on the cap;
+    anisotropic inertia through the scaled lever arm of the rows).  Teacher-forced against the oracle: go behind the
+    puck, hit it towards -x, come down on top of it; position entries of the packed row within 1e-4 except on the
+    oracle's own bifurcation steps (a rim point entering the jaw's face), bounded at 2e-3."""
+    o = O.OracleEnv("slide", seed=seed, binary_reward=False)
+    o.reset()
+    o.reset()
+    obs, rew = np.zeros(33, np.float32), np.zeros(1, np.float32)
+    dn, su = np.zeros(1, np.uint8), np.zeros(1, np.uint8)
+    errs, side, cap = [], 0, 0
+    xy0 = o.get_state()[46:48].copy()
+    for t in range(36):
+        st = o.get_state().astype(np.float32)
+        o.set_state(st.astype(np.float64))
+        tip, puck = o.link_state(0)[:3], st[46:49]
+        if t < 12:
+            a = np.clip((puck + np.array([0.06, 0.0, 0.0]) - tip) / 0.01, -1, 1)
+        elif t < 24:
+            a = np.array([-1.0, 0.0, 0.0])
+        else:
+            a = np.clip((puck + np.array([0.0, 0.0, 0.03]) - tip) / 0.01, -1, 1)
+        a = a.astype(np.float32)
+        ro, rr, rd, ri = o.step(a.astype(np.float64))
+        man = np.zeros(6 * 41, np.float32)
+        s2 = st.copy()
+        rc = emu.pmg_emu_block_step(5, _f(s2), _f(man), _f(a), C.c_float(0.05), 0, 50, _f(obs), _f(rew),
+                                    dn.ctypes.data_as(U8), su.ctypes.data_as(U8))
+        assert rc == 0, "divergent collective in the cooperative kernel"
+        want = np.concatenate([ro[k] for k in ("observation", "policy_state", "achieved_goal", "desired_goal")])
+        pos = np.r_[0:10, 20:33]
+        errs.append(float(np.abs(obs - want)[pos].max()))
+        assert abs(float(rew[0]) - rr) < 2e-3 and bool(dn[0]) == rd
+        cnt = [int(man[41 * k:41 * k + 1].view(np.int32)[0]) for k in range(6)]
+        assert cnt[2] == 4 and cnt[3] == 0           # the puck rests on the long table on its four rim points
+        side += cnt[4] + cnt[5]
+    errs = np.array(errs)
+    assert np.mean(errs < 1e-4) >= 0.9 and errs.max() < 2e-3, errs
+    assert np.linalg.norm(o.get_state()[46:48] - xy0) > 0.003 and side > 0   # the jaws touched and moved the puck

@@ -35,7 +35,7 @@ def test_philox_known_answers(emu):
         assert tuple(o) == want
 
 
-CASES = [("reach", 0, 0), ("push", 1, 0), ("pick_and_place", 1, 0), ("block_stack", 4, 0), ("block_stack", 5, 1),
+CASES = [("reach", 0, 0), ("push", 1, 0), ("pick_and_place", 1, 0), ("slide", 1, 0), ("block_stack", 4, 0), ("block_stack", 5, 1),
          ("block_stack", 2, 0), ("block_rearrange", 4, 0), ("block_rearrange", 3, 0)]
 
 
@@ -50,17 +50,19 @@ def test_device_spawn_rows_match_numpy_restatement(emu, task, nb, grip):
         got = np.zeros(want.size, dtype=np.float32)
         emu.pmg_emu_device_spawn(tid, nb, grip, seed, env, ep, got.ctypes.data_as(C.POINTER(C.c_float)))
         assert np.array_equal(got.view(np.uint32), want.view(np.uint32)), (task, seed, env, ep, got, want)
-        n = 0 if tid == 0 else (1 if tid < 3 else nb)
+        n = 0 if tid == 0 else (nb if tid in (3, 4) else 1)
         xy = got[:2 * n].reshape(n, 2).astype(np.float64)
         goal = got[2 * n:].astype(np.float64)
         tip = np.array(b["tip"], dtype=np.float64)
         if n:
             assert np.all(xy >= np.array(b["obj_lo"]) - 1e-6) and np.all(xy <= np.array(b["obj_hi"]) + 1e-6)
-        if tid in (1, 2):
+        if tid in (1, 2, 5):
             assert np.linalg.norm(xy[0] - tip[:2]) >= 0.1 - 1e-6                       # kuka_single_step_base_env.py:109
         if tid == 1:
             assert goal[2] == np.float32(0.175)
-        if tid >= 3:
+        if tid == 5:  # Slide: goals on the long table beyond the arm's reach (kuka_single_step_base_env.py:66-69)
+            assert goal[2] == np.float32(0.17) and -1.09 - 1e-6 <= goal[0] <= -0.75 + 1e-6 and abs(goal[1]) <= 0.2 + 1e-6
+        if tid in (3, 4):
             for i in range(n):
                 assert np.linalg.norm(xy[i] - tip[:2]) > 0.06 - 1e-6
                 for j in range(i):

@@ -8,7 +8,7 @@ import torch
 pytestmark = pytest.mark.gpu
 
 KEYS = ("observation", "policy_state", "achieved_goal", "desired_goal")
-CASES = [("reach", {}), ("push", dict(binary_reward=False)), ("pick_and_place", {}), ("block_stack", dict(num_block=4)),
+CASES = [("reach", {}), ("push", dict(binary_reward=False)), ("pick_and_place", {}), ("slide", {}), ("block_stack", dict(num_block=4)),
          ("block_stack", dict(num_block=3, grip_informed_goal=True)), ("block_rearrange", dict(num_block=4))]
 
 

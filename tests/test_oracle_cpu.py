@@ -137,6 +137,7 @@ def test_block_rests_on_table_and_arm_tracks(oracle):
 GOLDEN_VARIANTS = {
     "reach": dict(task="reach"), "push": dict(task="push", binary_reward=False),
     "pick_and_place": dict(task="pick_and_place"), "block_stack": dict(task="block_stack", num_block=4),
+    "slide": dict(task="slide", binary_reward=False),
     "block_rearrange": dict(task="block_rearrange", num_block=3),
     "block_stack_grip": dict(task="block_stack", num_block=3, grip_informed_goal=True),
     "reach_jc": dict(task="reach", joint_control=True),
@@ -177,3 +178,35 @@ def test_oracle_reproduces_reference_plumbing_goldens(oracle, name):
             np.testing.assert_allclose(flat, g["step_obs"][k], atol=1e-9, rtol=0, err_msg="%s step %d" % (name, k))
             assert r == g["reward"][k] and done == bool(g["done"][k]) and info["goal_achieved"] == bool(g["goal_achieved"][k])
             k += 1
+
+
+def test_slide_scene_known_answers(oracle):
+    """Slide (kuka_single_step_envs.py:49-59, kuka_single_step_base_env.py:53-56,66-69; long_table.urdf, cylinder_bulk.urdf):
+    bounds and dimensions from the reference's constants, a puck that rests quietly on the long table, and one that
+    keeps sliding on the 0.05-friction surface after the jaws hit it."""
+    e = oracle.OracleEnv("slide", seed=3, binary_reward=False)
+    assert e.dims == [20, 7, 3, 3] and e.adim == 3
+    for _ in range(20):
+        o = e.reset()
+        dg, puck, tip = o["desired_goal"], o["achieved_goal"], o["observation"][:3]
+        assert -1.09 - 1e-12 <= dg[0] <= -0.75 + 1e-12 and abs(dg[1]) <= 0.2 + 1e-12 and dg[2] == 0.17      # beyond the arm's reach (x >= -0.67)
+        assert -0.59 - 1e-12 <= puck[0] <= -0.45 + 1e-12 and abs(puck[1]) <= 0.1 + 1e-12 and puck[2] == 0.17
+        assert np.linalg.norm(puck[:2] - [-0.52, 0.0]) >= 0.1 and abs(tip[2] - 0.176) < 2e-3
+    for _ in range(5):
+        o, r, d, info = e.step(np.zeros(3))
+    st = e.get_state()
+    assert abs(st[48] - 0.17) < 2e-5 and np.abs(st[53:59]).max() < 1e-8 and len(e.contacts()) == 4   # at rest on four rim points
+    assert r == -np.linalg.norm(o["achieved_goal"] - o["desired_goal"])
+    # hit the puck from the +x side: it slides on towards -x after the jaws have stopped at the workspace limit
+    e = oracle.OracleEnv("slide", seed=0, binary_reward=False)
+    e.reset()
+    x0 = e.get_state()[46]
+    for t in range(34):
+        st = e.get_state()
+        tip = e.link_state(0)[:3]
+        a = np.clip((st[46:49] + [0.06, 0.0, 0.0] - tip) / 0.01, -1, 1) if t < 12 else np.array([-1.0, 0.0, 0.0])
+        e.step(a)
+    st = e.get_state()
+    assert st[46] < x0 - 0.1 and abs(st[48] - 0.17) < 1e-3          # pushed a long way, still flat on the table
+    q = st[49:53]
+    assert abs(q[0]) < 1e-3 and abs(q[1]) < 1e-3                      # no tilt (it may spin about z)

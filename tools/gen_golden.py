@@ -30,6 +30,8 @@ CONFIGS = [
     ("push", dict(task="push", binary_reward=False), 3, 100),
     ("pick_and_place", dict(task="pick_and_place", binary_reward=True), 4, 100),
     ("block_stack", dict(task="block_stack", binary_reward=True, num_block=4), 4, 100),
+    # Slide: long table, puck, goals beyond reach
+    ("slide", dict(task="slide", binary_reward=False), 3, 100),
     # "next" rows of SURVEY.md 8(f): same physics, more of the reference's plumbing
     ("block_rearrange", dict(task="block_rearrange", binary_reward=True, num_block=3), 3, 100),
     ("block_stack_grip", dict(task="block_stack", binary_reward=True, num_block=3, grip_informed_goal=True), 4, 100),
@@ -50,6 +52,7 @@ SUB_GOAL_SCHEDULE = {0: 0, 10: 1, 20: 2, 30: 5, 40: -1}
 VARIANTS = {
     "reach": dict(task="reach"), "push": dict(task="push", binary_reward=False),
     "pick_and_place": dict(task="pick_and_place"), "block_stack": dict(task="block_stack", num_block=4),
+    "slide": dict(task="slide", binary_reward=False),
     "block_rearrange": dict(task="block_rearrange", num_block=3),
     "block_stack_grip": dict(task="block_stack", num_block=3, grip_informed_goal=True),
     "reach_jc": dict(task="reach", joint_control=True),
@@ -79,7 +82,10 @@ def scripted_actions(name, adim, T, rng):
 
 def main():
     os.makedirs(OUT, exist_ok=True)
+    only = set(sys.argv[1:])  # e.g. `gen_golden.py slide`: (re)generate just these
     for name, kw, adim, T in CONFIGS:
+        if only and name not in only:
+            continue
         # make_env registers an env id once per process and the id does not encode num_block /
         # grip_informed_goal (__init__.py:56-85: first registration wins), so start from a clean registry
         from gym.envs.registration import registry
@@ -112,7 +118,7 @@ def main():
                     obs_now = steps[-1] if (steps and t > 0) else resets[-1]
                     tip = obs_now[0:3]
                     blk = obs_now[3:6] if not name.startswith("block_") else obs_now[8:11]
-                    tgt = blk + np.array([0.0, 0.0, 0.0 if (name in ("push", "block_rearrange") or t > 10) else 0.07])
+                    tgt = blk + np.array([0.0, 0.0, 0.0 if (name in ("push", "slide", "block_rearrange") or t > 10) else 0.07])
                     a[:3] = np.clip((tgt - tip) / 0.01, -1, 1)
                     if adim == 4:
                         a[3] = -1.0 if t < 16 else 1.0

@@ -121,6 +121,13 @@ def simple_box_urdf(path):
     return info
 
 
+def simple_cylinder_urdf(path):
+    root = ET.parse(path).getroot()
+    info = link_info(root.find("link"), os.path.dirname(path))
+    assert info["shape"] == "cylinder"
+    return info
+
+
 def fmt(a):
     return ", ".join("%.17g" % float(x) for x in np.asarray(a).ravel())
 
@@ -235,6 +242,19 @@ def main():
     w("#define PMG_BLOCK_MASS    %s" % fmt([block["mass"]]))
     w("#define PMG_BLOCK_INERTIA %s" % fmt([block["inertia"][0]]))
     w("#define PMG_BLOCK_FRICTION %s" % fmt([block["friction"]]))
+    # Slide scene (kuka_single_step_base_env.py:53-56,89-93): long table at x = -0.70, puck = cylinder_bulk.urdf (axis z)
+    long_table = simple_box_urdf(os.path.join(REF, "objects/long_table.urdf"))
+    puck = simple_cylinder_urdf(os.path.join(REF, "objects/cylinder_bulk.urdf"))
+    w("/* Slide: assets/objects/long_table.urdf:10,20 at (-0.70, 0, 0.08); assets/objects/cylinder_bulk.urdf:10-31 */")
+    w("#define PMG_LONG_TABLE_CENTER  { -0.70, 0.0, 0.08 }")
+    w("#define PMG_LONG_TABLE_HALF    { %s }" % fmt(long_table["dims"] / 2))
+    w("#define PMG_LONG_TABLE_FRICTION %s" % fmt([long_table["friction"]]))
+    w("#define PMG_PUCK_RADIUS   %s" % fmt([puck["dims"][0]]))
+    w("#define PMG_PUCK_HALF_LEN %s" % fmt([puck["dims"][1] / 2]))
+    w("#define PMG_PUCK_MASS     %s" % fmt([puck["mass"]]))
+    w("#define PMG_PUCK_INERTIA  { %s }  /* cylinder about z, x inertia_scaling */" % fmt(puck["inertia"]))
+    w("#define PMG_PUCK_FRICTION %s" % fmt([puck["friction"]]))
+    w("#define PMG_PUCK_SPAWN_Z  0.17  /* kuka_single_step_base_env.py:56 */")
     # Order in which Bullet visits the robot's 18 non-contact constraints (ids 0..8 = joint-limit
     # constraint of dof i, created while the URDF loads; 9..17 = joint motor of dof i-9, created
     # after the load).  btMultiBodyDynamicsWorld copies them in creation order and quick-sorts by
