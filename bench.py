@@ -43,10 +43,10 @@ sys.path.insert(0, ROOT)
 EPISODE = 50
 SETTLE_STEPS = 60
 UNIT = "env-steps/s"
-DEFAULT_BATCH = {"reach": 8192, "push": 4096, "pick_and_place": 4096, "block_stack": 2048, "block_rearrange": 2048}
+DEFAULT_BATCH = {"reach": 8192, "push": 4096, "pick_and_place": 4096, "block_stack": 2048, "block_rearrange": 2048, "slide": 4096}
 HEADLINE = "env-steps/sec (random policy) KukaReach batch=8192"
 # algorithmic HBM bytes per env-step (fp32, 100 substeps fused in one kernel)
-BYTES_PER_ENV_STEP = {"reach": 282, "push": 470, "pick_and_place": 474, "block_stack": 1138, "block_rearrange": 1134}
+BYTES_PER_ENV_STEP = {"reach": 282, "push": 470, "pick_and_place": 474, "block_stack": 1138, "block_rearrange": 1134, "slide": 470}
 
 
 def workload_text(task, per_gpu, world, scaling):
@@ -147,7 +147,7 @@ def cpu_port_rate(task, n_env, n_steps, threads, warm_steps):
 
 
 def cpu_sample_size(task, threads):
-    per_thread = {"reach": 32, "push": 16, "pick_and_place": 16}.get(task, 8)
+    per_thread = {"reach": 32, "push": 16, "pick_and_place": 16, "slide": 16}.get(task, 8)
     return max(threads * per_thread, 64)
 
 
@@ -338,7 +338,7 @@ def main():
             par = "env-sharded x%d, one NCCL all-gather of the obs batch per step" % world
         else:
             par = "single GPU"
-        kname = {"reach": "PMG_COOP", "push": "PMG_COOP_BLOCK", "pick_and_place": "PMG_COOP_BLOCK"}.get(task, "PMG_COOP_STACK")
+        kname = {"reach": "PMG_COOP", "push": "PMG_COOP_BLOCK", "pick_and_place": "PMG_COOP_BLOCK", "slide": "PMG_COOP_BLOCK"}.get(task, "PMG_COOP_STACK")
         coop = os.environ.get(kname, "1") != "0"
         d2h = (B * world if env_s is not None else B) * (Wd * 4 + 4 + 2)
         line = {
@@ -363,7 +363,7 @@ def main():
         if not args.no_cpu_baseline and world == 1:
             threads = os.cpu_count() or 1
             n_env = cpu_sample_size(task, threads)
-            n_steps = 100 if task in ("reach", "push", "pick_and_place") else 50
+            n_steps = 100 if task in ("reach", "push", "pick_and_place", "slide") else 50
             rate, secs, flags = cpu_port_rate(task, n_env, n_steps, threads, 60)
             line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": threads, "kind": "port",
                                     "sample": "%d of %d envs x %d steps (%.1f s) after 60 warm-up steps, staggered episodes with resets, %d pthreads, "
