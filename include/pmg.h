@@ -207,6 +207,13 @@ int pmg_set_state(pmg_handle* h, const float* state_host);
 int pmg_kernel_timing(pmg_handle* h, int32_t on);
 int pmg_kernel_time_ms(pmg_handle* h, double* total_ms, int64_t* count);
 
+/* Test aid (tests/test_gpu_physics.py): the box-box narrowphase of the path run on the device over n independent pairs,
+ * one thread per pair.  in_host: n x 30 floats = p1[3] R1[9, row-major] half1[3] p2[3] R2[9] half2[3]; out_host: n x 32
+ * floats = contact count, then <= 4 x (point on box 2 [3], normal on box 2 [3], signed distance).  stat: 0 = the
+ * general 15-axis search, 1 / 2 = box 1 / box 2 is a static axis-aligned box (the fast path the step kernels use for
+ * the table and the floor; results must be bit-identical to stat = 0). */
+int pmg_debug_box_box(const float* in_host, int64_t n, int32_t stat, float* out_host, int32_t device);
+
 /* number of kernels this library has launched on the handle since creation */
 int64_t pmg_launch_count(const pmg_handle* h);
 /* contact points dropped because a per-env scratch pool overflowed (0 in every shipped config) */

@@ -308,17 +308,17 @@ constexpr int COOP_TABLE_BYTES = coop::GL * coop::LC_W * sizeof(float);
 static_assert(COOP_TABLE_BYTES % 16 == 0, "EnvSmem must stay 16-byte aligned behind the constant table");
 constexpr int COOP_MIN_BLOCKS = 14;  // batch 8192 = 2048 blocks = 13.8 per SM: keep them all resident
 template <bool JC>
-__global__ void __launch_bounds__(32, COOP_MIN_BLOCKS) step_kernel_coop_reach(StepIO io) {
+__global__ void __launch_bounds__(64, COOP_MIN_BLOCKS / 2) step_kernel_coop_reach(StepIO io) {
   extern __shared__ __align__(16) unsigned char coop_smem[];
-  const int lane32 = threadIdx.x & 31, grp = lane32 >> 3;
+  const int lane32 = threadIdx.x & 31, grp = lane32 >> 3, warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
   float* lane_consts = reinterpret_cast<float*>(coop_smem);
-  if (lane32 < coop::GL) coop::fill_lane_constants(lane_consts + lane32 * coop::LC_W, lane32);
-  __syncwarp();
-  const int env = blockIdx.x * io.epb + grp;      // io.epb environments per one-warp block (octets beyond it stay idle)
-  if (grp >= io.epb || env >= io.batch) return;   // a whole octet leaves together
+  if (threadIdx.x < coop::GL) coop::fill_lane_constants(lane_consts + threadIdx.x * coop::LC_W, threadIdx.x);
+  if (wpb > 1) __syncthreads(); else __syncwarp();
+  const int env = (blockIdx.x * wpb + warp) * io.epb + grp;  // io.epb environments per warp (octets beyond it stay idle)
+  if (grp >= io.epb || env >= io.batch) return;   // a whole octet leaves together (exited threads do not hold up the block barrier)
   coop::Grp g;
   g.lane = lane32 & (coop::GL - 1); g.shift = grp * coop::GL; g.mask = 0xffu << g.shift;
-  coop::EnvSmem& sm = reinterpret_cast<coop::EnvSmem*>(coop_smem + COOP_TABLE_BYTES)[grp];
+  coop::EnvSmem& sm = reinterpret_cast<coop::EnvSmem*>(coop_smem + COOP_TABLE_BYTES)[warp * io.epb + grp];
   coop::step_env_reach<JC>(g, sm, lane_consts, io, env);
 }
 
@@ -326,34 +326,34 @@ __global__ void __launch_bounds__(32, COOP_MIN_BLOCKS) step_kernel_coop_reach(St
 // (7.1 KB per environment with the first 12 contact points' rows; 7 one-warp blocks = 28 environments per SM, so a
 // 4096-environment batch is one wave of 1024 blocks on 148 SMs).
 template <int TASK>
-__global__ void __launch_bounds__(32, 7) step_kernel_coop_block(StepIO io) {
+__global__ void __launch_bounds__(64, 3) step_kernel_coop_block(StepIO io) {
   extern __shared__ __align__(16) unsigned char coop_smem[];
-  const int lane32 = threadIdx.x & 31, grp = lane32 >> 3;
+  const int lane32 = threadIdx.x & 31, grp = lane32 >> 3, warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
   float* lane_consts = reinterpret_cast<float*>(coop_smem);
-  if (lane32 < coop::GL) coop::fill_lane_constants(lane_consts + lane32 * coop::LC_W, lane32);
-  __syncwarp();
-  const int env = blockIdx.x * io.epb + grp;      // io.epb environments per one-warp block (octets beyond it stay idle)
-  if (grp >= io.epb || env >= io.batch) return;   // a whole octet leaves together
+  if (threadIdx.x < coop::GL) coop::fill_lane_constants(lane_consts + threadIdx.x * coop::LC_W, threadIdx.x);
+  if (wpb > 1) __syncthreads(); else __syncwarp();
+  const int env = (blockIdx.x * wpb + warp) * io.epb + grp;  // io.epb environments per warp (octets beyond it stay idle)
+  if (grp >= io.epb || env >= io.batch) return;   // a whole octet leaves together (exited threads do not hold up the block barrier)
   coop::Grp g;
   g.lane = lane32 & (coop::GL - 1); g.shift = grp * coop::GL; g.mask = 0xffu << g.shift;
-  coop::EnvSmemT<1, TASK == 5>& sm = reinterpret_cast<coop::EnvSmemT<1, TASK == 5>*>(coop_smem + COOP_TABLE_BYTES)[grp];
+  coop::EnvSmemT<1, TASK == 5>& sm = reinterpret_cast<coop::EnvSmemT<1, TASK == 5>*>(coop_smem + COOP_TABLE_BYTES)[warp * io.epb + grp];
   coop::step_env_block<TASK>(g, sm, lane_consts, io, env);
 }
 
 // Lane-cooperative BlockStack / BlockRearrange step (NBLK = 2..5), the default for these tasks since round 2: it passes
 // the same GPU parity tests as the thread-per-env kernel (PMG_COOP_STACK=0), racecheck-clean, 1.9x its rate at B = 2048.
 template <int NBLK>
-__global__ void __launch_bounds__(32, 3) step_kernel_coop_multi(StepIO io) {
+__global__ void __launch_bounds__(128, 1) step_kernel_coop_multi(StepIO io) {
   extern __shared__ __align__(16) unsigned char coop_smem[];
-  const int lane32 = threadIdx.x & 31, grp = lane32 >> 3;
+  const int lane32 = threadIdx.x & 31, grp = lane32 >> 3, warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
   float* lane_consts = reinterpret_cast<float*>(coop_smem);
-  if (lane32 < coop::GL) coop::fill_lane_constants(lane_consts + lane32 * coop::LC_W, lane32);
-  __syncwarp();
-  const int env = blockIdx.x * io.epb + grp;      // io.epb environments per one-warp block (octets beyond it stay idle)
-  if (grp >= io.epb || env >= io.batch) return;   // a whole octet leaves together
+  if (threadIdx.x < coop::GL) coop::fill_lane_constants(lane_consts + threadIdx.x * coop::LC_W, threadIdx.x);
+  if (wpb > 1) __syncthreads(); else __syncwarp();
+  const int env = (blockIdx.x * wpb + warp) * io.epb + grp;  // io.epb environments per warp (octets beyond it stay idle)
+  if (grp >= io.epb || env >= io.batch) return;   // a whole octet leaves together (exited threads do not hold up the block barrier)
   coop::Grp g;
   g.lane = lane32 & (coop::GL - 1); g.shift = grp * coop::GL; g.mask = 0xffu << g.shift;
-  coop::EnvSmemT<NBLK>& sm = reinterpret_cast<coop::EnvSmemT<NBLK>*>(coop_smem + COOP_TABLE_BYTES)[grp];
+  coop::EnvSmemT<NBLK>& sm = reinterpret_cast<coop::EnvSmemT<NBLK>*>(coop_smem + COOP_TABLE_BYTES)[warp * io.epb + grp];
   coop::step_env_multi<NBLK>(g, sm, lane_consts, io, env);
 }
 
@@ -463,6 +463,24 @@ __global__ void __launch_bounds__(32) reset_kernel(ResetIO r) {
   reset_env<TASK, NBLK>(r, i, r.mask == nullptr || r.mask[i] != 0);
 }
 
+
+// test aid (pmg_debug_box_box): one box pair per thread through the narrowphase of the step kernels
+__global__ void debug_box_box_kernel(const float* in, int64_t n, int stat, float* out) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float* r = in + 30 * i;
+  M3 R1, R2;
+  R1.r0 = v3(r[3], r[4], r[5]); R1.r1 = v3(r[6], r[7], r[8]); R1.r2 = v3(r[9], r[10], r[11]);
+  R2.r0 = v3(r[18], r[19], r[20]); R2.r1 = v3(r[21], r[22], r[23]); R2.r2 = v3(r[24], r[25], r[26]);
+  BoxScratch scr;
+  const int nc = box_box(v3(r[0], r[1], r[2]), R1, v3(r[12], r[13], r[14]), v3(r[15], r[16], r[17]), R2, v3(r[27], r[28], r[29]), scr, stat);
+  float* o = out + 32 * i;
+  o[0] = (float)nc;
+  for (int k = 0; k < nc; k++) {
+    o[1 + 7 * k] = scr.out[k].pB.x; o[2 + 7 * k] = scr.out[k].pB.y; o[3 + 7 * k] = scr.out[k].pB.z;
+    o[4 + 7 * k] = scr.out[k].nB.x; o[5 + 7 * k] = scr.out[k].nB.y; o[6 + 7 * k] = scr.out[k].nB.z; o[7 + 7 * k] = scr.out[k].dist;
+  }
+}
 
 // packed rows [B, W] -> four contiguous blocks [B, O] [B, P] [B, G] [B, G] (pmg_step_host_blocks)
 __global__ void split_rows_kernel(const float* packed, int B, int W, int O, int P, int G, float* blocks) {
@@ -689,7 +707,7 @@ struct pmg_handle {
   bool coop_block = true;  // Push / PickAndPlace: lane-cooperative kernel (PMG_COOP_BLOCK=0 selects the thread-per-env kernel)
   bool coop_stack = true;  // BlockStack / BlockRearrange with >= 2 blocks: lane-cooperative kernel (PMG_COOP_STACK=0 selects the thread-per-env kernel)
   bool hinted = false;  // shared-memory carve-out hint of this handle's step kernel has been set on its device
-  int epb = 0;          // lane-cooperative kernels: environments per one-warp block, chosen at the first launch (coop_geometry)
+  int epb = 0, wpb = 1;  // lane-cooperative kernels: environments per warp and warps per block, chosen at the first launch (coop_geometry)
   // device-side reset sampling (pmg_spawn.cuh) and auto-reset
   bool dev_rng = false, auto_reset = false, last_spawn_on_device = false;
   uint64_t rng_seed = 0; int64_t env_base = 0;
@@ -837,7 +855,7 @@ StepIO make_io(pmg_handle* h, const float* action, float* obs, float* reward, ui
 // than the instruction cache.  So the shards of the 8-GPU configs (256 - 1024 environments) get emptier warps, the
 // single-GPU configs keep 4 per warp.  PMG_COOP_EPB overrides.
 template <class K>
-int coop_geometry(pmg_handle* h, K kernel, size_t table_bytes, size_t env_bytes) {
+int coop_geometry(pmg_handle* h, K kernel, size_t table_bytes, size_t env_bytes, int max_wpb) {
   if (h->epb) return h->epb;
   int sms = 148;
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->cfg.device);
@@ -853,7 +871,34 @@ int coop_geometry(pmg_handle* h, K kernel, size_t table_bytes, size_t env_bytes)
   }
   if (const char* ev = getenv("PMG_COOP_EPB")) { const int v = atoi(ev); if (v == 1 || v == 2 || v == 4) best = v; }
   h->epb = best;
+  // Warps per block.  One-warp blocks spread a small batch over all SMs; once an SM holds several warps anyway they
+  // go into one block and run the substep loop in lockstep (Grp::block_sync), sharing its instruction stream --
+  // as many warps per block as an SM would hold, while the whole batch still fits one wave.
+  int wpb = 1, max_optin = 227 * 1024;
+  cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, h->cfg.device);
+  const long warps = ((long)h->cfg.batch + best - 1) / best;
+  for (int w = max_wpb; w >= 2; w >>= 1) {
+    if (warps < (long)w * sms) continue;             // fewer than w warps per SM: leave them on their own SMs
+    const size_t smem = table_bytes + (size_t)w * best * env_bytes;
+    if (smem > (size_t)max_optin) continue;
+    if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) { cudaGetLastError(); continue; }
+    int per_sm = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, 32 * w, smem) != cudaSuccess) { cudaGetLastError(); continue; }
+    if ((warps + w - 1) / w > (long)per_sm * sms) continue;  // would need a second wave
+    wpb = w;
+    break;
+  }
+  if (const char* ev = getenv("PMG_COOP_WPB")) { const int v = atoi(ev); if (v == 1 || ((v == 2 || v == 4) && v <= max_wpb)) wpb = v; }
+  if (wpb > 1) cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(table_bytes + (size_t)wpb * best * env_bytes));
+  h->wpb = wpb;
   return best;
+}
+
+// Grid, block and dynamic shared memory of a lane-cooperative launch (after coop_geometry)
+struct CoopLaunch { int blocks, threads; size_t smem; };
+CoopLaunch coop_launch(const pmg_handle* h, size_t table_bytes, size_t env_bytes) {
+  const int per_block = h->epb * h->wpb;
+  return {(h->cfg.batch + per_block - 1) / per_block, 32 * h->wpb, table_bytes + (size_t)per_block * env_bytes};
 }
 
 // one warp per block: the block scheduler then spreads the (few) warps evenly over the 148 SMs
@@ -866,13 +911,11 @@ void launch_step(pmg_handle* h, const StepIO& io_in, cudaStream_t st) {
       else cudaFuncSetAttribute(step_kernel_coop_reach<false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
       h->hinted = true;
     }
-    const int EPB = h->jc ? coop_geometry(h, step_kernel_coop_reach<true>, COOP_TABLE_BYTES, sizeof(coop::EnvSmem))
-                          : coop_geometry(h, step_kernel_coop_reach<false>, COOP_TABLE_BYTES, sizeof(coop::EnvSmem));
-    io.epb = EPB;
-    const size_t smem = COOP_TABLE_BYTES + EPB * sizeof(coop::EnvSmem);
-    const int blocks = (h->cfg.batch + EPB - 1) / EPB;
-    if (h->jc) step_kernel_coop_reach<true><<<blocks, 32, smem, st>>>(io);
-    else step_kernel_coop_reach<false><<<blocks, 32, smem, st>>>(io);
+    io.epb = h->jc ? coop_geometry(h, step_kernel_coop_reach<true>, COOP_TABLE_BYTES, sizeof(coop::EnvSmem), 2)
+                   : coop_geometry(h, step_kernel_coop_reach<false>, COOP_TABLE_BYTES, sizeof(coop::EnvSmem), 2);
+    const CoopLaunch cl = coop_launch(h, COOP_TABLE_BYTES, sizeof(coop::EnvSmem));
+    if (h->jc) step_kernel_coop_reach<true><<<cl.blocks, cl.threads, cl.smem, st>>>(io);
+    else step_kernel_coop_reach<false><<<cl.blocks, cl.threads, cl.smem, st>>>(io);
     return;
   }
   if constexpr (TASK == 3 && NBLK >= 2) {
@@ -882,10 +925,9 @@ void launch_step(pmg_handle* h, const StepIO& io_in, cudaStream_t st) {
         cudaFuncSetAttribute(step_kernel_coop_multi<NBLK>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
         h->hinted = true;
       }
-      const int EPB = coop_geometry(h, step_kernel_coop_multi<NBLK>, COOP_TABLE_BYTES, sizeof(coop::EnvSmemT<NBLK>));
-      io.epb = EPB;
-      const size_t smem = COOP_TABLE_BYTES + EPB * sizeof(coop::EnvSmemT<NBLK>);
-      step_kernel_coop_multi<NBLK><<<(h->cfg.batch + EPB - 1) / EPB, 32, smem, st>>>(io);
+      io.epb = coop_geometry(h, step_kernel_coop_multi<NBLK>, COOP_TABLE_BYTES, sizeof(coop::EnvSmemT<NBLK>), 4);
+      const CoopLaunch cl = coop_launch(h, COOP_TABLE_BYTES, sizeof(coop::EnvSmemT<NBLK>));
+      step_kernel_coop_multi<NBLK><<<cl.blocks, cl.threads, cl.smem, st>>>(io);
       return;
     }
   }
@@ -901,15 +943,14 @@ void launch_step(pmg_handle* h, const StepIO& io_in, cudaStream_t st) {
       h->hinted = true;
     }
     if (h->cfg.task == PMG_SLIDE) {  // Push's layout with the long table and the puck (EnvSmemT<1, true>)
-      const int EPB = coop_geometry(h, step_kernel_coop_block<5>, COOP_TABLE_BYTES, sizeof(coop::EnvSmemT<1, true>));
-      io.epb = EPB;
-      step_kernel_coop_block<5><<<(h->cfg.batch + EPB - 1) / EPB, 32, COOP_TABLE_BYTES + EPB * sizeof(coop::EnvSmemT<1, true>), st>>>(io);
+      io.epb = coop_geometry(h, step_kernel_coop_block<5>, COOP_TABLE_BYTES, sizeof(coop::EnvSmemT<1, true>), 2);
+      const CoopLaunch cl = coop_launch(h, COOP_TABLE_BYTES, sizeof(coop::EnvSmemT<1, true>));
+      step_kernel_coop_block<5><<<cl.blocks, cl.threads, cl.smem, st>>>(io);
       return;
     }
-    const int EPB = coop_geometry(h, step_kernel_coop_block<TASK == 2 ? 2 : 1>, COOP_TABLE_BYTES, sizeof(coop::EnvSmemT<1>));
-    io.epb = EPB;
-    const size_t smem = COOP_TABLE_BYTES + EPB * sizeof(coop::EnvSmemT<1>);
-    step_kernel_coop_block<TASK == 2 ? 2 : 1><<<(h->cfg.batch + EPB - 1) / EPB, 32, smem, st>>>(io);
+    io.epb = coop_geometry(h, step_kernel_coop_block<TASK == 2 ? 2 : 1>, COOP_TABLE_BYTES, sizeof(coop::EnvSmemT<1>), 2);
+    const CoopLaunch cl = coop_launch(h, COOP_TABLE_BYTES, sizeof(coop::EnvSmemT<1>));
+    step_kernel_coop_block<TASK == 2 ? 2 : 1><<<cl.blocks, cl.threads, cl.smem, st>>>(io);
     return;
   }
   // The per-thread scratch lives in L1-cached local memory: ask for the smallest shared-memory
@@ -1452,6 +1493,21 @@ int pmg_kernel_time_ms(pmg_handle* h, double* total_ms, int64_t* count) {
     sum += ms;
   }
   *total_ms = sum; *count = n;
+  return PMG_OK;
+}
+
+int pmg_debug_box_box(const float* in_host, int64_t n, int32_t stat, float* out_host, int32_t device) {
+  if (!in_host || !out_host || n < 1 || stat < 0 || stat > 2) return fail(PMG_ERR_INVALID, "pmg_debug_box_box: invalid argument%s");
+  CUDA_TRY(cudaSetDevice(device));
+  float *d_in = nullptr, *d_out = nullptr;
+  CUDA_TRY(cudaMalloc(&d_in, sizeof(float) * 30 * n));
+  CUDA_TRY(cudaMalloc(&d_out, sizeof(float) * 32 * n));
+  CUDA_TRY(cudaMemcpy(d_in, in_host, sizeof(float) * 30 * n, cudaMemcpyHostToDevice));
+  CUDA_TRY(cudaMemset(d_out, 0, sizeof(float) * 32 * n));
+  debug_box_box_kernel<<<(unsigned)((n + 63) / 64), 64>>>(d_in, n, stat, d_out);
+  CUDA_TRY(cudaGetLastError());
+  CUDA_TRY(cudaMemcpy(out_host, d_out, sizeof(float) * 32 * n, cudaMemcpyDeviceToHost));
+  cudaFree(d_in); cudaFree(d_out);
   return PMG_OK;
 }
 

@@ -93,9 +93,15 @@ struct Grp {
     return r;
   }
   __device__ void sync() const { pmg_emu::sync(); }
+  __device__ void block_sync() const {}
 #else
   unsigned mask;  // the octet's lanes inside the warp
   int shift;      // first lane of the octet
+  // Warps of one block that run the substep loop side by side share its instruction stream: the loop body (39 KB
+  // without contacts, 90-130 KB with) does not fit the 32 KB instruction cache, so a warp on its own streams it
+  // from L2 every substep; the first of a group that stays together fetches a line, the others hit.
+  // (blocks of several warps meet at the top of every substep; blockDim sits in the constant bank: no register)
+  __device__ __forceinline__ void block_sync() const { if (blockDim.x > 32) __syncthreads(); }
   __device__ __forceinline__ float shfl(float v, int src) const { return __shfl_sync(mask, v, src, GL); }
   __device__ __forceinline__ unsigned ballot(bool p) const { return (__ballot_sync(mask, p) >> shift) & 0xffu; }
   __device__ __forceinline__ unsigned reduce_or(unsigned v) const { return __reduce_or_sync(mask, v); }  // one REDUX
@@ -1165,7 +1171,7 @@ __device__ void substep(const Grp& g, SM& sm, Lane& L) {
         pb = v3(bk[BK_POS], bk[BK_POS + 1], bk[BK_POS + 2]);
         Rb.r0 = v3(bk[BK_R], bk[BK_R + 1], bk[BK_R + 2]); Rb.r1 = v3(bk[BK_R + 3], bk[BK_R + 4], bk[BK_R + 5]); Rb.r2 = v3(bk[BK_R + 6], bk[BK_R + 7], bk[BK_R + 8]);
       }
-      collide_pair(mr, k, pa, Ra, geom_half(pi.ka), geom_anchor(pi.ka), geom_static(pi.ka), pb, Rb, geom_half(pi.kb), geom_anchor(pi.kb), scr);
+      collide_pair(mr, k, pa, Ra, geom_half(pi.ka), geom_anchor(pi.ka), geom_static(pi.ka), pb, Rb, geom_half(pi.kb), geom_anchor(pi.kb), scr, false, geom_static(pi.kb));
     }
   } else if (lane < SM::NPAIRS) {
     ManRef mr; mr.man = sm.man; mr.stride = 1;
@@ -1175,7 +1181,7 @@ __device__ void substep(const Grp& g, SM& sm, Lane& L) {
     BoxScratch& scr = *reinterpret_cast<BoxScratch*>(&sm.rows[0][0] + lane * SCR_STRIDE);
     if constexpr (!BLK) {
       collide_pair(mr, lane, lane == 0 ? pf1 : pf2, Rg, v3(fh[0], fh[1], fh[2]), v3(0, 0, 0), false,
-                   v3(tc[0], tc[1], tc[2]), m3_identity(), v3(th[0], th[1], th[2]), geom_anchor(G_TABLE), scr);
+                   v3(tc[0], tc[1], tc[2]), m3_identity(), v3(th[0], th[1], th[2]), geom_anchor(G_TABLE), scr, false, true);
     } else {
       // lane k runs pair k: finger1-table, finger2-table, table-block, floor-block, finger1-block, finger2-block
       const PairInfo pi = pair_info<SM::NB>(lane);
@@ -1191,7 +1197,7 @@ __device__ void substep(const Grp& g, SM& sm, Lane& L) {
         Rb.r0 = v3(bk[BK_R], bk[BK_R + 1], bk[BK_R + 2]); Rb.r1 = v3(bk[BK_R + 3], bk[BK_R + 4], bk[BK_R + 5]); Rb.r2 = v3(bk[BK_R + 6], bk[BK_R + 7], bk[BK_R + 8]);
       }
       collide_pair(mr, lane, pa, Ra, geom_half(pi.ka, SM::PUCK), geom_anchor(pi.ka), geom_static(pi.ka), pb, Rb, geom_half(pi.kb, SM::PUCK), geom_anchor(pi.kb), scr,
-                   SM::PUCK && pi.kb == G_BLOCK);
+                   SM::PUCK && pi.kb == G_BLOCK, geom_static(pi.kb));
     }
   }
   PMG_T(t_col1);
@@ -1543,7 +1549,7 @@ __device__ void step_env_reach(const Grp& g, EnvSmem& sm, const float* lane_cons
   for (int call = 0; call < CALLS_PER_ENV_STEP; call++) {
     L.dtau0 = -L.lc[LC_DAMP] * L.qd0;  // joint damping torque, sampled once per stepSimulation call
     L.dtau1 = 0.0f;
-    for (int sub = 0; sub < SUBSTEPS_PER_CALL; sub++) substep(g, sm, L);
+    for (int sub = 0; sub < SUBSTEPS_PER_CALL; sub++) { g.block_sync(); substep(g, sm, L); }
   }
   // ---- observation, reward, flags (kuka_single_step_base_env.py:193-244) ----
   M3 R; V3 p;
@@ -1632,7 +1638,7 @@ __device__ void step_env_block(const Grp& g, EnvSmemT<1, TASK == 5>& sm, const f
   for (int call = 0; call < CALLS_PER_ENV_STEP; call++) {
     L.dtau0 = -L.lc[LC_DAMP] * L.qd0;  // joint damping torque, sampled once per stepSimulation call
     L.dtau1 = 0.0f;
-    for (int sub = 0; sub < SUBSTEPS_PER_CALL; sub++) substep(g, sm, L);
+    for (int sub = 0; sub < SUBSTEPS_PER_CALL; sub++) { g.block_sync(); substep(g, sm, L); }
   }
   // ---- observation, reward, flags (kuka.py:227-256, kuka_single_step_base_env.py:193-244) ----
   M3 R; V3 p;
@@ -1748,7 +1754,7 @@ __device__ void step_env_multi(const Grp& g, EnvSmemT<NBLK>& sm, const float* la
   for (int call = 0; call < CALLS_PER_ENV_STEP; call++) {
     L.dtau0 = -L.lc[LC_DAMP] * L.qd0;
     L.dtau1 = 0.0f;
-    for (int sub = 0; sub < SUBSTEPS_PER_CALL; sub++) substep(g, sm, L);
+    for (int sub = 0; sub < SUBSTEPS_PER_CALL; sub++) { g.block_sync(); substep(g, sm, L); }
   }
   // ---- observation, reward, flags ----
   M3 R; V3 p;

@@ -535,10 +535,33 @@ __device__ void cull_points(int n, const float* p, int m, int i0, int* iret, flo
 
 // Boxes: centre p, orientation R (columns = box axes), half extents.  Up to 4 contacts out:
 // point on B, normal on B (pointing from B to A), signed distance (<= 0).
-__device__ int box_box(V3 p1, const M3& R1, V3 A, V3 p2, const M3& R2, V3 B, BoxScratch& scr) {
+//
+// stat: 1 / 2 = box 1 / box 2 is a STATIC, AXIS-ALIGNED box (the table, the floor; R = identity) -- 0 = no promise.
+// When the other box D lies over the static box S's top face, well inside its outline, the separating-axis search
+// is decided before it starts: with m = the distance of D's centre from the nearest side of S's top face (in the
+// plane), r = D's half diagonal and delta = the penetration along z, every unit axis n has
+//   overlap(n) >= m (|nx| + |ny|) - (z_D - z_top) |nz| + support_D(n) >= (m - r) |n_xy| + delta |nz| >= delta
+// as soon as m - r >= delta (support_D(n) >= |x* . n| for D's lowest point x*, |x*_xy| <= r, 1 - |nz| <= |n_xy|).
+// So S's two side axes and the nine edge-edge axes (which must even beat the best face by the 1.05 fudge factor)
+// cannot win; they are skipped.  The four remaining face axes (S's z, D's three) are evaluated with the general
+// path's arithmetic, in its order, so the winner -- ties included -- and every contact are bit-identical to stat = 0
+// (tests/test_coop_emu.py::test_box_box_static_fast_path_is_bit_identical).  This is the usual contact of the path:
+// a finger or a block resting on the table.
+__device__ int box_box(V3 p1, const M3& R1, V3 A, V3 p2, const M3& R2, V3 B, BoxScratch& scr, int stat = 0) {
   Contact* out = scr.out;
   V3 p = p2 - p1;
   V3 pp = mulT(R1, p);
+  bool top = false;  // the fast path applies
+  if (stat) {
+    const V3 c = stat == 1 ? p : -p;                 // D's centre relative to S's (world axes = S's axes)
+    const V3 S = stat == 1 ? A : B, D = stat == 1 ? B : A;
+    const M3& RD = stat == 1 ? R2 : R1;
+    const float rz = D.x * fabsf(RD.r2.x) + D.y * fabsf(RD.r2.y) + D.z * fabsf(RD.r2.z);   // D's extent along z
+    const float delta = rz - (c.z - S.z);            // penetration along z (< 0: separated, the z axis test returns)
+    const float m = fminf(S.x - fabsf(c.x), S.y - fabsf(c.y));
+    top = c.z > 0.0f && m - norm(D) >= fmaxf(delta, 0.0f) + 1e-3f;
+  }
+  const bool skip1 = top && stat == 1, skip2 = top && stat == 2;
   float R[3][3], Q[3][3];
 #pragma unroll
   for (int i = 0; i < 3; i++) {
@@ -553,17 +576,20 @@ __device__ int box_box(V3 p1, const M3& R1, V3 A, V3 p2, const M3& R2, V3 B, Box
   V3 normalC = v3(0, 0, 0);
 #pragma unroll
   for (int i = 0; i < 3; i++) {
+    if (i < 2 && skip1) continue;
     s2 = fabsf(ppa[i]) - (Ah[i] + Bh[0] * Q[i][0] + Bh[1] * Q[i][1] + Bh[2] * Q[i][2]);
     if (s2 > 0) return 0;
     if (s2 > s) { s = s2; from_R = 1; ncol = i; invert = ppa[i] < 0; code = i + 1; }
   }
 #pragma unroll
   for (int j = 0; j < 3; j++) {
+    if (j < 2 && skip2) continue;
     float e1 = dot(col(R2, j), p);
     s2 = fabsf(e1) - (Ah[0] * Q[0][j] + Ah[1] * Q[1][j] + Ah[2] * Q[2][j] + Bh[j]);
     if (s2 > 0) return 0;
     if (s2 > s) { s = s2; from_R = 2; ncol = j; invert = e1 < 0; code = j + 4; }
   }
+  if (!top) {
 #pragma unroll
   for (int i = 0; i < 3; i++) {
 #pragma unroll
@@ -592,6 +618,7 @@ __device__ int box_box(V3 p1, const M3& R1, V3 A, V3 p2, const M3& R2, V3 B, Box
       }
     }
   }
+  }  // !top
   if (!code) return 0;
   V3 normal = from_R == 1 ? col(R1, ncol) : (from_R == 2 ? col(R2, ncol) : mul(R1, normalC));
   if (invert) normal = -normal;

@@ -171,8 +171,9 @@ __device__ unsigned long long g_coop_cycles[16];
 // narrowphase and the manifold run in coordinates relative to the static box's anchor (else to B's centre),
 // so that penetration depths are differences of small numbers.
 // cylB: body B is the Slide puck (a cylinder about its z axis, hb = (r, r, h)): box_cyl instead of box_box.
+// b_static: body B is the static box (the finger-table pairs); with a_static it selects box_box's static fast path.
 __device__ void collide_pair(ManRef& e, int k, V3 pa, const M3& Ra, V3 ha, V3 aA, bool a_static, V3 pb, const M3& Rb, V3 hb, V3 aB, BoxScratch& scr,
-                             bool cylB = false) {
+                             bool cylB = false, bool b_static = false) {
   V3 d = pa - pb;
   float ex = fabsf(Ra.r0.x) * ha.x + fabsf(Ra.r0.y) * ha.y + fabsf(Ra.r0.z) * ha.z + fabsf(Rb.r0.x) * hb.x + fabsf(Rb.r0.y) * hb.y + fabsf(Rb.r0.z) * hb.z + 2 * BROADPHASE_MARGIN;
   float ey = fabsf(Ra.r1.x) * ha.x + fabsf(Ra.r1.y) * ha.y + fabsf(Ra.r1.z) * ha.z + fabsf(Rb.r1.x) * hb.x + fabsf(Rb.r1.y) * hb.y + fabsf(Rb.r1.z) * hb.z + 2 * BROADPHASE_MARGIN;
@@ -189,7 +190,7 @@ __device__ void collide_pair(ManRef& e, int k, V3 pa, const M3& Ra, V3 ha, V3 aA
 #ifdef PMG_COOP_TIMING
   const long long t0 = clock64();
 #endif
-  int nc = cylB ? box_cyl(a0, Ra, ha, b0, Rb, hb.x, hb.z, scr.out) : box_box(a0, Ra, ha, b0, Rb, hb, scr);
+  int nc = cylB ? box_cyl(a0, Ra, ha, b0, Rb, hb.x, hb.z, scr.out) : box_box(a0, Ra, ha, b0, Rb, hb, scr, a_static ? 1 : (b_static ? 2 : 0));
 #ifdef PMG_COOP_TIMING
   const long long t1 = clock64();
 #endif
@@ -236,7 +237,7 @@ __device__ void collide(Env<NBLK>& e, const Frames& f) {
     const V3 a0 = pa - O, b0 = pb - O, a1 = a0 + aA, b1 = b0 + aB;
     BoxScratch scr;
     const Contact* c = scr.out;
-    int nc = box_box(a0, Ra, ha, b0, Rb, hb, scr);
+    int nc = box_box(a0, Ra, ha, b0, Rb, hb, scr, geom_static(pi.ka) ? 1 : (geom_static(pi.kb) ? 2 : 0));
     for (int i = 0; i < nc; i++) {
       V3 wa = c[i].pB + c[i].dist * c[i].nB;
       manifold_add(e, k, thr, mulT(Ra, wa - a1), mulT(Rb, c[i].pB - b1), c[i].nB, c[i].dist);

@@ -323,3 +323,20 @@ extern "C" void pmg_emu_device_spawn(int task, int nb, int grip, unsigned long l
   pmg::spawn::sample_row(r, task, nb, grip, b, out);
 }
 extern "C" void pmg_emu_philox(const unsigned* ctr, const unsigned* key, unsigned* out) { pmg::spawn::philox_block(ctr, key, out); }
+
+// box_box on one pair of boxes: in = p1[3] R1[9, rows] A[3] p2[3] R2[9] B[3]; out = count, then 4 x (pB[3] nB[3] dist).
+// stat selects the static fast path (pmg_physics.cuh); the equivalence test runs every case with stat = 0 as well.
+extern "C" int pmg_emu_box_box(const float* in, int stat, float* out) {
+  using namespace pmg;
+  auto m3 = [](const float* r) { M3 m; m.r0 = v3(r[0], r[1], r[2]); m.r1 = v3(r[3], r[4], r[5]); m.r2 = v3(r[6], r[7], r[8]); return m; };
+  BoxScratch scr;
+  const M3 R1 = m3(in + 3), R2 = m3(in + 18);
+  const int n = box_box(v3(in[0], in[1], in[2]), R1, v3(in[12], in[13], in[14]), v3(in[15], in[16], in[17]), R2, v3(in[27], in[28], in[29]), scr, stat);
+  out[0] = (float)n;
+  for (int i = 0; i < n; i++) {
+    float* o = out + 1 + 7 * i;
+    o[0] = scr.out[i].pB.x; o[1] = scr.out[i].pB.y; o[2] = scr.out[i].pB.z;
+    o[3] = scr.out[i].nB.x; o[4] = scr.out[i].nB.y; o[5] = scr.out[i].nB.z; o[6] = scr.out[i].dist;
+  }
+  return n;
+}

@@ -471,3 +471,50 @@ def test_cooperative_slide_step_matches_oracle(emu, seed):
     errs = np.array(errs)
     assert np.mean(errs < 1e-4) >= 0.9 and errs.max() < 2e-3, errs
     assert np.linalg.norm(o.get_state()[46:48] - xy0) > 0.003 and side > 0   # the jaws touched and moved the puck
+
+
+def _rot(rng, tilt):
+    """Rotation about a random axis: by up to `tilt` radians about a horizontal axis after a free yaw."""
+    yaw, ang, phi = rng.uniform(-np.pi, np.pi), rng.uniform(0, tilt), rng.uniform(-np.pi, np.pi)
+    cz, sz = np.cos(yaw), np.sin(yaw)
+    Rz = np.array([[cz, -sz, 0], [sz, cz, 0], [0, 0, 1.0]])
+    ax = np.array([np.cos(phi), np.sin(phi), 0.0])
+    K = np.array([[0, -ax[2], ax[1]], [ax[2], 0, -ax[0]], [-ax[1], ax[0], 0]])
+    Rt = np.eye(3) + np.sin(ang) * K + (1 - np.cos(ang)) * K @ K
+    return Rt @ Rz
+
+
+@pytest.mark.parametrize("stat", [1, 2])
+def test_box_box_static_fast_path_is_bit_identical(emu, stat):
+    """box_box(stat = 1 / 2) -- the separating-axis search cut down to four face axes for a box lying over a static
+    box's top face, well inside its outline (pmg_physics.cuh) -- returns exactly the contacts of the full 15-axis
+    search: random fingers / cubes over the table, flat, tilted and on an edge, touching, deep and clear of it, and
+    near and across the table's sides, where the fast path must hand over to the general one."""
+    rng = np.random.RandomState(40 + stat)
+    table_half = np.array([0.4, 0.5, 0.0775], np.float32)  # order of magnitude of the reference's tables
+    out0, out1 = np.zeros(32, np.float32), np.zeros(32, np.float32)
+    touching = fast_cases = 0
+    for case in range(4000):
+        half = (np.array([0.02, 0.02, 0.02]) if case % 2 else np.array([0.01, 0.004, 0.04])).astype(np.float32)
+        R = _rot(rng, [0.0, 1e-4, 0.05, 0.8, np.pi][case % 5]).astype(np.float32)
+        reach = float(np.abs(R[2]) @ half)  # extent along z
+        edge = case % 7 == 0                # over a side of the table: general path
+        x = rng.uniform(0.36, 0.46) if edge else rng.uniform(-0.3, 0.3)
+        z = table_half[2] + reach + rng.choice([-3e-2, -2e-3, -1e-4, -1e-6, 0.0, 1e-6, 1e-3])
+        pD = np.array([x, rng.uniform(-0.4, 0.4), z], np.float32)
+        # coordinates relative to the table's top-face centre, as collide_pair passes them
+        pS = np.array([0, 0, -table_half[2]], np.float32)
+        pD = pD + pS
+        I = np.eye(3, dtype=np.float32)
+        if stat == 1:
+            rec = np.concatenate([pS, I.ravel(), table_half, pD, R.ravel(), half])
+        else:
+            rec = np.concatenate([pD, R.ravel(), half, pS, I.ravel(), table_half])
+        rec = np.ascontiguousarray(rec, np.float32)
+        out0[:] = 0; out1[:] = 0
+        n0 = emu.pmg_emu_box_box(_f(rec), 0, _f(out0))
+        n1 = emu.pmg_emu_box_box(_f(rec), stat, _f(out1))
+        assert n0 == n1 and out0.tobytes() == out1.tobytes(), (case, n0, n1, out0[:1 + 7 * n0], out1[:1 + 7 * n1])
+        touching += n0 > 0
+        fast_cases += (not edge)
+    assert touching > 1000 and fast_cases > 3000
