@@ -960,43 +960,38 @@ __device__ __noinline__ float contact_sweep_multi(Grp g, SM& sm, int nrow_it, in
   // (no barrier: a static point's impulses are private to its lane, a general point's are written identically by all)
   // ---- friction rows: the two tangent rows of a point projected together onto the cone ----
   {
-    float4 DA[4], XA[4], DB[4], XB[4];
-    float2 MA[4];
-    float denB[4], apA[4], apB[4];
+    // (The records are fetched point by point: holding all four points' friction records at once -- 84 registers --
+    // pushed this function past what the call site leaves free, and every call then saved and restored ~40 registers
+    // through local memory, whose L1 share next to 200 KB of shared memory is tiny: 24 % of the block_stack step.)
 #pragma unroll
     for (int i = 0; i < 4; i++)
       if (s0 + i < s1) {
         const float* ra = srow + (i * 3 + 1) * SM::SROW_W;
         const float* rb = ra + SM::SROW_W;
-        DA[i] = ld4(ra); XA[i] = ld4(ra + 4); DB[i] = ld4(rb); XB[i] = ld4(rb + 4);
-        MA[i] = *reinterpret_cast<const float2*>(ra + 8);  // denominator, friction coefficient
-        denB[i] = rb[8];
-        apA[i] = app_rd[(s0 + i) * 3 + 1]; apB[i] = app_rd[(s0 + i) * 3 + 2];
-      }
-#pragma unroll
-    for (int i = 0; i < 4; i++)
-      if (s0 + i < s1) {
+        const float4 da = ld4(ra), xba = ld4(ra + 4), db = ld4(rb), xbb = ld4(rb + 4);
+        const float2 ma = *reinterpret_cast<const float2*>(ra + 8);  // denominator, friction coefficient
+        const float denb = rb[8];
+        const float apa = app_rd[(s0 + i) * 3 + 1], apb = app_rd[(s0 + i) * 3 + 2];
         const float total = sn[i];
-        float sA = apA[i], sB = apB[i];
+        float sA = apa, sB = apb;
         if (total > 0.0f) {
-          const float4 da = DA[i], xba = XA[i], db = DB[i], xbb = XB[i];
           const float vA = -((da.x * bd[0] + da.y * bd[1] + da.z * bd[2]) + (xba.x * bd[3] + xba.y * bd[4] + xba.z * bd[5]));
           const float vB = -((db.x * bd[0] + db.y * bd[1] + db.z * bd[2]) + (xbb.x * bd[3] + xbb.y * bd[4] + xbb.z * bd[5]));
-          const float lim = MA[i].y * total;
+          const float lim = ma.y * total;
           float dA = da.w - vA * xba.w, dB = db.w - vB * xbb.w;
-          sA = apA[i] + dA; sB = apB[i] + dB;
+          sA = apa + dA; sB = apb + dB;
           const float s2 = sA * sA + sB * sB;
           if (s2 >= lim * lim) {
             const float sc = s2 > 0.0f ? lim * rsqrtf(s2) : 0.0f;
             const float cA = fabsf(sA) * sc, cB = s2 > 0.0f ? fabsf(sB) * sc : lim;
             sA = fminf(fmaxf(sA, -cA), cA);
             sB = fminf(fmaxf(sB, -cB), cB);
-            dA = sA - apA[i]; dB = sB - apB[i];
+            dA = sA - apa; dB = sB - apb;
           }
           const float lmA = dA * BLOCK_INV_MASS, liA = dA * BLOCK_INV_INERTIA, lmB = dB * BLOCK_INV_MASS, liB = dB * BLOCK_INV_INERTIA;
           bd[0] -= lmA * da.x; bd[1] -= lmA * da.y; bd[2] -= lmA * da.z; bd[3] -= liA * xba.x; bd[4] -= liA * xba.y; bd[5] -= liA * xba.z;
           bd[0] -= lmB * db.x; bd[1] -= lmB * db.y; bd[2] -= lmB * db.z; bd[3] -= liB * xbb.x; bd[4] -= liB * xbb.y; bd[5] -= liB * xbb.z;
-          const float r1_ = dA * MA[i].x, r2_ = dB * denB[i];
+          const float r1_ = dA * ma.x, r2_ = dB * denb;
           cres = fmaxf(cres, fmaxf(r1_ * r1_, r2_ * r2_));
         }
         app_wr[(s0 + i) * 3 + 1] = sA; app_wr[(s0 + i) * 3 + 2] = sB;
