@@ -54,7 +54,7 @@
 #define NB PMG_NBODY
 #define ND PMG_NDOF
 #define MAXBLK PMGO_MAX_BLOCKS
-#define MAX_PAIRS (2 + 4 * MAXBLK + MAXBLK * (MAXBLK - 1) / 2)
+#define MAX_PAIRS (2 + 4 * MAXBLK + MAXBLK * (MAXBLK - 1) / 2 + MAXBLK)
 #define MAX_ROWS (2 * ND + ND + 3 * 4 * MAX_PAIRS)
 
 static const int B_PARENT[NB] = PMG_BODY_PARENT;
@@ -918,6 +918,19 @@ static void build_pairs(PmgoEnv* e) {
       e->pairs[n].a = make_geom(2, i, bh, PMG_BLOCK_FRICTION);
       e->pairs[n++].b = make_geom(2, j, bh, PMG_BLOCK_FRICTION);
     }
+  /* Multi-block scenes: the gripper-base cylinder (r 0.05, 0.045 - 0.085 above the tip) against every block -- it
+   * reaches the top of a stack of two or more blocks (hard part 4; one block on the table stays
+   * 3 cm below it at the lowest tip height).  Default lateral friction (the link has no <contact> tag).  Body A is
+   * the cylinder: box_cyl runs with the roles exchanged and collide() turns its contacts round. */
+  if (e->nb >= 2) {
+    double gh[3] = {PMG_GBASE_RADIUS, PMG_GBASE_RADIUS, PMG_GBASE_HALF_LEN};
+    Geom gb = make_geom(1, PMG_BODY_GBASE, gh, PMG_GBASE_FRICTION);
+    gb.cylinder = 1;
+    for (int i = 0; i < e->nb; i++) {
+      e->pairs[n].a = gb;
+      e->pairs[n++].b = make_geom(2, i, bh, PMG_BLOCK_FRICTION);
+    }
+  }
   e->npair = n;
   memset(e->man, 0, sizeof e->man);
 }
@@ -983,8 +996,16 @@ static void collide(PmgoEnv* e) {
     if (!overlap) { m->n = 0; continue; }
     double thr = BREAKING_THRESHOLD_FACTOR * (pr->a.radius < pr->b.radius ? pr->a.radius : pr->b.radius);
     ContactOut c[4];
-    int nc = pr->b.cylinder ? box_cyl(pa, Ra, pr->a.half, pb, Rb, pr->b.half[0], pr->b.half[2], c)
-                            : box_box(pa, Ra, pr->a.half, pb, Rb, pr->b.half, c);
+    int nc;
+    if (pr->a.cylinder) { /* cylinder A against box B: box_cyl with the roles exchanged, contacts turned round */
+      nc = box_cyl(pb, Rb, pr->b.half, pa, Ra, pr->a.half[0], pr->a.half[2], c);
+      for (int i = 0; i < nc; i++) { /* point on the box = point on the cylinder + n * distance; the normal flips */
+        axpy3(c[i].pB, c[i].dist, c[i].nB);
+        for (int k = 0; k < 3; k++) c[i].nB[k] = -c[i].nB[k];
+      }
+    } else
+      nc = pr->b.cylinder ? box_cyl(pa, Ra, pr->a.half, pb, Rb, pr->b.half[0], pr->b.half[2], c)
+                          : box_box(pa, Ra, pr->a.half, pb, Rb, pr->b.half, c);
     for (int i = 0; i < nc; i++) {
       double wa[3], lA[3], lB[3], t[3];
       copy3(wa, c[i].pB);

@@ -735,7 +735,7 @@ template <class SM>
 __device__ __noinline__ void contact_row_setup_general(SM& sm, int gidx) {
   const int c = sm.glist[gidx], k = sm.ppair[gidx], i = sm.pidx[gidx];
   const PairInfo pi = pair_info<SM::NB>(k);
-  const bool robotA = pi.ka == G_FINGER1 || pi.ka == G_FINGER2, blockA = pi.ka == G_BLOCK, blockB = pi.kb == G_BLOCK;
+  const bool robotA = geom_robot(pi.ka), blockA = pi.ka == G_BLOCK, blockB = pi.kb == G_BLOCK;
   const float* mp = sm.man + k * MAN_WORDS + 1 + 10 * i;
   const V3 lA = v3(mp[0], mp[1], mp[2]), lB = v3(mp[3], mp[4], mp[5]), nB = v3(mp[6], mp[7], mp[8]);
   const float dist = mp[9];
@@ -755,7 +755,8 @@ __device__ __noinline__ void contact_row_setup_general(SM& sm, int gidx) {
   Rg.r0 = v3(hd[0], hd[1], hd[2]); Rg.r1 = v3(hd[3], hd[4], hd[5]); Rg.r2 = v3(hd[6], hd[7], hd[8]);
   const V3 pf1 = v3(hd[9], hd[10], hd[11]), pf2 = v3(hd[12], hd[13], hd[14]), Pref = v3(hd[15], hd[16], hd[17]);
   const V3 ax1 = v3(hd[18], hd[19], hd[20]), ax2 = -ax1;
-  const V3 wr = robotA ? mul(Rg, lA) + (pi.ka == G_FINGER1 ? pf1 : pf2) - Pref : v3(0, 0, 0);
+  // contact point on the robot body relative to Pref (the gripper base's own frame sits AT Pref; its rows have no finger column)
+  const V3 wr = robotA ? mul(Rg, lA) + (pi.ka == G_GBASE ? v3(0, 0, 0) : (pi.ka == G_FINGER1 ? pf1 : pf2) - Pref) : v3(0, 0, 0);
   V3 rA = v3(0, 0, 0), av = v3(0, 0, 0), aw = v3(0, 0, 0);
   if (blockA) {
     const float* bk = sm.blk + 24 * pi.ia;
@@ -1134,7 +1135,7 @@ __device__ void substep(const Grp& g, SM& sm, Lane& L) {
     BoxScratch& scr = *reinterpret_cast<BoxScratch*>(&sm.rows[0][0] + lane * SCR_STRIDE);
     const float tc[3] = PMG_TABLE_CENTER, fc[3] = PMG_FLOOR_CENTER;
     // Position p of the schedule -> pair: the table-block pairs (always touching in a scene at rest: a full SAT +
-    // clipping each) come first, one per lane, then finger-table, finger-block, block-block, floor-block.
+    // clipping each) come first, one per lane, then finger-table, finger-block, block-block, floor-block, base-block.
     auto scheduled_pair = [](int p) {
       constexpr int NB = SM::NB, NBB = NB * (NB - 1) / 2;
       if (p < NB) return 2 + 4 * p;
@@ -1144,15 +1145,36 @@ __device__ void substep(const Grp& g, SM& sm, Lane& L) {
       if (p < 2 * NB) return 2 + 4 * (p >> 1) + 2 + (p & 1);
       p -= 2 * NB;
       if (p < NBB) return 2 + 4 * NB + p;
-      return 2 + 4 * (p - NBB) + 1;
+      p -= NBB;
+      if (p < NB) return 2 + 4 * p + 1;
+      return 2 + 4 * NB + NBB + (p - NB);  // gripper base - block
     };
+    // The gripper-base pairs (the last NB positions) all fail the broadphase while the cylinder's world box -- grown by
+    // the largest box a cube can fill and the margins -- stays above every block: the usual case (a block on the table
+    // is 3 cm below the base at the lowest tip height).  One comparison per block then replaces their round of the loop.
+    int npos = SM::NPAIRS;
+    {
+      const float ez = (fabsf(Rg.r2.x) + fabsf(Rg.r2.y)) * (float)PMG_GBASE_RADIUS + fabsf(Rg.r2.z) * (float)PMG_GBASE_HALF_LEN;
+      const float low = Pref.z - (ez + 1.7320508f * BLOCK_HALF + 2 * BROADPHASE_MARGIN);
+      bool reach = false;
+#pragma unroll
+      for (int b = 0; b < SM::NB; b++) reach = reach || !(sm.blk[24 * b + BK_POS + 2] < low);
+      if (!reach) {
+        npos -= SM::NB;
+        if (lane < SM::NB) {  // what collide_pair's own broadphase would do: forget the cached points
+          float& cnt = sm.man[(2 + 4 * SM::NB + SM::NB * (SM::NB - 1) / 2 + lane) * MAN_WORDS];
+          if (__float_as_int(cnt) != 0) cnt = __int_as_float(0);
+        }
+      }
+    }
 #pragma unroll 1
-    for (int pos = lane; pos < SM::NPAIRS; pos += GL) {
+    for (int pos = lane; pos < npos; pos += GL) {
       const int k = scheduled_pair(pos);
       const PairInfo pi = pair_info<SM::NB>(k);
       V3 pa, pb;
       M3 Ra = m3_identity(), Rb = m3_identity();
       if (pi.ka == G_FINGER1 || pi.ka == G_FINGER2) { pa = pi.ka == G_FINGER1 ? pf1 : pf2; Ra = Rg; }
+      else if (pi.ka == G_GBASE) { pa = Pref; Ra = Rg; }  // the cylinder is centred on the gripper-base frame
       else if (pi.ka == G_TABLE) pa = v3(tc[0], tc[1], tc[2]);
       else if (pi.ka == G_FLOOR) pa = v3(fc[0], fc[1], fc[2]);
       else {
@@ -1166,7 +1188,8 @@ __device__ void substep(const Grp& g, SM& sm, Lane& L) {
         pb = v3(bk[BK_POS], bk[BK_POS + 1], bk[BK_POS + 2]);
         Rb.r0 = v3(bk[BK_R], bk[BK_R + 1], bk[BK_R + 2]); Rb.r1 = v3(bk[BK_R + 3], bk[BK_R + 4], bk[BK_R + 5]); Rb.r2 = v3(bk[BK_R + 6], bk[BK_R + 7], bk[BK_R + 8]);
       }
-      collide_pair(mr, k, pa, Ra, geom_half(pi.ka), geom_anchor(pi.ka), geom_static(pi.ka), pb, Rb, geom_half(pi.kb), geom_anchor(pi.kb), scr, false, geom_static(pi.kb));
+      collide_pair(mr, k, pa, Ra, geom_half(pi.ka), geom_anchor(pi.ka), geom_static(pi.ka), pb, Rb, geom_half(pi.kb), geom_anchor(pi.kb), scr, false, geom_static(pi.kb),
+                   pi.ka == G_GBASE);
     }
   } else if (lane < SM::NPAIRS) {
     ManRef mr; mr.man = sm.man; mr.stride = 1;

@@ -871,6 +871,17 @@ __device__ int box_cyl(V3 pa, const M3& Ra, V3 ha, V3 pb, const M3& Rb, float r,
   return n;
 }
 
+// Cylinder A (axis = its local z) against box B: box_cyl with the roles exchanged, its contacts turned round to this
+// file's convention (point on B, normal on B pointing from B towards A).  The gripper base against a block.
+__device__ __forceinline__ int cyl_box(V3 pa, const M3& Ra, float r, float h, V3 pb, const M3& Rb, V3 hb, Contact* out) {
+  const int n = box_cyl(pb, Rb, hb, pa, Ra, r, h, out);
+  for (int i = 0; i < n; i++) {
+    out[i].pB = out[i].pB + out[i].dist * out[i].nB;  // point on the box = point on the cylinder + n * distance
+    out[i].nB = -out[i].nB;
+  }
+  return n;
+}
+
 __device__ __forceinline__ void plane_space(V3 n, V3& p, V3& q) {  // btPlaneSpace1
   if (fabsf(n.z) > 0.70710678118654752440f) {
     float a = n.y * n.y + n.z * n.z, k = 1.0f / sqrtf(a);

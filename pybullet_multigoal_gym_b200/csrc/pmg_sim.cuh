@@ -17,12 +17,14 @@ namespace pmg {
 constexpr int MAN_WORDS = 41;  // per pair
 constexpr int ST_Q = 0, ST_QD = 9, ST_EE = 18, ST_REST = 21, ST_MT = 28, ST_MI = 37, ST_BLK = 46;
 
-__host__ __device__ constexpr int num_pairs(int nblk) { return 2 + 4 * nblk + nblk * (nblk - 1) / 2; }
+// finger-table (2), per block table / floor / finger1 / finger2 (4 each), block-block, and -- scenes with two or more
+// blocks, where a stack reaches it -- the gripper-base cylinder against every block
+__host__ __device__ constexpr int num_pairs(int nblk) { return 2 + 4 * nblk + nblk * (nblk - 1) / 2 + (nblk >= 2 ? nblk : 0); }
 __host__ __device__ constexpr int max_points(int nblk) { return nblk <= 1 ? 4 * num_pairs(nblk) : 48; }
 __host__ __device__ constexpr int max_robot_points(int nblk) { return nblk == 0 ? 8 : 16; }
 
 // geometry endpoints of a collision pair
-enum GeomKind { G_TABLE = 0, G_FLOOR = 1, G_FINGER1 = 2, G_FINGER2 = 3, G_BLOCK = 4 };
+enum GeomKind { G_TABLE = 0, G_FLOOR = 1, G_FINGER1 = 2, G_FINGER2 = 3, G_BLOCK = 4, G_GBASE = 5 /* gripper-base cylinder: (r, r, h) */ };
 struct PairInfo { int ka, kb, ia, ib; };  // kinds and block indices (for G_BLOCK)
 
 template <int NBLK>
@@ -37,11 +39,16 @@ __device__ __forceinline__ PairInfo pair_info(int k) {
     return p;
   }
   k -= 4 * NBLK;
+  if (k >= NBLK * (NBLK - 1) / 2) {  // gripper base (a robot end, like the fingers) against block k
+    p.ka = G_GBASE; p.kb = G_BLOCK; p.ib = k - NBLK * (NBLK - 1) / 2;
+    return p;
+  }
   int i = 0;
   while (k >= NBLK - 1 - i) { k -= NBLK - 1 - i; i++; }
   p.ka = G_BLOCK; p.kb = G_BLOCK; p.ia = i; p.ib = i + 1 + k;
   return p;
 }
+__device__ __forceinline__ bool geom_robot(int kind) { return kind == G_FINGER1 || kind == G_FINGER2 || kind == G_GBASE; }
 
 // puck: the Slide scene (long low-friction table, the block is a cylinder about its z axis: half = (r, r, h))
 __device__ __forceinline__ V3 geom_half(int kind, bool puck = false) {
@@ -49,6 +56,7 @@ __device__ __forceinline__ V3 geom_half(int kind, bool puck = false) {
   if (kind == G_TABLE) return puck ? v3(lh[0], lh[1], lh[2]) : v3(th[0], th[1], th[2]);
   if (kind == G_FLOOR) return v3(fh[0], fh[1], fh[2]);
   if (kind == G_BLOCK) return puck ? v3((float)PMG_PUCK_RADIUS, (float)PMG_PUCK_RADIUS, (float)PMG_PUCK_HALF_LEN) : v3(BLOCK_HALF, BLOCK_HALF, BLOCK_HALF);
+  if (kind == G_GBASE) return v3((float)PMG_GBASE_RADIUS, (float)PMG_GBASE_RADIUS, (float)PMG_GBASE_HALF_LEN);
   return v3(gh[0], gh[1], gh[2]);
 }
 __device__ __forceinline__ V3 table_center(bool puck = false) {
@@ -60,6 +68,7 @@ __device__ __forceinline__ float geom_friction(int kind, bool puck = false) {
   if (kind == G_BLOCK && puck) return (float)PMG_PUCK_FRICTION;
   if (kind == G_FLOOR) return (float)PMG_FLOOR_FRICTION;
   if (kind == G_BLOCK) return (float)PMG_BLOCK_FRICTION;
+  if (kind == G_GBASE) return (float)PMG_GBASE_FRICTION;
   return (float)PMG_FINGER_FRICTION;
 }
 
@@ -99,6 +108,7 @@ __device__ __forceinline__ void geom_pose(const Env<NBLK>& e, const Frames& f, i
   else if (kind == G_FLOOR) { p = v3(fc[0], fc[1], fc[2]); R = m3_identity(); }
   else if (kind == G_FINGER1) { p = f.p[PMG_BODY_FINGER1]; R = f.R[PMG_BODY_FINGER1]; }
   else if (kind == G_FINGER2) { p = f.p[PMG_BODY_FINGER2]; R = f.R[PMG_BODY_FINGER2]; }
+  else if (kind == G_GBASE) { p = f.p[PMG_BODY_GBASE]; R = f.R[PMG_BODY_GBASE]; }
   else { p = e.bpos[idx]; R = e.bR[idx]; }
 }
 
@@ -171,6 +181,7 @@ __device__ unsigned long long g_coop_cycles[16];
 // narrowphase and the manifold run in coordinates relative to the static box's anchor (else to B's centre),
 // so that penetration depths are differences of small numbers.
 // cylB: body B is the Slide puck (a cylinder about its z axis, hb = (r, r, h)): box_cyl instead of box_box.
+// cylA: body A is the gripper-base cylinder (ha = (r, r, h)): box_cyl with the roles exchanged (cyl_box).
 // b_static: body B is the static box (the finger-table pairs); with a_static it selects box_box's static fast path.
 #ifdef PMG_X_NP_NOINLINE
 #define PMG_NP_INLINE __noinline__
@@ -178,7 +189,7 @@ __device__ unsigned long long g_coop_cycles[16];
 #define PMG_NP_INLINE
 #endif
 __device__ PMG_NP_INLINE void collide_pair(ManRef& e, int k, V3 pa, const M3& Ra, V3 ha, V3 aA, bool a_static, V3 pb, const M3& Rb, V3 hb, V3 aB, BoxScratch& scr,
-                             bool cylB = false, bool b_static = false) {
+                             bool cylB = false, bool b_static = false, bool cylA = false) {
   V3 d = pa - pb;
   float ex = fabsf(Ra.r0.x) * ha.x + fabsf(Ra.r0.y) * ha.y + fabsf(Ra.r0.z) * ha.z + fabsf(Rb.r0.x) * hb.x + fabsf(Rb.r0.y) * hb.y + fabsf(Rb.r0.z) * hb.z + 2 * BROADPHASE_MARGIN;
   float ey = fabsf(Ra.r1.x) * ha.x + fabsf(Ra.r1.y) * ha.y + fabsf(Ra.r1.z) * ha.z + fabsf(Rb.r1.x) * hb.x + fabsf(Rb.r1.y) * hb.y + fabsf(Rb.r1.z) * hb.z + 2 * BROADPHASE_MARGIN;
@@ -195,7 +206,9 @@ __device__ PMG_NP_INLINE void collide_pair(ManRef& e, int k, V3 pa, const M3& Ra
 #ifdef PMG_COOP_TIMING
   const long long t0 = clock64();
 #endif
-  int nc = cylB ? box_cyl(a0, Ra, ha, b0, Rb, hb.x, hb.z, scr.out) : box_box(a0, Ra, ha, b0, Rb, hb, scr, a_static ? 1 : (b_static ? 2 : 0));
+  int nc;
+  if (cylA) nc = cyl_box(a0, Ra, ha.x, ha.z, b0, Rb, hb, scr.out);  // the gripper base against a block
+  else nc = cylB ? box_cyl(a0, Ra, ha, b0, Rb, hb.x, hb.z, scr.out) : box_box(a0, Ra, ha, b0, Rb, hb, scr, a_static ? 1 : (b_static ? 2 : 0));
 #ifdef PMG_COOP_TIMING
   const long long t1 = clock64();
 #endif
@@ -242,7 +255,8 @@ __device__ void collide(Env<NBLK>& e, const Frames& f) {
     const V3 a0 = pa - O, b0 = pb - O, a1 = a0 + aA, b1 = b0 + aB;
     BoxScratch scr;
     const Contact* c = scr.out;
-    int nc = box_box(a0, Ra, ha, b0, Rb, hb, scr, geom_static(pi.ka) ? 1 : (geom_static(pi.kb) ? 2 : 0));
+    int nc = pi.ka == G_GBASE ? cyl_box(a0, Ra, ha.x, ha.z, b0, Rb, hb, scr.out)
+                              : box_box(a0, Ra, ha, b0, Rb, hb, scr, geom_static(pi.ka) ? 1 : (geom_static(pi.kb) ? 2 : 0));
     for (int i = 0; i < nc; i++) {
       V3 wa = c[i].pB + c[i].dist * c[i].nB;
       manifold_add(e, k, thr, mulT(Ra, wa - a1), mulT(Rb, c[i].pB - b1), c[i].nB, c[i].dist);
@@ -449,7 +463,7 @@ __device__ void solve_constraints(Env<NBLK>& e, const Frames& f, const float (*M
     geom_pose(e, f, pi.kb, pi.ib, pb, Rb);
     const V3 pa_anchor = pa + geom_anchor(pi.ka), pb_anchor = pb + geom_anchor(pi.kb);  // what lA / lB refer to
     const float mu = geom_friction(pi.ka) * geom_friction(pi.kb);
-    const bool robotA = pi.ka == G_FINGER1 || pi.ka == G_FINGER2;
+    const bool robotA = geom_robot(pi.ka);  // the gripper base moves with the 7 arm joints only (both finger columns zero)
     const bool blockA = pi.ka == G_BLOCK, blockB = pi.kb == G_BLOCK;
 #pragma unroll 1
     for (int i = 0; i < n; i++) {

@@ -114,7 +114,7 @@ def test_thread_per_env_physics_on_host_matches_oracle(emu, task, nb):
     o.step(a)   # motors on, arm moving down
     st = o.get_state().astype(np.float32)
     o.set_state(st.astype(np.float64))
-    npairs = 2 + 4 * nb + nb * (nb - 1) // 2
+    npairs = 2 + 4 * nb + nb * (nb - 1) // 2 + (nb if nb >= 2 else 0)  # + gripper base against every block
     man = np.zeros(41 * npairs, np.float32)
     s2 = st.copy()
     for call in range(5):
@@ -293,7 +293,7 @@ def _multi_scenario(emu, nb, nsteps, window, init, policy, seed=4, grip=False, t
     st = o.get_state()
     init(st)
     o.set_state(st)
-    npairs = 2 + 4 * nb + nb * (nb - 1) // 2
+    npairs = 2 + 4 * nb + nb * (nb - 1) // 2 + (nb if nb >= 2 else 0)  # + gripper base against every block
     G = 3 * nb + (4 if grip else 0)
     width = (8 + 16 * nb) + (4 + 3 * nb) + 2 * G
     ovf = (C.c_int * 1)(0)
@@ -419,6 +419,31 @@ def test_cooperative_multi_block_pick_carry_release_matches_oracle(emu):
     worst_p, worst_v, worst_o, pairs, most = _multi_scenario(emu, 3, 60, [36, 50, 56, 57, 59], lambda st: None, policy)
     assert worst_p < 1e-4 and worst_v < 1e-3 and worst_o < 1e-4, (worst_p, worst_v, worst_o)
     assert {4, 5, 14} <= pairs   # both jaws on block 0 while carrying; block 0 on block 1 at the end
+
+
+def test_cooperative_multi_block_gripper_base_lands_on_a_stack(emu):
+    """The gripper-base cylinder (iiwa14_parallel_jaw.urdf:399-416: r 0.05, 0.045 - 0.085 above the tip) against the
+    blocks (hard part 4): with the jaws open around a three-block stack the arm comes down until
+    the base sits on the top block (pair 2 + 4*3 + 3 + 2 = 19: rows with a robot end that has no finger column and a
+    block end) and presses on it.  Every step from the approach over the first touch to the loaded stack against the
+    oracle (the topple that follows is a bifurcation: not compared)."""
+    sx, sy = -0.45, 0.10
+
+    def init(st):
+        for b in range(3):
+            st[46 + 13 * b:49 + 13 * b] = [sx, sy, 0.175 + 0.03 * b]
+            st[49 + 13 * b:53 + 13 * b] = [0, 0, 0, 1]
+            st[53 + 13 * b:59 + 13 * b] = 0.0
+
+    def policy(t, st, tip):
+        tgt = np.array([tip[0], tip[1], 0.32]) if t < 8 else (np.array([sx, sy, 0.32]) if t < 24 else np.array([sx, sy, 0.19]))
+        a = np.zeros(4)
+        a[:3] = np.clip((tgt - tip) / 0.01, -1, 1)
+        a[3] = -1.0
+        return a
+    worst_p, worst_v, worst_o, pairs, most = _multi_scenario(emu, 3, 38, range(33, 38), init, policy, seed=3)
+    assert worst_p < 1e-4 and worst_v < 2e-3 and worst_o < 1e-4, (worst_p, worst_v, worst_o)
+    assert {2, 14, 16, 19} <= pairs   # the stack on the table, block on block twice, the gripper base on the top block
 
 
 def test_cooperative_multi_block_rearrange_matches_oracle(emu):

@@ -232,6 +232,40 @@ def test_teacher_forced_contact_parity(oracle, task, kernel):
     assert env.overflow_count == 0
 
 
+def test_gripper_base_lands_on_a_stack(oracle, kernel):
+    """The gripper-base cylinder against the blocks (iiwa14_parallel_jaw.urdf:399-416; SURVEY.md section 7, hard part
+    4): three blocks stacked by hand (set_state), jaws open around the stack, the arm comes down until the base sits
+    on the top block and presses on it.  Teacher-forced from the oracle over the approach, the first touch and the
+    loaded stack, on both kernel families."""
+    from tests import _teacher
+    B = 4
+    env = _mk("block_stack", B, num_block=3, binary_reward=False)
+    env.reset()
+    refs, twins = _twinned(oracle, "block_stack", env.last_spawn(), range(B), num_block=3, binary_reward=False)
+    stacks = [(-0.45, 0.10), (-0.47, -0.08), (-0.50, 0.12), (-0.44, -0.11)]
+    for o, (sx, sy) in zip(refs, stacks):
+        st = o.get_state()
+        for b in range(3):
+            st[46 + 13 * b:59 + 13 * b] = [sx, sy, 0.175 + 0.03 * b, 0, 0, 0, 1, 0, 0, 0, 0, 0, 0]
+        o.set_state(st)
+    touched = [0] * B
+
+    def fn(t, j, st, tip, a):
+        sx, sy = stacks[j]
+        tgt = np.array([tip[0], tip[1], 0.32]) if t < 8 else (np.array([sx, sy, 0.32]) if t < 26 else np.array([sx, sy, 0.19]))
+        a[:3] = np.clip((tgt - tip) / 0.01, -1, 1)
+        a[3] = -1.0
+        # the base's lower face (0.045 above the tip) down on the top block's upper face, over it
+        touched[j] += int(tip[2] + 0.045 - (st[74] + 0.015) < 5e-4 and abs(tip[0] - st[72]) < 0.03 and abs(tip[1] - st[73]) < 0.03)
+        return a
+    vel = _teacher.velocity_mask("block_stack", 3, env.row_width)
+    stats = _teacher.run(env, oracle, refs, twins, 40, fn, vel, np.random.RandomState(11), "block_stack(3), gripper base on a stack [%s kernel]" % kernel, perturb_block=True)
+    pos, _ = stats.report()
+    assert all(n >= 2 for n in touched), touched          # every environment's base reached its stack
+    assert float(np.mean(pos < TOL)) >= 0.97
+    assert env.overflow_count == 0
+
+
 @pytest.mark.parametrize("task,batch", [("pick_and_place", 4096), ("block_stack", 2048)])
 def test_teacher_forced_parity_at_config_batch(oracle, task, batch):
     """The same comparison at the batch BASELINE.json's configs 4 / 5 run at (full grids, every SM busy, the

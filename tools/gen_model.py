@@ -230,6 +230,12 @@ def main():
     assert f1["shape"] == "box" and np.allclose(rows[9]["dims"], f1["dims"])
     w("#define PMG_FINGER_HALF   { %s }" % fmt(f1["dims"] / 2))
     w("#define PMG_FINGER_FRICTION %s" % fmt([f1["friction"]]))
+    gb = rows[7]
+    assert gb["shape"] == "cylinder"
+    w("/* gripper base: a cylinder about its z axis centred on its link frame (iiwa14_parallel_jaw.urdf:399-416, no <contact> tag) */")
+    w("#define PMG_GBASE_RADIUS   %s" % fmt([gb["dims"][0]]))
+    w("#define PMG_GBASE_HALF_LEN %s" % fmt([gb["dims"][1] / 2]))
+    w("#define PMG_GBASE_FRICTION %s" % fmt([gb["friction"]]))
     w("/* static boxes: table (kuka_single_step_base_env.py:49) and the robot's own 'plane' base link */")
     w("#define PMG_TABLE_CENTER  { -0.52, 0.0, 0.08 }")
     w("#define PMG_TABLE_HALF    { %s }" % fmt(table["dims"] / 2))
