@@ -958,7 +958,10 @@ __device__ __noinline__ float contact_sweep_multi(Grp g, SM& sm, int nrow_it, in
 #pragma unroll 1
     for (int gi = SM::SPTS; gi < ngen; gi++) normal_row(sm.spill_row(gi * 3), sm.glist[gi]);
   }
-  // (no barrier: a static point's impulses are private to its lane, a general point's are written identically by all)
+  // A static point's impulses are private to its lane; a general point's normal impulse was just stored by every lane
+  // of the octet (the same value) and is read back by the friction pass: one octet barrier orders those accesses
+  // (racecheck reports the unordered identical stores as hazards), only when there are such points.
+  if (ngen) g.sync();
   // ---- friction rows: the two tangent rows of a point projected together onto the cone ----
   {
     // (The records are fetched point by point: holding all four points' friction records at once -- 84 registers --

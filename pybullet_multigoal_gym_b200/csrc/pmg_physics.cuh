@@ -873,7 +873,8 @@ __device__ int box_cyl(V3 pa, const M3& Ra, V3 ha, V3 pb, const M3& Rb, float r,
 
 // Cylinder A (axis = its local z) against box B: box_cyl with the roles exchanged, its contacts turned round to this
 // file's convention (point on B, normal on B pointing from B towards A).  The gripper base against a block.
-__device__ __forceinline__ int cyl_box(V3 pa, const M3& Ra, float r, float h, V3 pb, const M3& Rb, V3 hb, Contact* out) {
+// Out of line: it runs only while the base is within reach of a block, and its code stays out of the narrowphase loop.
+__device__ __noinline__ int cyl_box(V3 pa, const M3& Ra, float r, float h, V3 pb, const M3& Rb, V3 hb, Contact* out) {
   const int n = box_cyl(pb, Rb, hb, pa, Ra, r, h, out);
   for (int i = 0; i < n; i++) {
     out[i].pB = out[i].pB + out[i].dist * out[i].nB;  // point on the box = point on the cylinder + n * distance
