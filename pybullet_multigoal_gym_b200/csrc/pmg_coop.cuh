@@ -19,8 +19,11 @@
 //     replicated on a gathered delta-velocity vector (no shuffles on a path that usually runs diverged);
 //   * narrowphase: lanes over collision pairs; Push / PickAndPlace (EnvSmemT<1>) add the block body, four
 //     more pairs and rows with a block end point, specialised by which ends a row has;
-//   * nothing lives in local memory: per-lane state is ~100 registers, exchange goes through shuffles
-//     and 3.3 KB (Reach) / 7.1 KB (one block) of shared memory per environment.
+//   * no per-thread work arrays in local memory: per-lane state is ~100 registers, exchange goes through shuffles and
+//     3.6 KB (Reach) / 7.1 KB (one block) / 13.4 KB (four blocks) of shared memory per environment (what remains in
+//     local memory are ptxas' register spills: ~100 bytes per thread in the Reach kernel at its 128-register budget,
+//     none in the one-block kernels, ~40 bytes in the multi-block kernels);
+//   * multi-block scenes (NBLK = 2..5): lane b owns block b and solves its static (table / floor) rows on its own.
 // The arithmetic is the same system the thread-per-env kernel (pmg_sim.cuh) and the oracle solve --
 // reference call sequence robots/kuka.py:167-225, envs/base_envs/base_env.py:215-219 -- organised for
 // lanes; the group primitives below are the only device-specific part, and tests/emu/ runs this very
