@@ -318,7 +318,7 @@ __global__ void __launch_bounds__(64, COOP_MIN_BLOCKS / 2) step_kernel_coop_reac
   if (grp >= io.epb || env >= io.batch) return;   // a whole octet leaves together (exited threads do not hold up the block barrier)
   coop::Grp g;
   g.lane = lane32 & (coop::GL - 1); g.shift = grp * coop::GL; g.mask = 0xffu << g.shift;
-  coop::EnvSmem& sm = reinterpret_cast<coop::EnvSmem*>(coop_smem + COOP_TABLE_BYTES)[warp * io.epb + grp];
+  coop::EnvSmem& sm = *reinterpret_cast<coop::EnvSmem*>(coop_smem + COOP_TABLE_BYTES + (warp * io.epb + grp) * coop::env_stride<coop::EnvSmem>());
   coop::step_env_reach<JC>(g, sm, lane_consts, io, env);
 }
 
@@ -336,7 +336,7 @@ __global__ void __launch_bounds__(64, 3) step_kernel_coop_block(StepIO io) {
   if (grp >= io.epb || env >= io.batch) return;   // a whole octet leaves together (exited threads do not hold up the block barrier)
   coop::Grp g;
   g.lane = lane32 & (coop::GL - 1); g.shift = grp * coop::GL; g.mask = 0xffu << g.shift;
-  coop::EnvSmemT<1, TASK == 5>& sm = reinterpret_cast<coop::EnvSmemT<1, TASK == 5>*>(coop_smem + COOP_TABLE_BYTES)[warp * io.epb + grp];
+  coop::EnvSmemT<1, TASK == 5>& sm = *reinterpret_cast<coop::EnvSmemT<1, TASK == 5>*>(coop_smem + COOP_TABLE_BYTES + (warp * io.epb + grp) * coop::env_stride<coop::EnvSmemT<1, TASK == 5>>());
   coop::step_env_block<TASK>(g, sm, lane_consts, io, env);
 }
 
@@ -353,7 +353,7 @@ __global__ void __launch_bounds__(128, 1) step_kernel_coop_multi(StepIO io) {
   if (grp >= io.epb || env >= io.batch) return;   // a whole octet leaves together (exited threads do not hold up the block barrier)
   coop::Grp g;
   g.lane = lane32 & (coop::GL - 1); g.shift = grp * coop::GL; g.mask = 0xffu << g.shift;
-  coop::EnvSmemT<NBLK>& sm = reinterpret_cast<coop::EnvSmemT<NBLK>*>(coop_smem + COOP_TABLE_BYTES)[warp * io.epb + grp];
+  coop::EnvSmemT<NBLK>& sm = *reinterpret_cast<coop::EnvSmemT<NBLK>*>(coop_smem + COOP_TABLE_BYTES + (warp * io.epb + grp) * coop::env_stride<coop::EnvSmemT<NBLK>>());
   coop::step_env_multi<NBLK>(g, sm, lane_consts, io, env);
 }
 
@@ -911,9 +911,9 @@ void launch_step(pmg_handle* h, const StepIO& io_in, cudaStream_t st) {
       else cudaFuncSetAttribute(step_kernel_coop_reach<false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
       h->hinted = true;
     }
-    io.epb = h->jc ? coop_geometry(h, step_kernel_coop_reach<true>, COOP_TABLE_BYTES, sizeof(coop::EnvSmem), 2)
-                   : coop_geometry(h, step_kernel_coop_reach<false>, COOP_TABLE_BYTES, sizeof(coop::EnvSmem), 2);
-    const CoopLaunch cl = coop_launch(h, COOP_TABLE_BYTES, sizeof(coop::EnvSmem));
+    io.epb = h->jc ? coop_geometry(h, step_kernel_coop_reach<true>, COOP_TABLE_BYTES, coop::env_stride<coop::EnvSmem>(), 2)
+                   : coop_geometry(h, step_kernel_coop_reach<false>, COOP_TABLE_BYTES, coop::env_stride<coop::EnvSmem>(), 2);
+    const CoopLaunch cl = coop_launch(h, COOP_TABLE_BYTES, coop::env_stride<coop::EnvSmem>());
     if (h->jc) step_kernel_coop_reach<true><<<cl.blocks, cl.threads, cl.smem, st>>>(io);
     else step_kernel_coop_reach<false><<<cl.blocks, cl.threads, cl.smem, st>>>(io);
     return;
@@ -921,12 +921,12 @@ void launch_step(pmg_handle* h, const StepIO& io_in, cudaStream_t st) {
   if constexpr (TASK == 3 && NBLK >= 2) {
     if (h->coop_stack && !h->jc) {
       if (!h->hinted) {
-        cudaFuncSetAttribute(step_kernel_coop_multi<NBLK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(COOP_TABLE_BYTES + 4 * sizeof(coop::EnvSmemT<NBLK>)));
+        cudaFuncSetAttribute(step_kernel_coop_multi<NBLK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(COOP_TABLE_BYTES + 4 * coop::env_stride<coop::EnvSmemT<NBLK>>()));
         cudaFuncSetAttribute(step_kernel_coop_multi<NBLK>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
         h->hinted = true;
       }
-      io.epb = coop_geometry(h, step_kernel_coop_multi<NBLK>, COOP_TABLE_BYTES, sizeof(coop::EnvSmemT<NBLK>), 4);
-      const CoopLaunch cl = coop_launch(h, COOP_TABLE_BYTES, sizeof(coop::EnvSmemT<NBLK>));
+      io.epb = coop_geometry(h, step_kernel_coop_multi<NBLK>, COOP_TABLE_BYTES, coop::env_stride<coop::EnvSmemT<NBLK>>(), 4);
+      const CoopLaunch cl = coop_launch(h, COOP_TABLE_BYTES, coop::env_stride<coop::EnvSmemT<NBLK>>());
       step_kernel_coop_multi<NBLK><<<cl.blocks, cl.threads, cl.smem, st>>>(io);
       return;
     }
@@ -943,13 +943,13 @@ void launch_step(pmg_handle* h, const StepIO& io_in, cudaStream_t st) {
       h->hinted = true;
     }
     if (h->cfg.task == PMG_SLIDE) {  // Push's layout with the long table and the puck (EnvSmemT<1, true>)
-      io.epb = coop_geometry(h, step_kernel_coop_block<5>, COOP_TABLE_BYTES, sizeof(coop::EnvSmemT<1, true>), 2);
-      const CoopLaunch cl = coop_launch(h, COOP_TABLE_BYTES, sizeof(coop::EnvSmemT<1, true>));
+      io.epb = coop_geometry(h, step_kernel_coop_block<5>, COOP_TABLE_BYTES, coop::env_stride<coop::EnvSmemT<1, true>>(), 2);
+      const CoopLaunch cl = coop_launch(h, COOP_TABLE_BYTES, coop::env_stride<coop::EnvSmemT<1, true>>());
       step_kernel_coop_block<5><<<cl.blocks, cl.threads, cl.smem, st>>>(io);
       return;
     }
-    io.epb = coop_geometry(h, step_kernel_coop_block<TASK == 2 ? 2 : 1>, COOP_TABLE_BYTES, sizeof(coop::EnvSmemT<1>), 2);
-    const CoopLaunch cl = coop_launch(h, COOP_TABLE_BYTES, sizeof(coop::EnvSmemT<1>));
+    io.epb = coop_geometry(h, step_kernel_coop_block<TASK == 2 ? 2 : 1>, COOP_TABLE_BYTES, coop::env_stride<coop::EnvSmemT<1>>(), 2);
+    const CoopLaunch cl = coop_launch(h, COOP_TABLE_BYTES, coop::env_stride<coop::EnvSmemT<1>>());
     step_kernel_coop_block<TASK == 2 ? 2 : 1><<<cl.blocks, cl.threads, cl.smem, st>>>(io);
     return;
   }

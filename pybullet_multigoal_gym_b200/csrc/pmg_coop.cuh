@@ -82,6 +82,21 @@ struct __align__(16) EnvSmemT : RowSpill<NBLK>, GenList<NBLK> {
   __device__ __forceinline__ float* spill_row(int r) { return this->spill + (r - SPTS * 3) * ROW_W; }  // r >= 3 SPTS
 };
 using EnvSmem = EnvSmemT<0>;
+// Distance between the shared-memory copies of the environments of one block.  The four octets of a warp execute every
+// shared-memory instruction together, each on its own copy at the same offset; sizeof(EnvSmemT<0>) and <1> are 16 banks
+// mod 32, which puts octets 0 / 2 and 1 / 3 on the same banks: every LDS / STS of the kernel a 2-way conflict
+// (ncu: 124 M conflict wavefronts per Push launch).  A stride of 24 banks (96 bytes mod 128) lays the octets' banks
+// side by side (0, 24, 16, 8): conflict-free for every access in which an octet touches <= 8 consecutive banks.
+template <class SM>
+__host__ __device__ constexpr size_t env_stride() {
+#ifdef PMG_ENV_STRIDE_PLAIN
+  return sizeof(SM);
+#else
+  size_t s = sizeof(SM);
+  while (s % 128 != 96) s += 16;
+  return s;
+#endif
+}
 constexpr int BK_POS = 0, BK_QUAT = 3, BK_V = 7, BK_W = 10, BK_R = 13;
 
 // ---- the group (octet) interface ---------------------------------------------------------------
