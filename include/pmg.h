@@ -214,6 +214,14 @@ int pmg_kernel_time_ms(pmg_handle* h, double* total_ms, int64_t* count);
  * the table and the floor; results must be bit-identical to stat = 0). */
 int pmg_debug_box_box(const float* in_host, int64_t n, int32_t stat, float* out_host, int32_t device);
 
+/* replaces: `assert self.action_space.contains(a)` (kuka.py:168) on the DEVICE path, without a host round trip per step:
+ * every step kernel tests its environments' action rows against Box(-1, 1) (NaN fails) and raises a word in mapped host
+ * memory; the step itself still runs with the action as given.  Returns 1 if any step COMPLETED so far saw such an
+ * action (the caller decides when to look: after a synchronise for an exact answer, or at the next call for an
+ * asynchronous one, as CUDA reports its own errors); clear != 0 resets the word.  pmg_step_host* check their host
+ * buffer before launching and return PMG_ERR_INVALID at once. */
+int pmg_action_error(pmg_handle* h, int32_t clear);
+
 /* number of kernels this library has launched on the handle since creation */
 int64_t pmg_launch_count(const pmg_handle* h);
 /* contact points dropped because a per-env scratch pool overflowed (0 in every shipped config) */

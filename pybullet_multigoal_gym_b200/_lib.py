@@ -17,7 +17,7 @@ SYMBOLS = [
     "pmg_abi_version", "pmg_last_error", "pmg_create", "pmg_destroy", "pmg_dims", "pmg_seed",
     "pmg_reset", "pmg_set_device_rng", "pmg_reset_device", "pmg_set_auto_reset", "pmg_spawn_width", "pmg_last_spawn", "pmg_set_curriculum_update", "pmg_get_curriculum", "pmg_set_sub_goal", "pmg_step", "pmg_gather_create", "pmg_gather_connect", "pmg_gather_layout", "pmg_step_gather", "pmg_step_host", "pmg_step_host_blocks",
     "pmg_compute_reward", "pmg_her_sample", "pmg_her_relabel", "pmg_state_width", "pmg_get_state", "pmg_set_state",
-    "pmg_kernel_timing", "pmg_kernel_time_ms", "pmg_launch_count", "pmg_overflow_count", "pmg_debug_box_box",
+    "pmg_kernel_timing", "pmg_kernel_time_ms", "pmg_launch_count", "pmg_overflow_count", "pmg_debug_box_box", "pmg_action_error",
 ]
 
 
@@ -67,6 +67,7 @@ def load():
     L.pmg_step_gather.argtypes = [vp, fp, C.POINTER(vp), vp]
     L.pmg_step_host.argtypes = [vp, fp, fp, fp, u8p, u8p, vp]
     L.pmg_debug_box_box.argtypes = [fp, C.c_int64, C.c_int32, fp, C.c_int32]
+    L.pmg_action_error.argtypes = [vp, C.c_int32]
     L.pmg_step_host_blocks.argtypes = [vp, fp, fp, fp, u8p, u8p, vp]
     L.pmg_compute_reward.argtypes = [fp, fp, C.c_int64, C.c_int32, C.c_float, C.c_int32, fp, u8p, vp]
     L.pmg_her_sample.argtypes = [C.c_int64, C.c_int32, C.c_int32, C.c_float, C.c_uint64, vp, vp, vp, vp]

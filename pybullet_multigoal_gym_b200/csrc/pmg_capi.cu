@@ -232,6 +232,7 @@ __global__ void __launch_bounds__(32) step_kernel(StepIO io) {
   using D = Dims<TASK, NBLK>;
   const int i = env_of_thread(io);
   const size_t B = io.batch;
+  if (i >= 0) check_action_row(io, i, 0, 1);
   Env<NBLK> e;
   float ee0[3];
   if (io.bulk) {  // full warps only (epw == 32, batch % 32 == 0): no idle lanes on this path
@@ -319,6 +320,7 @@ __global__ void __launch_bounds__(64, COOP_MIN_BLOCKS / 2) step_kernel_coop_reac
   coop::Grp g;
   g.lane = lane32 & (coop::GL - 1); g.shift = grp * coop::GL; g.mask = 0xffu << g.shift;
   coop::EnvSmem& sm = *reinterpret_cast<coop::EnvSmem*>(coop_smem + COOP_TABLE_BYTES + (warp * io.epb + grp) * coop::env_stride<coop::EnvSmem>());
+  check_action_row(io, env, g.lane, coop::GL);
   coop::step_env_reach<JC>(g, sm, lane_consts, io, env);
 }
 
@@ -337,6 +339,7 @@ __global__ void __launch_bounds__(64, 3) step_kernel_coop_block(StepIO io) {
   coop::Grp g;
   g.lane = lane32 & (coop::GL - 1); g.shift = grp * coop::GL; g.mask = 0xffu << g.shift;
   coop::EnvSmemT<1, TASK == 5>& sm = *reinterpret_cast<coop::EnvSmemT<1, TASK == 5>*>(coop_smem + COOP_TABLE_BYTES + (warp * io.epb + grp) * coop::env_stride<coop::EnvSmemT<1, TASK == 5>>());
+  check_action_row(io, env, g.lane, coop::GL);
   coop::step_env_block<TASK>(g, sm, lane_consts, io, env);
 }
 
@@ -354,6 +357,7 @@ __global__ void __launch_bounds__(128, 1) step_kernel_coop_multi(StepIO io) {
   coop::Grp g;
   g.lane = lane32 & (coop::GL - 1); g.shift = grp * coop::GL; g.mask = 0xffu << g.shift;
   coop::EnvSmemT<NBLK>& sm = *reinterpret_cast<coop::EnvSmemT<NBLK>*>(coop_smem + COOP_TABLE_BYTES + (warp * io.epb + grp) * coop::env_stride<coop::EnvSmemT<NBLK>>());
+  check_action_row(io, env, g.lane, coop::GL);
   coop::step_env_multi<NBLK>(g, sm, lane_consts, io, env);
 }
 
@@ -719,6 +723,7 @@ struct pmg_handle {
   unsigned g_seq = 0;
   unsigned* d_g_counter = nullptr;
   int* g_err_host = nullptr; int* g_err_dev = nullptr;
+  int* bad_host = nullptr; int* bad_dev = nullptr;  // mapped host word the step kernels raise on an out-of-range action
   size_t g_parity_bytes = 0, g_off_reward = 0, g_off_done = 0, g_off_success = 0, g_flags_off = 0, g_total = 0;
   // optional CUDA-event timing of the step kernel alone (pmg_kernel_timing): a ring of event pairs on the launch stream
   bool timing = false;
@@ -842,6 +847,7 @@ StepIO make_io(pmg_handle* h, const float* action, float* obs, float* reward, ui
   io.grasp = h->grasp; io.jc = h->jc; io.grip_goal = h->grip; io.td = h->td || h->cur; io.cur = h->cur;
   io.adim = h->A; io.goal_dim = h->G; io.row_width = h->W;
   io.g_n = 0; io.g_in_step = 0; io.g_world = 0; io.g_seq = 0; io.g_flags_local = nullptr; io.g_counter = nullptr; io.g_err = nullptr;
+  io.bad_action = h->bad_dev;
   return io;
 }
 
@@ -1080,6 +1086,9 @@ int pmg_create(const pmg_config* cfg, pmg_handle** out) {
   ALLOC(h->d_spawn, sizeof(float) * h->spawn_w * B);
   ALLOC(h->d_mask, B);
   ALLOC(h->d_overflow, sizeof(int));
+  if (cudaHostAlloc((void**)&h->bad_host, sizeof(int), cudaHostAllocMapped) != cudaSuccess ||
+      cudaHostGetDevicePointer((void**)&h->bad_dev, h->bad_host, 0) != cudaSuccess) { pmg_destroy(h); return fail(PMG_ERR_CUDA, "pmg_create: cannot map the action-error word%s"); }
+  *h->bad_host = 0;
   ALLOC(h->d_episode, sizeof(uint32_t) * B);
   ALLOC(h->d_spawn_dev, sizeof(float) * h->spawn_w * B);
   if (h->cfg.task == PMG_SLIDE && !h->coop_block) { pmg_destroy(h); return fail(PMG_ERR_INVALID, "pmg_create: slide runs on the lane-cooperative kernel only (PMG_COOP_BLOCK=0 is set)%s"); }
@@ -1122,6 +1131,7 @@ int pmg_destroy(pmg_handle* h) {
   }
   cudaFree(h->d_g_counter);
   if (h->g_err_host) cudaFreeHost(h->g_err_host);
+  if (h->bad_host) cudaFreeHost(h->bad_host);
   for (auto& e : h->t_ev) cudaEventDestroy(e);
   cudaFree(h->d_action); cudaFree(h->d_obs); cudaFree(h->d_blocks); cudaFree(h->d_reward); cudaFree(h->d_done); cudaFree(h->d_success);
   if (h->h_spawn) cudaFreeHost(h->h_spawn);
@@ -1366,11 +1376,17 @@ int pmg_step_gather(pmg_handle* h, const float* action_dev, void** gathered_dev_
   return PMG_OK;
 }
 
+static bool host_actions_in_box(const float* a, size_t n) {  // kuka.py:168: action_space.contains(a); NaN fails
+  for (size_t i = 0; i < n; i++) if (!(a[i] >= -1.0f && a[i] <= 1.0f)) return false;
+  return true;
+}
+
 int pmg_step_host(pmg_handle* h, const float* action_host, float* obs_host, float* reward_host, uint8_t* done_host, uint8_t* success_host, void* stream) {
   if (!h || !action_host || !obs_host || !reward_host || !done_host || !success_host) return fail(PMG_ERR_INVALID, "pmg_step_host: null argument%s");
   cudaStream_t st = (cudaStream_t)stream;
   CUDA_TRY(cudaSetDevice(h->cfg.device));
   const size_t B = h->cfg.batch;
+  if (!host_actions_in_box(action_host, (size_t)h->A * B)) return fail(PMG_ERR_INVALID, "pmg_step_host: action outside the action space Box(-1, 1)%s");
   CUDA_TRY(cudaMemcpyAsync(h->d_action, action_host, sizeof(float) * h->A * B, cudaMemcpyHostToDevice, st));
   int rc = pmg_step(h, h->d_action, h->d_obs, h->d_reward, h->d_done, h->d_success, stream);
   if (rc != PMG_OK) return rc;
@@ -1388,6 +1404,7 @@ int pmg_step_host_blocks(pmg_handle* h, const float* action_host, float* blocks_
   cudaStream_t st = (cudaStream_t)stream;
   CUDA_TRY(cudaSetDevice(h->cfg.device));
   const size_t B = h->cfg.batch;
+  if (!host_actions_in_box(action_host, (size_t)h->A * B)) return fail(PMG_ERR_INVALID, "pmg_step_host_blocks: action outside the action space Box(-1, 1)%s");
   CUDA_TRY(cudaMemcpyAsync(h->d_action, action_host, sizeof(float) * h->A * B, cudaMemcpyHostToDevice, st));
   int rc = pmg_step(h, h->d_action, h->d_obs, h->d_reward, h->d_done, h->d_success, stream);
   if (rc != PMG_OK) return rc;
@@ -1520,6 +1537,13 @@ int pmg_debug_coop_cycles(unsigned long long* out16) {
   return cudaMemcpyToSymbol(pmg::g_coop_cycles, zero, sizeof zero) == cudaSuccess ? 0 : -2;
 }
 #endif
+
+int pmg_action_error(pmg_handle* h, int32_t clear) {
+  if (!h) return 0;
+  const int v = *(volatile int*)h->bad_host;
+  if (clear) *(volatile int*)h->bad_host = 0;
+  return v != 0;
+}
 
 int64_t pmg_overflow_count(pmg_handle* h) {
   if (!h) return 0;

@@ -655,7 +655,16 @@ struct StepIO {
   const unsigned* g_flags_local;  // the world flag words of the own buffer
   unsigned* g_counter;   // arrivals of this launch (one per environment), reset by the last one
   int* g_err;            // mapped host word: set when a peer's flag did not arrive in time
+  int* bad_action;       // mapped host word: set when an action entry lies outside [-1, 1] (NaN included); see pmg_action_error
 };
+
+// Box(-1, 1).contains of one environment's action row (kuka.py:168 asserts it), by the `nl` lanes that own the environment
+__device__ __forceinline__ void check_action_row(const StepIO& io, int env, int lane, int nl) {
+  const float* a = io.action + (size_t)env * io.adim;
+  bool bad = false;
+  for (int k = lane; k < io.adim; k += nl) bad = bad || !(a[k] >= -1.0f && a[k] <= 1.0f);
+  if (bad) *(volatile int*)io.bad_action = 1;
+}
 
 #ifndef PMG_EMULATE
 // Called once per environment after its row, reward and flags are stored locally AND on the peers.  The last arrival

@@ -324,9 +324,11 @@ class KukaBulletMGEnv:
             raise ActionError("action outside the action space Box(-1, 1, (%d,))" % self.action_dim)
 
     def step(self, action):
-        """base_env.py:130-138 + TimeLimit.  CUDA tensor in -> CUDA tensors out (asynchronous on the current stream
-        when the env was made with check_actions=False; the range check of the default reads a flag back, i.e.
-        synchronises); numpy / CPU tensor in -> numpy out through the host-buffer C-ABI call."""
+        """base_env.py:130-138 + TimeLimit.  CUDA tensor in -> CUDA tensors out, asynchronous on the current stream: the
+        action-space check of the reference (kuka.py:168) runs inside the step kernel, which raises a flag in mapped
+        host memory; it is looked at here WITHOUT synchronising, so an out-of-range action raises ActionError at the
+        first later step / `action_error()` call that finds its kernel finished (the way CUDA reports its own errors).
+        numpy / CPU tensor in -> numpy out through the host-buffer C-ABI call, checked before anything is launched."""
         if torch.is_tensor(action) and action.is_cuda:
             return self._step_device(action)
         a = np.asarray(action.numpy() if torch.is_tensor(action) else action, dtype=np.float32)
@@ -370,8 +372,8 @@ class KukaBulletMGEnv:
         if tuple(action.shape) != (self.batch, self.action_dim):
             raise ActionError("action must have shape (%d, %d)" % (self.batch, self.action_dim))
         action = action.to(dtype=torch.float32).contiguous()
-        if self.check_actions and not bool(((action >= -1.0) & (action <= 1.0)).all()):  # NaN fails the test, like Box.contains
-            raise ActionError("action outside the action space Box(-1, 1, (%d,))" % self.action_dim)
+        if self.check_actions and self._L.pmg_action_error(self._h, 1):  # raised by the kernel of an EARLIER step (no sync here)
+            raise ActionError("an earlier step was given an action outside the action space Box(-1, 1, (%d,))" % self.action_dim)
         with torch.cuda.device(self.device):
             out = torch.empty((self.batch, self.row_width), dtype=torch.float32, device=self.device)
             reward = torch.empty((self.batch,), dtype=torch.float32, device=self.device)
@@ -384,6 +386,13 @@ class KukaBulletMGEnv:
         if self._terminal is not None:
             info["terminal_observation"] = self._split(self._terminal)
         return obs, reward, done, info
+
+    def action_error(self, synchronize=True):
+        """True if a device-path step was given an action outside Box(-1, 1) (NaN included) since the last query;
+        synchronises the device first by default, so that the answer covers every step enqueued so far."""
+        if synchronize:
+            torch.cuda.synchronize(self.device)
+        return bool(self._L.pmg_action_error(self._h, 1))
 
     def step_packed(self, action, out, reward, done, success):
         """Zero-allocation device path: caller-owned CUDA buffers (used by bench.py and the sharded env)."""

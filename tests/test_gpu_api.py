@@ -165,3 +165,27 @@ def test_both_host_buffer_entry_points_agree():
         assert np.array_equal(obs["observation"], packed[:, :O]) and np.array_equal(obs["policy_state"], packed[:, O:O + P])
         assert np.array_equal(obs["achieved_goal"], packed[:, O + P:O + P + G]) and np.array_equal(obs["desired_goal"], packed[:, O + P + G:])
         assert np.array_equal(r2.astype(np.float32), r) and np.array_equal(d2, d.astype(bool)) and np.array_equal(info["goal_achieved"], s.astype(bool))
+
+
+def test_device_path_action_check_runs_in_the_kernel():
+    """kuka.py:168 asserts action_space.contains(a).  On the device path the step kernel tests the action rows itself
+    and raises a flag in mapped host memory (pmg_action_error): no host synchronisation per step; the error surfaces
+    at the next step that finds the kernel finished, or on demand through env.action_error()."""
+    import torch
+    import pybullet_multigoal_gym_b200 as pmg
+    for task, bad in (("reach", 1.5), ("pick_and_place", float("nan")), ("block_stack", -1.01)):
+        env = pmg.make_env(task=task, batch=37, num_block=2)
+        env.reset()
+        a = torch.zeros((37, env.action_dim), device="cuda")
+        env.step(a)
+        assert not env.action_error()
+        a[23, env.action_dim - 1] = bad
+        env.step(a)                      # runs, flagged by the kernel
+        torch.cuda.synchronize()
+        with pytest.raises(pmg.ActionError):
+            env.step(torch.zeros_like(a))
+        assert not env.action_error()    # the query cleared it
+        env.step(torch.zeros_like(a))
+        with pytest.raises(ValueError):  # host-buffer path: checked before anything is launched
+            env.step(np.full((37, env.action_dim), 2.0, np.float32))
+        env.close()
