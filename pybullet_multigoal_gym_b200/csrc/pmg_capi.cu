@@ -81,13 +81,13 @@ __device__ void load_env(Env<NBLK>& e, const StepIO& io, int i, const float* s, 
     e.bv[b] = v3(bs[7 * B], bs[8 * B], bs[9 * B]);
     e.bw[b] = v3(bs[10 * B], bs[11 * B], bs[12 * B]);
   }
-  e.man = io.manifold + i; e.stride = io.batch; e.overflow = 0;
+  e.man = io.manifold + man_off(io, i); e.stride = io.tile; e.overflow = 0;
 }
 
 template <int TASK, int NBLK>
 __device__ void store_env(const Env<NBLK>& e, const StepIO& io, int i) {
-  const size_t B = io.batch;
-  float* s = io.state + i;
+  const size_t B = io.tile;  // distance between consecutive words of an environment (StepIO::tile)
+  float* s = io.state + state_off(io, i);
 #pragma unroll
   for (int k = 0; k < ND; k++) {
     s[(ST_Q + k) * B] = e.q[k]; s[(ST_QD + k) * B] = e.qd[k];
@@ -144,7 +144,7 @@ __device__ __forceinline__ void gather_finish_thread(const StepIO& io, int i) {
 template <int TASK, int NBLK, bool DIRECT = false>
 __device__ float write_obs(const Env<NBLK>& e, const StepIO& io, int i) {
   using D = Dims<TASK, NBLK>;
-  const size_t B = io.batch;
+  const size_t B = io.tile;
   Frames f;
   forward_kinematics<NB>(e.q, f);
   V3 tip = tip_position(f), tv, tw;
@@ -168,7 +168,7 @@ __device__ float write_obs(const Env<NBLK>& e, const StepIO& io, int i) {
 #pragma unroll
     for (int k = 0; k < 7; k++) { row[k] = e.q[k]; row[O + k] = e.q[k]; }
   }
-  const float* goal = io.state + (size_t)(ST_BLK + 13 * NBLK) * B + i;
+  const float* goal = io.state + state_off(io, i) + (size_t)(ST_BLK + 13 * NBLK) * B;
   for (int k = 0; k < G; k++) dg[k] = goal[k * B];
   if (TASK == 0) {
     obs[0] = pol[0] = ag[0] = tip.x; obs[1] = pol[1] = ag[1] = tip.y; obs[2] = pol[2] = ag[2] = tip.z;
@@ -231,7 +231,7 @@ template <int TASK, int NBLK>
 __global__ void __launch_bounds__(32) step_kernel(StepIO io) {
   using D = Dims<TASK, NBLK>;
   const int i = env_of_thread(io);
-  const size_t B = io.batch;
+  const size_t B = io.tile;
   if (i >= 0) check_action_row(io, i, 0, 1);
   Env<NBLK> e;
   float ee0[3];
@@ -240,18 +240,18 @@ __global__ void __launch_bounds__(32) step_kernel(StepIO io) {
     __shared__ __align__(8) uint64_t bar;
     float* tile = dyn_smem + io.tile_offset;
     const int env0 = (blockIdx.x * blockDim.x + threadIdx.x) & ~31;
-    bulk_load_state_tile<D::STATE>(tile, io.state + env0, B, &bar);
+    bulk_load_state_tile<D::STATE>(tile, io.state + state_off(io, env0), B, &bar);
     const float* ts = tile + (threadIdx.x & 31);
     load_env<TASK, NBLK>(e, io, i, ts, 32);
 #pragma unroll
     for (int k = 0; k < 3; k++) ee0[k] = ts[(ST_EE + k) * 32];
   } else {
     if (i < 0) { stage_row(nullptr, io, false); return; }  // idle lanes only help the staged store
-    load_env<TASK, NBLK>(e, io, i, io.state + i, B);
+    load_env<TASK, NBLK>(e, io, i, io.state + state_off(io, i), B);
 #pragma unroll
-    for (int k = 0; k < 3; k++) ee0[k] = io.state[(ST_EE + k) * B + i];
+    for (int k = 0; k < 3; k++) ee0[k] = io.state[state_off(io, i) + (ST_EE + k) * B];
   }
-  float* s = io.state + i;
+  float* s = io.state + state_off(io, max(i, 0));
   // ---- Kuka.apply_action (kuka.py:167-222) ----
   float a[8];
 #pragma unroll
@@ -377,7 +377,7 @@ struct ResetIO {
 template <int TASK, int NBLK>
 __device__ void reset_env(const ResetIO& r, int i, bool doit) {
   const StepIO& io = r.io;
-  const size_t B = io.batch;
+  const size_t B = io.tile;
   if (r.auto_rows && r.terminal) {
     const float* src = io.obs + (size_t)i * io.row_width;
     float* dst = r.terminal + (size_t)i * io.row_width;
@@ -385,8 +385,8 @@ __device__ void reset_env(const ResetIO& r, int i, bool doit) {
   }
 
   Env<NBLK> e;
-  load_env<TASK, NBLK>(e, io, i, io.state + i, B);
-  float* s = io.state + i;
+  load_env<TASK, NBLK>(e, io, i, io.state + state_off(io, i), B);
+  float* s = io.state + state_off(io, i);
   if (doit) {
     // Kuka.robot_specific_reset (kuka.py:157-165): joints to the rest pose, rest pose <- IK(start
     // position) seeded there, joints to the new rest pose, jaws closed with their motor on.
@@ -610,18 +610,19 @@ __global__ void her_relabel_kernel(const float* ag, const float* dg, int horizon
 
 // Construction-time state: BaseBulletMGEnv.__init__ resets the robot once on its own (base_env.py:41)
 // before its first self.reset(), i.e. the rest pose (kuka.py:27) gets one IK refinement here.
-__global__ void init_state_kernel(float* state, int batch, int nblk, float tx, float ty, float tz) {
+__global__ void init_state_kernel(float* state_base, int batch, int tile, int words, int nblk, float tx, float ty, float tz) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= batch) return;
-  const size_t B = batch;
+  const size_t B = tile;  // [tile][word][env in tile], see StepIO::tile
+  float* state = state_base + (size_t)(i / tile) * words * tile + i % tile;
   float q[ND];
   for (int k = 0; k < 7; k++) q[k] = c_rest_pose0[k];
   q[7] = q[8] = 0.0f;
   const float tq[4] = {0.f, -1.f, 0.f, 0.f};
   inverse_kinematics(q, v3(tx, ty, tz), tq);
-  for (int k = 0; k < 7; k++) { state[(ST_REST + k) * B + i] = q[k]; state[(ST_Q + k) * B + i] = q[k]; }
-  for (int k = 7; k < ND; k++) state[(ST_Q + k) * B + i] = GRIPPER_ABS_LIMIT;
-  for (int b = 0; b < nblk; b++) state[(ST_BLK + 13 * b + 6) * B + i] = 1.0f;  // identity quaternion
+  for (int k = 0; k < 7; k++) { state[(ST_REST + k) * B] = q[k]; state[(ST_Q + k) * B] = q[k]; }
+  for (int k = 7; k < ND; k++) state[(ST_Q + k) * B] = GRIPPER_ABS_LIMIT;
+  for (int b = 0; b < nblk; b++) state[(ST_BLK + 13 * b + 6) * B] = 1.0f;  // identity quaternion
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -686,6 +687,9 @@ int fail(int code, const char* fmt, const char* detail = "") {
 struct pmg_handle {
   pmg_config cfg;
   int nblk, O, P, G, W, A, state_words, man_words, spawn_w;
+  int tile = 0;           // environments per tile of the state / manifold arrays (StepIO::tile)
+  size_t batch_pad = 0;   // batch rounded up to whole tiles: what the two arrays are allocated for
+  size_t state_index(size_t word, size_t env) const { return (env / tile * state_words + word) * tile + env % tile; }
   bool multi = false, grasp = false, grip = false, jc = false, td = false, cur = false;  // task variants, see pmg_config
   // curriculum state, one reference env's worth per environment (kuka_multi_step_base_env.py:122-140)
   bool cur_update = false;
@@ -839,6 +843,7 @@ void sample_spawn(pmg_handle* h, int i, float* out) {
 StepIO make_io(pmg_handle* h, const float* action, float* obs, float* reward, uint8_t* done, uint8_t* success) {
   StepIO io;
   io.state = h->d_state; io.manifold = h->d_man; io.batch = h->cfg.batch; io.state_words = h->state_words;
+  io.tile = h->tile; io.man_words = h->man_words;
   io.action = action; io.obs = obs; io.reward = reward; io.done = done; io.success = success;
   io.thr = h->cfg.distance_threshold; io.binary = h->cfg.binary_reward; io.max_steps = h->cfg.max_episode_steps;
   io.overflow = h->d_overflow; io.row_spill = h->d_row_spill;
@@ -939,7 +944,7 @@ void launch_step(pmg_handle* h, const StepIO& io_in, cudaStream_t st) {
   }
   int warps = (h->cfg.batch + h->epw - 1) / h->epw;
   size_t stage_floats = (size_t)h->epw * h->W;
-  io.bulk = (h->epw == 32 && h->cfg.batch % 32 == 0 && !h->no_bulk && !h->grip && !h->td && !h->cur) ? 1 : 0;
+  io.bulk = (h->epw == 32 && h->cfg.batch % 32 == 0 && !h->no_bulk && !h->grip && !h->td && !h->cur && h->tile != 32 / coop::GL) ? 1 : 0;
   io.tile_offset = (int)((stage_floats + 31) / 32 * 32);
   size_t smem = (io.bulk ? io.tile_offset + (size_t)Dims<TASK, NBLK>::STATE * 32 : stage_floats) * sizeof(float);
   if ((TASK == 1 || TASK == 2) && h->coop_block) {
@@ -1081,8 +1086,18 @@ int pmg_create(const pmg_config* cfg, pmg_handle** out) {
   h->rng.resize(B);
   for (size_t i = 0; i < B; i++) h->rng[i].init_genrand(5489u + (uint32_t)i);
 #define ALLOC(ptr, bytes) do { cudaError_t e_ = cudaMalloc((void**)&(ptr), (bytes)); if (e_ != cudaSuccess) { pmg_destroy(h); return fail(PMG_ERR_CUDA, "cudaMalloc: %s", cudaGetErrorString(e_)); } } while (0)
-  ALLOC(h->d_state, sizeof(float) * h->state_words * B);
-  ALLOC(h->d_man, sizeof(float) * h->man_words * B);
+  {
+    // which kernel family steps this handle (the conditions of launch_step): 4-environment tiles for the lane-cooperative
+    // kernels, 32 for the thread-per-env ones, PMG_STATE_TILE=0: the plain [word][env] arrays
+    const int t = h->cfg.task;
+    const bool coop_handle = (t == PMG_REACH && h->coop) || ((t == PMG_PUSH || t == PMG_PICK_AND_PLACE || t == PMG_SLIDE) && h->coop_block) ||
+                             (h->multi && h->nblk >= 2 && h->coop_stack && !h->jc);
+    h->tile = coop_handle ? 32 / coop::GL : 32;
+    if (const char* ev = getenv("PMG_STATE_TILE")) { if (atoi(ev) == 0) h->tile = (int)B; }
+    h->batch_pad = (B + h->tile - 1) / h->tile * h->tile;
+  }
+  ALLOC(h->d_state, sizeof(float) * h->state_words * h->batch_pad);
+  ALLOC(h->d_man, sizeof(float) * h->man_words * h->batch_pad);
   ALLOC(h->d_spawn, sizeof(float) * h->spawn_w * B);
   ALLOC(h->d_mask, B);
   ALLOC(h->d_overflow, sizeof(int));
@@ -1108,12 +1123,12 @@ int pmg_create(const pmg_config* cfg, pmg_handle** out) {
     if (cudaMallocHost((void**)&h->h_stage[k], sizeof(float) * h->spawn_w * B) != cudaSuccess ||
         cudaEventCreateWithFlags(&h->stage_done[k], cudaEventDisableTiming) != cudaSuccess) { pmg_destroy(h); return fail(PMG_ERR_CUDA, "cudaMallocHost failed%s"); }
   memset(h->h_spawn, 0, sizeof(float) * h->spawn_w * B);
-  cudaMemset(h->d_state, 0, sizeof(float) * h->state_words * B);
-  cudaMemset(h->d_man, 0, sizeof(float) * h->man_words * B);
+  cudaMemset(h->d_state, 0, sizeof(float) * h->state_words * h->batch_pad);
+  cudaMemset(h->d_man, 0, sizeof(float) * h->man_words * h->batch_pad);
   cudaMemset(h->d_overflow, 0, sizeof(int));
   cudaMemset(h->d_episode, 0, sizeof(uint32_t) * B);
   cudaMemset(h->d_spawn_dev, 0, sizeof(float) * h->spawn_w * B);
-  init_state_kernel<<<(int)((B + 31) / 32), 32>>>(h->d_state, (int)B, h->nblk, (float)h->tip_init[0], (float)h->tip_init[1], (float)h->tip_init[2]);
+  init_state_kernel<<<(int)((B + 31) / 32), 32>>>(h->d_state, (int)B, h->tile, h->state_words, h->nblk, (float)h->tip_init[0], (float)h->tip_init[1], (float)h->tip_init[2]);
   h->launches++;
   CUDA_TRY(cudaDeviceSynchronize());
   *out = h;
@@ -1256,8 +1271,11 @@ int pmg_set_sub_goal(pmg_handle* h, const int32_t* ind_host, void* stream) {
       if (ind_host[i] < -nsub || ind_host[i] >= nsub) return fail(PMG_ERR_INVALID, "pmg_set_sub_goal: list index out of range%s");
       v[i] = (float)ind_host[i];
     }
-  const size_t word = (size_t)ST_BLK + 13 * h->nblk + h->G;  // [word][env]: one contiguous row of the state
-  CUDA_TRY(cudaMemcpyAsync(h->d_state + word * B, v.data(), sizeof(float) * B, cudaMemcpyHostToDevice, st));
+  // one word of every environment: runs of `tile` floats, one per tile, (state_words * tile) floats apart
+  const size_t word = (size_t)ST_BLK + 13 * h->nblk + h->G;
+  v.resize(h->batch_pad, -1.0f);
+  CUDA_TRY(cudaMemcpy2DAsync(h->d_state + word * h->tile, sizeof(float) * h->state_words * h->tile, v.data(), sizeof(float) * h->tile,
+                             sizeof(float) * h->tile, h->batch_pad / h->tile, cudaMemcpyHostToDevice, st));
   CUDA_TRY(cudaStreamSynchronize(st));  // v is a temporary
   return PMG_OK;
 }
@@ -1464,10 +1482,10 @@ int pmg_get_state(pmg_handle* h, float* out) {
   if (!h || !out) return fail(PMG_ERR_INVALID, "pmg_get_state: null argument%s");
   CUDA_TRY(cudaSetDevice(h->cfg.device));
   const size_t B = h->cfg.batch, Wd = h->state_words;
-  std::vector<float> tmp(B * Wd);
+  std::vector<float> tmp(h->batch_pad * Wd);
   CUDA_TRY(cudaDeviceSynchronize());
-  CUDA_TRY(cudaMemcpy(tmp.data(), h->d_state, sizeof(float) * B * Wd, cudaMemcpyDeviceToHost));
-  for (size_t i = 0; i < B; i++) for (size_t w = 0; w < Wd; w++) out[i * Wd + w] = tmp[w * B + i];
+  CUDA_TRY(cudaMemcpy(tmp.data(), h->d_state, sizeof(float) * h->batch_pad * Wd, cudaMemcpyDeviceToHost));
+  for (size_t i = 0; i < B; i++) for (size_t w = 0; w < Wd; w++) out[i * Wd + w] = tmp[h->state_index(w, i)];
   return PMG_OK;
 }
 
@@ -1475,11 +1493,11 @@ int pmg_set_state(pmg_handle* h, const float* in) {
   if (!h || !in) return fail(PMG_ERR_INVALID, "pmg_set_state: null argument%s");
   CUDA_TRY(cudaSetDevice(h->cfg.device));
   const size_t B = h->cfg.batch, Wd = h->state_words;
-  std::vector<float> tmp(B * Wd);
-  for (size_t i = 0; i < B; i++) for (size_t w = 0; w < Wd; w++) tmp[w * B + i] = in[i * Wd + w];
+  std::vector<float> tmp(h->batch_pad * Wd, 0.0f);
+  for (size_t i = 0; i < B; i++) for (size_t w = 0; w < Wd; w++) tmp[h->state_index(w, i)] = in[i * Wd + w];
   CUDA_TRY(cudaDeviceSynchronize());
-  CUDA_TRY(cudaMemcpy(h->d_state, tmp.data(), sizeof(float) * B * Wd, cudaMemcpyHostToDevice));
-  CUDA_TRY(cudaMemset(h->d_man, 0, sizeof(float) * h->man_words * B));
+  CUDA_TRY(cudaMemcpy(h->d_state, tmp.data(), sizeof(float) * h->batch_pad * Wd, cudaMemcpyHostToDevice));
+  CUDA_TRY(cudaMemset(h->d_man, 0, sizeof(float) * h->man_words * h->batch_pad));
   h->was_reset = true;
   return PMG_OK;
 }

@@ -1529,6 +1529,30 @@ __device__ void substep(const Grp& g, SM& sm, Lane& L) {
 #endif
 }
 
+// ---- persistent manifolds between HBM and shared memory ------------------------------------------------------
+// Only what exists is moved: every pair's point count, and the 10 words of each cached point (a contact-free Reach
+// environment: 2 words instead of 82; a block-stack scene at rest: 28 counts + 16 points instead of 1148 words).  Words
+// beyond a pair's count are never read (manifold_add / manifold_refresh / the row set-up all stop at the count).
+template <int NPAIRS>
+__device__ __forceinline__ void load_manifolds(const Grp& g, float* sman, const float* mg, size_t B) {
+  for (int k = g.lane; k < NPAIRS; k += GL) sman[k * MAN_WORDS] = mg[(size_t)(k * MAN_WORDS) * B];
+  g.sync();
+#pragma unroll 1
+  for (int k = 0; k < NPAIRS; k++) {
+    const int n = __float_as_int(sman[k * MAN_WORDS]);
+    for (int w = 1 + g.lane; w < 1 + 10 * n; w += GL) sman[k * MAN_WORDS + w] = mg[(size_t)(k * MAN_WORDS + w) * B];
+  }
+}
+template <int NPAIRS>
+__device__ __forceinline__ void store_manifolds(const Grp& g, const float* sman, float* mg, size_t B) {
+  for (int k = g.lane; k < NPAIRS; k += GL) mg[(size_t)(k * MAN_WORDS) * B] = sman[k * MAN_WORDS];
+#pragma unroll 1
+  for (int k = 0; k < NPAIRS; k++) {
+    const int n = __float_as_int(sman[k * MAN_WORDS]);
+    for (int w = 1 + g.lane; w < 1 + 10 * n; w += GL) mg[(size_t)(k * MAN_WORDS + w) * B] = sman[k * MAN_WORDS + w];
+  }
+}
+
 // ---- fused gather: the octet copies its finished row, reward and flags to the peers' gather buffers -------------
 // (multi-GPU sharding, include/pmg.h pmg_step_gather).  The row was just written to this rank's own buffer by lanes
 // of this octet; after the octet barrier the 8 lanes copy it with 32-byte segments to every peer over NVLink, then
@@ -1558,8 +1582,8 @@ __device__ void step_env_reach(const Grp& g, EnvSmem& sm, const float* lane_cons
   using D = Dims<0, 0>;
   const int lane = g.lane;
   const bool arm = lane < 7, hand = lane == 7;
-  const size_t B = io.batch;
-  float* s = io.state + env;
+  const size_t B = io.tile;  // distance between consecutive words of this environment (StepIO::tile)
+  float* s = io.state + state_off(io, env);
   Lane L;
   L.lc = lane_consts + lane * LC_W;
   L.dof0 = lane;  // lane 7 -> dof 7 (finger1); it also owns dof 8 in slot 1
@@ -1567,7 +1591,7 @@ __device__ void step_env_reach(const Grp& g, EnvSmem& sm, const float* lane_cons
   L.q1 = hand ? s[(ST_Q + 8) * B] : 0.0f; L.qd1 = hand ? s[(ST_QD + 8) * B] : 0.0f;
   L.mt1 = hand ? s[(ST_MT + 8) * B] : 0.0f; L.mi1 = hand ? s[(ST_MI + 8) * B] : 0.0f;
   L.dtau0 = L.dtau1 = 0.0f;
-  for (int w = lane; w < EnvSmem::NPAIRS * MAN_WORDS; w += GL) sm.man[w] = io.manifold[(size_t)w * B + env];
+  load_manifolds<EnvSmem::NPAIRS>(g, sm.man, io.manifold + man_off(io, env), B);
   // ---- Kuka.apply_action (kuka.py:167-222) ----
   const float lo[3] = {-0.67f, -0.20f, 0.175f}, hi[3] = {-0.37f, 0.20f, 0.55f};  // kuka.py:40-41
   float ee[3];
@@ -1596,7 +1620,7 @@ __device__ void step_env_reach(const Grp& g, EnvSmem& sm, const float* lane_cons
   s[(ST_Q + lane) * B] = L.q0; s[(ST_QD + lane) * B] = L.qd0; s[(ST_MT + lane) * B] = L.mt0; s[(ST_MI + lane) * B] = L.mi0;
   if (hand) { s[(ST_Q + 8) * B] = L.q1; s[(ST_QD + 8) * B] = L.qd1; s[(ST_MT + 8) * B] = L.mt1; s[(ST_MI + 8) * B] = L.mi1; }
   g.sync();
-  for (int w = lane; w < EnvSmem::NPAIRS * MAN_WORDS; w += GL) io.manifold[(size_t)w * B + env] = sm.man[w];
+  store_manifolds<EnvSmem::NPAIRS>(g, sm.man, io.manifold + man_off(io, env), B);
   // joint control prepends the 7 joint positions to observation and policy_state (kuka_single_step_base_env.py:214-216)
   constexpr int jo = JC ? 7 : 0;
   if (JC && arm) {
@@ -1607,7 +1631,7 @@ __device__ void step_env_reach(const Grp& g, EnvSmem& sm, const float* lane_cons
     const float t[3] = PMG_TIP_OFFSET;
     const V3 tip = p + mul(R, v3(t[0], t[1], t[2]));
     float* row = io.obs + (size_t)env * (D::W + 2 * jo);
-    const float* goal = io.state + (size_t)(ST_BLK) * B + env;
+    const float* goal = s + (size_t)(ST_BLK) * B;
     const float g0 = goal[0], g1 = goal[B], g2 = goal[2 * B];
     float* ob = row + jo; float* pol = row + 3 + 2 * jo; float* ag = row + 6 + 2 * jo;
     ob[0] = pol[0] = ag[0] = tip.x; ob[1] = pol[1] = ag[1] = tip.y; ob[2] = pol[2] = ag[2] = tip.z;
@@ -1637,8 +1661,8 @@ __device__ void step_env_block(const Grp& g, EnvSmemT<1, TASK == 5>& sm, const f
   using D = Dims<TASK == 5 ? 1 : TASK, 1>;
   const int lane = g.lane;
   const bool arm = lane < 7, hand = lane == 7;
-  const size_t B = io.batch;
-  float* s = io.state + env;
+  const size_t B = io.tile;  // distance between consecutive words of this environment (StepIO::tile)
+  float* s = io.state + state_off(io, env);
   Lane L;
   L.lc = lane_consts + lane * LC_W;
   L.dof0 = lane;
@@ -1646,7 +1670,7 @@ __device__ void step_env_block(const Grp& g, EnvSmemT<1, TASK == 5>& sm, const f
   L.q1 = hand ? s[(ST_Q + 8) * B] : 0.0f; L.qd1 = hand ? s[(ST_QD + 8) * B] : 0.0f;
   L.mt1 = hand ? s[(ST_MT + 8) * B] : 0.0f; L.mi1 = hand ? s[(ST_MI + 8) * B] : 0.0f;
   L.dtau0 = L.dtau1 = 0.0f;
-  for (int w = lane; w < SM::NPAIRS * MAN_WORDS; w += GL) sm.man[w] = io.manifold[(size_t)w * B + env];
+  load_manifolds<SM::NPAIRS>(g, sm.man, io.manifold + man_off(io, env), B);
   for (int w = lane; w < 13; w += GL) sm.blk[w] = s[(size_t)(ST_BLK + w) * B];
   if (lane == 0) {
     sm.blk[23] = 0.0f;  // contact points dropped because the row pool was full
@@ -1691,7 +1715,7 @@ __device__ void step_env_block(const Grp& g, EnvSmemT<1, TASK == 5>& sm, const f
   s[(ST_Q + lane) * B] = L.q0; s[(ST_QD + lane) * B] = L.qd0; s[(ST_MT + lane) * B] = L.mt0; s[(ST_MI + lane) * B] = L.mi0;
   if (hand) { s[(ST_Q + 8) * B] = L.q1; s[(ST_QD + 8) * B] = L.qd1; s[(ST_MT + 8) * B] = L.mt1; s[(ST_MI + 8) * B] = L.mi1; }
   g.sync();  // the block state of the last substep
-  for (int wd = lane; wd < SM::NPAIRS * MAN_WORDS; wd += GL) io.manifold[(size_t)wd * B + env] = sm.man[wd];
+  store_manifolds<SM::NPAIRS>(g, sm.man, io.manifold + man_off(io, env), B);
   for (int wd = lane; wd < 13; wd += GL) s[(size_t)(ST_BLK + wd) * B] = sm.blk[wd];
   if (lane == 0 && sm.blk[23] > 0.0f && io.overflow) atomicAdd(io.overflow, (int)sm.blk[23]);
   // tip pose / velocity from lane 6 (link_7); jaw quantities on lane 7 (gripper base), which writes the row
@@ -1729,7 +1753,7 @@ __device__ void step_env_block(const Grp& g, EnvSmemT<1, TASK == 5>& sm, const f
     obs[14] = rv.x; obs[15] = rv.y; obs[16] = rv.z; obs[17] = rw.x; obs[18] = rw.y; obs[19] = rw.z;
     pol[0] = tip.x; pol[1] = tip.y; pol[2] = tip.z; pol[3] = closeness; pol[4] = rel.x; pol[5] = rel.y; pol[6] = rel.z;
     ag[0] = bx.x; ag[1] = bx.y; ag[2] = bx.z;
-    const float* goal = io.state + (size_t)(ST_BLK + 13) * B + env;
+    const float* goal = s + (size_t)(ST_BLK + 13) * B;
     const float g0 = goal[0], g1 = goal[B], g2 = goal[2 * B];
     dg[0] = g0; dg[1] = g1; dg[2] = g2;
     const float dx = bx.x - g0, dy = bx.y - g1, dz = bx.z - g2;
@@ -1758,8 +1782,8 @@ __device__ void step_env_multi(const Grp& g, EnvSmemT<NBLK>& sm, const float* la
   using D = Dims<3, NBLK>;
   const int lane = g.lane;
   const bool arm = lane < 7, hand = lane == 7;
-  const size_t B = io.batch;
-  float* s = io.state + env;
+  const size_t B = io.tile;  // distance between consecutive words of this environment (StepIO::tile)
+  float* s = io.state + state_off(io, env);
   Lane L;
   L.lc = lane_consts + lane * LC_W;
   L.dof0 = lane;
@@ -1767,7 +1791,7 @@ __device__ void step_env_multi(const Grp& g, EnvSmemT<NBLK>& sm, const float* la
   L.q1 = hand ? s[(ST_Q + 8) * B] : 0.0f; L.qd1 = hand ? s[(ST_QD + 8) * B] : 0.0f;
   L.mt1 = hand ? s[(ST_MT + 8) * B] : 0.0f; L.mi1 = hand ? s[(ST_MI + 8) * B] : 0.0f;
   L.dtau0 = L.dtau1 = 0.0f;
-  for (int w = lane; w < SM::NPAIRS * MAN_WORDS; w += GL) sm.man[w] = io.manifold[(size_t)w * B + env];
+  load_manifolds<SM::NPAIRS>(g, sm.man, io.manifold + man_off(io, env), B);
   for (int w = lane; w < 13 * NBLK; w += GL) sm.blk[24 * (w / 13) + w % 13] = s[(size_t)(ST_BLK + w) * B];
   if (lane == 0) {
     sm.blk[23] = 0.0f;  // contact points dropped because the row pool was full
@@ -1807,7 +1831,7 @@ __device__ void step_env_multi(const Grp& g, EnvSmemT<NBLK>& sm, const float* la
   s[(ST_Q + lane) * B] = L.q0; s[(ST_QD + lane) * B] = L.qd0; s[(ST_MT + lane) * B] = L.mt0; s[(ST_MI + lane) * B] = L.mi0;
   if (hand) { s[(ST_Q + 8) * B] = L.q1; s[(ST_QD + 8) * B] = L.qd1; s[(ST_MT + 8) * B] = L.mt1; s[(ST_MI + 8) * B] = L.mi1; }
   g.sync();  // the block states of the last substep
-  for (int wd = lane; wd < SM::NPAIRS * MAN_WORDS; wd += GL) io.manifold[(size_t)wd * B + env] = sm.man[wd];
+  store_manifolds<SM::NPAIRS>(g, sm.man, io.manifold + man_off(io, env), B);
   for (int wd = lane; wd < 13 * NBLK; wd += GL) s[(size_t)(ST_BLK + wd) * B] = sm.blk[24 * (wd / 13) + wd % 13];
   if (lane == 0 && sm.blk[23] > 0.0f && io.overflow) atomicAdd(io.overflow, (int)sm.blk[23]);
   const float t[3] = PMG_TIP_OFFSET;
@@ -1841,7 +1865,7 @@ __device__ void step_env_multi(const Grp& g, EnvSmemT<NBLK>& sm, const float* la
       ag[3 * n] = bx.x; ag[3 * n + 1] = bx.y; ag[3 * n + 2] = bx.z;
     }
     if (io.grip_goal) { ag[3 * NBLK] = tip.x; ag[3 * NBLK + 1] = tip.y; ag[3 * NBLK + 2] = tip.z; ag[3 * NBLK + 3] = closeness; }
-    const float* goal = io.state + (size_t)(ST_BLK + 13 * NBLK) * B + env;
+    const float* goal = s + (size_t)(ST_BLK + 13 * NBLK) * B;
     for (int k = 0; k < G; k++) dg[k] = goal[(size_t)k * B];
     if (io.td) {  // sub-goal rebuilt from the current block positions (see write_obs in pmg_capi.cu)
       const int nsub = io.grip_goal ? 2 * NBLK : NBLK;

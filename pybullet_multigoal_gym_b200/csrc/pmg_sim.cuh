@@ -629,6 +629,12 @@ __device__ void substep(Env<NBLK>& e) {
 // ---- kernel I/O (shared by the thread-per-env and the lane-cooperative kernels) -----------------
 struct StepIO {
   float* state; float* manifold; int batch; int state_words;
+  // Layout of the two persistent arrays: tiles of `tile` consecutive environments, [tile][word][env in tile], so that a
+  // warp's accesses to one word of its environments are one contiguous run: tile = 4 for the lane-cooperative kernels
+  // (lane l of each of the warp's four octets reads word w0 + l: 32 consecutive floats, one 128-byte line per
+  // instruction), 32 for the thread-per-env kernels; tile = batch is the plain [word][env] array of round 1
+  // (PMG_STATE_TILE=0), which the cooperative kernels read 16 bytes per 32-byte sector.
+  int tile; int man_words;
   const float* action; float* obs; float* reward; uint8_t* done; uint8_t* success;
   float thr; int binary; int max_steps; int* overflow;
   int epw;  // environments per warp: lanes [0, epw) of every warp own one environment each
@@ -657,6 +663,10 @@ struct StepIO {
   int* g_err;            // mapped host word: set when a peer's flag did not arrive in time
   int* bad_action;       // mapped host word: set when an action entry lies outside [-1, 1] (NaN included); see pmg_action_error
 };
+
+// offset of environment `env`'s word 0 in the state / manifold array; its consecutive words are io.tile floats apart
+__device__ __forceinline__ size_t state_off(const StepIO& io, int env) { return (size_t)(env / io.tile) * io.state_words * io.tile + env % io.tile; }
+__device__ __forceinline__ size_t man_off(const StepIO& io, int env) { return (size_t)(env / io.tile) * io.man_words * io.tile + env % io.tile; }
 
 // Box(-1, 1).contains of one environment's action row (kuka.py:168 asserts it), by the `nl` lanes that own the environment
 __device__ __forceinline__ void check_action_row(const StepIO& io, int env, int lane, int nl) {

@@ -143,7 +143,7 @@ int pmg_emu_reach_step(float* state, float* manifold, const float* action, float
   StepArgs a;
   a.sm = &sm;
   memset(&a.io, 0, sizeof a.io);
-  a.io.state = state; a.io.manifold = manifold; a.io.batch = 1; a.io.state_words = Dims<0, 0>::STATE;
+  a.io.state = state; a.io.manifold = manifold; a.io.batch = 1; a.io.tile = 1; a.io.man_words = 0; a.io.state_words = Dims<0, 0>::STATE;
   a.io.action = action; a.io.obs = obs_row; a.io.reward = reward; a.io.done = done; a.io.success = success;
   a.io.thr = thr; a.io.binary = binary; a.io.max_steps = max_steps; a.io.overflow = nullptr; a.io.epw = 4;
   return pmg_emu::run_group(step_body, &a);
@@ -230,7 +230,7 @@ int pmg_emu_block_step(int task, float* state, float* manifold, const float* act
   BlkArgs a;
   a.sm = &sm; a.smp = &smp; a.task = task;
   memset(&a.io, 0, sizeof a.io);
-  a.io.state = state; a.io.manifold = manifold; a.io.batch = 1; a.io.state_words = Dims<1, 1>::STATE;
+  a.io.state = state; a.io.manifold = manifold; a.io.batch = 1; a.io.tile = 1; a.io.man_words = 0; a.io.state_words = Dims<1, 1>::STATE;
   a.io.action = action; a.io.obs = obs_row; a.io.reward = reward; a.io.done = done; a.io.success = success;
   a.io.thr = thr; a.io.binary = binary; a.io.max_steps = max_steps; a.io.overflow = nullptr; a.io.epw = 4;
   a.io.grasp = task == 2; a.io.adim = task == 2 ? 4 : 3; a.io.goal_dim = 3; a.io.row_width = 33;
@@ -256,7 +256,7 @@ static int multi_step(float* state, float* manifold, const float* action, int* o
   a.sm = &sm;
   memset(&a.io, 0, sizeof a.io);
   const int G = 3 * NB + (grip > 0 ? 4 : 0);
-  a.io.state = state; a.io.manifold = manifold; a.io.batch = 1; a.io.state_words = ST_BLK + 13 * NB + G + (td ? 1 : 0) + 1;
+  a.io.state = state; a.io.manifold = manifold; a.io.batch = 1; a.io.tile = 1; a.io.man_words = 0; a.io.state_words = ST_BLK + 13 * NB + G + (td ? 1 : 0) + 1;
   a.io.action = action; a.io.obs = obs_row; a.io.reward = reward; a.io.done = done; a.io.success = success;
   a.io.thr = thr; a.io.binary = binary; a.io.max_steps = max_steps;
   a.io.overflow = overflow; a.io.epw = 4; a.io.grasp = grip >= 0; a.io.adim = grip >= 0 ? 4 : 3; a.io.row_spill = spill;
@@ -289,7 +289,7 @@ int pmg_emu_step_jc(int task, float* state, float* manifold, const float* action
                     float* obs_row, float* reward, uint8_t* done, uint8_t* success) {
   StepIO io;
   memset(&io, 0, sizeof io);
-  io.state = state; io.manifold = manifold; io.batch = 1; io.state_words = task == 0 ? Dims<0, 0>::STATE : Dims<1, 1>::STATE;
+  io.state = state; io.manifold = manifold; io.batch = 1; io.tile = 1; io.man_words = 0; io.state_words = task == 0 ? Dims<0, 0>::STATE : Dims<1, 1>::STATE;
   io.action = action; io.obs = obs_row; io.reward = reward; io.done = done; io.success = success;
   io.thr = thr; io.binary = binary; io.max_steps = max_steps; io.overflow = nullptr; io.epw = 4;
   io.jc = 1; io.grasp = task == 2; io.adim = task == 2 ? 8 : 7; io.goal_dim = 3; io.row_width = task == 0 ? 26 : 47;
