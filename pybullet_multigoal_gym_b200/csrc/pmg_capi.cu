@@ -307,14 +307,39 @@ __global__ void __launch_bounds__(32) step_kernel(StepIO io) {
 // narrowphase branches.)
 constexpr int COOP_TABLE_BYTES = coop::GL * coop::LC_W * sizeof(float);
 static_assert(COOP_TABLE_BYTES % 16 == 0, "EnvSmem must stay 16-byte aligned behind the constant table");
+
+// The per-body model constants of the chain (joint frames, centres of mass, inertias, masses, limits, damping: 8 rows of
+// LC_W floats, pmg_coop.cuh LC_*) live once per device in global memory, laid out exactly as the kernels read them, and
+// every block stages them into its shared memory with ONE bulk asynchronous copy (TMA, cp.async.bulk, 896 bytes) that
+// completes on an mbarrier -- instead of eight threads assembling the table from ~30 __constant__ loads each.
+__device__ __align__(16) float g_lane_table[coop::GL * coop::LC_W];
+__global__ void fill_lane_table_kernel() {
+  if (threadIdx.x < coop::GL) coop::fill_lane_constants(g_lane_table + threadIdx.x * coop::LC_W, threadIdx.x);
+}
+// Every thread of the block calls this; returns when the table is in `dst` (16-byte aligned shared memory).
+__device__ __forceinline__ void stage_lane_table(float* dst) {
+  __shared__ __align__(8) uint64_t table_bar;
+  const uint32_t bar_a = smem_u32(&table_bar);
+  if (threadIdx.x == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar_a), "r"(1) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_a), "r"(COOP_TABLE_BYTES) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst)), "l"(g_lane_table), "r"(COOP_TABLE_BYTES), "r"(bar_a) : "memory");
+  }
+  if (blockDim.x > 32) __syncthreads(); else __syncwarp();  // the barrier is initialised before anybody polls it
+  uint32_t done = 0;
+  while (!done)
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(done) : "r"(bar_a), "r"(0) : "memory");
+}
 constexpr int COOP_MIN_BLOCKS = 14;  // batch 8192 = 2048 blocks = 13.8 per SM: keep them all resident
 template <bool JC>
 __global__ void __launch_bounds__(64, COOP_MIN_BLOCKS / 2) step_kernel_coop_reach(StepIO io) {
   extern __shared__ __align__(16) unsigned char coop_smem[];
   const int lane32 = threadIdx.x & 31, grp = lane32 >> 3, warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
   float* lane_consts = reinterpret_cast<float*>(coop_smem);
-  if (threadIdx.x < coop::GL) coop::fill_lane_constants(lane_consts + threadIdx.x * coop::LC_W, threadIdx.x);
-  if (wpb > 1) __syncthreads(); else __syncwarp();
+  stage_lane_table(lane_consts);
   const int env = (blockIdx.x * wpb + warp) * io.epb + grp;  // io.epb environments per warp (octets beyond it stay idle)
   if (grp >= io.epb || env >= io.batch) return;   // a whole octet leaves together (exited threads do not hold up the block barrier)
   coop::Grp g;
@@ -332,8 +357,7 @@ __global__ void __launch_bounds__(64, 3) step_kernel_coop_block(StepIO io) {
   extern __shared__ __align__(16) unsigned char coop_smem[];
   const int lane32 = threadIdx.x & 31, grp = lane32 >> 3, warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
   float* lane_consts = reinterpret_cast<float*>(coop_smem);
-  if (threadIdx.x < coop::GL) coop::fill_lane_constants(lane_consts + threadIdx.x * coop::LC_W, threadIdx.x);
-  if (wpb > 1) __syncthreads(); else __syncwarp();
+  stage_lane_table(lane_consts);
   const int env = (blockIdx.x * wpb + warp) * io.epb + grp;  // io.epb environments per warp (octets beyond it stay idle)
   if (grp >= io.epb || env >= io.batch) return;   // a whole octet leaves together (exited threads do not hold up the block barrier)
   coop::Grp g;
@@ -350,8 +374,7 @@ __global__ void __launch_bounds__(128, 1) step_kernel_coop_multi(StepIO io) {
   extern __shared__ __align__(16) unsigned char coop_smem[];
   const int lane32 = threadIdx.x & 31, grp = lane32 >> 3, warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
   float* lane_consts = reinterpret_cast<float*>(coop_smem);
-  if (threadIdx.x < coop::GL) coop::fill_lane_constants(lane_consts + threadIdx.x * coop::LC_W, threadIdx.x);
-  if (wpb > 1) __syncthreads(); else __syncwarp();
+  stage_lane_table(lane_consts);
   const int env = (blockIdx.x * wpb + warp) * io.epb + grp;  // io.epb environments per warp (octets beyond it stay idle)
   if (grp >= io.epb || env >= io.batch) return;   // a whole octet leaves together (exited threads do not hold up the block barrier)
   coop::Grp g;
@@ -1128,6 +1151,7 @@ int pmg_create(const pmg_config* cfg, pmg_handle** out) {
   cudaMemset(h->d_overflow, 0, sizeof(int));
   cudaMemset(h->d_episode, 0, sizeof(uint32_t) * B);
   cudaMemset(h->d_spawn_dev, 0, sizeof(float) * h->spawn_w * B);
+  fill_lane_table_kernel<<<1, 32>>>();  // per device (a __device__ array): cheap enough to redo per handle
   init_state_kernel<<<(int)((B + 31) / 32), 32>>>(h->d_state, (int)B, h->tile, h->state_words, h->nblk, (float)h->tip_init[0], (float)h->tip_init[1], (float)h->tip_init[2]);
   h->launches++;
   CUDA_TRY(cudaDeviceSynchronize());
