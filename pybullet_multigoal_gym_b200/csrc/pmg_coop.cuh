@@ -38,6 +38,9 @@ namespace pmg {
 namespace coop {
 
 constexpr int GL = 8;        // lanes per environment
+#ifndef PMG_SPTS1
+#define PMG_SPTS1 12         // one-block kernels: contact points whose rows live in shared memory (the rest: global spill)
+#endif
 constexpr int R_J = 0, R_RHS = 9, R_DINV = 10, R_MJ = 12, R_DENOM = 21, R_MU = 22;  // contact row record, robot part
 constexpr int R_BD = 24, R_BA = 28;  // block part (NBLK > 0): direction d[3] has_robot | lever arm r_B x d [3] has_block
 constexpr int R_AA = 32, R_IDX = 36;  // NBLK > 1: lever arm r_A x d [3] . | block index of end A, of end B (-1: none)
@@ -61,7 +64,7 @@ struct __align__(16) EnvSmemT : RowSpill<NBLK>, GenList<NBLK> {
   static constexpr bool PUCK = PUCK_;  // Slide: long table, the block is a cylinder with an anisotropic inertia
   static constexpr int NPAIRS = num_pairs(NBLK);                // 2 / 6
   static constexpr int MAXPTS = NBLK == 0 ? 8 : (NBLK == 1 ? 24 : 48);  // cached contact points that get rows
-  static constexpr int SPTS = NBLK == 0 ? 8 : (NBLK == 1 ? 12 : 8);  // ... of which in shared memory (NBLK > 1: of the points that are not static)
+  static constexpr int SPTS = NBLK == 0 ? 8 : (NBLK == 1 ? PMG_SPTS1 : 8);  // ... of which in shared memory (NBLK > 1: of the points that are not static)
   static constexpr int ROW_W = NBLK == 0 ? 24 : (NBLK == 1 ? 32 : 40);  // floats per contact row record (16-byte aligned parts)
   static constexpr int SROWS = NBLK > 1 ? NBLK * 4 * 3 : 0;     // NBLK > 1: compact rows of the static points (table / floor against a block), 4 points per block
   static constexpr int SROW_W = 12;                             // d[3] rhs | r_B x d [3] dinv | denom mu . .
