@@ -189,3 +189,31 @@ def test_device_path_action_check_runs_in_the_kernel():
         with pytest.raises(ValueError):  # host-buffer path: checked before anything is launched
             env.step(np.full((37, env.action_dim), 2.0, np.float32))
         env.close()
+
+
+@pytest.mark.parametrize("task", ["reach", "pick_and_place", "block_stack"])
+def test_state_tile_layout_does_not_change_results(task, monkeypatch):
+    """The persistent state / manifold arrays are tiled ([tile][word][env in tile], 4 environments per tile for the
+    lane-cooperative kernels); PMG_STATE_TILE=0 restores the plain [word][env] arrays of round 1.  Same seeds, same
+    actions, odd batch (a partial last tile): bit-identical rows, rewards and flags, and get_state round-trips."""
+    import pybullet_multigoal_gym_b200 as pmg
+    outs = []
+    for plain in (False, True):
+        if plain:
+            monkeypatch.setenv("PMG_STATE_TILE", "0")
+        env = pmg.make_env(task=task, batch=37, num_block=3, seed=5)
+        env.reset()
+        gen = torch.Generator(device="cuda")
+        gen.manual_seed(11)
+        rows = []
+        for t in range(12):
+            a = torch.rand((37, env.action_dim), device="cuda", generator=gen) * 2 - 1
+            a[:, 2] = -1.0   # down onto the table / the blocks: contacts, manifolds in use
+            obs, r, done, info = env.step(a)
+            rows.append(torch.cat([obs[k] for k in ("observation", "policy_state", "achieved_goal", "desired_goal")] + [r[:, None]], dim=1).cpu().numpy())
+        st = env.get_state()
+        env.set_state(st)
+        assert np.array_equal(env.get_state(), st)
+        outs.append((np.stack(rows), st))
+        env.close()
+    assert np.array_equal(outs[0][0], outs[1][0]) and np.array_equal(outs[0][1], outs[1][1])
