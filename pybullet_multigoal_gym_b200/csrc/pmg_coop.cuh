@@ -39,7 +39,7 @@ namespace coop {
 
 constexpr int GL = 8;        // lanes per environment
 #ifndef PMG_SPTS1
-#define PMG_SPTS1 12         // one-block kernels: contact points whose rows live in shared memory (the rest: global spill)
+#define PMG_SPTS1 12         // one-block kernels: contact points whose rows live in shared memory (the rest: global spill); 11 measured slower, DESIGN.md section 9
 #endif
 constexpr int R_J = 0, R_RHS = 9, R_DINV = 10, R_MJ = 12, R_DENOM = 21, R_MU = 22;  // contact row record, robot part
 constexpr int R_BD = 24, R_BA = 28;  // block part (NBLK > 0): direction d[3] has_robot | lever arm r_B x d [3] has_block

@@ -183,12 +183,7 @@ __device__ unsigned long long g_coop_cycles[16];
 // cylB: body B is the Slide puck (a cylinder about its z axis, hb = (r, r, h)): box_cyl instead of box_box.
 // cylA: body A is the gripper-base cylinder (ha = (r, r, h)): box_cyl with the roles exchanged (cyl_box).
 // b_static: body B is the static box (the finger-table pairs); with a_static it selects box_box's static fast path.
-#ifdef PMG_X_NP_NOINLINE
-#define PMG_NP_INLINE __noinline__
-#else
-#define PMG_NP_INLINE
-#endif
-__device__ PMG_NP_INLINE void collide_pair(ManRef& e, int k, V3 pa, const M3& Ra, V3 ha, V3 aA, bool a_static, V3 pb, const M3& Rb, V3 hb, V3 aB, BoxScratch& scr,
+__device__ void collide_pair(ManRef& e, int k, V3 pa, const M3& Ra, V3 ha, V3 aA, bool a_static, V3 pb, const M3& Rb, V3 hb, V3 aB, BoxScratch& scr,
                              bool cylB = false, bool b_static = false, bool cylA = false) {
   V3 d = pa - pb;
   float ex = fabsf(Ra.r0.x) * ha.x + fabsf(Ra.r0.y) * ha.y + fabsf(Ra.r0.z) * ha.z + fabsf(Rb.r0.x) * hb.x + fabsf(Rb.r0.y) * hb.y + fabsf(Rb.r0.z) * hb.z + 2 * BROADPHASE_MARGIN;
