@@ -52,9 +52,11 @@ typedef struct {
                                  kuka_single_step_base_env.py:214-216) */
   int32_t task_decomposition; /* block_stack only: the desired goal is one of the sub-goals of
                                  kuka_multi_step_envs.py:88-120, selected with pmg_set_sub_goal */
-  int32_t use_curriculum;     /* block_stack only (exclusive with task_decomposition): every reset draws a goal
-                                 difficulty level from a per-env probability schedule
-                                 (kuka_multi_step_base_env.py:122-140,350-379; kuka_multi_step_envs.py:124-148) */
+  int32_t use_curriculum;     /* block_stack (exclusive with task_decomposition) and block_rearrange: every reset
+                                 draws a goal difficulty level from a per-env probability schedule
+                                 (kuka_multi_step_base_env.py:122-140,350-379; kuka_multi_step_envs.py:124-148);
+                                 block_rearrange then gives targets to level + 1 randomly chosen blocks
+                                 (kuka_multi_step_envs.py:193-227) */
   int32_t num_goals_to_generate; /* make_env(num_goals_to_generate=...): goals per level = this // num_block */
 } pmg_config;
 
@@ -82,7 +84,8 @@ int pmg_seed(pmg_handle* h, const uint32_t* keys_host, const int32_t* key_lens_h
  * mask_host: nullable [batch] bytes, non-zero = reset that env (NULL = all).
  * spawn_host: nullable [batch, spawn_width] floats = [block xy (2*nb) | desired_goal (G)]
  *   (G includes the 4 gripper entries of a grip-informed goal; curriculum handles append the sub-goal index
- *   equivalent to the drawn level: level, or 2 * level + 1 with grip-informed goals);
+ *   equivalent to the drawn level: level, or 2 * level + 1 with grip-informed goals; block_rearrange: the bit
+ *   mask of the blocks that have targets -- their goal words hold the targets, the other blocks' are ignored);
  *   NULL = sample on the host from each env's numpy-compatible MT19937 stream, exactly as the
  *   reference consumes it.
  * obs_dev: [batch, packed-row width] row-major, rows of envs not reset are rewritten unchanged. */

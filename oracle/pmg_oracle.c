@@ -1334,7 +1334,7 @@ PmgoEnv* pmgo_create_ex3(int task, int num_block, int binary_reward, double thr,
   PmgoEnv* e = (PmgoEnv*)calloc(1, sizeof *e);
   e->td = task_decomposition && task == PMGO_BLOCK_STACK;
   e->sub_goal_ind = -1;
-  e->cur = use_curriculum && task == PMGO_BLOCK_STACK && !e->td; /* mutually exclusive (:113,121) */
+  e->cur = use_curriculum && (task == PMGO_BLOCK_STACK || task == PMGO_BLOCK_REARRANGE) && !e->td; /* mutually exclusive (:113,121) */
   if (e->cur) {
     e->cur_prob[0] = 1.0;
     e->cur_goals_per = (double)(num_goals_to_generate / num_block); /* floor division (:138) */
@@ -1465,7 +1465,13 @@ static void write_obs(PmgoEnv* e, double* o) {
     }
   }
   memcpy(dg, e->goal, sizeof(double) * e->dims[3]);
-  if (e->td || e->cur) {
+  if (e->cur && e->task == PMGO_BLOCK_REARRANGE) {
+    /* kuka_multi_step_envs.py:218-225: the blocks picked for this episode (e->sub_goal_ind holds them as a bit
+     * mask) take the sampled targets in order, every other block's goal is wherever it is now */
+    int j = 0;
+    for (int i = 0; i < e->nb; i++)
+      copy3(dg + 3 * i, ((e->sub_goal_ind >> i) & 1) ? e->last_targets[j++] : e->bpos[i]);
+  } else if (e->td || e->cur) {
     /* The curriculum goal of level L (kuka_multi_step_envs.py:124-148) is the "place" sub-goal of level L;
      * e->sub_goal_ind holds the equivalent sub-goal index in that mode. */
     /* kuka_multi_step_envs.py:88-120 + kuka_multi_step_base_env.py:159-165,311-313: the desired goal is
@@ -1518,6 +1524,19 @@ static void place_blocks(PmgoEnv* e, const double* xy) {
   }
 }
 
+/* level = np_random.choice(num_curriculum, p=curriculum_prob), i.e. cdf.searchsorted(random_sample(),
+ * side='right') in numpy's legacy RandomState (kuka_multi_step_envs.py:127,197) */
+static int draw_curriculum_level(PmgoEnv* e) {
+  double cdf[MAXBLK], acc = 0;
+  for (int k = 0; k < e->nb; k++) { acc += e->cur_prob[k]; cdf[k] = acc; }
+  for (int k = 0; k < e->nb; k++) cdf[k] /= acc;
+  const double u = mt_double(&e->rng);
+  int level = 0;
+  while (level < e->nb && cdf[level] <= u) level++;
+  e->cur_level = level;
+  return level;
+}
+
 void pmgo_reset(PmgoEnv* e, double* obs_out) {
   robot_reset(e);
   e->elapsed = 0;
@@ -1549,6 +1568,23 @@ void pmgo_reset(PmgoEnv* e, double* obs_out) {
           if (ok) { txy[2 * b] = x; txy[2 * b + 1] = y; break; }
         }
         set3(e->goal + 3 * b, txy[2 * b], txy[2 * b + 1], 0.175);
+        set3(e->last_targets[b], txy[2 * b], txy[2 * b + 1], 0.175);
+      }
+      if (e->cur) {
+        /* kuka_multi_step_envs.py:197-212: level = np_random.choice(num_curriculum, p=curriculum_prob), then the
+         * level + 1 blocks to move = sort(np_random.choice(arange(nb), size=level + 1, replace=False)), which in
+         * numpy's legacy RandomState is permutation(nb)[:level + 1] (a shuffle of arange(nb)) */
+        const int level = draw_curriculum_level(e);
+        int64_t perm[MAXBLK];
+        for (int k = 0; k < e->nb; k++) perm[k] = k;
+        pmgo_rng_shuffle(e, perm, e->nb);
+        int mask = 0;
+        for (int k = 0; k <= level; k++) mask |= 1 << (int)perm[k];
+        e->sub_goal_ind = mask;
+        if (e->cur_update) { e->cur_count[level] += 1; update_curriculum_prob(e); }
+        /* the goal words of the moved blocks hold their targets (what a spawn row carries, pmgo_reset_with) */
+        int j = 0;
+        for (int i = 0; i < e->nb; i++) if ((mask >> i) & 1) copy3(e->goal + 3 * i, e->last_targets[j++]);
       }
       write_obs(e, obs_out);
       return;
@@ -1572,15 +1608,8 @@ void pmgo_reset(PmgoEnv* e, double* obs_out) {
     }
     if (e->grip) { copy3(e->goal + 3 * e->nb, e->last_targets[e->nb - 1]); e->goal[3 * e->nb + 3] = 0.03; } /* :75-77 */
     if (e->cur) {
-      /* kuka_multi_step_envs.py:127-134: level = np_random.choice(num_curriculum, p=curriculum_prob), i.e.
-       * cdf.searchsorted(random_sample(), side='right') in numpy's legacy RandomState */
-      double cdf[MAXBLK], acc = 0;
-      for (int k = 0; k < e->nb; k++) { acc += e->cur_prob[k]; cdf[k] = acc; }
-      for (int k = 0; k < e->nb; k++) cdf[k] /= acc;
-      const double u = mt_double(&e->rng);
-      int level = 0;
-      while (level < e->nb && cdf[level] <= u) level++;
-      e->cur_level = level;
+      /* kuka_multi_step_envs.py:127-134 */
+      const int level = draw_curriculum_level(e);
       e->sub_goal_ind = e->grip ? 2 * level + 1 : level;
       if (e->cur_update) { e->cur_count[level] += 1; update_curriculum_prob(e); }
     }
@@ -1618,6 +1647,12 @@ void pmgo_reset_with(PmgoEnv* e, const double* spawn, double* obs_out) {
   if (e->cur) e->cur_level = e->grip ? e->sub_goal_ind >> 1 : e->sub_goal_ind;
   place_blocks(e, spawn);
   memcpy(e->goal, spawn + 2 * e->nb, sizeof(double) * e->dims[3]);
+  if (e->cur && e->task == PMGO_BLOCK_REARRANGE) {
+    /* the index word is the mask of the blocks to move; their goal words hold the targets, in order */
+    int j = 0;
+    for (int i = 0; i < e->nb; i++) if ((e->sub_goal_ind >> i) & 1) copy3(e->last_targets[j++], e->goal + 3 * i);
+    e->cur_level = j - 1;
+  }
   if (e->task == PMGO_BLOCK_STACK) {
     /* recover order/targets from the goal: level k <=> z = 0.175 + 0.03 k */
     for (int b = 0; b < e->nb; b++) {
@@ -1701,6 +1736,10 @@ void pmgo_set_state(PmgoEnv* e, const double* o) {
       e->last_order[k] = b;
       copy3(e->last_targets[k], e->goal + 3 * b);
     }
+  if (e->cur && e->task == PMGO_BLOCK_REARRANGE) {
+    int j = 0;
+    for (int i = 0; i < e->nb; i++) if ((e->sub_goal_ind >> i) & 1) copy3(e->last_targets[j++], e->goal + 3 * i);
+  }
   memset(e->man, 0, sizeof e->man);
 }
 

@@ -6,7 +6,8 @@ reference's numpy shapes), `device`, `seed`, and the throughput options `device_
 device from Philox streams instead of the reference's host MT19937 streams) / `auto_reset` (environments reset
 themselves on the device when their episode ends).  Tasks on the accelerated path: reach, push,
 pick_and_place, slide, block_stack, block_rearrange with the parallel-jaw gripper and state observations,
-including the `joint_control` and (block_stack) `grip_informed_goal` / `task_decomposition` / `use_curriculum` variants.
+including the `joint_control`, (block_stack) `grip_informed_goal` / `task_decomposition` and (block_stack, block_rearrange)
+`use_curriculum` variants.
 """
 from .envs import (ActionError, KukaBlockRearrangeEnv, KukaBlockStackEnv, KukaBulletMGEnv,  # noqa: F401
                    KukaPickAndPlaceEnv, KukaPushEnv, KukaReachEnv, KukaSlideEnv)
@@ -51,13 +52,12 @@ def make_env(task='reach', gripper='parallel_jaw', num_block=5, render=False, bi
             raise AssertionError("Block rearranging task does not support task decomposition.")
         if task in _TAGS:
             task_decomposition = False  # the single-step tasks do not take the kwarg (__init__.py:88-106)
-    if use_curriculum and task != 'block_stack':
-        if task in ('reach', 'push', 'pick_and_place', 'slide'):
-            use_curriculum = False  # the single-step tasks do not take the kwarg (__init__.py:88-106)
+    if use_curriculum and task in ('reach', 'push', 'pick_and_place', 'slide'):
+        use_curriculum = False  # the single-step tasks do not take the kwarg (__init__.py:88-106)
     for name, val in (('render', render),
                       ('image_observation', image_observation), ('depth_image', depth_image),
                       ('goal_image', goal_image), ('point_cloud', point_cloud), ('state_noise', state_noise),
-                      ('use_curriculum', use_curriculum and task != 'block_stack')):
+                      ('use_curriculum', use_curriculum and task not in ('block_stack', 'block_rearrange'))):
         if val:
             unsupported.append("%s=True" % name)
     if primitive is not None:

@@ -193,7 +193,14 @@ __device__ float write_obs(const Env<NBLK>& e, const StepIO& io, int i) {
       ag[3 * n] = bx.x; ag[3 * n + 1] = bx.y; ag[3 * n + 2] = bx.z;
     }
     if (io.grip_goal) { ag[3 * NBLK] = tip.x; ag[3 * NBLK + 1] = tip.y; ag[3 * NBLK + 2] = tip.z; ag[3 * NBLK + 3] = closeness; }
-    if (io.td) {
+    if (io.td == 2) {
+      // BlockRearrange curriculum (kuka_multi_step_envs.py:193-227): the state word behind the goal is the bit mask of
+      // the blocks this episode moves; their goal words hold their targets, every other block's goal is where it is
+      const int moved = (int)goal[(size_t)G * B];
+#pragma unroll
+      for (int n = 0; n < NBLK; n++)
+        if (!((moved >> n) & 1)) { dg[3 * n] = e.bpos[n].x; dg[3 * n + 1] = e.bpos[n].y; dg[3 * n + 2] = e.bpos[n].z; }
+    } else if (io.td) {
       // Task decomposition (kuka_multi_step_envs.py:88-120, kuka_multi_step_base_env.py:159-165,311-313): the
       // desired goal is sub_goals[ind], rebuilt from the current block positions.  The stored goal is the final
       // one; a block's stack level is its target height.  Without the grip goal sub-goal k has levels <= k on
@@ -761,6 +768,40 @@ constexpr int TIMING_RING = 2048;
 
 namespace {
 
+// level = np_random.choice(num_curriculum, p=curriculum_prob) (kuka_multi_step_envs.py:127,197), which is
+// cdf.searchsorted(random_sample(), side='right') in numpy's legacy RandomState
+int draw_curriculum_level(pmg_handle* h, int i, MT& r) {
+  const int nb = h->nblk;
+  const double* prob = &h->cur_prob[(size_t)i * nb];
+  double cdf[5], acc = 0;
+  for (int k = 0; k < nb; k++) { acc += prob[k]; cdf[k] = acc; }
+  const double u = r.random_sample();
+  int level = 0;
+  while (level < nb && cdf[level] / acc <= u) level++;
+  h->cur_level[i] = level;
+  return level;
+}
+
+// _update_curriculum_prob (kuka_multi_step_base_env.py:350-379), statement by statement, on environment i's own schedule
+void update_curriculum_prob(pmg_handle* h, int i, int level) {
+  if (!h->cur_update) return;
+  const int nb = h->nblk;
+  double* prob = &h->cur_prob[(size_t)i * nb];
+  double* count = &h->cur_count[(size_t)i * nb];
+  count[level] += 1;
+  bool fin[5], half[5];
+  for (int k = 0; k < nb; k++) {
+    fin[k] = count[k] >= h->cur_goals_per; half[k] = count[k] >= h->cur_goals_per / 2;
+    if (fin[k]) prob[k] = 0.0;
+  }
+  if (half[0] && !fin[0]) { prob[0] = 0.5; prob[1] = 0.5; }
+  for (int k = 1; k < nb - 1; k++)
+    if (fin[k - 1] && !fin[k]) {
+      if (half[k]) { prob[k] = 0.5; prob[k + 1] = 0.5; } else prob[k] = 1.0;
+    }
+  if (fin[nb - 2]) prob[nb - 1] = 1.0;
+}
+
 // Sampling of one reset, consuming the env's stream exactly like the reference:
 // kuka_single_step_base_env.py:104-148, kuka_multi_step_base_env.py:223-240, kuka_multi_step_envs.py:34-63
 void sample_spawn(pmg_handle* h, int i, float* out) {
@@ -792,6 +833,26 @@ void sample_spawn(pmg_handle* h, int i, float* out) {
         }
         goal[3 * b] = (float)txy[2 * b]; goal[3 * b + 1] = (float)txy[2 * b + 1]; goal[3 * b + 2] = 0.175f;
       }
+      if (h->cur) {
+        // kuka_multi_step_envs.py:197-225: a level, then the level + 1 blocks to move =
+        // sort(np_random.choice(arange(nb), size=level + 1, replace=False)), which numpy's legacy RandomState
+        // evaluates as permutation(nb)[:level + 1] (a shuffle of arange(nb)); the moved blocks take the sampled
+        // targets in order, the others keep their own position as the goal (rebuilt every observation by the kernels)
+        const int level = draw_curriculum_level(h, i, r);
+        int perm[5];
+        for (int k = 0; k < nb; k++) perm[k] = k;
+        for (int k = nb - 1; k > 0; k--) { int j = (int)r.interval((uint32_t)k); int t = perm[k]; perm[k] = perm[j]; perm[j] = t; }
+        int moved = 0;
+        for (int k = 0; k <= level; k++) moved |= 1 << perm[k];
+        update_curriculum_prob(h, i, level);
+        int j = 0;
+        for (int b = 0; b < nb; b++) {
+          const bool mv = (moved >> b) & 1;
+          goal[3 * b] = (float)(mv ? txy[2 * j] : xy[2 * b]); goal[3 * b + 1] = (float)(mv ? txy[2 * j + 1] : xy[2 * b + 1]);
+          if (mv) j++;
+        }
+        goal[h->G] = (float)moved;  // consumed by reset_kernel like the stack curriculum's sub-goal index
+      }
       return;
     }
     int order[5];
@@ -813,33 +874,10 @@ void sample_spawn(pmg_handle* h, int i, float* out) {
       goal[3 * nb] = (float)bx; goal[3 * nb + 1] = (float)by;
       goal[3 * nb + 2] = (float)(nb == 1 ? 0.175 : 0.175 + 0.03 * (nb - 1)); goal[3 * nb + 3] = 0.03f;
     }
-    if (h->cur) {
-      // kuka_multi_step_envs.py:127-134: level = np_random.choice(num_curriculum, p=curriculum_prob), which is
-      // cdf.searchsorted(random_sample(), side='right') in numpy's legacy RandomState; then
-      // _update_curriculum_prob (kuka_multi_step_base_env.py:350-379), statement by statement
-      double* prob = &h->cur_prob[(size_t)i * nb];
-      double* count = &h->cur_count[(size_t)i * nb];
-      double cdf[5], acc = 0;
-      for (int k = 0; k < nb; k++) { acc += prob[k]; cdf[k] = acc; }
-      const double u = r.random_sample();
-      int level = 0;
-      while (level < nb && cdf[level] / acc <= u) level++;
-      h->cur_level[i] = level;
+    if (h->cur) {  // kuka_multi_step_envs.py:127-134
+      const int level = draw_curriculum_level(h, i, r);
       goal[h->G] = (float)(h->grip ? 2 * level + 1 : level);  // the equivalent sub-goal index, consumed by reset_kernel
-      if (h->cur_update) {
-        count[level] += 1;
-        bool fin[5], half[5];
-        for (int k = 0; k < nb; k++) {
-          fin[k] = count[k] >= h->cur_goals_per; half[k] = count[k] >= h->cur_goals_per / 2;
-          if (fin[k]) prob[k] = 0.0;
-        }
-        if (half[0] && !fin[0]) { prob[0] = 0.5; prob[1] = 0.5; }
-        for (int k = 1; k < nb - 1; k++)
-          if (fin[k - 1] && !fin[k]) {
-            if (half[k]) { prob[k] = 0.5; prob[k + 1] = 0.5; } else prob[k] = 1.0;
-          }
-        if (fin[nb - 2]) prob[nb - 1] = 1.0;
-      }
+      update_curriculum_prob(h, i, level);
     }
     return;
   }
@@ -872,7 +910,7 @@ StepIO make_io(pmg_handle* h, const float* action, float* obs, float* reward, ui
   io.overflow = h->d_overflow; io.row_spill = h->d_row_spill;
   io.epw = h->epw; io.epb = 32 / coop::GL;
   io.bulk = 0; io.tile_offset = 0;
-  io.grasp = h->grasp; io.jc = h->jc; io.grip_goal = h->grip; io.td = h->td || h->cur; io.cur = h->cur;
+  io.grasp = h->grasp; io.jc = h->jc; io.grip_goal = h->grip; io.td = (h->td || h->cur) ? (h->cfg.task == PMG_BLOCK_REARRANGE ? 2 : 1) : 0; io.cur = h->cur;
   io.adim = h->A; io.goal_dim = h->G; io.row_width = h->W;
   io.g_n = 0; io.g_in_step = 0; io.g_world = 0; io.g_seq = 0; io.g_flags_local = nullptr; io.g_counter = nullptr; io.g_err = nullptr;
   io.bad_action = h->bad_dev;
@@ -1050,7 +1088,7 @@ int pmg_create(const pmg_config* cfg, pmg_handle** out) {
   if (multi && (cfg->num_block < 1 || cfg->num_block > 5)) return fail(PMG_ERR_INVALID, "pmg_create: only support up to 5 blocks%s");
   if (cfg->grip_informed_goal && cfg->task != PMG_BLOCK_STACK) return fail(PMG_ERR_INVALID, "pmg_create: grip_informed_goal is a block_stack option%s");
   if (cfg->task_decomposition && cfg->task != PMG_BLOCK_STACK) return fail(PMG_ERR_INVALID, "pmg_create: task_decomposition is a block_stack option%s");
-  if (cfg->use_curriculum && (cfg->task != PMG_BLOCK_STACK || cfg->num_block < 2)) return fail(PMG_ERR_INVALID, "pmg_create: use_curriculum needs block_stack with at least 2 blocks%s");
+  if (cfg->use_curriculum && (!multi || cfg->num_block < 2)) return fail(PMG_ERR_INVALID, "pmg_create: use_curriculum needs block_stack / block_rearrange with at least 2 blocks%s");
   if (cfg->use_curriculum && cfg->task_decomposition) return fail(PMG_ERR_INVALID, "pmg_create: if using curriculum, task decomposition should be False, vice versa%s");
   if (cfg->batch < 1) return fail(PMG_ERR_INVALID, "pmg_create: batch must be >= 1%s");
   if (cfg->max_episode_steps < 1 || cfg->max_episode_steps >= (1 << 24)) return fail(PMG_ERR_INVALID, "pmg_create: max_episode_steps out of range%s");
@@ -1218,7 +1256,10 @@ int pmg_reset(pmg_handle* h, const uint8_t* mask_host, const float* spawn_host, 
     if (mask_host && !mask_host[i]) continue;
     if (spawn_host) {
       memcpy(h->h_spawn + i * h->spawn_w, spawn_host + i * h->spawn_w, sizeof(float) * h->spawn_w);
-      if (h->cur) { const int ind = (int)spawn_host[i * h->spawn_w + h->spawn_w - 1]; h->cur_level[i] = h->grip ? ind >> 1 : ind; }
+      if (h->cur) {
+        const int ind = (int)spawn_host[i * h->spawn_w + h->spawn_w - 1];
+        h->cur_level[i] = h->cfg.task == PMG_BLOCK_REARRANGE ? __builtin_popcount((unsigned)ind) - 1 : (h->grip ? ind >> 1 : ind);  // rearrange: the mask of moved blocks
+      }
     }
     else sample_spawn(h, (int)i, h->h_spawn + i * h->spawn_w);
   }

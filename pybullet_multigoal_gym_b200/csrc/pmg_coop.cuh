@@ -1870,7 +1870,12 @@ __device__ void step_env_multi(const Grp& g, EnvSmemT<NBLK>& sm, const float* la
     if (io.grip_goal) { ag[3 * NBLK] = tip.x; ag[3 * NBLK + 1] = tip.y; ag[3 * NBLK + 2] = tip.z; ag[3 * NBLK + 3] = closeness; }
     const float* goal = s + (size_t)(ST_BLK + 13 * NBLK) * B;
     for (int k = 0; k < G; k++) dg[k] = goal[(size_t)k * B];
-    if (io.td) {  // sub-goal rebuilt from the current block positions (see write_obs in pmg_capi.cu)
+    if (io.td == 2) {  // BlockRearrange curriculum: only the blocks of the episode's mask have targets (write_obs in pmg_capi.cu)
+      const int moved = (int)goal[(size_t)G * B];
+#pragma unroll 1
+      for (int n = 0; n < NBLK; n++)
+        if (!((moved >> n) & 1)) { const float* bk = sm.blk + 24 * n; dg[3 * n] = bk[BK_POS]; dg[3 * n + 1] = bk[BK_POS + 1]; dg[3 * n + 2] = bk[BK_POS + 2]; }
+    } else if (io.td) {  // sub-goal rebuilt from the current block positions (see write_obs in pmg_capi.cu)
       const int nsub = io.grip_goal ? 2 * NBLK : NBLK;
       int ind = (int)goal[(size_t)G * B];
       if (ind < 0) ind += nsub;

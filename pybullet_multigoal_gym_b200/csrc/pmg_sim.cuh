@@ -640,7 +640,7 @@ struct StepIO {
   int grasp;        // the last action column drives the jaws and finger_closeness / finger_vel are observed
   int jc;           // joint-space control: 7 joint deltas (+ grip), joint poses prepended to observation / policy_state
   int grip_goal;    // grip-informed goal: achieved / desired goal gain gripper xyz + finger closeness
-  int td;           // task decomposition / curriculum: desired goal = the sub-goal named by the state word behind the goal
+  int td;           // task decomposition / curriculum: desired goal = the sub-goal named by the state word behind the goal (1); 2: BlockRearrange curriculum, that word is the bit mask of the blocks with targets
   int cur;          // curriculum: that word is set by the reset (from the spawn row) instead of -1
   int adim, goal_dim, row_width;  // action columns, goal length, packed row width (all after the variants above)
   float* row_spill;               // cooperative block kernel: contact-row records beyond the shared-memory ones

@@ -101,7 +101,7 @@ class KukaBulletMGEnv:
             # kuka_multi_step_envs.py:13-17, kuka_multi_step_base_env.py:116-119: demonstrations [0], [0, 1], ...
             self.num_steps = self.num_block * (2 if self.grip_informed_goal else 1)
             self.step_demonstrator = StepDemonstrator([list(range(i + 1)) for i in range(self.num_steps)])
-        self.curriculum = bool(use_curriculum) and task == "block_stack"
+        self.curriculum = bool(use_curriculum) and task in ("block_stack", "block_rearrange")
         if self.curriculum:
             # kuka_multi_step_base_env.py:112-140
             assert not self.task_decomposition, 'if using curriculum, task decomposition should be False, vice versa'
@@ -297,6 +297,16 @@ class KukaBulletMGEnv:
     def last_curriculum_level(self):
         lv = self._curriculum_state()[1]
         return int(lv[0]) if self._squeeze else lv
+
+    @property
+    def last_ind_block_to_move(self):
+        """block_rearrange with the curriculum (kuka_multi_step_envs.py:201-205): the sorted indices of the blocks the
+        last reset gave targets to; a list (single env) or one list per environment."""
+        if not (self.curriculum and self.task == "block_rearrange"):
+            return None
+        masks = self.last_spawn()[:, -1].astype(np.int64)
+        moved = [[b for b in range(self.num_block) if (int(m) >> b) & 1] for m in masks]
+        return moved[0] if self._squeeze else moved
 
     @property
     def curriculum_goal_step(self):

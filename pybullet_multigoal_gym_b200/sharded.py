@@ -84,6 +84,7 @@ class ShardedKukaEnv:
         else:
             self.env = KukaBulletMGEnv(task, batch=hi - lo, device=device, seed=seed + lo, **kw)
         self.local_batch = hi - lo
+        self._fused_required = fused is True  # None: use it when the box allows (NCCL group of <= 8 ranks with peer access)
         if fused is None:
             fused = dist.get_backend(group) == "nccl" and self.world <= 8
         self.fused = bool(fused)
@@ -102,12 +103,30 @@ class ShardedKukaEnv:
         views of the two parity copies of the gather buffer, built once."""
         L, h = self.env._L, self.env._h
         mine = (C.c_char * 64)()
-        _lib.check(L.pmg_gather_create(h, self.rank, self.world, mine))
+        err = None
+        try:
+            _lib.check(L.pmg_gather_create(h, self.rank, self.world, mine))
+        except (RuntimeError, ValueError) as e:
+            err = e
         handles = [None] * self.world
-        dist.all_gather_object(handles, bytes(mine.raw), group=self.group)
-        blob = b"".join(handles)
-        _lib.check(L.pmg_gather_connect(h, C.c_char_p(blob)))
-        dist.barrier(group=self.group)  # every rank has mapped every buffer before the first step publishes into them
+        dist.all_gather_object(handles, None if err else bytes(mine.raw), group=self.group)
+        if err is None and all(x is not None for x in handles):
+            try:
+                _lib.check(L.pmg_gather_connect(h, C.c_char_p(b"".join(handles))))
+            except (RuntimeError, ValueError) as e:
+                err = e
+        # one reduction doubles as the barrier (every rank has mapped every buffer before the first step publishes
+        # into them) and as the agreement on the path: a box without peer access between some pair of GPUs (no
+        # NVLink / IPC disabled in the container) puts ALL ranks on the NCCL all-gather, never a mix
+        ok = torch.tensor([0 if (err is not None or any(x is None for x in handles)) else 1], dtype=torch.int32, device=self.env.device)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=self.group)
+        if int(ok.item()) == 0:
+            if self._fused_required:
+                raise RuntimeError("fused gather unavailable on this box: %s" % (err or "a peer rank could not map the gather buffers"))
+            import warnings
+            warnings.warn("peer-memory gather unavailable (%s): falling back to one NCCL all-gather per step" % (err or "peer rank failed"))
+            self.fused = False
+            return
         lay = (C.c_int64 * 6)()
         _lib.check(L.pmg_gather_layout(h, lay))
         self._parity_bytes, _, off_r, off_d, off_s, _ = [int(v) for v in lay]

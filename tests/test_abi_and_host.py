@@ -66,7 +66,7 @@ def test_make_env_validation_matches_reference():
     with pytest.raises(AssertionError):      # kuka_multi_step_envs.py:159
         pmg.make_env(task="block_rearrange", num_block=3, task_decomposition=True)
     for kw in (dict(task="insertion"), dict(task="chest_push"), dict(task="reach", gripper="robotiq85"),
-               dict(task="push", image_observation=True), dict(task="block_rearrange", num_block=4, use_curriculum=True)):
+               dict(task="push", image_observation=True), dict(task="chest_pick_and_place", use_curriculum=True)):
         with pytest.raises(NotImplementedError):
             pmg.make_env(**kw)
 

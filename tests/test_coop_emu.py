@@ -280,14 +280,16 @@ def test_cooperative_tumbling_block_matches_oracle(emu, seed):
     assert pairs == {2} and most == 4 and abs(z - 0.175) < 1e-3   # flat on the table at the end
 
 
-def _multi_scenario(emu, nb, nsteps, window, init, policy, seed=4, grip=False, td=False, sub_goal=None, task="block_stack"):
+def _multi_scenario(emu, nb, nsteps, window, init, policy, seed=4, grip=False, td=False, sub_goal=None, task="block_stack", cur=False):
     """Teacher-forced cooperative multi-block steps against the oracle (state and packed observation row); the
     emulator runs only for t in `window` (the oracle alone drives the approach).  Returns worst joint/block pose error,
     worst block velocity error, worst observation-row error away from the velocity entries, the collision pairs that
     held points at a step end, most points at a step end."""
-    o = O.OracleEnv(task, num_block=nb, seed=seed, binary_reward=False, grip_informed_goal=grip, task_decomposition=td)
+    o = O.OracleEnv(task, num_block=nb, seed=seed, binary_reward=False, grip_informed_goal=grip, task_decomposition=td, use_curriculum=cur)
     o.reset()
     o.reset()
+    if cur:  # the step kernels read the curriculum word like a sub-goal index (block_stack) / as the mask of moved blocks (block_rearrange: td = 2)
+        td = 2 if task == "block_rearrange" else 1
     if sub_goal is not None:
         o.set_sub_goal(sub_goal)
     st = o.get_state()
@@ -452,6 +454,21 @@ def test_cooperative_multi_block_rearrange_matches_oracle(emu):
     def policy(t, st, tip):
         return np.array([0.3, 0.6, -0.4])
     worst_p, worst_v, worst_o, pairs, most = _multi_scenario(emu, 3, 2, range(0, 2), lambda st: None, policy, task="block_rearrange")
+    assert worst_p < 1e-4 and worst_v < 1e-3 and worst_o < 1e-4, (worst_p, worst_v, worst_o)
+
+
+@pytest.mark.parametrize("level", [0, 1])
+def test_cooperative_multi_block_rearrange_curriculum_goal_matches_oracle(emu, level):
+    """BlockRearrange with the curriculum (kuka_multi_step_envs.py:193-227): the blocks of the episode's mask keep their
+    sampled targets, every other block's desired goal follows the block; the tip pushes block 0 along."""
+    def policy(t, st, tip):
+        return np.clip((st[46:49] - tip) / 0.01, -1, 1)
+
+    def init(st):
+        assert st[-2] in (1.0, 2.0, 4.0)           # level 0: one moved block
+        if level == 1:
+            st[-2] = 5.0                            # blocks 0 and 2 moved: their goal words are the targets
+    worst_p, worst_v, worst_o, pairs, most = _multi_scenario(emu, 3, 4, range(0, 4), init, policy, task="block_rearrange", cur=True)
     assert worst_p < 1e-4 and worst_v < 1e-3 and worst_o < 1e-4, (worst_p, worst_v, worst_o)
 
 

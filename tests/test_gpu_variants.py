@@ -170,7 +170,7 @@ def test_task_decomposition_sub_goals_match_oracle(oracle, name):
     assert torch.equal(env.set_sub_goal(-1), final) and torch.equal(env.set_sub_goal(nsub - 1), final)
 
 
-@pytest.mark.parametrize("name,grip", [("block_stack_cur", False), ("block_stack_cur_grip", True)])
+@pytest.mark.parametrize("name,grip", [("block_stack_cur", False), ("block_stack_cur_grip", True), ("block_rearrange_cur", False)])
 def test_curriculum_schedule_matches_reference_plumbing_golden(oracle, name, grip):
     """use_curriculum=True (kuka_multi_step_base_env.py:122-157,350-379; kuka_multi_step_envs.py:124-148): every
     environment draws its goal level with np_random.choice from its own probability schedule.  Env 0 (seed 0)
@@ -179,6 +179,8 @@ def test_curriculum_schedule_matches_reference_plumbing_golden(oracle, name, gri
     import warnings
     g = np.load(os.path.join(GOLDEN, "ref_plumbing_%s.npz" % name))
     kw = dict(task="block_stack", num_block=3, use_curriculum=True, num_goals_to_generate=12, grip_informed_goal=grip)
+    if name == "block_rearrange_cur":  # kuka_multi_step_envs.py:193-227: level + 1 randomly chosen blocks get the targets
+        kw = dict(task="block_rearrange", num_block=3, use_curriculum=True, num_goals_to_generate=12)
     B = 4
     with warnings.catch_warnings():
         warnings.simplefilter("ignore")
@@ -202,6 +204,8 @@ def test_curriculum_schedule_matches_reference_plumbing_golden(oracle, name, gri
         assert int(env.last_curriculum_level[0]) == int(g["curriculum_level"][ep])
         np.testing.assert_allclose(env.curriculum_prob[0], g["curriculum_prob"][ep], atol=0)
         assert int(env.curriculum_goal_step[0]) == int(g["curriculum_goal_step"][ep])
+        if name == "block_rearrange_cur":
+            assert sum(1 << b for b in env.last_ind_block_to_move[0]) == int(g["curriculum_moved_mask"][ep])
         for i in range(B):
             ro = refs[i].reset()
             prob, level = refs[i].curriculum()

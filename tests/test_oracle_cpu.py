@@ -146,6 +146,7 @@ GOLDEN_VARIANTS = {
     "block_stack_td_grip": dict(task="block_stack", num_block=3, task_decomposition=True, grip_informed_goal=True),
     "block_stack_cur": dict(task="block_stack", num_block=3, use_curriculum=True, num_goals_to_generate=12),
     "block_stack_cur_grip": dict(task="block_stack", num_block=3, use_curriculum=True, grip_informed_goal=True, num_goals_to_generate=12),
+    "block_rearrange_cur": dict(task="block_rearrange", num_block=3, use_curriculum=True, num_goals_to_generate=12),
 }
 
 

@@ -44,6 +44,8 @@ CONFIGS = [
     # through its whole schedule (kuka_multi_step_base_env.py:350-379); max_episode_steps = 2
     ("block_stack_cur", dict(task="block_stack", binary_reward=True, num_block=3, use_curriculum=True, num_goals_to_generate=12, max_episode_steps=2), 4, 48),
     ("block_stack_cur_grip", dict(task="block_stack", binary_reward=True, num_block=3, use_curriculum=True, grip_informed_goal=True, num_goals_to_generate=12, max_episode_steps=2), 4, 48),
+    # block_rearrange with the curriculum (kuka_multi_step_envs.py:193-227): level + 1 randomly chosen blocks get targets
+    ("block_rearrange_cur", dict(task="block_rearrange", binary_reward=True, num_block=3, use_curriculum=True, num_goals_to_generate=12, max_episode_steps=2), 3, 48),
 ]
 # (step within the episode) -> sub-goal index handed to env.set_sub_goal before that step; indices beyond the
 # variant's number of sub-goals are taken modulo it by the script
@@ -61,6 +63,7 @@ VARIANTS = {
     "block_stack_td_grip": dict(task="block_stack", num_block=3, task_decomposition=True, grip_informed_goal=True),
     "block_stack_cur": dict(task="block_stack", num_block=3, use_curriculum=True, num_goals_to_generate=12, max_episode_steps=2),
     "block_stack_cur_grip": dict(task="block_stack", num_block=3, use_curriculum=True, grip_informed_goal=True, num_goals_to_generate=12, max_episode_steps=2),
+    "block_rearrange_cur": dict(task="block_rearrange", num_block=3, use_curriculum=True, num_goals_to_generate=12, max_episode_steps=2),
 }
 
 
@@ -96,7 +99,7 @@ def main():
         actions = scripted_actions(name, adim, T, rng)
         resets, steps, rewards, dones, oks = [], [], [], [], []
         sub_goal_calls, sub_goal_returns = [], []
-        cur_prob, cur_level, cur_goal_step = [], [], []
+        cur_prob, cur_level, cur_goal_step, cur_moved = [], [], [], []
         L = T // 2
         if "_cur" in name:
             L = 2
@@ -109,7 +112,11 @@ def main():
             if "_cur" in name:
                 inner = env.unwrapped if hasattr(env, "unwrapped") else env.env
                 cur_prob.append(np.array(inner.curriculum_prob, dtype=np.float64))
-                cur_level.append(int(inner.last_curriculum_level))
+                if kw["task"] == "block_rearrange":  # the level is implied by the blocks it picked (:204-208)
+                    cur_level.append(len(inner.last_ind_block_to_move) - 1)
+                    cur_moved.append(sum(1 << int(b) for b in inner.last_ind_block_to_move))
+                else:
+                    cur_level.append(int(inner.last_curriculum_level))
                 cur_goal_step.append(int(inner.curriculum_goal_step))
             for t in range(L):
                 a = actions[ep * L + t]
@@ -142,6 +149,7 @@ def main():
                             goal_achieved=np.array(oks), episode_len=L,
                             curriculum_prob=np.array(cur_prob), curriculum_level=np.array(cur_level, dtype=np.int64),
                             curriculum_goal_step=np.array(cur_goal_step, dtype=np.int64),
+                            curriculum_moved_mask=np.array(cur_moved, dtype=np.int64),
                             dims=np.array([len(np.ravel(obs[k])) for k in KEYS]),
                             max_episode_steps=env._max_episode_steps,
                             sub_goal_calls=np.array(sub_goal_calls, dtype=np.int64).reshape(-1, 2),
