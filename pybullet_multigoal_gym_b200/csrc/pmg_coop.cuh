@@ -705,100 +705,6 @@ __device__ __noinline__ float contact_sweep(Grp g, SM& sm, int nrow_it) {  // nr
   return cres;
 }
 
-// ---- Reach: the contact sweep, software-pipelined ---------------------------------------------------------------------
-// The step lasts as long as its slowest environment (an arm resting on the table: 24 rows x 5 iterations x 100
-// substeps), and in contact_sweep a row's six 16-byte loads are issued only after the previous row's update has issued,
-// i.e. behind its clamp: load -> dot -> clamp -> axpy is ~90 dependent cycles per row.  Here row c + 1's J is fetched
-// while row c's clamp is in flight -- into the registers J_c has just been read from, so the register needs do not grow
-// (a prefetch into extra registers was measured slower) -- and M^-1 J^T, needed last, at the top.
-#ifndef PMG_SWEEP_PIPE
-#define PMG_SWEEP_PIPE 1
-#endif
-__device__ __noinline__ float contact_sweep_pipe(Grp g, EnvSmem& sm, int nrow_it) {  // nrow | iteration parity << 8
-  const int nrow = nrow_it & 0xff, it = nrow_it >> 8;
-  const float* app_rd = sm.app[it & 1];
-  float* app_wr = sm.app[(it & 1) ^ 1];
-  float dq[ND];
-#pragma unroll
-  for (int j = 0; j < ND; j++) dq[j] = sm.vq[j];
-  float cres = 0.0f;
-  auto ld4 = [](const float* p) { return *reinterpret_cast<const float4*>(p); };
-  constexpr int STRIDE = 3 * EnvSmem::ROW_W;
-  const float* last = sm.rows[(nrow - 1) * 3];
-  {  // normal rows
-    const float* row = sm.rows[0];
-    RowVec j; j.a = ld4(row + R_J); j.b = ld4(row + R_J + 4); j.c = ld4(row + R_J + 8);  // c = (J8 rhs dinv .)
-#pragma unroll 1
-    for (int c = 0; c < nrow; c++) {
-      RowVec mj;
-      mj.a = ld4(row + R_MJ); mj.b = ld4(row + R_MJ + 4); mj.c = ld4(row + R_MJ + 8);  // c = (MJ8 denom . .)
-      const float app = app_rd[c * 3];
-      const float v = row_dot(j, dq);
-      const float rhs = j.c.y, dinv = j.c.z;
-      const float* rown = row < last ? row + STRIDE : row;  // the last row is fetched again instead of a branch
-      j.a = ld4(rown + R_J); j.b = ld4(rown + R_J + 4); j.c = ld4(rown + R_J + 8);
-      float dl = rhs - v * dinv;
-      const float sum = fminf(fmaxf(app + dl, 0.0f), 1e10f);
-      dl = sum - app;
-      row_axpy(mj, dl, dq);
-      const float rr = dl * mj.c.y;
-      cres = fmaxf(cres, rr * rr);
-      app_wr[c * 3] = sum;
-      row = rown;
-    }
-  }
-  g.sync();  // the new normal impulses bound the friction rows
-  {  // friction pairs, implicit cone
-    const float mu = (float)PMG_FINGER_FRICTION * (float)PMG_TABLE_FRICTION;
-    const float* ra = sm.rows[1];
-    RowVec ja, jb;
-    ja.a = ld4(ra + R_J); ja.b = ld4(ra + R_J + 4); ja.c = ld4(ra + R_J + 8);
-    jb.a = ld4(ra + EnvSmem::ROW_W + R_J); jb.b = ld4(ra + EnvSmem::ROW_W + R_J + 4); jb.c = ld4(ra + EnvSmem::ROW_W + R_J + 8);
-    last += EnvSmem::ROW_W;
-#pragma unroll 1
-    for (int c = 0; c < nrow; c++) {
-      const float* rb = ra + EnvSmem::ROW_W;
-      RowVec mja, mjb;
-      mja.a = ld4(ra + R_MJ); mja.b = ld4(ra + R_MJ + 4); mja.c = ld4(ra + R_MJ + 8);
-      mjb.a = ld4(rb + R_MJ); mjb.b = ld4(rb + R_MJ + 4); mjb.c = ld4(rb + R_MJ + 8);
-      const float total = app_wr[c * 3];
-      const float appA = app_rd[c * 3 + 1], appB = app_rd[c * 3 + 2];
-      const float vA = row_dot(ja, dq), vB = row_dot(jb, dq);
-      const float rhsA = ja.c.y, dinvA = ja.c.z, rhsB = jb.c.y, dinvB = jb.c.z;
-      const float* ran = ra < last ? ra + STRIDE : ra;
-      ja.a = ld4(ran + R_J); ja.b = ld4(ran + R_J + 4); ja.c = ld4(ran + R_J + 8);
-      jb.a = ld4(ran + EnvSmem::ROW_W + R_J); jb.b = ld4(ran + EnvSmem::ROW_W + R_J + 4); jb.c = ld4(ran + EnvSmem::ROW_W + R_J + 8);
-      float sA = appA, sB = appB, dA = 0.0f, dB = 0.0f;
-      if (total > 0.0f) {
-        const float lim = mu * total;
-        dA = rhsA - vA * dinvA; dB = rhsB - vB * dinvB;
-        sA = appA + dA; sB = appB + dB;
-        const float s2 = sA * sA + sB * sB;
-        if (s2 >= lim * lim) {
-          // |lim sin(atan2(sA, sB))| = lim |sA| / sqrt(sA^2 + sB^2), likewise the cosine for sB
-          const float sc = s2 > 0.0f ? lim * rsqrtf(s2) : 0.0f;
-          const float cA = fabsf(sA) * sc, cB = s2 > 0.0f ? fabsf(sB) * sc : lim;
-          sA = fminf(fmaxf(sA, -cA), cA);
-          sB = fminf(fmaxf(sB, -cB), cB);
-          dA = sA - appA; dB = sB - appB;
-        }
-      }
-      row_axpy(mja, dA, dq); row_axpy(mjb, dB, dq);  // an open point: dA = dB = 0
-      const float r1_ = dA * mja.c.y, r2_ = dB * mjb.c.y;
-      cres = fmaxf(cres, fmaxf(r1_ * r1_, r2_ * r2_));
-      app_wr[c * 3 + 1] = sA; app_wr[c * 3 + 2] = sB;  // carried over unchanged while the point is open
-      ra = ran;
-    }
-  }
-  g.sync();  // every lane has read sm.vq
-  if (g.lane == 0) {
-#pragma unroll
-    for (int j = 0; j < ND; j++) sm.vq[j] = dq[j];
-  }
-  g.sync();
-  return cres;
-}
-
 // ---- multi-block environments (BlockStack / BlockRearrange, NBLK > 1) ------------------------------------------------
 // Row set-up: as contact_row_setup_blk, but either end may be a block (block-block pairs have two) and the blocks are
 // looked up by index.  Signs as in the thread-per-env kernels (pmg_sim.cuh row_velocity / row_apply): end A sees
@@ -1581,9 +1487,6 @@ __device__ void substep(const Grp& g, SM& sm, Lane& L) {
       }
       PMG_T(t_sw0);
       if constexpr (MULTI) res = fmaxf(res, contact_sweep_multi(g, sm, ((it & 1) << 8) | (ngen << 16), srange));
-#if PMG_SWEEP_PIPE
-      else if constexpr (!BLK) res = fmaxf(res, contact_sweep_pipe(g, sm, nrow | ((it & 1) << 8)));
-#endif
       else res = fmaxf(res, contact_sweep(g, sm, nrow | ((it & 1) << 8) | row_kinds));
 #ifdef PMG_COOP_TIMING
       t_sweeps += clock64() - t_sw0;
