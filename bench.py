@@ -230,7 +230,7 @@ def main():
     kw = dict(num_block=4, check_actions=False, device_sampling=True, auto_reset=True, seed=1234)
     with contextlib.redirect_stdout(io.StringIO()):  # make_env prints 'Task id: ...' like the reference
         if distributed:
-            env_s = ShardedKukaEnv(task, B * world, device=local_rank, fused=(args.gather == "fused"), **kw)
+            env_s = ShardedKukaEnv(task, B * world, device=local_rank, fused=(None if args.gather == "fused" else False), **kw)  # None: peer-memory gather when the box allows, else NCCL on all ranks
             env = env_s.env
         else:
             env_s = None

@@ -667,6 +667,9 @@ __device__ __noinline__ float contact_sweep(Grp g, SM& sm, int nrow_it) {  // nr
   // one loop per kind (not one loop with a three-way branch): the four environments of a warp then run the same
   // form together even when their point counts differ
   const int e1 = c1 < nsh ? c1 : nsh, e2 = c2 < nsh ? c2 : nsh;
+#ifdef PMG_COOP_TIMING
+  const long long t_n0 = clock64();
+#endif
 #pragma unroll 1
   for (int c = 0; c < e1; c++) normal_row(T(), F(), sm.rows[c * 3], c);
   if constexpr (BLK) {
@@ -679,7 +682,13 @@ __device__ __noinline__ float contact_sweep(Grp g, SM& sm, int nrow_it) {  // nr
 #pragma unroll 1
     for (int c = SM::SPTS; c < nrow; c++) normal_row(T(), T(), sm.spill_row(c * 3), c);
   }
+#ifdef PMG_COOP_TIMING
+  const long long t_n1 = clock64();
+#endif
   g.sync();  // the new normal impulses bound the friction rows
+#ifdef PMG_COOP_TIMING
+  const long long t_f0 = clock64();
+#endif
 #pragma unroll 1
   for (int c = 0; c < e1; c++) friction_rows(T(), F(), sm.rows[c * 3 + 1], sm.rows[c * 3 + 2], c);
   if constexpr (BLK) {
@@ -692,6 +701,13 @@ __device__ __noinline__ float contact_sweep(Grp g, SM& sm, int nrow_it) {  // nr
 #pragma unroll 1
     for (int c = SM::SPTS; c < nrow; c++) friction_rows(T(), T(), sm.spill_row(c * 3 + 1), sm.spill_row(c * 3 + 2), c);
   }
+#ifdef PMG_COOP_TIMING
+  if (g.lane == 0) {  // [12] normal loops, [13] friction loops, [14] row visits (normal + friction pair = 2 per point), [15] calls
+    const long long t_f1 = clock64();
+    atomicAdd(&pmg::g_coop_cycles[12], (unsigned long long)(t_n1 - t_n0)); atomicAdd(&pmg::g_coop_cycles[13], (unsigned long long)(t_f1 - t_f0));
+    atomicAdd(&pmg::g_coop_cycles[14], (unsigned long long)(2 * nrow)); atomicAdd(&pmg::g_coop_cycles[15], 1ull);
+  }
+#endif
   g.sync();  // every lane has read sm.vq
   if (g.lane == 0) {
 #pragma unroll

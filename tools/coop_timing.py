@@ -34,5 +34,8 @@ for t in range(50):
         hot_n, cold_n = max(c[4], 1), max(c[6], 1)
         print("after step %2d: hot octet-substeps %8d: substep %7.0f cyc = narrowphase %6.0f + row set-up %6.0f + sweeps %6.0f + rest %6.0f | cold %9d: substep %6.0f cyc (broadphase %4.0f)"
               % (t, c[4], c[0] / hot_n, c[1] / hot_n, c[2] / hot_n, c[3] / hot_n, (c[0] - c[1] - c[2] - c[3]) / hot_n, c[6], c[5] / cold_n, c[7] / cold_n))
+        if c[15]:
+            print("               contact_sweep (one-block / Reach kernels): %.2f calls per hot substep, %.1f row visits per call; per call: normal loop %5.0f + friction loop %5.0f cycles of %5.0f (call, barriers, delta-velocity round trip: the rest)"
+                  % (c[15] / hot_n, c[14] / c[15], c[12] / c[15], c[13] / c[15], c[3] / c[15]))
         if c[11]:
             print("               narrowphase of a touching pair: box_box %5.0f + manifold_add %5.0f + refresh %5.0f cycles" % (c[8] / c[11], c[9] / c[11], c[10] / c[11]))
