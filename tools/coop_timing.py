@@ -1,7 +1,7 @@
 """Development aid: per-phase cycle counts of the cooperative kernels for octets with / without contacts.
 Usage: coop_timing.py [down] [task[:batch]]   (default reach:8192)
 
-Build (here):  nvcc ... -DPMG_COOP_TIMING -o gpurun_out/libpmg_timing.so   (see tools/gpu_timing.sh)
+Build (here):  nvcc ... -DPMG_COOP_TIMING -o gpurun_out/libpmg_timing.so   (see tools/gpu_calls/gpu_timing.sh)
 Run (GPU box): PMG_LIBRARY=pybullet_multigoal_gym_b200/libpmg_timing.so python tools/coop_timing.py"""
 import ctypes as C
 import os

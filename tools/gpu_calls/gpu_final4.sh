@@ -35,5 +35,5 @@ timeout 200 compute-sanitizer --tool memcheck python tools/prof_one.py block_rea
 timeout 300 compute-sanitizer --tool racecheck python tools/prof_one.py reach 16 11 down > gpurun_out/racecheck_coop.log 2>&1; tail -1 gpurun_out/racecheck_coop.log
 timeout 300 compute-sanitizer --tool racecheck python tools/prof_one.py pick_and_place 16 6 > gpurun_out/racecheck_coop_pnp.log 2>&1; tail -1 gpurun_out/racecheck_coop_pnp.log
 timeout 300 compute-sanitizer --tool memcheck python tools/prof_one.py push 64 6 > gpurun_out/memcheck_coop_push.log 2>&1; tail -1 gpurun_out/memcheck_coop_push.log
-bash tools/gpu_timing.sh | tee gpurun_out/coop_timing.txt
-bash tools/gpu_timing_blk.sh | tee gpurun_out/coop_timing_blk.txt
+bash tools/gpu_calls/gpu_timing.sh | tee gpurun_out/coop_timing.txt
+bash tools/gpu_calls/gpu_timing_blk.sh | tee gpurun_out/coop_timing_blk.txt
