@@ -169,6 +169,75 @@ def test_single_all_gather_of_the_flat_step_output_gloo_world2():
         assert done == [False] * 4 + [True] * 4
 
 
+class _FakeGatherLib:
+    """Stands in for libpmg.so's gather entry points: rank `bad` cannot create its gather buffer."""
+    def __init__(self, rank, bad):
+        self.rank, self.bad, self.connected = rank, bad, False
+
+    def pmg_gather_create(self, h, rank, world, out):
+        return -2 if self.rank == self.bad else 0
+
+    def pmg_gather_connect(self, h, blob):
+        self.connected = True
+        return 0
+
+    def pmg_gather_layout(self, h, lay):
+        for i, v in enumerate((1024, 0, 256, 512, 768, 0)):
+            lay[i] = v
+        return 0
+
+
+def _connect_worker(rank, world, port, bad, required, q):
+    import types
+    import warnings
+    import torch.distributed as dist
+    from pybullet_multigoal_gym_b200 import _lib, sharded
+    dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%d" % port, rank=rank, world_size=world)
+    _lib.check = lambda rc: None if rc == 0 else (_ for _ in ()).throw(_lib.PmgError("pmg error %d: no peer access" % rc))
+    fake = _FakeGatherLib(rank, bad)
+    e = object.__new__(sharded.ShardedKukaEnv)
+    e.group, e.rank, e.world, e.fused, e._fused_required = None, rank, world, True, required
+    e.global_batch, e.local_batch = 8, 4
+    e.env = types.SimpleNamespace(_L=fake, _h=None, device=torch.device("cpu"), row_width=6, action_dim=3)
+    outcome = "ok"
+    with warnings.catch_warnings(record=True) as w:
+        warnings.simplefilter("always")
+        try:
+            # pinned host mirrors need a CUDA runtime: the test only follows the agreement, so stop before them
+            torch.Tensor.pin_memory = lambda self, *a, **k: self
+            e._connect_peers()
+        except RuntimeError as err:
+            outcome = "raised: %s" % err
+    q.put((rank, e.fused, fake.connected, outcome, [str(x.message) for x in w]))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("bad,required", [(-1, False), (1, False), (1, True)])
+def test_peer_gather_is_agreed_by_all_ranks_gloo_world2(bad, required):
+    """ShardedKukaEnv._connect_peers: when any rank cannot set up the peer-memory gather, EVERY rank falls back to the
+    NCCL all-gather (fused=None) or every rank raises (fused=True) -- never a mix, never a hang."""
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 31000 + (os.getpid() + 7 * (bad + 2) + int(required)) % 2000
+    procs = [ctx.Process(target=_connect_worker, args=(r, 2, port, bad, required, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    results = sorted(q.get(timeout=120) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank, fused, connected, outcome, warns in results:
+        if bad < 0:
+            assert fused and connected and outcome == "ok" and not warns
+        elif required:
+            assert outcome.startswith("raised: fused gather unavailable")
+        else:
+            assert not fused and outcome == "ok" and any("falling back to one NCCL all-gather" in m for m in warns)
+            assert not connected   # nobody maps a peer buffer unless everybody can
+
+
 def test_step_demonstrator_matches_reference_golden():
     """envs.StepDemonstrator against a trace of the reference's utils/demonstrator.py (tools/gen_demonstrator_golden.py)."""
     import json
