@@ -146,9 +146,18 @@ def cpu_port_rate(task, n_env, n_steps, threads, warm_steps):
     return n_env * n_steps / secs, secs, flags
 
 
-def cpu_sample_size(task, threads):
+def cpu_sample_size(task, threads, steps=None):
+    """Environments of the CPU sample.  With `steps` (the reference arm: the driver passes few) the sample grows until the
+    timed region holds ~2 s of work on 16 cores, so that thread start-up and the last thread's tail do not weigh on the
+    rate (a 0.4 s region read 20 % low)."""
     per_thread = {"reach": 32, "push": 16, "pick_and_place": 16, "slide": 16}.get(task, 8)
-    return max(threads * per_thread, 64)
+    n = max(threads * per_thread, 64)
+    if steps:
+        target = {"reach": 60000, "push": 40000, "pick_and_place": 40000, "slide": 40000}.get(task, 24000)  # env-steps in the timed region
+        want = -(-target // max(steps, 1))
+        want = -(-want // threads) * threads
+        n = max(n, min(want, 4096))
+    return n
 
 
 def run_reference(args, task, per_gpu):
@@ -158,7 +167,7 @@ def run_reference(args, task, per_gpu):
     if rank != 0:
         return
     threads = os.cpu_count() or 1
-    n_env = cpu_sample_size(task, threads)
+    n_env = min(cpu_sample_size(task, threads, max(args.steps, 1)), per_gpu)
     warm = max(args.warmup, 60)  # settle the contact mix and the CPU clocks / caches before timing
     steps = max(args.steps, 1)
     rate, secs, flags = cpu_port_rate(task, n_env, steps, threads, warm)
